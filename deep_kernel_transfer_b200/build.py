@@ -1,0 +1,56 @@
+"""Build libdktb200.so (sm_100a) in-tree with nvcc.  ``python -m deep_kernel_transfer_b200.build``."""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libdktb200.so")
+SOURCES = ["conv_fp32.cu", "bn_pool.cu", "head.cu", "gp.cu", "optim.cu", "conv_tc.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--use_fast_math=false"]
+
+
+def _nvcc():
+    for c in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found: cannot build libdktb200.so")
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    if not force and not needs_build():
+        return LIB
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+    objs = []
+    bdir = os.path.join(HERE, "build")
+    os.makedirs(bdir, exist_ok=True)
+    procs = []
+    for s in srcs:
+        o = os.path.join(bdir, os.path.basename(s)[:-3] + ".o")
+        cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-I", CSRC, "-c", s, "-o", o]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(o)
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode != 0:
+            sys.stdout.write(out)
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-lcuda"]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

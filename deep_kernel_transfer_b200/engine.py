@@ -1,0 +1,283 @@
+"""Host-side orchestration of the dktb200 kernels: packed-episode forward/backward of the ConvNet
+backbone (reference backbone.py:105-132, 250-268) and of the exact-GP head (methods/DKT.py:141-164,
+170-193, 236-269).  PyTorch is used for device memory, streams and (elsewhere) torch.distributed
+only -- every arithmetic step below is a call through the C ABI in include/dktb200.h.
+
+Data layout in HBM (all fp32):
+  x        [B,3,H,W]            NCHW exactly as the loader delivers it (B = E episodes x ipe images)
+  y[0]     [B,H,W,64]           pre-BN conv1 output (NHWC)
+  y[i>0]   [B,H_i+2,W_i+2,64]   pre-BN conv output in the padded-flat layout (border never read)
+  act[i]   [B,Ho+2,Wo+2,64]     block output = next conv's input, ZERO border (written once at alloc)
+  feats    [B, P*64]            last block output, NHWC-flattened
+  gy[i], gact[i]                gradients in the same layouts (gy borders stay zero: dgrad/wgrad read them)
+"""
+import math
+
+import torch
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+def _stream(dev):
+    if dev.type == "cuda":
+        return torch.cuda.current_stream(dev).cuda_stream
+    return 0
+
+
+class ConvNetParams:
+    """Plain container of the tensors one ConvNet needs (views into the flat parameter buffer)."""
+
+    def __init__(self, depth):
+        self.depth = depth
+        self.conv_w = [None] * depth
+        self.conv_b = [None] * depth
+        self.bn_w = [None] * depth
+        self.bn_b = [None] * depth
+        self.bn_rm = [None] * depth
+        self.bn_rv = [None] * depth
+
+
+class ConvNetEngine:
+    """Conv4 / Conv6 (``ConvNet(depth)``) over packed episodes."""
+
+    def __init__(self, lib, depth=4, image_size=84, device="cuda", use_tc=False):
+        self.lib = lib
+        self.depth = depth
+        self.dev = torch.device(device)
+        self.use_tc = use_tc and lib.has("dktb_conv3x3_tc_fwd")
+        self.layers = []
+        h = image_size
+        for i in range(depth):
+            pool = i < 4
+            self.layers.append({"H": h, "W": h, "pool": pool})
+            if pool:
+                h = h // 2
+        self.Hf = h
+        self.P = h * h
+        self.D = 64 * self.P
+        self.cap = 0
+        self.ws = None
+
+    # ------------------------------------------------------------------ workspace
+    def _alloc(self, B, E):
+        dev, f32 = self.dev, torch.float32
+        ws = {"y": [], "act": [], "gy": [], "gact": [], "mean": [], "invstd": [], "partials": [], "T": [],
+              "wt_f": [], "wt_d": []}
+        lib = self.lib
+        max_part = 0
+        for i, L in enumerate(self.layers):
+            H, W = L["H"], L["W"]
+            Ho, Wo = (H // 2, W // 2) if L["pool"] else (H, W)
+            last = i == self.depth - 1
+            if i == 0:
+                ws["y"].append(torch.empty(B, H, W, 64, device=dev, dtype=f32))
+                ws["gy"].append(torch.empty(B, H, W, 64, device=dev, dtype=f32))
+                T = lib.conv1_tiles(H, W)
+            else:
+                ws["y"].append(torch.zeros(B, H + 2, W + 2, 64, device=dev, dtype=f32))
+                ws["gy"].append(torch.zeros(B, H + 2, W + 2, 64, device=dev, dtype=f32))
+                T = lib.conv3x3_tiles(H, W)
+            if last:
+                ws["act"].append(torch.empty(B, Ho, Wo, 64, device=dev, dtype=f32))
+                ws["gact"].append(None)     # provided by the head
+            else:
+                ws["act"].append(torch.zeros(B, Ho + 2, Wo + 2, 64, device=dev, dtype=f32))
+                ws["gact"].append(torch.zeros(B, Ho + 2, Wo + 2, 64, device=dev, dtype=f32))
+            ws["T"].append(T)
+            ws["partials"].append(torch.empty(B * T * 128, device=dev, dtype=f32))
+            ws["mean"].append(torch.empty(E, 64, device=dev, dtype=f32))
+            ws["invstd"].append(torch.empty(E, 64, device=dev, dtype=f32))
+            ws["wt_f"].append(torch.empty(9, 64, 64, device=dev, dtype=f32) if i > 0 else None)
+            ws["wt_d"].append(torch.empty(9, 64, 64, device=dev, dtype=f32) if i > 0 else None)
+            max_part = max(max_part, B * lib.bn_bwd_chunks(H, W, int(L["pool"])) * 128)
+        ws["eval_mean"] = torch.empty(self.depth, 64, device=dev, dtype=f32)
+        ws["eval_invstd"] = torch.empty(self.depth, 64, device=dev, dtype=f32)
+        ws["bwd_partial"] = torch.empty(max_part, device=dev, dtype=f32)
+        ws["bwd_sums"] = torch.empty(E * 128, device=dev, dtype=f32)
+        ws["scratch_d"] = torch.empty(E * 128, device=dev, dtype=torch.float64)
+        n1 = lib.conv1_wgrad_nsplit() * 28 * 64
+        ws["wgrad_scratch"] = torch.empty(max(n1, lib.conv3x3_wgrad_scratch_floats()), device=dev, dtype=f32)
+        self.ws, self.cap, self.cap_E = ws, B, E
+
+    def ensure(self, B, E):
+        if self.ws is None or B != self.cap or E != self.cap_E:
+            self._alloc(B, E)
+
+    # ------------------------------------------------------------------ forward
+    def prepare_weights(self, P):
+        st = _stream(self.dev)
+        for i in range(1, self.depth):
+            self.lib.prep_weights(P.conv_w[i], self.ws["wt_f"][i], self.ws["wt_d"][i], st)
+
+    def forward(self, x, P, ipe, training, update_running=True):
+        """x [B,3,H,W] (device, contiguous).  Returns features [B, D] (NHWC-flattened view of a workspace)."""
+        B = x.shape[0]
+        assert x.is_contiguous() and x.dtype == torch.float32 and B % ipe == 0
+        E = B // ipe
+        self.ensure(B, E)
+        ws, lib, st = self.ws, self.lib, _stream(self.dev)
+        self.prepare_weights(P)
+        for i, L in enumerate(self.layers):
+            H, W, pool = L["H"], L["W"], int(L["pool"])
+            last = i == self.depth - 1
+            partials = ws["partials"][i] if training else None
+            if i == 0:
+                lib.conv1_fwd(x, P.conv_w[0], P.conv_b[0], ws["y"][0], partials, B, H, W, st)
+            else:
+                lib.conv3x3_fwd(ws["act"][i - 1], ws["wt_f"][i], P.conv_b[i], ws["y"][i], partials, B, H, W, st)
+            if training:
+                lib.bn_finalize(partials, B, ws["T"][i], ipe, H * W, ws["mean"][i], ws["invstd"][i],
+                                P.bn_rm[i] if update_running else None, P.bn_rv[i] if update_running else None,
+                                ws["scratch_d"], BN_MOMENTUM, BN_EPS, st)
+                mean, invstd, ipe_arg = ws["mean"][i], ws["invstd"][i], ipe
+            else:
+                lib.bn_eval_prepare(P.bn_rm[i], P.bn_rv[i], ws["eval_mean"][i], ws["eval_invstd"][i], 64, BN_EPS, st)
+                mean, invstd, ipe_arg = ws["eval_mean"][i], ws["eval_invstd"][i], 0
+            lib.bn_relu_pool_fwd(ws["y"][i], mean, invstd, P.bn_w[i], P.bn_b[i], ws["act"][i], B, H, W, ipe_arg,
+                                 0 if i == 0 else 1, 0 if last else 1, pool, st)
+        return ws["act"][-1].view(B, self.D)
+
+    # ------------------------------------------------------------------ backward (after a training forward)
+    def backward(self, x, gfeat, P, G, ipe):
+        """gfeat [B, D] gradient w.r.t. the features; fills G (a ConvNetParams of gradient tensors)."""
+        B = x.shape[0]
+        ws, lib, st = self.ws, self.lib, _stream(self.dev)
+        gout = gfeat
+        for i in range(self.depth - 1, -1, -1):
+            L = self.layers[i]
+            H, W, pool = L["H"], L["W"], int(L["pool"])
+            last = i == self.depth - 1
+            lib.bn_relu_pool_bwd(ws["y"][i], gout, ws["mean"][i], ws["invstd"][i], P.bn_w[i], P.bn_b[i], ws["gy"][i],
+                                 G.bn_w[i], G.bn_b[i], ws["bwd_partial"], ws["bwd_sums"], B, H, W, ipe,
+                                 0 if i == 0 else 1, 0 if last else 1, pool, st)
+            if i == 0:
+                lib.conv1_wgrad(x, ws["gy"][0], G.conv_w[0], G.conv_b[0], ws["wgrad_scratch"], B, H, W, st)
+            else:
+                lib.conv3x3_wgrad(ws["act"][i - 1], ws["gy"][i], G.conv_w[i], G.conv_b[i], ws["wgrad_scratch"], B, H,
+                                  W, st)
+                lib.conv3x3_fwd(ws["gy"][i], ws["wt_d"][i], None, ws["gact"][i - 1], None, B, H, W, st)
+                gout = ws["gact"][i - 1]
+
+
+class GPHeadParams:
+    """Tensors of the GP head: bn_out (optional) + per-class raw hyper-parameters."""
+
+    def __init__(self):
+        self.bn_w = self.bn_b = self.bn_rm = self.bn_rv = None
+        self.raw_outputscale = self.constant = self.raw_noise = None
+
+
+class GPHead:
+    """bn_out -> L2 normalise -> Gram -> C exact GPs, forward/backward/predict over E packed episodes.
+
+    ``kernel`` in {"bncossim", "cossim", "linear"(variance frozen at its value)}: the base kernel is the
+    Gram matrix of the (normalised) features, shared by the C one-vs-rest models (DKT.py:366-370).
+    """
+
+    def __init__(self, lib, kernel, n_way, D, Cch, P, device="cuda"):
+        assert kernel in ("bncossim", "cossim"), kernel
+        self.lib, self.kernel, self.C, self.D, self.Cch, self.P = lib, kernel, n_way, D, Cch, P
+        self.dev = torch.device(device)
+        self.bn = kernel == "bncossim"
+        self.normalize = kernel in ("bncossim", "cossim")
+        self.key = None
+
+    def _alloc(self, E, N):
+        dev, f32, C, D = self.dev, torch.float32, self.C, self.D
+        w = {}
+        w["z"] = torch.empty(E, N, D, device=dev, dtype=f32)
+        w["zh"] = torch.empty(E, N, D, device=dev, dtype=f32)
+        w["zh_train"] = torch.empty(E, N, D, device=dev, dtype=f32)
+        w["inv"] = torch.empty(E * N, device=dev, dtype=f32)
+        w["bn_mean"] = torch.empty(E, D, device=dev, dtype=f32)
+        w["bn_invstd"] = torch.empty(E, D, device=dev, dtype=f32)
+        w["bn_var"] = torch.empty(E, D, device=dev, dtype=f32)
+        w["gram"] = torch.empty(E, N, N, device=dev, dtype=f32)
+        w["alpha"] = torch.empty(E, C, N, device=dev, dtype=f32)
+        w["loss_terms"] = torch.empty(E, C, device=dev, dtype=f32)
+        w["info"] = torch.zeros(E, C, device=dev, dtype=torch.int32)
+        w["dk"] = torch.empty(E, C, N, N, device=dev, dtype=f32)
+        w["dhyper"] = torch.empty(E, C, 3, device=dev, dtype=f32)
+        w["loss"] = torch.empty(E, device=dev, dtype=f32)
+        w["hyper"] = torch.empty(C, 3, device=dev, dtype=f32)
+        w["dzh"] = torch.empty(E, N, D, device=dev, dtype=f32)
+        w["dz"] = torch.empty(E, N, D, device=dev, dtype=f32)
+        w["df"] = torch.empty(E, N, D, device=dev, dtype=f32)
+        w["pgrad"] = torch.empty(E * 2 * D, device=dev, dtype=f32)
+        self.w, self.key = w, (E, N)
+
+    def ensure(self, E, N):
+        if self.key != (E, N):
+            self._alloc(E, N)
+
+    def embed(self, feats, HP, E, N, training, update_running=True, out=None):
+        """features [E*N, D] -> (normalised) embedding [E,N,D] (reference: bn_out in the trunk + F.normalize)."""
+        lib, st, w = self.lib, _stream(self.dev), self.w
+        cur = feats.view(E, N, self.D)
+        if self.bn:
+            lib.bn1d_fwd(cur, HP.bn_w, HP.bn_b, HP.bn_rm, HP.bn_rv, w["z"], w["bn_mean"], w["bn_invstd"], w["bn_var"],
+                         E, N, self.D, self.Cch, self.P, int(training), int(update_running), BN_MOMENTUM, BN_EPS, st)
+            cur = w["z"]
+        if self.normalize:
+            dst = out if out is not None else w["zh"]
+            lib.l2norm_fwd(cur, dst, w["inv"] if training else None, E * N, self.D, 1e-12, st)
+            cur = dst
+        return cur
+
+    def fit(self, zh, targets, HP, E, N, want_grad, grad_scale=1.0, jitter=0.0):
+        """Gram + C Cholesky systems per episode.  targets [C,N] (shared by all episodes)."""
+        lib, st, w, C = self.lib, _stream(self.dev), self.w, self.C
+        lib.gram(zh, zh, w["gram"], E, N, N, self.D, st)
+        lib.gp_fit(w["gram"], 0, targets, 0, HP.raw_outputscale, HP.constant, HP.raw_noise, w["alpha"], None,
+                   w["loss_terms"], w["info"], w["dk"] if want_grad else None, w["dhyper"] if want_grad else None,
+                   grad_scale, jitter, E, C, N, st)
+        lib.gp_reduce(w["loss_terms"], w["dhyper"] if want_grad else None, w["loss"], w["hyper"] if want_grad else None,
+                      E, C, st)
+        return w["loss"]
+
+    def backward(self, feats, zh, HP, GH, E, N):
+        """Gradient w.r.t. the backbone features [E*N, D]; fills GH.{bn_w,bn_b,raw_outputscale,constant}."""
+        lib, st, w = self.lib, _stream(self.dev), self.w
+        lib.gram_bwd(w["dk"], zh, w["dzh"], E, self.C, N, self.D, 1.0, st)
+        g = w["dzh"]
+        if self.normalize:
+            lib.l2norm_bwd(zh, g, w["inv"], w["dz"], E * N, self.D, st)
+            g = w["dz"]
+        if self.bn:
+            lib.bn1d_bwd(feats.view(E, N, self.D), g, HP.bn_w, w["bn_mean"], w["bn_invstd"], w["df"], GH.bn_w, GH.bn_b,
+                         w["pgrad"], E, N, self.D, self.Cch, self.P, st)
+            g = w["df"]
+        GH.raw_outputscale.copy_(w["hyper"][:, 0])
+        GH.constant.copy_(w["hyper"][:, 1])
+        return g.view(E * N, self.D)
+
+    def predict(self, zh_test, zh_train, HP, E, M, N, mean_out, pred_out, kx_buf):
+        """Predictive mean [E,C,M] + class arg-max [E,M]; expects alpha of the current fit in the workspace."""
+        lib, st = self.lib, _stream(self.dev)
+        lib.gram(zh_test, zh_train, kx_buf, E, M, N, self.D, st)
+        lib.gp_predict(kx_buf, 0, self.w["alpha"], HP.raw_outputscale, HP.constant, mean_out, pred_out, E, self.C, M,
+                       N, st)
+
+
+def make_targets(n_way, per_class, device):
+    """methods/DKT.py:129-136 / 227-234: one +-1 target vector per class, class-major sample order."""
+    t = -torch.ones(n_way, n_way * per_class, dtype=torch.float32)
+    for c in range(n_way):
+        t[c, c * per_class:(c + 1) * per_class] = 1.0
+    return t.to(device)
+
+
+def check_info(info, what="Cholesky"):
+    bad = int((info != 0).sum().item())
+    if bad:
+        raise RuntimeError("NotPSDError: %s failed for %d (episode, class) systems (first pivots: %s)"
+                           % (what, bad, info[info != 0][:4].tolist()))
+
+
+def adam_hparams():
+    return dict(beta1=0.9, beta2=0.999, eps=1e-8)
+
+
+def softplus_inv(x):
+    return x + math.log(-math.expm1(-x))

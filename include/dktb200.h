@@ -1,0 +1,117 @@
+/* dktb200 -- C ABI of the B200-native DKT per-episode GP inference path.
+ *
+ * The reference (BayesWatch/deep-kernel-transfer) is pure Python and has no FFI: its boundary for this
+ * path is the Python plugin API of methods/DKT.py / methods/DKT_regression.py / backbone.py (kept by
+ * deep_kernel_transfer_b200/methods + backbone).  This header is the boundary *underneath* that API:
+ * every entry point replaces one implicit library call the reference makes through PyTorch/GPyTorch
+ * (cited per function).  Conventions:
+ *   - extern "C", plain pointers and sizes; every pointer is a DEVICE pointer owned by the caller;
+ *   - explicit cudaStream_t; no hidden allocation, no global mutable state (re-entrant across streams);
+ *   - caller-provided scratch (sizes stated per function);
+ *   - return 0 = ok, <0 = bad argument, >0 = cudaError_t of the launch;
+ *   - activations are NHWC fp32; "padded" tensors are [img][H+2][W+2][64] with a zero border that the
+ *     caller zero-initialises once (kernels only ever write the interior);
+ *   - E episodes are packed along the image axis, `ipe` images per episode; every BatchNorm batch is
+ *     one episode (methods/DKT.py:140-141).
+ */
+#ifndef DKTB200_H
+#define DKTB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+int dktb_version(void);
+
+/* ---- backbone: ConvBlock = Conv2d(3x3,pad 1,bias) -> BatchNorm2d -> ReLU -> MaxPool2d(2)
+ *      (backbone.py:105-132; nn.Conv2d / nn.BatchNorm2d / nn.MaxPool2d calls at 115-121) -------------- */
+/* first layer, Cin = 3: x [B,3,H,W] NCHW (as the loader delivers it, train.py:142) -> y [B,H,W,64];
+ * partials (nullable) [B*tiles][2][64] BatchNorm partial sums, tiles = dktb_conv1_tiles(H,W). */
+int dktb_conv1_tiles(int H, int W);
+int dktb_conv1_fwd(const float* x, const float* w, const float* bias, float* y, float* partials, int B, int H, int W,
+                   cudaStream_t stream);
+/* dw [64,3,3,3], db [64] (nullable); scratch: dktb_conv1_wgrad_nsplit()*28*64 floats. */
+int dktb_conv1_wgrad_nsplit(void);
+int dktb_conv1_wgrad(const float* x, const float* gy, float* dw, float* db, float* scratch, int B, int H, int W,
+                     cudaStream_t stream);
+/* weight re-layout for the 64->64 kernels: w [64,64,3,3] -> wt_fwd [9][ci][co], wt_dgrad [9][co][ci] (flipped). */
+int dktb_prep_weights(const float* w, float* wt_fwd, float* wt_dgrad, cudaStream_t stream);
+/* 64->64 3x3 conv over padded NHWC: out[q] = sum_tap A[q+off(tap)] * wt[tap]; forward (wt_fwd, bias, partials)
+ * and dgrad (a = gy, wt = wt_dgrad, bias = partials = NULL).  partials [B*tiles][2][64], tiles =
+ * dktb_conv3x3_tiles(H,W).  fp32 CUDA-core version; dktb_conv3x3_tc_* is the tcgen05 3xTF32 version. */
+int dktb_conv3x3_tiles(int H, int W);
+int dktb_conv3x3_fwd(const float* a, const float* wt, const float* bias, float* out, float* partials, int B, int H,
+                     int W, cudaStream_t stream);
+int dktb_conv3x3_wgrad_nsplit(void);
+long dktb_conv3x3_wgrad_scratch_floats(void);
+int dktb_conv3x3_wgrad(const float* a, const float* gy, float* dw, float* db, float* scratch, int B, int H, int W,
+                       cudaStream_t stream);
+
+/* BatchNorm2d statistics (train: per-episode batch stats from the conv partial sums + running-stat EMA,
+ * momentum 0.1, unbiased running variance; eval: running stats).  scratch_d: (B/ipe)*128 doubles. */
+int dktb_bn_finalize(const float* partials, int B, int T, int ipe, int hw, float* mean, float* invstd,
+                     float* running_mean, float* running_var, double* scratch_d, float momentum, float eps,
+                     cudaStream_t stream);
+int dktb_bn_eval_prepare(const float* running_mean, const float* running_var, float* mean, float* invstd, int n,
+                         float eps, cudaStream_t stream);
+/* out = maxpool2(relu(bn(y))); y [B][H+2*in_pad][W+2*in_pad][64]; out [B][Ho+2*out_pad][Wo+2*out_pad][64];
+ * mean/invstd [B/ipe][64] (ipe == 0: one row for all images = eval mode); pool = 0 keeps the resolution. */
+int dktb_bn_relu_pool_fwd(const float* y, const float* mean, const float* invstd, const float* gamma,
+                          const float* beta, float* out, int B, int H, int W, int ipe, int in_pad, int out_pad,
+                          int pool, cudaStream_t stream);
+/* backward of the above (train mode): gy (same layout as y), dgamma/dbeta [64];
+ * partial: B*dktb_bn_bwd_chunks(H,W,pool)*128 floats, sums: (B/ipe)*128 floats. */
+int dktb_bn_bwd_chunks(int H, int W, int pool);
+int dktb_bn_relu_pool_bwd(const float* y, const float* gout, const float* mean, const float* invstd,
+                          const float* gamma, const float* beta, float* gy, float* dgamma, float* dbeta,
+                          float* partial, float* sums, int B, int H, int W, int ipe, int in_pad, int out_pad, int pool,
+                          cudaStream_t stream);
+
+/* ---- feature head: bn_out BatchNorm1d (methods/DKT.py:45-48) + F.normalize (methods/DKT.py:142) -------
+ * features f [E][N][D] NHWC-flattened (j = p*Cch + c); parameters indexed in the reference's NCHW-flatten
+ * order (c*P + p); P <= 1 means identity mapping. */
+int dktb_bn1d_fwd(const float* f, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                  float* z, float* mean, float* invstd, float* var, int E, int N, int D, int Cch, int P, int training,
+                  int update_running, float momentum, float eps, cudaStream_t stream);
+int dktb_bn1d_bwd(const float* f, const float* gz, const float* gamma, const float* mean, const float* invstd,
+                  float* gf, float* dgamma, float* dbeta, float* pgrad /* E*2*D */, int E, int N, int D, int Cch,
+                  int P, cudaStream_t stream);
+int dktb_l2norm_fwd(const float* z, float* zhat, float* inv, long rows, int D, float eps, cudaStream_t stream);
+int dktb_l2norm_bwd(const float* zhat, const float* gzhat, const float* inv, float* gz, long rows, int D,
+                    cudaStream_t stream);
+
+/* ---- exact GP (GPyTorch call sites methods/DKT.py:161-162,177,187,265; DKT_regression.py:52-54,90-93) -- */
+/* out[e][m][n] = <x1[e][m], x2[e][n]>  (LinearKernel / cross-kernel) */
+int dktb_gram(const float* x1, const float* x2, float* out, int E, int M, int N, int D, cudaStream_t stream);
+/* per (episode, class): K~ = softplus(raw_outputscale_c)*Kb + (softplus(raw_noise_c)+1e-4+jitter) I -> Cholesky ->
+ * alpha_c = K~^-1 (y_c - constant_c), loss_terms[e][c] = -log p_c/(N*C), info[e][c] = 0 | failing pivot (1-based).
+ * Optional: linv [E][C][N][N]; dkbase [E][C][N][N] = grad_scale*dLoss/dKb_c; dhyper [E][C][3] =
+ * grad_scale*dLoss/d(raw_outputscale, constant, raw_noise).  raw_outputscale == NULL: no ScaleKernel.
+ * N <= dktb_gp_max_n(). */
+int dktb_gp_max_n(void);
+int dktb_gp_fit(const float* kbase, long kbase_class_stride, const float* y, long y_episode_stride,
+                const float* raw_outputscale, const float* constant, const float* raw_noise, float* alpha,
+                float* linv, float* loss_terms, int* info, float* dkbase, float* dhyper, float grad_scale,
+                float jitter, int E, int C, int N, cudaStream_t stream);
+int dktb_gp_reduce(const float* loss_terms, const float* dhyper, float* loss, float* hyper, int E, int C,
+                   cudaStream_t stream);
+/* dZ = scale * (S + S^T) Z,  S = sum_c w[e][c] */
+int dktb_gram_bwd(const float* w, const float* z, float* dz, int E, int C, int N, int D, float scale,
+                  cudaStream_t stream);
+/* mean[e][c][m] = constant_c + s_c * kx[e][(c)][m][:] . alpha[e][c][:]; pred[e][m] = argmax_c sigmoid(mean) */
+int dktb_gp_predict(const float* kx, long kx_class_stride, const float* alpha, const float* raw_outputscale,
+                    const float* constant, float* mean, int* pred, int E, int C, int M, int N, cudaStream_t stream);
+
+/* ---- optimiser (torch.optim.Adam, methods/DKT.py:114-115,164) ---------------------------------------- */
+int dktb_adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2,
+                   float eps, int step, float grad_scale, cudaStream_t stream);
+int dktb_scale(float* x, long n, float a, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DKTB200_H */

@@ -1,0 +1,265 @@
+"""Per-kernel parity checks shared by the CPU-emulation tests (tests/test_kernels_emu.py, host logic of the
+same kernel sources) and the GPU tests proper (tests/test_kernels_gpu.py, through the C ABI on a B200).
+The reference for every check is plain torch fp32/fp64 on CPU (the oracle for single operators)."""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from oracle import gp as ogp
+
+
+def to_padded_nhwc(x, pad=1):
+    """[B,C,H,W] -> [B,H+2p,W+2p,C] with a zero border."""
+    b, c, h, w = x.shape
+    out = torch.zeros(b, h + 2 * pad, w + 2 * pad, c, dtype=x.dtype)
+    out[:, pad:pad + h, pad:pad + w, :] = x.permute(0, 2, 3, 1)
+    return out
+
+
+def from_padded_nhwc(x, pad=1):
+    b, hp, wp, c = x.shape
+    return x[:, pad:hp - pad, pad:wp - pad, :].permute(0, 3, 1, 2).contiguous()
+
+
+def _close(a, b, rtol=1e-4, atol=1e-5, what=""):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    err = (a - b).abs().max().item()
+    ref = b.abs().max().item()
+    assert err <= atol + rtol * ref, "%s: max abs err %.3e vs ref scale %.3e" % (what, err, ref)
+
+
+def check_conv1(lib, dev, B=3, H=10, W=37, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, 3, H, W, generator=g)
+    w = torch.randn(64, 3, 3, 3, generator=g) * 0.2
+    b = torch.randn(64, generator=g)
+    ref = F.conv2d(x, w, b, padding=1)
+    T = lib.conv1_tiles(H, W)
+    y = torch.empty(B, H, W, 64, device=dev)
+    part = torch.zeros(B * T * 128, device=dev)
+    lib.conv1_fwd(x.to(dev), w.to(dev), b.to(dev), y, part, B, H, W, 0)
+    _close(y.cpu().permute(0, 3, 1, 2), ref, what="conv1 fwd")
+    p = part.cpu().view(B, T, 2, 64).sum(1)
+    _close(p[:, 0], ref.sum((2, 3)), rtol=1e-4, atol=1e-3, what="conv1 sum")
+    _close(p[:, 1], (ref * ref).sum((2, 3)), rtol=1e-4, atol=1e-3, what="conv1 sumsq")
+    # wgrad
+    gy = torch.randn(B, 64, H, W, generator=g)
+    xr = x.clone().requires_grad_(False)
+    wr = w.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    (F.conv2d(xr, wr, br, padding=1) * gy).sum().backward()
+    dw = torch.empty(64, 3, 3, 3, device=dev)
+    db = torch.empty(64, device=dev)
+    scratch = torch.empty(lib.conv1_wgrad_nsplit() * 28 * 64, device=dev)
+    lib.conv1_wgrad(x.to(dev), gy.permute(0, 2, 3, 1).contiguous().to(dev), dw, db, scratch, B, H, W, 0)
+    _close(dw, wr.grad, rtol=1e-4, atol=1e-4, what="conv1 wgrad")
+    _close(db, br.grad, rtol=1e-4, atol=1e-4, what="conv1 bgrad")
+
+
+def check_conv3x3(lib, dev, B=3, H=6, W=5, seed=1, fwd_name="conv3x3_fwd", wgrad_name="conv3x3_wgrad", rtol=1e-4):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, 64, H, W, generator=g)
+    w = torch.randn(64, 64, 3, 3, generator=g) * 0.05
+    b = torch.randn(64, generator=g)
+    gy = torch.randn(B, 64, H, W, generator=g)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.conv2d(xr, wr, br, padding=1)
+    (ref * gy).sum().backward()
+    wt_f = torch.empty(9, 64, 64, device=dev)
+    wt_d = torch.empty(9, 64, 64, device=dev)
+    lib.prep_weights(w.to(dev), wt_f, wt_d, 0)
+    a = to_padded_nhwc(x).to(dev)
+    T = lib.conv3x3_tiles(H, W)
+    y = torch.full((B, H + 2, W + 2, 64), float("nan"), device=dev)
+    part = torch.zeros(B * T * 128, device=dev)
+    getattr(lib, fwd_name)(a, wt_f, b.to(dev), y, part, B, H, W, 0)
+    _close(from_padded_nhwc(y.cpu()), ref, rtol=rtol, what="conv3x3 fwd")
+    p = part.cpu().view(B, T, 2, 64).sum(1)
+    _close(p[:, 0], ref.detach().sum((2, 3)), rtol=1e-4, atol=1e-3, what="conv3x3 sum")
+    _close(p[:, 1], (ref.detach() ** 2).sum((2, 3)), rtol=1e-4, atol=1e-3, what="conv3x3 sumsq")
+    # dgrad = same kernel on gy with flipped weights
+    gyp = to_padded_nhwc(gy).to(dev)
+    gx = torch.full((B, H + 2, W + 2, 64), float("nan"), device=dev)
+    getattr(lib, fwd_name)(gyp, wt_d, None, gx, None, B, H, W, 0)
+    _close(from_padded_nhwc(gx.cpu()), xr.grad, rtol=rtol, what="conv3x3 dgrad")
+    # wgrad
+    dw = torch.empty(64, 64, 3, 3, device=dev)
+    db = torch.empty(64, device=dev)
+    scratch = torch.empty(lib.conv3x3_wgrad_scratch_floats(), device=dev)
+    getattr(lib, wgrad_name)(a, gyp, dw, db, scratch, B, H, W, 0)
+    _close(dw, wr.grad, rtol=rtol, atol=1e-4, what="conv3x3 wgrad")
+    _close(db, br.grad, rtol=rtol, atol=1e-4, what="conv3x3 bgrad")
+
+
+def check_bn_relu_pool(lib, dev, E=2, ipe=3, H=7, W=6, pool=1, in_pad=1, out_pad=1, seed=2):
+    g = torch.Generator().manual_seed(seed)
+    B = E * ipe
+    y = torch.randn(B, 64, H, W, generator=g) * 1.5 + 0.3
+    gamma = torch.rand(64, generator=g) + 0.5
+    gamma[3] = -0.7   # a negative scale must still pool correctly
+    beta = torch.randn(64, generator=g) * 0.3
+    rm0, rv0 = torch.randn(64, generator=g) * 0.1, torch.rand(64, generator=g) + 0.5
+    Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+    gout = torch.randn(B, 64, Ho, Wo, generator=g)
+    # reference: one BatchNorm batch per episode, sequential running-stat updates
+    yr = y.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm, rv = rm0.clone(), rv0.clone()
+    outs = []
+    for e in range(E):
+        o = F.batch_norm(yr[e * ipe:(e + 1) * ipe], rm, rv, gr, br, True, 0.1, 1e-5)
+        o = F.relu(o)
+        outs.append(F.max_pool2d(o, 2) if pool else o)
+    ref = torch.cat(outs, 0)
+    (ref * gout).sum().backward()
+    # device: partial sums as the conv epilogue would emit them (one "tile" per image)
+    part = torch.stack([y.sum((2, 3)), (y * y).sum((2, 3))], 1).reshape(-1).to(dev)   # [B][1][2][64]
+    mean = torch.empty(E, 64, device=dev)
+    invstd = torch.empty(E, 64, device=dev)
+    drm, drv = rm0.clone().to(dev), rv0.clone().to(dev)
+    scratch_d = torch.empty(E * 128, device=dev, dtype=torch.float64)
+    lib.bn_finalize(part, B, 1, ipe, H * W, mean, invstd, drm, drv, scratch_d, 0.1, 1e-5, 0)
+    _close(drm, rm, what="running_mean")
+    _close(drv, rv, what="running_var")
+    yd = (to_padded_nhwc(y) if in_pad else y.permute(0, 2, 3, 1).contiguous()).to(dev)
+    out = torch.zeros(B, Ho + 2 * out_pad, Wo + 2 * out_pad, 64, device=dev)
+    lib.bn_relu_pool_fwd(yd, mean, invstd, gamma.to(dev), beta.to(dev), out, B, H, W, ipe, in_pad, out_pad, pool, 0)
+    got = from_padded_nhwc(out.cpu()) if out_pad else out.cpu().permute(0, 3, 1, 2)
+    _close(got, ref, what="bn_relu_pool fwd")
+    if out_pad:
+        assert float(out.cpu()[:, 0].abs().max()) == 0.0
+    # backward
+    gd = (to_padded_nhwc(gout) if out_pad else gout.permute(0, 2, 3, 1).contiguous()).to(dev)
+    gy = torch.zeros_like(yd)
+    dg, db = torch.empty(64, device=dev), torch.empty(64, device=dev)
+    chunks = lib.bn_bwd_chunks(H, W, pool)
+    partial = torch.empty(B * chunks * 128, device=dev)
+    sums = torch.empty(E * 128, device=dev)
+    lib.bn_relu_pool_bwd(yd, gd, mean, invstd, gamma.to(dev), beta.to(dev), gy, dg, db, partial, sums, B, H, W, ipe,
+                         in_pad, out_pad, pool, 0)
+    got_gy = from_padded_nhwc(gy.cpu()) if in_pad else gy.cpu().permute(0, 3, 1, 2)
+    _close(got_gy, yr.grad, rtol=2e-4, atol=1e-5, what="bn_relu_pool bwd gy")
+    _close(dg, gr.grad, rtol=2e-4, atol=1e-4, what="dgamma")
+    _close(db, br.grad, rtol=2e-4, atol=1e-4, what="dbeta")
+    # eval mode
+    em, ei = torch.empty(64, device=dev), torch.empty(64, device=dev)
+    lib.bn_eval_prepare(drm, drv, em, ei, 64, 1e-5, 0)
+    out2 = torch.zeros_like(out)
+    lib.bn_relu_pool_fwd(yd, em, ei, gamma.to(dev), beta.to(dev), out2, B, H, W, 0, in_pad, out_pad, pool, 0)
+    o = F.relu(F.batch_norm(y, rm, rv, gamma, beta, False, 0.1, 1e-5))
+    ref2 = F.max_pool2d(o, 2) if pool else o
+    got2 = from_padded_nhwc(out2.cpu()) if out_pad else out2.cpu().permute(0, 3, 1, 2)
+    _close(got2, ref2, what="bn_relu_pool eval")
+
+
+def check_head(lib, dev, E=2, N=7, Cch=8, P=4, seed=3):
+    g = torch.Generator().manual_seed(seed)
+    D = Cch * P
+    f_ref = torch.randn(E, N, D, generator=g) * 2 + 0.5           # reference (NCHW-flatten) feature order
+    gamma, beta = torch.rand(D, generator=g) + 0.5, torch.randn(D, generator=g) * 0.2
+    rm0, rv0 = torch.randn(D, generator=g) * 0.1, torch.rand(D, generator=g) + 0.5
+    gzh = torch.randn(E, N, D, generator=g)
+    perm = torch.tensor([(j % Cch) * P + j // Cch for j in range(D)])   # nhwc index j -> reference index
+    fr = f_ref.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm, rv = rm0.clone(), rv0.clone()
+    zs = []
+    for e in range(E):
+        z = F.batch_norm(fr[e], rm, rv, gr, br, True, 0.1, 1e-5)
+        zs.append(F.normalize(z, p=2, dim=1))
+    zh_ref = torch.stack(zs)
+    (zh_ref * gzh).sum().backward()
+    f_dev = f_ref[:, :, perm].contiguous().to(dev)                      # our NHWC-flatten order
+    z = torch.empty(E, N, D, device=dev)
+    zh = torch.empty(E, N, D, device=dev)
+    mean, invstd, var = (torch.empty(E, D, device=dev) for _ in range(3))
+    inv = torch.empty(E * N, device=dev)
+    drm, drv = rm0.clone().to(dev), rv0.clone().to(dev)
+    lib.bn1d_fwd(f_dev, gamma.to(dev), beta.to(dev), drm, drv, z, mean, invstd, var, E, N, D, Cch, P, 1, 1, 0.1, 1e-5, 0)
+    lib.l2norm_fwd(z, zh, inv, E * N, D, 1e-12, 0)
+    _close(zh.cpu(), zh_ref[:, :, perm], what="head fwd")
+    _close(drm, rm, what="bn_out running_mean")
+    _close(drv, rv, what="bn_out running_var")
+    gz = torch.empty(E, N, D, device=dev)
+    gf = torch.empty(E, N, D, device=dev)
+    dg, db = torch.zeros(D, device=dev), torch.zeros(D, device=dev)
+    pgrad = torch.empty(E * 2 * D, device=dev)
+    lib.l2norm_bwd(zh, gzh[:, :, perm].contiguous().to(dev), inv, gz, E * N, D, 0)
+    lib.bn1d_bwd(f_dev, gz, gamma.to(dev), mean, invstd, gf, dg, db, pgrad, E, N, D, Cch, P, 0)
+    _close(gf.cpu(), fr.grad[:, :, perm], rtol=2e-4, atol=1e-6, what="head bwd")
+    _close(dg, gr.grad, rtol=2e-4, atol=1e-5, what="bn_out dgamma")
+    _close(db, br.grad, rtol=2e-4, atol=1e-5, what="bn_out dbeta")
+    # eval mode
+    z2 = torch.empty(E, N, D, device=dev)
+    lib.bn1d_fwd(f_dev, gamma.to(dev), beta.to(dev), drm, drv, z2, None, None, None, E, N, D, Cch, P, 0, 0, 0.1, 1e-5, 0)
+    ref2 = F.batch_norm(f_ref.view(E * N, D), rm, rv, gamma, beta, False, 0.1, 1e-5).view(E, N, D)
+    _close(z2.cpu(), ref2[:, :, perm], what="bn_out eval")
+
+
+def check_gp(lib, dev, E=3, C=3, per_class=4, D=24, M=9, seed=4, rtol=2e-4):
+    g = torch.Generator().manual_seed(seed)
+    N = C * per_class
+    z = F.normalize(torch.randn(E, N, D, generator=g), dim=2)
+    zt = F.normalize(torch.randn(E, M, D, generator=g), dim=2)
+    targets = -torch.ones(C, N)
+    for c in range(C):
+        targets[c, c * per_class:(c + 1) * per_class] = 1.0
+    p = ogp.default_gp_params("bncossim", C, D)
+    p["raw_outputscale"] = torch.tensor([0.3, -0.4, 0.9][:C])
+    p["constant"] = torch.tensor([0.05, -0.1, 0.2][:C])
+    zr = z.clone().requires_grad_(True)
+    p["raw_outputscale"].requires_grad_(True)
+    p["constant"].requires_grad_(True)
+    losses = [ogp.mll_loss("bncossim", zr[e], targets, p) for e in range(E)]
+    (sum(losses) / E).backward()
+    zd = z.to(dev)
+    gram = torch.empty(E, N, N, device=dev)
+    lib.gram(zd, zd, gram, E, N, N, D, 0)
+    _close(gram, z @ z.transpose(1, 2), what="gram")
+    alpha = torch.empty(E, C, N, device=dev)
+    lt = torch.empty(E, C, device=dev)
+    info = torch.ones(E, C, device=dev, dtype=torch.int32)
+    dk = torch.empty(E, C, N, N, device=dev)
+    dh = torch.empty(E, C, 3, device=dev)
+    ros, cst, rn = (p[k].detach().to(dev) for k in ("raw_outputscale", "constant", "raw_noise"))
+    lib.gp_fit(gram, 0, targets.to(dev), 0, ros, cst, rn, alpha, None, lt, info, dk, dh, 1.0 / E, 0.0, E, C, N, 0)
+    assert int(info.cpu().abs().sum()) == 0
+    loss = torch.empty(E, device=dev)
+    hyper = torch.empty(C, 3, device=dev)
+    lib.gp_reduce(lt, dh, loss, hyper, E, C, 0)
+    _close(loss, torch.stack([l.detach() for l in losses]), rtol=rtol, what="mll loss")
+    _close(hyper[:, 0], p["raw_outputscale"].grad, rtol=rtol, atol=1e-6, what="d raw_outputscale")
+    _close(hyper[:, 1], p["constant"].grad, rtol=rtol, atol=1e-6, what="d constant")
+    dz = torch.empty(E, N, D, device=dev)
+    lib.gram_bwd(dk, zd, dz, E, C, N, D, 1.0, 0)
+    _close(dz, zr.grad, rtol=rtol, atol=1e-6, what="d z")
+    # prediction
+    kx = torch.empty(E, M, N, device=dev)
+    lib.gram(zt.to(dev), zd, kx, E, M, N, D, 0)
+    mean = torch.empty(E, C, M, device=dev)
+    pred = torch.empty(E, M, device=dev, dtype=torch.int32)
+    lib.gp_predict(kx, 0, alpha, ros, cst, mean, pred, E, C, M, N, 0)
+    with torch.no_grad():
+        pd = {k: v.detach() for k, v in p.items()}
+        ref_mean = torch.stack([ogp.predict("bncossim", z[e], targets, zt[e], pd) for e in range(E)])
+    _close(mean, ref_mean, rtol=rtol, atol=1e-5, what="predictive mean")
+    ref_pred = torch.sigmoid(ref_mean).numpy().argmax(axis=1)
+    assert np.array_equal(pred.cpu().numpy(), ref_pred)
+    # a non-PD system must be reported, not silently factorised
+    bad = -torch.eye(N).repeat(E, 1, 1).to(dev)
+    lib.gp_fit(bad, 0, targets.to(dev), 0, ros, cst, rn, alpha, None, lt, info, None, None, 1.0, 0.0, E, C, N, 0)
+    assert int((info.cpu() != 0).sum()) == E * C
+
+
+def check_adam(lib, dev, n=1000, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    p0 = torch.randn(n, generator=g)
+    pr = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pr], lr=1e-3)
+    pd, m, v = p0.clone().to(dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    for step in range(1, 4):
+        gr = torch.randn(n, generator=g) * (10.0 ** (step - 3))
+        pr.grad = gr.clone()
+        opt.step()
+        lib.adam_step(pd, gr.to(dev), m, v, n, 1e-3, 0.9, 0.999, 1e-8, step, 1.0, 0)
+    _close(pd, pr.detach(), rtol=1e-6, atol=1e-7, what="adam")

@@ -1,0 +1,52 @@
+"""Host-logic tests (no GPU): the plain-CUDA kernel sources compiled with g++ against the CPU
+emulation of the CUDA execution model (tests/emu) and driven through the same C ABI + ctypes binding
+as the product.  They check index math / staging / reductions of every kernel against torch on CPU.
+The emulation library is test infrastructure: the product never loads it."""
+import os
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+import build_emu  # noqa: E402
+import kernel_checks as kc  # noqa: E402
+from deep_kernel_transfer_b200._lib import DktbLib  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return DktbLib(build_emu.build())
+
+
+DEV = torch.device("cpu")
+
+
+def test_conv1(lib):
+    kc.check_conv1(lib, DEV)
+
+
+def test_conv3x3(lib):
+    kc.check_conv3x3(lib, DEV)
+
+
+def test_conv3x3_odd(lib):
+    kc.check_conv3x3(lib, DEV, B=2, H=10, W=10, seed=11)
+
+
+@pytest.mark.parametrize("pool,in_pad,out_pad,H,W", [(1, 1, 1, 7, 6), (1, 0, 1, 8, 8), (0, 1, 0, 5, 5), (1, 1, 0, 10, 10)])
+def test_bn_relu_pool(lib, pool, in_pad, out_pad, H, W):
+    kc.check_bn_relu_pool(lib, DEV, pool=pool, in_pad=in_pad, out_pad=out_pad, H=H, W=W)
+
+
+def test_head(lib):
+    kc.check_head(lib, DEV)
+    kc.check_head(lib, DEV, E=1, N=5, Cch=12, P=1, seed=8)
+
+
+def test_gp(lib):
+    kc.check_gp(lib, DEV)
+
+
+def test_adam(lib):
+    kc.check_adam(lib, DEV)
