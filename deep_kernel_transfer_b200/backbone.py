@@ -1,0 +1,154 @@
+"""Feature extractors with the reference's ``backbone.py`` API surface (factory names used by
+``io_utils.model_dict``, ``.trunk``, ``.final_feat_dim``, ``forward(x)``; reference backbone.py:250-268,
+404-435) whose arithmetic runs in the hand-written sm_100a kernels (csrc/) instead of cuDNN.
+
+The ``nn.Conv2d`` / ``nn.BatchNorm2d`` objects below are PARAMETER CONTAINERS only: they keep the
+reference's ``state_dict`` key names (``trunk.0.C.weight``, ``trunk.0.BN.running_mean``, the aliased
+``trunk.0.trunk.0.weight`` ...) so checkpoints stay interchangeable; their torch ``forward`` is never
+called.  The hot path (methods/DKT.py) drives ``ConvNetEngine`` directly over packed episodes;
+``ConvNet.forward`` is the public single-batch entry (one BatchNorm batch = the whole input, like the
+reference).  There is no CPU path: tensors must live on a CUDA device.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .engine import ConvNetEngine, ConvNetParams
+
+
+def init_layer(L):
+    """backbone.py:13-20: conv weights ~ N(0, sqrt(2/(k*k*out))); BN weight 1 / bias 0."""
+    if isinstance(L, nn.Conv2d):
+        n = L.kernel_size[0] * L.kernel_size[1] * L.out_channels
+        L.weight.data.normal_(0, math.sqrt(2.0 / float(n)))
+    elif isinstance(L, nn.BatchNorm2d):
+        L.weight.data.fill_(1)
+        L.bias.data.fill_(0)
+
+
+class Flatten(nn.Module):
+    def forward(self, x):
+        return x.view(x.size(0), -1)
+
+
+class ConvBlock(nn.Module):
+    """Conv3x3(pad 1, bias) -> BatchNorm2d -> ReLU -> [MaxPool2d(2)]  (backbone.py:105-132)."""
+    maml = False
+
+    def __init__(self, indim, outdim, pool=True, padding=1):
+        super().__init__()
+        if self.maml:
+            raise NotImplementedError("MAML fast-weight layers are outside the DKT hot path")
+        if padding != 1:
+            raise NotImplementedError("only padding=1 ConvBlocks are on the DKT hot path")
+        self.indim, self.outdim, self.pool_flag = indim, outdim, pool
+        self.C = nn.Conv2d(indim, outdim, 3, padding=padding)
+        self.BN = nn.BatchNorm2d(outdim)
+        self.relu = nn.ReLU(inplace=True)
+        self.parametrized_layers = [self.C, self.BN, self.relu]
+        if pool:
+            self.pool = nn.MaxPool2d(2)
+            self.parametrized_layers.append(self.pool)
+        for layer in self.parametrized_layers:
+            init_layer(layer)
+        self.trunk = nn.Sequential(*self.parametrized_layers)   # aliases C/BN exactly like the reference
+
+    def forward(self, x):
+        raise RuntimeError("ConvBlock is evaluated by the fused dktb200 kernels through ConvNet.forward / DKT")
+
+
+class ConvNet(nn.Module):
+    def __init__(self, depth, flatten=True, image_size=84):
+        super().__init__()
+        if not flatten:
+            raise NotImplementedError("un-flattened ConvNet is only used by RelationNet (out of scope)")
+        self.depth = depth
+        trunk = [ConvBlock(3 if i == 0 else 64, 64, pool=(i < 4)) for i in range(depth)]
+        trunk.append(Flatten())
+        self.trunk = nn.Sequential(*trunk)
+        # 1600 for the reference's 84x84 inputs (backbone.py:264); other sizes are an extension used by tests
+        side = image_size
+        for i in range(min(depth, 4)):
+            side //= 2
+        self.final_feat_dim = 64 * side * side
+        self._engine = None
+
+    # -- engine plumbing -------------------------------------------------------------------------
+    def blocks(self):
+        return [m for m in self.trunk if isinstance(m, ConvBlock)]
+
+    def engine_params(self):
+        P = ConvNetParams(self.depth)
+        for i, b in enumerate(self.blocks()):
+            P.conv_w[i], P.conv_b[i] = b.C.weight.data, b.C.bias.data
+            P.bn_w[i], P.bn_b[i] = b.BN.weight.data, b.BN.bias.data
+            P.bn_rm[i], P.bn_rv[i] = b.BN.running_mean, b.BN.running_var
+        return P
+
+    def engine(self, image_size, device, lib=None):
+        dev = torch.device(device)
+        if self._engine is None or self._engine.layers[0]["H"] != image_size or self._engine.dev != dev:
+            self._engine = ConvNetEngine(lib or _lib.load(), self.depth, image_size, dev)
+        return self._engine
+
+    def forward(self, x):
+        """x [n,3,H,W] on a CUDA device -> features [n, 1600] in the reference's NCHW-flatten order
+        (through ``bn_out`` when DKT appended it to the trunk, methods/DKT.py:45-48)."""
+        if x.device.type != "cuda":
+            raise RuntimeError("dktb200 has no CPU path: move the input to a CUDA device")
+        n = x.shape[0]
+        eng = self.engine(x.shape[-1], x.device)
+        feats = eng.forward(x.contiguous().float(), self.engine_params(), ipe=n, training=self.training)
+        out = feats.view(n, eng.P, 64).transpose(1, 2).reshape(n, 64 * eng.P)      # NHWC-flat -> NCHW-flat
+        if hasattr(self.trunk, "bn_out"):
+            bn = self.trunk.bn_out
+            z = torch.empty(1, n, out.shape[1], device=x.device)
+            st = [torch.empty(1, out.shape[1], device=x.device) for _ in range(3)]
+            eng.lib.bn1d_fwd(out.contiguous(), bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, z,
+                             st[0], st[1], st[2], 1, n, out.shape[1], 64, 1, int(self.training), 1, 0.1, 1e-5,
+                             torch.cuda.current_stream(x.device).cuda_stream)
+            out = z.view(n, -1)
+        return out
+
+
+def _not_on_hot_path(name):
+    def factory(*a, **k):
+        raise NotImplementedError(name + " belongs to other few-shot methods (RelationNet / omniglot) and is outside "
+                                  "the DKT hot path this package implements")
+    factory.__name__ = name
+    return factory
+
+
+def Conv4():
+    return ConvNet(4)
+
+
+def Conv6():
+    return ConvNet(6)
+
+
+Conv4NP = _not_on_hot_path("Conv4NP")
+Conv6NP = _not_on_hot_path("Conv6NP")
+Conv4S = _not_on_hot_path("Conv4S")
+Conv4SNP = _not_on_hot_path("Conv4SNP")
+ResNet10 = _not_on_hot_path("ResNet10")
+ResNet18 = _not_on_hot_path("ResNet18")
+ResNet34 = _not_on_hot_path("ResNet34")
+ResNet50 = _not_on_hot_path("ResNet50")
+ResNet101 = _not_on_hot_path("ResNet101")
+Conv3 = _not_on_hot_path("Conv3")
+
+# class attributes train.py:163-167 pokes for MAML (kept so the driver imports cleanly)
+class SimpleBlock:      # noqa: E302
+    maml = False
+
+
+class BottleneckBlock:
+    maml = False
+
+
+class ResNet:
+    maml = False

@@ -1,0 +1,103 @@
+"""Parameter containers that mirror the GPyTorch module tree the reference builds in
+``DKT.get_model_likelihood_mll`` (methods/DKT.py:58-71, 337-378) so that ``state_dict()`` keys
+(``model.models.0.covar_module.raw_outputscale`` ...) and ``model.parameters()`` keep their meaning
+with GPyTorch removed.  No arithmetic happens here: the exact-GP math is csrc/gp.cu.
+Shapes follow GPyTorch 1.0.1: raw_noise [1], constant [1], raw_outputscale [], raw_lengthscale /
+raw_variance / raw_offset [1,1].
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+CLASSIFICATION_KERNELS = ("linear", "rbf", "RBF", "matern", "poli1", "poli2", "cossim", "bncossim")
+
+
+def inv_softplus(x):
+    return x + math.log(-math.expm1(-x))
+
+
+class _NoiseCovar(nn.Module):
+    def __init__(self, noise=None, learn=True):
+        super().__init__()
+        raw = 0.0 if noise is None else inv_softplus(noise - 1e-4)     # noise = softplus(raw) + 1e-4
+        self.raw_noise = nn.Parameter(torch.full((1,), raw), requires_grad=learn)
+
+
+class GaussianLikelihood(nn.Module):
+    def __init__(self, noise=None, learn=True):
+        super().__init__()
+        self.noise_covar = _NoiseCovar(noise, learn)
+
+    @property
+    def noise(self):
+        return torch.nn.functional.softplus(self.noise_covar.raw_noise) + 1e-4
+
+
+class ConstantMean(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.constant = nn.Parameter(torch.zeros(1))
+
+
+class _BaseKernel(nn.Module):
+    def __init__(self, kind):
+        super().__init__()
+        self.kind = kind
+        if kind in ("linear", "cossim", "bncossim"):
+            frozen = kind != "linear"     # DKT.py:369-370: variance := 1.0, requires_grad False
+            self.raw_variance = nn.Parameter(torch.full((1, 1), inv_softplus(1.0) if frozen else 0.0),
+                                             requires_grad=not frozen)
+        elif kind in ("rbf", "matern"):
+            self.raw_lengthscale = nn.Parameter(torch.zeros(1, 1))
+        elif kind in ("poli1", "poli2"):
+            self.raw_offset = nn.Parameter(torch.zeros(1))
+
+    @property
+    def lengthscale(self):
+        if hasattr(self, "raw_lengthscale"):
+            return torch.nn.functional.softplus(self.raw_lengthscale)
+        return None
+
+
+class ScaleKernel(nn.Module):
+    def __init__(self, kind):
+        super().__init__()
+        self.base_kernel = _BaseKernel(kind)
+        self.raw_outputscale = nn.Parameter(torch.zeros(()))
+
+    @property
+    def outputscale(self):
+        return torch.nn.functional.softplus(self.raw_outputscale)
+
+
+class ExactGPLayer(nn.Module):
+    """One one-vs-rest exact GP of the classifier (methods/DKT.py:337-378)."""
+
+    def __init__(self, likelihood, kernel="linear"):
+        super().__init__()
+        k = "rbf" if kernel == "RBF" else kernel
+        if k not in ("linear", "rbf", "matern", "poli1", "poli2", "cossim", "bncossim"):
+            raise ValueError("[ERROR] the kernel '" + str(kernel) + "' is not supported!")
+        self.likelihood = likelihood
+        self.mean_module = ConstantMean()
+        self.covar_module = ScaleKernel(k)
+
+
+class IndependentModelList(nn.Module):
+    def __init__(self, *models):
+        super().__init__()
+        self.models = nn.ModuleList(models)
+
+
+class LikelihoodList(nn.Module):
+    def __init__(self, *likelihoods):
+        super().__init__()
+        self.likelihoods = nn.ModuleList(likelihoods)
+
+
+class SumMarginalLogLikelihood(nn.Module):
+    def __init__(self, likelihood, model):
+        super().__init__()
+        self.likelihood = likelihood
+        self.model = model

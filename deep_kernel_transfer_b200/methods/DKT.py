@@ -1,0 +1,326 @@
+"""Deep Kernel Transfer, few-shot classification -- drop-in for the reference ``methods/DKT.py``
+(class ``DKT``: __init__ 33-50, get_model_likelihood_mll 58-71, train_loop 113-197, correct 199-272,
+test_loop 274-295, get_logits 297-335) with GPyTorch and cuDNN removed from the hot path: every
+arithmetic step runs in the hand-written sm_100a kernels behind include/dktb200.h.
+
+Same constructor / methods / attributes / printed fields as the reference, so the reference's
+``train.py`` / ``test.py`` / ``test_uncertainty.py`` run against it unmodified.  Extensions (all optional,
+defaults reproduce the reference): ``kernel=`` overrides ``configs.kernel_type``; ``episodes_per_step=E``
+packs E loader episodes into one meta-step (mean of the per-episode losses; E=1 is the reference's
+one-episode-per-Adam-step); under ``torch.distributed`` the flat gradient buffer is all-reduced once
+per step (episode-level data parallelism).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+from time import gmtime, strftime
+
+from .. import _lib, configs, gp_modules as gpm
+from ..engine import GPHead, GPHeadParams, ConvNetParams, check_info, make_targets, _stream
+from ..flat import FlatPack
+from .meta_template import MetaTemplate
+
+kernel_type = configs.kernel_type      # read at import time, like the reference (DKT.py:14)
+
+try:
+    from tensorboardX import SummaryWriter
+    IS_TBX_INSTALLED = True
+except ImportError:
+    IS_TBX_INSTALLED = False
+
+
+class DKT(MetaTemplate):
+    def __init__(self, model_func, n_way, n_support, kernel=None, episodes_per_step=1, lib=None):
+        super(DKT, self).__init__(model_func, n_way, n_support)
+        self.kernel = kernel if kernel is not None else kernel_type
+        if self.kernel == "RBF":
+            self.kernel = "rbf"
+        self.iteration = 0
+        self.writer = None
+        self.feature_extractor = self.feature
+        self.get_model_likelihood_mll()
+        if self.kernel == "cossim":
+            self.normalize = True
+        elif self.kernel == "bncossim":
+            self.normalize = True
+            latent_size = int(np.prod(self.feature_extractor.final_feat_dim))
+            self.feature_extractor.trunk.add_module("bn_out", nn.BatchNorm1d(latent_size))
+        else:
+            self.normalize = False
+        if self.kernel not in ("cossim", "bncossim"):
+            raise NotImplementedError("kernel '%s' is not on the CUDA path yet (cossim / bncossim are)" % self.kernel)
+        self.episodes_per_step = int(episodes_per_step)
+        self.monitor = True
+        self._lib = lib
+        self._pack = None
+        self._head = None
+        self._adam = None
+        self.last_step = None
+
+    # ------------------------------------------------------------------ construction (DKT.py:52-71)
+    def init_summary(self):
+        if IS_TBX_INSTALLED:
+            time_string = strftime("%d%m%Y_%H%M%S", gmtime())
+            self.writer = SummaryWriter(log_dir="./log/" + time_string)
+
+    def get_model_likelihood_mll(self, train_x_list=None, train_y_list=None):
+        models, likelihoods = [], []
+        for _ in range(self.n_way):
+            likelihood = gpm.GaussianLikelihood(noise=0.1, learn=False)   # DKT.py:346-347
+            models.append(gpm.ExactGPLayer(likelihood, kernel=self.kernel))
+            likelihoods.append(likelihood)
+        self.model = gpm.IndependentModelList(*models)
+        self.likelihood = gpm.LikelihoodList(*likelihoods)
+        self.mll = gpm.SumMarginalLogLikelihood(self.likelihood, self.model)
+        return self.model, self.likelihood, self.mll
+
+    # ------------------------------------------------------------------ flat parameter buffers
+    def _device(self):
+        return next(self.feature.parameters()).device
+
+    def _ensure_packed(self):
+        dev = self._device()
+        if self._pack is not None and self._pack.intact() and self._bufs.intact():
+            return
+        if dev.type != "cuda" and self._lib is None:
+            raise RuntimeError("dktb200 has no CPU path: call .cuda() on the model first")
+        lib = self._lib or _lib.load()
+        self.lib = lib
+        C = self.n_way
+        ms = self.model.models
+        train = [("gp.raw_outputscale.%d" % c, ms[c].covar_module.raw_outputscale, 1) for c in range(C)]
+        train += [("gp.constant.%d" % c, ms[c].mean_module.constant, 1) for c in range(C)]
+        self._gp_count = len(train)
+        blocks = self.feature.blocks()
+        for i, b in enumerate(blocks):
+            train += [("bb.%d.C.weight" % i, b.C.weight, 4), ("bb.%d.C.bias" % i, b.C.bias, 4),
+                      ("bb.%d.BN.weight" % i, b.BN.weight, 4), ("bb.%d.BN.bias" % i, b.BN.bias, 4)]
+        bn_out = getattr(self.feature.trunk, "bn_out", None)
+        if bn_out is not None:
+            train += [("bn_out.weight", bn_out.weight, 4), ("bn_out.bias", bn_out.bias, 4)]
+        bufs = [("gp.raw_noise.%d" % c, ms[c].likelihood.noise_covar.raw_noise, 1) for c in range(C)]
+        for i, b in enumerate(blocks):
+            bufs += [("bb.%d.BN.running_mean" % i, b.BN.running_mean, 4), ("bb.%d.BN.running_var" % i, b.BN.running_var, 4)]
+        if bn_out is not None:
+            bufs += [("bn_out.running_mean", bn_out.running_mean, 4), ("bn_out.running_var", bn_out.running_var, 4)]
+        self._pack = FlatPack(train, dev)
+        self._bufs = FlatPack(bufs, dev, with_grad=False)
+        gp_end = self._pack.offsets[self._gp_count]
+        self._gp_range = (0, gp_end)
+        self._bb_range = (gp_end, self._pack.numel)
+        pk = self._pack
+        # engine-facing parameter / gradient views
+        P, G = ConvNetParams(len(blocks)), ConvNetParams(len(blocks))
+        for i, b in enumerate(blocks):
+            for holder, grad in ((P, False), (G, True)):
+                holder.conv_w[i] = pk.view("bb.%d.C.weight" % i, grad)
+                holder.conv_b[i] = pk.view("bb.%d.C.bias" % i, grad)
+                holder.bn_w[i] = pk.view("bb.%d.BN.weight" % i, grad)
+                holder.bn_b[i] = pk.view("bb.%d.BN.bias" % i, grad)
+            P.bn_rm[i], P.bn_rv[i] = b.BN.running_mean, b.BN.running_var
+        self._P, self._G = P, G
+        HP, GH = GPHeadParams(), GPHeadParams()
+        HP.raw_outputscale = pk.flat[0:C]
+        HP.constant = pk.flat[C:2 * C]
+        GH.raw_outputscale = pk.grad[0:C]
+        GH.constant = pk.grad[C:2 * C]
+        HP.raw_noise = self._bufs.flat[0:C]
+        if bn_out is not None:
+            HP.bn_w, HP.bn_b = pk.view("bn_out.weight"), pk.view("bn_out.bias")
+            GH.bn_w, GH.bn_b = pk.view("bn_out.weight", True), pk.view("bn_out.bias", True)
+            HP.bn_rm, HP.bn_rv = bn_out.running_mean, bn_out.running_var
+        self._HP, self._GH = HP, GH
+        self._head = None
+        self._adam = None
+
+    def _get_head(self, eng):
+        if self._head is None or self._head.dev != eng.dev or self._head.D != eng.D:
+            self._head = GPHead(self.lib, self.kernel, self.n_way, eng.D, 64, eng.P, eng.dev)
+        return self._head
+
+    def _new_adam(self):
+        """A fresh Adam at every train_loop call: GP lr 1e-4, backbone lr 1e-3 (DKT.py:114-115)."""
+        n = self._pack.numel
+        dev = self._pack.flat.device
+        self._adam = {"m": torch.zeros(n, device=dev), "v": torch.zeros(n, device=dev), "step": 0,
+                      "lr_gp": 1e-4, "lr_bb": 1e-3}
+
+    # ------------------------------------------------------------------ one packed meta-train step
+    def _world(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist, dist.get_world_size()
+        return None, 1
+
+    def train_step(self, x_dev):
+        """x_dev [E, C, S+Q, 3, H, W] on the device.  Steps 1-6 of the reference's loop body
+        (DKT.py:117-193) for E packed episodes.  Returns device tensors (no host sync)."""
+        self._ensure_packed()
+        if self._adam is None:
+            self._new_adam()
+        lib = self.lib
+        E, C, SQ = x_dev.shape[0], x_dev.shape[1], x_dev.shape[2]
+        N = C * SQ
+        dev = x_dev.device
+        st = _stream(dev)
+        x_all = x_dev.reshape(E * N, *x_dev.shape[3:])
+        eng = self.feature.engine(x_dev.shape[-1], dev, lib)
+        head = self._get_head(eng)
+        head.ensure(E, N)
+        dist, world = self._world()
+        targets = make_targets(C, SQ, dev)
+        # 1-3: train-mode features, prior, -mll
+        feats = eng.forward(x_all, self._P, ipe=N, training=True)
+        zh = head.embed(feats, self._HP, E, N, training=True, out=head.w["zh_train"])
+        loss = head.fit(zh, targets, self._HP, E, N, want_grad=True, grad_scale=1.0 / E)
+        # 4: backward + Adam
+        gfeat = head.backward(feats, zh, self._HP, self._GH, E, N)
+        eng.backward(x_all, gfeat, self._P, self._G, ipe=N)
+        if world > 1:
+            dist.all_reduce(self._pack.grad)
+        ad = self._adam
+        ad["step"] += 1
+        (g0, g1), (b0, b1) = self._gp_range, self._bb_range
+        fl, gr = self._pack.flat, self._pack.grad
+        if g1 > g0:
+            lib.adam_step(fl[g0:g1], gr[g0:g1], ad["m"][g0:g1], ad["v"][g0:g1], g1 - g0, ad["lr_gp"], 0.9, 0.999, 1e-8,
+                          ad["step"], 1.0 / world, st)
+        lib.adam_step(fl[b0:b1], gr[b0:b1], ad["m"][b0:b1], ad["v"][b0:b1], b1 - b0, ad["lr_bb"], 0.9, 0.999, 1e-8,
+                      ad["step"], 1.0 / world, st)
+        if world > 1:      # keep replicas identical: average the BatchNorm running statistics
+            dist.all_reduce(self._bufs.flat)
+            lib.scale(self._bufs.flat, self._bufs.numel, 1.0 / world, st)
+        for b in self.feature.blocks():
+            b.BN.num_batches_tracked += E
+        out = {"loss": loss.clone(), "info": head.w["info"]}
+        if self.monitor:
+            # 5-6: eval-mode features of the same images; the GP stays conditioned on the pre-update
+            # train-mode features but uses the post-update hyper-parameters (Appendix B.4)
+            feats_e = eng.forward(x_all, self._P, ipe=N, training=False)
+            zh_e = head.embed(feats_e, self._HP, E, N, training=False, out=head.w["zh"])
+            head.fit(head.w["zh_train"], targets, self._HP, E, N, want_grad=False)
+            if "mon_mean" not in head.w or head.w["mon_mean"].shape != (E, C, N):
+                head.w["mon_mean"] = torch.empty(E, C, N, device=dev)
+                head.w["mon_pred"] = torch.empty(E, N, device=dev, dtype=torch.int32)
+                head.w["mon_kx"] = torch.empty(E, N, N, device=dev)
+            head.predict(zh_e, head.w["zh_train"], self._HP, E, N, N, head.w["mon_mean"], head.w["mon_pred"],
+                         head.w["mon_kx"])
+            labels = torch.arange(C, device=dev, dtype=torch.int32).repeat_interleave(SQ)
+            hit = (head.w["mon_pred"] == labels.unsqueeze(0)).view(E, C, SQ)
+            out["acc_support"] = hit[:, :, :self.n_support].float().mean((1, 2)) * 100.0
+            out["acc_query"] = hit[:, :, self.n_support:].float().mean((1, 2)) * 100.0
+            out["mean"] = head.w["mon_mean"]
+        self.last_step = out
+        return out
+
+    # ------------------------------------------------------------------ reference API
+    def train_loop(self, epoch, train_loader, optimizer=None, print_freq=10):
+        # the reference ignores `optimizer` and builds its own Adam here, every call (DKT.py:114-115)
+        self._ensure_packed()
+        self._new_adam()
+        dev = self._device()
+        pend = []
+        n_items = len(train_loader)
+        step_i = 0
+        for i, (x, _) in enumerate(train_loader):
+            self.n_query = x.size(1) - self.n_support
+            if self.change_way:
+                self.n_way = x.size(0)
+            pend.append(x)
+            if len(pend) < self.episodes_per_step and i + 1 < n_items:
+                continue
+            xs = torch.stack(pend, 0) if len(pend) > 1 else pend[0].unsqueeze(0)
+            pend = []
+            x_dev = xs.to(dev, non_blocking=True).float().contiguous()
+            out = self.train_step(x_dev)
+            self.iteration = i + (epoch * n_items)
+            if step_i % print_freq == 0:
+                check_info(out["info"])
+                ms = self.model.models
+                outputscale = float(np.mean([m.covar_module.outputscale.item() for m in ms]))
+                noise = float(np.mean([m.likelihood.noise.item() for m in ms]))
+                ls = [m.covar_module.base_kernel.lengthscale for m in ms]
+                lenghtscale = float(np.mean([l.mean().item() for l in ls])) if ls[0] is not None else 0.0
+                loss = out["loss"].mean().item()
+                acc_s = out["acc_support"].mean().item() if self.monitor else float("nan")
+                acc_q = out["acc_query"].mean().item() if self.monitor else float("nan")
+                if self.writer is not None:
+                    self.writer.add_scalar("loss", loss, self.iteration)
+                    self.writer.add_scalar("GP_support_accuracy", acc_s, self.iteration)
+                    self.writer.add_scalar("GP_query_accuracy", acc_q, self.iteration)
+                print('Epoch [{:d}] [{:d}/{:d}] | Outscale {:f} | Lenghtscale {:f} | Noise {:f} | Loss {:f} | Supp. {:f} | Query {:f}'.format(
+                    epoch, i, n_items, outputscale, lenghtscale, noise, loss, acc_s, acc_q))
+            step_i += 1
+
+    def _episode_logits(self, x):
+        """x [C, S+Q, 3, H, W] (any device) -> (mean [C, M] device tensor, pred [M] int32 device tensor)."""
+        self._ensure_packed()
+        dev = self._device()
+        C, SQ = x.shape[0], x.shape[1]
+        S = self.n_support
+        Q = SQ - S
+        x_dev = x.to(dev, non_blocking=True).float().contiguous().view(C * SQ, *x.shape[2:])
+        eng = self.feature.engine(x.shape[-1], dev, self.lib)
+        head = self._get_head(eng)
+        B = C * SQ
+        feats = eng.forward(x_dev, self._P, ipe=B, training=False)          # eval-mode BN is per-sample
+        head.ensure(1, B)
+        zh_all = head.embed(feats, self._HP, 1, B, training=False, out=head.w["zh"])[0]       # [B, D]
+        idx = torch.arange(B, device=dev).view(C, SQ)
+        zh_s = zh_all.index_select(0, idx[:, :S].reshape(-1)).unsqueeze(0).contiguous()       # [1, C*S, D]
+        zh_q = zh_all.index_select(0, idx[:, S:].reshape(-1)).unsqueeze(0).contiguous()       # [1, C*Q, D]
+        N, M = C * S, C * Q
+        fit_head = self._test_head(eng, N)
+        fit_head.fit(zh_s, make_targets(C, S, dev), self._HP, 1, N, want_grad=False)
+        mean = torch.empty(1, C, M, device=dev)
+        pred = torch.empty(1, M, device=dev, dtype=torch.int32)
+        kx = torch.empty(1, M, N, device=dev)
+        fit_head.predict(zh_q, zh_s, self._HP, 1, M, N, mean, pred, kx)
+        self._last_info = fit_head.w["info"]
+        return mean[0], pred[0]
+
+    def _test_head(self, eng, N):
+        h = getattr(self, "_thead", None)
+        if h is None or h.dev != eng.dev or h.D != eng.D:
+            h = GPHead(self.lib, self.kernel, self.n_way, eng.D, 64, eng.P, eng.dev)
+            self._thead = h
+        h.ensure(1, N)
+        return h
+
+    def correct(self, x, N=0, laplace=False):
+        if laplace or N != 0:
+            raise NotImplementedError("Laplace / test-time hyper-parameter adaptation are not on the CUDA path yet")
+        C = x.shape[0]
+        self.n_query = x.size(1) - self.n_support
+        _, pred = self._episode_logits(x)
+        check_info(self._last_info)
+        y_query = np.repeat(range(C), self.n_query)
+        top1_correct = np.sum(pred.cpu().numpy() == y_query)
+        return float(top1_correct), len(y_query), 0.0
+
+    def test_loop(self, test_loader, record=None, return_std=False):
+        acc_all = []
+        iter_num = len(test_loader)
+        for i, (x, _) in enumerate(test_loader):
+            self.n_query = x.size(1) - self.n_support
+            if self.change_way:
+                self.n_way = x.size(0)
+            correct_this, count_this, loss_value = self.correct(x)
+            acc_all.append(correct_this / count_this * 100)
+            if i % 100 == 0:
+                acc_mean = np.mean(np.asarray(acc_all))
+                print('Test | Batch {:d}/{:d} | Loss {:f} | Acc {:f}'.format(i, len(test_loader), loss_value, acc_mean))
+        acc_all = np.asarray(acc_all)
+        acc_mean = np.mean(acc_all)
+        acc_std = np.std(acc_all)
+        print('%d Test Acc = %4.2f%% +- %4.2f%%' % (iter_num, acc_mean, 1.96 * acc_std / np.sqrt(iter_num)))
+        if self.writer is not None:
+            self.writer.add_scalar('test_accuracy', acc_mean, self.iteration)
+        if return_std:
+            return acc_mean, acc_std
+        return acc_mean
+
+    def get_logits(self, x):
+        self.n_query = x.size(1) - self.n_support
+        mean, _ = self._episode_logits(x)
+        return mean.t().contiguous()          # [C*Q, C]  (torch.stack(means, 1), DKT.py:333-335)

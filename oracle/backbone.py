@@ -55,7 +55,7 @@ def _put(params, prefix, d):
         params[prefix + "." + k] = v
 
 
-def init_params(arch, seed=0, bn_out=False):
+def init_params(arch, seed=0, bn_out=False, bn_out_dim=None):
     """Random-init parameters with the reference's init_layer semantics (synthetic weights)."""
     g = torch.Generator().manual_seed(seed)
     p = {}
@@ -99,7 +99,7 @@ def init_params(arch, seed=0, bn_out=False):
                 indim = outdim
                 t += 1
     if bn_out:
-        _put(p, "trunk.bn_out", _bn_init(feat_dim(arch)))   # DKT.py:45-48
+        _put(p, "trunk.bn_out", _bn_init(bn_out_dim or feat_dim(arch)))   # DKT.py:45-48
     return p
 
 

@@ -34,11 +34,12 @@ def features(arch, bb, x, kernel, training, update_running=True):
 class OracleDKT:
     """Holds backbone + GP parameters and an Adam pair exactly like DKT.train_loop (DKT.py:114-115)."""
 
-    def __init__(self, arch="Conv4", kernel="bncossim", n_way=5, n_support=5, seed=0, dtype=torch.float32):
+    def __init__(self, arch="Conv4", kernel="bncossim", n_way=5, n_support=5, seed=0, dtype=torch.float32,
+                 feat_dim=None):
         self.arch, self.kernel, self.n_way, self.n_support = arch, kernel, n_way, n_support
-        self.bb = obb.init_params(arch, seed=seed, bn_out=(kernel == "bncossim"))
+        self.bb = obb.init_params(arch, seed=seed, bn_out=(kernel == "bncossim"), bn_out_dim=feat_dim)
         self.bb = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in self.bb.items()}
-        self.gp = ogp.default_gp_params(kernel, n_way, obb.feat_dim(arch), dtype=dtype, classification=True)
+        self.gp = ogp.default_gp_params(kernel, n_way, feat_dim or obb.feat_dim(arch), dtype=dtype, classification=True)
         self.optimizer = None
 
     # -- parameter bookkeeping

@@ -1,0 +1,153 @@
+"""End-to-end parity checks of the drop-in ``DKT`` module against the CPU oracle (oracle/episode.py),
+shared by the emulation tests (CPU, host logic) and the GPU tests (parity proper)."""
+import numpy as np
+import torch
+
+from oracle import episode as oep
+
+
+def load_oracle_params(model, oracle):
+    """Copy the oracle's backbone + GP parameters into the module (reference state_dict key names)."""
+    sd = model.feature.state_dict()
+    new = {}
+    for k in sd:
+        kk = k
+        if kk not in oracle.bb:                     # ConvBlock aliases: trunk.i.trunk.{0,1}.*
+            head, tail = kk.split(".trunk.", 1)
+            idx, rest = tail.split(".", 1)
+            kk = head + (".C." if idx == "0" else ".BN.") + rest
+        new[k] = oracle.bb[kk].detach().clone()
+    model.feature.load_state_dict(new)
+    for c, m in enumerate(model.model.models):
+        m.covar_module.raw_outputscale.data.fill_(float(oracle.gp["raw_outputscale"][c]))
+        m.mean_module.constant.data.fill_(float(oracle.gp["constant"][c]))
+
+
+def model_cpu_sync(model, oracle, dev):
+    """Re-synchronise the device model from the oracle's current parameters / buffers."""
+    load_oracle_params(model, oracle)
+    model._ensure_packed()
+
+
+def rel_err(a, b):
+    a, b = a.detach().cpu().double().reshape(-1), b.detach().cpu().double().reshape(-1)
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def check_train_step(model_factory, dev, image_size=32, n_way=2, n_support=1, n_query=2, E=2, tol=1e-4,
+                     steps=2, kernel="bncossim", lib=None):
+    """Runs `steps` packed meta-train steps on the device path and on the oracle from identical weights
+    and inputs; checks loss, every gradient, the post-Adam parameters, BN running statistics and the
+    monitoring predictions (argmax bit-exact).  Tolerance: 1e-4 relative (north_star)."""
+    from deep_kernel_transfer_b200.methods.DKT import DKT
+    torch.manual_seed(0)
+    oracle = oep.OracleDKT("Conv4", kernel, n_way=n_way, n_support=n_support, seed=0,
+                           feat_dim=64 * (image_size // 16) ** 2)
+    # non-trivial GP hyper-parameters / affine parameters so that every gradient path is exercised
+    oracle.gp["raw_outputscale"] = torch.linspace(-0.3, 0.6, n_way)
+    oracle.gp["constant"] = torch.linspace(0.1, -0.2, n_way)
+    g = torch.Generator().manual_seed(5)
+    for k in oracle.bb:
+        if k.endswith("BN.weight") or k.endswith("bn_out.weight"):
+            oracle.bb[k] = 1.0 + 0.2 * torch.randn(oracle.bb[k].shape, generator=g)
+        if k.endswith("BN.bias") or k.endswith("bn_out.bias"):
+            oracle.bb[k] = 0.1 * torch.randn(oracle.bb[k].shape, generator=g)
+    oracle64 = oep.OracleDKT("Conv4", kernel, n_way=n_way, n_support=n_support, seed=0, dtype=torch.float64,
+                             feat_dim=64 * (image_size // 16) ** 2)
+    model = DKT(model_factory, n_way, n_support, kernel=kernel, episodes_per_step=E, lib=lib)
+    load_oracle_params(model, oracle)
+    model = model.to(dev)
+    model.train()
+    worst = {}
+
+    floor = {}
+
+    def upd(key, val, val32=0.0):
+        """val: device vs fp64 oracle; val32: fp32 oracle vs fp64 oracle (the reference's own rounding envelope)."""
+        worst[key] = max(worst.get(key, 0.0), val)
+        floor[key] = max(floor.get(key, 0.0), val32)
+
+    for step in range(steps):
+        xs = torch.stack([oep.synthetic_episode(100 * step + e, n_way, n_support, n_query, image_size)
+                          for e in range(E)])
+        # Parity is defined per step from IDENTICAL weights: Adam turns rounding-level
+        # differences of near-zero gradients into +-lr moves, so trajectories are only comparable step-wise.
+        oracle.optimizer = None
+        if step > 0:
+            for k in list(oracle.bb):
+                oracle.bb[k] = oracle.bb[k].detach().clone()
+            for k in list(oracle.gp):
+                oracle.gp[k] = oracle.gp[k].detach().clone()
+            model_cpu_sync(model, oracle, dev)
+        w_before = [b.C.weight.detach().cpu().clone() for b in model.feature.blocks()]
+        oracle64.optimizer = None
+        oracle64.bb = {k: (v.detach().double() if v.is_floating_point() else v.clone()) for k, v in oracle.bb.items()}
+        oracle64.gp = {k: v.detach().double() for k, v in oracle.gp.items()}
+        r64 = oracle64.train_step(xs.double(), monitor=False)
+        ref = oracle.train_step(xs)
+        model._ensure_packed()
+        model._new_adam()
+        out = model.train_step(xs.to(dev))
+        assert int(out["info"].cpu().abs().sum()) == 0
+        upd("loss", rel_err(out["loss"], r64["loss"]), rel_err(ref["loss"], r64["loss"]))
+        for i, b in enumerate(model.feature.blocks()):
+            for nm, t in (("C.weight", b.C.weight), ("C.bias", b.C.bias), ("BN.weight", b.BN.weight),
+                          ("BN.bias", b.BN.bias)):
+                key = "trunk.%d.%s" % (i, nm)
+                if nm == "C.bias":
+                    # the conv bias cancels inside BatchNorm: its gradient is rounding noise around zero;
+                    # only require it to be negligible w.r.t. the weight gradient scale
+                    scale = float(ref["grads"]["trunk.%d.C.weight" % i].abs().max())
+                    assert float(t.grad.abs().max()) <= 1e-3 * scale + 1e-6, key
+                    continue
+                upd("g." + key, rel_err(t.grad, r64["grads"][key]), rel_err(ref["grads"][key], r64["grads"][key]))
+            # first Adam step moves every weight by lr*sign(g) (|g| >> eps): compare where the sign is
+            # numerically determined
+            gref = ref["grads"]["trunk.%d.C.weight" % i]
+            mask = gref.abs() > 1e-3 * gref.abs().max()
+            d_dev = (b.C.weight.detach().cpu() - w_before[i])[mask]
+            d_ref = (oracle.bb["trunk.%d.C.weight" % i].detach() - w_before[i])[mask]
+            upd("adam.w%d" % i, float((d_dev - d_ref).abs().max() / 1e-3))
+            upd("rv%d" % i, rel_err(b.BN.running_var, oracle.bb["trunk.%d.BN.running_var" % i]))
+        if kernel == "bncossim":
+            bn = model.feature.trunk.bn_out
+            upd("g.bn_out.w", rel_err(bn.weight.grad, r64["grads"]["trunk.bn_out.weight"]),
+                rel_err(ref["grads"]["trunk.bn_out.weight"], r64["grads"]["trunk.bn_out.weight"]))
+            upd("g.bn_out.b", rel_err(bn.bias.grad, r64["grads"]["trunk.bn_out.bias"]),
+                rel_err(ref["grads"]["trunk.bn_out.bias"], r64["grads"]["trunk.bn_out.bias"]))
+        gos = torch.stack([m.covar_module.raw_outputscale.grad for m in model.model.models])
+        gct = torch.stack([m.mean_module.constant.grad.view(()) for m in model.model.models])
+        upd("g.outputscale", rel_err(gos, r64["grads"]["raw_outputscale"]),
+            rel_err(ref["grads"]["raw_outputscale"], r64["grads"]["raw_outputscale"]))
+        upd("g.constant", rel_err(gct, r64["grads"]["constant"]), rel_err(ref["grads"]["constant"], r64["grads"]["constant"]))
+        # monitoring predictions: weights differ after Adam only by sign flips of noise-level gradients
+        # (conv biases, which BatchNorm cancels) -> means still agree to a few 1e-4
+        C, SQ = n_way, n_support + n_query
+        mean = out["mean"].cpu().view(E, C, C, SQ)
+        mean_s = mean[:, :, :, :n_support].reshape(E, C, C * n_support)
+        mean_q = mean[:, :, :, n_support:].reshape(E, C, C * n_query)
+        upd("mon.mean_s", rel_err(mean_s, ref["mean_support"]))
+        upd("mon.mean_q", rel_err(mean_q, ref["mean_query"]))
+        np.testing.assert_allclose(out["acc_support"].cpu().numpy(), ref["acc_support"], atol=1e-4)
+        np.testing.assert_allclose(out["acc_query"].cpu().numpy(), ref["acc_query"], atol=1e-4)
+    mon = {k: worst.pop(k) for k in list(worst) if k.startswith("mon.")}
+    assert all(v <= 2e-2 for v in mon.values()), mon
+    # bar: 1e-4 relative (north_star), or the fp32 reference's own distance to the fp64 truth where the tiny
+    # test batches make BatchNorm's backward ill-conditioned (the device path must be as good as torch fp32)
+    bad = {k: (v, floor.get(k, 0.0)) for k, v in worst.items() if v > max(tol, 3.0 * floor.get(k, 0.0))}
+    assert not bad, "parity above max(%g, 3x fp32-reference envelope): %s" % (tol, bad)
+    return model, oracle, worst
+
+
+def check_correct(model, oracle, dev, image_size=32, n_way=2, n_support=1, n_query=3, tol=1e-4):
+    model_cpu_sync(model, oracle, dev)      # identical weights / running statistics on both sides
+    model.eval()
+    for ep in range(2):
+        x = oep.synthetic_episode(900 + ep, n_way, n_support, n_query, image_size)
+        ref_logits = oracle.get_logits(x)
+        got = model.get_logits(x)
+        assert rel_err(got, ref_logits) <= tol
+        ref_c = oracle.correct(x)
+        got_c = model.correct(x)
+        assert got_c[:2] == ref_c[:2], (got_c, ref_c)
+        assert np.array_equal(got.cpu().numpy().argmax(1), ref_logits.numpy().argmax(1))

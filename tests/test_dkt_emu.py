@@ -1,0 +1,32 @@
+"""End-to-end host-logic test (no GPU): the drop-in DKT module driving the g++-emulated kernels through the
+same engine / flat-buffer / Adam code as on the device, against the CPU oracle.  Test infrastructure only:
+the product refuses CPU tensors unless a test injects the emulation library."""
+import os
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+import build_emu  # noqa: E402
+import dkt_checks  # noqa: E402
+from deep_kernel_transfer_b200 import backbone  # noqa: E402
+from deep_kernel_transfer_b200._lib import DktbLib  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return DktbLib(build_emu.build())
+
+
+def test_train_step_and_correct_match_oracle(lib):
+    model, oracle, worst = dkt_checks.check_train_step(lambda: backbone.ConvNet(4, image_size=32), torch.device("cpu"), lib=lib)
+    print(worst)
+    dkt_checks.check_correct(model, oracle, torch.device("cpu"))
+
+
+def test_product_refuses_cpu_without_library():
+    from deep_kernel_transfer_b200.methods.DKT import DKT
+    m = DKT(backbone.Conv4, 2, 1)
+    with pytest.raises(RuntimeError):
+        m._ensure_packed()
