@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""Benchmark of the DKT meta-train hot path (BASELINE.json metric: episodes/sec, 5-way 5-shot Conv4
+bncossim, synthetic 84x84x3 episodes).
+
+  python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path (one rank per GPU)
+  python bench.py --impl reference ...                   # the reference's CPU path (oracle port), rank 0 only
+
+One "step" = one packed meta-step: every rank runs E episodes (weak scaling, fixed E per GPU) through the
+full reference loop body (DKT.train_loop steps 1-6: train-mode forward over N=105 images, C=5 exact-GP
+marginal likelihoods, backward, Adam, and the eval-mode monitoring forward + predictive means + arg-max),
+followed under torch.distributed by one all-reduce of the flat gradient buffer.  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_WAY, N_SUPPORT, N_QUERY, IMAGE = 5, 5, 16, 84
+WORKLOAD = "5-way 5-shot Conv4 bncossim, synthetic 84x84x3, meta-train step incl. monitoring (DKT.train_loop body)"
+# algorithmic work per training episode: N*(6*M_bb - 2*M_first) + monitoring 2*M_bb*N + GP
+M_BB, M_FIRST = 97164288, 12192768
+
+
+def episode_flops(n=N_WAY * (N_SUPPORT + N_QUERY), d=1600, c=N_WAY, monitor=True):
+    f = n * (6 * M_BB - 2 * M_FIRST) + 4 * n * n * d + c * n ** 3
+    if monitor:
+        f += 2 * M_BB * n
+    return f
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples in timed region"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(n_timed=3, n_warm=1):
+    """The reference's CPU path (oracle port: reference backbone.py semantics + restated GPyTorch math) on the
+    host cores: full train_loop body per episode, E=1 (the reference's own granularity)."""
+    import torch
+    from oracle import episode as oep
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    o = oep.OracleDKT("Conv4", "bncossim", n_way=N_WAY, n_support=N_SUPPORT, seed=0)
+    ts = []
+    for i in range(n_warm + n_timed):
+        x = oep.synthetic_episode(i, N_WAY, N_SUPPORT, N_QUERY, IMAGE)
+        t0 = time.perf_counter()
+        o.train_step(x, monitor=True)
+        dt = time.perf_counter() - t0
+        if i >= n_warm:
+            ts.append(dt)
+    ts.sort()
+    med = ts[len(ts) // 2]
+    return {"value": 1.0 / med, "unit": "episodes/s", "cores": threads, "kind": "port",
+            "sample": "%d warm-up + %d timed single-episode meta-train steps (median), same synthetic episodes"
+                      % (n_warm, n_timed), "s_per_episode": med}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    cb = cpu_baseline(n_timed=steps, n_warm=warm)
+    line = {"metric": "episodes/sec (meta-train)", "value": cb["value"], "unit": "episodes/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": 1000.0 * cb["s_per_episode"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": WORKLOAD, "episodes_per_step": 1, "note":
+                       "reference CPU path = oracle port (GPyTorch is not installable offline; backbone pinned to the "
+                       "reference's backbone.py); each step is one episode, the reference's own granularity"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "episodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--episodes-per-gpu", type=int, default=32)
+    ap.add_argument("--no-monitor", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from deep_kernel_transfer_b200 import _lib, backbone
+    from deep_kernel_transfer_b200.methods.DKT import DKT
+    from oracle import episode as oep      # synthetic-episode generator only (no arithmetic of the product path)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    E = args.episodes_per_gpu
+    W = max(3, args.warmup)
+    K = args.steps
+    torch.manual_seed(0)
+    model = DKT(backbone.Conv4, N_WAY, N_SUPPORT, kernel="bncossim", episodes_per_step=E).to(dev)
+    model.monitor = not args.no_monitor
+    model.train()
+    model._ensure_packed()
+    model._new_adam()
+    # synthetic episodes: a small pool of distinct seeded episodes per rank, tiled to E (content does not
+    # change the work); the pinned host copy feeds the end-to-end leg
+    pool = torch.stack([oep.synthetic_episode(1000 * rank + i, N_WAY, N_SUPPORT, N_QUERY, IMAGE) for i in range(4)])
+    host = pool[torch.arange(E) % 4].contiguous().pin_memory()
+    x_dev = host.to(dev)
+    step_bytes_in = host.numel() * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident leg: inputs already in HBM
+    for _ in range(W):
+        model.train_step(x_dev)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    l0 = lib.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    ev0.record()
+    for _ in range(K):
+        out = model.train_step(x_dev)
+    ev1.record()
+    barrier()
+    t_wall1 = time.time()
+    launches = lib.launches - l0
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    info_bad = int((out["info"] != 0).sum().item())
+    # ---------------- end-to-end leg: pinned host input -> H2D -> step -> D2H of the losses, every step
+    for _ in range(2):
+        model.train_step(host.to(dev, non_blocking=True))["loss"].cpu()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    d2h = 0
+    for _ in range(K):
+        o = model.train_step(host.to(dev, non_blocking=True))
+        res = torch.cat([o["loss"], o["acc_support"], o["acc_query"]] if model.monitor else [o["loss"]]).cpu()
+        d2h = res.numel() * 4
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    # ---------------- roofline of the dominant kernel (64->64 3x3 conv at 42x42), timed live on its stream
+    roof = None
+    if rank == 0:
+        roof = dominant_kernel_roofline(model, lib, dev, E)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    eps = E * world * K / (ms / 1000.0)
+    eps_e2e = E * world * K / (ms_e2e / 1000.0)
+    line = {
+        "metric": "episodes/sec (meta-train)", "value": eps, "unit": "episodes/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_way": N_WAY, "n_shot": N_SUPPORT, "n_query": N_QUERY, "image": IMAGE,
+                   "episodes_per_gpu_per_step": E, "global_episodes_per_step": E * world, "monitor": model.monitor,
+                   "parallelism": "episodes sharded dp%d, one all-reduce of the flat gradient per step" % world,
+                   "l2": "per-step working set (~%.1f GB activations) far exceeds the 126 MB L2" % (E * 0.6)},
+        "gpu_launches": launches,
+        "tflops_algorithmic": eps * episode_flops(monitor=model.monitor) / 1e12,
+        "cholesky_failures": info_bad,
+        "e2e": {"value": eps_e2e, "unit": "episodes/s", "h2d_bytes_per_step": step_bytes_in,
+                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K},
+        "clocks": clocks, "roofline": roof,
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def dominant_kernel_roofline(model, lib, dev, E):
+    """Time the layer-2 convolution forward (64->64, 42x42: 67% of the backbone MACs) alone on its stream."""
+    import torch
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    eng = model.feature._engine
+    ws = eng.ws
+    B = ws["act"][0].shape[0]
+    H = W = eng.layers[1]["H"]
+    st = torch.cuda.current_stream(dev).cuda_stream
+    use_tc = lib.has("dktb_conv3x3_tc_fwd") and getattr(eng, "use_tc", False)
+
+    def launch():
+        if use_tc:
+            eng.tc_fwd(1, B, H, W)
+        else:
+            lib.conv3x3_fwd(ws["act"][0], ws["wt_f"][1], model._P.conv_b[1], ws["y"][1], ws["partials"][1], B, H, W, st)
+
+    for _ in range(3):
+        launch()
+    torch.cuda.synchronize()
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        launch()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flops = 2.0 * B * H * W * 64 * 576
+    achieved = flops / (ms / 1e3) / 1e12
+    if use_tc:
+        peak = peaks.get("bf16_tflops_sustained", 1400.0) / 2.0
+        which = "measured bf16 sustained / 2 (= dense TF32); 3xTF32 error-compensated split issues 3 MMAs per product"
+    else:
+        peak = 75.0
+        which = "nominal fp32 FFMA peak (148 SMs x 128 FMA x ~1.97 GHz); no measured fp32 figure in MEASURED_PEAKS.json"
+    return {"kernel": "conv3x3 64->64 forward, 42x42, B=%d images (%s)" % (B, "tcgen05 3xTF32" if use_tc else "fp32 FFMA"),
+            "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "traffic": None, "ms_per_launch": ms, "peak_source": which,
+            "algorithmic_flops_per_launch": flops}
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,53 @@
+"""Parity tests proper: every kernel through the C ABI on the B200 against torch CPU references."""
+import pytest
+import torch
+
+import kernel_checks as kc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from deep_kernel_transfer_b200 import _lib
+    return _lib.load()
+
+
+DEV = torch.device("cuda", 0) if torch.cuda.is_available() else None
+
+
+def test_conv1(lib):
+    kc.check_conv1(lib, DEV)
+    kc.check_conv1(lib, DEV, B=4, H=84, W=84, seed=3)
+
+
+def test_conv3x3_small(lib):
+    kc.check_conv3x3(lib, DEV)
+    kc.check_conv3x3(lib, DEV, B=2, H=10, W=10, seed=11)
+
+
+def test_conv3x3_layer_shapes(lib):
+    kc.check_conv3x3(lib, DEV, B=5, H=42, W=42, seed=12)
+    kc.check_conv3x3(lib, DEV, B=7, H=21, W=21, seed=13)
+
+
+@pytest.mark.parametrize("pool,in_pad,out_pad,H,W", [(1, 1, 1, 7, 6), (1, 0, 1, 84, 84), (0, 1, 0, 5, 5),
+                                                      (1, 1, 1, 21, 21), (1, 1, 0, 10, 10)])
+def test_bn_relu_pool(lib, pool, in_pad, out_pad, H, W):
+    kc.check_bn_relu_pool(lib, DEV, pool=pool, in_pad=in_pad, out_pad=out_pad, H=H, W=W)
+
+
+def test_head(lib):
+    kc.check_head(lib, DEV)
+    kc.check_head(lib, DEV, E=3, N=105, Cch=64, P=25, seed=8)
+
+
+def test_gp(lib):
+    kc.check_gp(lib, DEV)
+    kc.check_gp(lib, DEV, E=4, C=5, per_class=21, D=1600, M=75, seed=9)     # N = 105 (5-way 5-shot, Q=16)
+    kc.check_gp(lib, DEV, E=2, C=5, per_class=17, D=1600, M=75, seed=10)    # N = 85  (5-way 1-shot)
+    kc.check_gp(lib, DEV, E=2, C=5, per_class=1, D=64, M=75, seed=11)       # N = 5   (1-shot test episode)
+
+
+def test_adam(lib):
+    kc.check_adam(lib, DEV, n=100003)
