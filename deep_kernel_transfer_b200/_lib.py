@@ -26,6 +26,8 @@ SIGNATURES = {
     "dktb_conv3x3_wgrad_nsplit": ("", ctypes.c_int),
     "dktb_conv3x3_wgrad_scratch_floats": ("", ctypes.c_long),
     "dktb_conv3x3_wgrad": ("pppppiiis", ctypes.c_int),
+    "dktb_prep_weights_tc": ("ppps", ctypes.c_int),
+    "dktb_conv3x3_tc_fwd": ("ppppppiiis", ctypes.c_int),
     "dktb_bn_finalize": ("piiiipppppffs", ctypes.c_int),
     "dktb_bn_eval_prepare": ("ppppifs", ctypes.c_int),
     "dktb_bn_relu_pool_fwd": ("ppppppiiiiiiis", ctypes.c_int),

@@ -47,7 +47,7 @@ def build(force=False, verbose=False):
             sys.stdout.write(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcuda"]
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
     subprocess.check_call(cmd)
     return LIB
 

@@ -12,6 +12,7 @@ Data layout in HBM (all fp32):
   gy[i], gact[i]                gradients in the same layouts (gy borders stay zero: dgrad/wgrad read them)
 """
 import math
+import os
 
 import torch
 
@@ -41,11 +42,14 @@ class ConvNetParams:
 class ConvNetEngine:
     """Conv4 / Conv6 (``ConvNet(depth)``) over packed episodes."""
 
-    def __init__(self, lib, depth=4, image_size=84, device="cuda", use_tc=False):
+    def __init__(self, lib, depth=4, image_size=84, device="cuda", use_tc=None):
         self.lib = lib
         self.depth = depth
         self.dev = torch.device(device)
-        self.use_tc = use_tc and lib.has("dktb_conv3x3_tc_fwd")
+        if use_tc is None:
+            use_tc = os.environ.get("DKTB_CONV", "fp32") == "tc"
+        # tcgen05 3xTF32 kernels for the 64->64 convolutions (forward + dgrad); fp32 CUDA-core kernels otherwise
+        self.use_tc = bool(use_tc) and lib.has("dktb_conv3x3_tc_fwd") and self.dev.type == "cuda"
         self.layers = []
         h = image_size
         for i in range(depth):
@@ -88,9 +92,11 @@ class ConvNetEngine:
             ws["partials"].append(torch.empty(B * T * 128, device=dev, dtype=f32))
             ws["mean"].append(torch.empty(E, 64, device=dev, dtype=f32))
             ws["invstd"].append(torch.empty(E, 64, device=dev, dtype=f32))
-            ws["wt_f"].append(torch.empty(9, 64, 64, device=dev, dtype=f32) if i > 0 else None)
-            ws["wt_d"].append(torch.empty(9, 64, 64, device=dev, dtype=f32) if i > 0 else None)
+            shape = (2, 9, 64, 64) if self.use_tc else (9, 64, 64)
+            ws["wt_f"].append(torch.empty(*shape, device=dev, dtype=f32) if i > 0 else None)
+            ws["wt_d"].append(torch.empty(*shape, device=dev, dtype=f32) if i > 0 else None)
             max_part = max(max_part, B * lib.bn_bwd_chunks(H, W, int(L["pool"])) * 128)
+        ws["tc_err"] = torch.zeros(1, device=dev, dtype=torch.int32)
         ws["eval_mean"] = torch.empty(self.depth, 64, device=dev, dtype=f32)
         ws["eval_invstd"] = torch.empty(self.depth, 64, device=dev, dtype=f32)
         ws["bwd_partial"] = torch.empty(max_part, device=dev, dtype=f32)
@@ -108,7 +114,21 @@ class ConvNetEngine:
     def prepare_weights(self, P):
         st = _stream(self.dev)
         for i in range(1, self.depth):
-            self.lib.prep_weights(P.conv_w[i], self.ws["wt_f"][i], self.ws["wt_d"][i], st)
+            if self.use_tc:
+                self.lib.prep_weights_tc(P.conv_w[i], self.ws["wt_f"][i], self.ws["wt_d"][i], st)
+            else:
+                self.lib.prep_weights(P.conv_w[i], self.ws["wt_f"][i], self.ws["wt_d"][i], st)
+
+    def conv64(self, a, wt, bias, out, partials, B, H, W, st):
+        """64->64 3x3 convolution over the padded layout (forward: wt_f + bias + partials; dgrad: wt_d)."""
+        if self.use_tc:
+            self.lib.conv3x3_tc_fwd(a, wt, bias, out, partials, self.ws["tc_err"], B, H, W, st)
+        else:
+            self.lib.conv3x3_fwd(a, wt, bias, out, partials, B, H, W, st)
+
+    def check_tc(self):
+        if self.use_tc and int(self.ws["tc_err"].item()) != 0:
+            raise RuntimeError("tcgen05 convolution pipeline reported a barrier time-out")
 
     def forward(self, x, P, ipe, training, update_running=True):
         """x [B,3,H,W] (device, contiguous).  Returns features [B, D] (NHWC-flattened view of a workspace)."""
@@ -125,7 +145,7 @@ class ConvNetEngine:
             if i == 0:
                 lib.conv1_fwd(x, P.conv_w[0], P.conv_b[0], ws["y"][0], partials, B, H, W, st)
             else:
-                lib.conv3x3_fwd(ws["act"][i - 1], ws["wt_f"][i], P.conv_b[i], ws["y"][i], partials, B, H, W, st)
+                self.conv64(ws["act"][i - 1], ws["wt_f"][i], P.conv_b[i], ws["y"][i], partials, B, H, W, st)
             if training:
                 lib.bn_finalize(partials, B, ws["T"][i], ipe, H * W, ws["mean"][i], ws["invstd"][i],
                                 P.bn_rm[i] if update_running else None, P.bn_rv[i] if update_running else None,
@@ -156,7 +176,7 @@ class ConvNetEngine:
             else:
                 lib.conv3x3_wgrad(ws["act"][i - 1], ws["gy"][i], G.conv_w[i], G.conv_b[i], ws["wgrad_scratch"], B, H,
                                   W, st)
-                lib.conv3x3_fwd(ws["gy"][i], ws["wt_d"][i], None, ws["gact"][i - 1], None, B, H, W, st)
+                self.conv64(ws["gy"][i], ws["wt_d"][i], None, ws["gact"][i - 1], None, B, H, W, st)
                 gout = ws["gact"][i - 1]
 
 

@@ -194,24 +194,35 @@ class DKT(MetaTemplate):
             b.BN.num_batches_tracked += E
         out = {"loss": loss.clone(), "info": head.w["info"]}
         if self.monitor:
-            # 5-6: eval-mode features of the same images; the GP stays conditioned on the pre-update
-            # train-mode features but uses the post-update hyper-parameters (Appendix B.4)
-            feats_e = eng.forward(x_all, self._P, ipe=N, training=False)
-            zh_e = head.embed(feats_e, self._HP, E, N, training=False, out=head.w["zh"])
-            head.fit(head.w["zh_train"], targets, self._HP, E, N, want_grad=False)
-            if "mon_mean" not in head.w or head.w["mon_mean"].shape != (E, C, N):
-                head.w["mon_mean"] = torch.empty(E, C, N, device=dev)
-                head.w["mon_pred"] = torch.empty(E, N, device=dev, dtype=torch.int32)
-                head.w["mon_kx"] = torch.empty(E, N, N, device=dev)
-            head.predict(zh_e, head.w["zh_train"], self._HP, E, N, N, head.w["mon_mean"], head.w["mon_pred"],
-                         head.w["mon_kx"])
-            labels = torch.arange(C, device=dev, dtype=torch.int32).repeat_interleave(SQ)
-            hit = (head.w["mon_pred"] == labels.unsqueeze(0)).view(E, C, SQ)
-            out["acc_support"] = hit[:, :, :self.n_support].float().mean((1, 2)) * 100.0
-            out["acc_query"] = hit[:, :, self.n_support:].float().mean((1, 2)) * 100.0
-            out["mean"] = head.w["mon_mean"]
+            out.update(self.monitor_step(x_dev))
         self.last_step = out
         return out
+
+    def monitor_step(self, x_dev):
+        """Steps 5-6 of the loop body (DKT.py:170-193): eval-mode features of the same images; the GP stays
+        conditioned on the pre-update train-mode features kept by ``train_step`` but uses the post-update
+        hyper-parameters (Appendix B.4).  Returns per-episode support / query accuracies and the means."""
+        E, C, SQ = x_dev.shape[0], x_dev.shape[1], x_dev.shape[2]
+        N = C * SQ
+        dev = x_dev.device
+        x_all = x_dev.reshape(E * N, *x_dev.shape[3:])
+        eng = self.feature.engine(x_dev.shape[-1], dev, self.lib)
+        head = self._get_head(eng)
+        targets = make_targets(C, SQ, dev)
+        feats_e = eng.forward(x_all, self._P, ipe=N, training=False)
+        zh_e = head.embed(feats_e, self._HP, E, N, training=False, out=head.w["zh"])
+        head.fit(head.w["zh_train"], targets, self._HP, E, N, want_grad=False)
+        if "mon_mean" not in head.w or head.w["mon_mean"].shape != (E, C, N):
+            head.w["mon_mean"] = torch.empty(E, C, N, device=dev)
+            head.w["mon_pred"] = torch.empty(E, N, device=dev, dtype=torch.int32)
+            head.w["mon_kx"] = torch.empty(E, N, N, device=dev)
+        head.predict(zh_e, head.w["zh_train"], self._HP, E, N, N, head.w["mon_mean"], head.w["mon_pred"],
+                     head.w["mon_kx"])
+        labels = torch.arange(C, device=dev, dtype=torch.int32).repeat_interleave(SQ)
+        hit = (head.w["mon_pred"] == labels.unsqueeze(0)).view(E, C, SQ)
+        return {"acc_support": hit[:, :, :self.n_support].float().mean((1, 2)) * 100.0,
+                "acc_query": hit[:, :, self.n_support:].float().mean((1, 2)) * 100.0,
+                "mean": head.w["mon_mean"], "pred": head.w["mon_pred"]}
 
     # ------------------------------------------------------------------ reference API
     def train_loop(self, epoch, train_loader, optimizer=None, print_freq=10):

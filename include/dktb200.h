@@ -51,6 +51,14 @@ long dktb_conv3x3_wgrad_scratch_floats(void);
 int dktb_conv3x3_wgrad(const float* a, const float* gy, float* dw, float* db, float* scratch, int B, int H, int W,
                        cudaStream_t stream);
 
+/* tcgen05 + TMA version of the 64->64 convolution (forward and dgrad), fp32-class accuracy via an error-compensated
+ * 3xTF32 split.  wb = [2][9][64][64] hi/lo weight tensor written by dktb_prep_weights_tc ([hl][tap][n][k]; wb_dgrad has
+ * the taps flipped and n/k swapped).  err: device int, zero-initialised by the caller, set to 1 when a pipeline
+ * barrier wait timed out (a bug guard: results are then invalid).  Same layouts/partials as dktb_conv3x3_fwd. */
+int dktb_prep_weights_tc(const float* w, float* wb_fwd, float* wb_dgrad, cudaStream_t stream);
+int dktb_conv3x3_tc_fwd(const float* a, const float* wb, const float* bias, float* out, float* partials, int* err,
+                        int B, int H, int W, cudaStream_t stream);
+
 /* BatchNorm2d statistics (train: per-episode batch stats from the conv partial sums + running-stat EMA,
  * momentum 0.1, unbiased running variance; eval: running stats).  scratch_d: (B/ipe)*128 doubles. */
 int dktb_bn_finalize(const float* partials, int B, int T, int ipe, int hw, float* mean, float* invstd,

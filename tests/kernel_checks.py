@@ -263,3 +263,35 @@ def check_adam(lib, dev, n=1000, seed=5):
         opt.step()
         lib.adam_step(pd, gr.to(dev), m, v, n, 1e-3, 0.9, 0.999, 1e-8, step, 1.0, 0)
     _close(pd, pr.detach(), rtol=1e-6, atol=1e-7, what="adam")
+
+
+def check_conv3x3_tc(lib, dev, B=3, H=6, W=5, seed=21, rtol=2e-5):
+    """tcgen05 3xTF32 forward / dgrad kernel against fp64 convolution (fp32-class accuracy expected)."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, 64, H, W, generator=g)
+    w = torch.randn(64, 64, 3, 3, generator=g) * 0.05
+    b = torch.randn(64, generator=g)
+    gy = torch.randn(B, 64, H, W, generator=g)
+    xr = x.double().requires_grad_(True)
+    ref = F.conv2d(xr, w.double(), b.double(), padding=1)
+    (ref * gy.double()).sum().backward()
+    wb_f = torch.empty(2, 9, 64, 64, device=dev)
+    wb_d = torch.empty(2, 9, 64, 64, device=dev)
+    lib.prep_weights_tc(w.to(dev), wb_f, wb_d, 0)
+    err = torch.zeros(1, device=dev, dtype=torch.int32)
+    a = to_padded_nhwc(x).to(dev)
+    T = lib.conv3x3_tiles(H, W)
+    y = torch.full((B, H + 2, W + 2, 64), float("nan"), device=dev)
+    part = torch.zeros(B * T * 128, device=dev)
+    lib.conv3x3_tc_fwd(a, wb_f, b.to(dev), y, part, err, B, H, W, 0)
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0, "pipeline time-out"
+    _close(from_padded_nhwc(y.cpu()), ref.detach(), rtol=rtol, atol=1e-6, what="tc conv fwd")
+    p = part.cpu().view(B, T, 2, 64).sum(1)
+    _close(p[:, 0], ref.detach().sum((2, 3)), rtol=1e-4, atol=1e-3, what="tc conv sum")
+    _close(p[:, 1], (ref.detach() ** 2).sum((2, 3)), rtol=1e-4, atol=1e-3, what="tc conv sumsq")
+    gx = torch.full((B, H + 2, W + 2, 64), float("nan"), device=dev)
+    lib.conv3x3_tc_fwd(to_padded_nhwc(gy).to(dev), wb_d, None, gx, None, err, B, H, W, 0)
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0, "pipeline time-out"
+    _close(from_padded_nhwc(gx.cpu()), xr.grad, rtol=rtol, atol=1e-6, what="tc conv dgrad")

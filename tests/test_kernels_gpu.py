@@ -51,3 +51,11 @@ def test_gp(lib):
 
 def test_adam(lib):
     kc.check_adam(lib, DEV, n=100003)
+
+
+def test_conv3x3_tc(lib):
+    """tcgen05 + TMA 3xTF32 convolution (forward and dgrad) at small and at the real layer shapes."""
+    kc.check_conv3x3_tc(lib, DEV)
+    kc.check_conv3x3_tc(lib, DEV, B=2, H=10, W=10, seed=22)
+    kc.check_conv3x3_tc(lib, DEV, B=4, H=42, W=42, seed=23)
+    kc.check_conv3x3_tc(lib, DEV, B=5, H=21, W=21, seed=24)
