@@ -205,8 +205,8 @@ def check_gp(lib, dev, E=3, C=3, per_class=4, D=24, M=9, seed=4, rtol=2e-4):
     for c in range(C):
         targets[c, c * per_class:(c + 1) * per_class] = 1.0
     p = ogp.default_gp_params("bncossim", C, D)
-    p["raw_outputscale"] = torch.tensor([0.3, -0.4, 0.9][:C])
-    p["constant"] = torch.tensor([0.05, -0.1, 0.2][:C])
+    p["raw_outputscale"] = torch.linspace(-0.4, 0.9, C)
+    p["constant"] = torch.linspace(-0.1, 0.2, C)
     zr = z.clone().requires_grad_(True)
     p["raw_outputscale"].requires_grad_(True)
     p["constant"].requires_grad_(True)
