@@ -28,6 +28,9 @@ SIGNATURES = {
     "dktb_conv3x3_wgrad": ("pppppiiis", ctypes.c_int),
     "dktb_prep_weights_tc": ("ppps", ctypes.c_int),
     "dktb_conv3x3_tc_fwd": ("ppppppiiis", ctypes.c_int),
+    "dktb_conv3x3_tc2_fwd": ("ppppppiiis", ctypes.c_int),
+    "dktb_conv3x3_wgrad_tc": ("ppppppiiis", ctypes.c_int),
+    "dktb_conv3x3_wgrad_reduce": ("pipps", ctypes.c_int),
     "dktb_bn_finalize": ("piiiipppppffs", ctypes.c_int),
     "dktb_bn_eval_prepare": ("ppppifs", ctypes.c_int),
     "dktb_bn_relu_pool_fwd": ("ppppppiiiiiiis", ctypes.c_int),

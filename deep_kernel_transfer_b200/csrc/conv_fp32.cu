@@ -458,6 +458,14 @@ __global__ void conv3x3_wgrad_reduce_kernel(const float* __restrict__ partial, i
   }
 }
 
+DKTB_EXPORT int dktb_conv3x3_wgrad_reduce(const float* partial, int nsplit, float* dw, float* db,
+                                          cudaStream_t stream) {
+  DKTB_CHECK_ARG(partial && dw && nsplit > 0);
+  DKTB_LAUNCH(conv3x3_wgrad_reduce_kernel, dim3((WG_PSTRIDE + 255) / 256), dim3(256), 0, stream, partial, nsplit, dw,
+              db);
+  return dktb_launch_status();
+}
+
 DKTB_EXPORT int dktb_conv3x3_wgrad_nsplit(void) { return 296; }
 DKTB_EXPORT long dktb_conv3x3_wgrad_scratch_floats(void) { return (long)296 * WG_PSTRIDE; }
 

@@ -121,7 +121,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const float4 v = *pa;
         float4 hi, lo;
         hi.x = tc::to_tf32_rna(v.x); hi.y = tc::to_tf32_rna(v.y); hi.z = tc::to_tf32_rna(v.z); hi.w = tc::to_tf32_rna(v.w);
-        lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+        lo.x = tc::to_tf32_rna(v.x - hi.x); lo.y = tc::to_tf32_rna(v.y - hi.y);
+        lo.z = tc::to_tf32_rna(v.z - hi.z); lo.w = tc::to_tf32_rna(v.w - hi.w);
         *pa = hi;
         *pl = lo;
       }
@@ -179,6 +180,383 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   if (warp == 1) tc::tmem_dealloc<64>(d_tmem);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// v2: A operand from TMEM.  The activation halo of the tile (128 + 2*(Wp+1) padded-flat rows x 64 channels) is loaded
+// ONCE by TMA (two SWIZZLE_128B channel halves); for every (tap, half) the 128 stager threads read their own shifted
+// row from the halo (conflict-free thanks to the swizzle), split it into tf32 hi / exact lo in registers and write
+// both straight into TMEM (tcgen05.st, lane = output pixel, column = input channel).  tcgen05.mma then takes A from
+// TMEM and only the 2 KB weight slice from shared memory, so the tensor pipe is no longer starved by the 4 KB/MMA
+// A re-read that bounds the SS version at N = 64.  Weights stream through a 3-stage TMA ring (hi + lo, 16 KB/stage).
+// TMEM: 256 columns = accumulator [0,64) + two A stages of {hi 32 | lo 32} columns.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kHaloBox = 32;                  // rows per halo TMA box
+constexpr int kWStages = 3;
+constexpr int kWStageBytes = 16384;           // W hi 8K | W lo 8K for one (tap, half)
+
+__global__ void __launch_bounds__(192, 2)
+conv3x3_tc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                     const float* __restrict__ bias, float* __restrict__ out, float* __restrict__ partials, int B, int H,
+                     int W, int halo_rows_pad, int* __restrict__ err) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar_halo, bar_wfull[kWStages], bar_wempty[kWStages], bar_afull[2], bar_aempty[2], bar_acc;
+  __shared__ uint32_t s_tmem;
+  __shared__ int s_err;
+  __shared__ float s_valid[kRows];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Hp = H + 2, Wp = W + 2;
+  const int img = blockIdx.y;
+  const int q0 = (Wp + 1) + blockIdx.x * kRows;
+  const long img_base = (long)img * Hp * Wp;
+  const int half_bytes = halo_rows_pad * 128;
+  unsigned char* s_halo = smem;                               // [2][halo_rows_pad][128 B]
+  unsigned char* s_w = smem + 2 * half_bytes;                 // [kWStages][16 KB]
+
+  if (tid == 0) {
+    tc::mbar_init(&bar_halo, 1);
+    for (int s = 0; s < kWStages; ++s) { tc::mbar_init(&bar_wfull[s], 1); tc::mbar_init(&bar_wempty[s], 1); }
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(&bar_afull[s], 128); tc::mbar_init(&bar_aempty[s], 1); }
+    tc::mbar_init(&bar_acc, 1);
+    s_err = 0;
+    tc::fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { tc::prefetch_tmap(&map_a); tc::prefetch_tmap(&map_w); }
+  if (warp == 1) tc::tmem_alloc<256>(&s_tmem);
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t d_tmem = s_tmem;
+  const uint32_t a_tmem = s_tmem + 64;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // halo: rows q0-(Wp+1) .. +halo_rows_pad, both channel halves
+      tc::mbar_expect_tx(&bar_halo, 2 * half_bytes);
+      const int row0 = (int)(img_base + q0 - (Wp + 1));
+      for (int h = 0; h < 2; ++h)
+        for (int r = 0; r < halo_rows_pad; r += kHaloBox)
+          tc::tma_load_2d(s_halo + h * half_bytes + r * 128, &map_a, &bar_halo, h * 32, row0 + r);
+      for (int it = 0; it < kIters; ++it) {
+        const int s = it % kWStages, ph = (it / kWStages) & 1;
+        const int tap = it >> 1, half = it & 1;
+        if (!tc::mbar_wait(&bar_wempty[s], ph ^ 1)) { s_err = 1; break; }
+        tc::mbar_expect_tx(&bar_wfull[s], kWStageBytes);
+        tc::tma_load_2d(s_w + s * kWStageBytes, &map_w, &bar_wfull[s], half * 32, tap * 64);
+        tc::tma_load_2d(s_w + s * kWStageBytes + 8192, &map_w, &bar_wfull[s], half * 32, (9 + tap) * 64);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = tc::umma_idesc(2, 128, 64, 0, 0);
+      bool ok = true;
+      for (int it = 0; it < kIters && ok; ++it) {
+        const int sw = it % kWStages, pw = (it / kWStages) & 1;
+        const int sa = it & 1, pa = (it >> 1) & 1;
+        ok = tc::mbar_wait(&bar_wfull[sw], pw) && tc::mbar_wait(&bar_afull[sa], pa);
+        if (!ok) break;
+        tc::tcgen05_fence_after();
+        const uint32_t wbase = tc::smem_u32(s_w + sw * kWStageBytes);
+        const uint32_t acol = a_tmem + sa * 64;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t w_hi = tc::umma_desc_sw128(wbase + k * 32, 16, 1024);
+          const uint64_t w_lo = tc::umma_desc_sw128(wbase + 8192 + k * 32, 16, 1024);
+          tc::umma_tf32_ts(d_tmem, acol + 32 + k * 8, w_hi, idesc, (it | k) ? 1u : 0u);   // a_lo * w_hi
+          tc::umma_tf32_ts(d_tmem, acol + k * 8, w_lo, idesc, 1u);                         // a_hi * w_lo
+          tc::umma_tf32_ts(d_tmem, acol + k * 8, w_hi, idesc, 1u);                         // a_hi * w_hi
+        }
+        tc::umma_commit(&bar_aempty[sa]);
+        tc::umma_commit(&bar_wempty[sw]);
+      }
+      if (!ok) s_err = 1;
+      tc::umma_commit(&bar_acc);
+    }
+  } else {
+    const int ct = tid - 64;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;                       // accumulator row / TMEM lane of this thread
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    bool ok = tc::mbar_wait(&bar_halo, 0);
+    for (int it = 0; it < kIters && ok; ++it) {
+      const int sa = it & 1, pa = (it >> 1) & 1;
+      const int tap = it >> 1, half = it & 1;
+      ok = tc::mbar_wait(&bar_aempty[sa], pa ^ 1);
+      if (!ok) break;
+      tc::tcgen05_fence_after();
+      const int row = r + (tap / 3) * Wp + (tap % 3);
+      const unsigned char* src = s_halo + half * half_bytes + row * 128;
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 v = *reinterpret_cast<const float4*>(src + ((j ^ (row & 7)) << 4));
+        const float h0 = tc::to_tf32_rna(v.x), h1 = tc::to_tf32_rna(v.y), h2 = tc::to_tf32_rna(v.z), h3 = tc::to_tf32_rna(v.w);
+        hi[4 * j + 0] = __float_as_uint(h0); hi[4 * j + 1] = __float_as_uint(h1);
+        hi[4 * j + 2] = __float_as_uint(h2); hi[4 * j + 3] = __float_as_uint(h3);
+        lo[4 * j + 0] = __float_as_uint(tc::to_tf32_rna(v.x - h0)); lo[4 * j + 1] = __float_as_uint(tc::to_tf32_rna(v.y - h1));
+        lo[4 * j + 2] = __float_as_uint(tc::to_tf32_rna(v.z - h2)); lo[4 * j + 3] = __float_as_uint(tc::to_tf32_rna(v.w - h3));
+      }
+      const uint32_t dst = a_tmem + sa * 64 + lane_base;
+      tc::tmem_st16(dst, hi);
+      tc::tmem_st16(dst + 16, hi + 16);
+      tc::tmem_st16(dst + 32, lo);
+      tc::tmem_st16(dst + 48, lo + 16);
+      tc::tmem_st_wait();
+      tc::tcgen05_fence_before();
+      tc::mbar_arrive(&bar_afull[sa]);
+    }
+    if (!ok) s_err = 1;
+    ok = ok && tc::mbar_wait(&bar_acc, 0);
+    tc::tcgen05_fence_after();
+    float* s_out = reinterpret_cast<float*>(smem);          // [128][kOutLd] over the (now idle) halo
+    const int q = q0 + r;
+    const int hp = q / Wp, wp = q - hp * Wp;
+    const bool valid = ok && q < Hp * Wp && hp >= 1 && hp <= H && wp >= 1 && wp <= W;
+    s_valid[r] = valid ? 1.f : 0.f;
+    if (ok) {
+#pragma unroll
+      for (int c = 0; c < 64; c += 16) {
+        uint32_t v[16];
+        tc::tmem_ld16(d_tmem + lane_base + c, v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float b = bias ? bias[c + j] : 0.f;
+          s_out[r * kOutLd + c + j] = __uint_as_float(v[j]) + b;
+        }
+      }
+    }
+    tc::tcgen05_fence_before();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int idx = ct; idx < kRows * 16; idx += 128) {
+      const int rr = idx >> 4, c4 = (idx & 15) * 4;
+      if (s_valid[rr] != 0.f) {
+        const float* src = s_out + rr * kOutLd + c4;
+        dktb_st4(out + (img_base + q0 + rr) * 64 + c4, make_float4(src[0], src[1], src[2], src[3]));
+      }
+    }
+    if (partials != nullptr) {
+      const int which = ct >> 6, c = ct & 63;
+      float t = 0.f;
+      for (int rr = 0; rr < kRows; ++rr) {
+        const float v = s_out[rr * kOutLd + c] * s_valid[rr];
+        t += which ? v * v : v;
+      }
+      const long blk = (long)img * gridDim.x + blockIdx.x;
+      partials[(blk * 2 + which) * 64 + c] = t;
+    }
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (tid == 0 && s_err) atomicExch(err, 1);
+  if (warp == 1) tc::tmem_dealloc<256>(d_tmem);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// wgrad on tcgen05:  dW[tap][ci][co] = sum_q X[q + off(tap)][ci] * G[q][co]  over ALL padded-flat rows (both operands
+// have zero borders, so images concatenate seamlessly).  GEMM view: M = 128 = 2 taps x 64 ci, N = 64 co, K = rows.
+// Both operands are "MN-major" in HBM (channels contiguous), which tcgen05 only supports for 32-bit data through a
+// dedicated swizzle mode; instead the stager threads transpose on the fly:
+//   A = X^T goes to TMEM (lane = (tap-in-pair, ci), column = row), 3xTF32-split in registers, read straight from the
+//       TMA-loaded halo [rows][64 ch] (one scalar LDS per element, conflict-free: a warp reads 32 consecutive channels);
+//   B = G is re-laid-out K-major ([co][32 rows], SWIZZLE_128B pattern written by hand) as hi / lo tiles in smem.
+// Each persistent CTA owns a strided set of 32-row K-blocks and keeps all five 128x64 fp32 accumulators
+// (taps {0,1},{2,3},{4,5},{6,7},{8,-}) in TMEM (320 columns) + three A stages (3 x 64 columns); the partial dW of
+// every CTA is written once and reduced by dktb_conv3x3_wgrad_reduce in a fixed order (deterministic).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kKR = 32;                         // rows per K-block
+constexpr int kWgAStages = 3;
+
+__global__ void __launch_bounds__(192, 1)
+conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g,
+                        float* __restrict__ partial, long total_rows, int Wp, int halo_pad, int pstride,
+                        int* __restrict__ err) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar_raw_full[2], bar_raw_empty[2], bar_bfull[2], bar_afull[kWgAStages], bar_aempty[kWgAStages],
+      bar_acc;
+  __shared__ uint32_t s_tmem;
+  __shared__ int s_err;
+  __shared__ float s_bias[2][64];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int x_half_bytes = halo_pad * 128;
+  const int stage_bytes = 2 * x_half_bytes + 8192 + 16384;   // X raw | G raw | B hi | B lo
+  const long nkb = (total_rows + kKR - 1) / kKR;
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&bar_raw_full[s], 1);
+      tc::mbar_init(&bar_raw_empty[s], 129);      // 128 stagers done reading + 1 tcgen05.commit (B consumed)
+      tc::mbar_init(&bar_bfull[s], 128);
+    }
+    for (int s = 0; s < kWgAStages; ++s) { tc::mbar_init(&bar_afull[s], 128); tc::mbar_init(&bar_aempty[s], 1); }
+    tc::mbar_init(&bar_acc, 1);
+    s_err = 0;
+    tc::fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { tc::prefetch_tmap(&map_x); tc::prefetch_tmap(&map_g); }
+  if (warp == 1) tc::tmem_alloc<512>(&s_tmem);
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem = s_tmem;
+  const uint32_t a_tmem = tmem + 320;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int n = 0;
+      for (long kb = blockIdx.x; kb < nkb; kb += gridDim.x, ++n) {
+        const int s = n & 1, ph = (n >> 1) & 1;
+        if (!tc::mbar_wait(&bar_raw_empty[s], ph ^ 1)) { s_err = 1; break; }
+        unsigned char* st = smem + s * stage_bytes;
+        tc::mbar_expect_tx(&bar_raw_full[s], 2 * x_half_bytes + 8192);
+        const long q0 = kb * kKR;
+        const int xrow0 = (int)(q0 - (Wp + 1));
+        for (int h = 0; h < 2; ++h) {
+          for (int r = 0; r < halo_pad; r += kHaloBox)
+            tc::tma_load_2d(st + h * x_half_bytes + r * 128, &map_x, &bar_raw_full[s], h * 32, xrow0 + r);
+          tc::tma_load_2d(st + 2 * x_half_bytes + h * 4096, &map_g, &bar_raw_full[s], h * 32, (int)q0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = tc::umma_idesc(2, 128, 64, 0, 0);
+      bool ok = true;
+      int n = 0, ai = 0;
+      for (long kb = blockIdx.x; kb < nkb && ok; kb += gridDim.x, ++n) {
+        const int s = n & 1, ph = (n >> 1) & 1;
+        ok = tc::mbar_wait(&bar_bfull[s], ph);
+        if (!ok) break;
+        const uint32_t bbase = tc::smem_u32(smem + s * stage_bytes + 2 * x_half_bytes + 8192);
+        for (int g = 0; g < 5 && ok; ++g, ++ai) {
+          const int sa = ai % kWgAStages, pa = (ai / kWgAStages) & 1;
+          ok = tc::mbar_wait(&bar_afull[sa], pa);
+          if (!ok) break;
+          tc::tcgen05_fence_after();
+          const uint32_t acol = a_tmem + sa * 64;
+          const uint32_t dcol = tmem + g * 64;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t b_hi = tc::umma_desc_sw128(bbase + k * 32, 16, 1024);
+            const uint64_t b_lo = tc::umma_desc_sw128(bbase + 8192 + k * 32, 16, 1024);
+            tc::umma_tf32_ts(dcol, acol + 32 + k * 8, b_hi, idesc, (n | k) ? 1u : 0u);
+            tc::umma_tf32_ts(dcol, acol + k * 8, b_lo, idesc, 1u);
+            tc::umma_tf32_ts(dcol, acol + k * 8, b_hi, idesc, 1u);
+          }
+          tc::umma_commit(&bar_aempty[sa]);
+        }
+        tc::umma_commit(&bar_raw_empty[s]);
+      }
+      if (!ok) s_err = 1;
+      tc::umma_commit(&bar_acc);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int L = quarter * 32 + lane;                       // TMEM lane: (tap-in-pair, ci)
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const int ci = L & 63, tsel = L >> 6;
+    const int co = L & 63, khalf = L >> 6;                    // roles for the G transpose
+    float bias_acc = 0.f;
+    bool ok = true;
+    int n = 0, ai = 0;
+    for (long kb = blockIdx.x; kb < nkb && ok; kb += gridDim.x, ++n) {
+      const int s = n & 1, ph = (n >> 1) & 1;
+      ok = tc::mbar_wait(&bar_raw_full[s], ph);
+      if (!ok) break;
+      unsigned char* st = smem + s * stage_bytes;
+      // ---- B: G[k][co] -> K-major [co][k] hi / lo (16 k values per thread)
+      {
+        const unsigned char* graw = st + 2 * x_half_bytes + (co >> 5) * 4096;
+        unsigned char* bhi = st + 2 * x_half_bytes + 8192 + co * 128;
+        unsigned char* blo = bhi + 8192;
+        const int cq = (co & 31) >> 2, cr = co & 3;
+#pragma unroll
+        for (int kq = 0; kq < 4; ++kq) {
+          float h[4], l[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = khalf * 16 + kq * 4 + j;
+            const float v = *reinterpret_cast<const float*>(graw + k * 128 + ((cq ^ (k & 7)) << 4) + cr * 4);
+            bias_acc += v;
+            h[j] = tc::to_tf32_rna(v);
+            l[j] = tc::to_tf32_rna(v - h[j]);
+          }
+          const int kchunk = khalf * 4 + kq;                 // 16-byte chunk index along K (4 floats)
+          const int off = (kchunk ^ (co & 7)) << 4;
+          *reinterpret_cast<float4*>(bhi + off) = make_float4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<float4*>(blo + off) = make_float4(l[0], l[1], l[2], l[3]);
+        }
+        tc::fence_proxy_async_smem();
+        tc::mbar_arrive(&bar_bfull[s]);
+      }
+      // ---- A: five tap-pair groups into TMEM
+      for (int g = 0; g < 5 && ok; ++g, ++ai) {
+        const int sa = ai % kWgAStages, pa = (ai / kWgAStages) & 1;
+        ok = tc::mbar_wait(&bar_aempty[sa], pa ^ 1);
+        if (!ok) break;
+        tc::tcgen05_fence_after();
+        const int tap = 2 * g + tsel;
+        uint32_t hi[32], lo[32];
+        if (tap < 9) {
+          const int shift = (tap / 3) * Wp + (tap % 3);
+          const unsigned char* xh = st + (ci >> 5) * x_half_bytes;
+          const int cq = (ci & 31) >> 2, cr = ci & 3;
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const int row = k + shift;
+            const float v = *reinterpret_cast<const float*>(xh + row * 128 + ((cq ^ (row & 7)) << 4) + cr * 4);
+            const float h = tc::to_tf32_rna(v);
+            hi[k] = __float_as_uint(h);
+            lo[k] = __float_as_uint(tc::to_tf32_rna(v - h));
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) { hi[k] = 0u; lo[k] = 0u; }
+        }
+        const uint32_t dst = a_tmem + sa * 64 + lane_base;
+        tc::tmem_st16(dst, hi);
+        tc::tmem_st16(dst + 16, hi + 16);
+        tc::tmem_st16(dst + 32, lo);
+        tc::tmem_st16(dst + 48, lo + 16);
+        tc::tmem_st_wait();
+        tc::tcgen05_fence_before();
+        tc::mbar_arrive(&bar_afull[sa]);
+      }
+      if (ok) tc::mbar_arrive(&bar_raw_empty[s]);             // this thread is done with the raw stage
+    }
+    if (!ok) s_err = 1;
+    ok = ok && tc::mbar_wait(&bar_acc, 0);
+    tc::tcgen05_fence_after();
+    float* out = partial + (long)blockIdx.x * pstride;
+    if (ok) {
+      for (int g = 0; g < 5; ++g) {
+        const int tap = 2 * g + tsel;
+#pragma unroll
+        for (int c = 0; c < 64; c += 16) {
+          uint32_t v[16];
+          tc::tmem_ld16(tmem + g * 64 + lane_base + c, v);
+          tc::tmem_ld_wait();
+          if (tap < 9) {
+            float* o = out + ((long)tap * 64 + ci) * 64 + c;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              dktb_st4(o + j, make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                          __uint_as_float(v[j + 3])));
+          }
+        }
+      }
+    }
+    s_bias[khalf][co] = bias_acc;
+    tc::tcgen05_fence_before();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (khalf == 0) out[9 * 64 * 64 + co] = s_bias[0][co] + s_bias[1][co];
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (tid == 0 && s_err) atomicExch(err, 1);
+  if (warp == 1) tc::tmem_dealloc<512>(tmem);
+}
+
 // w_ref [co][ci][3][3] -> wb_fwd / wb_dgrad [hl][tap][n][k] (hi = rna_tf32, lo = exact remainder)
 __global__ void prep_weights_tc_kernel(const float* __restrict__ w, float* __restrict__ wb_fwd,
                                        float* __restrict__ wb_dgrad) {
@@ -186,7 +564,7 @@ __global__ void prep_weights_tc_kernel(const float* __restrict__ w, float* __res
   if (i >= 64 * 64 * 9) return;
   const int tap = i % 9, ci = (i / 9) % 64, co = i / (9 * 64);
   const float v = w[i];
-  const float hi = tc::to_tf32_rna(v), lo = v - hi;
+  const float hi = tc::to_tf32_rna(v), lo = tc::to_tf32_rna(v - hi);
   if (wb_fwd) {
     wb_fwd[((0 * 9 + tap) * 64 + co) * 64 + ci] = hi;
     wb_fwd[((1 * 9 + tap) * 64 + co) * 64 + ci] = lo;
@@ -225,6 +603,54 @@ DKTB_EXPORT int dktb_conv3x3_tc_fwd(const float* a, const float* wb, const float
   dim3 grid((span + kRows - 1) / kRows, B);
   conv3x3_tc_kernel<<<grid, 192, kSmemBytes, stream>>>(map_a, map_w, bias, out, partials, B, H, W, err);
   return dktb_launch_status();
+}
+
+// v2 (A operand staged in TMEM): same contract as dktb_conv3x3_tc_fwd.
+DKTB_EXPORT int dktb_conv3x3_tc2_fwd(const float* a, const float* wb, const float* bias, float* out, float* partials,
+                                     int* err, int B, int H, int W, cudaStream_t stream) {
+  DKTB_CHECK_ARG(a && wb && out && err && B > 0 && H > 0 && W > 0 && B <= 65535);
+  const int Hp = H + 2, Wp = W + 2;
+  const long rows = (long)B * Hp * Wp;
+  DKTB_CHECK_ARG(rows < 2147483000L);
+  const int halo = kRows + 2 * (Wp + 1);
+  const int halo_pad = (halo + kHaloBox - 1) / kHaloBox * kHaloBox;
+  const int smem = 2 * halo_pad * 128 + kWStages * kWStageBytes + 1024;
+  DKTB_CHECK_ARG(smem <= 227 * 1024 && 2 * halo_pad * 128 >= kRows * kOutLd * 4);
+  CUtensorMap map_a, map_w;
+  if (tc_make_tmap_2d(&map_a, a, 64, (uint64_t)rows, 32, kHaloBox) != 0) return DKTB_BAD_ARG - 1;
+  if (tc_make_tmap_2d(&map_w, wb, 64, 2 * 9 * 64, 32, 64) != 0) return DKTB_BAD_ARG - 1;
+  cudaFuncSetAttribute(conv3x3_tc_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int span = Hp * Wp - 2 * (Wp + 1);
+  dim3 grid((span + kRows - 1) / kRows, B);
+  conv3x3_tc_ts_kernel<<<grid, 192, smem, stream>>>(map_a, map_w, bias, out, partials, B, H, W, halo_pad, err);
+  return dktb_launch_status();
+}
+
+extern "C" int dktb_conv3x3_wgrad_reduce(const float* partial, int nsplit, float* dw, float* db, cudaStream_t stream);
+
+// tcgen05 wgrad: same contract as dktb_conv3x3_wgrad (scratch >= dktb_conv3x3_wgrad_scratch_floats()), plus err.
+DKTB_EXPORT int dktb_conv3x3_wgrad_tc(const float* a, const float* gy, float* dw, float* db, float* scratch, int* err,
+                                      int B, int H, int W, cudaStream_t stream) {
+  DKTB_CHECK_ARG(a && gy && dw && scratch && err && B > 0);
+  const int Hp = H + 2, Wp = W + 2;
+  const long rows = (long)B * Hp * Wp;
+  DKTB_CHECK_ARG(rows < 2147483000L);
+  const int halo = kKR + 2 * (Wp + 1);
+  const int halo_pad = (halo + kHaloBox - 1) / kHaloBox * kHaloBox;
+  const int stage = 2 * halo_pad * 128 + 8192 + 16384;
+  const int smem = 2 * stage + 1024;
+  DKTB_CHECK_ARG(smem <= 227 * 1024);
+  CUtensorMap map_x, map_g;
+  if (tc_make_tmap_2d(&map_x, a, 64, (uint64_t)rows, 32, kHaloBox) != 0) return DKTB_BAD_ARG - 1;
+  if (tc_make_tmap_2d(&map_g, gy, 64, (uint64_t)rows, 32, kKR) != 0) return DKTB_BAD_ARG - 1;
+  cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const long nkb = (rows + kKR - 1) / kKR;
+  const int pstride = 9 * 64 * 64 + 64;
+  const int nsplit = (int)(nkb < 148 ? nkb : 148);
+  conv3x3_wgrad_tc_kernel<<<nsplit, 192, smem, stream>>>(map_x, map_g, scratch, rows, Wp, halo_pad, pstride, err);
+  int rc = dktb_launch_status();
+  if (rc != 0) return rc;
+  return dktb_conv3x3_wgrad_reduce(scratch, nsplit, dw, db, stream);
 }
 
 #endif  // DKTB_EMU

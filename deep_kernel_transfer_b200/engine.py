@@ -46,10 +46,13 @@ class ConvNetEngine:
         self.lib = lib
         self.depth = depth
         self.dev = torch.device(device)
+        mode = os.environ.get("DKTB_CONV", "fp32")
         if use_tc is None:
-            use_tc = os.environ.get("DKTB_CONV", "fp32") == "tc"
+            use_tc = mode in ("tc", "tc2")
         # tcgen05 3xTF32 kernels for the 64->64 convolutions (forward + dgrad); fp32 CUDA-core kernels otherwise
         self.use_tc = bool(use_tc) and lib.has("dktb_conv3x3_tc_fwd") and self.dev.type == "cuda"
+        self.tc_fn = "conv3x3_tc_fwd" if mode == "tc" else "conv3x3_tc2_fwd"
+        self.wgrad_tc = os.environ.get("DKTB_WGRAD", "tc") == "tc" and lib.has("dktb_conv3x3_wgrad_tc")
         self.layers = []
         h = image_size
         for i in range(depth):
@@ -122,7 +125,7 @@ class ConvNetEngine:
     def conv64(self, a, wt, bias, out, partials, B, H, W, st):
         """64->64 3x3 convolution over the padded layout (forward: wt_f + bias + partials; dgrad: wt_d)."""
         if self.use_tc:
-            self.lib.conv3x3_tc_fwd(a, wt, bias, out, partials, self.ws["tc_err"], B, H, W, st)
+            getattr(self.lib, self.tc_fn)(a, wt, bias, out, partials, self.ws["tc_err"], B, H, W, st)
         else:
             self.lib.conv3x3_fwd(a, wt, bias, out, partials, B, H, W, st)
 
@@ -174,8 +177,12 @@ class ConvNetEngine:
             if i == 0:
                 lib.conv1_wgrad(x, ws["gy"][0], G.conv_w[0], G.conv_b[0], ws["wgrad_scratch"], B, H, W, st)
             else:
-                lib.conv3x3_wgrad(ws["act"][i - 1], ws["gy"][i], G.conv_w[i], G.conv_b[i], ws["wgrad_scratch"], B, H,
-                                  W, st)
+                if self.use_tc and self.wgrad_tc:
+                    lib.conv3x3_wgrad_tc(ws["act"][i - 1], ws["gy"][i], G.conv_w[i], G.conv_b[i], ws["wgrad_scratch"],
+                                         ws["tc_err"], B, H, W, st)
+                else:
+                    lib.conv3x3_wgrad(ws["act"][i - 1], ws["gy"][i], G.conv_w[i], G.conv_b[i], ws["wgrad_scratch"], B,
+                                      H, W, st)
                 self.conv64(ws["gy"][i], ws["wt_d"][i], None, ws["gact"][i - 1], None, B, H, W, st)
                 gout = ws["gact"][i - 1]
 

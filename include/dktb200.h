@@ -58,6 +58,16 @@ int dktb_conv3x3_wgrad(const float* a, const float* gy, float* dw, float* db, fl
 int dktb_prep_weights_tc(const float* w, float* wb_fwd, float* wb_dgrad, cudaStream_t stream);
 int dktb_conv3x3_tc_fwd(const float* a, const float* wb, const float* bias, float* out, float* partials, int* err,
                         int B, int H, int W, cudaStream_t stream);
+/* v2 of the same kernel: activation halo loaded once per tile, A operand split in registers and staged in TMEM. */
+int dktb_conv3x3_tc2_fwd(const float* a, const float* wb, const float* bias, float* out, float* partials, int* err,
+                         int B, int H, int W, cudaStream_t stream);
+
+/* tcgen05 wgrad (A = X^T staged in TMEM, B = gy re-laid-out K-major in smem, 3xTF32); same contract as
+ * dktb_conv3x3_wgrad plus the err flag.  dktb_conv3x3_wgrad_reduce: fixed-order reduction of per-CTA partials
+ * [nsplit][9*64*64 + 64] into dw [64,64,3,3] / db [64]. */
+int dktb_conv3x3_wgrad_tc(const float* a, const float* gy, float* dw, float* db, float* scratch, int* err, int B, int H,
+                          int W, cudaStream_t stream);
+int dktb_conv3x3_wgrad_reduce(const float* partial, int nsplit, float* dw, float* db, cudaStream_t stream);
 
 /* BatchNorm2d statistics (train: per-episode batch stats from the conv partial sums + running-stat EMA,
  * momentum 0.1, unbiased running variance; eval: running stats).  scratch_d: (B/ipe)*128 doubles. */

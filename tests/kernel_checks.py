@@ -265,7 +265,7 @@ def check_adam(lib, dev, n=1000, seed=5):
     _close(pd, pr.detach(), rtol=1e-6, atol=1e-7, what="adam")
 
 
-def check_conv3x3_tc(lib, dev, B=3, H=6, W=5, seed=21, rtol=2e-5):
+def check_conv3x3_tc(lib, dev, B=3, H=6, W=5, seed=21, rtol=2e-5, fn="conv3x3_tc_fwd"):
     """tcgen05 3xTF32 forward / dgrad kernel against fp64 convolution (fp32-class accuracy expected)."""
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(B, 64, H, W, generator=g)
@@ -283,7 +283,7 @@ def check_conv3x3_tc(lib, dev, B=3, H=6, W=5, seed=21, rtol=2e-5):
     T = lib.conv3x3_tiles(H, W)
     y = torch.full((B, H + 2, W + 2, 64), float("nan"), device=dev)
     part = torch.zeros(B * T * 128, device=dev)
-    lib.conv3x3_tc_fwd(a, wb_f, b.to(dev), y, part, err, B, H, W, 0)
+    getattr(lib, fn)(a, wb_f, b.to(dev), y, part, err, B, H, W, 0)
     torch.cuda.synchronize()
     assert int(err.item()) == 0, "pipeline time-out"
     _close(from_padded_nhwc(y.cpu()), ref.detach(), rtol=rtol, atol=1e-6, what="tc conv fwd")
@@ -291,7 +291,26 @@ def check_conv3x3_tc(lib, dev, B=3, H=6, W=5, seed=21, rtol=2e-5):
     _close(p[:, 0], ref.detach().sum((2, 3)), rtol=1e-4, atol=1e-3, what="tc conv sum")
     _close(p[:, 1], (ref.detach() ** 2).sum((2, 3)), rtol=1e-4, atol=1e-3, what="tc conv sumsq")
     gx = torch.full((B, H + 2, W + 2, 64), float("nan"), device=dev)
-    lib.conv3x3_tc_fwd(to_padded_nhwc(gy).to(dev), wb_d, None, gx, None, err, B, H, W, 0)
+    getattr(lib, fn)(to_padded_nhwc(gy).to(dev), wb_d, None, gx, None, err, B, H, W, 0)
     torch.cuda.synchronize()
     assert int(err.item()) == 0, "pipeline time-out"
     _close(from_padded_nhwc(gx.cpu()), xr.grad, rtol=rtol, atol=1e-6, what="tc conv dgrad")
+
+
+def check_conv3x3_wgrad_tc(lib, dev, B=3, H=6, W=5, seed=31, rtol=2e-5):
+    """tcgen05 wgrad (A = X^T staged in TMEM, B = gy transposed in smem) against fp64 autograd."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, 64, H, W, generator=g)
+    gy = torch.randn(B, 64, H, W, generator=g)
+    wr = (torch.randn(64, 64, 3, 3, generator=g) * 0.05).double().requires_grad_(True)
+    br = torch.zeros(64, dtype=torch.float64, requires_grad=True)
+    (F.conv2d(x.double(), wr, br, padding=1) * gy.double()).sum().backward()
+    dw = torch.full((64, 64, 3, 3), float("nan"), device=dev)
+    db = torch.full((64,), float("nan"), device=dev)
+    scratch = torch.empty(lib.conv3x3_wgrad_scratch_floats(), device=dev)
+    err = torch.zeros(1, device=dev, dtype=torch.int32)
+    lib.conv3x3_wgrad_tc(to_padded_nhwc(x).to(dev), to_padded_nhwc(gy).to(dev), dw, db, scratch, err, B, H, W, 0)
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0, "pipeline time-out"
+    _close(dw, wr.grad, rtol=rtol, atol=1e-5, what="tc wgrad")
+    _close(db, br.grad, rtol=rtol, atol=1e-4, what="tc bgrad")

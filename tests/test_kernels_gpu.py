@@ -53,9 +53,17 @@ def test_adam(lib):
     kc.check_adam(lib, DEV, n=100003)
 
 
-def test_conv3x3_tc(lib):
+@pytest.mark.parametrize("fn", ["conv3x3_tc_fwd", "conv3x3_tc2_fwd"])
+def test_conv3x3_tc(lib, fn):
     """tcgen05 + TMA 3xTF32 convolution (forward and dgrad) at small and at the real layer shapes."""
-    kc.check_conv3x3_tc(lib, DEV)
-    kc.check_conv3x3_tc(lib, DEV, B=2, H=10, W=10, seed=22)
-    kc.check_conv3x3_tc(lib, DEV, B=4, H=42, W=42, seed=23)
-    kc.check_conv3x3_tc(lib, DEV, B=5, H=21, W=21, seed=24)
+    kc.check_conv3x3_tc(lib, DEV, fn=fn)
+    kc.check_conv3x3_tc(lib, DEV, B=2, H=10, W=10, seed=22, fn=fn)
+    kc.check_conv3x3_tc(lib, DEV, B=4, H=42, W=42, seed=23, fn=fn)
+    kc.check_conv3x3_tc(lib, DEV, B=5, H=21, W=21, seed=24, fn=fn)
+
+
+def test_conv3x3_wgrad_tc(lib):
+    kc.check_conv3x3_wgrad_tc(lib, DEV)
+    kc.check_conv3x3_wgrad_tc(lib, DEV, B=2, H=10, W=10, seed=32)
+    kc.check_conv3x3_wgrad_tc(lib, DEV, B=6, H=42, W=42, seed=33)
+    kc.check_conv3x3_wgrad_tc(lib, DEV, B=64, H=21, W=21, seed=34)
