@@ -35,7 +35,8 @@ SIGNATURES = {
     "dktb_bn_eval_prepare": ("ppppifs", ctypes.c_int),
     "dktb_bn_relu_pool_fwd": ("ppppppiiiiiiis", ctypes.c_int),
     "dktb_bn_bwd_chunks": ("iii", ctypes.c_int),
-    "dktb_bn_relu_pool_bwd": ("pppppppppppiiiiiiis", ctypes.c_int),
+    "dktb_bn_relu_pool_bwd": ("ppppppppppppiiiiiiis", ctypes.c_int),
+    "dktb_bn_scratch_doubles": ("i", ctypes.c_long),
     "dktb_bn1d_fwd": ("pppppppppiiiiiiiffs", ctypes.c_int),
     "dktb_bn1d_bwd": ("pppppppppiiiiis", ctypes.c_int),
     "dktb_l2norm_fwd": ("ppplifs", ctypes.c_int),

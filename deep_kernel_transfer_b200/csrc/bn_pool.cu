@@ -9,30 +9,40 @@
 #include "dktb_common.cuh"
 
 // ------------------------------------------------------------------------------------------------
-// partials [B][T][2][64]  ->  sums [E][2][64]  (fixed order, double accumulation)
+// partials [B][T][2][64]  ->  sums [E][2][64]  (fixed order, double accumulation), two levels:
+// grid (E, ES_CHUNKS) CTAs each sum a contiguous slice into chunk_sums [E][ES_CHUNKS][128] (double),
+// then one small CTA per episode adds the ES_CHUNKS slices in order.
 // ------------------------------------------------------------------------------------------------
+#define ES_CHUNKS 32
 __global__ void __launch_bounds__(256) episode_sum_kernel(const float* __restrict__ partials, int T, int ipe,
-                                                          float* __restrict__ sums, double* __restrict__ sums_d) {
-  __shared__ double s_acc[4][128];
-  const int e = blockIdx.x;
+                                                          double* __restrict__ chunk_sums) {
+  __shared__ double s_acc[2][128];
+  const int e = blockIdx.x, ch = blockIdx.y;
   const int tid = threadIdx.x;
   const int col = tid % 128, slice = tid / 128;     // col = which*64 + c ; 2 slices
   const long n = (long)ipe * T;
+  const long per = (n + ES_CHUNKS - 1) / ES_CHUNKS;
+  const long lo = ch * per, hi = (lo + per < n) ? lo + per : n;
   const float* base = partials + (long)e * n * 128;
   double acc0 = 0.0, acc1 = 0.0;
-  long i = slice;
-  for (; i + 2 < n; i += 4) {
+  long i = lo + slice;
+  for (; i + 2 < hi; i += 4) {
     acc0 += (double)base[i * 128 + col];
     acc1 += (double)base[(i + 2) * 128 + col];
   }
-  for (; i < n; i += 2) acc0 += (double)base[i * 128 + col];
+  for (; i < hi; i += 2) acc0 += (double)base[i * 128 + col];
   s_acc[slice][col] = acc0 + acc1;
   __syncthreads();
-  if (tid < 128) {
-    const double t = s_acc[0][tid] + s_acc[1][tid];
-    if (sums) sums[(long)e * 128 + tid] = (float)t;
-    if (sums_d) sums_d[(long)e * 128 + tid] = t;
-  }
+  if (tid < 128) chunk_sums[((long)e * ES_CHUNKS + ch) * 128 + tid] = s_acc[0][tid] + s_acc[1][tid];
+}
+
+__global__ void episode_sum_final_kernel(const double* __restrict__ chunk_sums, float* __restrict__ sums,
+                                         double* __restrict__ sums_d) {
+  const int e = blockIdx.x, tid = threadIdx.x;     // 128 threads
+  double t = 0.0;
+  for (int ch = 0; ch < ES_CHUNKS; ++ch) t += chunk_sums[((long)e * ES_CHUNKS + ch) * 128 + tid];
+  if (sums) sums[(long)e * 128 + tid] = (float)t;
+  if (sums_d) sums_d[(long)e * 128 + tid] = t;
 }
 
 // sums_d [E][2][64] (sum, sumsq) -> mean, invstd [E][64]; sequential running-stat EMA over episodes
@@ -75,13 +85,18 @@ DKTB_EXPORT int dktb_bn_eval_prepare(const float* running_mean, const float* run
   return dktb_launch_status();
 }
 
-// Train-mode statistics from conv partial sums.  scratch_d: E*128 doubles.
+DKTB_EXPORT long dktb_bn_scratch_doubles(int E) { return (long)E * 128 * (1 + ES_CHUNKS); }
+
+// Train-mode statistics from conv partial sums.  scratch_d: dktb_bn_scratch_doubles(E) doubles.
 DKTB_EXPORT int dktb_bn_finalize(const float* partials, int B, int T, int ipe, int hw, float* mean, float* invstd,
                                  float* running_mean, float* running_var, double* scratch_d, float momentum, float eps,
                                  cudaStream_t stream) {
   DKTB_CHECK_ARG(partials && mean && invstd && scratch_d && B > 0 && T > 0 && ipe > 0 && B % ipe == 0 && hw > 0);
   const int E = B / ipe;
-  DKTB_LAUNCH(episode_sum_kernel, dim3(E), dim3(256), 0, stream, partials, T, ipe, (float*)nullptr, scratch_d);
+  double* chunk = scratch_d + (long)E * 128;
+  DKTB_LAUNCH(episode_sum_kernel, dim3(E, ES_CHUNKS), dim3(256), 0, stream, partials, T, ipe, chunk);
+  DKTB_LAUNCH(episode_sum_final_kernel, dim3(E), dim3(128), 0, stream, (const double*)chunk, (float*)nullptr,
+              scratch_d);
   DKTB_LAUNCH(bn_stats_kernel, dim3(1), dim3(64), 0, stream, (const double*)scratch_d, E, (double)ipe * (double)hw,
               mean, invstd, running_mean, running_var, momentum, eps);
   return dktb_launch_status();
@@ -300,19 +315,21 @@ DKTB_EXPORT int dktb_bn_bwd_chunks(int H, int W, int pool) {
 }
 
 // Full BatchNorm+ReLU+pool backward.  partial: B*chunks*128 floats; sums: E*128 floats (kept: it is
-// read by the apply pass); dgamma/dbeta [64] are overwritten.
+// read by the apply pass); scratch_d: dktb_bn_scratch_doubles(E); dgamma/dbeta [64] are overwritten.
 DKTB_EXPORT int dktb_bn_relu_pool_bwd(const float* y, const float* gout, const float* mean, const float* invstd,
                                       const float* gamma, const float* beta, float* gy, float* dgamma, float* dbeta,
-                                      float* partial, float* sums, int B, int H, int W, int ipe, int in_pad,
-                                      int out_pad, int pool, cudaStream_t stream) {
+                                      float* partial, float* sums, double* scratch_d, int B, int H, int W, int ipe,
+                                      int in_pad, int out_pad, int pool, cudaStream_t stream) {
   DKTB_CHECK_ARG(y && gout && mean && invstd && gamma && beta && gy && dgamma && dbeta && partial && sums);
   DKTB_CHECK_ARG(B > 0 && ipe > 0 && B % ipe == 0 && B <= 65535);
   const int chunks = dktb_bn_bwd_chunks(H, W, pool);
   const int E = B / ipe;
   DKTB_LAUNCH(bn_relu_pool_bwd_reduce_kernel, dim3(chunks, B), dim3(256), 0, stream, y, gout, mean, invstd, gamma, beta,
               partial, H, W, ipe, in_pad, out_pad, pool);
-  DKTB_LAUNCH(episode_sum_kernel, dim3(E), dim3(256), 0, stream, (const float*)partial, chunks, ipe, sums,
-              (double*)nullptr);
+  DKTB_CHECK_ARG(scratch_d != nullptr);
+  double* chunk = scratch_d + (long)E * 128;
+  DKTB_LAUNCH(episode_sum_kernel, dim3(E, ES_CHUNKS), dim3(256), 0, stream, (const float*)partial, chunks, ipe, chunk);
+  DKTB_LAUNCH(episode_sum_final_kernel, dim3(E), dim3(128), 0, stream, (const double*)chunk, sums, (double*)nullptr);
   DKTB_LAUNCH(bn_param_grad_kernel, dim3(1), dim3(64), 0, stream, (const float*)sums, E, dgamma, dbeta);
   const int Hc = pool ? (H + 1) / 2 : H, Wc = pool ? (W + 1) / 2 : W;
   const long total = (long)B * Hc * Wc * 16;

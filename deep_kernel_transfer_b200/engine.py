@@ -104,7 +104,7 @@ class ConvNetEngine:
         ws["eval_invstd"] = torch.empty(self.depth, 64, device=dev, dtype=f32)
         ws["bwd_partial"] = torch.empty(max_part, device=dev, dtype=f32)
         ws["bwd_sums"] = torch.empty(E * 128, device=dev, dtype=f32)
-        ws["scratch_d"] = torch.empty(E * 128, device=dev, dtype=torch.float64)
+        ws["scratch_d"] = torch.empty(lib.bn_scratch_doubles(E), device=dev, dtype=torch.float64)
         n1 = lib.conv1_wgrad_nsplit() * 28 * 64
         ws["wgrad_scratch"] = torch.empty(max(n1, lib.conv3x3_wgrad_scratch_floats()), device=dev, dtype=f32)
         self.ws, self.cap, self.cap_E = ws, B, E
@@ -172,7 +172,7 @@ class ConvNetEngine:
             H, W, pool = L["H"], L["W"], int(L["pool"])
             last = i == self.depth - 1
             lib.bn_relu_pool_bwd(ws["y"][i], gout, ws["mean"][i], ws["invstd"][i], P.bn_w[i], P.bn_b[i], ws["gy"][i],
-                                 G.bn_w[i], G.bn_b[i], ws["bwd_partial"], ws["bwd_sums"], B, H, W, ipe,
+                                 G.bn_w[i], G.bn_b[i], ws["bwd_partial"], ws["bwd_sums"], ws["scratch_d"], B, H, W, ipe,
                                  0 if i == 0 else 1, 0 if last else 1, pool, st)
             if i == 0:
                 lib.conv1_wgrad(x, ws["gy"][0], G.conv_w[0], G.conv_b[0], ws["wgrad_scratch"], B, H, W, st)

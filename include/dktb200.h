@@ -70,7 +70,8 @@ int dktb_conv3x3_wgrad_tc(const float* a, const float* gy, float* dw, float* db,
 int dktb_conv3x3_wgrad_reduce(const float* partial, int nsplit, float* dw, float* db, cudaStream_t stream);
 
 /* BatchNorm2d statistics (train: per-episode batch stats from the conv partial sums + running-stat EMA,
- * momentum 0.1, unbiased running variance; eval: running stats).  scratch_d: (B/ipe)*128 doubles. */
+ * momentum 0.1, unbiased running variance; eval: running stats).  scratch_d: dktb_bn_scratch_doubles(B/ipe). */
+long dktb_bn_scratch_doubles(int E);
 int dktb_bn_finalize(const float* partials, int B, int T, int ipe, int hw, float* mean, float* invstd,
                      float* running_mean, float* running_var, double* scratch_d, float momentum, float eps,
                      cudaStream_t stream);
@@ -82,12 +83,13 @@ int dktb_bn_relu_pool_fwd(const float* y, const float* mean, const float* invstd
                           const float* beta, float* out, int B, int H, int W, int ipe, int in_pad, int out_pad,
                           int pool, cudaStream_t stream);
 /* backward of the above (train mode): gy (same layout as y), dgamma/dbeta [64];
- * partial: B*dktb_bn_bwd_chunks(H,W,pool)*128 floats, sums: (B/ipe)*128 floats. */
+ * partial: B*dktb_bn_bwd_chunks(H,W,pool)*128 floats, sums: (B/ipe)*128 floats,
+ * scratch_d: dktb_bn_scratch_doubles(B/ipe) doubles. */
 int dktb_bn_bwd_chunks(int H, int W, int pool);
 int dktb_bn_relu_pool_bwd(const float* y, const float* gout, const float* mean, const float* invstd,
                           const float* gamma, const float* beta, float* gy, float* dgamma, float* dbeta,
-                          float* partial, float* sums, int B, int H, int W, int ipe, int in_pad, int out_pad, int pool,
-                          cudaStream_t stream);
+                          float* partial, float* sums, double* scratch_d, int B, int H, int W, int ipe, int in_pad,
+                          int out_pad, int pool, cudaStream_t stream);
 
 /* ---- feature head: bn_out BatchNorm1d (methods/DKT.py:45-48) + F.normalize (methods/DKT.py:142) -------
  * features f [E][N][D] NHWC-flattened (j = p*Cch + c); parameters indexed in the reference's NCHW-flatten

@@ -117,7 +117,7 @@ def check_bn_relu_pool(lib, dev, E=2, ipe=3, H=7, W=6, pool=1, in_pad=1, out_pad
     mean = torch.empty(E, 64, device=dev)
     invstd = torch.empty(E, 64, device=dev)
     drm, drv = rm0.clone().to(dev), rv0.clone().to(dev)
-    scratch_d = torch.empty(E * 128, device=dev, dtype=torch.float64)
+    scratch_d = torch.empty(lib.bn_scratch_doubles(E), device=dev, dtype=torch.float64)
     lib.bn_finalize(part, B, 1, ipe, H * W, mean, invstd, drm, drv, scratch_d, 0.1, 1e-5, 0)
     _close(drm, rm, what="running_mean")
     _close(drv, rv, what="running_var")
@@ -135,8 +135,8 @@ def check_bn_relu_pool(lib, dev, E=2, ipe=3, H=7, W=6, pool=1, in_pad=1, out_pad
     chunks = lib.bn_bwd_chunks(H, W, pool)
     partial = torch.empty(B * chunks * 128, device=dev)
     sums = torch.empty(E * 128, device=dev)
-    lib.bn_relu_pool_bwd(yd, gd, mean, invstd, gamma.to(dev), beta.to(dev), gy, dg, db, partial, sums, B, H, W, ipe,
-                         in_pad, out_pad, pool, 0)
+    lib.bn_relu_pool_bwd(yd, gd, mean, invstd, gamma.to(dev), beta.to(dev), gy, dg, db, partial, sums, scratch_d, B, H,
+                         W, ipe, in_pad, out_pad, pool, 0)
     got_gy = from_padded_nhwc(gy.cpu()) if in_pad else gy.cpu().permute(0, 3, 1, 2)
     _close(got_gy, yr.grad, rtol=2e-4, atol=1e-5, what="bn_relu_pool bwd gy")
     _close(dg, gr.grad, rtol=2e-4, atol=1e-4, what="dgamma")
