@@ -47,6 +47,11 @@ SIGNATURES = {
     "dktb_gp_reduce": ("ppppiis", ctypes.c_int),
     "dktb_gram_bwd": ("pppiiiifs", ctypes.c_int),
     "dktb_gp_predict": ("plpppppiiiis", ctypes.c_int),
+    "dktb_center_rows": ("pppiiiis", ctypes.c_int),
+    "dktb_row_sqnorm": ("pplis", ctypes.c_int),
+    "dktb_kernel_fwd": ("ipppppiiiis", ctypes.c_int),
+    "dktb_kernel_bwd": ("ipppppppiiis", ctypes.c_int),
+    "dktb_gp_predict_var": ("plplppppiiiis", ctypes.c_int),
     "dktb_adam_step": ("pppplffffifs", ctypes.c_int),
     "dktb_scale": ("plfs", ctypes.c_int),
 }

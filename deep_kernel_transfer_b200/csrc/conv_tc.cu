@@ -192,14 +192,23 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 constexpr int kHaloBox = 32;                  // rows per halo TMA box
 constexpr int kWStages = 3;
 constexpr int kWStageBytes = 16384;           // W hi 8K | W lo 8K for one (tap, half)
+constexpr int kAStages = 3;                   // TMEM A stages of {hi 32 | lo 32} columns
+constexpr int kTsThreads = 64 + 256;          // TMA warp, MMA warp, 8 stager / epilogue warps
 
-__global__ void __launch_bounds__(192, 2)
+// tf32 split with full-rate integer ops: hi = round-to-nearest(-away) to 10 mantissa bits, lo = rounded remainder
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u;
+  lo = (__float_as_uint(v - __uint_as_float(hi)) + 0x1000u) & 0xFFFFE000u;
+}
+
+__global__ void __launch_bounds__(kTsThreads, 2)
 conv3x3_tc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                      const float* __restrict__ bias, float* __restrict__ out, float* __restrict__ partials, int B, int H,
                      int W, int halo_rows_pad, int* __restrict__ err) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t bar_halo, bar_wfull[kWStages], bar_wempty[kWStages], bar_afull[2], bar_aempty[2], bar_acc;
+  __shared__ uint64_t bar_halo, bar_wfull[kWStages], bar_wempty[kWStages], bar_afull[kAStages], bar_aempty[kAStages],
+      bar_acc;
   __shared__ uint32_t s_tmem;
   __shared__ int s_err;
   __shared__ float s_valid[kRows];
@@ -215,7 +224,7 @@ conv3x3_tc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   if (tid == 0) {
     tc::mbar_init(&bar_halo, 1);
     for (int s = 0; s < kWStages; ++s) { tc::mbar_init(&bar_wfull[s], 1); tc::mbar_init(&bar_wempty[s], 1); }
-    for (int s = 0; s < 2; ++s) { tc::mbar_init(&bar_afull[s], 128); tc::mbar_init(&bar_aempty[s], 1); }
+    for (int s = 0; s < kAStages; ++s) { tc::mbar_init(&bar_afull[s], 256); tc::mbar_init(&bar_aempty[s], 1); }
     tc::mbar_init(&bar_acc, 1);
     s_err = 0;
     tc::fence_barrier_init();
@@ -230,7 +239,6 @@ conv3x3_tc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 
   if (warp == 0) {
     if (lane == 0) {
-      // halo: rows q0-(Wp+1) .. +halo_rows_pad, both channel halves
       tc::mbar_expect_tx(&bar_halo, 2 * half_bytes);
       const int row0 = (int)(img_base + q0 - (Wp + 1));
       for (int h = 0; h < 2; ++h)
@@ -251,7 +259,7 @@ conv3x3_tc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       bool ok = true;
       for (int it = 0; it < kIters && ok; ++it) {
         const int sw = it % kWStages, pw = (it / kWStages) & 1;
-        const int sa = it & 1, pa = (it >> 1) & 1;
+        const int sa = it % kAStages, pa = (it / kAStages) & 1;
         ok = tc::mbar_wait(&bar_wfull[sw], pw) && tc::mbar_wait(&bar_afull[sa], pa);
         if (!ok) break;
         tc::tcgen05_fence_after();
@@ -272,34 +280,32 @@ conv3x3_tc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       tc::umma_commit(&bar_acc);
     }
   } else {
-    const int ct = tid - 64;
+    const int ct = tid - 64;                                 // 0..255
+    const int set = ct >> 7;                                 // which 16-channel quarter-slice of the 32-channel half
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;                       // accumulator row / TMEM lane of this thread
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     bool ok = tc::mbar_wait(&bar_halo, 0);
     for (int it = 0; it < kIters && ok; ++it) {
-      const int sa = it & 1, pa = (it >> 1) & 1;
+      const int sa = it % kAStages, pa = (it / kAStages) & 1;
       const int tap = it >> 1, half = it & 1;
+      const int row = r + (tap / 3) * Wp + (tap % 3);
+      const unsigned char* src = s_halo + half * half_bytes + row * 128;
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 v = *reinterpret_cast<const float4*>(src + (((set * 4 + j) ^ (row & 7)) << 4));
+        split_tf32(v.x, hi[4 * j + 0], lo[4 * j + 0]);
+        split_tf32(v.y, hi[4 * j + 1], lo[4 * j + 1]);
+        split_tf32(v.z, hi[4 * j + 2], lo[4 * j + 2]);
+        split_tf32(v.w, hi[4 * j + 3], lo[4 * j + 3]);
+      }
       ok = tc::mbar_wait(&bar_aempty[sa], pa ^ 1);
       if (!ok) break;
       tc::tcgen05_fence_after();
-      const int row = r + (tap / 3) * Wp + (tap % 3);
-      const unsigned char* src = s_halo + half * half_bytes + row * 128;
-      uint32_t hi[32], lo[32];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 v = *reinterpret_cast<const float4*>(src + ((j ^ (row & 7)) << 4));
-        const float h0 = tc::to_tf32_rna(v.x), h1 = tc::to_tf32_rna(v.y), h2 = tc::to_tf32_rna(v.z), h3 = tc::to_tf32_rna(v.w);
-        hi[4 * j + 0] = __float_as_uint(h0); hi[4 * j + 1] = __float_as_uint(h1);
-        hi[4 * j + 2] = __float_as_uint(h2); hi[4 * j + 3] = __float_as_uint(h3);
-        lo[4 * j + 0] = __float_as_uint(tc::to_tf32_rna(v.x - h0)); lo[4 * j + 1] = __float_as_uint(tc::to_tf32_rna(v.y - h1));
-        lo[4 * j + 2] = __float_as_uint(tc::to_tf32_rna(v.z - h2)); lo[4 * j + 3] = __float_as_uint(tc::to_tf32_rna(v.w - h3));
-      }
-      const uint32_t dst = a_tmem + sa * 64 + lane_base;
+      const uint32_t dst = a_tmem + sa * 64 + lane_base + set * 16;
       tc::tmem_st16(dst, hi);
-      tc::tmem_st16(dst + 16, hi + 16);
       tc::tmem_st16(dst + 32, lo);
-      tc::tmem_st16(dst + 48, lo + 16);
       tc::tmem_st_wait();
       tc::tcgen05_fence_before();
       tc::mbar_arrive(&bar_afull[sa]);
@@ -311,10 +317,11 @@ conv3x3_tc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const int q = q0 + r;
     const int hp = q / Wp, wp = q - hp * Wp;
     const bool valid = ok && q < Hp * Wp && hp >= 1 && hp <= H && wp >= 1 && wp <= W;
-    s_valid[r] = valid ? 1.f : 0.f;
+    if (set == 0) s_valid[r] = valid ? 1.f : 0.f;
     if (ok) {
 #pragma unroll
-      for (int c = 0; c < 64; c += 16) {
+      for (int cc = 0; cc < 32; cc += 16) {
+        const int c = set * 32 + cc;
         uint32_t v[16];
         tc::tmem_ld16(d_tmem + lane_base + c, v);
         tc::tmem_ld_wait();
@@ -326,15 +333,15 @@ conv3x3_tc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       }
     }
     tc::tcgen05_fence_before();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    for (int idx = ct; idx < kRows * 16; idx += 128) {
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    for (int idx = ct; idx < kRows * 16; idx += 256) {
       const int rr = idx >> 4, c4 = (idx & 15) * 4;
       if (s_valid[rr] != 0.f) {
         const float* src = s_out + rr * kOutLd + c4;
         dktb_st4(out + (img_base + q0 + rr) * 64 + c4, make_float4(src[0], src[1], src[2], src[3]));
       }
     }
-    if (partials != nullptr) {
+    if (partials != nullptr && ct < 128) {
       const int which = ct >> 6, c = ct & 63;
       float t = 0.f;
       for (int rr = 0; rr < kRows; ++rr) {
@@ -366,7 +373,7 @@ conv3x3_tc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 constexpr int kKR = 32;                         // rows per K-block
 constexpr int kWgAStages = 3;
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kTsThreads, 1)
 conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g,
                         float* __restrict__ partial, long total_rows, int Wp, int halo_pad, int pstride,
                         int* __restrict__ err) {
@@ -376,7 +383,7 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       bar_acc;
   __shared__ uint32_t s_tmem;
   __shared__ int s_err;
-  __shared__ float s_bias[2][64];
+  __shared__ float s_bias[4][64];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int x_half_bytes = halo_pad * 128;
   const int stage_bytes = 2 * x_half_bytes + 8192 + 16384;   // X raw | G raw | B hi | B lo
@@ -385,10 +392,10 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&bar_raw_full[s], 1);
-      tc::mbar_init(&bar_raw_empty[s], 129);      // 128 stagers done reading + 1 tcgen05.commit (B consumed)
-      tc::mbar_init(&bar_bfull[s], 128);
+      tc::mbar_init(&bar_raw_empty[s], 257);      // 256 stagers done reading + 1 tcgen05.commit (B consumed)
+      tc::mbar_init(&bar_bfull[s], 256);
     }
-    for (int s = 0; s < kWgAStages; ++s) { tc::mbar_init(&bar_afull[s], 128); tc::mbar_init(&bar_aempty[s], 1); }
+    for (int s = 0; s < kWgAStages; ++s) { tc::mbar_init(&bar_afull[s], 256); tc::mbar_init(&bar_aempty[s], 1); }
     tc::mbar_init(&bar_acc, 1);
     s_err = 0;
     tc::fence_barrier_init();
@@ -451,11 +458,13 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       tc::umma_commit(&bar_acc);
     }
   } else {
+    const int ct = tid - 64;                                  // 0..255
+    const int set = ct >> 7;                                  // k range [set*16, +16) of the 32-row K-block
     const int quarter = warp & 3;
-    const int L = quarter * 32 + lane;                       // TMEM lane: (tap-in-pair, ci)
+    const int L = quarter * 32 + lane;                        // TMEM lane: (tap-in-pair, ci)
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const int ci = L & 63, tsel = L >> 6;
-    const int co = L & 63, khalf = L >> 6;                    // roles for the G transpose
+    const int co = ct & 63, kq8 = ct >> 6;                    // G transpose: 8 k values [kq8*8, +8) of channel co
     float bias_acc = 0.f;
     bool ok = true;
     int n = 0, ai = 0;
@@ -464,60 +473,55 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       ok = tc::mbar_wait(&bar_raw_full[s], ph);
       if (!ok) break;
       unsigned char* st = smem + s * stage_bytes;
-      // ---- B: G[k][co] -> K-major [co][k] hi / lo (16 k values per thread)
+      // ---- B: G[k][co] -> K-major [co][k] hi / lo (8 k values per thread)
       {
         const unsigned char* graw = st + 2 * x_half_bytes + (co >> 5) * 4096;
         unsigned char* bhi = st + 2 * x_half_bytes + 8192 + co * 128;
         unsigned char* blo = bhi + 8192;
         const int cq = (co & 31) >> 2, cr = co & 3;
 #pragma unroll
-        for (int kq = 0; kq < 4; ++kq) {
-          float h[4], l[4];
+        for (int kq = 0; kq < 2; ++kq) {
+          uint32_t h[4], l[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int k = khalf * 16 + kq * 4 + j;
+            const int k = kq8 * 8 + kq * 4 + j;
             const float v = *reinterpret_cast<const float*>(graw + k * 128 + ((cq ^ (k & 7)) << 4) + cr * 4);
             bias_acc += v;
-            h[j] = tc::to_tf32_rna(v);
-            l[j] = tc::to_tf32_rna(v - h[j]);
+            split_tf32(v, h[j], l[j]);
           }
-          const int kchunk = khalf * 4 + kq;                 // 16-byte chunk index along K (4 floats)
+          const int kchunk = kq8 * 2 + kq;                   // 16-byte chunk index along K (4 floats)
           const int off = (kchunk ^ (co & 7)) << 4;
-          *reinterpret_cast<float4*>(bhi + off) = make_float4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<float4*>(blo + off) = make_float4(l[0], l[1], l[2], l[3]);
+          *reinterpret_cast<uint4*>(bhi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(blo + off) = make_uint4(l[0], l[1], l[2], l[3]);
         }
         tc::fence_proxy_async_smem();
         tc::mbar_arrive(&bar_bfull[s]);
       }
-      // ---- A: five tap-pair groups into TMEM
+      // ---- A: five tap-pair groups into TMEM (this thread: 16 of the 32 K rows of its lane)
       for (int g = 0; g < 5 && ok; ++g, ++ai) {
         const int sa = ai % kWgAStages, pa = (ai / kWgAStages) & 1;
-        ok = tc::mbar_wait(&bar_aempty[sa], pa ^ 1);
-        if (!ok) break;
-        tc::tcgen05_fence_after();
         const int tap = 2 * g + tsel;
-        uint32_t hi[32], lo[32];
+        uint32_t hi[16], lo[16];
         if (tap < 9) {
-          const int shift = (tap / 3) * Wp + (tap % 3);
+          const int shift = (tap / 3) * Wp + (tap % 3) + set * 16;
           const unsigned char* xh = st + (ci >> 5) * x_half_bytes;
           const int cq = (ci & 31) >> 2, cr = ci & 3;
 #pragma unroll
-          for (int k = 0; k < 32; ++k) {
+          for (int k = 0; k < 16; ++k) {
             const int row = k + shift;
             const float v = *reinterpret_cast<const float*>(xh + row * 128 + ((cq ^ (row & 7)) << 4) + cr * 4);
-            const float h = tc::to_tf32_rna(v);
-            hi[k] = __float_as_uint(h);
-            lo[k] = __float_as_uint(tc::to_tf32_rna(v - h));
+            split_tf32(v, hi[k], lo[k]);
           }
         } else {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) { hi[k] = 0u; lo[k] = 0u; }
+          for (int k = 0; k < 16; ++k) { hi[k] = 0u; lo[k] = 0u; }
         }
-        const uint32_t dst = a_tmem + sa * 64 + lane_base;
+        ok = tc::mbar_wait(&bar_aempty[sa], pa ^ 1);
+        if (!ok) break;
+        tc::tcgen05_fence_after();
+        const uint32_t dst = a_tmem + sa * 64 + lane_base + set * 16;
         tc::tmem_st16(dst, hi);
-        tc::tmem_st16(dst + 16, hi + 16);
         tc::tmem_st16(dst + 32, lo);
-        tc::tmem_st16(dst + 48, lo + 16);
         tc::tmem_st_wait();
         tc::tcgen05_fence_before();
         tc::mbar_arrive(&bar_afull[sa]);
@@ -532,7 +536,8 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       for (int g = 0; g < 5; ++g) {
         const int tap = 2 * g + tsel;
 #pragma unroll
-        for (int c = 0; c < 64; c += 16) {
+        for (int cc = 0; cc < 32; cc += 16) {
+          const int c = set * 32 + cc;
           uint32_t v[16];
           tc::tmem_ld16(tmem + g * 64 + lane_base + c, v);
           tc::tmem_ld_wait();
@@ -546,10 +551,10 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         }
       }
     }
-    s_bias[khalf][co] = bias_acc;
+    s_bias[kq8][co] = bias_acc;
     tc::tcgen05_fence_before();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (khalf == 0) out[9 * 64 * 64 + co] = s_bias[0][co] + s_bias[1][co];
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (kq8 == 0) out[9 * 64 * 64 + co] = (s_bias[0][co] + s_bias[1][co]) + (s_bias[2][co] + s_bias[3][co]);
   }
   tc::tcgen05_fence_before();
   __syncthreads();
@@ -622,7 +627,7 @@ DKTB_EXPORT int dktb_conv3x3_tc2_fwd(const float* a, const float* wb, const floa
   cudaFuncSetAttribute(conv3x3_tc_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int span = Hp * Wp - 2 * (Wp + 1);
   dim3 grid((span + kRows - 1) / kRows, B);
-  conv3x3_tc_ts_kernel<<<grid, 192, smem, stream>>>(map_a, map_w, bias, out, partials, B, H, W, halo_pad, err);
+  conv3x3_tc_ts_kernel<<<grid, kTsThreads, smem, stream>>>(map_a, map_w, bias, out, partials, B, H, W, halo_pad, err);
   return dktb_launch_status();
 }
 
@@ -647,7 +652,7 @@ DKTB_EXPORT int dktb_conv3x3_wgrad_tc(const float* a, const float* gy, float* dw
   const long nkb = (rows + kKR - 1) / kKR;
   const int pstride = 9 * 64 * 64 + 64;
   const int nsplit = (int)(nkb < 148 ? nkb : 148);
-  conv3x3_wgrad_tc_kernel<<<nsplit, 192, smem, stream>>>(map_x, map_g, scratch, rows, Wp, halo_pad, pstride, err);
+  conv3x3_wgrad_tc_kernel<<<nsplit, kTsThreads, smem, stream>>>(map_x, map_g, scratch, rows, Wp, halo_pad, pstride, err);
   int rc = dktb_launch_status();
   if (rc != 0) return rc;
   return dktb_conv3x3_wgrad_reduce(scratch, nsplit, dw, db, stream);

@@ -168,23 +168,25 @@ __global__ void __launch_bounds__(128) kernel_bwd_kernel(int kind, const float* 
   if (tid == 0 && (kind == KIND_RBF || kind == KIND_MATERN)) dg[(long)e * N * N + (long)i * N + i] += diag_extra;
 }
 
-// dparam[e][c] = sum_i dparam_rows[e][c][i]   (fixed order)
-__global__ void kernel_bwd_reduce_kernel(const float* __restrict__ rows, float* __restrict__ dparam, int total, int N) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
+// dparam[c] = sum_e sum_i dparam_rows[e][c][i]   (fixed order)
+__global__ void kernel_bwd_reduce_kernel(const float* __restrict__ rows, float* __restrict__ dparam, int E, int C,
+                                         int N) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
   float t = 0.f;
-  for (int n = 0; n < N; ++n) t += rows[(long)i * N + n];
-  dparam[i] = t;
+  for (int e = 0; e < E; ++e)
+    for (int n = 0; n < N; ++n) t += rows[((long)e * C + c) * N + n];
+  dparam[c] = t;
 }
 
-// dparam [E][C] (already multiplied by sigmoid(raw)); scratch: E*C*N floats
+// dparam [C] = dLoss/d raw_param summed over episodes; scratch: E*C*N floats
 DKTB_EXPORT int dktb_kernel_bwd(int kind, const float* g, const float* sq, const float* raw_param, const float* dkb,
                                 float* dg, float* dparam, float* scratch, int E, int C, int N, cudaStream_t stream) {
   DKTB_CHECK_ARG(g && raw_param && dkb && dg && dparam && scratch && E > 0 && C > 0 && N > 0 && kind >= 0 && kind <= 4);
   DKTB_CHECK_ARG((kind != KIND_RBF && kind != KIND_MATERN) || sq);
   DKTB_LAUNCH(kernel_bwd_kernel, dim3(N, E), dim3(128), 0, stream, kind, g, sq, raw_param, dkb, dg, scratch, C, N);
-  DKTB_LAUNCH(kernel_bwd_reduce_kernel, dim3((E * C + 127) / 128), dim3(128), 0, stream, (const float*)scratch, dparam,
-              E * C, N);
+  DKTB_LAUNCH(kernel_bwd_reduce_kernel, dim3((C + 31) / 32), dim3(32), 0, stream, (const float*)scratch, dparam, E, C,
+              N);
   return dktb_launch_status();
 }
 

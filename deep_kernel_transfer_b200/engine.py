@@ -193,6 +193,7 @@ class GPHeadParams:
     def __init__(self):
         self.bn_w = self.bn_b = self.bn_rm = self.bn_rv = None
         self.raw_outputscale = self.constant = self.raw_noise = None
+        self.raw_param = None      # per-class raw variance / lengthscale / offset of the kernel family
 
 
 class GPHead:
@@ -202,12 +203,18 @@ class GPHead:
     Gram matrix of the (normalised) features, shared by the C one-vs-rest models (DKT.py:366-370).
     """
 
+    FAMILY = {"linear": 0, "rbf": 1, "matern": 2, "poli1": 3, "poli2": 4}
+
     def __init__(self, lib, kernel, n_way, D, Cch, P, device="cuda"):
-        assert kernel in ("bncossim", "cossim"), kernel
+        assert kernel in ("bncossim", "cossim") or kernel in self.FAMILY, kernel
         self.lib, self.kernel, self.C, self.D, self.Cch, self.P = lib, kernel, n_way, D, Cch, P
         self.dev = torch.device(device)
         self.bn = kernel == "bncossim"
         self.normalize = kernel in ("bncossim", "cossim")
+        # cossim / bncossim: the Gram matrix of the normalised features IS the base kernel, shared by all classes
+        # (variance frozen at 1).  Other kernels: per-class epilogue on the Gram of the (centred) features.
+        self.family = self.FAMILY.get(kernel)
+        self.centred = kernel in ("rbf", "matern")
         self.key = None
 
     def _alloc(self, E, N):
@@ -232,6 +239,13 @@ class GPHead:
         w["dz"] = torch.empty(E, N, D, device=dev, dtype=f32)
         w["df"] = torch.empty(E, N, D, device=dev, dtype=f32)
         w["pgrad"] = torch.empty(E * 2 * D, device=dev, dtype=f32)
+        if self.family is not None:
+            w["xc"] = torch.empty(E, N, D, device=dev, dtype=f32)
+            w["sq"] = torch.empty(E, N, device=dev, dtype=f32)
+            w["kb"] = torch.empty(E, C, N, N, device=dev, dtype=f32)
+            w["dg"] = torch.empty(E, N, N, device=dev, dtype=f32)
+            w["dparam"] = torch.empty(C, device=dev, dtype=f32)
+            w["kscratch"] = torch.empty(E * C * N, device=dev, dtype=f32)
         self.w, self.key = w, (E, N)
 
     def ensure(self, E, N):
@@ -246,27 +260,51 @@ class GPHead:
             lib.bn1d_fwd(cur, HP.bn_w, HP.bn_b, HP.bn_rm, HP.bn_rv, w["z"], w["bn_mean"], w["bn_invstd"], w["bn_var"],
                          E, N, self.D, self.Cch, self.P, int(training), int(update_running), BN_MOMENTUM, BN_EPS, st)
             cur = w["z"]
+        dst = out if out is not None else w["zh"]
         if self.normalize:
-            dst = out if out is not None else w["zh"]
             lib.l2norm_fwd(cur, dst, w["inv"] if training else None, E * N, self.D, 1e-12, st)
-            cur = dst
-        return cur
+        else:
+            dst.copy_(cur)      # keep the embedding out of the backbone workspace (device memcpy)
+        return dst
 
     def fit(self, zh, targets, HP, E, N, want_grad, grad_scale=1.0, jitter=0.0):
         """Gram + C Cholesky systems per episode.  targets [C,N] (shared by all episodes)."""
         lib, st, w, C = self.lib, _stream(self.dev), self.w, self.C
-        lib.gram(zh, zh, w["gram"], E, N, N, self.D, st)
-        lib.gp_fit(w["gram"], 0, targets, 0, HP.raw_outputscale, HP.constant, HP.raw_noise, w["alpha"], None,
+        if self.family is None:
+            lib.gram(zh, zh, w["gram"], E, N, N, self.D, st)
+            kb, stride = w["gram"], 0
+        else:
+            xc = self._centre(zh, zh, w["xc"], E, N, N)
+            lib.gram(xc, xc, w["gram"], E, N, N, self.D, st)
+            lib.row_sqnorm(xc, w["sq"], E * N, self.D, st)
+            lib.kernel_fwd(self.family, w["gram"], w["sq"], w["sq"], HP.raw_param, w["kb"], E, C, N, N, st)
+            kb, stride = w["kb"], N * N
+        lib.gp_fit(kb, stride, targets, 0, HP.raw_outputscale, HP.constant, HP.raw_noise, w["alpha"], None,
                    w["loss_terms"], w["info"], w["dk"] if want_grad else None, w["dhyper"] if want_grad else None,
                    grad_scale, jitter, E, C, N, st)
         lib.gp_reduce(w["loss_terms"], w["dhyper"] if want_grad else None, w["loss"], w["hyper"] if want_grad else None,
                       E, C, st)
         return w["loss"]
 
+    def _centre(self, x, ref, out, E, N, Nr):
+        if not self.centred:
+            return x
+        self.lib.center_rows(x, ref, out, E, N, Nr, self.D, _stream(self.dev))
+        return out
+
     def backward(self, feats, zh, HP, GH, E, N):
-        """Gradient w.r.t. the backbone features [E*N, D]; fills GH.{bn_w,bn_b,raw_outputscale,constant}."""
+        """Gradient w.r.t. the backbone features [E*N, D]; fills GH.{bn_w,bn_b,raw_outputscale,constant,raw_param}."""
         lib, st, w = self.lib, _stream(self.dev), self.w
-        lib.gram_bwd(w["dk"], zh, w["dzh"], E, self.C, N, self.D, 1.0, st)
+        if self.family is None:
+            lib.gram_bwd(w["dk"], zh, w["dzh"], E, self.C, N, self.D, 1.0, st)
+        else:
+            xc = w["xc"] if self.centred else zh
+            lib.kernel_bwd(self.family, w["gram"], w["sq"], HP.raw_param, w["dk"], w["dg"], w["dparam"], w["kscratch"],
+                           E, self.C, N, st)
+            GH.raw_param.copy_(w["dparam"])
+            # rbf / matern are translation invariant: the gradient w.r.t. the centred rows already sums to zero,
+            # so the centring needs no backward pass
+            lib.gram_bwd(w["dg"], xc, w["dzh"], E, 1, N, self.D, 1.0, st)
         g = w["dzh"]
         if self.normalize:
             lib.l2norm_bwd(zh, g, w["inv"], w["dz"], E * N, self.D, st)
@@ -282,9 +320,26 @@ class GPHead:
     def predict(self, zh_test, zh_train, HP, E, M, N, mean_out, pred_out, kx_buf):
         """Predictive mean [E,C,M] + class arg-max [E,M]; expects alpha of the current fit in the workspace."""
         lib, st = self.lib, _stream(self.dev)
-        lib.gram(zh_test, zh_train, kx_buf, E, M, N, self.D, st)
-        lib.gp_predict(kx_buf, 0, self.w["alpha"], HP.raw_outputscale, HP.constant, mean_out, pred_out, E, self.C, M,
-                       N, st)
+        if self.family is None:
+            lib.gram(zh_test, zh_train, kx_buf, E, M, N, self.D, st)
+            lib.gp_predict(kx_buf, 0, self.w["alpha"], HP.raw_outputscale, HP.constant, mean_out, pred_out, E, self.C,
+                           M, N, st)
+            return
+        dev, f32, C = self.dev, torch.float32, self.C
+        t = self.w.setdefault("pred_tmp", {})
+        key = (E, M, N)
+        if t.get("key") != key:
+            t.update(key=key, xt=torch.empty(E, M, self.D, device=dev, dtype=f32),
+                     xr=torch.empty(E, N, self.D, device=dev, dtype=f32), sqt=torch.empty(E, M, device=dev, dtype=f32),
+                     sqr=torch.empty(E, N, device=dev, dtype=f32), kx=torch.empty(E, C, M, N, device=dev, dtype=f32))
+        xr = self._centre(zh_train, zh_train, t["xr"], E, N, N)
+        xt = self._centre(zh_test, zh_train, t["xt"], E, M, N)
+        lib.gram(xt, xr, kx_buf, E, M, N, self.D, st)
+        lib.row_sqnorm(xt, t["sqt"], E * M, self.D, st)
+        lib.row_sqnorm(xr, t["sqr"], E * N, self.D, st)
+        lib.kernel_fwd(self.family, kx_buf, t["sqt"], t["sqr"], HP.raw_param, t["kx"], E, C, M, N, st)
+        lib.gp_predict(t["kx"], M * N, self.w["alpha"], HP.raw_outputscale, HP.constant, mean_out, pred_out, E, C, M, N,
+                       st)
 
 
 def make_targets(n_way, per_class, device):

@@ -47,8 +47,8 @@ class DKT(MetaTemplate):
             self.feature_extractor.trunk.add_module("bn_out", nn.BatchNorm1d(latent_size))
         else:
             self.normalize = False
-        if self.kernel not in ("cossim", "bncossim"):
-            raise NotImplementedError("kernel '%s' is not on the CUDA path yet (cossim / bncossim are)" % self.kernel)
+        if self.kernel not in ("cossim", "bncossim", "linear", "rbf", "matern", "poli1", "poli2"):
+            raise ValueError("[ERROR] the kernel '" + str(self.kernel) + "' is not supported!")
         self.episodes_per_step = int(episodes_per_step)
         self.monitor = True
         self._lib = lib
@@ -90,6 +90,11 @@ class DKT(MetaTemplate):
         ms = self.model.models
         train = [("gp.raw_outputscale.%d" % c, ms[c].covar_module.raw_outputscale, 1) for c in range(C)]
         train += [("gp.constant.%d" % c, ms[c].mean_module.constant, 1) for c in range(C)]
+        self._family = self.kernel not in ("cossim", "bncossim")
+        if self._family:      # per-class raw variance / lengthscale / offset (learned, DKT.py:352-365)
+            pname = {"linear": "raw_variance", "rbf": "raw_lengthscale", "matern": "raw_lengthscale",
+                     "poli1": "raw_offset", "poli2": "raw_offset"}[self.kernel]
+            train += [("gp.raw_param.%d" % c, getattr(ms[c].covar_module.base_kernel, pname), 1) for c in range(C)]
         self._gp_count = len(train)
         blocks = self.feature.blocks()
         for i, b in enumerate(blocks):
@@ -125,6 +130,9 @@ class DKT(MetaTemplate):
         GH.raw_outputscale = pk.grad[0:C]
         GH.constant = pk.grad[C:2 * C]
         HP.raw_noise = self._bufs.flat[0:C]
+        if self._family:
+            HP.raw_param = pk.flat[2 * C:3 * C]
+            GH.raw_param = pk.grad[2 * C:3 * C]
         if bn_out is not None:
             HP.bn_w, HP.bn_b = pk.view("bn_out.weight"), pk.view("bn_out.bias")
             GH.bn_w, GH.bn_b = pk.view("bn_out.weight", True), pk.view("bn_out.bias", True)

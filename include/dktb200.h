@@ -126,6 +126,22 @@ int dktb_gram_bwd(const float* w, const float* z, float* dz, int E, int C, int N
 int dktb_gp_predict(const float* kx, long kx_class_stride, const float* alpha, const float* raw_outputscale,
                     const float* constant, float* mean, int* pred, int E, int C, int M, int N, cudaStream_t stream);
 
+/* ---- base-kernel family (ExactGPLayer, methods/DKT.py:352-372; DKT_regression.py:117-124) as an epilogue on the Gram
+ * matrix of mean-centred features.  kind: 0 linear (softplus(raw)=variance), 1 rbf, 2 matern-2.5 (lengthscale),
+ * 3 poli1, 4 poli2 (offset).  kb [E][C][M][N]: one kernel matrix per one-vs-rest model. */
+int dktb_center_rows(const float* x, const float* ref, float* out, int E, int N, int Nr, int D, cudaStream_t stream);
+int dktb_row_sqnorm(const float* x, float* sq, long rows, int D, cudaStream_t stream);
+int dktb_kernel_fwd(int kind, const float* g, const float* sq1, const float* sq2, const float* raw_param, float* kb,
+                    int E, int C, int M, int N, cudaStream_t stream);
+/* dkb [E][C][N][N] = dLoss/dKb_c -> dg [E][N][N] (summed over classes, incl. the diagonal terms through the norms),
+ * dparam [C] = dLoss/d raw_param; scratch: E*C*N floats */
+int dktb_kernel_bwd(int kind, const float* g, const float* sq, const float* raw_param, const float* dkb, float* dg,
+                    float* dparam, float* scratch, int E, int C, int N, cudaStream_t stream);
+/* predictive variance of likelihood(model(x*)): s*kss - ||L^-1 s kx||^2 + noise  (DKT_regression.py:90-93) */
+int dktb_gp_predict_var(const float* kx, long kx_class_stride, const float* kss, long kss_class_stride,
+                        const float* linv, const float* raw_outputscale, const float* raw_noise, float* var, int E,
+                        int C, int M, int N, cudaStream_t stream);
+
 /* ---- optimiser (torch.optim.Adam, methods/DKT.py:114-115,164) ---------------------------------------- */
 int dktb_adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2,
                    float eps, int step, float grad_scale, cudaStream_t stream);

@@ -21,6 +21,9 @@ def load_oracle_params(model, oracle):
     for c, m in enumerate(model.model.models):
         m.covar_module.raw_outputscale.data.fill_(float(oracle.gp["raw_outputscale"][c]))
         m.mean_module.constant.data.fill_(float(oracle.gp["constant"][c]))
+        for nm in ("raw_variance", "raw_lengthscale", "raw_offset"):
+            if nm in oracle.gp and hasattr(m.covar_module.base_kernel, nm):
+                getattr(m.covar_module.base_kernel, nm).data.fill_(float(oracle.gp[nm][c]))
 
 
 def model_cpu_sync(model, oracle, dev):
@@ -46,6 +49,11 @@ def check_train_step(model_factory, dev, image_size=32, n_way=2, n_support=1, n_
     # non-trivial GP hyper-parameters / affine parameters so that every gradient path is exercised
     oracle.gp["raw_outputscale"] = torch.linspace(-0.3, 0.6, n_way)
     oracle.gp["constant"] = torch.linspace(0.1, -0.2, n_way)
+    for nm in ("raw_lengthscale", "raw_offset"):
+        if nm in oracle.gp:
+            oracle.gp[nm] = torch.linspace(1.5, 2.5, n_way) if nm == "raw_lengthscale" else torch.linspace(0.2, 0.6, n_way)
+    if kernel == "linear":
+        oracle.gp["raw_variance"] = torch.linspace(-0.2, 0.4, n_way)
     g = torch.Generator().manual_seed(5)
     for k in oracle.bb:
         if k.endswith("BN.weight") or k.endswith("bn_out.weight"):
@@ -120,6 +128,10 @@ def check_train_step(model_factory, dev, image_size=32, n_way=2, n_support=1, n_
         upd("g.outputscale", rel_err(gos, r64["grads"]["raw_outputscale"]),
             rel_err(ref["grads"]["raw_outputscale"], r64["grads"]["raw_outputscale"]))
         upd("g.constant", rel_err(gct, r64["grads"]["constant"]), rel_err(ref["grads"]["constant"], r64["grads"]["constant"]))
+        for nm in ("raw_variance", "raw_lengthscale", "raw_offset"):
+            if nm in ref["grads"]:
+                gp_ = torch.stack([getattr(m.covar_module.base_kernel, nm).grad.view(()) for m in model.model.models])
+                upd("g." + nm, rel_err(gp_, r64["grads"][nm]), rel_err(ref["grads"][nm], r64["grads"][nm]))
         # monitoring (steps 5-6): after Adam the two sides differ by +-lr sign flips of noise-level gradients
         # (conv biases), so the strict check re-synchronises the post-update weights from the oracle and
         # re-runs the device monitoring, which still holds the pre-update train-mode features

@@ -314,3 +314,99 @@ def check_conv3x3_wgrad_tc(lib, dev, B=3, H=6, W=5, seed=31, rtol=2e-5):
     assert int(err.item()) == 0, "pipeline time-out"
     _close(dw, wr.grad, rtol=rtol, atol=1e-5, what="tc wgrad")
     _close(db, br.grad, rtol=rtol, atol=1e-4, what="tc bgrad")
+
+
+KIND = {"linear": 0, "rbf": 1, "matern": 2, "poli1": 3, "poli2": 4}
+PARAM_NAME = {"linear": "raw_variance", "rbf": "raw_lengthscale", "matern": "raw_lengthscale", "poli1": "raw_offset",
+              "poli2": "raw_offset"}
+
+
+def check_gp_family(lib, dev, kernel, E=2, C=3, per_class=3, D=12, M=7, seed=40, rtol=3e-4):
+    """Kernel family (linear / rbf / matern / poli1 / poli2): centre -> Gram -> kernel epilogue -> gp_fit -> backward
+    through the epilogue and the Gram, prediction with mean and variance -- against the oracle's autograd."""
+    g = torch.Generator().manual_seed(seed)
+    N = C * per_class
+    scale = 0.6 if kernel in ("rbf", "matern") else 0.4
+    z = torch.randn(E, N, D, generator=g) * scale
+    zt = torch.randn(E, M, D, generator=g) * scale
+    targets = -torch.ones(C, N)
+    for c in range(C):
+        targets[c, c * per_class:(c + 1) * per_class] = 1.0
+    p = ogp.default_gp_params(kernel, C, D)
+    pn = PARAM_NAME[kernel]
+    p["raw_outputscale"] = torch.linspace(-0.4, 0.5, C)
+    p["constant"] = torch.linspace(-0.1, 0.2, C)
+    p[pn] = torch.linspace(0.3, 1.2, C)
+    zr = z.clone().requires_grad_(True)
+    for k in ("raw_outputscale", "constant", pn):
+        p[k].requires_grad_(True)
+    losses = [ogp.mll_loss(kernel, zr[e], targets, p) for e in range(E)]
+    (sum(losses) / E).backward()
+    kind = KIND[kernel]
+    centred = kernel in ("rbf", "matern")
+    zd = z.to(dev)
+    xc = torch.empty_like(zd)
+    if centred:
+        lib.center_rows(zd, zd, xc, E, N, N, D, 0)
+    else:
+        xc = zd
+    gram = torch.empty(E, N, N, device=dev)
+    lib.gram(xc, xc, gram, E, N, N, D, 0)
+    sq = torch.empty(E, N, device=dev)
+    lib.row_sqnorm(xc, sq, E * N, D, 0)
+    rp = p[pn].detach().to(dev)
+    kb = torch.empty(E, C, N, N, device=dev)
+    lib.kernel_fwd(kind, gram, sq, sq, rp, kb, E, C, N, N, 0)
+    alpha = torch.empty(E, C, N, device=dev)
+    linv = torch.empty(E, C, N, N, device=dev)
+    lt = torch.empty(E, C, device=dev)
+    info = torch.ones(E, C, device=dev, dtype=torch.int32)
+    dk = torch.empty(E, C, N, N, device=dev)
+    dh = torch.empty(E, C, 3, device=dev)
+    ros, cst, rn = (p[k].detach().to(dev) for k in ("raw_outputscale", "constant", "raw_noise"))
+    lib.gp_fit(kb, N * N, targets.to(dev), 0, ros, cst, rn, alpha, linv, lt, info, dk, dh, 1.0 / E, 0.0, E, C, N, 0)
+    assert int(info.cpu().abs().sum()) == 0
+    loss = torch.empty(E, device=dev)
+    hyper = torch.empty(C, 3, device=dev)
+    lib.gp_reduce(lt, dh, loss, hyper, E, C, 0)
+    _close(loss, torch.stack([l.detach() for l in losses]), rtol=rtol, what=kernel + " loss")
+    _close(hyper[:, 0], p["raw_outputscale"].grad, rtol=rtol, atol=1e-6, what=kernel + " d outputscale")
+    _close(hyper[:, 1], p["constant"].grad, rtol=rtol, atol=1e-6, what=kernel + " d constant")
+    dg = torch.empty(E, N, N, device=dev)
+    dparam = torch.empty(C, device=dev)
+    scratch = torch.empty(E * C * N, device=dev)
+    lib.kernel_bwd(kind, gram, sq, rp, dk, dg, dparam, scratch, E, C, N, 0)
+    _close(dparam, p[pn].grad, rtol=rtol, atol=1e-6, what=kernel + " d " + pn)
+    dz = torch.empty(E, N, D, device=dev)
+    lib.gram_bwd(dg, xc, dz, E, 1, N, D, 1.0, 0)
+    _close(dz, zr.grad, rtol=rtol, atol=1e-6, what=kernel + " d z")
+    # prediction: mean + variance
+    ztd = zt.to(dev)
+    xtc = torch.empty_like(ztd)
+    if centred:
+        lib.center_rows(ztd, zd, xtc, E, M, N, D, 0)
+    else:
+        xtc = ztd
+    gx = torch.empty(E, M, N, device=dev)
+    lib.gram(xtc, xc, gx, E, M, N, D, 0)
+    sqt = torch.empty(E, M, device=dev)
+    lib.row_sqnorm(xtc, sqt, E * M, D, 0)
+    kx = torch.empty(E, C, M, N, device=dev)
+    lib.kernel_fwd(kind, gx, sqt, sq, rp, kx, E, C, M, N, 0)
+    mean = torch.empty(E, C, M, device=dev)
+    pred = torch.empty(E, M, device=dev, dtype=torch.int32)
+    lib.gp_predict(kx, M * N, alpha, ros, cst, mean, pred, E, C, M, N, 0)
+    # k(x*,x*) diagonal: kernel epilogue on the 1x1 "Gram" ||x*||^2
+    kss = torch.empty(E, C, M, device=dev)
+    for c in range(C):
+        tmp = torch.empty(E * M, 1, 1, 1, device=dev)
+        lib.kernel_fwd(kind, sqt.view(E * M, 1, 1).contiguous(), sqt.view(E * M, 1).contiguous(),
+                       sqt.view(E * M, 1).contiguous(), rp[c:c + 1].contiguous(), tmp, E * M, 1, 1, 1, 0)
+        kss[:, c, :] = tmp.view(E, M)
+    var = torch.empty(E, C, M, device=dev)
+    lib.gp_predict_var(kx, M * N, kss.contiguous(), M, linv, ros, rn, var, E, C, M, N, 0)
+    with torch.no_grad():
+        pd = {k: v.detach() for k, v in p.items()}
+        ref = [ogp.predict(kernel, z[e], targets, zt[e], pd, want_var=True) for e in range(E)]
+    _close(mean, torch.stack([r[0] for r in ref]), rtol=rtol, atol=1e-5, what=kernel + " mean")
+    _close(var, torch.stack([r[1] for r in ref]), rtol=rtol, atol=1e-5, what=kernel + " variance")

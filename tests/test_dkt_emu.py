@@ -25,6 +25,13 @@ def test_train_step_and_correct_match_oracle(lib):
     dkt_checks.check_correct(model, oracle, torch.device("cpu"))
 
 
+@pytest.mark.parametrize("kernel", ["rbf", "linear"])
+def test_train_step_other_kernels(lib, kernel):
+    model, oracle, worst = dkt_checks.check_train_step(lambda: backbone.ConvNet(4, image_size=16), torch.device("cpu"),
+                                                       image_size=16, lib=lib, kernel=kernel, steps=1)
+    dkt_checks.check_correct(model, oracle, torch.device("cpu"), image_size=16)
+
+
 def test_product_refuses_cpu_without_library():
     from deep_kernel_transfer_b200.methods.DKT import DKT
     m = DKT(backbone.Conv4, 2, 1)

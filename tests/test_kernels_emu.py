@@ -50,3 +50,8 @@ def test_gp(lib):
 
 def test_adam(lib):
     kc.check_adam(lib, DEV)
+
+
+@pytest.mark.parametrize("kernel", ["linear", "rbf", "matern", "poli1", "poli2"])
+def test_gp_family(lib, kernel):
+    kc.check_gp_family(lib, DEV, kernel)
