@@ -52,6 +52,12 @@ SIGNATURES = {
     "dktb_kernel_fwd": ("ipppppiiiis", ctypes.c_int),
     "dktb_kernel_bwd": ("ipppppppiiis", ctypes.c_int),
     "dktb_gp_predict_var": ("plplppppiiiis", ctypes.c_int),
+    "dktb_conv2d_out_size": ("iiiii", ctypes.c_int),
+    "dktb_conv2d_fwd": ("ppppiiiiiiiiiiis", ctypes.c_int),
+    "dktb_conv2d_dgrad": ("ppppiiiiiiiiiiis", ctypes.c_int),
+    "dktb_conv2d_wgrad_nsplit": ("l", ctypes.c_int),
+    "dktb_conv2d_wgrad": ("ppppppiiiiiiiiiiis", ctypes.c_int),
+    "dktb_nchw_to_nhwc": ("ppiiiis", ctypes.c_int),
     "dktb_adam_step": ("pppplffffifs", ctypes.c_int),
     "dktb_scale": ("plfs", ctypes.c_int),
 }

@@ -116,8 +116,8 @@ class ConvNet(nn.Module):
 
 def _not_on_hot_path(name):
     def factory(*a, **k):
-        raise NotImplementedError(name + " belongs to other few-shot methods (RelationNet / omniglot) and is outside "
-                                  "the DKT hot path this package implements")
+        raise NotImplementedError(name + " is not on the dktb200 CUDA path (Conv4 / Conv6 / Conv3 are); there is no "
+                                  "CPU or cuDNN fallback")
     factory.__name__ = name
     return factory
 
@@ -139,7 +139,43 @@ ResNet18 = _not_on_hot_path("ResNet18")
 ResNet34 = _not_on_hot_path("ResNet34")
 ResNet50 = _not_on_hot_path("ResNet50")
 ResNet101 = _not_on_hot_path("ResNet101")
-Conv3 = _not_on_hot_path("Conv3")
+
+
+class Conv3(nn.Module):
+    """Backbone of the QMUL head-pose regression (reference backbone.py:379-402).  Parameter containers + engine."""
+
+    def __init__(self):
+        super().__init__()
+        self.layer1 = nn.Conv2d(3, 36, 3, stride=2, dilation=2)
+        self.layer2 = nn.Conv2d(36, 36, 3, stride=2, dilation=2)
+        self.layer3 = nn.Conv2d(36, 36, 3, stride=2, dilation=2)
+        self._engine = None
+
+    def return_clones(self):
+        return [l.weight.data.clone().detach() for l in (self.layer1, self.layer2, self.layer3)]
+
+    def assign_clones(self, weights_list):
+        for l, w in zip((self.layer1, self.layer2, self.layer3), weights_list):
+            l.weight.data.copy_(w)
+
+    def layers(self):
+        return (self.layer1, self.layer2, self.layer3)
+
+    def engine(self, device, lib=None):
+        from .engine import Conv3Engine
+        dev = torch.device(device)
+        if self._engine is None or self._engine.dev != dev:
+            self._engine = Conv3Engine(lib or _lib.load(), dev)
+        return self._engine
+
+    def forward(self, x):
+        """x [n,3,100,100] on a CUDA device -> [n, 2916] in the reference's NCHW-flatten order."""
+        if x.device.type != "cuda":
+            raise RuntimeError("dktb200 has no CPU path: move the input to a CUDA device")
+        eng = self.engine(x.device)
+        f = eng.forward(x.contiguous().float(), [l.weight.data for l in self.layers()], [l.bias.data for l in self.layers()])
+        n = x.shape[0]
+        return f.view(n, eng.P, 36).transpose(1, 2).reshape(n, -1)
 
 # class attributes train.py:163-167 pokes for MAML (kept so the driver imports cleanly)
 class SimpleBlock:      # noqa: E302

@@ -39,6 +39,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   __shared__ int s_err;
   __shared__ float s_valid[kRows];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (*reinterpret_cast<volatile int*>(err) != 0) return;   // a time-out was already reported: do not pile up waits
   const int Hp = H + 2, Wp = W + 2;
   const int img = blockIdx.y;
   const int q0 = (Wp + 1) + blockIdx.x * kRows;
@@ -66,11 +67,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      for (int it = 0; it < kIters; ++it) {
-        const int s = it % kStages, ph = (it / kStages) & 1;
-        const int tap = it >> 1, half = it & 1;
-        if (!tc::mbar_wait(&bar_empty[s], ph ^ 1)) { s_err = 1; break; }
+    for (int it = 0; it < kIters; ++it) {
+      const int s = it % kStages, ph = (it / kStages) & 1;
+      const int tap = it >> 1, half = it & 1;
+      if (!tc::mbar_wait(&bar_empty[s], ph ^ 1)) { s_err = 1; break; }
+      if (tc::elect_one()) {
         unsigned char* st = smem + s * kStageBytes;
         tc::mbar_expect_tx(&bar_full[s], 16384 + 8192 + 8192);
         const int row = (int)(img_base + q0 - (Wp + 1) + (tap / 3) * Wp + (tap % 3));
@@ -78,10 +79,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         tc::tma_load_2d(st + kOffWHi, &map_w, &bar_full[s], half * 32, tap * 64);
         tc::tma_load_2d(st + kOffWLo, &map_w, &bar_full[s], half * 32, (9 + tap) * 64);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (warp-converged, one elected lane)
+    {
       const uint32_t idesc = tc::umma_idesc(2, 128, 64, 0, 0);
       bool ok = true;
       for (int it = 0; it < kIters && ok; ++it) {
@@ -90,6 +92,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         if (!ok) break;
         tc::tcgen05_fence_after();
         const uint32_t base = tc::smem_u32(smem + s * kStageBytes);
+        if (tc::elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint64_t a_hi = tc::umma_desc_sw128(base + k * 32, 16, 1024);
@@ -101,9 +104,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           tc::umma_tf32_ss(d_tmem, a_hi, w_hi, idesc, 1u);
         }
         tc::umma_commit(&bar_empty[s]);
+        }
+        __syncwarp();
       }
       if (!ok) s_err = 1;
-      tc::umma_commit(&bar_acc);
+      if (tc::elect_one()) tc::umma_commit(&bar_acc);
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------------ splitter warps (128 threads)
@@ -213,6 +219,7 @@ conv3x3_tc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   __shared__ int s_err;
   __shared__ float s_valid[kRows];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (*reinterpret_cast<volatile int*>(err) != 0) return;   // a time-out was already reported: do not pile up waits
   const int Hp = H + 2, Wp = W + 2;
   const int img = blockIdx.y;
   const int q0 = (Wp + 1) + blockIdx.x * kRows;
@@ -238,23 +245,27 @@ conv3x3_tc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   const uint32_t a_tmem = s_tmem + 64;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       tc::mbar_expect_tx(&bar_halo, 2 * half_bytes);
       const int row0 = (int)(img_base + q0 - (Wp + 1));
       for (int h = 0; h < 2; ++h)
         for (int r = 0; r < halo_rows_pad; r += kHaloBox)
           tc::tma_load_2d(s_halo + h * half_bytes + r * 128, &map_a, &bar_halo, h * 32, row0 + r);
-      for (int it = 0; it < kIters; ++it) {
-        const int s = it % kWStages, ph = (it / kWStages) & 1;
-        const int tap = it >> 1, half = it & 1;
-        if (!tc::mbar_wait(&bar_wempty[s], ph ^ 1)) { s_err = 1; break; }
+    }
+    __syncwarp();
+    for (int it = 0; it < kIters; ++it) {
+      const int s = it % kWStages, ph = (it / kWStages) & 1;
+      const int tap = it >> 1, half = it & 1;
+      if (!tc::mbar_wait(&bar_wempty[s], ph ^ 1)) { s_err = 1; break; }
+      if (tc::elect_one()) {
         tc::mbar_expect_tx(&bar_wfull[s], kWStageBytes);
         tc::tma_load_2d(s_w + s * kWStageBytes, &map_w, &bar_wfull[s], half * 32, tap * 64);
         tc::tma_load_2d(s_w + s * kWStageBytes + 8192, &map_w, &bar_wfull[s], half * 32, (9 + tap) * 64);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = tc::umma_idesc(2, 128, 64, 0, 0);
       bool ok = true;
       for (int it = 0; it < kIters && ok; ++it) {
@@ -265,6 +276,7 @@ conv3x3_tc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         tc::tcgen05_fence_after();
         const uint32_t wbase = tc::smem_u32(s_w + sw * kWStageBytes);
         const uint32_t acol = a_tmem + sa * 64;
+        if (tc::elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint64_t w_hi = tc::umma_desc_sw128(wbase + k * 32, 16, 1024);
@@ -275,9 +287,12 @@ conv3x3_tc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         }
         tc::umma_commit(&bar_aempty[sa]);
         tc::umma_commit(&bar_wempty[sw]);
+        }
+        __syncwarp();
       }
       if (!ok) s_err = 1;
-      tc::umma_commit(&bar_acc);
+      if (tc::elect_one()) tc::umma_commit(&bar_acc);
+      __syncwarp();
     }
   } else {
     const int ct = tid - 64;                                 // 0..255
@@ -385,6 +400,7 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   __shared__ int s_err;
   __shared__ float s_bias[4][64];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (*reinterpret_cast<volatile int*>(err) != 0) return;   // a time-out was already reported: do not pile up waits
   const int x_half_bytes = halo_pad * 128;
   const int stage_bytes = 2 * x_half_bytes + 8192 + 16384;   // X raw | G raw | B hi | B lo
   const long nkb = (total_rows + kKR - 1) / kKR;
@@ -409,11 +425,11 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   const uint32_t a_tmem = tmem + 320;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int n = 0;
-      for (long kb = blockIdx.x; kb < nkb; kb += gridDim.x, ++n) {
-        const int s = n & 1, ph = (n >> 1) & 1;
-        if (!tc::mbar_wait(&bar_raw_empty[s], ph ^ 1)) { s_err = 1; break; }
+    int n = 0;
+    for (long kb = blockIdx.x; kb < nkb; kb += gridDim.x, ++n) {
+      const int s = n & 1, ph = (n >> 1) & 1;
+      if (!tc::mbar_wait(&bar_raw_empty[s], ph ^ 1)) { s_err = 1; break; }
+      if (tc::elect_one()) {
         unsigned char* st = smem + s * stage_bytes;
         tc::mbar_expect_tx(&bar_raw_full[s], 2 * x_half_bytes + 8192);
         const long q0 = kb * kKR;
@@ -424,9 +440,10 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
           tc::tma_load_2d(st + 2 * x_half_bytes + h * 4096, &map_g, &bar_raw_full[s], h * 32, (int)q0);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = tc::umma_idesc(2, 128, 64, 0, 0);
       bool ok = true;
       int n = 0, ai = 0;
@@ -442,6 +459,7 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
           tc::tcgen05_fence_after();
           const uint32_t acol = a_tmem + sa * 64;
           const uint32_t dcol = tmem + g * 64;
+          if (tc::elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t b_hi = tc::umma_desc_sw128(bbase + k * 32, 16, 1024);
@@ -451,11 +469,15 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             tc::umma_tf32_ts(dcol, acol + k * 8, b_hi, idesc, 1u);
           }
           tc::umma_commit(&bar_aempty[sa]);
+          }
+          __syncwarp();
         }
-        tc::umma_commit(&bar_raw_empty[s]);
+        if (tc::elect_one()) tc::umma_commit(&bar_raw_empty[s]);
+        __syncwarp();
       }
       if (!ok) s_err = 1;
-      tc::umma_commit(&bar_acc);
+      if (tc::elect_one()) tc::umma_commit(&bar_acc);
+      __syncwarp();
     }
   } else {
     const int ct = tid - 64;                                  // 0..255

@@ -187,6 +187,66 @@ class ConvNetEngine:
                 gout = ws["gact"][i - 1]
 
 
+class Conv3Engine:
+    """Conv3 of the QMUL regression path (reference backbone.py:379-402): three 3x3 / stride 2 / dilation 2 un-padded
+    convolutions, each followed by ReLU, then flatten.  NHWC generic-convolution kernels (csrc/conv_generic.cu)."""
+
+    CH = 36
+
+    def __init__(self, lib, device="cuda"):
+        self.lib, self.dev = lib, torch.device(device)
+        self.key = None
+
+    def _alloc(self, n, H, W):
+        lib, dev, f32 = self.lib, self.dev, torch.float32
+        sizes = [(H, W)]
+        for _ in range(3):
+            h, w = sizes[-1]
+            sizes.append((lib.conv2d_out_size(h, 3, 2, 0, 2), lib.conv2d_out_size(w, 3, 2, 0, 2)))
+        self.sizes = sizes
+        self.x_nhwc = torch.empty(n, H, W, 3, device=dev, dtype=f32)
+        self.act = [torch.empty(n, h, w, self.CH, device=dev, dtype=f32) for (h, w) in sizes[1:]]
+        self.gact = [torch.empty(n, h, w, self.CH, device=dev, dtype=f32) for (h, w) in sizes[1:3]]
+        big = 0
+        for i in range(3):
+            cin = 3 if i == 0 else self.CH
+            ho, wo = sizes[i + 1]
+            big = max(big, lib.conv2d_wgrad_nsplit(n * ho * wo) * 9 * cin * self.CH)
+        self.scratch = torch.empty(big, device=dev, dtype=f32)
+        self.D = sizes[3][0] * sizes[3][1] * self.CH
+        self.P = sizes[3][0] * sizes[3][1]
+        self.key = (n, H, W)
+
+    def forward(self, x, weights, biases):
+        """x [n,3,H,W] NCHW -> features [n, D] (NHWC-flattened view)."""
+        n, _, H, W = x.shape
+        if self.key != (n, H, W):
+            self._alloc(n, H, W)
+        lib, st = self.lib, _stream(self.dev)
+        lib.nchw_to_nhwc(x, self.x_nhwc, n, 3, H, W, st)
+        src = self.x_nhwc
+        for i in range(3):
+            h, w = self.sizes[i]
+            lib.conv2d_fwd(src, weights[i], biases[i], self.act[i], n, h, w, 3 if i == 0 else self.CH, self.CH, 3, 3, 2, 0,
+                           2, 1, st)
+            src = self.act[i]
+        return self.act[2].view(n, self.D)
+
+    def backward(self, gfeat, weights, gw, gb):
+        """gfeat [n, D]; fills gw[i] / gb[i] (reference layout)."""
+        n = self.key[0]
+        lib, st = self.lib, _stream(self.dev)
+        g = gfeat.view(self.act[2].shape)
+        for i in (2, 1, 0):
+            h, w = self.sizes[i]
+            cin = 3 if i == 0 else self.CH
+            src = self.x_nhwc if i == 0 else self.act[i - 1]
+            lib.conv2d_wgrad(src, g, self.act[i], gw[i], gb[i], self.scratch, n, h, w, cin, self.CH, 3, 3, 2, 0, 2, 1, st)
+            if i > 0:
+                lib.conv2d_dgrad(g, self.act[i], weights[i], self.gact[i - 1], n, h, w, cin, self.CH, 3, 3, 2, 0, 2, 1, st)
+                g = self.gact[i - 1]
+
+
 class GPHeadParams:
     """Tensors of the GP head: bn_out (optional) + per-class raw hyper-parameters."""
 

@@ -69,6 +69,21 @@ int dktb_conv3x3_wgrad_tc(const float* a, const float* gy, float* dw, float* db,
                           int W, cudaStream_t stream);
 int dktb_conv3x3_wgrad_reduce(const float* partial, int nsplit, float* dw, float* db, cudaStream_t stream);
 
+/* Generic NHWC fp32 convolution (any Cin/Cout, RxS, stride, padding, dilation) for the layers outside the 64->64 3x3
+ * case: Conv3 of the regression path (backbone.py:379-402) and strided / 1x1 / 7x7 ResNet layers.  Weights in the
+ * reference layout [Cout][Cin][R][S].  relu != 0: forward applies ReLU; dgrad / wgrad then take the forward output
+ * `yout` and mask gy with it.  wgrad scratch: dktb_conv2d_wgrad_nsplit(N*Ho*Wo)*R*S*Cin*Cout floats. */
+int dktb_conv2d_out_size(int H, int R, int stride, int pad, int dil);
+int dktb_conv2d_fwd(const float* x, const float* w, const float* bias, float* out, int N, int H, int W, int Cin,
+                    int Cout, int R, int S, int stride, int pad, int dil, int relu, cudaStream_t stream);
+int dktb_conv2d_dgrad(const float* gy, const float* yout, const float* w, float* gx, int N, int H, int W, int Cin,
+                      int Cout, int R, int S, int stride, int pad, int dil, int relu, cudaStream_t stream);
+int dktb_conv2d_wgrad_nsplit(long npix);
+int dktb_conv2d_wgrad(const float* x, const float* gy, const float* yout, float* dw, float* db, float* scratch, int N,
+                      int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int dil, int relu,
+                      cudaStream_t stream);
+int dktb_nchw_to_nhwc(const float* x, float* out, int N, int C, int H, int W, cudaStream_t stream);
+
 /* BatchNorm2d statistics (train: per-episode batch stats from the conv partial sums + running-stat EMA,
  * momentum 0.1, unbiased running variance; eval: running stats).  scratch_d: dktb_bn_scratch_doubles(B/ipe). */
 long dktb_bn_scratch_doubles(int E);

@@ -410,3 +410,35 @@ def check_gp_family(lib, dev, kernel, E=2, C=3, per_class=3, D=12, M=7, seed=40,
         ref = [ogp.predict(kernel, z[e], targets, zt[e], pd, want_var=True) for e in range(E)]
     _close(mean, torch.stack([r[0] for r in ref]), rtol=rtol, atol=1e-5, what=kernel + " mean")
     _close(var, torch.stack([r[1] for r in ref]), rtol=rtol, atol=1e-5, what=kernel + " variance")
+
+
+def check_conv2d(lib, dev, N=2, H=13, W=11, Cin=3, Cout=36, R=3, stride=2, pad=0, dil=2, relu=1, seed=50):
+    """Generic NHWC convolution forward / dgrad / wgrad (+ fused ReLU) against torch autograd."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, R, R, generator=g) * 0.2
+    b = torch.randn(Cout, generator=g) * 0.1
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.conv2d(xr, wr, br, stride=stride, padding=pad, dilation=dil)
+    if relu:
+        ref = F.relu(ref)
+    gy = torch.randn(ref.shape, generator=g)
+    (ref * gy).sum().backward()
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    assert lib.conv2d_out_size(H, R, stride, pad, dil) == Ho
+    x_nhwc = torch.empty(N, H, W, Cin, device=dev)
+    lib.nchw_to_nhwc(x.to(dev), x_nhwc, N, Cin, H, W, 0)
+    out = torch.empty(N, Ho, Wo, Cout, device=dev)
+    lib.conv2d_fwd(x_nhwc, w.to(dev), b.to(dev), out, N, H, W, Cin, Cout, R, R, stride, pad, dil, relu, 0)
+    _close(out.cpu().permute(0, 3, 1, 2), ref.detach(), what="conv2d fwd")
+    gyd = gy.permute(0, 2, 3, 1).contiguous().to(dev)
+    gx = torch.empty(N, H, W, Cin, device=dev)
+    lib.conv2d_dgrad(gyd, out, w.to(dev), gx, N, H, W, Cin, Cout, R, R, stride, pad, dil, relu, 0)
+    _close(gx.cpu().permute(0, 3, 1, 2), xr.grad, rtol=1e-4, atol=1e-5, what="conv2d dgrad")
+    dw = torch.empty(Cout, Cin, R, R, device=dev)
+    db = torch.empty(Cout, device=dev)
+    ns = lib.conv2d_wgrad_nsplit(N * Ho * Wo)
+    scratch = torch.empty(ns * R * R * Cin * Cout, device=dev)
+    lib.conv2d_wgrad(x_nhwc, gyd, out, dw, db, scratch, N, H, W, Cin, Cout, R, R, stride, pad, dil, relu, 0)
+    _close(dw, wr.grad, rtol=1e-4, atol=1e-4, what="conv2d wgrad")
+    _close(db, br.grad, rtol=1e-4, atol=1e-4, what="conv2d bgrad")

@@ -55,3 +55,9 @@ def test_adam(lib):
 @pytest.mark.parametrize("kernel", ["linear", "rbf", "matern", "poli1", "poli2"])
 def test_gp_family(lib, kernel):
     kc.check_gp_family(lib, DEV, kernel)
+
+
+@pytest.mark.parametrize("cfg", [dict(), dict(Cin=36, Cout=36, H=12, W=12), dict(Cin=5, Cout=70, R=1, stride=2, dil=1, relu=0),
+                                 dict(Cin=3, Cout=20, R=7, stride=2, pad=3, dil=1, relu=0, H=17, W=15)])
+def test_conv2d_generic(lib, cfg):
+    kc.check_conv2d(lib, DEV, **cfg)
