@@ -123,7 +123,7 @@ class DKT(nn.Module):
             p.grad.copy_(g)
 
     def train_step(self, inputs, labels):
-        """One person (DKT_regression.py:48-57, minus optimizer.zero_grad/step): returns (loss, mse) device scalars and
+        """One person (DKT_regression.py:48-57, minus optimizer.zero_grad/step): returns the loss (device scalar) and
         leaves the gradients in ``param.grad``."""
         lib = self._lib_get()
         fe = self.feature_extractor
@@ -148,10 +148,8 @@ class DKT(nn.Module):
         self._set_grad(m.mean_module.constant, w["hyper"][0, 1])
         self._set_grad(self.likelihood.noise_covar.raw_noise, w["hyper"][0, 2])
         self._set_grad(m.covar_module.base_kernel.raw_lengthscale, w["dparam"])
-        # `predictions.mean` of the prior in train mode is the constant mean (DKT_regression.py:58)
-        mse = ((m.mean_module.constant.data.view(()) - labels.float()) ** 2).mean()
         self._last_info = w["info"]
-        return w["loss"][0].clone(), mse
+        return w["loss"][0].clone()
 
     def train_loop(self, epoch, optimizer):
         get_batch, people = self._batch_source("train")
@@ -160,8 +158,10 @@ class DKT(nn.Module):
         batch, batch_labels = batch.to(dev), batch_labels.to(dev)
         for inputs, labels in zip(batch, batch_labels):
             optimizer.zero_grad()
-            loss, mse = self.train_step(inputs, labels)
+            loss = self.train_step(inputs, labels)
             optimizer.step()
+            # `predictions.mean` of the train-mode prior is a view of the constant-mean parameter (DKT_regression.py:58)
+            mse = ((self.model.mean_module.constant.data.view(()) - labels.float()) ** 2).mean()
             if epoch % 10 == 0:
                 check_info(self._last_info)
                 print('[%d] - Loss: %.3f  MSE: %.3f noise: %.3f' % (epoch, loss.item(), mse.item(),

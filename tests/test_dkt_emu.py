@@ -37,3 +37,21 @@ def test_product_refuses_cpu_without_library():
     m = DKT(backbone.Conv4, 2, 1)
     with pytest.raises(RuntimeError):
         m._ensure_packed()
+
+
+def test_regression_matches_oracle(lib):
+    model = dkt_checks.check_regression(torch.device("cpu"), lib=lib)
+    # the reference's train_loop / test_loop drive it through a batch source + the caller's optimizer
+    def get_batch(people):
+        g = torch.Generator().manual_seed(11)
+        return torch.randn(2, 19, 3, 36, 36, generator=g), torch.rand(2, 19, generator=g) * 2 - 1
+    model._get_batch = get_batch
+    opt = torch.optim.Adam([{"params": model.model.parameters(), "lr": 1e-3},
+                            {"params": model.feature_extractor.parameters(), "lr": 1e-3}])
+    before = model.feature_extractor.layer1.weight.detach().clone()
+    model.train_loop(1, opt)
+    assert not torch.equal(before, model.feature_extractor.layer1.weight.detach())
+    import numpy as np
+    np.random.seed(0)
+    mse = model.test_loop(5)
+    assert torch.isfinite(mse)

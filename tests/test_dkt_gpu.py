@@ -62,3 +62,16 @@ def test_full_size_properties():
     for _ in range(5):
         last = float(m.train_step(xs)["loss"].mean())
     assert last < first
+
+
+@pytest.mark.parametrize("kernel", ["rbf", "linear", "matern", "poli2", "cossim"])
+def test_train_step_other_kernels(kernel):
+    from deep_kernel_transfer_b200 import backbone
+    model, oracle, worst = dkt_checks.check_train_step(lambda: backbone.ConvNet(4, image_size=32), DEV, kernel=kernel, steps=1)
+    dkt_checks.check_correct(model, oracle, DEV)
+
+
+def test_regression_qmul_shape():
+    """DKT regression at the QMUL shape: 19 images of 100x100 -> Conv3 features [19, 2916], RBF GP, learned noise."""
+    model = dkt_checks.check_regression(DEV, image=100, n=19, n_support=4)
+    assert model.feature_extractor._engine.D == 2916

@@ -67,3 +67,16 @@ def test_conv3x3_wgrad_tc(lib):
     kc.check_conv3x3_wgrad_tc(lib, DEV, B=2, H=10, W=10, seed=32)
     kc.check_conv3x3_wgrad_tc(lib, DEV, B=6, H=42, W=42, seed=33)
     kc.check_conv3x3_wgrad_tc(lib, DEV, B=64, H=21, W=21, seed=34)
+
+
+@pytest.mark.parametrize("kernel", ["linear", "rbf", "matern", "poli1", "poli2"])
+def test_gp_family(lib, kernel):
+    kc.check_gp_family(lib, DEV, kernel)
+    kc.check_gp_family(lib, DEV, kernel, E=3, C=5, per_class=21, D=512, M=75, seed=41, rtol=1e-3)   # cfg4 shape (N=105, D=512)
+
+
+@pytest.mark.parametrize("cfg", [dict(), dict(Cin=36, Cout=36, H=48, W=48, N=19), dict(Cin=5, Cout=70, R=1, stride=2, dil=1, relu=0),
+                                 dict(Cin=3, Cout=64, R=7, stride=2, pad=3, dil=1, relu=0, H=56, W=56, N=3),
+                                 dict(N=19, H=100, W=100)])
+def test_conv2d_generic(lib, cfg):
+    kc.check_conv2d(lib, DEV, **cfg)
