@@ -58,6 +58,8 @@ SIGNATURES = {
     "dktb_conv2d_wgrad_nsplit": ("l", ctypes.c_int),
     "dktb_conv2d_wgrad": ("ppppppiiiiiiiiiiis", ctypes.c_int),
     "dktb_nchw_to_nhwc": ("ppiiiis", ctypes.c_int),
+    "dktb_spectral_fwd": ("pppppppiiiiiiis", ctypes.c_int),
+    "dktb_spectral_bwd": ("ppppppppppiiiiiis", ctypes.c_int),
     "dktb_adam_step": ("pppplffffifs", ctypes.c_int),
     "dktb_scale": ("plfs", ctypes.c_int),
 }

@@ -71,6 +71,18 @@ class ScaleKernel(nn.Module):
         return torch.nn.functional.softplus(self.raw_outputscale)
 
 
+class SpectralMixtureKernel(nn.Module):
+    """gpytorch.kernels.SpectralMixtureKernel(num_mixtures, ard_num_dims) parameter container (no ScaleKernel around
+    it, DKT_regression.py:122): raw_mixture_weights [Q], raw_mixture_means / raw_mixture_scales [Q,1,D], all zeros."""
+
+    def __init__(self, num_mixtures=4, ard_num_dims=2916):
+        super().__init__()
+        self.num_mixtures, self.ard_num_dims = num_mixtures, ard_num_dims
+        self.raw_mixture_weights = nn.Parameter(torch.zeros(num_mixtures))
+        self.raw_mixture_means = nn.Parameter(torch.zeros(num_mixtures, 1, ard_num_dims))
+        self.raw_mixture_scales = nn.Parameter(torch.zeros(num_mixtures, 1, ard_num_dims))
+
+
 class ExactGPLayer(nn.Module):
     """One one-vs-rest exact GP of the classifier (methods/DKT.py:337-378)."""
 

@@ -28,7 +28,7 @@ class ExactGPLayer(nn.Module):
         if kernel in ("rbf", "RBF"):
             self.covar_module = gpm.ScaleKernel("rbf")
         elif kernel == "spectral":
-            raise NotImplementedError("the spectral-mixture kernel is not on the CUDA path yet (rbf is)")
+            self.covar_module = gpm.SpectralMixtureKernel(num_mixtures=4, ard_num_dims=feat_dim)
         else:
             raise ValueError("[ERROR] the kernel '" + str(kernel) + "' is not supported for regression, use 'rbf' or 'spectral'.")
 
@@ -45,9 +45,10 @@ class _Pred:
 
 
 class DKT(nn.Module):
-    def __init__(self, backbone, kernel=None, lib=None, get_batch=None):
+    def __init__(self, backbone, kernel=None, lib=None, get_batch=None, feat_dim=2916):
         super(DKT, self).__init__()
         self.feature_extractor = backbone
+        self.feat_dim = feat_dim
         self.kernel = kernel if kernel is not None else ("rbf" if kernel_type not in ("rbf", "RBF", "spectral") else kernel_type)
         self._lib = lib
         self._get_batch = get_batch          # injection point for tests; default: the reference's data.qmul_loader
@@ -56,7 +57,7 @@ class DKT(nn.Module):
 
     def get_model_likelihood_mll(self, train_x=None, train_y=None):
         likelihood = gpm.GaussianLikelihood()                 # learned noise, default init (DKT_regression.py:29)
-        model = ExactGPLayer(likelihood, kernel=self.kernel)
+        model = ExactGPLayer(likelihood, kernel=self.kernel, feat_dim=self.feat_dim)
         self.model = model
         self.likelihood = likelihood
         self.mll = gpm.SumMarginalLogLikelihood(likelihood, model)
@@ -82,8 +83,15 @@ class DKT(nn.Module):
 
     def _hyper(self):
         m = self.model
+        if self.kernel == "spectral":
+            return (None, m.mean_module.constant.data.view(1), self.likelihood.noise_covar.raw_noise.data.view(1), None)
         return (m.covar_module.raw_outputscale.data.view(1), m.mean_module.constant.data.view(1),
                 self.likelihood.noise_covar.raw_noise.data.view(1), m.covar_module.base_kernel.raw_lengthscale.data.view(1))
+
+    def _spectral(self):
+        k = self.model.covar_module
+        Q = k.num_mixtures
+        return k.raw_mixture_weights.data, k.raw_mixture_means.data.view(Q, -1), k.raw_mixture_scales.data.view(Q, -1), Q
 
     def _work(self, N, M, D, dev):
         key = (N, M, D, str(dev))
@@ -94,6 +102,9 @@ class DKT(nn.Module):
                            dk=f(1, 1, N, N), dh=f(1, 1, 3), dg=f(1, N, N), dparam=f(1), ksc=f(N), dz=f(1, N, D),
                            xt=f(1, M, D), sqt=f(1, M), gx=f(1, M, N), kx=f(1, 1, M, N), mean=f(1, 1, M), var=f(1, 1, M),
                            kss=f(1, 1, M), loss=f(1), hyper=f(1, 3))
+            if self.kernel == "spectral":
+                Q = self.model.covar_module.num_mixtures
+                self._w.update(ec=f(1, Q, N, N), dw=f(Q), dmu=f(Q, D), dv=f(Q, D))
         return self._w
 
     def _fit(self, z, y, want_grad):
@@ -105,10 +116,15 @@ class DKT(nn.Module):
             else self._work(N, N, D, dev)
         ros, cst, rn, rl = self._hyper()
         zz = z.contiguous().view(1, N, D)
-        lib.center_rows(zz, zz, w["xc"], 1, N, N, D, st)
-        lib.gram(w["xc"], w["xc"], w["gram"], 1, N, N, D, st)
-        lib.row_sqnorm(w["xc"], w["sq"], N, D, st)
-        lib.kernel_fwd(1, w["gram"], w["sq"], w["sq"], rl, w["kb"], 1, 1, N, N, st)
+        if self.kernel == "spectral":
+            rw, rmu, rv, Q = self._spectral()
+            w["xc"].copy_(zz)
+            lib.spectral_fwd(w["xc"], w["xc"], rw, rmu, rv, w["kb"], w["ec"], 1, N, N, D, Q, 36, self._P, st)
+        else:
+            lib.center_rows(zz, zz, w["xc"], 1, N, N, D, st)
+            lib.gram(w["xc"], w["xc"], w["gram"], 1, N, N, D, st)
+            lib.row_sqnorm(w["xc"], w["sq"], N, D, st)
+            lib.kernel_fwd(1, w["gram"], w["sq"], w["sq"], rl, w["kb"], 1, 1, N, N, st)
         lib.gp_fit(w["kb"], N * N, y.contiguous().view(1, 1, N), N, ros, cst, rn, w["alpha"], w["linv"], w["lt"], w["info"],
                    w["dk"] if want_grad else None, w["dh"] if want_grad else None, 1.0, 0.0, 1, 1, N, st)
         lib.gp_reduce(w["lt"], w["dh"] if want_grad else None, w["loss"], w["hyper"] if want_grad else None, 1, 1, st)
@@ -132,11 +148,17 @@ class DKT(nn.Module):
         bs = [l.bias.data for l in fe.layers()]
         z = eng.forward(inputs.contiguous().float(), ws, bs)
         N, D = z.shape
+        self._P = eng.P
         w = self._fit(z, labels.float(), want_grad=True)
         st = _stream(inputs.device)
         ros, cst, rn, rl = self._hyper()
-        lib.kernel_bwd(1, w["gram"], w["sq"], rl, w["dk"], w["dg"], w["dparam"], w["ksc"], 1, 1, N, st)
-        lib.gram_bwd(w["dg"], w["xc"], w["dz"], 1, 1, N, D, 1.0, st)
+        if self.kernel == "spectral":
+            rw, rmu, rv, Q = self._spectral()
+            lib.spectral_bwd(w["xc"], rw, rmu, rv, w["dk"], w["ec"], w["dw"], w["dmu"], w["dv"], w["dz"], 1, N, D, Q, 36,
+                             self._P, st)
+        else:
+            lib.kernel_bwd(1, w["gram"], w["sq"], rl, w["dk"], w["dg"], w["dparam"], w["ksc"], 1, 1, N, st)
+            lib.gram_bwd(w["dg"], w["xc"], w["dz"], 1, 1, N, D, 1.0, st)
         gw = [torch.empty_like(t) for t in ws]
         gb = [torch.empty_like(t) for t in bs]
         eng.backward(w["dz"].view(N, D), ws, gw, gb)
@@ -144,10 +166,15 @@ class DKT(nn.Module):
             self._set_grad(l.weight, a)
             self._set_grad(l.bias, b)
         m = self.model
-        self._set_grad(m.covar_module.raw_outputscale, w["hyper"][0, 0])
         self._set_grad(m.mean_module.constant, w["hyper"][0, 1])
         self._set_grad(self.likelihood.noise_covar.raw_noise, w["hyper"][0, 2])
-        self._set_grad(m.covar_module.base_kernel.raw_lengthscale, w["dparam"])
+        if self.kernel == "spectral":
+            self._set_grad(m.covar_module.raw_mixture_weights, w["dw"])
+            self._set_grad(m.covar_module.raw_mixture_means, w["dmu"])
+            self._set_grad(m.covar_module.raw_mixture_scales, w["dv"])
+        else:
+            self._set_grad(m.covar_module.raw_outputscale, w["hyper"][0, 0])
+            self._set_grad(m.covar_module.base_kernel.raw_lengthscale, w["dparam"])
         self._last_info = w["info"]
         return w["loss"][0].clone()
 
@@ -185,16 +212,22 @@ class DKT(nn.Module):
         z_q = eng.forward(x_query.contiguous().float(), ws, bs).clone()
         N, D = z_s.shape
         M = z_q.shape[0]
+        self._P = eng.P
         self._w = None
         self._work(N, M, D, z_s.device)
         w = self._fit(z_s, y_support.float(), want_grad=False)
         ros, cst, rn, rl = self._hyper()
-        lib.center_rows(z_q.view(1, M, D), z_s.view(1, N, D), w["xt"], 1, M, N, D, st)
-        lib.gram(w["xt"], w["xc"], w["gx"], 1, M, N, D, st)
-        lib.row_sqnorm(w["xt"], w["sqt"], M, D, st)
-        lib.kernel_fwd(1, w["gx"], w["sqt"], w["sq"], rl, w["kx"], 1, 1, M, N, st)
+        if self.kernel == "spectral":
+            rw, rmu, rv, Q = self._spectral()
+            lib.spectral_fwd(z_q.view(1, M, D), w["xc"], rw, rmu, rv, w["kx"], None, 1, M, N, D, Q, 36, self._P, st)
+            w["kss"].copy_(torch.nn.functional.softplus(rw).sum().expand(1, 1, M))   # k(x*,x*) = sum_q w_q
+        else:
+            lib.center_rows(z_q.view(1, M, D), z_s.view(1, N, D), w["xt"], 1, M, N, D, st)
+            lib.gram(w["xt"], w["xc"], w["gx"], 1, M, N, D, st)
+            lib.row_sqnorm(w["xt"], w["sqt"], M, D, st)
+            lib.kernel_fwd(1, w["gx"], w["sqt"], w["sq"], rl, w["kx"], 1, 1, M, N, st)
+            w["kss"].fill_(1.0)          # k_rbf(x*, x*) = 1
         lib.gp_predict(w["kx"], M * N, w["alpha"], ros, cst, w["mean"], None, 1, 1, M, N, st)
-        w["kss"].fill_(1.0)          # k_rbf(x*, x*) = 1
         lib.gp_predict_var(w["kx"], M * N, w["kss"], M, w["linv"], ros, rn, w["var"], 1, 1, M, N, st)
         self._last_info = w["info"]
         return _Pred(w["mean"].view(M).clone(), w["var"].view(M).clone())

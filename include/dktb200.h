@@ -157,6 +157,16 @@ int dktb_gp_predict_var(const float* kx, long kx_class_stride, const float* kss,
                         const float* linv, const float* raw_outputscale, const float* raw_noise, float* var, int E,
                         int C, int M, int N, cudaStream_t stream);
 
+/* ---- spectral-mixture kernel with ARD (DKT_regression.py:122, sines/train_DKT.py:132): k = sum_q w_q prod_d
+ * exp(-2 pi^2 tau_d^2 v_qd^2) cos(2 pi tau_d mu_qd).  raw_w [Q], raw_mu / raw_v [Q][D] in the reference's feature order
+ * (index (j % Cch)*P + j / Cch for NHWC feature j; P <= 1: identity).  ec [E][Q][M][N] keeps the per-mixture terms
+ * for the backward pass.  bwd: dkb [E][N][N] -> dw [Q], dmu / dv [Q][D], dx [E][N][D]. */
+int dktb_spectral_fwd(const float* x1, const float* x2, const float* raw_w, const float* raw_mu, const float* raw_v,
+                      float* kb, float* ec, int E, int M, int N, int D, int Q, int Cch, int P, cudaStream_t stream);
+int dktb_spectral_bwd(const float* x, const float* raw_w, const float* raw_mu, const float* raw_v, const float* dkb,
+                      const float* ec, float* dw, float* dmu, float* dv, float* dx, int E, int N, int D, int Q, int Cch,
+                      int P, cudaStream_t stream);
+
 /* ---- optimiser (torch.optim.Adam, methods/DKT.py:114-115,164) ---------------------------------------- */
 int dktb_adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2,
                    float eps, int step, float grad_scale, cudaStream_t stream);

@@ -175,7 +175,7 @@ def check_correct(model, oracle, dev, image_size=32, n_way=2, n_support=1, n_que
         assert np.array_equal(got.cpu().numpy().argmax(1), ref_logits.numpy().argmax(1))
 
 
-def check_regression(dev, lib=None, image=36, n=7, n_support=4, tol=2e-4):
+def check_regression(dev, lib=None, image=36, n=7, n_support=4, tol=2e-4, kernel="rbf"):
     """DKT regression (Conv3 + RBF GP with learned noise): one train step (loss, every gradient) and one test episode
     (predictive mean, confidence region, MSE) against the oracle (fp64 arbiter for the gradients)."""
     from deep_kernel_transfer_b200 import backbone
@@ -186,20 +186,34 @@ def check_regression(dev, lib=None, image=36, n=7, n_support=4, tol=2e-4):
     for _ in range(3):
         side = (side - 5) // 2 + 1
     feat = 36 * side * side
-    o32 = oep.OracleDKTRegression("rbf", seed=0, feat_dim=feat)
-    o32.gp["raw_lengthscale"] = torch.tensor([1.2])
-    o32.gp["raw_outputscale"] = torch.tensor([0.4])
+    o32 = oep.OracleDKTRegression(kernel, seed=0, feat_dim=feat)
+    gq = torch.Generator().manual_seed(9)
+    if kernel == "rbf":
+        o32.gp["raw_lengthscale"] = torch.tensor([1.2])
+        o32.gp["raw_outputscale"] = torch.tensor([0.4])
+    else:       # small frequencies / scales so that the product over all feature dimensions does not underflow
+        o32.gp["raw_mixture_weights"] = torch.randn(4, generator=gq) * 0.3
+        o32.gp["raw_mixture_means"] = torch.randn(4, 1, feat, generator=gq) * 0.3 - 4.0
+        o32.gp["raw_mixture_scales"] = torch.randn(4, 1, feat, generator=gq) * 0.3 - 4.0
     o32.gp["constant"] = torch.tensor([0.1])
     o32.gp["raw_noise"] = torch.tensor([-1.0])
-    o64 = oep.OracleDKTRegression("rbf", seed=0, dtype=torch.float64, feat_dim=feat)
+    o64 = oep.OracleDKTRegression(kernel, seed=0, dtype=torch.float64, feat_dim=feat)
     o64.gp = {k: v.double() for k, v in o32.gp.items()}
-    model = DKTR(backbone.Conv3(), kernel="rbf", lib=lib)
+    model = DKTR(backbone.Conv3(), kernel=kernel, lib=lib, feat_dim=feat)
     sd = {k: v.clone() for k, v in o32.bb.items()}
     model.feature_extractor.load_state_dict(sd)
-    model.model.covar_module.base_kernel.raw_lengthscale.data.fill_(1.2)
-    model.model.covar_module.raw_outputscale.data.fill_(0.4)
-    model.model.mean_module.constant.data.fill_(0.1)
-    model.likelihood.noise_covar.raw_noise.data.fill_(-1.0)
+
+    def sync_gp(o):
+        cm = model.model.covar_module
+        if kernel == "rbf":
+            cm.base_kernel.raw_lengthscale.data.fill_(float(o.gp["raw_lengthscale"].detach()))
+            cm.raw_outputscale.data.fill_(float(o.gp["raw_outputscale"].detach()))
+        else:
+            for nm in ("raw_mixture_weights", "raw_mixture_means", "raw_mixture_scales"):
+                getattr(cm, nm).data.copy_(o.gp[nm].detach().float().to(getattr(cm, nm).device))
+        model.model.mean_module.constant.data.fill_(float(o.gp["constant"].detach()))
+        model.likelihood.noise_covar.raw_noise.data.fill_(float(o.gp["raw_noise"].detach()))
+    sync_gp(o32)
     model = model.to(dev)
     g = torch.Generator().manual_seed(3)
     x = torch.randn(n, 3, image, image, generator=g)
@@ -211,10 +225,14 @@ def check_regression(dev, lib=None, image=36, n=7, n_support=4, tol=2e-4):
     assert rel_err(loss, r64["loss"]) <= 1e-4
     got = {"layer%d.weight" % (i + 1): l.weight.grad for i, l in enumerate(model.feature_extractor.layers())}
     got.update({"layer%d.bias" % (i + 1): l.bias.grad for i, l in enumerate(model.feature_extractor.layers())})
-    got["raw_outputscale"] = model.model.covar_module.raw_outputscale.grad.view(1)
     got["constant"] = model.model.mean_module.constant.grad.view(1)
     got["raw_noise"] = model.likelihood.noise_covar.raw_noise.grad.view(1)
-    got["raw_lengthscale"] = model.model.covar_module.base_kernel.raw_lengthscale.grad.view(1)
+    if kernel == "rbf":
+        got["raw_outputscale"] = model.model.covar_module.raw_outputscale.grad.view(1)
+        got["raw_lengthscale"] = model.model.covar_module.base_kernel.raw_lengthscale.grad.view(1)
+    else:
+        for nm in ("raw_mixture_weights", "raw_mixture_means", "raw_mixture_scales"):
+            got[nm] = getattr(model.model.covar_module, nm).grad
     bad = {}
     for k, v in got.items():
         e = rel_err(v, r64["grads"][k])
@@ -223,14 +241,10 @@ def check_regression(dev, lib=None, image=36, n=7, n_support=4, tol=2e-4):
             bad[k] = (e, floor)
     assert not bad, bad
     # test episode: sync the (pre-step) parameters again, fit on a support subset, predict all
-    o = oep.OracleDKTRegression("rbf", seed=0, feat_dim=feat)
+    o = oep.OracleDKTRegression(kernel, seed=0, feat_dim=feat)
     o.gp = {k: v.detach().clone() for k, v in o32.gp.items()}
     model.feature_extractor.load_state_dict({k: v.detach().clone() for k, v in o.bb.items()})
-    for p_, v_ in ((model.model.covar_module.base_kernel.raw_lengthscale, o.gp["raw_lengthscale"]),
-                   (model.model.covar_module.raw_outputscale, o.gp["raw_outputscale"]),
-                   (model.model.mean_module.constant, o.gp["constant"]),
-                   (model.likelihood.noise_covar.raw_noise, o.gp["raw_noise"])):
-        p_.data.fill_(float(v_.detach()))
+    sync_gp(o)
     idx = [0, 2, 3, 5][:n_support]
     mse_ref, mean_ref, lo_ref, hi_ref = o.test_episode(x[idx], y[idx], x, y)
     pred = model.predict(x[idx].to(dev), y[idx].to(dev), x.to(dev))

@@ -442,3 +442,70 @@ def check_conv2d(lib, dev, N=2, H=13, W=11, Cin=3, Cout=36, R=3, stride=2, pad=0
     lib.conv2d_wgrad(x_nhwc, gyd, out, dw, db, scratch, N, H, W, Cin, Cout, R, R, stride, pad, dil, relu, 0)
     _close(dw, wr.grad, rtol=1e-4, atol=1e-4, what="conv2d wgrad")
     _close(db, br.grad, rtol=1e-4, atol=1e-4, what="conv2d bgrad")
+
+
+def check_spectral(lib, dev, E=2, N=6, M=5, Cch=4, P=3, Q=4, seed=60, rtol=3e-4):
+    """Spectral-mixture kernel (ARD) forward / backward + GP fit and prediction against the oracle's autograd."""
+    g = torch.Generator().manual_seed(seed)
+    D = Cch * P
+    x_ref = torch.randn(E, N, D, generator=g) * 0.3          # reference feature order
+    xt_ref = torch.randn(E, M, D, generator=g) * 0.3
+    y = torch.randn(E, N, generator=g)
+    perm = torch.tensor([(j % Cch) * P + j // Cch for j in range(D)])
+    p = ogp.default_gp_params("spectral", 1, D, classification=False)
+    p["raw_mixture_weights"] = torch.randn(Q, generator=g) * 0.3
+    p["raw_mixture_means"] = torch.randn(Q, 1, D, generator=g) * 0.5 - 1.0
+    p["raw_mixture_scales"] = torch.randn(Q, 1, D, generator=g) * 0.5 - 0.5
+    p["constant"] = torch.tensor([0.1])
+    p["raw_noise"] = torch.tensor([-0.5])
+    xr = x_ref.clone().requires_grad_(True)
+    names = ("raw_mixture_weights", "raw_mixture_means", "raw_mixture_scales", "constant", "raw_noise")
+    for k in names:
+        p[k].requires_grad_(True)
+    losses = [ogp.mll_loss("spectral", xr[e], y[e:e + 1], p) for e in range(E)]
+    (sum(losses) / E).backward()
+    xd = x_ref[:, :, perm].contiguous().to(dev)                # our NHWC-flatten order
+    rw, rmu, rv = (p[k].detach().reshape(Q, -1).contiguous().to(dev) if k != "raw_mixture_weights"
+                   else p[k].detach().to(dev) for k in names[:3])
+    kb = torch.empty(E, 1, N, N, device=dev)
+    ec = torch.empty(E, Q, N, N, device=dev)
+    lib.spectral_fwd(xd, xd, rw, rmu, rv, kb, ec, E, N, N, D, Q, Cch, P, 0)
+    alpha = torch.empty(E, 1, N, device=dev)
+    linv = torch.empty(E, 1, N, N, device=dev)
+    lt = torch.empty(E, 1, device=dev)
+    info = torch.ones(E, 1, device=dev, dtype=torch.int32)
+    dk = torch.empty(E, 1, N, N, device=dev)
+    dh = torch.empty(E, 1, 3, device=dev)
+    cst, rn = p["constant"].detach().to(dev), p["raw_noise"].detach().to(dev)
+    lib.gp_fit(kb, N * N, y.view(E, 1, N).contiguous().to(dev), N, None, cst, rn, alpha, linv, lt, info, dk, dh, 1.0 / E,
+               0.0, E, 1, N, 0)
+    assert int(info.cpu().abs().sum()) == 0
+    loss = torch.empty(E, device=dev)
+    hyper = torch.empty(1, 3, device=dev)
+    lib.gp_reduce(lt, dh, loss, hyper, E, 1, 0)
+    _close(loss, torch.stack([l.detach() for l in losses]), rtol=rtol, what="spectral loss")
+    _close(hyper[:, 1], p["constant"].grad, rtol=rtol, atol=1e-6, what="spectral d constant")
+    _close(hyper[:, 2], p["raw_noise"].grad, rtol=rtol, atol=1e-6, what="spectral d raw_noise")
+    dw = torch.empty(Q, device=dev)
+    dmu = torch.empty(Q, D, device=dev)
+    dv = torch.empty(Q, D, device=dev)
+    dx = torch.empty(E, N, D, device=dev)
+    lib.spectral_bwd(xd, rw, rmu, rv, dk, ec, dw, dmu, dv, dx, E, N, D, Q, Cch, P, 0)
+    _close(dw, p["raw_mixture_weights"].grad, rtol=rtol, atol=1e-6, what="d mixture weights")
+    _close(dmu, p["raw_mixture_means"].grad.view(Q, D), rtol=rtol, atol=1e-6, what="d mixture means")
+    _close(dv, p["raw_mixture_scales"].grad.view(Q, D), rtol=rtol, atol=1e-6, what="d mixture scales")
+    _close(dx.cpu(), xr.grad[:, :, perm], rtol=rtol, atol=1e-6, what="spectral d x")
+    # prediction
+    xtd = xt_ref[:, :, perm].contiguous().to(dev)
+    kx = torch.empty(E, 1, M, N, device=dev)
+    lib.spectral_fwd(xtd, xd, rw, rmu, rv, kx, None, E, M, N, D, Q, Cch, P, 0)
+    mean = torch.empty(E, 1, M, device=dev)
+    lib.gp_predict(kx, M * N, alpha, None, cst, mean, None, E, 1, M, N, 0)
+    kss = torch.nn.functional.softplus(p["raw_mixture_weights"].detach()).sum().expand(E, 1, M).contiguous().to(dev)
+    var = torch.empty(E, 1, M, device=dev)
+    lib.gp_predict_var(kx, M * N, kss, M, linv, None, rn, var, E, 1, M, N, 0)
+    with torch.no_grad():
+        pd = {k: v.detach() for k, v in p.items()}
+        ref = [ogp.predict("spectral", x_ref[e], y[e:e + 1], xt_ref[e], pd, want_var=True) for e in range(E)]
+    _close(mean, torch.stack([r[0] for r in ref]), rtol=rtol, atol=1e-5, what="spectral mean")
+    _close(var, torch.stack([r[1] for r in ref]), rtol=rtol, atol=1e-5, what="spectral variance")

@@ -39,6 +39,10 @@ def test_product_refuses_cpu_without_library():
         m._ensure_packed()
 
 
+def test_regression_spectral_matches_oracle(lib):
+    dkt_checks.check_regression(torch.device("cpu"), lib=lib, kernel="spectral", image=36, n=5, n_support=3)
+
+
 def test_regression_matches_oracle(lib):
     model = dkt_checks.check_regression(torch.device("cpu"), lib=lib)
     # the reference's train_loop / test_loop drive it through a batch source + the caller's optimizer

@@ -61,3 +61,7 @@ def test_gp_family(lib, kernel):
                                  dict(Cin=3, Cout=20, R=7, stride=2, pad=3, dil=1, relu=0, H=17, W=15)])
 def test_conv2d_generic(lib, cfg):
     kc.check_conv2d(lib, DEV, **cfg)
+
+
+def test_spectral(lib):
+    kc.check_spectral(lib, DEV)
