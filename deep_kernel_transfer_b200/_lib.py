@@ -29,6 +29,7 @@ SIGNATURES = {
     "dktb_prep_weights_tc": ("ppps", ctypes.c_int),
     "dktb_conv3x3_tc_fwd": ("ppppppiiis", ctypes.c_int),
     "dktb_conv3x3_tc2_fwd": ("ppppppiiis", ctypes.c_int),
+    "dktb_conv3x3_tc3_fwd": ("ppppppiiis", ctypes.c_int),
     "dktb_conv3x3_wgrad_tc": ("ppppppiiis", ctypes.c_int),
     "dktb_conv3x3_wgrad_reduce": ("pipps", ctypes.c_int),
     "dktb_bn_finalize": ("piiiipppppffs", ctypes.c_int),

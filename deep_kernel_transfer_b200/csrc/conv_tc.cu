@@ -374,6 +374,243 @@ conv3x3_tc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// v3: persistent version of the A-in-TMEM kernel.  One CTA per SM walks a static list of (image, tile) pairs; the
+// weight ring (6 x 16 KB) streams continuously across tiles, the activation halo and the accumulator are double
+// buffered, and four dedicated epilogue warps drain accumulator t while the stagers / MMA already work on tile t+1:
+// prologue, epilogue and L2 latency all overlap the tensor pipe.
+//   warp 0      TMA producer (halo of tile t+1 as soon as its buffer is free; weight ring)
+//   warp 1      MMA issuer (elected lane), TMEM owner
+//   warps 2-9   stagers: halo row -> tf32 hi/lo split -> tcgen05.st into one of 6 A stages
+//   warps 10-13 epilogue: tcgen05.ld accumulator -> +bias -> global store; BatchNorm partial sums by warp shuffles
+// TMEM (512 columns): accumulators [0,128), A stages [128, 512).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kP_WStages = 6;
+constexpr int kP_AStages = 6;
+constexpr int kP_Threads = 64 + 256 + 128;
+
+__global__ void __launch_bounds__(kP_Threads, 1)
+conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                             const float* __restrict__ bias, float* __restrict__ out, float* __restrict__ partials,
+                             int B, int H, int W, int halo_rows_pad, int tiles_per_img, int* __restrict__ err) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar_hfull[2], bar_hempty[2], bar_wfull[kP_WStages], bar_wempty[kP_WStages], bar_afull[kP_AStages],
+      bar_aempty[kP_AStages], bar_accfull[2], bar_accempty[2];
+  __shared__ uint32_t s_tmem;
+  __shared__ int s_err;
+  __shared__ float s_stat[2][4][64];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (*reinterpret_cast<volatile int*>(err) != 0) return;
+  const int Hp = H + 2, Wp = W + 2;
+  const int half_bytes = halo_rows_pad * 128;
+  unsigned char* s_halo = smem;                               // [2 buffers][2 halves][halo_rows_pad][128 B]
+  unsigned char* s_w = smem + 4 * half_bytes;                 // [kP_WStages][16 KB]
+  const long ntiles = (long)B * tiles_per_img;
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&bar_hfull[s], 1);
+      tc::mbar_init(&bar_hempty[s], 256);
+      tc::mbar_init(&bar_accfull[s], 1);
+      tc::mbar_init(&bar_accempty[s], 128);
+    }
+    for (int s = 0; s < kP_WStages; ++s) { tc::mbar_init(&bar_wfull[s], 1); tc::mbar_init(&bar_wempty[s], 1); }
+    for (int s = 0; s < kP_AStages; ++s) { tc::mbar_init(&bar_afull[s], 256); tc::mbar_init(&bar_aempty[s], 1); }
+    s_err = 0;
+    tc::fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { tc::prefetch_tmap(&map_a); tc::prefetch_tmap(&map_w); }
+  if (warp == 1) tc::tmem_alloc<512>(&s_tmem);
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem = s_tmem;
+  const uint32_t a_tmem = tmem + 128;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    int t = 0;
+    long wi = 0;
+    bool ok = true;
+    auto load_halo = [&](long tile, int tt) -> bool {
+      const int hb = tt & 1, hp = (tt >> 1) & 1;
+      const int img = (int)(tile / tiles_per_img), tix = (int)(tile % tiles_per_img);
+      const long img_base = (long)img * Hp * Wp;
+      const int q0 = (Wp + 1) + tix * kRows;
+      if (!tc::mbar_wait(&bar_hempty[hb], hp ^ 1)) return false;
+      if (tc::elect_one()) {
+        tc::mbar_expect_tx(&bar_hfull[hb], 2 * half_bytes);
+        const int row0 = (int)(img_base + q0 - (Wp + 1));
+        for (int h = 0; h < 2; ++h)
+          for (int r = 0; r < halo_rows_pad; r += kHaloBox)
+            tc::tma_load_2d(s_halo + (hb * 2 + h) * half_bytes + r * 128, &map_a, &bar_hfull[hb], h * 32, row0 + r);
+      }
+      __syncwarp();
+      return true;
+    };
+    if (blockIdx.x < ntiles) ok = load_halo(blockIdx.x, 0);
+    for (long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x, ++t) {
+      for (int it = 0; it < kIters && ok; ++it, ++wi) {
+        const int s = (int)(wi % kP_WStages), ph = (int)((wi / kP_WStages) & 1);
+        const int tap = it >> 1, half = it & 1;
+        ok = tc::mbar_wait(&bar_wempty[s], ph ^ 1);
+        if (!ok) break;
+        if (tc::elect_one()) {
+          tc::mbar_expect_tx(&bar_wfull[s], kWStageBytes);
+          tc::tma_load_2d(s_w + s * kWStageBytes, &map_w, &bar_wfull[s], half * 32, tap * 64);
+          tc::tma_load_2d(s_w + s * kWStageBytes + 8192, &map_w, &bar_wfull[s], half * 32, (9 + tap) * 64);
+        }
+        __syncwarp();
+        // prefetch the next tile's halo early in this tile (its buffer was released one tile ago)
+        if (it == 3 && tile + gridDim.x < ntiles) ok = load_halo(tile + gridDim.x, t + 1);
+      }
+    }
+    if (!ok) s_err = 1;
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = tc::umma_idesc(2, 128, 64, 0, 0);
+    int t = 0;
+    long wi = 0;
+    bool ok = true;
+    for (long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x, ++t) {
+      const int ab = t & 1, ap = (t >> 1) & 1;
+      ok = tc::mbar_wait(&bar_accempty[ab], ap ^ 1);
+      if (!ok) break;
+      tc::tcgen05_fence_after();
+      const uint32_t d_tmem = tmem + ab * 64;
+      for (int it = 0; it < kIters && ok; ++it, ++wi) {
+        const int sw = (int)(wi % kP_WStages), pw = (int)((wi / kP_WStages) & 1);
+        const int sa = (int)(wi % kP_AStages), pa = (int)((wi / kP_AStages) & 1);
+        ok = tc::mbar_wait(&bar_wfull[sw], pw) && tc::mbar_wait(&bar_afull[sa], pa);
+        if (!ok) break;
+        tc::tcgen05_fence_after();
+        const uint32_t wbase = tc::smem_u32(s_w + sw * kWStageBytes);
+        const uint32_t acol = a_tmem + sa * 64;
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t w_hi = tc::umma_desc_sw128(wbase + k * 32, 16, 1024);
+            const uint64_t w_lo = tc::umma_desc_sw128(wbase + 8192 + k * 32, 16, 1024);
+            tc::umma_tf32_ts(d_tmem, acol + 32 + k * 8, w_hi, idesc, (it | k) ? 1u : 0u);
+            tc::umma_tf32_ts(d_tmem, acol + k * 8, w_lo, idesc, 1u);
+            tc::umma_tf32_ts(d_tmem, acol + k * 8, w_hi, idesc, 1u);
+          }
+          tc::umma_commit(&bar_aempty[sa]);
+          tc::umma_commit(&bar_wempty[sw]);
+          if (it == kIters - 1) tc::umma_commit(&bar_accfull[ab]);
+        }
+        __syncwarp();
+      }
+    }
+    if (!ok) s_err = 1;
+  } else if (warp < 10) {
+    // ------------------------------------------------------------------ stagers (256 threads)
+    const int ct = tid - 64;
+    const int set = ct >> 7;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    int t = 0;
+    long wi = 0;
+    bool ok = true;
+    for (long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x, ++t) {
+      const int hb = t & 1, hp = (t >> 1) & 1;
+      ok = tc::mbar_wait(&bar_hfull[hb], hp);
+      if (!ok) break;
+      for (int it = 0; it < kIters && ok; ++it, ++wi) {
+        const int sa = (int)(wi % kP_AStages), pa = (int)((wi / kP_AStages) & 1);
+        const int tap = it >> 1, half = it & 1;
+        const int row = r + (tap / 3) * Wp + (tap % 3);
+        const unsigned char* src = s_halo + (hb * 2 + half) * half_bytes + row * 128;
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 v = *reinterpret_cast<const float4*>(src + (((set * 4 + j) ^ (row & 7)) << 4));
+          split_tf32(v.x, hi[4 * j + 0], lo[4 * j + 0]);
+          split_tf32(v.y, hi[4 * j + 1], lo[4 * j + 1]);
+          split_tf32(v.z, hi[4 * j + 2], lo[4 * j + 2]);
+          split_tf32(v.w, hi[4 * j + 3], lo[4 * j + 3]);
+        }
+        ok = tc::mbar_wait(&bar_aempty[sa], pa ^ 1);
+        if (!ok) break;
+        tc::tcgen05_fence_after();
+        const uint32_t dst = a_tmem + sa * 64 + lane_base + set * 16;
+        tc::tmem_st16(dst, hi);
+        tc::tmem_st16(dst + 32, lo);
+        tc::tmem_st_wait();
+        tc::tcgen05_fence_before();
+        tc::mbar_arrive(&bar_afull[sa]);
+      }
+      if (ok) tc::mbar_arrive(&bar_hempty[hb]);       // this thread no longer reads the halo buffer
+    }
+    if (!ok) s_err = 1;
+  } else {
+    // ------------------------------------------------------------------ epilogue (128 threads)
+    const int et = tid - 320;
+    const int quarter = warp & 3;
+    const int ew = et >> 5;                           // 0..3 (slot in s_stat)
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    int t = 0;
+    bool ok = true;
+    for (long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x, ++t) {
+      const int ab = t & 1, ap = (t >> 1) & 1;
+      const int img = (int)(tile / tiles_per_img), tix = (int)(tile % tiles_per_img);
+      const long img_base = (long)img * Hp * Wp;
+      const int q0 = (Wp + 1) + tix * kRows;
+      ok = tc::mbar_wait(&bar_accfull[ab], ap);
+      if (!ok) break;
+      tc::tcgen05_fence_after();
+      const int q = q0 + r;
+      const int hp = q / Wp, wp = q - hp * Wp;
+      const bool valid = q < Hp * Wp && hp >= 1 && hp <= H && wp >= 1 && wp <= W;
+      float* orow = out + (img_base + q) * 64;
+#pragma unroll
+      for (int c = 0; c < 64; c += 16) {
+        uint32_t v[16];
+        tc::tmem_ld16(tmem + ab * 64 + lane_base + c, v);
+        tc::tmem_ld_wait();
+        if (c == 48) {                                // accumulator fully read: hand the buffer back to the MMA warp
+          tc::tcgen05_fence_before();
+          tc::mbar_arrive(&bar_accempty[ab]);
+        }
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = valid ? __uint_as_float(v[j]) + (bias ? bias[c + j] : 0.f) : 0.f;
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) dktb_st4(orow + c + j, make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]));
+        }
+        if (partials != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float sm = f[j], sq = f[j] * f[j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              sm += __shfl_xor_sync(0xffffffffu, sm, o);
+              sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            }
+            if (lane == 0) { s_stat[0][ew][c + j] = sm; s_stat[1][ew][c + j] = sq; }
+          }
+        }
+      }
+      if (partials != nullptr) {
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        const int which = et >> 6, c = et & 63;
+        const float tsum = (s_stat[which][0][c] + s_stat[which][1][c]) + (s_stat[which][2][c] + s_stat[which][3][c]);
+        partials[(((long)img * tiles_per_img + tix) * 2 + which) * 64 + c] = tsum;
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+      }
+    }
+    if (!ok) s_err = 1;
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (tid == 0 && s_err) atomicExch(err, 1);
+  if (warp == 1) tc::tmem_dealloc<512>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // wgrad on tcgen05:  dW[tap][ci][co] = sum_q X[q + off(tap)][ci] * G[q][co]  over ALL padded-flat rows (both operands
 // have zero borders, so images concatenate seamlessly).  GEMM view: M = 128 = 2 taps x 64 ci, N = 64 co, K = rows.
 // Both operands are "MN-major" in HBM (channels contiguous), which tcgen05 only supports for 32-bit data through a
@@ -650,6 +887,33 @@ DKTB_EXPORT int dktb_conv3x3_tc2_fwd(const float* a, const float* wb, const floa
   const int span = Hp * Wp - 2 * (Wp + 1);
   dim3 grid((span + kRows - 1) / kRows, B);
   conv3x3_tc_ts_kernel<<<grid, kTsThreads, smem, stream>>>(map_a, map_w, bias, out, partials, B, H, W, halo_pad, err);
+  return dktb_launch_status();
+}
+
+// v3 (persistent, double-buffered halo / accumulator, dedicated epilogue warps): same contract as dktb_conv3x3_tc_fwd.
+DKTB_EXPORT int dktb_conv3x3_tc3_fwd(const float* a, const float* wb, const float* bias, float* out, float* partials,
+                                     int* err, int B, int H, int W, cudaStream_t stream) {
+  DKTB_CHECK_ARG(a && wb && out && err && B > 0 && H > 0 && W > 0);
+  const int Hp = H + 2, Wp = W + 2;
+  const long rows = (long)B * Hp * Wp;
+  DKTB_CHECK_ARG(rows < 2147483000L);
+  const int halo = kRows + 2 * (Wp + 1);
+  const int halo_pad = (halo + kHaloBox - 1) / kHaloBox * kHaloBox;
+  const int smem = 4 * halo_pad * 128 + kP_WStages * kWStageBytes + 1024;
+  DKTB_CHECK_ARG(smem <= 227 * 1024);
+  CUtensorMap map_a, map_w;
+  if (tc_make_tmap_2d(&map_a, a, 64, (uint64_t)rows, 32, kHaloBox) != 0) return DKTB_BAD_ARG - 1;
+  if (tc_make_tmap_2d(&map_w, wb, 64, 2 * 9 * 64, 32, 64) != 0) return DKTB_BAD_ARG - 1;
+  cudaFuncSetAttribute(conv3x3_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int span = Hp * Wp - 2 * (Wp + 1);
+  const int tiles_per_img = (span + kRows - 1) / kRows;
+  const long ntiles = (long)B * tiles_per_img;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = (int)(ntiles < sms ? ntiles : sms);
+  conv3x3_tc_persistent_kernel<<<grid, kP_Threads, smem, stream>>>(map_a, map_w, bias, out, partials, B, H, W, halo_pad,
+                                                                   tiles_per_img, err);
   return dktb_launch_status();
 }
 

@@ -48,10 +48,10 @@ class ConvNetEngine:
         self.dev = torch.device(device)
         mode = os.environ.get("DKTB_CONV", "fp32")
         if use_tc is None:
-            use_tc = mode in ("tc", "tc2")
+            use_tc = mode in ("tc", "tc2", "tc3")
         # tcgen05 3xTF32 kernels for the 64->64 convolutions (forward + dgrad); fp32 CUDA-core kernels otherwise
         self.use_tc = bool(use_tc) and lib.has("dktb_conv3x3_tc_fwd") and self.dev.type == "cuda"
-        self.tc_fn = "conv3x3_tc_fwd" if mode == "tc" else "conv3x3_tc2_fwd"
+        self.tc_fn = {"tc": "conv3x3_tc_fwd", "tc3": "conv3x3_tc3_fwd"}.get(mode, "conv3x3_tc2_fwd")
         self.wgrad_tc = os.environ.get("DKTB_WGRAD", "tc") == "tc" and lib.has("dktb_conv3x3_wgrad_tc")
         self.layers = []
         h = image_size

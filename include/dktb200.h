@@ -61,6 +61,10 @@ int dktb_conv3x3_tc_fwd(const float* a, const float* wb, const float* bias, floa
 /* v2 of the same kernel: activation halo loaded once per tile, A operand split in registers and staged in TMEM. */
 int dktb_conv3x3_tc2_fwd(const float* a, const float* wb, const float* bias, float* out, float* partials, int* err,
                          int B, int H, int W, cudaStream_t stream);
+/* v3: persistent CTAs (one per SM), 6-deep weight ring streaming across tiles, double-buffered halo and accumulator,
+ * dedicated epilogue warps. */
+int dktb_conv3x3_tc3_fwd(const float* a, const float* wb, const float* bias, float* out, float* partials, int* err,
+                         int B, int H, int W, cudaStream_t stream);
 
 /* tcgen05 wgrad (A = X^T staged in TMEM, B = gy re-laid-out K-major in smem, 3xTF32); same contract as
  * dktb_conv3x3_wgrad plus the err flag.  dktb_conv3x3_wgrad_reduce: fixed-order reduction of per-CTA partials
