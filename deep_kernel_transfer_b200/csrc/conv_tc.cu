@@ -207,7 +207,7 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
   lo = (__float_as_uint(v - __uint_as_float(hi)) + 0x1000u) & 0xFFFFE000u;
 }
 
-__global__ void __launch_bounds__(kTsThreads, 2)
+__global__ void __launch_bounds__(kTsThreads, 1)
 conv3x3_tc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                      const float* __restrict__ bias, float* __restrict__ out, float* __restrict__ partials, int B, int H,
                      int W, int halo_rows_pad, int* __restrict__ err) {
@@ -237,12 +237,12 @@ conv3x3_tc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     tc::fence_barrier_init();
   }
   if (warp == 0 && lane == 0) { tc::prefetch_tmap(&map_a); tc::prefetch_tmap(&map_w); }
-  if (warp == 1) tc::tmem_alloc<256>(&s_tmem);
+  if (warp == 1) tc::tmem_alloc<512>(&s_tmem);
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::tcgen05_fence_after();
   const uint32_t d_tmem = s_tmem;
-  const uint32_t a_tmem = s_tmem + 64;
+  const uint32_t a_tmem = s_tmem + 256;     // accumulators [0,256): four independent 64-column chains
 
   if (warp == 0) {
     if (tc::elect_one()) {
@@ -281,9 +281,12 @@ conv3x3_tc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         for (int k = 0; k < 4; ++k) {
           const uint64_t w_hi = tc::umma_desc_sw128(wbase + k * 32, 16, 1024);
           const uint64_t w_lo = tc::umma_desc_sw128(wbase + 8192 + k * 32, 16, 1024);
-          tc::umma_tf32_ts(d_tmem, acol + 32 + k * 8, w_hi, idesc, (it | k) ? 1u : 0u);   // a_lo * w_hi
-          tc::umma_tf32_ts(d_tmem, acol + k * 8, w_lo, idesc, 1u);                         // a_hi * w_lo
-          tc::umma_tf32_ts(d_tmem, acol + k * 8, w_hi, idesc, 1u);                         // a_hi * w_hi
+          // consecutive MMAs go to different accumulators: a K=8, N=64 MMA is far shorter than the accumulate
+          // latency of the tensor pipe, so one dependent chain would leave it idle ~3/4 of the time
+          const int j = (it * 4 + k) * 3;
+          tc::umma_tf32_ts(d_tmem + ((j + 0) & 3) * 64, acol + 32 + k * 8, w_hi, idesc, (j + 0) >= 4 ? 1u : 0u);   // a_lo * w_hi
+          tc::umma_tf32_ts(d_tmem + ((j + 1) & 3) * 64, acol + k * 8, w_lo, idesc, (j + 1) >= 4 ? 1u : 0u);        // a_hi * w_lo
+          tc::umma_tf32_ts(d_tmem + ((j + 2) & 3) * 64, acol + k * 8, w_hi, idesc, (j + 2) >= 4 ? 1u : 0u);        // a_hi * w_hi
         }
         tc::umma_commit(&bar_aempty[sa]);
         tc::umma_commit(&bar_wempty[sw]);
@@ -337,13 +340,17 @@ conv3x3_tc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 #pragma unroll
       for (int cc = 0; cc < 32; cc += 16) {
         const int c = set * 32 + cc;
-        uint32_t v[16];
-        tc::tmem_ld16(d_tmem + lane_base + c, v);
+        uint32_t v0[16], v1[16], v2[16], v3[16];
+        tc::tmem_ld16(d_tmem + lane_base + c, v0);
+        tc::tmem_ld16(d_tmem + 64 + lane_base + c, v1);
+        tc::tmem_ld16(d_tmem + 128 + lane_base + c, v2);
+        tc::tmem_ld16(d_tmem + 192 + lane_base + c, v3);
         tc::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float b = bias ? bias[c + j] : 0.f;
-          s_out[r * kOutLd + c + j] = __uint_as_float(v[j]) + b;
+          s_out[r * kOutLd + c + j] = ((__uint_as_float(v0[j]) + __uint_as_float(v1[j])) +
+                                       (__uint_as_float(v2[j]) + __uint_as_float(v3[j]))) + b;
         }
       }
     }
@@ -370,7 +377,7 @@ conv3x3_tc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   tc::tcgen05_fence_before();
   __syncthreads();
   if (tid == 0 && s_err) atomicExch(err, 1);
-  if (warp == 1) tc::tmem_dealloc<256>(d_tmem);
+  if (warp == 1) tc::tmem_dealloc<512>(d_tmem);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -821,6 +828,203 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   if (warp == 1) tc::tmem_dealloc<512>(tmem);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// First layer (3 -> 64 channels, K = 27 padded to 32) on tcgen05.  The im2col row of every output pixel is gathered by
+// the stager threads from a small NCHW input patch in shared memory, 3xTF32-split and written to TMEM (A operand);
+// the weights [64 co][32 k] hi / lo sit in shared memory for the whole CTA.  12 MMAs per 128-pixel tile: the kernel is
+// bound by its epilogue traffic, so three epilogues are provided:
+//   kC1_Y     : write the pre-BN output y [B,H,W,64] + per-tile BatchNorm partial sums (training forward)
+//   kC1_STATS : partial sums only (nothing written)
+//   kC1_APPLY : BatchNorm (given mean / invstd) + ReLU + MaxPool2d(2) fused, writes the zero-bordered block output
+//               [B,H/2+2,W/2+2,64] directly -- the 1.8 MB/image pre-BN tensor never goes to HBM (eval / monitoring)
+// One CTA = one image x one group of 4 rows, looping over the 32-column tiles of that group (same tile numbering as
+// the fp32 conv1 kernel, so the BatchNorm finalize kernel is shared).
+// ------------------------------------------------------------------------------------------------------------------
+enum { kC1_Y = 0, kC1_STATS = 1, kC1_APPLY = 2 };
+constexpr int kC1PatchW = 88;                  // patch row pitch (floats): W + 2 <= 88
+
+__global__ void __launch_bounds__(kTsThreads, 3)
+conv1_tc_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias,
+                float* __restrict__ y, float* __restrict__ partials, const float* __restrict__ mean,
+                const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                float* __restrict__ act, int ipe, int H, int W, int mode, int* __restrict__ err) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar_w, bar_afull, bar_acc;
+  __shared__ uint32_t s_tmem;
+  __shared__ int s_err;
+  __shared__ float s_valid[kRows];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (*reinterpret_cast<volatile int*>(err) != 0) return;
+  unsigned char* s_wt = smem;                                        // W1 hi 8 KB | W1 lo 8 KB
+  float* s_patch = reinterpret_cast<float*>(smem + 16384);           // [3][6][kC1PatchW]
+  float* s_out = s_patch + 3 * 6 * kC1PatchW;                        // [128][kOutLd]
+  const int b = blockIdx.y, h0 = blockIdx.x * 4;
+  const int TX = (W + 31) / 32;
+
+  if (tid == 0) {
+    tc::mbar_init(&bar_w, 1);
+    tc::mbar_init(&bar_afull, 256);
+    tc::mbar_init(&bar_acc, 1);
+    s_err = 0;
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc<128>(&s_tmem);
+  // input patch: rows h0-1 .. h0+4, columns -1 .. W, zero outside the image
+  for (int i = tid; i < 3 * 6 * kC1PatchW; i += kTsThreads) {
+    const int ci = i / (6 * kC1PatchW), rem = i % (6 * kC1PatchW);
+    const int r = rem / kC1PatchW, c = rem % kC1PatchW;
+    const int hh = h0 + r - 1, ww = c - 1;
+    float v = 0.f;
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = x[(((long)b * 3 + ci) * H + hh) * W + ww];
+    s_patch[i] = v;
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t d_tmem = s_tmem, a_tmem = s_tmem + 64;
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      tc::mbar_expect_tx(&bar_w, 16384);
+      tc::tma_load_2d(s_wt, &map_w, &bar_w, 0, 0);
+      tc::tma_load_2d(s_wt + 8192, &map_w, &bar_w, 0, 64);
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    const uint32_t idesc = tc::umma_idesc(2, 128, 64, 0, 0);
+    bool ok = tc::mbar_wait(&bar_w, 0);
+    for (int tx = 0; tx < TX && ok; ++tx) {
+      ok = tc::mbar_wait(&bar_afull, tx & 1);
+      if (!ok) break;
+      tc::tcgen05_fence_after();
+      const uint32_t wbase = tc::smem_u32(s_wt);
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t w_hi = tc::umma_desc_sw128(wbase + k * 32, 16, 1024);
+          const uint64_t w_lo = tc::umma_desc_sw128(wbase + 8192 + k * 32, 16, 1024);
+          tc::umma_tf32_ts(d_tmem, a_tmem + 32 + k * 8, w_hi, idesc, k ? 1u : 0u);
+          tc::umma_tf32_ts(d_tmem, a_tmem + k * 8, w_lo, idesc, 1u);
+          tc::umma_tf32_ts(d_tmem, a_tmem + k * 8, w_hi, idesc, 1u);
+        }
+        tc::umma_commit(&bar_acc);
+      }
+      __syncwarp();
+    }
+    if (!ok) s_err = 1;
+  } else {
+    const int ct = tid - 64;
+    const int set = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int p = quarter * 32 + lane;                       // pixel of the tile = accumulator row = TMEM lane
+    const int py = p >> 5, px = p & 31;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const int e = (ipe > 0) ? b / ipe : 0;
+    bool ok = true;
+    for (int tx = 0; tx < TX && ok; ++tx) {
+      const int w0 = tx * 32;
+      // ---- stage the im2col row (16 of the 32 k-slots per thread)
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int k = set * 16 + j;
+        float v = 0.f;
+        if (k < 27) {
+          const int ci = k / 9, rr = (k % 9) / 3, ss = k % 3;
+          v = s_patch[(ci * 6 + py + rr) * kC1PatchW + w0 + px + ss];
+        }
+        split_tf32(v, hi[j], lo[j]);
+      }
+      tc::tmem_st16(a_tmem + lane_base + set * 16, hi);
+      tc::tmem_st16(a_tmem + lane_base + 32 + set * 16, lo);
+      tc::tmem_st_wait();
+      tc::tcgen05_fence_before();
+      tc::mbar_arrive(&bar_afull);
+      // ---- accumulator -> smem tile
+      ok = tc::mbar_wait(&bar_acc, tx & 1);
+      if (!ok) break;
+      tc::tcgen05_fence_after();
+      const int hh = h0 + py, ww = w0 + px;
+      if (set == 0) s_valid[p] = (hh < H && ww < W) ? 1.f : 0.f;
+#pragma unroll
+      for (int cc = 0; cc < 32; cc += 16) {
+        const int c = set * 32 + cc;
+        uint32_t v[16];
+        tc::tmem_ld16(d_tmem + lane_base + c, v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s_out[p * kOutLd + c + j] = __uint_as_float(v[j]) + (bias ? bias[c + j] : 0.f);
+      }
+      tc::tcgen05_fence_before();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (mode == kC1_Y) {
+        for (int idx = ct; idx < kRows * 16; idx += 256) {
+          const int rr = idx >> 4, c4 = (idx & 15) * 4;
+          if (s_valid[rr] != 0.f) {
+            const float* src = s_out + rr * kOutLd + c4;
+            const int oh = h0 + (rr >> 5), ow = w0 + (rr & 31);
+            dktb_st4(y + (((long)b * H + oh) * W + ow) * 64 + c4, make_float4(src[0], src[1], src[2], src[3]));
+          }
+        }
+      }
+      if (mode != kC1_APPLY && partials != nullptr && ct < 128) {
+        const int which = ct >> 6, c = ct & 63;
+        float t = 0.f;
+        for (int rr = 0; rr < kRows; ++rr) {
+          const float v = s_out[rr * kOutLd + c] * s_valid[rr];
+          t += which ? v * v : v;
+        }
+        const long blk = ((long)b * gridDim.x + blockIdx.x) * TX + tx;
+        partials[(blk * 2 + which) * 64 + c] = t;
+      }
+      if (mode == kC1_APPLY) {
+        const int c4 = (ct & 15) * 4, pp = ct >> 4;          // pooled column pp (0..15), both pooled rows
+        const int Ho = H / 2, Wo = W / 2;
+        const float4 g = dktb_ld4(gamma + c4), bt = dktb_ld4(beta + c4);
+        const float4 m = dktb_ld4(mean + e * 64 + c4), is = dktb_ld4(invstd + e * 64 + c4);
+        const float sc[4] = {g.x * is.x, g.y * is.y, g.z * is.z, g.w * is.w};
+        const float mm[4] = {m.x, m.y, m.z, m.w}, bb[4] = {bt.x, bt.y, bt.z, bt.w};
+#pragma unroll
+        for (int pr = 0; pr < 2; ++pr) {
+          const int ho = (h0 >> 1) + pr, wo = (w0 >> 1) + pp;
+          if (ho < Ho && wo < Wo) {
+            float best[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+              for (int dx = 0; dx < 2; ++dx) {
+                const float* src = s_out + ((2 * pr + dy) * 32 + 2 * pp + dx) * kOutLd + c4;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) best[j] = fmaxf(best[j], fmaf(src[j] - mm[j], sc[j], bb[j]));
+              }
+            dktb_st4(act + (((long)b * (Ho + 2) + ho + 1) * (Wo + 2) + wo + 1) * 64 + c4,
+                     make_float4(best[0], best[1], best[2], best[3]));
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    if (!ok) s_err = 1;
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (tid == 0 && s_err) atomicExch(err, 1);
+  if (warp == 1) tc::tmem_dealloc<128>(d_tmem);
+}
+
+// w1 [64][3][3][3] -> wb1 [2][64][32]: hi / lo, k = ci*9 + r*3 + s, columns 27..31 zero
+__global__ void prep_weights_conv1_tc_kernel(const float* __restrict__ w, float* __restrict__ wb1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * 32) return;
+  const int co = i / 32, k = i % 32;
+  const float v = k < 27 ? w[co * 27 + k] : 0.f;
+  uint32_t h, l;
+  split_tf32(v, h, l);
+  wb1[i] = __uint_as_float(h);
+  wb1[64 * 32 + i] = __uint_as_float(l);
+}
+
 // w_ref [co][ci][3][3] -> wb_fwd / wb_dgrad [hl][tap][n][k] (hi = rna_tf32, lo = exact remainder)
 __global__ void prep_weights_tc_kernel(const float* __restrict__ w, float* __restrict__ wb_fwd,
                                        float* __restrict__ wb_dgrad) {
@@ -914,6 +1118,30 @@ DKTB_EXPORT int dktb_conv3x3_tc3_fwd(const float* a, const float* wb, const floa
   const int grid = (int)(ntiles < sms ? ntiles : sms);
   conv3x3_tc_persistent_kernel<<<grid, kP_Threads, smem, stream>>>(map_a, map_w, bias, out, partials, B, H, W, halo_pad,
                                                                    tiles_per_img, err);
+  return dktb_launch_status();
+}
+
+DKTB_EXPORT int dktb_prep_weights_conv1_tc(const float* w, float* wb1, cudaStream_t stream) {
+  DKTB_CHECK_ARG(w && wb1);
+  prep_weights_conv1_tc_kernel<<<8, 256, 0, stream>>>(w, wb1);
+  return dktb_launch_status();
+}
+
+// First-layer convolution on tcgen05.  mode 0: y + partials (same tile numbering as dktb_conv1_fwd); mode 1: partials only;
+// mode 2: fused BatchNorm(mean, invstd [B/ipe or 1][64]) + ReLU + MaxPool2d(2) -> act [B,H/2+2,W/2+2,64] (zero border kept).
+DKTB_EXPORT int dktb_conv1_tc(const float* x, const float* wb1, const float* bias, float* y, float* partials,
+                              const float* mean, const float* invstd, const float* gamma, const float* beta, float* act,
+                              int* err, int B, int H, int W, int ipe, int mode, cudaStream_t stream) {
+  DKTB_CHECK_ARG(x && wb1 && err && B > 0 && H > 0 && W > 0 && W + 2 <= kC1PatchW && B <= 65535 && mode >= 0 && mode <= 2);
+  DKTB_CHECK_ARG(mode != kC1_Y || y);
+  DKTB_CHECK_ARG(mode != kC1_APPLY || (mean && invstd && gamma && beta && act));
+  CUtensorMap map_w;
+  if (tc_make_tmap_2d(&map_w, wb1, 32, 128, 32, 64) != 0) return DKTB_BAD_ARG - 1;
+  const int smem = 16384 + 3 * 6 * kC1PatchW * 4 + kRows * kOutLd * 4 + 1024;
+  cudaFuncSetAttribute(conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  dim3 grid((H + 3) / 4, B);
+  conv1_tc_kernel<<<grid, kTsThreads, smem, stream>>>(x, map_w, bias, y, partials, mean, invstd, gamma, beta, act, ipe, H,
+                                                       W, mode, err);
   return dktb_launch_status();
 }
 

@@ -53,6 +53,9 @@ class ConvNetEngine:
         self.use_tc = bool(use_tc) and lib.has("dktb_conv3x3_tc_fwd") and self.dev.type == "cuda"
         self.tc_fn = {"tc": "conv3x3_tc_fwd", "tc3": "conv3x3_tc3_fwd"}.get(mode, "conv3x3_tc2_fwd")
         self.wgrad_tc = os.environ.get("DKTB_WGRAD", "tc") == "tc" and lib.has("dktb_conv3x3_wgrad_tc")
+        # first layer on tcgen05 (K = 27 im2col staged in TMEM); eval passes fuse BatchNorm + ReLU + pool into its epilogue
+        self.conv1_tc = self.use_tc and os.environ.get("DKTB_CONV1", "tc") == "tc" and lib.has("dktb_conv1_tc") \
+            and image_size + 2 <= 88
         self.layers = []
         h = image_size
         for i in range(depth):
@@ -100,6 +103,7 @@ class ConvNetEngine:
             ws["wt_d"].append(torch.empty(*shape, device=dev, dtype=f32) if i > 0 else None)
             max_part = max(max_part, B * lib.bn_bwd_chunks(H, W, int(L["pool"])) * 128)
         ws["tc_err"] = torch.zeros(1, device=dev, dtype=torch.int32)
+        ws["wb1"] = torch.empty(2, 64, 32, device=dev, dtype=f32)
         ws["eval_mean"] = torch.empty(self.depth, 64, device=dev, dtype=f32)
         ws["eval_invstd"] = torch.empty(self.depth, 64, device=dev, dtype=f32)
         ws["bwd_partial"] = torch.empty(max_part, device=dev, dtype=f32)
@@ -116,6 +120,8 @@ class ConvNetEngine:
     # ------------------------------------------------------------------ forward
     def prepare_weights(self, P):
         st = _stream(self.dev)
+        if self.conv1_tc:
+            self.lib.prep_weights_conv1_tc(P.conv_w[0], self.ws["wb1"], st)
         for i in range(1, self.depth):
             if self.use_tc:
                 self.lib.prep_weights_tc(P.conv_w[i], self.ws["wt_f"][i], self.ws["wt_d"][i], st)
@@ -145,7 +151,16 @@ class ConvNetEngine:
             H, W, pool = L["H"], L["W"], int(L["pool"])
             last = i == self.depth - 1
             partials = ws["partials"][i] if training else None
-            if i == 0:
+            if i == 0 and self.conv1_tc:
+                if training:
+                    lib.conv1_tc(x, ws["wb1"], P.conv_b[0], ws["y"][0], partials, None, None, None, None, None,
+                                 ws["tc_err"], B, H, W, ipe, 0, st)
+                else:       # fused conv1 + BatchNorm(running stats) + ReLU + MaxPool: y[0] is never materialised
+                    lib.bn_eval_prepare(P.bn_rm[0], P.bn_rv[0], ws["eval_mean"][0], ws["eval_invstd"][0], 64, BN_EPS, st)
+                    lib.conv1_tc(x, ws["wb1"], P.conv_b[0], None, None, ws["eval_mean"][0], ws["eval_invstd"][0],
+                                 P.bn_w[0], P.bn_b[0], ws["act"][0], ws["tc_err"], B, H, W, 0, 2, st)
+                    continue
+            elif i == 0:
                 lib.conv1_fwd(x, P.conv_w[0], P.conv_b[0], ws["y"][0], partials, B, H, W, st)
             else:
                 self.conv64(ws["act"][i - 1], ws["wt_f"][i], P.conv_b[i], ws["y"][i], partials, B, H, W, st)

@@ -1,0 +1,62 @@
+"""Host -> device episode feeder: overlaps the H2D copy of the next packed episode batch with the compute of the
+current one (two device buffers, a dedicated copy stream, CUDA events for the hand-over).  The reference moves every
+episode with a blocking ``.cuda()`` inside the loop (methods/DKT.py:120-124); at B200 step times the 284 MB / step copy
+would otherwise serialise with the kernels."""
+import torch
+
+
+class DevicePrefetcher:
+    def __init__(self, iterable, device):
+        self.it = iter(iterable)
+        self.dev = torch.device(device)
+        self.cuda = self.dev.type == "cuda"
+        self.copy_stream = torch.cuda.Stream(self.dev) if self.cuda else None
+        self.bufs = [None, None]
+        self.ready = [None, None]
+        self.free = [None, None]
+        self.k = 0
+        self._next = None
+        self._prefetch()
+
+    def _prefetch(self):
+        try:
+            x = next(self.it)
+        except StopIteration:
+            self._next = None
+            return
+        if not self.cuda:
+            self._next = (x.to(self.dev).float().contiguous(), None)
+            return
+        i = self.k & 1
+        if self.bufs[i] is None or self.bufs[i].shape != x.shape:
+            self.bufs[i] = torch.empty(x.shape, device=self.dev, dtype=torch.float32)
+        with torch.cuda.stream(self.copy_stream):
+            if self.free[i] is not None:
+                self.copy_stream.wait_event(self.free[i])      # the step that last read this buffer has finished
+            self.bufs[i].copy_(x, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        self._next = (self.bufs[i], ev)
+        self.k += 1
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._next is None:
+            raise StopIteration
+        buf, ev = self._next
+        if ev is not None:
+            torch.cuda.current_stream(self.dev).wait_event(ev)
+        self._prefetch()
+        return buf
+
+    def release(self, buf):
+        """Call after the kernels reading ``buf`` have been enqueued: marks the buffer reusable once they finish."""
+        if not self.cuda:
+            return
+        for i in range(2):
+            if self.bufs[i] is buf:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(self.dev))
+                self.free[i] = ev

@@ -238,20 +238,29 @@ class DKT(MetaTemplate):
         self._ensure_packed()
         self._new_adam()
         dev = self._device()
-        pend = []
         n_items = len(train_loader)
-        step_i = 0
-        for i, (x, _) in enumerate(train_loader):
-            self.n_query = x.size(1) - self.n_support
-            if self.change_way:
-                self.n_way = x.size(0)
-            pend.append(x)
-            if len(pend) < self.episodes_per_step and i + 1 < n_items:
-                continue
-            xs = torch.stack(pend, 0) if len(pend) > 1 else pend[0].unsqueeze(0)
+        E = self.episodes_per_step
+
+        def packs():
             pend = []
-            x_dev = xs.to(dev, non_blocking=True).float().contiguous()
+            for i, (x, _) in enumerate(train_loader):
+                pend.append(x)
+                if len(pend) < E and i + 1 < n_items:
+                    continue
+                xs = torch.stack(pend, 0) if len(pend) > 1 else pend[0].unsqueeze(0)
+                pend = []
+                yield xs
+
+        from ..feeder import DevicePrefetcher
+        feed = DevicePrefetcher(packs(), dev)       # H2D of pack k+1 overlaps the kernels of pack k
+        step_i = 0
+        for x_dev in feed:
+            i = min((step_i + 1) * E, n_items) - 1
+            self.n_query = x_dev.size(2) - self.n_support
+            if self.change_way:
+                self.n_way = x_dev.size(1)
             out = self.train_step(x_dev)
+            feed.release(x_dev)
             self.iteration = i + (epoch * n_items)
             if step_i % print_freq == 0:
                 check_info(out["info"])

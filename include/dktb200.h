@@ -66,6 +66,15 @@ int dktb_conv3x3_tc2_fwd(const float* a, const float* wb, const float* bias, flo
 int dktb_conv3x3_tc3_fwd(const float* a, const float* wb, const float* bias, float* out, float* partials, int* err,
                          int B, int H, int W, cudaStream_t stream);
 
+/* First layer (3->64, K=27 padded to 32) on tcgen05: im2col rows gathered from an NCHW patch, split and staged in TMEM.
+ * wb1 [2][64][32] from dktb_prep_weights_conv1_tc.  mode 0: y + BatchNorm partials (tile numbering of dktb_conv1_fwd);
+ * mode 1: partials only; mode 2: fused BatchNorm(mean, invstd: [B/ipe][64], ipe == 0: one row) + ReLU + MaxPool2d(2)
+ * writing the zero-bordered block output act [B,H/2+2,W/2+2,64] -- the pre-BN tensor never reaches HBM. */
+int dktb_prep_weights_conv1_tc(const float* w, float* wb1, cudaStream_t stream);
+int dktb_conv1_tc(const float* x, const float* wb1, const float* bias, float* y, float* partials, const float* mean,
+                  const float* invstd, const float* gamma, const float* beta, float* act, int* err, int B, int H, int W,
+                  int ipe, int mode, cudaStream_t stream);
+
 /* tcgen05 wgrad (A = X^T staged in TMEM, B = gy re-laid-out K-major in smem, 3xTF32); same contract as
  * dktb_conv3x3_wgrad plus the err flag.  dktb_conv3x3_wgrad_reduce: fixed-order reduction of per-CTA partials
  * [nsplit][9*64*64 + 64] into dw [64,64,3,3] / db [64]. */

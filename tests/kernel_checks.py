@@ -509,3 +509,48 @@ def check_spectral(lib, dev, E=2, N=6, M=5, Cch=4, P=3, Q=4, seed=60, rtol=3e-4)
         ref = [ogp.predict("spectral", x_ref[e], y[e:e + 1], xt_ref[e], pd, want_var=True) for e in range(E)]
     _close(mean, torch.stack([r[0] for r in ref]), rtol=rtol, atol=1e-5, what="spectral mean")
     _close(var, torch.stack([r[1] for r in ref]), rtol=rtol, atol=1e-5, what="spectral variance")
+
+
+def check_conv1_tc(lib, dev, E=2, ipe=3, H=84, W=84, seed=70, rtol=2e-5):
+    """tcgen05 first-layer convolution: mode 0 (y + partials), mode 1 (partials only), mode 2 (fused BN+ReLU+pool)."""
+    g = torch.Generator().manual_seed(seed)
+    B = E * ipe
+    x = torch.randn(B, 3, H, W, generator=g)
+    w = torch.randn(64, 3, 3, 3, generator=g) * 0.2
+    b = torch.randn(64, generator=g) * 0.1
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    wb1 = torch.empty(2, 64, 32, device=dev)
+    lib.prep_weights_conv1_tc(w.to(dev), wb1, 0)
+    err = torch.zeros(1, device=dev, dtype=torch.int32)
+    T = lib.conv1_tiles(H, W)
+    y = torch.full((B, H, W, 64), float("nan"), device=dev)
+    part = torch.zeros(B * T * 128, device=dev)
+    lib.conv1_tc(x.to(dev), wb1, b.to(dev), y, part, None, None, None, None, None, err, B, H, W, ipe, 0, 0)
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    _close(y.cpu().permute(0, 3, 1, 2), ref, rtol=rtol, atol=1e-6, what="conv1_tc y")
+    p = part.cpu().view(B, T, 2, 64).sum(1)
+    _close(p[:, 0], ref.sum((2, 3)), rtol=1e-4, atol=1e-3, what="conv1_tc sum")
+    _close(p[:, 1], (ref * ref).sum((2, 3)), rtol=1e-4, atol=1e-3, what="conv1_tc sumsq")
+    part2 = torch.zeros(B * T * 128, device=dev)
+    lib.conv1_tc(x.to(dev), wb1, b.to(dev), None, part2, None, None, None, None, None, err, B, H, W, ipe, 1, 0)
+    assert torch.equal(part2, part)
+    # fused apply with per-episode statistics
+    gamma = torch.rand(64, generator=g) + 0.5
+    gamma[5] = -0.6
+    beta = torch.randn(64, generator=g) * 0.3
+    mean = torch.randn(E, 64, generator=g) * 0.2
+    invstd = torch.rand(E, 64, generator=g) + 0.5
+    outs = []
+    for e in range(E):
+        r = ref[e * ipe:(e + 1) * ipe].float()
+        z = (r - mean[e].view(1, -1, 1, 1)) * (invstd[e] * gamma).view(1, -1, 1, 1) + beta.view(1, -1, 1, 1)
+        outs.append(F.max_pool2d(F.relu(z), 2))
+    ref_act = torch.cat(outs, 0)
+    act = torch.zeros(B, H // 2 + 2, W // 2 + 2, 64, device=dev)
+    lib.conv1_tc(x.to(dev), wb1, b.to(dev), None, None, mean.to(dev), invstd.to(dev), gamma.to(dev), beta.to(dev), act, err,
+                 B, H, W, ipe, 2, 0)
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    _close(from_padded_nhwc(act.cpu()), ref_act, rtol=1e-5, atol=1e-5, what="conv1_tc fused apply")
+    assert float(act.cpu()[:, 0].abs().max()) == 0.0 and float(act.cpu()[:, :, 0].abs().max()) == 0.0

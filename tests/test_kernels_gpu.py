@@ -80,3 +80,9 @@ def test_gp_family(lib, kernel):
                                  dict(N=19, H=100, W=100)])
 def test_conv2d_generic(lib, cfg):
     kc.check_conv2d(lib, DEV, **cfg)
+
+
+def test_conv1_tc(lib):
+    kc.check_conv1_tc(lib, DEV)
+    kc.check_conv1_tc(lib, DEV, E=1, ipe=2, H=32, W=32, seed=71)
+    kc.check_conv1_tc(lib, DEV, E=2, ipe=2, H=21, W=37, seed=72)
