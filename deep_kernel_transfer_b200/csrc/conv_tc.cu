@@ -76,8 +76,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         tc::mbar_expect_tx(&bar_full[s], 16384 + 8192 + 8192);
         const int row = (int)(img_base + q0 - (Wp + 1) + (tap / 3) * Wp + (tap % 3));
         tc::tma_load_2d(st, &map_a, &bar_full[s], half * 32, row);
-        tc::tma_load_2d(st + kOffWHi, &map_w, &bar_full[s], half * 32, tap * 64);
-        tc::tma_load_2d(st + kOffWLo, &map_w, &bar_full[s], half * 32, (9 + tap) * 64);
+        tc::tma_load_2d(st + kOffWHi, &map_w, &bar_full[s], half * 32, tap * 128);
+        tc::tma_load_2d(st + kOffWLo, &map_w, &bar_full[s], half * 32, tap * 128 + 64);
       }
       __syncwarp();
     }
@@ -207,7 +207,7 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
   lo = (__float_as_uint(v - __uint_as_float(hi)) + 0x1000u) & 0xFFFFE000u;
 }
 
-__global__ void __launch_bounds__(kTsThreads, 1)
+__global__ void __launch_bounds__(kTsThreads, 2)
 conv3x3_tc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                      const float* __restrict__ bias, float* __restrict__ out, float* __restrict__ partials, int B, int H,
                      int W, int halo_rows_pad, int* __restrict__ err) {
@@ -231,18 +231,18 @@ conv3x3_tc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   if (tid == 0) {
     tc::mbar_init(&bar_halo, 1);
     for (int s = 0; s < kWStages; ++s) { tc::mbar_init(&bar_wfull[s], 1); tc::mbar_init(&bar_wempty[s], 1); }
-    for (int s = 0; s < kAStages; ++s) { tc::mbar_init(&bar_afull[s], 256); tc::mbar_init(&bar_aempty[s], 1); }
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(&bar_afull[s], 256); tc::mbar_init(&bar_aempty[s], 1); }
     tc::mbar_init(&bar_acc, 1);
     s_err = 0;
     tc::fence_barrier_init();
   }
   if (warp == 0 && lane == 0) { tc::prefetch_tmap(&map_a); tc::prefetch_tmap(&map_w); }
-  if (warp == 1) tc::tmem_alloc<512>(&s_tmem);
+  if (warp == 1) tc::tmem_alloc<256>(&s_tmem);
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::tcgen05_fence_after();
   const uint32_t d_tmem = s_tmem;
-  const uint32_t a_tmem = s_tmem + 256;     // accumulators [0,256): four independent 64-column chains
+  const uint32_t a_tmem = s_tmem + 128;     // accumulator [0,128): columns j (x w_hi) and 64+j (x w_lo) are summed in the epilogue
 
   if (warp == 0) {
     if (tc::elect_one()) {
@@ -259,18 +259,20 @@ conv3x3_tc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       if (!tc::mbar_wait(&bar_wempty[s], ph ^ 1)) { s_err = 1; break; }
       if (tc::elect_one()) {
         tc::mbar_expect_tx(&bar_wfull[s], kWStageBytes);
-        tc::tma_load_2d(s_w + s * kWStageBytes, &map_w, &bar_wfull[s], half * 32, tap * 64);
-        tc::tma_load_2d(s_w + s * kWStageBytes + 8192, &map_w, &bar_wfull[s], half * 32, (9 + tap) * 64);
+        tc::tma_load_2d(s_w + s * kWStageBytes, &map_w, &bar_wfull[s], half * 32, tap * 128);   // [w_hi 64 rows | w_lo 64 rows]
       }
       __syncwarp();
     }
   } else if (warp == 1) {
     {
-      const uint32_t idesc = tc::umma_idesc(2, 128, 64, 0, 0);
+      // N = 128: the B tile is [w_hi | w_lo] stacked along N, so ONE instruction yields a*w_hi (columns 0..63) and
+      // a*w_lo (columns 64..127).  tcgen05.mma costs ~50-60 cycles per instruction at N = 64 but only ~65 at N = 128
+      // (profiles/r01_umma_microbench.log), so 2 x N128 per k-step beat 3 x N64 and add the lo*lo term for free.
+      const uint32_t idesc = tc::umma_idesc(2, 128, 128, 0, 0);
       bool ok = true;
       for (int it = 0; it < kIters && ok; ++it) {
         const int sw = it % kWStages, pw = (it / kWStages) & 1;
-        const int sa = it % kAStages, pa = (it / kAStages) & 1;
+        const int sa = it & 1, pa = (it >> 1) & 1;
         ok = tc::mbar_wait(&bar_wfull[sw], pw) && tc::mbar_wait(&bar_afull[sa], pa);
         if (!ok) break;
         tc::tcgen05_fence_after();
@@ -279,14 +281,9 @@ conv3x3_tc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         if (tc::elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint64_t w_hi = tc::umma_desc_sw128(wbase + k * 32, 16, 1024);
-          const uint64_t w_lo = tc::umma_desc_sw128(wbase + 8192 + k * 32, 16, 1024);
-          // consecutive MMAs go to different accumulators: a K=8, N=64 MMA is far shorter than the accumulate
-          // latency of the tensor pipe, so one dependent chain would leave it idle ~3/4 of the time
-          const int j = (it * 4 + k) * 3;
-          tc::umma_tf32_ts(d_tmem + ((j + 0) & 3) * 64, acol + 32 + k * 8, w_hi, idesc, (j + 0) >= 4 ? 1u : 0u);   // a_lo * w_hi
-          tc::umma_tf32_ts(d_tmem + ((j + 1) & 3) * 64, acol + k * 8, w_lo, idesc, (j + 1) >= 4 ? 1u : 0u);        // a_hi * w_lo
-          tc::umma_tf32_ts(d_tmem + ((j + 2) & 3) * 64, acol + k * 8, w_hi, idesc, (j + 2) >= 4 ? 1u : 0u);        // a_hi * w_hi
+          const uint64_t w_cat = tc::umma_desc_sw128(wbase + k * 32, 16, 1024);
+          tc::umma_tf32_ts(d_tmem, acol + 32 + k * 8, w_cat, idesc, (it | k) ? 1u : 0u);   // a_lo * [w_hi | w_lo]
+          tc::umma_tf32_ts(d_tmem, acol + k * 8, w_cat, idesc, 1u);                         // a_hi * [w_hi | w_lo]
         }
         tc::umma_commit(&bar_aempty[sa]);
         tc::umma_commit(&bar_wempty[sw]);
@@ -305,7 +302,7 @@ conv3x3_tc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     bool ok = tc::mbar_wait(&bar_halo, 0);
     for (int it = 0; it < kIters && ok; ++it) {
-      const int sa = it % kAStages, pa = (it / kAStages) & 1;
+      const int sa = it & 1, pa = (it >> 1) & 1;
       const int tap = it >> 1, half = it & 1;
       const int row = r + (tap / 3) * Wp + (tap % 3);
       const unsigned char* src = s_halo + half * half_bytes + row * 128;
@@ -340,17 +337,14 @@ conv3x3_tc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 #pragma unroll
       for (int cc = 0; cc < 32; cc += 16) {
         const int c = set * 32 + cc;
-        uint32_t v0[16], v1[16], v2[16], v3[16];
+        uint32_t v0[16], v1[16];
         tc::tmem_ld16(d_tmem + lane_base + c, v0);
         tc::tmem_ld16(d_tmem + 64 + lane_base + c, v1);
-        tc::tmem_ld16(d_tmem + 128 + lane_base + c, v2);
-        tc::tmem_ld16(d_tmem + 192 + lane_base + c, v3);
         tc::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float b = bias ? bias[c + j] : 0.f;
-          s_out[r * kOutLd + c + j] = ((__uint_as_float(v0[j]) + __uint_as_float(v1[j])) +
-                                       (__uint_as_float(v2[j]) + __uint_as_float(v3[j]))) + b;
+          s_out[r * kOutLd + c + j] = (__uint_as_float(v0[j]) + __uint_as_float(v1[j])) + b;
         }
       }
     }
@@ -377,7 +371,7 @@ conv3x3_tc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   tc::tcgen05_fence_before();
   __syncthreads();
   if (tid == 0 && s_err) atomicExch(err, 1);
-  if (warp == 1) tc::tmem_dealloc<512>(d_tmem);
+  if (warp == 1) tc::tmem_dealloc<256>(d_tmem);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -464,8 +458,8 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
         if (!ok) break;
         if (tc::elect_one()) {
           tc::mbar_expect_tx(&bar_wfull[s], kWStageBytes);
-          tc::tma_load_2d(s_w + s * kWStageBytes, &map_w, &bar_wfull[s], half * 32, tap * 64);
-          tc::tma_load_2d(s_w + s * kWStageBytes + 8192, &map_w, &bar_wfull[s], half * 32, (9 + tap) * 64);
+          tc::tma_load_2d(s_w + s * kWStageBytes, &map_w, &bar_wfull[s], half * 32, tap * 128);
+          tc::tma_load_2d(s_w + s * kWStageBytes + 8192, &map_w, &bar_wfull[s], half * 32, tap * 128 + 64);
         }
         __syncwarp();
         // prefetch the next tile's halo early in this tile (its buffer was released one tile ago)
@@ -1025,7 +1019,8 @@ __global__ void prep_weights_conv1_tc_kernel(const float* __restrict__ w, float*
   wb1[64 * 32 + i] = __uint_as_float(l);
 }
 
-// w_ref [co][ci][3][3] -> wb_fwd / wb_dgrad [hl][tap][n][k] (hi = rna_tf32, lo = exact remainder)
+// w_ref [co][ci][3][3] -> wb_fwd / wb_dgrad [tap][hl][n][k] (hi = tf32-rounded, lo = rounded remainder): the hi and lo
+// tiles of one tap are adjacent so that they also form one N = 128 operand [w_hi | w_lo]
 __global__ void prep_weights_tc_kernel(const float* __restrict__ w, float* __restrict__ wb_fwd,
                                        float* __restrict__ wb_dgrad) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1034,12 +1029,12 @@ __global__ void prep_weights_tc_kernel(const float* __restrict__ w, float* __res
   const float v = w[i];
   const float hi = tc::to_tf32_rna(v), lo = tc::to_tf32_rna(v - hi);
   if (wb_fwd) {
-    wb_fwd[((0 * 9 + tap) * 64 + co) * 64 + ci] = hi;
-    wb_fwd[((1 * 9 + tap) * 64 + co) * 64 + ci] = lo;
+    wb_fwd[((tap * 2 + 0) * 64 + co) * 64 + ci] = hi;
+    wb_fwd[((tap * 2 + 1) * 64 + co) * 64 + ci] = lo;
   }
   if (wb_dgrad) {
-    wb_dgrad[((0 * 9 + (8 - tap)) * 64 + ci) * 64 + co] = hi;
-    wb_dgrad[((1 * 9 + (8 - tap)) * 64 + ci) * 64 + co] = lo;
+    wb_dgrad[(((8 - tap) * 2 + 0) * 64 + ci) * 64 + co] = hi;
+    wb_dgrad[(((8 - tap) * 2 + 1) * 64 + ci) * 64 + co] = lo;
   }
 }
 
@@ -1051,7 +1046,7 @@ DKTB_EXPORT int dktb_prep_weights_tc(const float* w, float* wb_fwd, float* wb_dg
   return dktb_launch_status();
 }
 
-// Same contract as dktb_conv3x3_fwd, with wb = the [2][9][64][64] hi/lo weight tensor of dktb_prep_weights_tc.
+// Same contract as dktb_conv3x3_fwd, with wb = the [9][2][64][64] hi/lo weight tensor of dktb_prep_weights_tc.
 // err: device int, set to 1 if a pipeline wait timed out (must be zero-initialised by the caller).
 DKTB_EXPORT int dktb_conv3x3_tc_fwd(const float* a, const float* wb, const float* bias, float* out, float* partials,
                                     int* err, int B, int H, int W, cudaStream_t stream) {
@@ -1086,7 +1081,7 @@ DKTB_EXPORT int dktb_conv3x3_tc2_fwd(const float* a, const float* wb, const floa
   DKTB_CHECK_ARG(smem <= 227 * 1024 && 2 * halo_pad * 128 >= kRows * kOutLd * 4);
   CUtensorMap map_a, map_w;
   if (tc_make_tmap_2d(&map_a, a, 64, (uint64_t)rows, 32, kHaloBox) != 0) return DKTB_BAD_ARG - 1;
-  if (tc_make_tmap_2d(&map_w, wb, 64, 2 * 9 * 64, 32, 64) != 0) return DKTB_BAD_ARG - 1;
+  if (tc_make_tmap_2d(&map_w, wb, 64, 2 * 9 * 64, 32, 128) != 0) return DKTB_BAD_ARG - 1;
   cudaFuncSetAttribute(conv3x3_tc_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int span = Hp * Wp - 2 * (Wp + 1);
   dim3 grid((span + kRows - 1) / kRows, B);

@@ -52,7 +52,7 @@ int dktb_conv3x3_wgrad(const float* a, const float* gy, float* dw, float* db, fl
                        cudaStream_t stream);
 
 /* tcgen05 + TMA version of the 64->64 convolution (forward and dgrad), fp32-class accuracy via an error-compensated
- * 3xTF32 split.  wb = [2][9][64][64] hi/lo weight tensor written by dktb_prep_weights_tc ([hl][tap][n][k]; wb_dgrad has
+ * 3xTF32 split.  wb = [9][2][64][64] hi/lo weight tensor written by dktb_prep_weights_tc ([tap][hl][n][k]; wb_dgrad has
  * the taps flipped and n/k swapped).  err: device int, zero-initialised by the caller, set to 1 when a pipeline
  * barrier wait timed out (a bug guard: results are then invalid).  Same layouts/partials as dktb_conv3x3_fwd. */
 int dktb_prep_weights_tc(const float* w, float* wb_fwd, float* wb_dgrad, cudaStream_t stream);
