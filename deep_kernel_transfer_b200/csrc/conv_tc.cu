@@ -385,8 +385,10 @@ conv3x3_tc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 //   warps 10-13 epilogue: tcgen05.ld accumulator -> +bias -> global store; BatchNorm partial sums by warp shuffles
 // TMEM (512 columns): accumulators [0,128), A stages [128, 512).
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kP_WStages = 6;
-constexpr int kP_AStages = 6;
+constexpr int kP_WStages = 3;                 // full-tap weight stages: [half 0 | half 1] x [w_hi | w_lo] = 32 KB
+constexpr int kP_WStageBytes = 32768;
+constexpr int kP_AStages = 2;                 // full-tap A stages: {hi 64 | lo 64} columns
+constexpr int kP_Taps = 9;
 constexpr int kP_Threads = 64 + 256 + 128;
 
 __global__ void __launch_bounds__(kP_Threads, 1)
@@ -405,7 +407,7 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
   const int Hp = H + 2, Wp = W + 2;
   const int half_bytes = halo_rows_pad * 128;
   unsigned char* s_halo = smem;                               // [2 buffers][2 halves][halo_rows_pad][128 B]
-  unsigned char* s_w = smem + 4 * half_bytes;                 // [kP_WStages][16 KB]
+  unsigned char* s_w = smem + 4 * half_bytes;                 // [kP_WStages][32 KB]
   const long ntiles = (long)B * tiles_per_img;
 
   if (tid == 0) {
@@ -426,7 +428,7 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
   __syncthreads();
   tc::tcgen05_fence_after();
   const uint32_t tmem = s_tmem;
-  const uint32_t a_tmem = tmem + 128;
+  const uint32_t a_tmem = tmem + 256;                         // accumulators [0,256): 2 buffers x (x w_hi | x w_lo)
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -451,25 +453,23 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
     };
     if (blockIdx.x < ntiles) ok = load_halo(blockIdx.x, 0);
     for (long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x, ++t) {
-      for (int it = 0; it < kIters && ok; ++it, ++wi) {
+      for (int tap = 0; tap < kP_Taps && ok; ++tap, ++wi) {
         const int s = (int)(wi % kP_WStages), ph = (int)((wi / kP_WStages) & 1);
-        const int tap = it >> 1, half = it & 1;
         ok = tc::mbar_wait(&bar_wempty[s], ph ^ 1);
         if (!ok) break;
         if (tc::elect_one()) {
-          tc::mbar_expect_tx(&bar_wfull[s], kWStageBytes);
-          tc::tma_load_2d(s_w + s * kWStageBytes, &map_w, &bar_wfull[s], half * 32, tap * 128);
-          tc::tma_load_2d(s_w + s * kWStageBytes + 8192, &map_w, &bar_wfull[s], half * 32, tap * 128 + 64);
+          tc::mbar_expect_tx(&bar_wfull[s], kP_WStageBytes);
+          tc::tma_load_2d(s_w + s * kP_WStageBytes, &map_w, &bar_wfull[s], 0, tap * 128);
+          tc::tma_load_2d(s_w + s * kP_WStageBytes + 16384, &map_w, &bar_wfull[s], 32, tap * 128);
         }
         __syncwarp();
-        // prefetch the next tile's halo early in this tile (its buffer was released one tile ago)
-        if (it == 3 && tile + gridDim.x < ntiles) ok = load_halo(tile + gridDim.x, t + 1);
+        if (tap == 1 && tile + gridDim.x < ntiles) ok = load_halo(tile + gridDim.x, t + 1);
       }
     }
     if (!ok) s_err = 1;
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = tc::umma_idesc(2, 128, 64, 0, 0);
+    // ------------------------------------------------------------------ MMA issuer: 16 x (M128, N128, K8) per tap
+    const uint32_t idesc = tc::umma_idesc(2, 128, 128, 0, 0);
     int t = 0;
     long wi = 0;
     bool ok = true;
@@ -478,36 +478,34 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
       ok = tc::mbar_wait(&bar_accempty[ab], ap ^ 1);
       if (!ok) break;
       tc::tcgen05_fence_after();
-      const uint32_t d_tmem = tmem + ab * 64;
-      for (int it = 0; it < kIters && ok; ++it, ++wi) {
+      const uint32_t d_tmem = tmem + ab * 128;
+      for (int tap = 0; tap < kP_Taps && ok; ++tap, ++wi) {
         const int sw = (int)(wi % kP_WStages), pw = (int)((wi / kP_WStages) & 1);
-        const int sa = (int)(wi % kP_AStages), pa = (int)((wi / kP_AStages) & 1);
+        const int sa = (int)(wi & 1), pa = (int)((wi >> 1) & 1);
         ok = tc::mbar_wait(&bar_wfull[sw], pw) && tc::mbar_wait(&bar_afull[sa], pa);
         if (!ok) break;
         tc::tcgen05_fence_after();
-        const uint32_t wbase = tc::smem_u32(s_w + sw * kWStageBytes);
-        const uint32_t acol = a_tmem + sa * 64;
+        const uint32_t wbase = tc::smem_u32(s_w + sw * kP_WStageBytes);
+        const uint32_t acol = a_tmem + sa * 128;              // hi [0,64) | lo [64,128), channel c at column c
         if (tc::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t w_hi = tc::umma_desc_sw128(wbase + k * 32, 16, 1024);
-            const uint64_t w_lo = tc::umma_desc_sw128(wbase + 8192 + k * 32, 16, 1024);
-            tc::umma_tf32_ts(d_tmem, acol + 32 + k * 8, w_hi, idesc, (it | k) ? 1u : 0u);
-            tc::umma_tf32_ts(d_tmem, acol + k * 8, w_lo, idesc, 1u);
-            tc::umma_tf32_ts(d_tmem, acol + k * 8, w_hi, idesc, 1u);
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t w_cat = tc::umma_desc_sw128(wbase + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+            tc::umma_tf32_ts(d_tmem, acol + 64 + k * 8, w_cat, idesc, (tap | k) ? 1u : 0u);   // a_lo * [w_hi | w_lo]
+            tc::umma_tf32_ts(d_tmem, acol + k * 8, w_cat, idesc, 1u);                          // a_hi * [w_hi | w_lo]
           }
           tc::umma_commit(&bar_aempty[sa]);
           tc::umma_commit(&bar_wempty[sw]);
-          if (it == kIters - 1) tc::umma_commit(&bar_accfull[ab]);
+          if (tap == kP_Taps - 1) tc::umma_commit(&bar_accfull[ab]);
         }
         __syncwarp();
       }
     }
     if (!ok) s_err = 1;
   } else if (warp < 10) {
-    // ------------------------------------------------------------------ stagers (256 threads)
+    // ------------------------------------------------------------------ stagers (256 threads): 32 channels per thread
     const int ct = tid - 64;
-    const int set = ct >> 7;
+    const int set = ct >> 7;                          // channel half of the tap handled by this thread
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
@@ -518,15 +516,14 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
       const int hb = t & 1, hp = (t >> 1) & 1;
       ok = tc::mbar_wait(&bar_hfull[hb], hp);
       if (!ok) break;
-      for (int it = 0; it < kIters && ok; ++it, ++wi) {
-        const int sa = (int)(wi % kP_AStages), pa = (int)((wi / kP_AStages) & 1);
-        const int tap = it >> 1, half = it & 1;
+      for (int tap = 0; tap < kP_Taps && ok; ++tap, ++wi) {
+        const int sa = (int)(wi & 1), pa = (int)((wi >> 1) & 1);
         const int row = r + (tap / 3) * Wp + (tap % 3);
-        const unsigned char* src = s_halo + (hb * 2 + half) * half_bytes + row * 128;
-        uint32_t hi[16], lo[16];
+        const unsigned char* src = s_halo + (hb * 2 + set) * half_bytes + row * 128;
+        uint32_t hi[32], lo[32];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 v = *reinterpret_cast<const float4*>(src + (((set * 4 + j) ^ (row & 7)) << 4));
+        for (int j = 0; j < 8; ++j) {
+          const float4 v = *reinterpret_cast<const float4*>(src + ((j ^ (row & 7)) << 4));
           split_tf32(v.x, hi[4 * j + 0], lo[4 * j + 0]);
           split_tf32(v.y, hi[4 * j + 1], lo[4 * j + 1]);
           split_tf32(v.z, hi[4 * j + 2], lo[4 * j + 2]);
@@ -535,9 +532,11 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
         ok = tc::mbar_wait(&bar_aempty[sa], pa ^ 1);
         if (!ok) break;
         tc::tcgen05_fence_after();
-        const uint32_t dst = a_tmem + sa * 64 + lane_base + set * 16;
+        const uint32_t dst = a_tmem + sa * 128 + lane_base + set * 32;
         tc::tmem_st16(dst, hi);
-        tc::tmem_st16(dst + 32, lo);
+        tc::tmem_st16(dst + 16, hi + 16);
+        tc::tmem_st16(dst + 64, lo);
+        tc::tmem_st16(dst + 80, lo + 16);
         tc::tmem_st_wait();
         tc::tcgen05_fence_before();
         tc::mbar_arrive(&bar_afull[sa]);
@@ -568,8 +567,9 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
       float* orow = out + (img_base + q) * 64;
 #pragma unroll
       for (int c = 0; c < 64; c += 16) {
-        uint32_t v[16];
-        tc::tmem_ld16(tmem + ab * 64 + lane_base + c, v);
+        uint32_t v[16], u[16];
+        tc::tmem_ld16(tmem + ab * 128 + lane_base + c, v);
+        tc::tmem_ld16(tmem + ab * 128 + 64 + lane_base + c, u);
         tc::tmem_ld_wait();
         if (c == 48) {                                // accumulator fully read: hand the buffer back to the MMA warp
           tc::tcgen05_fence_before();
@@ -577,7 +577,8 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
         }
         float f[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = valid ? __uint_as_float(v[j]) + (bias ? bias[c + j] : 0.f) : 0.f;
+        for (int j = 0; j < 16; ++j)
+          f[j] = valid ? (__uint_as_float(v[j]) + __uint_as_float(u[j])) + (bias ? bias[c + j] : 0.f) : 0.f;
         if (valid) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) dktb_st4(orow + c + j, make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]));
@@ -1098,11 +1099,11 @@ DKTB_EXPORT int dktb_conv3x3_tc3_fwd(const float* a, const float* wb, const floa
   DKTB_CHECK_ARG(rows < 2147483000L);
   const int halo = kRows + 2 * (Wp + 1);
   const int halo_pad = (halo + kHaloBox - 1) / kHaloBox * kHaloBox;
-  const int smem = 4 * halo_pad * 128 + kP_WStages * kWStageBytes + 1024;
+  const int smem = 4 * halo_pad * 128 + kP_WStages * kP_WStageBytes + 1024;
   DKTB_CHECK_ARG(smem <= 227 * 1024);
   CUtensorMap map_a, map_w;
   if (tc_make_tmap_2d(&map_a, a, 64, (uint64_t)rows, 32, kHaloBox) != 0) return DKTB_BAD_ARG - 1;
-  if (tc_make_tmap_2d(&map_w, wb, 64, 2 * 9 * 64, 32, 64) != 0) return DKTB_BAD_ARG - 1;
+  if (tc_make_tmap_2d(&map_w, wb, 64, 2 * 9 * 64, 32, 128) != 0) return DKTB_BAD_ARG - 1;
   cudaFuncSetAttribute(conv3x3_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int span = Hp * Wp - 2 * (Wp + 1);
   const int tiles_per_img = (span + kRows - 1) / kRows;
