@@ -304,10 +304,17 @@ def dominant_kernel_roofline(model, lib, dev, E):
     else:
         peak = 75.0
         which = "nominal fp32 FFMA peak (148 SMs x 128 FMA x ~1.97 GHz); no measured fp32 figure in MEASURED_PEAKS.json"
-    return {"kernel": "conv3x3 64->64 forward, 42x42, B=%d images (%s)" % (B, "tcgen05 3xTF32" if use_tc else "fp32 FFMA"),
+    # DRAM traffic of this kernel from the committed ncu --set full capture (profiles/r01_conv3x3_tc_ts.summary.txt:
+    # 833.08 MB read + 718.68 MB written for B = 1680 images), scaled to this launch's B; algorithmic bytes are the
+    # padded activation tensor read once + the interior of y written once
+    traffic = (833.078272e6 + 718.676736e6) / 1680.0 * B if use_tc else None
+    alg_bytes = B * ((H + 2) * (W + 2) * 256.0 + H * W * 256.0)
+    return {"kernel": "conv3x3 64->64 forward, 42x42, B=%d images (%s)" % (B, "tcgen05 3xTF32, " + eng.tc_fn if use_tc else "fp32 FFMA"),
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": None, "ms_per_launch": ms, "peak_source": which,
-            "algorithmic_flops_per_launch": flops}
+            "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms, "peak_source": which,
+            "algorithmic_flops_per_launch": flops,
+            "note": "N = 64 output channels bound tcgen05.mma at ~50-65 cycles per (128xNx8) instruction "
+                    "(profiles/r01_umma_microbench.log): 3xTF32 on this layer tops out near 0.33 of dense TF32"}
 
 
 if __name__ == "__main__":

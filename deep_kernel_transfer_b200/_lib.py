@@ -63,6 +63,14 @@ SIGNATURES = {
     "dktb_nchw_to_nhwc": ("ppiiiis", ctypes.c_int),
     "dktb_spectral_fwd": ("pppppppiiiiiiis", ctypes.c_int),
     "dktb_spectral_bwd": ("ppppppppppiiiiiis", ctypes.c_int),
+    "dktb_bn2d_stats": ("ppppppiiiiffs", ctypes.c_int),
+    "dktb_bn2d_apply": ("pppppppiiiiis", ctypes.c_int),
+    "dktb_bn2d_bwd": ("ppppppppppppiiiiis", ctypes.c_int),
+    "dktb_maxpool3_fwd": ("pppiiiis", ctypes.c_int),
+    "dktb_maxpool3_bwd": ("pppiiiis", ctypes.c_int),
+    "dktb_avgpool_fwd": ("ppiiis", ctypes.c_int),
+    "dktb_avgpool_bwd": ("ppiiis", ctypes.c_int),
+    "dktb_add_inplace": ("ppls", ctypes.c_int),
     "dktb_adam_step": ("pppplffffifs", ctypes.c_int),
     "dktb_scale": ("plfs", ctypes.c_int),
 }

@@ -134,12 +134,131 @@ Conv4NP = _not_on_hot_path("Conv4NP")
 Conv6NP = _not_on_hot_path("Conv6NP")
 Conv4S = _not_on_hot_path("Conv4S")
 Conv4SNP = _not_on_hot_path("Conv4SNP")
-ResNet10 = _not_on_hot_path("ResNet10")
-ResNet18 = _not_on_hot_path("ResNet18")
-ResNet34 = _not_on_hot_path("ResNet34")
-ResNet50 = _not_on_hot_path("ResNet50")
-ResNet101 = _not_on_hot_path("ResNet101")
 
+
+class SimpleBlock(nn.Module):
+    """3x3 -> BN -> ReLU -> 3x3 -> BN (+ 1x1/BN shortcut) -> add -> ReLU  (backbone.py:135-185).  Parameter container."""
+    maml = False
+    kind = "simple"
+
+    def __init__(self, indim, outdim, half_res):
+        super().__init__()
+        self.indim, self.outdim, self.half_res = indim, outdim, half_res
+        self.C1 = nn.Conv2d(indim, outdim, kernel_size=3, stride=2 if half_res else 1, padding=1, bias=False)
+        self.BN1 = nn.BatchNorm2d(outdim)
+        self.C2 = nn.Conv2d(outdim, outdim, kernel_size=3, padding=1, bias=False)
+        self.BN2 = nn.BatchNorm2d(outdim)
+        self.relu1, self.relu2 = nn.ReLU(inplace=True), nn.ReLU(inplace=True)
+        self.parametrized_layers = [self.C1, self.C2, self.BN1, self.BN2]
+        if indim != outdim:
+            self.shortcut = nn.Conv2d(indim, outdim, 1, 2 if half_res else 1, bias=False)
+            self.BNshortcut = nn.BatchNorm2d(outdim)
+            self.parametrized_layers += [self.shortcut, self.BNshortcut]
+            self.shortcut_type = '1x1'
+        else:
+            self.shortcut_type = 'identity'
+        for layer in self.parametrized_layers:
+            init_layer(layer)
+
+
+class BottleneckBlock(nn.Module):
+    """1x1 -> 3x3 (with bias) -> 1x1 bottleneck; the 1x1 shortcut has NO BatchNorm (backbone.py:190-247)."""
+    maml = False
+    kind = "bottleneck"
+
+    def __init__(self, indim, outdim, half_res):
+        super().__init__()
+        b = int(outdim / 4)
+        self.indim, self.outdim, self.half_res = indim, outdim, half_res
+        self.C1 = nn.Conv2d(indim, b, kernel_size=1, bias=False)
+        self.BN1 = nn.BatchNorm2d(b)
+        self.C2 = nn.Conv2d(b, b, kernel_size=3, stride=2 if half_res else 1, padding=1)
+        self.BN2 = nn.BatchNorm2d(b)
+        self.C3 = nn.Conv2d(b, outdim, kernel_size=1, bias=False)
+        self.BN3 = nn.BatchNorm2d(outdim)
+        self.relu = nn.ReLU()
+        self.parametrized_layers = [self.C1, self.BN1, self.C2, self.BN2, self.C3, self.BN3]
+        if indim != outdim:
+            self.shortcut = nn.Conv2d(indim, outdim, 1, stride=2 if half_res else 1, bias=False)
+            self.parametrized_layers.append(self.shortcut)
+            self.shortcut_type = '1x1'
+        else:
+            self.shortcut_type = 'identity'
+        for layer in self.parametrized_layers:
+            init_layer(layer)
+
+
+class ResNet(nn.Module):
+    """Stem 7x7/2 -> BN -> ReLU -> MaxPool(3,2,1) -> 4 stages -> AvgPool(7) -> flatten  (backbone.py:330-376)."""
+    maml = False
+
+    def __init__(self, block, list_of_num_layers, list_of_out_dims, flatten=True):
+        super().__init__()
+        assert len(list_of_num_layers) == 4, 'Can have only four stages'
+        if not flatten:
+            raise NotImplementedError("un-flattened ResNet is only used by RelationNet (out of scope)")
+        conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        bn1 = nn.BatchNorm2d(64)
+        init_layer(conv1)
+        init_layer(bn1)
+        trunk = [conv1, bn1, nn.ReLU(), nn.MaxPool2d(kernel_size=3, stride=2, padding=1)]
+        indim = 64
+        for i in range(4):
+            for j in range(list_of_num_layers[i]):
+                half_res = (i >= 1) and (j == 0)
+                trunk.append(block(indim, list_of_out_dims[i], half_res))
+                indim = list_of_out_dims[i]
+        trunk += [nn.AvgPool2d(7), Flatten()]
+        self.final_feat_dim = indim
+        self.trunk = nn.Sequential(*trunk)
+        self._engine = None
+
+    def blocks(self):
+        return [m for m in self.trunk if isinstance(m, (SimpleBlock, BottleneckBlock))]
+
+    def engine(self, image_size, device, lib=None):
+        from .resnet_engine import ResNetEngine
+        dev = torch.device(device)
+        if self._engine is None or self._engine.dev != dev:
+            self._engine = ResNetEngine(lib or _lib.load(), self, dev)
+        return self._engine
+
+    def forward(self, x):
+        if x.device.type != "cuda":
+            raise RuntimeError("dktb200 has no CPU path: move the input to a CUDA device")
+        eng = self.engine(x.shape[-1], x.device)
+        out = eng.forward(x.contiguous().float(), ipe=x.shape[0], training=self.training)
+        eng.tape = []
+        if hasattr(self.trunk, "bn_out"):
+            bn = self.trunk.bn_out
+            n, d = out.shape
+            z = torch.empty(1, n, d, device=x.device)
+            stt = [torch.empty(1, d, device=x.device) for _ in range(3)]
+            eng.lib.bn1d_fwd(out.contiguous(), bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, z, stt[0],
+                             stt[1], stt[2], 1, n, d, d, 1, int(self.training), 1, 0.1, 1e-5,
+                             torch.cuda.current_stream(x.device).cuda_stream)
+            out = z.view(n, d)
+        return out
+
+
+def ResNet10(flatten=True):
+    return ResNet(SimpleBlock, [1, 1, 1, 1], [64, 128, 256, 512], flatten)
+
+
+def ResNet18(flatten=True):
+    return ResNet(SimpleBlock, [2, 2, 2, 2], [64, 128, 256, 512], flatten)
+
+
+def ResNet34(flatten=True):
+    return ResNet(SimpleBlock, [3, 4, 6, 3], [64, 128, 256, 512], flatten)
+
+
+def ResNet50(flatten=True):
+    return ResNet(BottleneckBlock, [3, 4, 6, 3], [256, 512, 1024, 2048], flatten)
+
+
+def ResNet101(flatten=True):
+    return ResNet(BottleneckBlock, [3, 4, 23, 3], [256, 512, 1024, 2048], flatten)
 
 class Conv3(nn.Module):
     """Backbone of the QMUL head-pose regression (reference backbone.py:379-402).  Parameter containers + engine."""
@@ -177,14 +296,3 @@ class Conv3(nn.Module):
         n = x.shape[0]
         return f.view(n, eng.P, 36).transpose(1, 2).reshape(n, -1)
 
-# class attributes train.py:163-167 pokes for MAML (kept so the driver imports cleanly)
-class SimpleBlock:      # noqa: E302
-    maml = False
-
-
-class BottleneckBlock:
-    maml = False
-
-
-class ResNet:
-    maml = False

@@ -1,0 +1,296 @@
+// Channel-generic NHWC building blocks of the ResNet backbones (reference backbone.py:135-247 SimpleBlock /
+// BottleneckBlock, 330-376 ResNet): BatchNorm2d with PER-EPISODE batch statistics for any channel count (+ fused
+// residual add and ReLU), MaxPool2d(3, stride 2, pad 1), global AvgPool2d, forward and backward.  HBM-bound
+// element-wise / reduction kernels; reductions are two-stage with a fixed order (deterministic).
+#include "dktb_common.cuh"
+
+// ------------------------------------------------------------------------------------------------ BN statistics
+// partial[b][c][2] = sum, sumsq over the HW pixels of image b.  grid (ceil(C/64), B), 256 threads = 64 ch x 4 slices
+__global__ void __launch_bounds__(256) bn2d_partial_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                           const float* __restrict__ y, const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd, float* __restrict__ partial,
+                                                           int HW, int C, int ipe, int mode) {
+  // mode 0: (x, x^2);  mode 1 (backward): g' = g * (y > 0 if y given), (g', g' * xhat)
+  __shared__ float s_red[2][4][64];
+  const int c = blockIdx.x * 64 + threadIdx.x % 64, sl = threadIdx.x / 64;
+  const int b = blockIdx.y;
+  float a0 = 0.f, a1 = 0.f;
+  if (c < C) {
+    float m = 0.f, is = 0.f;
+    if (mode == 1) {
+      const int e = b / ipe;
+      m = mean[(long)e * C + c];
+      is = invstd[(long)e * C + c];
+    }
+    const long base = (long)b * HW * C + c;
+    for (int p = sl; p < HW; p += 4) {
+      const float v = x[base + (long)p * C];
+      if (mode == 0) {
+        a0 += v;
+        a1 = fmaf(v, v, a1);
+      } else {
+        float gv = g[base + (long)p * C];
+        if (y != nullptr && !(y[base + (long)p * C] > 0.f)) gv = 0.f;
+        a0 += gv;
+        a1 = fmaf(gv, (v - m) * is, a1);
+      }
+    }
+  }
+  s_red[0][sl][threadIdx.x % 64] = a0;
+  s_red[1][sl][threadIdx.x % 64] = a1;
+  __syncthreads();
+  if (sl == 0 && c < C) {
+    const int t = threadIdx.x;
+    partial[((long)b * C + c) * 2 + 0] = (s_red[0][0][t] + s_red[0][1][t]) + (s_red[0][2][t] + s_red[0][3][t]);
+    partial[((long)b * C + c) * 2 + 1] = (s_red[1][0][t] + s_red[1][1][t]) + (s_red[1][2][t] + s_red[1][3][t]);
+  }
+}
+
+// forward statistics: mean / invstd per (episode, channel) + sequential running-stat EMA
+__global__ void bn2d_finalize_kernel(const float* __restrict__ partial, float* __restrict__ mean,
+                                     float* __restrict__ invstd, float* __restrict__ running_mean,
+                                     float* __restrict__ running_var, int E, int ipe, int HW, int C, float momentum,
+                                     float eps) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double n = (double)ipe * HW;
+  float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 0.f;
+  for (int e = 0; e < E; ++e) {
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < ipe; ++i) {
+      s += (double)partial[(((long)e * ipe + i) * C + c) * 2 + 0];
+      q += (double)partial[(((long)e * ipe + i) * C + c) * 2 + 1];
+    }
+    const double m = s / n;
+    double var = q / n - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[(long)e * C + c] = (float)m;
+    invstd[(long)e * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+    rm = (1.f - momentum) * rm + momentum * (float)m;
+    rv = (1.f - momentum) * rv + momentum * (float)(n > 1.0 ? var * n / (n - 1.0) : var);
+  }
+  if (running_mean) running_mean[c] = rm;
+  if (running_var) running_var[c] = rv;
+}
+
+// backward sums: sums[e][c][2] = sum over the episode's images; dgamma / dbeta = sum over episodes
+__global__ void bn2d_bwd_finalize_kernel(const float* __restrict__ partial, float* __restrict__ sums,
+                                         float* __restrict__ dgamma, float* __restrict__ dbeta, int E, int ipe, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double tg = 0.0, tb = 0.0;
+  for (int e = 0; e < E; ++e) {
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < ipe; ++i) {
+      s += (double)partial[(((long)e * ipe + i) * C + c) * 2 + 0];
+      q += (double)partial[(((long)e * ipe + i) * C + c) * 2 + 1];
+    }
+    sums[((long)e * C + c) * 2 + 0] = (float)s;
+    sums[((long)e * C + c) * 2 + 1] = (float)q;
+    tb += s;
+    tg += q;
+  }
+  dgamma[c] = (float)tg;
+  dbeta[c] = (float)tb;
+}
+
+DKTB_EXPORT int dktb_bn2d_stats(const float* x, float* mean, float* invstd, float* running_mean, float* running_var,
+                                float* partial, int B, int HW, int C, int ipe, float momentum, float eps,
+                                cudaStream_t stream) {
+  DKTB_CHECK_ARG(x && mean && invstd && partial && B > 0 && HW > 0 && C > 0 && ipe > 0 && B % ipe == 0 && B <= 65535);
+  DKTB_LAUNCH(bn2d_partial_kernel, dim3((C + 63) / 64, B), dim3(256), 0, stream, x, (const float*)nullptr,
+              (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, partial, HW, C, ipe, 0);
+  DKTB_LAUNCH(bn2d_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, stream, (const float*)partial, mean, invstd,
+              running_mean, running_var, B / ipe, ipe, HW, C, momentum, eps);
+  return dktb_launch_status();
+}
+
+// y = act( (x - mean) * invstd * gamma + beta (+ res) );  stats row = img / ipe (ipe == 0: row 0, eval mode)
+__global__ void __launch_bounds__(256) bn2d_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                                         const float* __restrict__ invstd,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         const float* __restrict__ res, float* __restrict__ y, long total4,
+                                                         int HW, int C, int ipe, int relu) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int c4 = (int)(i % (C / 4)) * 4;
+  const long pix = i / (C / 4);
+  const int e = ipe > 0 ? (int)(pix / HW / ipe) : 0;
+  const float4 v = dktb_ld4(x + i * 4);
+  const float4 m = dktb_ld4(mean + (long)e * C + c4), is = dktb_ld4(invstd + (long)e * C + c4);
+  const float4 g = dktb_ld4(gamma + c4), bt = dktb_ld4(beta + c4);
+  float4 o;
+  o.x = fmaf(v.x - m.x, is.x * g.x, bt.x);
+  o.y = fmaf(v.y - m.y, is.y * g.y, bt.y);
+  o.z = fmaf(v.z - m.z, is.z * g.z, bt.z);
+  o.w = fmaf(v.w - m.w, is.w * g.w, bt.w);
+  if (res != nullptr) {
+    const float4 r = dktb_ld4(res + i * 4);
+    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+  }
+  if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+  dktb_st4(y + i * 4, o);
+}
+
+DKTB_EXPORT int dktb_bn2d_apply(const float* x, const float* mean, const float* invstd, const float* gamma,
+                                const float* beta, const float* res, float* y, int B, int HW, int C, int ipe, int relu,
+                                cudaStream_t stream) {
+  DKTB_CHECK_ARG(x && mean && invstd && gamma && beta && y && B > 0 && HW > 0 && C > 0 && C % 4 == 0);
+  const long total4 = (long)B * HW * C / 4;
+  DKTB_LAUNCH(bn2d_apply_kernel, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, stream, x, mean, invstd, gamma,
+              beta, res, y, total4, HW, C, ipe, relu);
+  return dktb_launch_status();
+}
+
+// gx = gamma*invstd*(g' - s1/n - xhat*s2/n),  g' = gy * (y > 0) when relu;  gres (nullable) = g'
+__global__ void __launch_bounds__(256) bn2d_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                             const float* __restrict__ gy, const float* __restrict__ mean,
+                                                             const float* __restrict__ invstd,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ sums, float* __restrict__ gx,
+                                                             float* __restrict__ gres, long total, int HW, int C, int ipe,
+                                                             int relu, float inv_n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const long pix = i / C;
+  const int e = (int)(pix / HW / ipe);
+  float g = gy[i];
+  if (relu && !(y[i] > 0.f)) g = 0.f;
+  const float m = mean[(long)e * C + c], is = invstd[(long)e * C + c];
+  const float xh = (x[i] - m) * is;
+  const float s1 = sums[((long)e * C + c) * 2 + 0] * inv_n, s2 = sums[((long)e * C + c) * 2 + 1] * inv_n;
+  gx[i] = gamma[c] * is * (g - s1 - xh * s2);
+  if (gres != nullptr) gres[i] = g;
+}
+
+// x: BN input; y: block output after add/ReLU (for the ReLU mask; nullable when relu == 0); gy: gradient w.r.t. y.
+// partial: B*C*2 floats, sums: (B/ipe)*C*2 floats.
+DKTB_EXPORT int dktb_bn2d_bwd(const float* x, const float* y, const float* gy, const float* mean, const float* invstd,
+                              const float* gamma, float* gx, float* gres, float* dgamma, float* dbeta, float* partial,
+                              float* sums, int B, int HW, int C, int ipe, int relu, cudaStream_t stream) {
+  DKTB_CHECK_ARG(x && gy && mean && invstd && gamma && gx && dgamma && dbeta && partial && sums && (!relu || y));
+  DKTB_CHECK_ARG(B > 0 && ipe > 0 && B % ipe == 0 && B <= 65535);
+  DKTB_LAUNCH(bn2d_partial_kernel, dim3((C + 63) / 64, B), dim3(256), 0, stream, x, gy, relu ? y : (const float*)nullptr,
+              mean, invstd, partial, HW, C, ipe, 1);
+  DKTB_LAUNCH(bn2d_bwd_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, stream, (const float*)partial, sums, dgamma,
+              dbeta, B / ipe, ipe, C);
+  const long total = (long)B * HW * C;
+  DKTB_LAUNCH(bn2d_bwd_apply_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, x, y, gy, mean, invstd,
+              gamma, (const float*)sums, gx, gres, total, HW, C, ipe, relu, 1.0f / ((float)ipe * (float)HW));
+  return dktb_launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------ pooling
+// MaxPool2d(3, stride 2, padding 1); idx stores the arg-max tap (0..8, first maximum in scan order)
+__global__ void __launch_bounds__(256) maxpool3_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                           unsigned char* __restrict__ idx, int B, int H, int W, int C,
+                                                           int Ho, int Wo) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = (long)B * Ho * Wo * C;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  long t = i / C;
+  const int ow = (int)(t % Wo);
+  t /= Wo;
+  const int oh = (int)(t % Ho);
+  const int b = (int)(t / Ho);
+  float best = -INFINITY;
+  int arg = 0;
+  for (int r = 0; r < 3; ++r)
+    for (int s = 0; s < 3; ++s) {
+      const int ih = oh * 2 - 1 + r, iw = ow * 2 - 1 + s;
+      if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
+      const float v = x[(((long)b * H + ih) * W + iw) * C + c];
+      if (v > best) { best = v; arg = r * 3 + s; }
+    }
+  y[i] = best;
+  idx[i] = (unsigned char)arg;
+}
+
+__global__ void __launch_bounds__(256) maxpool3_bwd_kernel(const float* __restrict__ gy,
+                                                           const unsigned char* __restrict__ idx, float* __restrict__ gx,
+                                                           int B, int H, int W, int C, int Ho, int Wo) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = (long)B * H * W * C;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  long t = i / C;
+  const int iw = (int)(t % W);
+  t /= W;
+  const int ih = (int)(t % H);
+  const int b = (int)(t / H);
+  float g = 0.f;
+  for (int r = 0; r < 3; ++r)
+    for (int s = 0; s < 3; ++s) {
+      const int th = ih + 1 - r, tw = iw + 1 - s;
+      if (th < 0 || tw < 0 || (th & 1) || (tw & 1)) continue;
+      const int oh = th >> 1, ow = tw >> 1;
+      if (oh >= Ho || ow >= Wo) continue;
+      const long o = (((long)b * Ho + oh) * Wo + ow) * C + c;
+      if (idx[o] == r * 3 + s) g += gy[o];
+    }
+  gx[i] = g;
+}
+
+DKTB_EXPORT int dktb_maxpool3_fwd(const float* x, float* y, unsigned char* idx, int B, int H, int W, int C,
+                                  cudaStream_t stream) {
+  DKTB_CHECK_ARG(x && y && idx && B > 0 && H > 0 && W > 0 && C > 0);
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long total = (long)B * Ho * Wo * C;
+  DKTB_LAUNCH(maxpool3_fwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, x, y, idx, B, H, W, C, Ho,
+              Wo);
+  return dktb_launch_status();
+}
+
+DKTB_EXPORT int dktb_maxpool3_bwd(const float* gy, const unsigned char* idx, float* gx, int B, int H, int W, int C,
+                                  cudaStream_t stream) {
+  DKTB_CHECK_ARG(gy && idx && gx && B > 0 && H > 0 && W > 0 && C > 0);
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long total = (long)B * H * W * C;
+  DKTB_LAUNCH(maxpool3_bwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, gy, idx, gx, B, H, W, C,
+              Ho, Wo);
+  return dktb_launch_status();
+}
+
+// global average pooling over HW (AvgPool2d(7) on the 7x7 ResNet map): y[b][c] = mean_p x[b][p][c]
+__global__ void avgpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int HW, int C, long total) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const long b = i / C;
+  float s = 0.f;
+  for (int p = 0; p < HW; ++p) s += x[(b * HW + p) * C + c];
+  y[i] = s / (float)HW;
+}
+__global__ void avgpool_bwd_kernel(const float* __restrict__ gy, float* __restrict__ gx, int HW, int C, long total) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const long b = i / ((long)HW * C);
+  gx[i] = gy[b * C + c] / (float)HW;
+}
+
+DKTB_EXPORT int dktb_avgpool_fwd(const float* x, float* y, int B, int HW, int C, cudaStream_t stream) {
+  DKTB_CHECK_ARG(x && y && B > 0 && HW > 0 && C > 0);
+  const long total = (long)B * C;
+  DKTB_LAUNCH(avgpool_fwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, x, y, HW, C, total);
+  return dktb_launch_status();
+}
+DKTB_EXPORT int dktb_avgpool_bwd(const float* gy, float* gx, int B, int HW, int C, cudaStream_t stream) {
+  DKTB_CHECK_ARG(gy && gx && B > 0 && HW > 0 && C > 0);
+  const long total = (long)B * HW * C;
+  DKTB_LAUNCH(avgpool_bwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, gy, gx, HW, C, total);
+  return dktb_launch_status();
+}
+
+// a += b
+__global__ void add_inplace_kernel(float* __restrict__ a, const float* __restrict__ b, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] += b[i];
+}
+DKTB_EXPORT int dktb_add_inplace(float* a, const float* b, long n, cudaStream_t stream) {
+  DKTB_CHECK_ARG(a && b && n > 0);
+  DKTB_LAUNCH(add_inplace_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, a, b, n);
+  return dktb_launch_status();
+}

@@ -46,7 +46,7 @@ class ConvNetEngine:
         self.lib = lib
         self.depth = depth
         self.dev = torch.device(device)
-        mode = os.environ.get("DKTB_CONV", "fp32")
+        mode = os.environ.get("DKTB_CONV", "tc3")      # tc3 | tc2 | tc (tcgen05 variants) | fp32 (CUDA-core kernels)
         if use_tc is None:
             use_tc = mode in ("tc", "tc2", "tc3")
         # tcgen05 3xTF32 kernels for the 64->64 convolutions (forward + dgrad); fp32 CUDA-core kernels otherwise

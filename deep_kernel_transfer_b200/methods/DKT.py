@@ -96,34 +96,28 @@ class DKT(MetaTemplate):
                      "poli1": "raw_offset", "poli2": "raw_offset"}[self.kernel]
             train += [("gp.raw_param.%d" % c, getattr(ms[c].covar_module.base_kernel, pname), 1) for c in range(C)]
         self._gp_count = len(train)
-        blocks = self.feature.blocks()
-        for i, b in enumerate(blocks):
-            train += [("bb.%d.C.weight" % i, b.C.weight, 4), ("bb.%d.C.bias" % i, b.C.bias, 4),
-                      ("bb.%d.BN.weight" % i, b.BN.weight, 4), ("bb.%d.BN.bias" % i, b.BN.bias, 4)]
+        # every backbone parameter (named_parameters de-duplicates the ConvBlock / feature_extractor aliases; bn_out is
+        # part of the trunk) and every floating-point buffer (BatchNorm running statistics)
+        train += [("bb." + n, p_, 4) for n, p_ in self.feature.named_parameters()]
         bn_out = getattr(self.feature.trunk, "bn_out", None)
-        if bn_out is not None:
-            train += [("bn_out.weight", bn_out.weight, 4), ("bn_out.bias", bn_out.bias, 4)]
         bufs = [("gp.raw_noise.%d" % c, ms[c].likelihood.noise_covar.raw_noise, 1) for c in range(C)]
-        for i, b in enumerate(blocks):
-            bufs += [("bb.%d.BN.running_mean" % i, b.BN.running_mean, 4), ("bb.%d.BN.running_var" % i, b.BN.running_var, 4)]
-        if bn_out is not None:
-            bufs += [("bn_out.running_mean", bn_out.running_mean, 4), ("bn_out.running_var", bn_out.running_var, 4)]
+        bufs += [("bb." + n, b_, 4) for n, b_ in self.feature.named_buffers() if b_.is_floating_point()]
         self._pack = FlatPack(train, dev)
         self._bufs = FlatPack(bufs, dev, with_grad=False)
         gp_end = self._pack.offsets[self._gp_count]
         self._gp_range = (0, gp_end)
         self._bb_range = (gp_end, self._pack.numel)
         pk = self._pack
-        # engine-facing parameter / gradient views
-        P, G = ConvNetParams(len(blocks)), ConvNetParams(len(blocks))
-        for i, b in enumerate(blocks):
-            for holder, grad in ((P, False), (G, True)):
-                holder.conv_w[i] = pk.view("bb.%d.C.weight" % i, grad)
-                holder.conv_b[i] = pk.view("bb.%d.C.bias" % i, grad)
-                holder.bn_w[i] = pk.view("bb.%d.BN.weight" % i, grad)
-                holder.bn_b[i] = pk.view("bb.%d.BN.bias" % i, grad)
-            P.bn_rm[i], P.bn_rv[i] = b.BN.running_mean, b.BN.running_var
-        self._P, self._G = P, G
+        # engine-facing parameter / gradient views (the modules' storage now IS the flat buffer)
+        self._convnet = hasattr(self.feature, "engine_params")
+        if self._convnet:
+            blocks = self.feature.blocks()
+            P, G = ConvNetParams(len(blocks)), ConvNetParams(len(blocks))
+            for i, b in enumerate(blocks):
+                P.conv_w[i], P.conv_b[i], P.bn_w[i], P.bn_b[i] = b.C.weight.data, b.C.bias.data, b.BN.weight.data, b.BN.bias.data
+                G.conv_w[i], G.conv_b[i], G.bn_w[i], G.bn_b[i] = b.C.weight.grad, b.C.bias.grad, b.BN.weight.grad, b.BN.bias.grad
+                P.bn_rm[i], P.bn_rv[i] = b.BN.running_mean, b.BN.running_var
+            self._P, self._G = P, G
         HP, GH = GPHeadParams(), GPHeadParams()
         HP.raw_outputscale = pk.flat[0:C]
         HP.constant = pk.flat[C:2 * C]
@@ -134,16 +128,32 @@ class DKT(MetaTemplate):
             HP.raw_param = pk.flat[2 * C:3 * C]
             GH.raw_param = pk.grad[2 * C:3 * C]
         if bn_out is not None:
-            HP.bn_w, HP.bn_b = pk.view("bn_out.weight"), pk.view("bn_out.bias")
-            GH.bn_w, GH.bn_b = pk.view("bn_out.weight", True), pk.view("bn_out.bias", True)
+            HP.bn_w, HP.bn_b = bn_out.weight.data, bn_out.bias.data
+            GH.bn_w, GH.bn_b = bn_out.weight.grad, bn_out.bias.grad
             HP.bn_rm, HP.bn_rv = bn_out.running_mean, bn_out.running_var
         self._HP, self._GH = HP, GH
         self._head = None
         self._adam = None
 
+    def _bb_forward(self, x_all, ipe, training):
+        """Backbone forward over packed episodes -> (engine, features [B, D])."""
+        eng = self.feature.engine(x_all.shape[-1], x_all.device, self.lib)
+        if self._convnet:
+            return eng, eng.forward(x_all, self._P, ipe=ipe, training=training)
+        feats = eng.forward(x_all, ipe=ipe, training=training)
+        if not training:
+            eng.tape = []
+        return eng, feats
+
+    def _bb_backward(self, eng, x_all, gfeat, ipe):
+        if self._convnet:
+            eng.backward(x_all, gfeat, self._P, self._G, ipe=ipe)
+        else:
+            eng.backward(gfeat)
+
     def _get_head(self, eng):
         if self._head is None or self._head.dev != eng.dev or self._head.D != eng.D:
-            self._head = GPHead(self.lib, self.kernel, self.n_way, eng.D, 64, eng.P, eng.dev)
+            self._head = GPHead(self.lib, self.kernel, self.n_way, eng.D, 64 if eng.P > 1 else eng.D, eng.P, eng.dev)
         return self._head
 
     def _new_adam(self):
@@ -172,18 +182,17 @@ class DKT(MetaTemplate):
         dev = x_dev.device
         st = _stream(dev)
         x_all = x_dev.reshape(E * N, *x_dev.shape[3:])
-        eng = self.feature.engine(x_dev.shape[-1], dev, lib)
-        head = self._get_head(eng)
-        head.ensure(E, N)
         dist, world = self._world()
         targets = make_targets(C, SQ, dev)
         # 1-3: train-mode features, prior, -mll
-        feats = eng.forward(x_all, self._P, ipe=N, training=True)
+        eng, feats = self._bb_forward(x_all, N, True)
+        head = self._get_head(eng)
+        head.ensure(E, N)
         zh = head.embed(feats, self._HP, E, N, training=True, out=head.w["zh_train"])
         loss = head.fit(zh, targets, self._HP, E, N, want_grad=True, grad_scale=1.0 / E)
         # 4: backward + Adam
         gfeat = head.backward(feats, zh, self._HP, self._GH, E, N)
-        eng.backward(x_all, gfeat, self._P, self._G, ipe=N)
+        self._bb_backward(eng, x_all, gfeat, N)
         if world > 1:
             dist.all_reduce(self._pack.grad)
         ad = self._adam
@@ -198,8 +207,9 @@ class DKT(MetaTemplate):
         if world > 1:      # keep replicas identical: average the BatchNorm running statistics
             dist.all_reduce(self._bufs.flat)
             lib.scale(self._bufs.flat, self._bufs.numel, 1.0 / world, st)
-        for b in self.feature.blocks():
-            b.BN.num_batches_tracked += E
+        for m_ in self.feature.modules():
+            if isinstance(m_, (nn.BatchNorm2d, nn.BatchNorm1d)):
+                m_.num_batches_tracked += E
         out = {"loss": loss.clone(), "info": head.w["info"]}
         if self.monitor:
             out.update(self.monitor_step(x_dev))
@@ -214,10 +224,9 @@ class DKT(MetaTemplate):
         N = C * SQ
         dev = x_dev.device
         x_all = x_dev.reshape(E * N, *x_dev.shape[3:])
-        eng = self.feature.engine(x_dev.shape[-1], dev, self.lib)
-        head = self._get_head(eng)
         targets = make_targets(C, SQ, dev)
-        feats_e = eng.forward(x_all, self._P, ipe=N, training=False)
+        eng, feats_e = self._bb_forward(x_all, N, False)
+        head = self._get_head(eng)
         zh_e = head.embed(feats_e, self._HP, E, N, training=False, out=head.w["zh"])
         head.fit(head.w["zh_train"], targets, self._HP, E, N, want_grad=False)
         if "mon_mean" not in head.w or head.w["mon_mean"].shape != (E, C, N):
@@ -288,10 +297,9 @@ class DKT(MetaTemplate):
         S = self.n_support
         Q = SQ - S
         x_dev = x.to(dev, non_blocking=True).float().contiguous().view(C * SQ, *x.shape[2:])
-        eng = self.feature.engine(x.shape[-1], dev, self.lib)
-        head = self._get_head(eng)
         B = C * SQ
-        feats = eng.forward(x_dev, self._P, ipe=B, training=False)          # eval-mode BN is per-sample
+        eng, feats = self._bb_forward(x_dev, B, False)                      # eval-mode BN is per-sample
+        head = self._get_head(eng)
         head.ensure(1, B)
         zh_all = head.embed(feats, self._HP, 1, B, training=False, out=head.w["zh"])[0]       # [B, D]
         idx = torch.arange(B, device=dev).view(C, SQ)
@@ -310,7 +318,7 @@ class DKT(MetaTemplate):
     def _test_head(self, eng, N):
         h = getattr(self, "_thead", None)
         if h is None or h.dev != eng.dev or h.D != eng.D:
-            h = GPHead(self.lib, self.kernel, self.n_way, eng.D, 64, eng.P, eng.dev)
+            h = GPHead(self.lib, self.kernel, self.n_way, eng.D, 64 if eng.P > 1 else eng.D, eng.P, eng.dev)
             self._thead = h
         h.ensure(1, N)
         return h

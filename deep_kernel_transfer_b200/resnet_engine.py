@@ -1,0 +1,143 @@
+"""ResNet10/18/34/50/101 feature extractors (reference backbone.py:135-247 SimpleBlock / BottleneckBlock, 330-376
+ResNet) over packed episodes: NHWC fp32, generic convolution kernels (csrc/conv_generic.cu) + channel-generic
+BatchNorm / pooling kernels (csrc/resnet_ops.cu), every BatchNorm batch = one episode.  The forward records a tape of
+(op, tensors); the backward walks it in reverse and accumulates gradients where an activation feeds two consumers
+(block input -> main branch and shortcut).  Parameters / gradients are read straight from the modules (their storage
+is the flat buffer of methods/DKT.py)."""
+import torch
+
+from .engine import BN_EPS, BN_MOMENTUM, _stream
+
+
+class ResNetEngine:
+    def __init__(self, lib, net, device):
+        self.lib, self.net, self.dev = lib, net, torch.device(device)
+        self.tape = []
+        self.D = net.final_feat_dim
+        self.P = 1
+
+    # ------------------------------------------------------------------ helpers
+    def _new(self, *shape, dtype=torch.float32):
+        return torch.empty(*shape, device=self.dev, dtype=dtype)
+
+    def _conv(self, x, m, relu=0):
+        B, H, W, Cin = x.shape
+        R = m.kernel_size[0]
+        st, pad, dil = m.stride[0], m.padding[0], m.dilation[0]
+        Ho = self.lib.conv2d_out_size(H, R, st, pad, dil)
+        Wo = self.lib.conv2d_out_size(W, R, st, pad, dil)
+        out = self._new(B, Ho, Wo, m.out_channels)
+        self.lib.conv2d_fwd(x, m.weight.data, m.bias.data if m.bias is not None else None, out, B, H, W, Cin,
+                            m.out_channels, R, R, st, pad, dil, relu, _stream(self.dev))
+        self.tape.append(("conv", x, out, m, (B, H, W, Cin, R, st, pad, dil)))
+        return out
+
+    def _bn(self, x, m, ipe, training, res=None, relu=0):
+        B, H, W, C = x.shape
+        st = _stream(self.dev)
+        E = B // ipe if training else 1
+        mean, invstd = self._new(E, C), self._new(E, C)
+        if training:
+            partial = self._new(B * C * 2)
+            self.lib.bn2d_stats(x, mean, invstd, m.running_mean, m.running_var, partial, B, H * W, C, ipe, BN_MOMENTUM,
+                                BN_EPS, st)
+        else:
+            self.lib.bn_eval_prepare(m.running_mean, m.running_var, mean, invstd, C, BN_EPS, st)
+        y = self._new(B, H, W, C)
+        self.lib.bn2d_apply(x, mean, invstd, m.weight.data, m.bias.data, res, y, B, H * W, C, ipe if training else 0, relu,
+                            st)
+        self.tape.append(("bn", x, y, m, mean, invstd, res, relu, ipe))
+        return y
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x, ipe, training):
+        """x [B,3,H,W] NCHW -> features [B, D]."""
+        lib, st, net = self.lib, _stream(self.dev), self.net
+        self.tape = []
+        B, _, H, W = x.shape
+        xh = self._new(B, H, W, 3)
+        lib.nchw_to_nhwc(x, xh, B, 3, H, W, st)
+        t = net.trunk
+        out = self._conv(xh, t[0])
+        out = self._bn(out, t[1], ipe, training, relu=1)
+        Bq, Hq, Wq, Cq = out.shape
+        Ho, Wo = (Hq + 2 - 3) // 2 + 1, (Wq + 2 - 3) // 2 + 1
+        pooled = self._new(Bq, Ho, Wo, Cq)
+        idx = self._new(Bq, Ho, Wo, Cq, dtype=torch.uint8)
+        lib.maxpool3_fwd(out, pooled, idx, Bq, Hq, Wq, Cq, st)
+        self.tape.append(("maxpool", out, pooled, idx))
+        out = pooled
+        for blk in net.blocks():
+            if blk.kind == "simple":
+                o = self._conv(out, blk.C1)
+                o = self._bn(o, blk.BN1, ipe, training, relu=1)
+                o = self._conv(o, blk.C2)
+                if blk.shortcut_type == "identity":
+                    sh = out
+                else:
+                    sh = self._bn(self._conv(out, blk.shortcut), blk.BNshortcut, ipe, training, relu=0)
+                out = self._bn(o, blk.BN2, ipe, training, res=sh, relu=1)
+            else:
+                sh = out if blk.shortcut_type == "identity" else self._conv(out, blk.shortcut)
+                o = self._bn(self._conv(out, blk.C1), blk.BN1, ipe, training, relu=1)
+                o = self._bn(self._conv(o, blk.C2), blk.BN2, ipe, training, relu=1)
+                out = self._bn(self._conv(o, blk.C3), blk.BN3, ipe, training, res=sh, relu=1)
+        Bq, Hq, Wq, Cq = out.shape
+        feats = self._new(Bq, Cq)
+        lib.avgpool_fwd(out, feats, Bq, Hq * Wq, Cq, st)
+        self.tape.append(("avgpool", out, feats))
+        return feats
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, gfeat):
+        """gfeat [B, D]; fills ``.grad`` of every backbone parameter (views into the flat gradient buffer)."""
+        lib, st = self.lib, _stream(self.dev)
+        grads = {}
+
+        def give(t, g):
+            k = t.data_ptr()
+            if k in grads:
+                lib.add_inplace(grads[k], g, g.numel(), st)
+            else:
+                grads[k] = g
+
+        last = self.tape[-1]
+        give(last[2], gfeat.contiguous())
+        for rec in reversed(self.tape):
+            kind = rec[0]
+            if kind == "avgpool":
+                _, x, y = rec
+                gx = torch.empty_like(x)
+                lib.avgpool_bwd(grads.pop(y.data_ptr()), gx, x.shape[0], x.shape[1] * x.shape[2], x.shape[3], st)
+                give(x, gx)
+            elif kind == "maxpool":
+                _, x, y, idx = rec
+                gx = torch.empty_like(x)
+                lib.maxpool3_bwd(grads.pop(y.data_ptr()), idx, gx, x.shape[0], x.shape[1], x.shape[2], x.shape[3], st)
+                give(x, gx)
+            elif kind == "bn":
+                _, x, y, m, mean, invstd, res, relu, ipe = rec
+                B, H, W, C = x.shape
+                gy = grads.pop(y.data_ptr())
+                gx = torch.empty_like(x)
+                gres = torch.empty_like(x) if res is not None else None
+                partial = self._new(B * C * 2)
+                sums = self._new((B // ipe) * C * 2)
+                lib.bn2d_bwd(x, y, gy, mean, invstd, m.weight.data, gx, gres, m.weight.grad, m.bias.grad, partial, sums, B,
+                             H * W, C, ipe, relu, st)
+                give(x, gx)
+                if res is not None:
+                    give(res, gres)
+            elif kind == "conv":
+                _, x, y, m, (B, H, W, Cin, R, stv, pad, dil) = rec
+                gy = grads.pop(y.data_ptr())
+                Cout = m.out_channels
+                ns = lib.conv2d_wgrad_nsplit(y.shape[0] * y.shape[1] * y.shape[2])
+                scratch = self._new(ns * R * R * Cin * Cout)
+                lib.conv2d_wgrad(x, gy, None, m.weight.grad, m.bias.grad if m.bias is not None else None, scratch, B, H, W,
+                                 Cin, Cout, R, R, stv, pad, dil, 0, st)
+                if Cin > 3:      # no input gradient for the stem
+                    gx = torch.empty_like(x)
+                    lib.conv2d_dgrad(gy, None, m.weight.data, gx, B, H, W, Cin, Cout, R, R, stv, pad, dil, 0, st)
+                    give(x, gx)
+        self.tape = []

@@ -119,6 +119,22 @@ int dktb_bn_relu_pool_bwd(const float* y, const float* gout, const float* mean, 
                           float* partial, float* sums, double* scratch_d, int B, int H, int W, int ipe, int in_pad,
                           int out_pad, int pool, cudaStream_t stream);
 
+/* ---- channel-generic NHWC blocks of the ResNet backbones (backbone.py:135-247, 330-376): BatchNorm2d with per-episode
+ * batch statistics for any C (multiple of 4), optional fused residual add + ReLU; MaxPool2d(3,2,1); global AvgPool. */
+int dktb_bn2d_stats(const float* x, float* mean, float* invstd, float* running_mean, float* running_var, float* partial,
+                    int B, int HW, int C, int ipe, float momentum, float eps, cudaStream_t stream);   /* partial: B*C*2 */
+int dktb_bn2d_apply(const float* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                    const float* res, float* y, int B, int HW, int C, int ipe, int relu, cudaStream_t stream);
+int dktb_bn2d_bwd(const float* x, const float* y, const float* gy, const float* mean, const float* invstd,
+                  const float* gamma, float* gx, float* gres, float* dgamma, float* dbeta, float* partial, float* sums,
+                  int B, int HW, int C, int ipe, int relu, cudaStream_t stream);   /* sums: (B/ipe)*C*2 */
+int dktb_maxpool3_fwd(const float* x, float* y, unsigned char* idx, int B, int H, int W, int C, cudaStream_t stream);
+int dktb_maxpool3_bwd(const float* gy, const unsigned char* idx, float* gx, int B, int H, int W, int C,
+                      cudaStream_t stream);
+int dktb_avgpool_fwd(const float* x, float* y, int B, int HW, int C, cudaStream_t stream);
+int dktb_avgpool_bwd(const float* gy, float* gx, int B, int HW, int C, cudaStream_t stream);
+int dktb_add_inplace(float* a, const float* b, long n, cudaStream_t stream);
+
 /* ---- feature head: bn_out BatchNorm1d (methods/DKT.py:45-48) + F.normalize (methods/DKT.py:142) -------
  * features f [E][N][D] NHWC-flattened (j = p*Cch + c); parameters indexed in the reference's NCHW-flatten
  * order (c*P + p); P <= 1 means identity mapping. */

@@ -554,3 +554,79 @@ def check_conv1_tc(lib, dev, E=2, ipe=3, H=84, W=84, seed=70, rtol=2e-5):
     assert int(err.item()) == 0
     _close(from_padded_nhwc(act.cpu()), ref_act, rtol=1e-5, atol=1e-5, what="conv1_tc fused apply")
     assert float(act.cpu()[:, 0].abs().max()) == 0.0 and float(act.cpu()[:, :, 0].abs().max()) == 0.0
+
+
+def check_resnet_ops(lib, dev, E=2, ipe=2, H=9, W=7, C=8, seed=80):
+    """Generic BatchNorm2d (+residual, +ReLU) fwd/bwd with per-episode statistics, MaxPool(3,2,1), global AvgPool."""
+    g = torch.Generator().manual_seed(seed)
+    B = E * ipe
+    x = torch.randn(B, C, H, W, generator=g) * 1.3 + 0.2
+    res = torch.randn(B, C, H, W, generator=g)
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.2
+    rm0, rv0 = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5
+    gy = torch.randn(B, C, H, W, generator=g)
+    for relu, with_res in ((1, True), (0, False), (1, False)):
+        xr, rr = x.clone().requires_grad_(True), res.clone().requires_grad_(True)
+        gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+        rm, rv = rm0.clone(), rv0.clone()
+        outs = []
+        for e in range(E):
+            o = F.batch_norm(xr[e * ipe:(e + 1) * ipe], rm, rv, gr, br, True, 0.1, 1e-5)
+            if with_res:
+                o = o + rr[e * ipe:(e + 1) * ipe]
+            outs.append(F.relu(o) if relu else o)
+        ref = torch.cat(outs)
+        (ref * gy).sum().backward()
+        nh = lambda t: t.permute(0, 2, 3, 1).contiguous().to(dev)
+        xd, rd, gyd = nh(x), nh(res), nh(gy)
+        mean, invstd = torch.empty(E, C, device=dev), torch.empty(E, C, device=dev)
+        drm, drv = rm0.clone().to(dev), rv0.clone().to(dev)
+        partial = torch.empty(B * C * 2, device=dev)
+        lib.bn2d_stats(xd, mean, invstd, drm, drv, partial, B, H * W, C, ipe, 0.1, 1e-5, 0)
+        _close(drm, rm, what="bn2d running_mean")
+        _close(drv, rv, what="bn2d running_var")
+        y = torch.empty_like(xd)
+        lib.bn2d_apply(xd, mean, invstd, gamma.to(dev), beta.to(dev), rd if with_res else None, y, B, H * W, C, ipe, relu, 0)
+        _close(y.cpu().permute(0, 3, 1, 2), ref, what="bn2d fwd")
+        gx, gres = torch.empty_like(xd), torch.empty_like(xd)
+        dg, db = torch.empty(C, device=dev), torch.empty(C, device=dev)
+        sums = torch.empty(E * C * 2, device=dev)
+        lib.bn2d_bwd(xd, y, gyd, mean, invstd, gamma.to(dev), gx, gres if with_res else None, dg, db, partial, sums, B,
+                     H * W, C, ipe, relu, 0)
+        _close(gx.cpu().permute(0, 3, 1, 2), xr.grad, rtol=2e-4, atol=1e-5, what="bn2d bwd gx")
+        _close(dg, gr.grad, rtol=2e-4, atol=1e-4, what="bn2d dgamma")
+        _close(db, br.grad, rtol=2e-4, atol=1e-4, what="bn2d dbeta")
+        if with_res:
+            _close(gres.cpu().permute(0, 3, 1, 2), rr.grad, rtol=1e-5, atol=1e-6, what="bn2d gres")
+    # eval mode (ipe = 0: one statistics row)
+    em, ei = torch.empty(C, device=dev), torch.empty(C, device=dev)
+    lib.bn_eval_prepare(rm0.to(dev), rv0.to(dev), em, ei, C, 1e-5, 0)
+    y2 = torch.empty(B, H, W, C, device=dev)
+    lib.bn2d_apply(x.permute(0, 2, 3, 1).contiguous().to(dev), em, ei, gamma.to(dev), beta.to(dev), None, y2, B, H * W, C, 0, 1, 0)
+    _close(y2.cpu().permute(0, 3, 1, 2), F.relu(F.batch_norm(x, rm0, rv0, gamma, beta, False, 0.1, 1e-5)), what="bn2d eval")
+    # max pool 3x3 s2 p1
+    xr = x.clone().requires_grad_(True)
+    ref = F.max_pool2d(xr, 3, 2, 1)
+    gp = torch.randn(ref.shape, generator=g)
+    (ref * gp).sum().backward()
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    xd = x.permute(0, 2, 3, 1).contiguous().to(dev)
+    yp = torch.empty(B, Ho, Wo, C, device=dev)
+    idx = torch.empty(B, Ho, Wo, C, device=dev, dtype=torch.uint8)
+    lib.maxpool3_fwd(xd, yp, idx, B, H, W, C, 0)
+    _close(yp.cpu().permute(0, 3, 1, 2), ref, what="maxpool fwd")
+    gxp = torch.empty_like(xd)
+    lib.maxpool3_bwd(gp.permute(0, 2, 3, 1).contiguous().to(dev), idx, gxp, B, H, W, C, 0)
+    _close(gxp.cpu().permute(0, 3, 1, 2), xr.grad, what="maxpool bwd")
+    # global average pool
+    ya = torch.empty(B, C, device=dev)
+    lib.avgpool_fwd(xd, ya, B, H * W, C, 0)
+    _close(ya, x.mean((2, 3)), what="avgpool fwd")
+    ga = torch.randn(B, C, generator=g)
+    gxa = torch.empty_like(xd)
+    lib.avgpool_bwd(ga.to(dev), gxa, B, H * W, C, 0)
+    _close(gxa.cpu().permute(0, 3, 1, 2), (ga / (H * W)).view(B, C, 1, 1).expand(B, C, H, W), what="avgpool bwd")
+    a, b2 = torch.randn(1000, generator=g), torch.randn(1000, generator=g)
+    ad = a.clone().to(dev)
+    lib.add_inplace(ad, b2.to(dev), 1000, 0)
+    _close(ad, a + b2, what="add")

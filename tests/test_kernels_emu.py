@@ -65,3 +65,7 @@ def test_conv2d_generic(lib, cfg):
 
 def test_spectral(lib):
     kc.check_spectral(lib, DEV)
+
+
+def test_resnet_ops(lib):
+    kc.check_resnet_ops(lib, DEV)

@@ -86,3 +86,8 @@ def test_conv1_tc(lib):
     kc.check_conv1_tc(lib, DEV)
     kc.check_conv1_tc(lib, DEV, E=1, ipe=2, H=32, W=32, seed=71)
     kc.check_conv1_tc(lib, DEV, E=2, ipe=2, H=21, W=37, seed=72)
+
+
+def test_resnet_ops(lib):
+    kc.check_resnet_ops(lib, DEV)
+    kc.check_resnet_ops(lib, DEV, E=2, ipe=3, H=14, W=14, C=256, seed=81)
