@@ -167,7 +167,7 @@ def forward(arch, p, x, training=False, update_running=True):
                     out = F.relu(o + sh)
                 indim = outdim
                 t += 1
-        out = F.avg_pool2d(out, 7)
+        out = F.avg_pool2d(out, min(7, out.shape[-1]))   # 7 at the reference's 224x224 input (backbone.py:365)
         out = out.reshape(out.size(0), -1)
     if "trunk.bn_out.weight" in p:
         out = _bn(out, p, "trunk.bn_out", training, update_running)

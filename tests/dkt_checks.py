@@ -253,3 +253,63 @@ def check_regression(dev, lib=None, image=36, n=7, n_support=4, tol=2e-4, kernel
     assert rel_err(lo, lo_ref) <= 1e-4 and rel_err(hi, hi_ref) <= 1e-4
     assert rel_err(((pred.mean.cpu() - y) ** 2).mean(), mse_ref) <= 1e-4
     return model
+
+
+def check_train_step_arch(arch, model_factory, dev, image_size, n_way=2, n_support=1, n_query=2, E=2, kernel="rbf",
+                          lib=None, tol=1e-4, env_factor=4.0):
+    """One packed meta-train step of an arbitrary backbone (ResNet*) against the oracle: loss, every backbone / GP
+    gradient (fp64 arbiter + fp32 envelope), monitoring arg-max after re-synchronising the post-step weights."""
+    from deep_kernel_transfer_b200.methods.DKT import DKT
+    torch.manual_seed(0)
+    o32 = oep.OracleDKT(arch, kernel, n_way=n_way, n_support=n_support, seed=0)
+    o32.gp["raw_outputscale"] = torch.linspace(-0.3, 0.6, n_way)
+    o32.gp["constant"] = torch.linspace(0.1, -0.2, n_way)
+    if "raw_lengthscale" in o32.gp:
+        o32.gp["raw_lengthscale"] = torch.linspace(1.5, 2.5, n_way)
+    o64 = oep.OracleDKT(arch, kernel, n_way=n_way, n_support=n_support, seed=0, dtype=torch.float64)
+    o64.bb = {k: (v.detach().double() if v.is_floating_point() else v.clone()) for k, v in o32.bb.items()}
+    o64.gp = {k: v.detach().double() for k, v in o32.gp.items()}
+    model = DKT(model_factory, n_way, n_support, kernel=kernel, episodes_per_step=E, lib=lib)
+    sd = model.feature.state_dict()
+    model.feature.load_state_dict({k: o32.bb[k].detach().clone() for k in sd})
+    for c, m in enumerate(model.model.models):
+        m.covar_module.raw_outputscale.data.fill_(float(o32.gp["raw_outputscale"][c]))
+        m.mean_module.constant.data.fill_(float(o32.gp["constant"][c]))
+        if "raw_lengthscale" in o32.gp:
+            m.covar_module.base_kernel.raw_lengthscale.data.fill_(float(o32.gp["raw_lengthscale"][c]))
+    model = model.to(dev)
+    model.train()
+    xs = torch.stack([oep.synthetic_episode(e, n_way, n_support, n_query, image_size) for e in range(E)])
+    r64 = o64.train_step(xs.double(), monitor=False)
+    ref = o32.train_step(xs)
+    model._ensure_packed()
+    model._new_adam()
+    out = model.train_step(xs.to(dev))
+    assert int(out["info"].cpu().abs().sum()) == 0
+    assert rel_err(out["loss"], r64["loss"]) <= tol, rel_err(out["loss"], r64["loss"])
+    bad = {}
+    for name, p_ in model.feature.named_parameters():
+        if name.endswith(".bias") and name.replace(".bias", ".weight") in ref["grads"] and p_.dim() == 1 and \
+                ref["grads"][name].abs().max() < 1e-6 * ref["grads"][name.replace(".bias", ".weight")].abs().max():
+            continue      # a bias that BatchNorm cancels: rounding noise on both sides
+        e = rel_err(p_.grad, r64["grads"][name])
+        floor = rel_err(ref["grads"][name], r64["grads"][name])
+        if e > max(tol, env_factor * floor):
+            bad[name] = (e, floor)
+    gos = torch.stack([m.covar_module.raw_outputscale.grad for m in model.model.models])
+    e = rel_err(gos, r64["grads"]["raw_outputscale"])
+    if e > max(tol, env_factor * rel_err(ref["grads"]["raw_outputscale"], r64["grads"]["raw_outputscale"])):
+        bad["raw_outputscale"] = e
+    assert not bad, bad
+    # monitoring with the oracle's post-step weights
+    model.feature.load_state_dict({k: o32.bb[k].detach().clone() for k in sd})
+    for c, m in enumerate(model.model.models):
+        m.covar_module.raw_outputscale.data.fill_(float(o32.gp["raw_outputscale"][c].detach()))
+        m.mean_module.constant.data.fill_(float(o32.gp["constant"][c].detach()))
+        if "raw_lengthscale" in o32.gp:
+            m.covar_module.base_kernel.raw_lengthscale.data.fill_(float(o32.gp["raw_lengthscale"][c].detach()))
+    model._ensure_packed()
+    mon = model.monitor_step(xs.to(dev))
+    np.testing.assert_allclose(mon["acc_support"].cpu().numpy(), ref["acc_support"], atol=1e-4)
+    np.testing.assert_allclose(mon["acc_query"].cpu().numpy(), ref["acc_query"], atol=1e-4)
+    return model

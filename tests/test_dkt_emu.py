@@ -39,6 +39,7 @@ def test_product_refuses_cpu_without_library():
         m._ensure_packed()
 
 
+@pytest.mark.slow
 def test_regression_spectral_matches_oracle(lib):
     dkt_checks.check_regression(torch.device("cpu"), lib=lib, kernel="spectral", image=36, n=5, n_support=3)
 
@@ -59,3 +60,8 @@ def test_regression_matches_oracle(lib):
     np.random.seed(0)
     mse = model.test_loop(5)
     assert torch.isfinite(mse)
+
+
+@pytest.mark.slow
+def test_resnet10_train_step_matches_oracle(lib):
+    dkt_checks.check_train_step_arch("ResNet10", backbone.ResNet10, torch.device("cpu"), image_size=32, lib=lib)

@@ -75,3 +75,20 @@ def test_regression_qmul_shape():
     """DKT regression at the QMUL shape: 19 images of 100x100 -> Conv3 features [19, 2916], RBF GP, learned noise."""
     model = dkt_checks.check_regression(DEV, image=100, n=19, n_support=4)
     assert model.feature_extractor._engine.D == 2916
+
+
+def test_resnet10_small():
+    from deep_kernel_transfer_b200 import backbone
+    dkt_checks.check_train_step_arch("ResNet10", backbone.ResNet10, DEV, image_size=32)
+
+
+@pytest.mark.parametrize("arch", ["ResNet18", "ResNet50"])
+def test_resnet_reference_resolution(arch):
+    """224x224 inputs (the reference's ResNet resolution), RBF kernel (BASELINE config #4 / #5 backbones)."""
+    from deep_kernel_transfer_b200 import backbone
+    dkt_checks.check_train_step_arch(arch, getattr(backbone, arch), DEV, image_size=224, n_way=2, n_support=1, n_query=1,
+                                     E=1, env_factor=6.0)
+
+
+def test_regression_spectral():
+    dkt_checks.check_regression(DEV, kernel="spectral", image=36, n=5, n_support=3)
