@@ -176,3 +176,42 @@ class OracleDKTRegression:
             std = var.clamp_min(1e-10).sqrt()
             mse = ((mean - y_all) ** 2).mean()
         return mse, mean, mean - 2.0 * std, mean + 2.0 * std
+
+
+# ----------------------------------------------------------------------------- sines (sines/train_DKT.py)
+class OracleSines:
+    """MLP 1->40->40 (ReLU) + spectral-mixture GP (Q=4, ARD 40) + learned noise, Adam lr 1e-3 (sines/train_DKT.py:113-180)."""
+
+    def __init__(self, dtype=torch.float32, seed=0):
+        g = torch.Generator().manual_seed(seed)
+        u = lambda *s, b=1.0: ((torch.rand(*s, generator=g) * 2 - 1) * b).to(dtype)
+        self.p = {"layer1.weight": u(40, 1), "layer1.bias": u(40), "layer2.weight": u(40, 40, b=40 ** -0.5),
+                  "layer2.bias": u(40, b=40 ** -0.5)}
+        self.gp = ogp.default_gp_params("spectral", 1, 40, dtype=dtype, classification=False)
+        self.optimizer = None
+
+    def feats(self, x):
+        h = F.relu(F.linear(x, self.p["layer1.weight"], self.p["layer1.bias"]))
+        return F.relu(F.linear(h, self.p["layer2.weight"], self.p["layer2.bias"]))
+
+    def train_step(self, x, y):
+        names = ogp.trainable_gp_names("spectral", classification=False)
+        if self.optimizer is None:
+            for v in self.p.values():
+                v.requires_grad_(True)
+            for k in names:
+                self.gp[k].requires_grad_(True)
+            self.optimizer = torch.optim.Adam([{"params": [self.gp[k] for k in names], "lr": 1e-3},
+                                               {"params": list(self.p.values()), "lr": 1e-3}])
+        self.optimizer.zero_grad()
+        loss = ogp.mll_loss("spectral", self.feats(x), y.unsqueeze(0), self.gp)
+        loss.backward()
+        grads = {k: v.grad.clone() for k, v in self.p.items()}
+        grads.update({k: self.gp[k].grad.clone() for k in names})
+        self.optimizer.step()
+        return {"loss": loss.detach(), "grads": grads}
+
+    def predict(self, xs, ys, xq):
+        with torch.no_grad():
+            mean, var = ogp.predict("spectral", self.feats(xs), ys.unsqueeze(0), self.feats(xq), self.gp, want_var=True)
+        return mean[0], var[0]

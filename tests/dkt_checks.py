@@ -313,3 +313,48 @@ def check_train_step_arch(arch, model_factory, dev, image_size, n_way=2, n_suppo
     np.testing.assert_allclose(mon["acc_support"].cpu().numpy(), ref["acc_support"], atol=1e-4)
     np.testing.assert_allclose(mon["acc_query"].cpu().numpy(), ref["acc_query"], atol=1e-4)
     return model
+
+
+def check_sines(dev, lib=None, steps=3, tol=2e-4):
+    """sines/train_DKT.py protocol: per-step loss / gradients / Adam update and prediction against the oracle."""
+    from deep_kernel_transfer_b200.sines import SinesDKT, Task_Distribution
+    np.random.seed(0)
+    o = oep.OracleSines()
+    o64 = oep.OracleSines(dtype=torch.float64)
+    model = SinesDKT(lib=lib)
+    model.net.load_state_dict({k: v.detach().clone() for k, v in o.p.items()})
+    model = model.to(dev)
+    tasks = Task_Distribution()
+    for step in range(steps):
+        x, y = tasks.sample_task().sample_data(10, noise=0.1)
+        o64.p = {k: v.detach().double() for k, v in o.p.items()}
+        o64.gp = {k: v.detach().double() for k, v in o.gp.items()}
+        o64.optimizer = None
+        r64 = o64.train_step(x.double(), y.double())
+        ref = o.train_step(x, y)
+        loss = model.train_step(x.to(dev), y.to(dev))
+        assert int(model._last_info.cpu().abs().sum()) == 0
+        assert rel_err(loss, r64["loss"]) <= tol
+        got = {"layer1.weight": model.net.layer1.weight.grad, "layer1.bias": model.net.layer1.bias.grad,
+               "layer2.weight": model.net.layer2.weight.grad, "layer2.bias": model.net.layer2.bias.grad,
+               "constant": model.mean_module.constant.grad, "raw_noise": model.likelihood.noise_covar.raw_noise.grad,
+               "raw_mixture_weights": model.covar_module.raw_mixture_weights.grad,
+               "raw_mixture_means": model.covar_module.raw_mixture_means.grad,
+               "raw_mixture_scales": model.covar_module.raw_mixture_scales.grad}
+        bad = {}
+        for k, v in got.items():
+            e = rel_err(v, r64["grads"][k])
+            floor = rel_err(ref["grads"][k], r64["grads"][k])
+            if e > max(tol, 3.0 * floor):
+                bad[k] = (e, floor)
+        assert not bad, (step, bad)
+        # re-synchronise so that the next step starts from identical weights (Adam sign flips of noise-level gradients)
+        model.net.load_state_dict({k: v.detach().clone() for k, v in o.p.items()})
+        model.mean_module.constant.data.copy_(o.gp["constant"].detach())
+        model.likelihood.noise_covar.raw_noise.data.copy_(o.gp["raw_noise"].detach())
+        for nm in ("raw_mixture_weights", "raw_mixture_means", "raw_mixture_scales"):
+            getattr(model.covar_module, nm).data.copy_(o.gp[nm].detach().to(dev))
+    x_all, y_all = tasks.sample_task().sample_data(40, noise=0.1, sort=True)
+    mean_ref, var_ref = o.predict(x_all[:5], y_all[:5], x_all[5:])
+    mean, var = model.predict(x_all[:5].to(dev), y_all[:5].to(dev), x_all[5:].to(dev))
+    assert rel_err(mean, mean_ref) <= tol and rel_err(var, var_ref) <= tol

@@ -65,3 +65,7 @@ def test_regression_matches_oracle(lib):
 @pytest.mark.slow
 def test_resnet10_train_step_matches_oracle(lib):
     dkt_checks.check_train_step_arch("ResNet10", backbone.ResNet10, torch.device("cpu"), image_size=32, lib=lib)
+
+
+def test_sines_matches_oracle(lib):
+    dkt_checks.check_sines(torch.device("cpu"), lib=lib)

@@ -92,3 +92,7 @@ def test_resnet_reference_resolution(arch):
 
 def test_regression_spectral():
     dkt_checks.check_regression(DEV, kernel="spectral", image=36, n=5, n_support=3)
+
+
+def test_sines():
+    dkt_checks.check_sines(DEV, steps=5)
