@@ -52,7 +52,8 @@ SIGNATURES = {
     "dktb_gp_predict": ("plpppppiiiis", ctypes.c_int),
     "dktb_center_rows": ("pppiiiis", ctypes.c_int),
     "dktb_row_sqnorm": ("pplis", ctypes.c_int),
-    "dktb_kernel_fwd": ("ipppppiiiis", ctypes.c_int),
+    "dktb_sqdist": ("pppiiiis", ctypes.c_int),
+    "dktb_kernel_fwd": ("ippppiiiis", ctypes.c_int),
     "dktb_kernel_bwd": ("ipppppppiiis", ctypes.c_int),
     "dktb_gp_predict_var": ("plplppppiiiis", ctypes.c_int),
     "dktb_conv2d_out_size": ("iiiii", ctypes.c_int),

@@ -315,8 +315,7 @@ class GPHead:
         w["df"] = torch.empty(E, N, D, device=dev, dtype=f32)
         w["pgrad"] = torch.empty(E * 2 * D, device=dev, dtype=f32)
         if self.family is not None:
-            w["xc"] = torch.empty(E, N, D, device=dev, dtype=f32)
-            w["sq"] = torch.empty(E, N, device=dev, dtype=f32)
+            w["d2"] = torch.empty(E, N, N, device=dev, dtype=f32)
             w["kb"] = torch.empty(E, C, N, N, device=dev, dtype=f32)
             w["dg"] = torch.empty(E, N, N, device=dev, dtype=f32)
             w["dparam"] = torch.empty(C, device=dev, dtype=f32)
@@ -349,10 +348,12 @@ class GPHead:
             lib.gram(zh, zh, w["gram"], E, N, N, self.D, st)
             kb, stride = w["gram"], 0
         else:
-            xc = self._centre(zh, zh, w["xc"], E, N, N)
-            lib.gram(xc, xc, w["gram"], E, N, N, self.D, st)
-            lib.row_sqnorm(xc, w["sq"], E * N, self.D, st)
-            lib.kernel_fwd(self.family, w["gram"], w["sq"], w["sq"], HP.raw_param, w["kb"], E, C, N, N, st)
+            if self.centred:      # rbf / matern: direct squared distances (no Gram cancellation, exact zero diagonal)
+                lib.sqdist(zh, zh, w["d2"], E, N, N, self.D, st)
+                lib.kernel_fwd(self.family, None, w["d2"], HP.raw_param, w["kb"], E, C, N, N, st)
+            else:
+                lib.gram(zh, zh, w["gram"], E, N, N, self.D, st)
+                lib.kernel_fwd(self.family, w["gram"], None, HP.raw_param, w["kb"], E, C, N, N, st)
             kb, stride = w["kb"], N * N
         lib.gp_fit(kb, stride, targets, 0, HP.raw_outputscale, HP.constant, HP.raw_noise, w["alpha"], None,
                    w["loss_terms"], w["info"], w["dk"] if want_grad else None, w["dhyper"] if want_grad else None,
@@ -361,25 +362,18 @@ class GPHead:
                       E, C, st)
         return w["loss"]
 
-    def _centre(self, x, ref, out, E, N, Nr):
-        if not self.centred:
-            return x
-        self.lib.center_rows(x, ref, out, E, N, Nr, self.D, _stream(self.dev))
-        return out
-
     def backward(self, feats, zh, HP, GH, E, N):
         """Gradient w.r.t. the backbone features [E*N, D]; fills GH.{bn_w,bn_b,raw_outputscale,constant,raw_param}."""
         lib, st, w = self.lib, _stream(self.dev), self.w
         if self.family is None:
             lib.gram_bwd(w["dk"], zh, w["dzh"], E, self.C, N, self.D, 1.0, st)
         else:
-            xc = w["xc"] if self.centred else zh
-            lib.kernel_bwd(self.family, w["gram"], w["sq"], HP.raw_param, w["dk"], w["dg"], w["dparam"], w["kscratch"],
-                           E, self.C, N, st)
+            lib.kernel_bwd(self.family, None if self.centred else w["gram"], w["d2"] if self.centred else None,
+                           HP.raw_param, w["dk"], w["dg"], w["dparam"], w["kscratch"], E, self.C, N, st)
             GH.raw_param.copy_(w["dparam"])
-            # rbf / matern are translation invariant: the gradient w.r.t. the centred rows already sums to zero,
-            # so the centring needs no backward pass
-            lib.gram_bwd(w["dg"], xc, w["dzh"], E, 1, N, self.D, 1.0, st)
+            # dg carries the distance gradient both off the diagonal (-2 A / l^2) and on it (row sums), so
+            # (dg + dg^T) Z is exactly sum_j A_ij 2 (z_i - z_j) / l^2 -- no cancellation in the backward pass
+            lib.gram_bwd(w["dg"], zh, w["dzh"], E, 1, N, self.D, 1.0, st)
         g = w["dzh"]
         if self.normalize:
             lib.l2norm_bwd(zh, g, w["inv"], w["dz"], E * N, self.D, st)
@@ -404,15 +398,13 @@ class GPHead:
         t = self.w.setdefault("pred_tmp", {})
         key = (E, M, N)
         if t.get("key") != key:
-            t.update(key=key, xt=torch.empty(E, M, self.D, device=dev, dtype=f32),
-                     xr=torch.empty(E, N, self.D, device=dev, dtype=f32), sqt=torch.empty(E, M, device=dev, dtype=f32),
-                     sqr=torch.empty(E, N, device=dev, dtype=f32), kx=torch.empty(E, C, M, N, device=dev, dtype=f32))
-        xr = self._centre(zh_train, zh_train, t["xr"], E, N, N)
-        xt = self._centre(zh_test, zh_train, t["xt"], E, M, N)
-        lib.gram(xt, xr, kx_buf, E, M, N, self.D, st)
-        lib.row_sqnorm(xt, t["sqt"], E * M, self.D, st)
-        lib.row_sqnorm(xr, t["sqr"], E * N, self.D, st)
-        lib.kernel_fwd(self.family, kx_buf, t["sqt"], t["sqr"], HP.raw_param, t["kx"], E, C, M, N, st)
+            t.update(key=key, kx=torch.empty(E, C, M, N, device=dev, dtype=f32))
+        if self.centred:
+            lib.sqdist(zh_test, zh_train, kx_buf, E, M, N, self.D, st)
+            lib.kernel_fwd(self.family, None, kx_buf, HP.raw_param, t["kx"], E, C, M, N, st)
+        else:
+            lib.gram(zh_test, zh_train, kx_buf, E, M, N, self.D, st)
+            lib.kernel_fwd(self.family, kx_buf, None, HP.raw_param, t["kx"], E, C, M, N, st)
         lib.gp_predict(t["kx"], M * N, self.w["alpha"], HP.raw_outputscale, HP.constant, mean_out, pred_out, E, C, M, N,
                        st)
 

@@ -121,10 +121,9 @@ class DKT(nn.Module):
             w["xc"].copy_(zz)
             lib.spectral_fwd(w["xc"], w["xc"], rw, rmu, rv, w["kb"], w["ec"], 1, N, N, D, Q, 36, self._P, st)
         else:
-            lib.center_rows(zz, zz, w["xc"], 1, N, N, D, st)
-            lib.gram(w["xc"], w["xc"], w["gram"], 1, N, N, D, st)
-            lib.row_sqnorm(w["xc"], w["sq"], N, D, st)
-            lib.kernel_fwd(1, w["gram"], w["sq"], w["sq"], rl, w["kb"], 1, 1, N, N, st)
+            w["xc"].copy_(zz)
+            lib.sqdist(w["xc"], w["xc"], w["gram"], 1, N, N, D, st)          # w["gram"] holds squared distances
+            lib.kernel_fwd(1, None, w["gram"], rl, w["kb"], 1, 1, N, N, st)
         lib.gp_fit(w["kb"], N * N, y.contiguous().view(1, 1, N), N, ros, cst, rn, w["alpha"], w["linv"], w["lt"], w["info"],
                    w["dk"] if want_grad else None, w["dh"] if want_grad else None, 1.0, 0.0, 1, 1, N, st)
         lib.gp_reduce(w["lt"], w["dh"] if want_grad else None, w["loss"], w["hyper"] if want_grad else None, 1, 1, st)
@@ -157,7 +156,7 @@ class DKT(nn.Module):
             lib.spectral_bwd(w["xc"], rw, rmu, rv, w["dk"], w["ec"], w["dw"], w["dmu"], w["dv"], w["dz"], 1, N, D, Q, 36,
                              self._P, st)
         else:
-            lib.kernel_bwd(1, w["gram"], w["sq"], rl, w["dk"], w["dg"], w["dparam"], w["ksc"], 1, 1, N, st)
+            lib.kernel_bwd(1, None, w["gram"], rl, w["dk"], w["dg"], w["dparam"], w["ksc"], 1, 1, N, st)
             lib.gram_bwd(w["dg"], w["xc"], w["dz"], 1, 1, N, D, 1.0, st)
         gw = [torch.empty_like(t) for t in ws]
         gb = [torch.empty_like(t) for t in bs]
@@ -222,10 +221,8 @@ class DKT(nn.Module):
             lib.spectral_fwd(z_q.view(1, M, D), w["xc"], rw, rmu, rv, w["kx"], None, 1, M, N, D, Q, 36, self._P, st)
             w["kss"].copy_(torch.nn.functional.softplus(rw).sum().expand(1, 1, M))   # k(x*,x*) = sum_q w_q
         else:
-            lib.center_rows(z_q.view(1, M, D), z_s.view(1, N, D), w["xt"], 1, M, N, D, st)
-            lib.gram(w["xt"], w["xc"], w["gx"], 1, M, N, D, st)
-            lib.row_sqnorm(w["xt"], w["sqt"], M, D, st)
-            lib.kernel_fwd(1, w["gx"], w["sqt"], w["sq"], rl, w["kx"], 1, 1, M, N, st)
+            lib.sqdist(z_q.view(1, M, D), w["xc"], w["gx"], 1, M, N, D, st)
+            lib.kernel_fwd(1, None, w["gx"], rl, w["kx"], 1, 1, M, N, st)
             w["kss"].fill_(1.0)          # k_rbf(x*, x*) = 1
         lib.gp_predict(w["kx"], M * N, w["alpha"], ros, cst, w["mean"], None, 1, 1, M, N, st)
         lib.gp_predict_var(w["kx"], M * N, w["kss"], M, w["linv"], ros, rn, w["var"], 1, 1, M, N, st)

@@ -175,11 +175,13 @@ int dktb_gp_predict(const float* kx, long kx_class_stride, const float* alpha, c
  * 3 poli1, 4 poli2 (offset).  kb [E][C][M][N]: one kernel matrix per one-vs-rest model. */
 int dktb_center_rows(const float* x, const float* ref, float* out, int E, int N, int Nr, int D, cudaStream_t stream);
 int dktb_row_sqnorm(const float* x, float* sq, long rows, int D, cudaStream_t stream);
-int dktb_kernel_fwd(int kind, const float* g, const float* sq1, const float* sq2, const float* raw_param, float* kb,
-                    int E, int C, int M, int N, cudaStream_t stream);
+int dktb_sqdist(const float* x1, const float* x2, float* out, int E, int M, int N, int D, cudaStream_t stream);
+/* g = Gram matrix (linear / poli), d2 = squared distances from dktb_sqdist (rbf / matern); the unused one may be NULL */
+int dktb_kernel_fwd(int kind, const float* g, const float* d2, const float* raw_param, float* kb, int E, int C, int M,
+                    int N, cudaStream_t stream);
 /* dkb [E][C][N][N] = dLoss/dKb_c -> dg [E][N][N] (summed over classes, incl. the diagonal terms through the norms),
  * dparam [C] = dLoss/d raw_param; scratch: E*C*N floats */
-int dktb_kernel_bwd(int kind, const float* g, const float* sq, const float* raw_param, const float* dkb, float* dg,
+int dktb_kernel_bwd(int kind, const float* g, const float* d2, const float* raw_param, const float* dkb, float* dg,
                     float* dparam, float* scratch, int E, int C, int N, cudaStream_t stream);
 /* predictive variance of likelihood(model(x*)): s*kss - ||L^-1 s kx||^2 + noise  (DKT_regression.py:90-93) */
 int dktb_gp_predict_var(const float* kx, long kx_class_stride, const float* kss, long kss_class_stride,

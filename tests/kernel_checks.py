@@ -326,7 +326,7 @@ def check_gp_family(lib, dev, kernel, E=2, C=3, per_class=3, D=12, M=7, seed=40,
     through the epilogue and the Gram, prediction with mean and variance -- against the oracle's autograd."""
     g = torch.Generator().manual_seed(seed)
     N = C * per_class
-    scale = 0.6 if kernel in ("rbf", "matern") else 0.4
+    scale = 1.2 / D ** 0.5 if kernel in ("rbf", "matern") else 0.4     # keep ||x - x'||^2 / l^2 = O(1)
     z = torch.randn(E, N, D, generator=g) * scale
     zt = torch.randn(E, M, D, generator=g) * scale
     targets = -torch.ones(C, N)
@@ -345,18 +345,18 @@ def check_gp_family(lib, dev, kernel, E=2, C=3, per_class=3, D=12, M=7, seed=40,
     kind = KIND[kernel]
     centred = kernel in ("rbf", "matern")
     zd = z.to(dev)
-    xc = torch.empty_like(zd)
-    if centred:
-        lib.center_rows(zd, zd, xc, E, N, N, D, 0)
-    else:
-        xc = zd
+    xc = zd
     gram = torch.empty(E, N, N, device=dev)
+    d2 = torch.empty(E, N, N, device=dev)
     lib.gram(xc, xc, gram, E, N, N, D, 0)
+    lib.sqdist(xc, xc, d2, E, N, N, D, 0)
+    _close(d2, torch.cdist(z, z) ** 2, rtol=1e-5, atol=1e-6, what="sqdist")
+    assert float(d2.cpu().diagonal(dim1=1, dim2=2).abs().max()) == 0.0
     sq = torch.empty(E, N, device=dev)
     lib.row_sqnorm(xc, sq, E * N, D, 0)
     rp = p[pn].detach().to(dev)
     kb = torch.empty(E, C, N, N, device=dev)
-    lib.kernel_fwd(kind, gram, sq, sq, rp, kb, E, C, N, N, 0)
+    lib.kernel_fwd(kind, None if centred else gram, d2 if centred else None, rp, kb, E, C, N, N, 0)
     alpha = torch.empty(E, C, N, device=dev)
     linv = torch.empty(E, C, N, N, device=dev)
     lt = torch.empty(E, C, device=dev)
@@ -375,24 +375,23 @@ def check_gp_family(lib, dev, kernel, E=2, C=3, per_class=3, D=12, M=7, seed=40,
     dg = torch.empty(E, N, N, device=dev)
     dparam = torch.empty(C, device=dev)
     scratch = torch.empty(E * C * N, device=dev)
-    lib.kernel_bwd(kind, gram, sq, rp, dk, dg, dparam, scratch, E, C, N, 0)
+    lib.kernel_bwd(kind, None if centred else gram, d2 if centred else None, rp, dk, dg, dparam, scratch, E, C, N, 0)
     _close(dparam, p[pn].grad, rtol=rtol, atol=1e-6, what=kernel + " d " + pn)
     dz = torch.empty(E, N, D, device=dev)
     lib.gram_bwd(dg, xc, dz, E, 1, N, D, 1.0, 0)
     _close(dz, zr.grad, rtol=rtol, atol=1e-6, what=kernel + " d z")
     # prediction: mean + variance
     ztd = zt.to(dev)
-    xtc = torch.empty_like(ztd)
-    if centred:
-        lib.center_rows(ztd, zd, xtc, E, M, N, D, 0)
-    else:
-        xtc = ztd
+    xtc = ztd
     gx = torch.empty(E, M, N, device=dev)
-    lib.gram(xtc, xc, gx, E, M, N, D, 0)
+    if centred:
+        lib.sqdist(xtc, xc, gx, E, M, N, D, 0)
+    else:
+        lib.gram(xtc, xc, gx, E, M, N, D, 0)
     sqt = torch.empty(E, M, device=dev)
     lib.row_sqnorm(xtc, sqt, E * M, D, 0)
     kx = torch.empty(E, C, M, N, device=dev)
-    lib.kernel_fwd(kind, gx, sqt, sq, rp, kx, E, C, M, N, 0)
+    lib.kernel_fwd(kind, None if centred else gx, gx if centred else None, rp, kx, E, C, M, N, 0)
     mean = torch.empty(E, C, M, device=dev)
     pred = torch.empty(E, M, device=dev, dtype=torch.int32)
     lib.gp_predict(kx, M * N, alpha, ros, cst, mean, pred, E, C, M, N, 0)
@@ -400,8 +399,8 @@ def check_gp_family(lib, dev, kernel, E=2, C=3, per_class=3, D=12, M=7, seed=40,
     kss = torch.empty(E, C, M, device=dev)
     for c in range(C):
         tmp = torch.empty(E * M, 1, 1, 1, device=dev)
-        lib.kernel_fwd(kind, sqt.view(E * M, 1, 1).contiguous(), sqt.view(E * M, 1).contiguous(),
-                       sqt.view(E * M, 1).contiguous(), rp[c:c + 1].contiguous(), tmp, E * M, 1, 1, 1, 0)
+        zeros = torch.zeros(E * M, 1, 1, device=dev)
+        lib.kernel_fwd(kind, sqt.view(E * M, 1, 1).contiguous(), zeros, rp[c:c + 1].contiguous(), tmp, E * M, 1, 1, 1, 0)
         kss[:, c, :] = tmp.view(E, M)
     var = torch.empty(E, C, M, device=dev)
     lib.gp_predict_var(kx, M * N, kss.contiguous(), M, linv, ros, rn, var, E, C, M, N, 0)
