@@ -47,6 +47,9 @@ SIGNATURES = {
     "dktb_gram": ("pppiiiis", ctypes.c_int),
     "dktb_gp_max_n": ("", ctypes.c_int),
     "dktb_gp_fit": ("plplpppppppppffiiis", ctypes.c_int),
+    "dktb_gp_large_max_n": ("", ctypes.c_int),
+    "dktb_gp_large_work_floats": ("iii", ctypes.c_long),
+    "dktb_gp_fit_large": ("plplppppppppppffiiis", ctypes.c_int),
     "dktb_gp_reduce": ("ppppiis", ctypes.c_int),
     "dktb_gram_bwd": ("pppiiiifs", ctypes.c_int),
     "dktb_gp_predict": ("plpppppiiiis", ctypes.c_int),

@@ -355,9 +355,19 @@ class GPHead:
                 lib.gram(zh, zh, w["gram"], E, N, N, self.D, st)
                 lib.kernel_fwd(self.family, w["gram"], None, HP.raw_param, w["kb"], E, C, N, N, st)
             kb, stride = w["kb"], N * N
-        lib.gp_fit(kb, stride, targets, 0, HP.raw_outputscale, HP.constant, HP.raw_noise, w["alpha"], None,
-                   w["loss_terms"], w["info"], w["dk"] if want_grad else None, w["dhyper"] if want_grad else None,
-                   grad_scale, jitter, E, C, N, st)
+        if N <= lib.gp_max_n():
+            lib.gp_fit(kb, stride, targets, 0, HP.raw_outputscale, HP.constant, HP.raw_noise, w["alpha"], None,
+                       w["loss_terms"], w["info"], w["dk"] if want_grad else None, w["dhyper"] if want_grad else None,
+                       grad_scale, jitter, E, C, N, st)
+        else:               # beyond shared memory: blocked factorisation on a global workspace (csrc/gp_large.cu)
+            if N > lib.gp_large_max_n():
+                raise NotImplementedError("exact-GP systems with N = %d > %d" % (N, lib.gp_large_max_n()))
+            need = lib.gp_large_work_floats(E, C, N)
+            if w.get("gp_work") is None or w["gp_work"].numel() < need:
+                w["gp_work"] = torch.empty(need, device=self.dev)
+            lib.gp_fit_large(kb, stride, targets, 0, HP.raw_outputscale, HP.constant, HP.raw_noise, w["alpha"], None,
+                             w["loss_terms"], w["info"], w["dk"] if want_grad else None,
+                             w["dhyper"] if want_grad else None, w["gp_work"], grad_scale, jitter, E, C, N, st)
         lib.gp_reduce(w["loss_terms"], w["dhyper"] if want_grad else None, w["loss"], w["hyper"] if want_grad else None,
                       E, C, st)
         return w["loss"]

@@ -13,6 +13,7 @@ class ResNetEngine:
     def __init__(self, lib, net, device):
         self.lib, self.net, self.dev = lib, net, torch.device(device)
         self.tape = []
+        self.trace = None            # tests may set a list: backward appends (record, gy, gx, gres) per op
         self.D = net.final_feat_dim
         self.P = 1
 
@@ -125,6 +126,8 @@ class ResNetEngine:
                 sums = self._new((B // ipe) * C * 2)
                 lib.bn2d_bwd(x, y, gy, mean, invstd, m.weight.data, gx, gres, m.weight.grad, m.bias.grad, partial, sums, B,
                              H * W, C, ipe, relu, st)
+                if self.trace is not None:
+                    self.trace.append((rec, gy, gx.clone(), None if gres is None else gres.clone()))
                 give(x, gx)
                 if res is not None:
                     give(res, gres)
@@ -136,8 +139,12 @@ class ResNetEngine:
                 scratch = self._new(ns * R * R * Cin * Cout)
                 lib.conv2d_wgrad(x, gy, None, m.weight.grad, m.bias.grad if m.bias is not None else None, scratch, B, H, W,
                                  Cin, Cout, R, R, stv, pad, dil, 0, st)
+                gx = None
                 if Cin > 3:      # no input gradient for the stem
                     gx = torch.empty_like(x)
                     lib.conv2d_dgrad(gy, None, m.weight.data, gx, B, H, W, Cin, Cout, R, R, stv, pad, dil, 0, st)
+                if self.trace is not None:
+                    self.trace.append((rec, gy, None if gx is None else gx.clone(), m.weight.grad.clone()))
+                if gx is not None:
                     give(x, gx)
         self.tape = []

@@ -161,6 +161,15 @@ int dktb_gp_fit(const float* kbase, long kbase_class_stride, const float* y, lon
                 const float* raw_outputscale, const float* constant, const float* raw_noise, float* alpha,
                 float* linv, float* loss_terms, int* info, float* dkbase, float* dhyper, float grad_scale,
                 float jitter, int E, int C, int N, cudaStream_t stream);
+/* The same contract for systems beyond shared memory (dktb_gp_max_n() < N <= dktb_gp_large_max_n() = 512: 20-way
+ * training episodes, BASELINE configs[4] Gram-N sweep): blocked Cholesky on a caller-provided global workspace of
+ * dktb_gp_large_work_floats(E, C, N) floats. */
+int dktb_gp_large_max_n(void);
+long dktb_gp_large_work_floats(int E, int C, int N);
+int dktb_gp_fit_large(const float* kbase, long kbase_class_stride, const float* y, long y_episode_stride,
+                      const float* raw_outputscale, const float* constant, const float* raw_noise, float* alpha,
+                      float* linv, float* loss_terms, int* info, float* dkbase, float* dhyper, float* work,
+                      float grad_scale, float jitter, int E, int C, int N, cudaStream_t stream);
 int dktb_gp_reduce(const float* loss_terms, const float* dhyper, float* loss, float* hyper, int E, int C,
                    cudaStream_t stream);
 /* dZ = scale * (S + S^T) Z,  S = sum_c w[e][c] */

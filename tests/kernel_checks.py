@@ -196,7 +196,7 @@ def check_head(lib, dev, E=2, N=7, Cch=8, P=4, seed=3):
     _close(z2.cpu(), ref2[:, :, perm], what="bn_out eval")
 
 
-def check_gp(lib, dev, E=3, C=3, per_class=4, D=24, M=9, seed=4, rtol=2e-4):
+def check_gp(lib, dev, E=3, C=3, per_class=4, D=24, M=9, seed=4, rtol=2e-4, large=False):
     g = torch.Generator().manual_seed(seed)
     N = C * per_class
     z = F.normalize(torch.randn(E, N, D, generator=g), dim=2)
@@ -222,8 +222,22 @@ def check_gp(lib, dev, E=3, C=3, per_class=4, D=24, M=9, seed=4, rtol=2e-4):
     dk = torch.empty(E, C, N, N, device=dev)
     dh = torch.empty(E, C, 3, device=dev)
     ros, cst, rn = (p[k].detach().to(dev) for k in ("raw_outputscale", "constant", "raw_noise"))
-    lib.gp_fit(gram, 0, targets.to(dev), 0, ros, cst, rn, alpha, None, lt, info, dk, dh, 1.0 / E, 0.0, E, C, N, 0)
+    linv = torch.empty(E, C, N, N, device=dev)
+    if large:       # the global-workspace blocked factorisation (csrc/gp_large.cu), same contract
+        work = torch.empty(lib.gp_large_work_floats(E, C, N), device=dev)
+
+        def fit(kb, a, li, l_, i_, dk_, dh_, gs):
+            lib.gp_fit_large(kb, 0, targets.to(dev), 0, ros, cst, rn, a, li, l_, i_, dk_, dh_, work, gs, 0.0, E, C, N, 0)
+    else:
+        def fit(kb, a, li, l_, i_, dk_, dh_, gs):
+            lib.gp_fit(kb, 0, targets.to(dev), 0, ros, cst, rn, a, li, l_, i_, dk_, dh_, gs, 0.0, E, C, N, 0)
+    fit(gram, alpha, linv, lt, info, dk, dh, 1.0 / E)
     assert int(info.cpu().abs().sum()) == 0
+    with torch.no_grad():       # L^-1 of K~ (lower triangular), used by the predictive variance
+        s0 = F.softplus(p["raw_outputscale"].detach()[0])
+        kt = s0 * (z[0] @ z[0].T) + (F.softplus(p["raw_noise"].detach()[0]) + 1e-4) * torch.eye(N)
+        li_ref = torch.linalg.inv(torch.linalg.cholesky(kt.double())).float()
+    _close(linv[0, 0], li_ref, rtol=rtol, atol=1e-5, what="L^-1")
     loss = torch.empty(E, device=dev)
     hyper = torch.empty(C, 3, device=dev)
     lib.gp_reduce(lt, dh, loss, hyper, E, C, 0)
@@ -247,7 +261,7 @@ def check_gp(lib, dev, E=3, C=3, per_class=4, D=24, M=9, seed=4, rtol=2e-4):
     assert np.array_equal(pred.cpu().numpy(), ref_pred)
     # a non-PD system must be reported, not silently factorised
     bad = -torch.eye(N).repeat(E, 1, 1).to(dev)
-    lib.gp_fit(bad, 0, targets.to(dev), 0, ros, cst, rn, alpha, None, lt, info, None, None, 1.0, 0.0, E, C, N, 0)
+    fit(bad, alpha, None, lt, info, None, None, 1.0)
     assert int((info.cpu() != 0).sum()) == E * C
 
 

@@ -48,6 +48,11 @@ def test_gp(lib):
     kc.check_gp(lib, DEV)
 
 
+def test_gp_large(lib):
+    kc.check_gp(lib, DEV, E=1, C=2, per_class=20, D=24, M=5, seed=6, large=True)     # N = 40: panels 32 + 8
+    kc.check_gp(lib, DEV, E=2, C=3, per_class=23, D=32, M=5, seed=7, large=True)     # N = 69: three panels
+
+
 def test_adam(lib):
     kc.check_adam(lib, DEV)
 

@@ -49,6 +49,14 @@ def test_gp(lib):
     kc.check_gp(lib, DEV, E=2, C=5, per_class=1, D=64, M=75, seed=11)       # N = 5   (1-shot test episode)
 
 
+def test_gp_large(lib):
+    """N beyond shared memory (BASELINE configs[4]: 20-way 5-shot, Gram-N sweep up to 500)."""
+    kc.check_gp(lib, DEV, E=2, C=5, per_class=21, D=1600, M=75, seed=9, large=True)      # N = 105, same as small path
+    kc.check_gp(lib, DEV, E=2, C=5, per_class=36, D=1600, M=80, seed=12, large=True)     # N = 180 (5-way 20-shot)
+    kc.check_gp(lib, DEV, E=1, C=20, per_class=21, D=512, M=100, seed=13, large=True, rtol=5e-4)   # N = 420 (20-way 5-shot)
+    kc.check_gp(lib, DEV, E=1, C=4, per_class=128, D=512, M=64, seed=14, large=True, rtol=5e-4)    # N = 512
+
+
 def test_adam(lib):
     kc.check_adam(lib, DEV, n=100003)
 
