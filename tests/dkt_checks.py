@@ -263,7 +263,7 @@ def check_regression(dev, lib=None, image=36, n=7, n_support=4, tol=2e-4, kernel
 
 
 def check_train_step_arch(arch, model_factory, dev, image_size, n_way=2, n_support=1, n_query=2, E=2, kernel="rbf",
-                          lib=None, tol=1e-4, env_factor=4.0):
+                          lib=None, tol=1e-4, env_factor=4.0, grad_check=True):
     """One packed meta-train step of an arbitrary backbone (ResNet*) against the oracle: loss, every backbone / GP
     gradient (fp64 arbiter + fp32 envelope), monitoring arg-max after re-synchronising the post-step weights."""
     from deep_kernel_transfer_b200.methods.DKT import DKT
@@ -301,7 +301,7 @@ def check_train_step_arch(arch, model_factory, dev, image_size, n_way=2, n_suppo
             continue      # a bias that BatchNorm cancels: rounding noise on both sides
         e = rel_err(p_.grad, r64["grads"][name])
         floor = rel_err(ref["grads"][name], r64["grads"][name])
-        if e > max(tol, env_factor * floor):
+        if grad_check and e > max(tol, env_factor * floor):
             bad[name] = (e, floor)
     gos = torch.stack([m.covar_module.raw_outputscale.grad for m in model.model.models])
     e = rel_err(gos, r64["grads"]["raw_outputscale"])
@@ -365,3 +365,107 @@ def check_sines(dev, lib=None, steps=3, tol=2e-4):
     mean_ref, var_ref = o.predict(x_all[:5], y_all[:5], x_all[5:])
     mean, var = model.predict(x_all[:5].to(dev), y_all[:5].to(dev), x_all[5:].to(dev))
     assert rel_err(mean, mean_ref) <= tol and rel_err(var, var_ref) <= tol
+
+
+def check_resnet_same_branch(arch, dev, image_size, lib=None, B=4, ipe=4, tol=1e-4, fwd_tol=3e-5):
+    """ResNet forward/backward at a given resolution against exact (fp64) arithmetic on the SAME piecewise-linear branch.
+
+    A deep ReLU / max-pool network evaluated in fp32 picks a different gate than exact arithmetic wherever a
+    pre-activation lies within rounding of zero (~10 of the 1e7 activations of ResNet18 at 224x224); each such flip moves
+    every upstream gradient by ~1e-3 (measured: cuDNN's own fp32 path differs from fp64 by 1e-1 there), so raw
+    gradients are only comparable on a fixed branch.  The check therefore (1) requires the device features to match a
+    free-running fp64 replay of the op tape to `fwd_tol`, and that replay to match the oracle backbone (pinned to the
+    reference's backbone.py) to 1e-10; (2) replays the tape in fp64 with the device's ReLU masks / arg-max taps,
+    asserting every disagreeing gate sits on a near-zero pre-activation, and requires every parameter gradient to match
+    that replay to `tol`."""
+    import torch.nn.functional as F
+    from deep_kernel_transfer_b200 import backbone, _lib
+    from deep_kernel_transfer_b200.resnet_engine import ResNetEngine
+    from oracle import backbone as obb
+    lib = lib or _lib.load()
+    dev = torch.device(dev)
+    torch.manual_seed(0)
+    net = getattr(backbone, arch)().to(dev)
+    g = torch.Generator().manual_seed(3)
+    for _, p in net.named_parameters():
+        if p.dim() == 1:
+            p.data.add_(0.1 * torch.randn(p.shape, generator=g).to(dev))
+        p.grad = torch.zeros_like(p)
+    eng = ResNetEngine(lib, net, dev)
+    x = torch.randn(B, 3, image_size, image_size, generator=g).to(dev)
+    feats = eng.forward(x, ipe, True)
+    tape = list(eng.tape)
+    gf = torch.randn(feats.shape, generator=g).to(dev)
+    eng.backward(gf)
+    stats = {"relu_flips": 0, "pool_flips": 0, "gates": 0}
+
+    def nchw(t):
+        return t.detach().double().permute(0, 3, 1, 2)
+
+    def replay(device_gates):
+        vals, params = {}, {}
+
+        def P(t):
+            if id(t) not in params:
+                params[id(t)] = t.detach().double().clone().requires_grad_(True)
+            return params[id(t)]
+
+        vals[tape[0][1].data_ptr()] = nchw(tape[0][1])
+        for rec in tape:
+            if rec[0] == "conv":
+                _, xi, out, m, (_, _, _, _, _, st, pad, dil) = rec
+                vals[out.data_ptr()] = F.conv2d(vals[xi.data_ptr()], P(m.weight), None, st, pad, dil)
+            elif rec[0] == "bn":
+                _, xi, y, m, _, _, res, relu, _ = rec
+                o = F.batch_norm(vals[xi.data_ptr()], None, None, P(m.weight), P(m.bias), True, 0.0, 1e-5)
+                if res is not None:
+                    o = o + vals[res.data_ptr()]
+                if relu and device_gates:
+                    mask = nchw(y) > 0
+                    diff = mask != (o > 0)
+                    stats["gates"] += mask.numel()
+                    if bool(diff.any()):
+                        stats["relu_flips"] += int(diff.sum())
+                        assert float(o[diff].abs().max()) <= 1e-4 * float(o.abs().max()), "ReLU gate differs off zero"
+                    o = o * mask
+                elif relu:
+                    o = o.relu()
+                vals[y.data_ptr()] = o
+            elif rec[0] == "maxpool":
+                _, xi, y, idx = rec
+                v = vals[xi.data_ptr()]
+                if device_gates:
+                    vp = F.pad(v, (1, 1, 1, 1), value=float("-inf"))
+                    pt = vp.unfold(2, 3, 2).unfold(3, 3, 2)                      # [B,C,Ho,Wo,3,3]
+                    pt = pt.reshape(*pt.shape[:4], 9)
+                    tap = idx.permute(0, 3, 1, 2).long().unsqueeze(-1)
+                    o = pt.gather(-1, tap).squeeze(-1)
+                    best = pt.max(-1).values
+                    bad = o != best
+                    if bool(bad.any()):
+                        stats["pool_flips"] += int(bad.sum())
+                        assert float((best - o)[bad].max()) <= 1e-4 * float(best.abs().max()), "max-pool tap differs off a tie"
+                else:
+                    o = F.max_pool2d(v, 3, 2, 1)
+                vals[y.data_ptr()] = o
+            elif rec[0] == "avgpool":
+                v = vals[rec[1].data_ptr()]
+                vals[rec[2].data_ptr()] = F.avg_pool2d(v, v.shape[-1]).flatten(1)
+        return vals[tape[-1][2].data_ptr()], params
+
+    f_free, _ = replay(False)
+    sd = {k: v.detach().double().cpu() for k, v in net.state_dict().items()}
+    f_or = obb.forward(arch, sd, x.double().cpu(), training=True, update_running=False)
+    assert rel_err(f_free, f_or) <= 1e-10, ("tape replay vs oracle backbone", rel_err(f_free, f_or))
+    assert rel_err(feats, f_free) <= fwd_tol, ("features", rel_err(feats, f_free))
+    f_dev, params = replay(True)
+    f_dev.backward(gf.double())
+    bad = {}
+    for name, p in net.named_parameters():
+        if id(p) in params:
+            e = rel_err(p.grad, params[id(p)].grad)
+            if e > tol:
+                bad[name] = e
+    assert not bad, bad
+    assert stats["relu_flips"] + stats["pool_flips"] <= max(50, stats["gates"] // 100000), stats
+    return stats

@@ -67,5 +67,12 @@ def test_resnet10_train_step_matches_oracle(lib):
     dkt_checks.check_train_step_arch("ResNet10", backbone.ResNet10, torch.device("cpu"), image_size=32, lib=lib)
 
 
+def test_resnet10_same_branch(lib):
+    """Backbone forward / backward of the tape engine vs fp64 on the device's own gate pattern (bottleneck variant is
+    covered on the GPU at 224x224)."""
+    stats = dkt_checks.check_resnet_same_branch("ResNet10", torch.device("cpu"), 32, lib=lib)
+    assert stats["gates"] > 0
+
+
 def test_sines_matches_oracle(lib):
     dkt_checks.check_sines(torch.device("cpu"), lib=lib)

@@ -84,10 +84,15 @@ def test_resnet10_small():
 
 @pytest.mark.parametrize("arch", ["ResNet18", "ResNet50"])
 def test_resnet_reference_resolution(arch):
-    """224x224 inputs (the reference's ResNet resolution), RBF kernel (BASELINE config #4 / #5 backbones)."""
+    """224x224 inputs (the reference's ResNet resolution), RBF kernel (BASELINE configs[3] / [4] backbones).  Loss and
+    monitoring arg-max against the oracle end to end; gradients on the device's own ReLU / max-pool branch (at this size
+    a handful of gates sit within fp32 rounding of zero and each flip moves every upstream gradient by ~1e-3 -- see
+    dkt_checks.check_resnet_same_branch)."""
     from deep_kernel_transfer_b200 import backbone
     dkt_checks.check_train_step_arch(arch, getattr(backbone, arch), DEV, image_size=224, n_way=2, n_support=1, n_query=1,
-                                     E=1, env_factor=6.0)
+                                     E=1, grad_check=False)
+    stats = dkt_checks.check_resnet_same_branch(arch, DEV, 224)
+    print(arch, stats)
 
 
 def test_regression_spectral():
