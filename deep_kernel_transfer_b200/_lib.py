@@ -20,6 +20,7 @@ SIGNATURES = {
     "dktb_conv1_fwd": ("pppppiiis", ctypes.c_int),
     "dktb_conv1_wgrad_nsplit": ("", ctypes.c_int),
     "dktb_conv1_wgrad": ("pppppiiis", ctypes.c_int),
+    "dktb_conv1_bwd_fused": ("pppppppppppiiiiis", ctypes.c_int),
     "dktb_prep_weights": ("ppps", ctypes.c_int),
     "dktb_conv3x3_tiles": ("ii", ctypes.c_int),
     "dktb_conv3x3_fwd": ("pppppiiis", ctypes.c_int),

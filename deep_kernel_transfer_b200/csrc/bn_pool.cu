@@ -163,20 +163,6 @@ struct Win4 {
   float4 v[4];     // raw y of the (up to) 4 window positions
 };
 
-__device__ __forceinline__ void bn_bwd_route(const float yv[4], int npos, float m, float is, float sc, float bt,
-                                             float gout, int& arg, float& gz, float& xhat_arg) {
-  float bestz = 0.f;
-  arg = 0;
-  float zs0 = fmaxf(fmaf(yv[0] - m, sc, bt), 0.f);
-  bestz = zs0;
-  for (int k = 1; k < npos; ++k) {
-    const float z = fmaxf(fmaf(yv[k] - m, sc, bt), 0.f);
-    if (z > bestz) { bestz = z; arg = k; }
-  }
-  gz = bestz > 0.f ? gout : 0.f;
-  xhat_arg = (yv[arg] - m) * is;
-}
-
 // pass 1: partial[(b*chunks + chunk)][2][64] = { sum g_z , sum g_z * xhat } over the chunk's pixels
 #define BWD_PIX_PER_CHUNK 256
 __global__ void __launch_bounds__(256) bn_relu_pool_bwd_reduce_kernel(
@@ -320,7 +306,7 @@ DKTB_EXPORT int dktb_bn_relu_pool_bwd(const float* y, const float* gout, const f
                                       const float* gamma, const float* beta, float* gy, float* dgamma, float* dbeta,
                                       float* partial, float* sums, double* scratch_d, int B, int H, int W, int ipe,
                                       int in_pad, int out_pad, int pool, cudaStream_t stream) {
-  DKTB_CHECK_ARG(y && gout && mean && invstd && gamma && beta && gy && dgamma && dbeta && partial && sums);
+  DKTB_CHECK_ARG(y && gout && mean && invstd && gamma && beta && dgamma && dbeta && partial && sums);
   DKTB_CHECK_ARG(B > 0 && ipe > 0 && B % ipe == 0 && B <= 65535);
   const int chunks = dktb_bn_bwd_chunks(H, W, pool);
   const int E = B / ipe;
@@ -331,6 +317,7 @@ DKTB_EXPORT int dktb_bn_relu_pool_bwd(const float* y, const float* gout, const f
   DKTB_LAUNCH(episode_sum_kernel, dim3(E, ES_CHUNKS), dim3(256), 0, stream, (const float*)partial, chunks, ipe, chunk);
   DKTB_LAUNCH(episode_sum_final_kernel, dim3(E), dim3(128), 0, stream, (const double*)chunk, sums, (double*)nullptr);
   DKTB_LAUNCH(bn_param_grad_kernel, dim3(1), dim3(64), 0, stream, (const float*)sums, E, dgamma, dbeta);
+  if (gy == nullptr) return dktb_launch_status();      // sums / parameter gradients only (dktb_conv1_bwd_fused follows)
   const int Hc = pool ? (H + 1) / 2 : H, Wc = pool ? (W + 1) / 2 : W;
   const long total = (long)B * Hc * Wc * 16;
   const float inv_count = 1.0f / ((float)ipe * (float)H * (float)W);

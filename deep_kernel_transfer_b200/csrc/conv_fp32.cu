@@ -216,6 +216,126 @@ __global__ void conv1_wgrad_reduce_kernel(const float* __restrict__ partial, int
   else if (db != nullptr) db[co] = t;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Fused first-layer backward: gy = BatchNorm/ReLU/MaxPool backward of the pooled gradient (second pass: the episode sums
+// s1, s2 are already known) evaluated tile by tile in shared memory and consumed on the spot by the weight-gradient
+// accumulation -- the 1.8 MB/image gradient of the pre-BN map is never written to (or re-read from) HBM.
+// One CTA loops over 4 x 32 pixel tiles (2 x 16 pool windows); thread (co, row) accumulates all 27 taps of its tile row.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 3) conv1_bwd_fused_kernel(
+    const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gout,
+    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+    const float* __restrict__ beta, const float* __restrict__ sums, float* __restrict__ partial, int B, int H, int W,
+    int ipe, int out_pad, float inv_count) {
+  __shared__ __align__(16) float s_in[3][C1_TH + 2][C1_TW + 4];
+  __shared__ float s_g[C1_TH * C1_TW][64 + 1];
+  float (*s_fin)[28][64] = reinterpret_cast<float (*)[28][64]>(&s_g[0][0]);   // reused after the tile loop
+  const int tid = threadIdx.x;
+  const int co = tid % 64, row = tid / 64;
+  const int TX = (W + C1_TW - 1) / C1_TW, TY = (H + C1_TH - 1) / C1_TH;
+  const long ntiles = (long)B * TX * TY;
+  const int Ho = H / 2, Wo = W / 2, Hq = Ho + 2 * out_pad, Wq = Wo + 2 * out_pad;
+  float acc[3][3][3];
+  float accb = 0.f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s) acc[a][r][s] = 0.f;
+  for (long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int b = (int)(t / (TX * TY));
+    const int rem = (int)(t % (TX * TY));
+    const int h0 = (rem / TX) * C1_TH, w0 = (rem % TX) * C1_TW;
+    const int e = b / ipe;
+    __syncthreads();
+    for (int i = tid; i < 3 * (C1_TH + 2) * (C1_TW + 2); i += 256) {
+      const int ci = i / ((C1_TH + 2) * (C1_TW + 2));
+      const int rm = i % ((C1_TH + 2) * (C1_TW + 2));
+      const int r = rm / (C1_TW + 2), c = rm % (C1_TW + 2);
+      const int hh = h0 + r - 1, ww = w0 + c - 1;
+      float v = 0.f;
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = x[(((long)b * 3 + ci) * H + hh) * W + ww];
+      s_in[ci][r][c] = v;
+    }
+    // gradient tile: work item = (pool window of the tile, 4 channels); 32 windows x 16 channel groups
+    for (int i = tid; i < (C1_TH / 2) * (C1_TW / 2) * 16; i += 256) {
+      const int c4 = (i % 16) * 4, wi = i / 16;
+      const int wy = wi / (C1_TW / 2), wx = wi % (C1_TW / 2);
+      const int oh = h0 / 2 + wy, ow = w0 / 2 + wx;
+      const float4 m = dktb_ld4(mean + e * 64 + c4), is = dktb_ld4(invstd + e * 64 + c4);
+      const float4 g = dktb_ld4(gamma + c4), bt = dktb_ld4(beta + c4);
+      const float4 q1 = dktb_ld4(sums + (long)e * 128 + c4), q2 = dktb_ld4(sums + (long)e * 128 + 64 + c4);
+      const float mm[4] = {m.x, m.y, m.z, m.w}, ii[4] = {is.x, is.y, is.z, is.w};
+      const float ss[4] = {g.x * is.x, g.y * is.y, g.z * is.z, g.w * is.w}, bb[4] = {bt.x, bt.y, bt.z, bt.w};
+      const float a1[4] = {q1.x * inv_count, q1.y * inv_count, q1.z * inv_count, q1.w * inv_count};
+      const float a2[4] = {q2.x * inv_count, q2.y * inv_count, q2.z * inv_count, q2.w * inv_count};
+      const bool full = (oh < Ho) && (ow < Wo);
+      float gg[4] = {0.f, 0.f, 0.f, 0.f};
+      if (full) {
+        const float4 go = dktb_ld4(gout + (((long)b * Hq + oh + out_pad) * Wq + ow + out_pad) * 64 + c4);
+        gg[0] = go.x; gg[1] = go.y; gg[2] = go.z; gg[3] = go.w;
+      }
+      float yv[4][4];
+      bool inb[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int hh = h0 + 2 * wy + (k >> 1), ww = w0 + 2 * wx + (k & 1);
+        inb[k] = (hh < H) && (ww < W);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (inb[k]) v = dktb_ld4(y + (((long)b * H + hh) * W + ww) * 64 + c4);
+        yv[0][k] = v.x; yv[1][k] = v.y; yv[2][k] = v.z; yv[3][k] = v.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int arg = -1; float gz = 0.f, xh = 0.f;
+        if (full) bn_bwd_route(yv[j], 4, mm[j], ii[j], ss[j], bb[j], gg[j], arg, gz, xh);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float xhat = (yv[j][k] - mm[j]) * ii[j];
+          const float gzk = (k == arg) ? gz : 0.f;
+          const int p = (2 * wy + (k >> 1)) * C1_TW + 2 * wx + (k & 1);
+          s_g[p][c4 + j] = inb[k] ? ss[j] * (gzk - a1[j] - xhat * a2[j]) : 0.f;
+        }
+      }
+    }
+    __syncthreads();
+    for (int c0 = 0; c0 < C1_TW; c0 += 4) {
+      float g[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) g[p] = s_g[row * C1_TW + c0 + p][co];
+      accb += (g[0] + g[1]) + (g[2] + g[3]);
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const float4 v0 = dktb_ld4(&s_in[ci][row + r][c0]);
+          const float2 v1 = *reinterpret_cast<const float2*>(&s_in[ci][row + r][c0 + 4]);
+          const float v[6] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y};
+#pragma unroll
+          for (int s = 0; s < 3; ++s)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[ci][r][s] = fmaf(v[p + s], g[p], acc[ci][r][s]);
+        }
+    }
+  }
+  // the four tile rows of the CTA -> one partial (fixed order)
+  __syncthreads();
+#pragma unroll
+  for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s) s_fin[row][ci * 9 + r * 3 + s][co] = acc[ci][r][s];
+  s_fin[row][27][co] = accb;
+  __syncthreads();
+  float* out = partial + (long)blockIdx.x * (28 * 64);
+  for (int i = tid; i < 28 * 64; i += 256) {
+    const int k = i / 64, c = i % 64;
+    out[i] = (s_fin[0][k][c] + s_fin[1][k][c]) + (s_fin[2][k][c] + s_fin[3][k][c]);
+  }
+}
+
 DKTB_EXPORT int dktb_conv1_wgrad_nsplit(void) { return 592; }
 
 DKTB_EXPORT int dktb_conv1_wgrad(const float* x, const float* gy, float* dw, float* db, float* scratch, int B, int H,
@@ -479,5 +599,24 @@ DKTB_EXPORT int dktb_conv3x3_wgrad(const float* a, const float* gy, float* dw, f
   DKTB_LAUNCH(conv3x3_wgrad_kernel, dim3(nsplit, 3), dim3(256), 0, stream, a, gy, scratch, total_rows, Wp);
   DKTB_LAUNCH(conv3x3_wgrad_reduce_kernel, dim3((WG_PSTRIDE + 255) / 256), dim3(256), 0, stream, scratch, nsplit, dw,
               db);
+  return dktb_launch_status();
+}
+
+// Fused second half of the first block's backward (after dktb_bn_relu_pool_bwd(..., gy = NULL, ...) produced `sums`
+// [B/ipe][2][64] and the BatchNorm parameter gradients): BN/ReLU/MaxPool2d(2) backward of `gout` [B,H/2+2p,W/2+2p,64]
+// (p = out_pad) fused into the conv1 weight / bias gradient.  y [B,H,W,64] is the pre-BN conv1 output.
+// scratch: dktb_conv1_wgrad_nsplit()*28*64 floats.
+DKTB_EXPORT int dktb_conv1_bwd_fused(const float* x, const float* y, const float* gout, const float* mean,
+                                     const float* invstd, const float* gamma, const float* beta, const float* sums,
+                                     float* dw, float* db, float* scratch, int B, int H, int W, int ipe, int out_pad,
+                                     cudaStream_t stream) {
+  DKTB_CHECK_ARG(x && y && gout && mean && invstd && gamma && beta && sums && dw && scratch);
+  DKTB_CHECK_ARG(B > 0 && H > 0 && W > 0 && ipe > 0 && B % ipe == 0);
+  const long ntiles = (long)B * ((W + C1_TW - 1) / C1_TW) * ((H + C1_TH - 1) / C1_TH);
+  const int nsplit = (int)(ntiles < 444 ? ntiles : 444);      // 3 resident CTAs per SM x 148 SMs, one wave
+  const float inv_count = 1.0f / ((float)ipe * (float)H * (float)W);
+  DKTB_LAUNCH(conv1_bwd_fused_kernel, dim3(nsplit), dim3(256), 0, stream, x, y, gout, mean, invstd, gamma, beta, sums,
+              scratch, B, H, W, ipe, out_pad, inv_count);
+  DKTB_LAUNCH(conv1_wgrad_reduce_kernel, dim3(7), dim3(256), 0, stream, (const float*)scratch, nsplit, dw, db);
   return dktb_launch_status();
 }

@@ -53,6 +53,23 @@ __device__ __forceinline__ double dktb_warp_sum_d(double v) {
 __device__ __forceinline__ float dktb_softplus(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 __device__ __forceinline__ float dktb_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
 
+// BatchNorm + ReLU + MaxPool backward gate of one pool window and one channel: which of the (up to) 4 raw conv outputs
+// receives the pooled gradient (first maximum of the post-ReLU values in scan order, as torch's max_pool2d), the gated
+// gradient and the normalised value at that position.  Shared by bn_pool.cu and the fused first-layer backward.
+__device__ __forceinline__ void bn_bwd_route(const float yv[4], int npos, float m, float is, float sc, float bt,
+                                             float gout, int& arg, float& gz, float& xhat_arg) {
+  float bestz = 0.f;
+  arg = 0;
+  float zs0 = fmaxf(fmaf(yv[0] - m, sc, bt), 0.f);
+  bestz = zs0;
+  for (int k = 1; k < npos; ++k) {
+    const float z = fmaxf(fmaf(yv[k] - m, sc, bt), 0.f);
+    if (z > bestz) { bestz = z; arg = k; }
+  }
+  gz = bestz > 0.f ? gout : 0.f;
+  xhat_arg = (yv[arg] - m) * is;
+}
+
 // Padded activation layout helpers: [img][H+2][W+2][64], zero border.
 __host__ __device__ __forceinline__ long dktb_prow(int img, int hp, int wp, int Hp, int Wp) {
   return ((long)img * Hp + hp) * Wp + wp;

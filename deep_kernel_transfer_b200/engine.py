@@ -56,6 +56,8 @@ class ConvNetEngine:
         # first layer on tcgen05 (K = 27 im2col staged in TMEM); eval passes fuse BatchNorm + ReLU + pool into its epilogue
         self.conv1_tc = self.use_tc and os.environ.get("DKTB_CONV1", "tc") == "tc" and lib.has("dktb_conv1_tc") \
             and image_size + 2 <= 88
+        # first-block backward: BN/ReLU/pool backward fused into the conv1 weight gradient (no gy[0] tensor at all)
+        self.l0_fused = os.environ.get("DKTB_L0BWD", "fused") == "fused" and lib.has("dktb_conv1_bwd_fused")
         self.layers = []
         h = image_size
         for i in range(depth):
@@ -82,7 +84,7 @@ class ConvNetEngine:
             last = i == self.depth - 1
             if i == 0:
                 ws["y"].append(torch.empty(B, H, W, 64, device=dev, dtype=f32))
-                ws["gy"].append(torch.empty(B, H, W, 64, device=dev, dtype=f32))
+                ws["gy"].append(None if (self.l0_fused and L["pool"]) else torch.empty(B, H, W, 64, device=dev, dtype=f32))
                 T = lib.conv1_tiles(H, W)
             else:
                 ws["y"].append(torch.zeros(B, H + 2, W + 2, 64, device=dev, dtype=f32))
@@ -189,7 +191,11 @@ class ConvNetEngine:
             lib.bn_relu_pool_bwd(ws["y"][i], gout, ws["mean"][i], ws["invstd"][i], P.bn_w[i], P.bn_b[i], ws["gy"][i],
                                  G.bn_w[i], G.bn_b[i], ws["bwd_partial"], ws["bwd_sums"], ws["scratch_d"], B, H, W, ipe,
                                  0 if i == 0 else 1, 0 if last else 1, pool, st)
-            if i == 0:
+            if i == 0 and ws["gy"][0] is None:
+                lib.conv1_bwd_fused(x, ws["y"][0], gout, ws["mean"][0], ws["invstd"][0], P.bn_w[0], P.bn_b[0],
+                                    ws["bwd_sums"], G.conv_w[0], G.conv_b[0], ws["wgrad_scratch"], B, H, W, ipe,
+                                    0 if last else 1, st)
+            elif i == 0:
                 lib.conv1_wgrad(x, ws["gy"][0], G.conv_w[0], G.conv_b[0], ws["wgrad_scratch"], B, H, W, st)
             else:
                 if self.use_tc and self.wgrad_tc:

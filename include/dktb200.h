@@ -38,6 +38,14 @@ int dktb_conv1_fwd(const float* x, const float* w, const float* bias, float* y, 
 int dktb_conv1_wgrad_nsplit(void);
 int dktb_conv1_wgrad(const float* x, const float* gy, float* dw, float* db, float* scratch, int B, int H, int W,
                      cudaStream_t stream);
+/* Fused first-block backward: BatchNorm + ReLU + MaxPool2d(2) backward of the pooled gradient `gout`
+ * [B,H/2+2*out_pad,W/2+2*out_pad,64] evaluated tile-wise and consumed directly by the conv1 weight / bias gradient
+ * (the gradient of the pre-BN map never touches HBM).  Call dktb_bn_relu_pool_bwd(..., gy = NULL, ...) first: it
+ * produces `sums` [B/ipe][2][64] and dgamma / dbeta.  Replaces loss.backward() through trunk[0] (backbone.py:93-102).
+ * scratch: dktb_conv1_wgrad_nsplit()*28*64 floats. */
+int dktb_conv1_bwd_fused(const float* x, const float* y, const float* gout, const float* mean, const float* invstd,
+                         const float* gamma, const float* beta, const float* sums, float* dw, float* db, float* scratch,
+                         int B, int H, int W, int ipe, int out_pad, cudaStream_t stream);
 /* weight re-layout for the 64->64 kernels: w [64,64,3,3] -> wt_fwd [9][ci][co], wt_dgrad [9][co][ci] (flipped). */
 int dktb_prep_weights(const float* w, float* wt_fwd, float* wt_dgrad, cudaStream_t stream);
 /* 64->64 3x3 conv over padded NHWC: out[q] = sum_tap A[q+off(tap)] * wt[tap]; forward (wt_fwd, bias, partials)

@@ -643,3 +643,50 @@ def check_resnet_ops(lib, dev, E=2, ipe=2, H=9, W=7, C=8, seed=80):
     ad = a.clone().to(dev)
     lib.add_inplace(ad, b2.to(dev), 1000, 0)
     _close(ad, a + b2, what="add")
+
+
+def check_conv1_bwd_fused(lib, dev, E=2, ipe=2, H=10, W=37, out_pad=1, seed=21):
+    """First block backward, fused (BN/ReLU/MaxPool backward inside the conv1 weight gradient), against torch autograd of
+    conv1 -> per-episode BatchNorm -> ReLU -> MaxPool2d(2) and against the split device path."""
+    g = torch.Generator().manual_seed(seed)
+    B = E * ipe
+    x = torch.randn(B, 3, H, W, generator=g)
+    w = (torch.randn(64, 3, 3, 3, generator=g) * 0.2).requires_grad_(True)
+    b = torch.randn(64, generator=g).requires_grad_(True)
+    gamma = (1 + 0.2 * torch.randn(64, generator=g)).requires_grad_(True)
+    beta = (0.1 * torch.randn(64, generator=g)).requires_grad_(True)
+    Ho, Wo = H // 2, W // 2
+    gout = torch.randn(B, 64, Ho, Wo, generator=g)
+    y = F.conv2d(x, w, b, padding=1)
+    outs = []
+    for e in range(E):
+        ye = y[e * ipe:(e + 1) * ipe]
+        outs.append(F.max_pool2d(F.relu(F.batch_norm(ye, None, None, gamma, beta, True, 0.0, 1e-5)), 2))
+    (torch.cat(outs) * gout).sum().backward()
+    yd = y.detach().permute(0, 2, 3, 1).contiguous().to(dev)
+    yv = y.detach().view(E, ipe, 64, H, W)
+    mean = yv.mean((1, 3, 4)).to(dev).contiguous()
+    invstd = (1.0 / torch.sqrt(yv.var((1, 3, 4), unbiased=False) + 1e-5)).to(dev).contiguous()
+    gpad = torch.zeros(B, Ho + 2 * out_pad, Wo + 2 * out_pad, 64)
+    gpad[:, out_pad:out_pad + Ho, out_pad:out_pad + Wo] = gout.permute(0, 2, 3, 1)
+    gpad = gpad.to(dev)
+    chunks = lib.bn_bwd_chunks(H, W, 1)
+    partial = torch.empty(B * chunks * 128, device=dev)
+    sums = torch.empty(E * 128, device=dev)
+    scratch_d = torch.empty(lib.bn_scratch_doubles(E), device=dev, dtype=torch.float64)
+    dg, dbt = torch.empty(64, device=dev), torch.empty(64, device=dev)
+    gd, bd = gamma.detach().to(dev), beta.detach().to(dev)
+    lib.bn_relu_pool_bwd(yd, gpad, mean, invstd, gd, bd, None, dg, dbt, partial, sums, scratch_d, B, H, W, ipe, 0, out_pad, 1, 0)
+    _close(dg, gamma.grad, rtol=2e-4, atol=1e-4, what="fused L0: d gamma")
+    _close(dbt, beta.grad, rtol=2e-4, atol=1e-4, what="fused L0: d beta")
+    dw, db = torch.empty(64, 3, 3, 3, device=dev), torch.empty(64, device=dev)
+    scratch = torch.empty(lib.conv1_wgrad_nsplit() * 28 * 64, device=dev)
+    lib.conv1_bwd_fused(x.to(dev), yd, gpad, mean, invstd, gd, bd, sums, dw, db, scratch, B, H, W, ipe, out_pad, 0)
+    _close(dw, w.grad, rtol=2e-4, atol=2e-4, what="fused L0: d conv1 weight")
+    assert float(db.abs().max()) <= 1e-3 * float(w.grad.abs().max()) + 1e-5      # cancelled by BatchNorm
+    # split path: same numbers up to summation order
+    gy = torch.empty(B, H, W, 64, device=dev)
+    lib.bn_relu_pool_bwd(yd, gpad, mean, invstd, gd, bd, gy, dg, dbt, partial, sums, scratch_d, B, H, W, ipe, 0, out_pad, 1, 0)
+    dw2, db2 = torch.empty_like(dw), torch.empty_like(db)
+    lib.conv1_wgrad(x.to(dev), gy, dw2, db2, scratch, B, H, W, 0)
+    _close(dw, dw2, rtol=1e-4, atol=1e-4, what="fused vs split")

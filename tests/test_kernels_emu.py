@@ -39,6 +39,11 @@ def test_bn_relu_pool(lib, pool, in_pad, out_pad, H, W):
     kc.check_bn_relu_pool(lib, DEV, pool=pool, in_pad=in_pad, out_pad=out_pad, H=H, W=W)
 
 
+def test_conv1_bwd_fused(lib):
+    kc.check_conv1_bwd_fused(lib, DEV)
+    kc.check_conv1_bwd_fused(lib, DEV, E=1, ipe=3, H=9, W=8, out_pad=0, seed=22)     # odd height: dropped edge row
+
+
 def test_head(lib):
     kc.check_head(lib, DEV)
     kc.check_head(lib, DEV, E=1, N=5, Cch=12, P=1, seed=8)

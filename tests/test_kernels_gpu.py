@@ -49,6 +49,12 @@ def test_gp(lib):
     kc.check_gp(lib, DEV, E=2, C=5, per_class=1, D=64, M=75, seed=11)       # N = 5   (1-shot test episode)
 
 
+def test_conv1_bwd_fused(lib):
+    kc.check_conv1_bwd_fused(lib, DEV)
+    kc.check_conv1_bwd_fused(lib, DEV, E=1, ipe=3, H=9, W=8, out_pad=0, seed=22)
+    kc.check_conv1_bwd_fused(lib, DEV, E=2, ipe=5, H=84, W=84, out_pad=1, seed=23)   # BASELINE geometry
+
+
 def test_gp_large(lib):
     """N beyond shared memory (BASELINE configs[4]: 20-way 5-shot, Gram-N sweep up to 500)."""
     kc.check_gp(lib, DEV, E=2, C=5, per_class=21, D=1600, M=75, seed=9, large=True)      # N = 105, same as small path
