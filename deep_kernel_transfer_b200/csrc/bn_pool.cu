@@ -106,13 +106,13 @@ DKTB_EXPORT int dktb_bn_finalize(const float* partials, int B, int T, int ipe, i
 // forward: out = maxpool2( relu( (y - mean) * invstd * gamma + beta ) )
 // y: [B][H+2ip][W+2ip][64] (ip = in_pad), out: [B][Ho+2op][Wo+2op][64]; stats row = img/ipe (ipe==0: row 0)
 // ------------------------------------------------------------------------------------------------
+template <int POOL>
 __global__ void __launch_bounds__(256) bn_relu_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ mean,
                                                                const float* __restrict__ invstd,
                                                                const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, float* __restrict__ out,
-                                                               int B, int H, int W, int ipe, int in_pad, int out_pad,
-                                                               int pool) {
-  const int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
+                                                               int B, int H, int W, int ipe, int in_pad, int out_pad) {
+  const int Ho = POOL ? H / 2 : H, Wo = POOL ? W / 2 : W;
   const long total = (long)B * Ho * Wo * 16;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -123,21 +123,26 @@ __global__ void __launch_bounds__(256) bn_relu_pool_fwd_kernel(const float* __re
   const int oh = (int)(t % Ho);
   const int img = (int)(t / Ho);
   const int e = ipe > 0 ? img / ipe : 0;
+  const int Hi = H + 2 * in_pad, Wi = W + 2 * in_pad;
+  constexpr int NP = POOL ? 2 : 1;
+  // all window loads in flight before any arithmetic
+  const float* src = y + (((long)img * Hi + (POOL ? oh * 2 : oh) + in_pad) * Wi + (POOL ? ow * 2 : ow) + in_pad) * 64 + c4;
+  float4 v[NP * NP];
+#pragma unroll
+  for (int dy = 0; dy < NP; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < NP; ++dx) v[dy * NP + dx] = dktb_ld4(src + ((long)dy * Wi + dx) * 64);
   const float4 m = dktb_ld4(mean + e * 64 + c4), is = dktb_ld4(invstd + e * 64 + c4);
   const float4 g = dktb_ld4(gamma + c4), bt = dktb_ld4(beta + c4);
   const float4 sc = make_float4(g.x * is.x, g.y * is.y, g.z * is.z, g.w * is.w);
-  const int Hi = H + 2 * in_pad, Wi = W + 2 * in_pad;
   float4 best = make_float4(0.f, 0.f, 0.f, 0.f);     // relu floor doubles as the max identity
-  const int np = pool ? 2 : 1;
-  for (int dy = 0; dy < np; ++dy)
-    for (int dx = 0; dx < np; ++dx) {
-      const int h = (pool ? oh * 2 : oh) + dy, w = (pool ? ow * 2 : ow) + dx;
-      const float4 v = dktb_ld4(y + (((long)img * Hi + h + in_pad) * Wi + w + in_pad) * 64 + c4);
-      best.x = fmaxf(best.x, fmaf(v.x - m.x, sc.x, bt.x));
-      best.y = fmaxf(best.y, fmaf(v.y - m.y, sc.y, bt.y));
-      best.z = fmaxf(best.z, fmaf(v.z - m.z, sc.z, bt.z));
-      best.w = fmaxf(best.w, fmaf(v.w - m.w, sc.w, bt.w));
-    }
+#pragma unroll
+  for (int k = 0; k < NP * NP; ++k) {
+    best.x = fmaxf(best.x, fmaf(v[k].x - m.x, sc.x, bt.x));
+    best.y = fmaxf(best.y, fmaf(v[k].y - m.y, sc.y, bt.y));
+    best.z = fmaxf(best.z, fmaf(v[k].z - m.z, sc.z, bt.z));
+    best.w = fmaxf(best.w, fmaf(v[k].w - m.w, sc.w, bt.w));
+  }
   const int Hq = Ho + 2 * out_pad, Wq = Wo + 2 * out_pad;
   dktb_st4(out + (((long)img * Hq + oh + out_pad) * Wq + ow + out_pad) * 64 + c4, best);
 }
@@ -149,8 +154,13 @@ DKTB_EXPORT int dktb_bn_relu_pool_fwd(const float* y, const float* mean, const f
   const int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
   const long total = (long)B * Ho * Wo * 16;
   DKTB_CHECK_ARG(total > 0);
-  DKTB_LAUNCH(bn_relu_pool_fwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, y, mean, invstd,
-              gamma, beta, out, B, H, W, ipe, in_pad, out_pad, pool);
+  if (pool) {
+    DKTB_LAUNCH(bn_relu_pool_fwd_kernel<1>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, y, mean, invstd,
+                gamma, beta, out, B, H, W, ipe, in_pad, out_pad);
+  } else {
+    DKTB_LAUNCH(bn_relu_pool_fwd_kernel<0>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, y, mean, invstd,
+                gamma, beta, out, B, H, W, ipe, in_pad, out_pad);
+  }
   return dktb_launch_status();
 }
 

@@ -227,14 +227,18 @@ __global__ void __launch_bounds__(256, 3) conv1_bwd_fused_kernel(
     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
     const float* __restrict__ beta, const float* __restrict__ sums, float* __restrict__ partial, int B, int H, int W,
     int ipe, int out_pad, float inv_count) {
+  constexpr int GLD = 68;                                  // gradient tile pitch: float4 rows
   __shared__ __align__(16) float s_in[3][C1_TH + 2][C1_TW + 4];
-  __shared__ float s_g[C1_TH * C1_TW][64 + 1];
-  float (*s_fin)[28][64] = reinterpret_cast<float (*)[28][64]>(&s_g[0][0]);   // reused after the tile loop
+  __shared__ __align__(16) float s_g[C1_TH * C1_TW * GLD];
+  // per-episode channel constants: mean, gamma*invstd, beta, A = -ss*s1/n, Bc = -ss*s2/n*invstd, ss
+  __shared__ __align__(16) float s_k[6][64];
+  float (*s_fin)[28][64] = reinterpret_cast<float (*)[28][64]>(s_g);            // reused after the tile loop
   const int tid = threadIdx.x;
   const int co = tid % 64, row = tid / 64;
   const int TX = (W + C1_TW - 1) / C1_TW, TY = (H + C1_TH - 1) / C1_TH;
   const long ntiles = (long)B * TX * TY;
   const int Ho = H / 2, Wo = W / 2, Hq = Ho + 2 * out_pad, Wq = Wo + 2 * out_pad;
+  const int c4 = (tid % 16) * 4;                            // staging role: 4 channels, windows tid/16 and tid/16 + 16
   float acc[3][3][3];
   float accb = 0.f;
 #pragma unroll
@@ -243,11 +247,24 @@ __global__ void __launch_bounds__(256, 3) conv1_bwd_fused_kernel(
     for (int r = 0; r < 3; ++r)
 #pragma unroll
       for (int s = 0; s < 3; ++s) acc[a][r][s] = 0.f;
+  int e_cur = -1;
   for (long t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int b = (int)(t / (TX * TY));
     const int rem = (int)(t % (TX * TY));
     const int h0 = (rem / TX) * C1_TH, w0 = (rem % TX) * C1_TW;
     const int e = b / ipe;
+    if (e != e_cur) {                                       // uniform over the CTA (depends on t only)
+      if (tid < 64) {
+        const float is = invstd[e * 64 + tid], ss = gamma[tid] * is;
+        s_k[0][tid] = mean[e * 64 + tid];
+        s_k[1][tid] = ss;
+        s_k[2][tid] = beta[tid];
+        s_k[3][tid] = -ss * (sums[(long)e * 128 + tid] * inv_count);
+        s_k[4][tid] = -ss * (sums[(long)e * 128 + 64 + tid] * inv_count) * is;
+        s_k[5][tid] = ss;
+      }
+      e_cur = e;
+    }
     __syncthreads();
     for (int i = tid; i < 3 * (C1_TH + 2) * (C1_TW + 2); i += 256) {
       const int ci = i / ((C1_TH + 2) * (C1_TW + 2));
@@ -258,44 +275,50 @@ __global__ void __launch_bounds__(256, 3) conv1_bwd_fused_kernel(
       if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = x[(((long)b * 3 + ci) * H + hh) * W + ww];
       s_in[ci][r][c] = v;
     }
-    // gradient tile: work item = (pool window of the tile, 4 channels); 32 windows x 16 channel groups
-    for (int i = tid; i < (C1_TH / 2) * (C1_TW / 2) * 16; i += 256) {
-      const int c4 = (i % 16) * 4, wi = i / 16;
+    // gradient tile: work item = (pool window of the tile, 4 channels), handled as two channel pairs to bound the
+    // live registers next to the 28 accumulators; 32 windows x 16 channel groups = 2 items per thread
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int wi = tid / 16 + 16 * half;
       const int wy = wi / (C1_TW / 2), wx = wi % (C1_TW / 2);
       const int oh = h0 / 2 + wy, ow = w0 / 2 + wx;
-      const float4 m = dktb_ld4(mean + e * 64 + c4), is = dktb_ld4(invstd + e * 64 + c4);
-      const float4 g = dktb_ld4(gamma + c4), bt = dktb_ld4(beta + c4);
-      const float4 q1 = dktb_ld4(sums + (long)e * 128 + c4), q2 = dktb_ld4(sums + (long)e * 128 + 64 + c4);
-      const float mm[4] = {m.x, m.y, m.z, m.w}, ii[4] = {is.x, is.y, is.z, is.w};
-      const float ss[4] = {g.x * is.x, g.y * is.y, g.z * is.z, g.w * is.w}, bb[4] = {bt.x, bt.y, bt.z, bt.w};
-      const float a1[4] = {q1.x * inv_count, q1.y * inv_count, q1.z * inv_count, q1.w * inv_count};
-      const float a2[4] = {q2.x * inv_count, q2.y * inv_count, q2.z * inv_count, q2.w * inv_count};
       const bool full = (oh < Ho) && (ow < Wo);
-      float gg[4] = {0.f, 0.f, 0.f, 0.f};
-      if (full) {
-        const float4 go = dktb_ld4(gout + (((long)b * Hq + oh + out_pad) * Wq + ow + out_pad) * 64 + c4);
-        gg[0] = go.x; gg[1] = go.y; gg[2] = go.z; gg[3] = go.w;
-      }
-      float yv[4][4];
-      bool inb[4];
+      const int hh0 = h0 + 2 * wy, ww0 = w0 + 2 * wx;
+      const bool inr[2] = {hh0 < H, hh0 + 1 < H}, inc[2] = {ww0 < W, ww0 + 1 < W};
+      const float* yb = y + (((long)b * H + hh0) * W + ww0) * 64 + c4;
+      const float* gb = gout + (((long)b * Hq + oh + out_pad) * Wq + ow + out_pad) * 64 + c4;
+      float* sg = s_g + ((2 * wy) * C1_TW + 2 * wx) * GLD + c4;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int hh = h0 + 2 * wy + (k >> 1), ww = w0 + 2 * wx + (k & 1);
-        inb[k] = (hh < H) && (ww < W);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (inb[k]) v = dktb_ld4(y + (((long)b * H + hh) * W + ww) * 64 + c4);
-        yv[0][k] = v.x; yv[1][k] = v.y; yv[2][k] = v.z; yv[3][k] = v.w;
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        int arg = -1; float gz = 0.f, xh = 0.f;
-        if (full) bn_bwd_route(yv[j], 4, mm[j], ii[j], ss[j], bb[j], gg[j], arg, gz, xh);
+      for (int jp = 0; jp < 2; ++jp) {
+        const int c = c4 + 2 * jp;
+        const float2 mm = *reinterpret_cast<const float2*>(&s_k[0][c]), sc = *reinterpret_cast<const float2*>(&s_k[1][c]);
+        const float2 bb = *reinterpret_cast<const float2*>(&s_k[2][c]), aa = *reinterpret_cast<const float2*>(&s_k[3][c]);
+        const float2 bc = *reinterpret_cast<const float2*>(&s_k[4][c]);
+        float2 gg = make_float2(0.f, 0.f);
+        if (full) gg = *reinterpret_cast<const float2*>(gb + 2 * jp);
+        float2 d[4];                                        // y - mean at the 4 window positions
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float xhat = (yv[j][k] - mm[j]) * ii[j];
-          const float gzk = (k == arg) ? gz : 0.f;
-          const int p = (2 * wy + (k >> 1)) * C1_TW + 2 * wx + (k & 1);
-          s_g[p][c4 + j] = inb[k] ? ss[j] * (gzk - a1[j] - xhat * a2[j]) : 0.f;
+          float2 v = make_float2(0.f, 0.f);
+          if (inr[k >> 1] && inc[k & 1]) v = *reinterpret_cast<const float2*>(yb + ((long)(k >> 1) * W + (k & 1)) * 64 + 2 * jp);
+          d[k] = make_float2(v.x - mm.x, v.y - mm.y);
+        }
+        // first maximum of the post-ReLU values in scan order receives the pooled gradient (if positive)
+        float bx = fmaxf(fmaf(d[0].x, sc.x, bb.x), 0.f), by = fmaxf(fmaf(d[0].y, sc.y, bb.y), 0.f);
+        int ax = 0, ay = 0;
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+          const float zx = fmaxf(fmaf(d[k].x, sc.x, bb.x), 0.f), zy = fmaxf(fmaf(d[k].y, sc.y, bb.y), 0.f);
+          if (zx > bx) { bx = zx; ax = k; }
+          if (zy > by) { by = zy; ay = k; }
+        }
+        const float hx = (full && bx > 0.f) ? sc.x * gg.x : 0.f, hy = (full && by > 0.f) ? sc.y * gg.y : 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float2 r = make_float2(fmaf(d[k].x, bc.x, aa.x + (k == ax ? hx : 0.f)),
+                                 fmaf(d[k].y, bc.y, aa.y + (k == ay ? hy : 0.f)));
+          if (!(inr[k >> 1] && inc[k & 1])) r = make_float2(0.f, 0.f);
+          *reinterpret_cast<float2*>(sg + ((k >> 1) * C1_TW + (k & 1)) * GLD + 2 * jp) = r;
         }
       }
     }
@@ -303,7 +326,7 @@ __global__ void __launch_bounds__(256, 3) conv1_bwd_fused_kernel(
     for (int c0 = 0; c0 < C1_TW; c0 += 4) {
       float g[4];
 #pragma unroll
-      for (int p = 0; p < 4; ++p) g[p] = s_g[row * C1_TW + c0 + p][co];
+      for (int p = 0; p < 4; ++p) g[p] = s_g[(row * C1_TW + c0 + p) * GLD + co];
       accb += (g[0] + g[1]) + (g[2] + g[3]);
 #pragma unroll
       for (int ci = 0; ci < 3; ++ci)

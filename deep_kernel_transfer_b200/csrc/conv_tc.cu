@@ -837,6 +837,20 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
 // ------------------------------------------------------------------------------------------------------------------
 enum { kC1_Y = 0, kC1_STATS = 1, kC1_APPLY = 2 };
 constexpr int kC1PatchW = 88;                  // patch row pitch (floats): W + 2 <= 88
+constexpr int kC1OutLd = 68;                   // epilogue staging pitch: float4 rows, conflict-free for 16 B accesses
+
+// im2col slots SET*16 .. SET*16+15 of one output pixel (k = ci*9 + r*3 + s; slots 27..31 are zero): every patch offset is
+// a compile-time constant relative to `base` = &patch[py][w0 + px]
+template <int SET>
+__device__ __forceinline__ void c1_stage_row(const float* __restrict__ base, uint32_t (&hi)[16], uint32_t (&lo)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int k = SET * 16 + j;
+    float v = 0.f;
+    if (k < 27) v = base[((k / 9) * 6 + (k % 9) / 3) * kC1PatchW + (k % 3)];
+    split_tf32(v, hi[j], lo[j]);
+  }
+}
 
 __global__ void __launch_bounds__(kTsThreads, 3)
 conv1_tc_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias,
@@ -848,12 +862,12 @@ conv1_tc_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
   __shared__ uint64_t bar_w, bar_afull, bar_acc;
   __shared__ uint32_t s_tmem;
   __shared__ int s_err;
-  __shared__ float s_valid[kRows];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (*reinterpret_cast<volatile int*>(err) != 0) return;
   unsigned char* s_wt = smem;                                        // W1 hi 8 KB | W1 lo 8 KB
   float* s_patch = reinterpret_cast<float*>(smem + 16384);           // [3][6][kC1PatchW]
-  float* s_out = s_patch + 3 * 6 * kC1PatchW;                        // [128][kOutLd]
+  float* s_out = s_patch + 3 * 6 * kC1PatchW;                        // [128][kC1OutLd]
+  __shared__ float s_stat[2][2][64];
   const int b = blockIdx.y, h0 = blockIdx.x * 4;
   const int TX = (W + 31) / 32;
 
@@ -865,14 +879,12 @@ conv1_tc_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc<128>(&s_tmem);
-  // input patch: rows h0-1 .. h0+4, columns -1 .. W, zero outside the image
-  for (int i = tid; i < 3 * 6 * kC1PatchW; i += kTsThreads) {
-    const int ci = i / (6 * kC1PatchW), rem = i % (6 * kC1PatchW);
-    const int r = rem / kC1PatchW, c = rem % kC1PatchW;
-    const int hh = h0 + r - 1, ww = c - 1;
-    float v = 0.f;
-    if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = x[(((long)b * 3 + ci) * H + hh) * W + ww];
-    s_patch[i] = v;
+  // input patch: rows h0-1 .. h0+4, columns -1 .. W, zero outside the image; one warp per (channel, row)
+  for (int rowi = warp; rowi < 18; rowi += kTsThreads / 32) {
+    const int ci = rowi / 6, hh = h0 + rowi % 6 - 1;
+    const bool rok = hh >= 0 && hh < H;
+    const float* src = x + (((long)b * 3 + ci) * H + (rok ? hh : 0)) * W - 1;
+    for (int c = lane; c < kC1PatchW; c += 32) s_patch[rowi * kC1PatchW + c] = (rok && c >= 1 && c <= W) ? src[c] : 0.f;
   }
   tc::tcgen05_fence_before();
   __syncthreads();
@@ -916,69 +928,75 @@ conv1_tc_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
     const int py = p >> 5, px = p & 31;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const int e = (ipe > 0) ? b / ipe : 0;
+    const float* prow = s_patch + py * kC1PatchW + px;
+    float* orow = s_out + p * kC1OutLd + set * 32;
+    const float* brow = bias ? bias + set * 32 : nullptr;
+    // epilogue roles (fixed per thread): Y store = 16 threads per pixel row; stats = (sum | sumsq, row half, channel)
+    const int st_r0 = ct >> 4, st_c4 = (ct & 15) * 4;
+    const int sw = ct >> 7, sh = (ct >> 6) & 1, sc = ct & 63;
     bool ok = true;
     for (int tx = 0; tx < TX && ok; ++tx) {
       const int w0 = tx * 32;
       // ---- stage the im2col row (16 of the 32 k-slots per thread)
       uint32_t hi[16], lo[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int k = set * 16 + j;
-        float v = 0.f;
-        if (k < 27) {
-          const int ci = k / 9, rr = (k % 9) / 3, ss = k % 3;
-          v = s_patch[(ci * 6 + py + rr) * kC1PatchW + w0 + px + ss];
-        }
-        split_tf32(v, hi[j], lo[j]);
-      }
+      if (set == 0) c1_stage_row<0>(prow + w0, hi, lo);
+      else c1_stage_row<1>(prow + w0, hi, lo);
       tc::tmem_st16(a_tmem + lane_base + set * 16, hi);
       tc::tmem_st16(a_tmem + lane_base + 32 + set * 16, lo);
       tc::tmem_st_wait();
       tc::tcgen05_fence_before();
       tc::mbar_arrive(&bar_afull);
-      // ---- accumulator -> smem tile
+      // ---- accumulator (+ bias) -> smem tile; pixels outside the image are stored as zeros
       ok = tc::mbar_wait(&bar_acc, tx & 1);
       if (!ok) break;
       tc::tcgen05_fence_after();
-      const int hh = h0 + py, ww = w0 + px;
-      if (set == 0) s_valid[p] = (hh < H && ww < W) ? 1.f : 0.f;
+      const bool valid = (h0 + py < H) && (w0 + px < W);
 #pragma unroll
       for (int cc = 0; cc < 32; cc += 16) {
-        const int c = set * 32 + cc;
         uint32_t v[16];
-        tc::tmem_ld16(d_tmem + lane_base + c, v);
+        tc::tmem_ld16(d_tmem + lane_base + set * 32 + cc, v);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) s_out[p * kOutLd + c + j] = __uint_as_float(v[j]) + (bias ? bias[c + j] : 0.f);
+        for (int j = 0; j < 16; j += 4) {
+          float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                 __uint_as_float(v[j + 3]));
+          if (brow) {
+            const float4 bv = dktb_ld4(brow + cc + j);
+            o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+          }
+          if (!valid) o = make_float4(0.f, 0.f, 0.f, 0.f);
+          dktb_st4(orow + cc + j, o);
+        }
       }
       tc::tcgen05_fence_before();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (mode == kC1_Y) {
-        for (int idx = ct; idx < kRows * 16; idx += 256) {
-          const int rr = idx >> 4, c4 = (idx & 15) * 4;
-          if (s_valid[rr] != 0.f) {
-            const float* src = s_out + rr * kOutLd + c4;
-            const int oh = h0 + (rr >> 5), ow = w0 + (rr & 31);
-            dktb_st4(y + (((long)b * H + oh) * W + ow) * 64 + c4, make_float4(src[0], src[1], src[2], src[3]));
-          }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int oh = h0 + (it >> 1), ow = w0 + st_r0 + 16 * (it & 1);
+          if (oh < H && ow < W)
+            dktb_st4(y + (((long)b * H + oh) * W + ow) * 64 + st_c4,
+                     dktb_ld4(s_out + (st_r0 + 16 * it) * kC1OutLd + st_c4));
         }
       }
-      if (mode != kC1_APPLY && partials != nullptr && ct < 128) {
-        const int which = ct >> 6, c = ct & 63;
+      if (mode != kC1_APPLY && partials != nullptr) {
+        const float* col = s_out + (sh * 64) * kC1OutLd + sc;
         float t = 0.f;
-        for (int rr = 0; rr < kRows; ++rr) {
-          const float v = s_out[rr * kOutLd + c] * s_valid[rr];
-          t += which ? v * v : v;
+        if (sw) {
+#pragma unroll 16
+          for (int rr = 0; rr < 64; ++rr) { const float v = col[rr * kC1OutLd]; t = fmaf(v, v, t); }
+        } else {
+#pragma unroll 16
+          for (int rr = 0; rr < 64; ++rr) t += col[rr * kC1OutLd];
         }
-        const long blk = ((long)b * gridDim.x + blockIdx.x) * TX + tx;
-        partials[(blk * 2 + which) * 64 + c] = t;
+        s_stat[sw][sh][sc] = t;
       }
       if (mode == kC1_APPLY) {
         const int c4 = (ct & 15) * 4, pp = ct >> 4;          // pooled column pp (0..15), both pooled rows
         const int Ho = H / 2, Wo = W / 2;
         const float4 g = dktb_ld4(gamma + c4), bt = dktb_ld4(beta + c4);
         const float4 m = dktb_ld4(mean + e * 64 + c4), is = dktb_ld4(invstd + e * 64 + c4);
-        const float sc[4] = {g.x * is.x, g.y * is.y, g.z * is.z, g.w * is.w};
+        const float sc4[4] = {g.x * is.x, g.y * is.y, g.z * is.z, g.w * is.w};
         const float mm[4] = {m.x, m.y, m.z, m.w}, bb[4] = {bt.x, bt.y, bt.z, bt.w};
 #pragma unroll
         for (int pr = 0; pr < 2; ++pr) {
@@ -989,9 +1007,10 @@ conv1_tc_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
             for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
               for (int dx = 0; dx < 2; ++dx) {
-                const float* src = s_out + ((2 * pr + dy) * 32 + 2 * pp + dx) * kOutLd + c4;
+                const float4 q = dktb_ld4(s_out + ((2 * pr + dy) * 32 + 2 * pp + dx) * kC1OutLd + c4);
+                const float src[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) best[j] = fmaxf(best[j], fmaf(src[j] - mm[j], sc[j], bb[j]));
+                for (int j = 0; j < 4; ++j) best[j] = fmaxf(best[j], fmaf(src[j] - mm[j], sc4[j], bb[j]));
               }
             dktb_st4(act + (((long)b * (Ho + 2) + ho + 1) * (Wo + 2) + wo + 1) * 64 + c4,
                      make_float4(best[0], best[1], best[2], best[3]));
@@ -999,6 +1018,10 @@ conv1_tc_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
         }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (mode != kC1_APPLY && partials != nullptr && ct < 128) {
+        const long blk = ((long)b * gridDim.x + blockIdx.x) * TX + tx;
+        partials[(blk * 2 + sw) * 64 + sc] = s_stat[sw][0][sc] + s_stat[sw][1][sc];
+      }
     }
     if (!ok) s_err = 1;
   }
@@ -1133,7 +1156,7 @@ DKTB_EXPORT int dktb_conv1_tc(const float* x, const float* wb1, const float* bia
   DKTB_CHECK_ARG(mode != kC1_APPLY || (mean && invstd && gamma && beta && act));
   CUtensorMap map_w;
   if (tc_make_tmap_2d(&map_w, wb1, 32, 128, 32, 64) != 0) return DKTB_BAD_ARG - 1;
-  const int smem = 16384 + 3 * 6 * kC1PatchW * 4 + kRows * kOutLd * 4 + 1024;
+  const int smem = 16384 + 3 * 6 * kC1PatchW * 4 + kRows * kC1OutLd * 4 + 1024;
   cudaFuncSetAttribute(conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   dim3 grid((H + 3) / 4, B);
   conv1_tc_kernel<<<grid, kTsThreads, smem, stream>>>(x, map_w, bias, y, partials, mean, invstd, gamma, beta, act, ipe, H,
