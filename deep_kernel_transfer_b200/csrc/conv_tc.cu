@@ -1020,7 +1020,8 @@ conv1_tc_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (mode != kC1_APPLY && partials != nullptr && ct < 128) {
         const long blk = ((long)b * gridDim.x + blockIdx.x) * TX + tx;
-        partials[(blk * 2 + sw) * 64 + sc] = s_stat[sw][0][sc] + s_stat[sw][1][sc];
+        const int w2 = ct >> 6;                               // 0: sum, 1: sum of squares
+        partials[(blk * 2 + w2) * 64 + sc] = s_stat[w2][0][sc] + s_stat[w2][1][sc];
       }
     }
     if (!ok) s_err = 1;
