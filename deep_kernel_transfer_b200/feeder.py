@@ -6,8 +6,10 @@ import torch
 
 
 class DevicePrefetcher:
-    def __init__(self, iterable, device):
+    def __init__(self, iterable, device, timing=False):
         self.it = iter(iterable)
+        self.timing = timing                 # keep (start, end) CUDA events of every H2D copy (bench.py reads them)
+        self.copy_events = []
         self.dev = torch.device(device)
         self.cuda = self.dev.type == "cuda"
         self.copy_stream = torch.cuda.Stream(self.dev) if self.cuda else None
@@ -33,9 +35,14 @@ class DevicePrefetcher:
         with torch.cuda.stream(self.copy_stream):
             if self.free[i] is not None:
                 self.copy_stream.wait_event(self.free[i])      # the step that last read this buffer has finished
+            if self.timing:
+                t0 = torch.cuda.Event(enable_timing=True)
+                t0.record(self.copy_stream)
             self.bufs[i].copy_(x, non_blocking=True)
-            ev = torch.cuda.Event()
+            ev = torch.cuda.Event(enable_timing=self.timing)
             ev.record(self.copy_stream)
+            if self.timing:
+                self.copy_events.append((t0, ev))
         self._next = (self.bufs[i], ev)
         self.k += 1
 
@@ -60,3 +67,42 @@ class DevicePrefetcher:
                 ev = torch.cuda.Event()
                 ev.record(torch.cuda.current_stream(self.dev))
                 self.free[i] = ev
+
+
+def bind_to_gpu_numa(device_index=0):
+    """Pin this process (and therefore its later pinned-host allocations, first-touch) to the CPUs of the NUMA node the
+    GPU hangs off: on a two-socket host a feeder running on the far socket pushes every episode batch across the
+    inter-socket link first.  Best effort -- returns the CPU set used, or None if the topology cannot be read."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = device_index
+        if visible:
+            tok = visible.split(",")[device_index].strip()
+            if tok.isdigit():
+                idx = int(tok)
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:          # nvml prints an 8-digit PCI domain, sysfs uses 4
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
