@@ -13,6 +13,7 @@
 #include "dktb_common.cuh"
 
 #ifndef DKTB_EMU
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 namespace {
@@ -394,7 +395,8 @@ constexpr int kP_Threads = 64 + 256 + 128;
 __global__ void __launch_bounds__(kP_Threads, 1)
 conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                              const float* __restrict__ bias, float* __restrict__ out, float* __restrict__ partials,
-                             int B, int H, int W, int halo_rows_pad, int tiles_per_img, int* __restrict__ err) {
+                             int B, int H, int W, int halo_rows_pad, int tiles_per_img, int lo_n64,
+                             int* __restrict__ err) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar_hfull[2], bar_hempty[2], bar_wfull[kP_WStages], bar_wempty[kP_WStages], bar_afull[kP_AStages],
@@ -470,6 +472,9 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer: 16 x (M128, N128, K8) per tap
     const uint32_t idesc = tc::umma_idesc(2, 128, 128, 0, 0);
+    // 3xTF32 needs a_hi*w_hi + a_hi*w_lo + a_lo*w_hi: the a_lo pass only has to cover the w_hi half of the stacked
+    // operand (N = 64, ~50 instead of ~65 issue cycles); lo_n64 == 0 keeps the symmetric N = 128 form (adds a_lo*w_lo)
+    const uint32_t idesc_lo = lo_n64 ? tc::umma_idesc(2, 128, 64, 0, 0) : idesc;
     int t = 0;
     long wi = 0;
     bool ok = true;
@@ -491,8 +496,8 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const uint64_t w_cat = tc::umma_desc_sw128(wbase + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
-            tc::umma_tf32_ts(d_tmem, acol + 64 + k * 8, w_cat, idesc, (tap | k) ? 1u : 0u);   // a_lo * [w_hi | w_lo]
-            tc::umma_tf32_ts(d_tmem, acol + k * 8, w_cat, idesc, 1u);                          // a_hi * [w_hi | w_lo]
+            tc::umma_tf32_ts(d_tmem, acol + k * 8, w_cat, idesc, (tap | k) ? 1u : 0u);        // a_hi * [w_hi | w_lo]
+            tc::umma_tf32_ts(d_tmem, acol + 64 + k * 8, w_cat, idesc_lo, 1u);                  // a_lo * w_hi (| w_lo)
           }
           tc::umma_commit(&bar_aempty[sa]);
           tc::umma_commit(&bar_wempty[sw]);
@@ -1136,8 +1141,13 @@ DKTB_EXPORT int dktb_conv3x3_tc3_fwd(const float* a, const float* wb, const floa
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = (int)(ntiles < sms ? ntiles : sms);
+  static int lo_n64 = -1;
+  if (lo_n64 < 0) {
+    const char* v = getenv("DKTB_TC3_LO_N64");
+    lo_n64 = (v != nullptr && v[0] == '0') ? 0 : 1;
+  }
   conv3x3_tc_persistent_kernel<<<grid, kP_Threads, smem, stream>>>(map_a, map_w, bias, out, partials, B, H, W, halo_pad,
-                                                                   tiles_per_img, err);
+                                                                   tiles_per_img, lo_n64, err);
   return dktb_launch_status();
 }
 
