@@ -203,7 +203,19 @@ constexpr int kAStages = 3;                   // TMEM A stages of {hi 32 | lo 32
 constexpr int kTsThreads = 64 + 256;          // TMA warp, MMA warp, 8 stager / epilogue warps
 
 // tf32 split with full-rate integer ops: hi = round-to-nearest(-away) to 10 mantissa bits, lo = rounded remainder
+// DKTB_SPLIT_ROUND_LO: also round the remainder (2 more integer ops per element).  Default: hand the exact remainder
+// v - hi to the tensor core, which truncates it to tf32 -- the operand is then carried to 2^-21 instead of 2^-22
+// (|lo| <= 2^-11 |v|, truncation loses < 2^-10 |lo|), well inside the 1e-4 parity bar, and the stager warps (the
+// bottleneck of the convolution kernels: tensor pipe 55% busy) issue 3 instead of 5 instructions per element.
 __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u;
+#ifdef DKTB_SPLIT_ROUND_LO
+  lo = (__float_as_uint(v - __uint_as_float(hi)) + 0x1000u) & 0xFFFFE000u;
+#else
+  lo = __float_as_uint(v - __uint_as_float(hi));
+#endif
+}
+__device__ __forceinline__ void split_tf32_exact(float v, uint32_t& hi, uint32_t& lo) {      // weights (prepared once)
   hi = (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u;
   lo = (__float_as_uint(v - __uint_as_float(hi)) + 0x1000u) & 0xFFFFE000u;
 }
@@ -1044,7 +1056,7 @@ __global__ void prep_weights_conv1_tc_kernel(const float* __restrict__ w, float*
   const int co = i / 32, k = i % 32;
   const float v = k < 27 ? w[co * 27 + k] : 0.f;
   uint32_t h, l;
-  split_tf32(v, h, l);
+  split_tf32_exact(v, h, l);
   wb1[i] = __uint_as_float(h);
   wb1[64 * 32 + i] = __uint_as_float(l);
 }
