@@ -400,7 +400,8 @@ conv3x3_tc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kP_WStages = 3;                 // full-tap weight stages: [half 0 | half 1] x [w_hi | w_lo] = 32 KB
 constexpr int kP_WStageBytes = 32768;
-constexpr int kP_AStages = 2;                 // full-tap A stages: {hi 64 | lo 64} columns
+constexpr int kP_AStages = 4;                 // half-tap A stages (32 channels): {hi 32 | lo 32} columns each; a ring of
+                                              // four gives a stage three MMA groups of slack before it is needed again
 constexpr int kP_Taps = 9;
 constexpr int kP_Threads = 64 + 256 + 128;
 
@@ -432,7 +433,7 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
       tc::mbar_init(&bar_accempty[s], 128);
     }
     for (int s = 0; s < kP_WStages; ++s) { tc::mbar_init(&bar_wfull[s], 1); tc::mbar_init(&bar_wempty[s], 1); }
-    for (int s = 0; s < kP_AStages; ++s) { tc::mbar_init(&bar_afull[s], 256); tc::mbar_init(&bar_aempty[s], 1); }
+    for (int s = 0; s < kP_AStages; ++s) { tc::mbar_init(&bar_afull[s], 128); tc::mbar_init(&bar_aempty[s], 1); }
     s_err = 0;
     tc::fence_barrier_init();
   }
@@ -498,24 +499,32 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
       const uint32_t d_tmem = tmem + ab * 128;
       for (int tap = 0; tap < kP_Taps && ok; ++tap, ++wi) {
         const int sw = (int)(wi % kP_WStages), pw = (int)((wi / kP_WStages) & 1);
-        const int sa = (int)(wi & 1), pa = (int)((wi >> 1) & 1);
-        ok = tc::mbar_wait(&bar_wfull[sw], pw) && tc::mbar_wait(&bar_afull[sa], pa);
+        const int pa = (int)((wi >> 1) & 1);
+        ok = tc::mbar_wait(&bar_wfull[sw], pw);
         if (!ok) break;
-        tc::tcgen05_fence_after();
         const uint32_t wbase = tc::smem_u32(s_w + sw * kP_WStageBytes);
-        const uint32_t acol = a_tmem + sa * 128;              // hi [0,64) | lo [64,128), channel c at column c
-        if (tc::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint64_t w_cat = tc::umma_desc_sw128(wbase + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
-            tc::umma_tf32_ts(d_tmem, acol + k * 8, w_cat, idesc, (tap | k) ? 1u : 0u);        // a_hi * [w_hi | w_lo]
-            tc::umma_tf32_ts(d_tmem, acol + 64 + k * 8, w_cat, idesc_lo, 1u);                  // a_lo * w_hi (| w_lo)
+        for (int h = 0; h < 2; ++h) {                         // channel halves: separately staged, separately released
+          const int sa = (int)((wi & 1) << 1) | h;
+          ok = tc::mbar_wait(&bar_afull[sa], pa);
+          if (!ok) break;
+          tc::tcgen05_fence_after();
+          const uint32_t acol = a_tmem + sa * 64;             // hi [0,32) | lo [32,64): channel 32 h + c at column c
+          if (tc::elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t w_cat = tc::umma_desc_sw128(wbase + h * 16384 + k * 32, 16, 1024);
+              tc::umma_tf32_ts(d_tmem, acol + k * 8, w_cat, idesc, (tap | h | k) ? 1u : 0u);   // a_hi * [w_hi | w_lo]
+              tc::umma_tf32_ts(d_tmem, acol + 32 + k * 8, w_cat, idesc_lo, 1u);                 // a_lo * w_hi (| w_lo)
+            }
+            tc::umma_commit(&bar_aempty[sa]);
+            if (h == 1) {
+              tc::umma_commit(&bar_wempty[sw]);
+              if (tap == kP_Taps - 1) tc::umma_commit(&bar_accfull[ab]);
+            }
           }
-          tc::umma_commit(&bar_aempty[sa]);
-          tc::umma_commit(&bar_wempty[sw]);
-          if (tap == kP_Taps - 1) tc::umma_commit(&bar_accfull[ab]);
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
     if (!ok) s_err = 1;
@@ -534,7 +543,7 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
       ok = tc::mbar_wait(&bar_hfull[hb], hp);
       if (!ok) break;
       for (int tap = 0; tap < kP_Taps && ok; ++tap, ++wi) {
-        const int sa = (int)(wi & 1), pa = (int)((wi >> 1) & 1);
+        const int sa = (int)((wi & 1) << 1) | set, pa = (int)((wi >> 1) & 1);      // this channel half's own stage ring
         const int row = r + (tap / 3) * Wp + (tap % 3);
         const unsigned char* src = s_halo + (hb * 2 + set) * half_bytes + row * 128;
         uint32_t hi[32], lo[32];
@@ -549,11 +558,11 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
         ok = tc::mbar_wait(&bar_aempty[sa], pa ^ 1);
         if (!ok) break;
         tc::tcgen05_fence_after();
-        const uint32_t dst = a_tmem + sa * 128 + lane_base + set * 32;
+        const uint32_t dst = a_tmem + sa * 64 + lane_base;
         tc::tmem_st16(dst, hi);
         tc::tmem_st16(dst + 16, hi + 16);
-        tc::tmem_st16(dst + 64, lo);
-        tc::tmem_st16(dst + 80, lo + 16);
+        tc::tmem_st16(dst + 32, lo);
+        tc::tmem_st16(dst + 48, lo + 16);
         tc::tmem_st_wait();
         tc::tcgen05_fence_before();
         tc::mbar_arrive(&bar_afull[sa]);
@@ -643,6 +652,17 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kKR = 32;                         // rows per K-block
 constexpr int kWgAStages = 3;
+
+// 16 consecutive rows (row pitch 128 B, SWIZZLE_128B) of one channel -> tf32 hi / lo; A = swizzle phase of the first row
+template <int A>
+__device__ __forceinline__ void wg_gather16(const unsigned char* __restrict__ xb, const int (&off)[8], uint32_t (&hi)[16],
+                                            uint32_t (&lo)[16]) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const float v = *reinterpret_cast<const float*>(xb + k * 128 + off[(A + k) & 7]);
+    split_tf32(v, hi[k], lo[k]);
+  }
+}
 
 __global__ void __launch_bounds__(kTsThreads, 1)
 conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g,
@@ -743,6 +763,9 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const int ci = L & 63, tsel = L >> 6;
     const int co = ct & 63, kq8 = ct >> 6;                    // G transpose: 8 k values [kq8*8, +8) of channel co
+    int xoff[8];                                              // byte offset of channel ci inside a row of swizzle phase p
+#pragma unroll
+    for (int p8 = 0; p8 < 8; ++p8) xoff[p8] = ((((ci & 31) >> 2) ^ p8) << 4) + (ci & 3) * 4;
     float bias_acc = 0.f;
     bool ok = true;
     int n = 0, ai = 0;
@@ -781,14 +804,19 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         const int tap = 2 * g + tsel;
         uint32_t hi[16], lo[16];
         if (tap < 9) {
+          // rows shift .. shift+15 of channel ci: the 128-byte swizzle phase of row r is r & 7, so with the (warp-uniform)
+          // phase of the first row as a template constant every offset below is a register picked at compile time
           const int shift = (tap / 3) * Wp + (tap % 3) + set * 16;
-          const unsigned char* xh = st + (ci >> 5) * x_half_bytes;
-          const int cq = (ci & 31) >> 2, cr = ci & 3;
-#pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const int row = k + shift;
-            const float v = *reinterpret_cast<const float*>(xh + row * 128 + ((cq ^ (row & 7)) << 4) + cr * 4);
-            split_tf32(v, hi[k], lo[k]);
+          const unsigned char* xb = st + (ci >> 5) * x_half_bytes + shift * 128;
+          switch (shift & 7) {
+            case 0: wg_gather16<0>(xb, xoff, hi, lo); break;
+            case 1: wg_gather16<1>(xb, xoff, hi, lo); break;
+            case 2: wg_gather16<2>(xb, xoff, hi, lo); break;
+            case 3: wg_gather16<3>(xb, xoff, hi, lo); break;
+            case 4: wg_gather16<4>(xb, xoff, hi, lo); break;
+            case 5: wg_gather16<5>(xb, xoff, hi, lo); break;
+            case 6: wg_gather16<6>(xb, xoff, hi, lo); break;
+            default: wg_gather16<7>(xb, xoff, hi, lo); break;
           }
         } else {
 #pragma unroll

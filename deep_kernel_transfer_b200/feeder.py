@@ -6,7 +6,7 @@ import torch
 
 
 class DevicePrefetcher:
-    def __init__(self, iterable, device, timing=False):
+    def __init__(self, iterable, device, timing=False, start=True):
         self.it = iter(iterable)
         self.timing = timing                 # keep (start, end) CUDA events of every H2D copy (bench.py reads them)
         self.copy_events = []
@@ -18,7 +18,20 @@ class DevicePrefetcher:
         self.free = [None, None]
         self.k = 0
         self._next = None
-        self._prefetch()
+        self._started = False
+        if start:
+            self.start()
+
+    def preallocate(self, shape):
+        """Allocate both device buffers up front (keeps cudaMalloc out of the first steps)."""
+        if self.cuda:
+            for i in range(2):
+                self.bufs[i] = torch.empty(tuple(shape), device=self.dev, dtype=torch.float32)
+
+    def start(self):
+        if not self._started:
+            self._started = True
+            self._prefetch()
 
     def _prefetch(self):
         try:
@@ -50,6 +63,7 @@ class DevicePrefetcher:
         return self
 
     def __next__(self):
+        self.start()
         if self._next is None:
             raise StopIteration
         buf, ev = self._next
