@@ -473,9 +473,13 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
         ok = tc::mbar_wait(&bar_wempty[s], ph ^ 1);
         if (!ok) break;
         if (tc::elect_one()) {
-          tc::mbar_expect_tx(&bar_wfull[s], kP_WStageBytes);
-          tc::tma_load_2d(s_w + s * kP_WStageBytes, &map_w, &bar_wfull[s], 0, tap * 128);
-          tc::tma_load_2d(s_w + s * kP_WStageBytes + 16384, &map_w, &bar_wfull[s], 32, tap * 128);
+          if ((lo_n64 & 2) && wi >= kP_WStages) {            // timing experiment only: reuse the stage contents
+            tc::mbar_arrive(&bar_wfull[s]);
+          } else {
+            tc::mbar_expect_tx(&bar_wfull[s], kP_WStageBytes);
+            tc::tma_load_2d(s_w + s * kP_WStageBytes, &map_w, &bar_wfull[s], 0, tap * 128);
+            tc::tma_load_2d(s_w + s * kP_WStageBytes + 16384, &map_w, &bar_wfull[s], 32, tap * 128);
+          }
         }
         __syncwarp();
         if (tap == 1 && tile + gridDim.x < ntiles) ok = load_halo(tile + gridDim.x, t + 1);
@@ -487,7 +491,7 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
     const uint32_t idesc = tc::umma_idesc(2, 128, 128, 0, 0);
     // 3xTF32 needs a_hi*w_hi + a_hi*w_lo + a_lo*w_hi: the a_lo pass only has to cover the w_hi half of the stacked
     // operand (N = 64, ~50 instead of ~65 issue cycles); lo_n64 == 0 keeps the symmetric N = 128 form (adds a_lo*w_lo)
-    const uint32_t idesc_lo = lo_n64 ? tc::umma_idesc(2, 128, 64, 0, 0) : idesc;
+    const uint32_t idesc_lo = (lo_n64 & 1) ? tc::umma_idesc(2, 128, 64, 0, 0) : idesc;
     int t = 0;
     long wi = 0;
     bool ok = true;
@@ -547,6 +551,12 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
         const int row = r + (tap / 3) * Wp + (tap % 3);
         const unsigned char* src = s_halo + (hb * 2 + set) * half_bytes + row * 128;
         uint32_t hi[32], lo[32];
+        if (lo_n64 & 4) {                                      // timing experiment only: handshakes without the staging work
+          ok = tc::mbar_wait(&bar_aempty[sa], pa ^ 1);
+          if (!ok) break;
+          tc::mbar_arrive(&bar_afull[sa]);
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 v = *reinterpret_cast<const float4*>(src + ((j ^ (row & 7)) << 4));
@@ -1185,6 +1195,8 @@ DKTB_EXPORT int dktb_conv3x3_tc3_fwd(const float* a, const float* wb, const floa
   if (lo_n64 < 0) {
     const char* v = getenv("DKTB_TC3_LO_N64");
     lo_n64 = (v != nullptr && v[0] == '0') ? 0 : 1;
+    const char* d = getenv("DKTB_TC3_TIMING_EXPERIMENT");     // bit 1: no weight streaming, bit 2: no staging (wrong results!)
+    if (d != nullptr) lo_n64 |= (atoi(d) & 6);
   }
   conv3x3_tc_persistent_kernel<<<grid, kP_Threads, smem, stream>>>(map_a, map_w, bias, out, partials, B, H, W, halo_pad,
                                                                    tiles_per_img, lo_n64, err);
