@@ -21,6 +21,8 @@ SIGNATURES = {
     "dktb_conv1_wgrad_nsplit": ("", ctypes.c_int),
     "dktb_conv1_wgrad": ("pppppiiis", ctypes.c_int),
     "dktb_conv1_bwd_fused": ("pppppppppppiiiiis", ctypes.c_int),
+    "dktb_conv1_bwd_fused_mma": ("pppppppppppiiiiis", ctypes.c_int),
+    "dktb_conv1_wgrad_reduce": ("pipps", ctypes.c_int),
     "dktb_prep_weights": ("ppps", ctypes.c_int),
     "dktb_conv3x3_tiles": ("ii", ctypes.c_int),
     "dktb_conv3x3_fwd": ("pppppiiis", ctypes.c_int),

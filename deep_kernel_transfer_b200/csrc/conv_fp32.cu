@@ -359,6 +359,13 @@ __global__ void __launch_bounds__(256, 3) conv1_bwd_fused_kernel(
   }
 }
 
+// partial [nsplit][28*64] -> dw / db (fixed order); shared with the tensor-core first-block backward
+DKTB_EXPORT int dktb_conv1_wgrad_reduce(const float* partial, int nsplit, float* dw, float* db, cudaStream_t stream) {
+  DKTB_CHECK_ARG(partial && dw && nsplit > 0);
+  DKTB_LAUNCH(conv1_wgrad_reduce_kernel, dim3(7), dim3(256), 0, stream, partial, nsplit, dw, db);
+  return dktb_launch_status();
+}
+
 DKTB_EXPORT int dktb_conv1_wgrad_nsplit(void) { return 592; }
 
 DKTB_EXPORT int dktb_conv1_wgrad(const float* x, const float* gy, float* dw, float* db, float* scratch, int B, int H,

@@ -53,6 +53,41 @@ __device__ __forceinline__ double dktb_warp_sum_d(double v) {
 __device__ __forceinline__ float dktb_softplus(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 __device__ __forceinline__ float dktb_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
 
+// Warp-level tensor-core MMA D(16x8) += A(16x8, row) * B(8x8, col), tf32 inputs / fp32 accumulate
+// (mma.sync.aligned.m16n8k8).  Fragment ownership with g = lane / 4, t = lane % 4:
+//   a0 = A[g][t]   a1 = A[g+8][t]   a2 = A[g][t+4]   a3 = A[g+8][t+4]
+//   b0 = B[t][g]   b1 = B[t+4][g]
+//   d0 = D[g][2t]  d1 = D[g][2t+1]  d2 = D[g+8][2t]  d3 = D[g+8][2t+1]
+// The tensor core reads the upper 19 bits of each operand.  The g++ emulation (tests only) rebuilds the products with
+// warp shuffles so that the fragment indexing of the callers is exercised without a GPU.
+__device__ __forceinline__ void dktb_mma_m16n8k8_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+#ifdef DKTB_EMU
+  const int lane = threadIdx.x % 32, g = lane >> 2, t = lane & 3;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k = 0; k < 8; ++k) {
+    const int kr = k & 3, khi = k >> 2;
+    // A[g][k], A[g+8][k]: owner lane g*4 + kr, registers (khi ? a2 : a0), (khi ? a3 : a1)
+    const unsigned alo = __shfl_sync(0xffffffffu, khi ? a[2] : a[0], g * 4 + kr);
+    const unsigned ahi = __shfl_sync(0xffffffffu, khi ? a[3] : a[1], g * 4 + kr);
+    // B[k][2t], B[k][2t+1]: owner lanes (2t)*4 + kr, (2t+1)*4 + kr, register (khi ? b1 : b0)
+    const unsigned b0v = __shfl_sync(0xffffffffu, khi ? b[1] : b[0], (2 * t) * 4 + kr);
+    const unsigned b1v = __shfl_sync(0xffffffffu, khi ? b[1] : b[0], (2 * t + 1) * 4 + kr);
+    const float fa0 = __uint_as_float(alo & 0xFFFFE000u), fa1 = __uint_as_float(ahi & 0xFFFFE000u);
+    const float fb0 = __uint_as_float(b0v & 0xFFFFE000u), fb1 = __uint_as_float(b1v & 0xFFFFE000u);
+    acc[0] = fmaf(fa0, fb0, acc[0]);
+    acc[1] = fmaf(fa0, fb1, acc[1]);
+    acc[2] = fmaf(fa1, fb0, acc[2]);
+    acc[3] = fmaf(fa1, fb1, acc[3]);
+  }
+  for (int i = 0; i < 4; ++i) d[i] += acc[i];
+#else
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+#endif
+}
+
 // BatchNorm + ReLU + MaxPool backward gate of one pool window and one channel: which of the (up to) 4 raw conv outputs
 // receives the pooled gradient (first maximum of the post-ReLU values in scan order, as torch's max_pool2d), the gated
 // gradient and the normalised value at that position.  Shared by bn_pool.cu and the fused first-layer backward.

@@ -57,7 +57,9 @@ class ConvNetEngine:
         self.conv1_tc = self.use_tc and os.environ.get("DKTB_CONV1", "tc") == "tc" and lib.has("dktb_conv1_tc") \
             and image_size + 2 <= 88
         # first-block backward: BN/ReLU/pool backward fused into the conv1 weight gradient (no gy[0] tensor at all)
-        self.l0_fused = os.environ.get("DKTB_L0BWD", "fused") == "fused" and lib.has("dktb_conv1_bwd_fused")
+        l0 = os.environ.get("DKTB_L0BWD", "mma")            # mma (tensor-core wgrad) | fused (FFMA wgrad) | split
+        self.l0_fused = l0 in ("mma", "fused") and lib.has("dktb_conv1_bwd_fused")
+        self.l0_fn = "conv1_bwd_fused_mma" if (l0 == "mma" and lib.has("dktb_conv1_bwd_fused_mma")) else "conv1_bwd_fused"
         self.layers = []
         h = image_size
         for i in range(depth):
@@ -192,9 +194,9 @@ class ConvNetEngine:
                                  G.bn_w[i], G.bn_b[i], ws["bwd_partial"], ws["bwd_sums"], ws["scratch_d"], B, H, W, ipe,
                                  0 if i == 0 else 1, 0 if last else 1, pool, st)
             if i == 0 and ws["gy"][0] is None:
-                lib.conv1_bwd_fused(x, ws["y"][0], gout, ws["mean"][0], ws["invstd"][0], P.bn_w[0], P.bn_b[0],
-                                    ws["bwd_sums"], G.conv_w[0], G.conv_b[0], ws["wgrad_scratch"], B, H, W, ipe,
-                                    0 if last else 1, st)
+                getattr(lib, self.l0_fn)(x, ws["y"][0], gout, ws["mean"][0], ws["invstd"][0], P.bn_w[0], P.bn_b[0],
+                                         ws["bwd_sums"], G.conv_w[0], G.conv_b[0], ws["wgrad_scratch"], B, H, W, ipe,
+                                         0 if last else 1, st)
             elif i == 0:
                 lib.conv1_wgrad(x, ws["gy"][0], G.conv_w[0], G.conv_b[0], ws["wgrad_scratch"], B, H, W, st)
             else:

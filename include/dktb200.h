@@ -46,6 +46,12 @@ int dktb_conv1_wgrad(const float* x, const float* gy, float* dw, float* db, floa
 int dktb_conv1_bwd_fused(const float* x, const float* y, const float* gout, const float* mean, const float* invstd,
                          const float* gamma, const float* beta, const float* sums, float* dw, float* db, float* scratch,
                          int B, int H, int W, int ipe, int out_pad, cudaStream_t stream);
+/* The same contract with the weight-gradient GEMM on warp-level tensor-core MMAs (mma.sync m16n8k8 tf32, 3xTF32). */
+int dktb_conv1_bwd_fused_mma(const float* x, const float* y, const float* gout, const float* mean, const float* invstd,
+                             const float* gamma, const float* beta, const float* sums, float* dw, float* db,
+                             float* scratch, int B, int H, int W, int ipe, int out_pad, cudaStream_t stream);
+/* Fixed-order reduction of nsplit per-CTA partials [28][64] (27 taps + bias row) into dw [64,3,3,3] / db [64]. */
+int dktb_conv1_wgrad_reduce(const float* partial, int nsplit, float* dw, float* db, cudaStream_t stream);
 /* weight re-layout for the 64->64 kernels: w [64,64,3,3] -> wt_fwd [9][ci][co], wt_dgrad [9][co][ci] (flipped). */
 int dktb_prep_weights(const float* w, float* wt_fwd, float* wt_dgrad, cudaStream_t stream);
 /* 64->64 3x3 conv over padded NHWC: out[q] = sum_tap A[q+off(tap)] * wt[tap]; forward (wt_fwd, bias, partials)

@@ -645,7 +645,7 @@ def check_resnet_ops(lib, dev, E=2, ipe=2, H=9, W=7, C=8, seed=80):
     _close(ad, a + b2, what="add")
 
 
-def check_conv1_bwd_fused(lib, dev, E=2, ipe=2, H=10, W=37, out_pad=1, seed=21):
+def check_conv1_bwd_fused(lib, dev, E=2, ipe=2, H=10, W=37, out_pad=1, seed=21, fn="conv1_bwd_fused"):
     """First block backward, fused (BN/ReLU/MaxPool backward inside the conv1 weight gradient), against torch autograd of
     conv1 -> per-episode BatchNorm -> ReLU -> MaxPool2d(2) and against the split device path."""
     g = torch.Generator().manual_seed(seed)
@@ -681,7 +681,7 @@ def check_conv1_bwd_fused(lib, dev, E=2, ipe=2, H=10, W=37, out_pad=1, seed=21):
     _close(dbt, beta.grad, rtol=2e-4, atol=1e-4, what="fused L0: d beta")
     dw, db = torch.empty(64, 3, 3, 3, device=dev), torch.empty(64, device=dev)
     scratch = torch.empty(lib.conv1_wgrad_nsplit() * 28 * 64, device=dev)
-    lib.conv1_bwd_fused(x.to(dev), yd, gpad, mean, invstd, gd, bd, sums, dw, db, scratch, B, H, W, ipe, out_pad, 0)
+    getattr(lib, fn)(x.to(dev), yd, gpad, mean, invstd, gd, bd, sums, dw, db, scratch, B, H, W, ipe, out_pad, 0)
     _close(dw, w.grad, rtol=2e-4, atol=2e-4, what="fused L0: d conv1 weight")
     assert float(db.abs().max()) <= 1e-3 * float(w.grad.abs().max()) + 1e-5      # cancelled by BatchNorm
     # split path: same numbers up to summation order

@@ -39,9 +39,10 @@ def test_bn_relu_pool(lib, pool, in_pad, out_pad, H, W):
     kc.check_bn_relu_pool(lib, DEV, pool=pool, in_pad=in_pad, out_pad=out_pad, H=H, W=W)
 
 
-def test_conv1_bwd_fused(lib):
-    kc.check_conv1_bwd_fused(lib, DEV)
-    kc.check_conv1_bwd_fused(lib, DEV, E=1, ipe=3, H=9, W=8, out_pad=0, seed=22)     # odd height: dropped edge row
+@pytest.mark.parametrize("fn", ["conv1_bwd_fused", "conv1_bwd_fused_mma"])
+def test_conv1_bwd_fused(lib, fn):
+    kc.check_conv1_bwd_fused(lib, DEV, fn=fn)
+    kc.check_conv1_bwd_fused(lib, DEV, E=1, ipe=3, H=9, W=8, out_pad=0, seed=22, fn=fn)     # odd height: dropped edge row
 
 
 def test_head(lib):

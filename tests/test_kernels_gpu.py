@@ -49,10 +49,11 @@ def test_gp(lib):
     kc.check_gp(lib, DEV, E=2, C=5, per_class=1, D=64, M=75, seed=11)       # N = 5   (1-shot test episode)
 
 
-def test_conv1_bwd_fused(lib):
-    kc.check_conv1_bwd_fused(lib, DEV)
-    kc.check_conv1_bwd_fused(lib, DEV, E=1, ipe=3, H=9, W=8, out_pad=0, seed=22)
-    kc.check_conv1_bwd_fused(lib, DEV, E=2, ipe=5, H=84, W=84, out_pad=1, seed=23)   # BASELINE geometry
+@pytest.mark.parametrize("fn", ["conv1_bwd_fused", "conv1_bwd_fused_mma"])
+def test_conv1_bwd_fused(lib, fn):
+    kc.check_conv1_bwd_fused(lib, DEV, fn=fn)
+    kc.check_conv1_bwd_fused(lib, DEV, E=1, ipe=3, H=9, W=8, out_pad=0, seed=22, fn=fn)
+    kc.check_conv1_bwd_fused(lib, DEV, E=2, ipe=5, H=84, W=84, out_pad=1, seed=23, fn=fn)   # BASELINE geometry
 
 
 def test_gp_large(lib):
