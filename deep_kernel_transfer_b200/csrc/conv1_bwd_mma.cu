@@ -71,27 +71,52 @@ __global__ void __launch_bounds__(256, 2) conv1_bwd_mma_kernel(
       e_cur = e;
     }
     __syncthreads();
-    // input patch rows h0-1 .. h0+4, columns w0-1 .. w0+32 (zero outside the image)
-    for (int i = tid; i < 3 * (CM_TH + 2) * (CM_TW + 2); i += 256) {
-      const int ci = i / ((CM_TH + 2) * (CM_TW + 2));
-      const int rm = i % ((CM_TH + 2) * (CM_TW + 2));
-      const int r = rm / (CM_TW + 2), c = rm % (CM_TW + 2);
-      const int hh = h0 + r - 1, ww = w0 + c - 1;
-      float v = 0.f;
-      if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = x[(((long)b * 3 + ci) * H + hh) * W + ww];
-      s_in[ci * IPLANE + r * IW + c] = v;
+    // input patch rows h0-1 .. h0+4, columns w0-1 .. w0+32 (zero outside the image): loads now, stores after the
+    // gradient-tile loads have been issued as well
+    float xv[3];
+    int xdst[3];
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+      const int i = tid + 256 * it;
+      xv[it] = 0.f;
+      xdst[it] = -1;
+      if (i < 3 * (CM_TH + 2) * (CM_TW + 2)) {
+        const int ci = i / ((CM_TH + 2) * (CM_TW + 2));
+        const int rm = i % ((CM_TH + 2) * (CM_TW + 2));
+        const int r = rm / (CM_TW + 2), c = rm % (CM_TW + 2);
+        const int hh = h0 + r - 1, ww = w0 + c - 1;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) xv[it] = x[(((long)b * 3 + ci) * H + hh) * W + ww];
+        xdst[it] = ci * IPLANE + r * IW + c;
+      }
     }
-    // gradient tile (see conv1_bwd_fused_kernel): work item = (pool window, 4 channels) as two channel pairs
+    // all global loads of both windows are issued before any arithmetic: one memory round trip per tile
+    float4 yv[2][4], gv[2];
+    bool full2[2], inb[2][4];
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const int wi = tid / 16 + 16 * half;
       const int wy = wi / (CM_TW / 2), wx = wi % (CM_TW / 2);
       const int oh = h0 / 2 + wy, ow = w0 / 2 + wx;
-      const bool full = (oh < Ho) && (ow < Wo);
+      full2[half] = (oh < Ho) && (ow < Wo);
       const int hh0 = h0 + 2 * wy, ww0 = w0 + 2 * wx;
-      const bool inr[2] = {hh0 < H, hh0 + 1 < H}, inc[2] = {ww0 < W, ww0 + 1 < W};
       const float* yb = y + (((long)b * H + hh0) * W + ww0) * 64 + c4;
-      const float* gb = gout + (((long)b * Hq + oh + out_pad) * Wq + ow + out_pad) * 64 + c4;
+      gv[half] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (full2[half]) gv[half] = dktb_ld4(gout + (((long)b * Hq + oh + out_pad) * Wq + ow + out_pad) * 64 + c4);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        inb[half][k] = (hh0 + (k >> 1) < H) && (ww0 + (k & 1) < W);
+        yv[half][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (inb[half][k]) yv[half][k] = dktb_ld4(yb + ((long)(k >> 1) * W + (k & 1)) * 64);
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < 3; ++it)
+      if (xdst[it] >= 0) s_in[xdst[it]] = xv[it];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int wi = tid / 16 + 16 * half;
+      const int wy = wi / (CM_TW / 2), wx = wi % (CM_TW / 2);
+      const bool full = full2[half];
       float* sg = s_g + ((2 * wy) * CM_TW + 2 * wx) * CM_GLD + c4;
 #pragma unroll
       for (int jp = 0; jp < 2; ++jp) {
@@ -99,13 +124,11 @@ __global__ void __launch_bounds__(256, 2) conv1_bwd_mma_kernel(
         const float2 mm = *reinterpret_cast<const float2*>(&s_k[0][c]), sc = *reinterpret_cast<const float2*>(&s_k[1][c]);
         const float2 bb = *reinterpret_cast<const float2*>(&s_k[2][c]), aa = *reinterpret_cast<const float2*>(&s_k[3][c]);
         const float2 bc = *reinterpret_cast<const float2*>(&s_k[4][c]);
-        float2 gg = make_float2(0.f, 0.f);
-        if (full) gg = *reinterpret_cast<const float2*>(gb + 2 * jp);
+        const float2 gg = jp ? make_float2(gv[half].z, gv[half].w) : make_float2(gv[half].x, gv[half].y);
         float2 d[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          float2 v = make_float2(0.f, 0.f);
-          if (inr[k >> 1] && inc[k & 1]) v = *reinterpret_cast<const float2*>(yb + ((long)(k >> 1) * W + (k & 1)) * 64 + 2 * jp);
+          const float2 v = jp ? make_float2(yv[half][k].z, yv[half][k].w) : make_float2(yv[half][k].x, yv[half][k].y);
           d[k] = make_float2(v.x - mm.x, v.y - mm.y);
         }
         float bx = fmaxf(fmaf(d[0].x, sc.x, bb.x), 0.f), by = fmaxf(fmaf(d[0].y, sc.y, bb.y), 0.f);
@@ -121,7 +144,7 @@ __global__ void __launch_bounds__(256, 2) conv1_bwd_mma_kernel(
         for (int k = 0; k < 4; ++k) {
           float2 r = make_float2(fmaf(d[k].x, bc.x, aa.x + (k == ax ? hx : 0.f)),
                                  fmaf(d[k].y, bc.y, aa.y + (k == ay ? hy : 0.f)));
-          if (!(inr[k >> 1] && inc[k & 1])) r = make_float2(0.f, 0.f);
+          if (!inb[half][k]) r = make_float2(0.f, 0.f);
           *reinterpret_cast<float2*>(sg + ((k >> 1) * CM_TW + (k & 1)) * CM_GLD + 2 * jp) = r;
         }
       }

@@ -893,6 +893,8 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
 enum { kC1_Y = 0, kC1_STATS = 1, kC1_APPLY = 2 };
 constexpr int kC1PatchW = 88;                  // patch row pitch (floats): W + 2 <= 88
 constexpr int kC1OutLd = 68;                   // epilogue staging pitch: float4 rows, conflict-free for 16 B accesses
+constexpr int kC1RG = 2;                       // 4-row groups per CTA (amortises patch load / TMEM / barrier set-up)
+constexpr int kC1PR = 4 * kC1RG + 2;           // patch rows per input channel
 
 // im2col slots SET*16 .. SET*16+15 of one output pixel (k = ci*9 + r*3 + s; slots 27..31 are zero): every patch offset is
 // a compile-time constant relative to `base` = &patch[py][w0 + px]
@@ -902,7 +904,7 @@ __device__ __forceinline__ void c1_stage_row(const float* __restrict__ base, uin
   for (int j = 0; j < 16; ++j) {
     const int k = SET * 16 + j;
     float v = 0.f;
-    if (k < 27) v = base[((k / 9) * 6 + (k % 9) / 3) * kC1PatchW + (k % 3)];
+    if (k < 27) v = base[((k / 9) * kC1PR + (k % 9) / 3) * kC1PatchW + (k % 3)];
     split_tf32(v, hi[j], lo[j]);
   }
 }
@@ -920,11 +922,13 @@ conv1_tc_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (*reinterpret_cast<volatile int*>(err) != 0) return;
   unsigned char* s_wt = smem;                                        // W1 hi 8 KB | W1 lo 8 KB
-  float* s_patch = reinterpret_cast<float*>(smem + 16384);           // [3][6][kC1PatchW]
-  float* s_out = s_patch + 3 * 6 * kC1PatchW;                        // [128][kC1OutLd]
+  float* s_patch = reinterpret_cast<float*>(smem + 16384);           // [3][kC1PR][kC1PatchW]
+  float* s_out = s_patch + 3 * kC1PR * kC1PatchW;                    // [128][kC1OutLd]
   __shared__ float s_stat[2][2][64];
-  const int b = blockIdx.y, h0 = blockIdx.x * 4;
-  const int TX = (W + 31) / 32;
+  const int b = blockIdx.y, hbase = blockIdx.x * 4 * kC1RG;
+  const int TX = (W + 31) / 32, RGtot = (H + 3) / 4;
+  const int ngroups = min(kC1RG, RGtot - (int)blockIdx.x * kC1RG);
+  const int ntile = ngroups * TX;                                    // tiles of this CTA: (row group, 32-column tile)
 
   if (tid == 0) {
     tc::mbar_init(&bar_w, 1);
@@ -934,9 +938,9 @@ conv1_tc_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc<128>(&s_tmem);
-  // input patch: rows h0-1 .. h0+4, columns -1 .. W, zero outside the image; one warp per (channel, row)
-  for (int rowi = warp; rowi < 18; rowi += kTsThreads / 32) {
-    const int ci = rowi / 6, hh = h0 + rowi % 6 - 1;
+  // input patch: rows hbase-1 .. hbase+4*kC1RG, columns -1 .. W, zero outside the image; one warp per (channel, row)
+  for (int rowi = warp; rowi < 3 * kC1PR; rowi += kTsThreads / 32) {
+    const int ci = rowi / kC1PR, hh = hbase + rowi % kC1PR - 1;
     const bool rok = hh >= 0 && hh < H;
     const float* src = x + (((long)b * 3 + ci) * H + (rok ? hh : 0)) * W - 1;
     for (int c = lane; c < kC1PatchW; c += 32) s_patch[rowi * kC1PatchW + c] = (rok && c >= 1 && c <= W) ? src[c] : 0.f;
@@ -956,8 +960,8 @@ conv1_tc_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
   } else if (warp == 1) {
     const uint32_t idesc = tc::umma_idesc(2, 128, 64, 0, 0);
     bool ok = tc::mbar_wait(&bar_w, 0);
-    for (int tx = 0; tx < TX && ok; ++tx) {
-      ok = tc::mbar_wait(&bar_afull, tx & 1);
+    for (int ti = 0; ti < ntile && ok; ++ti) {
+      ok = tc::mbar_wait(&bar_afull, ti & 1);
       if (!ok) break;
       tc::tcgen05_fence_after();
       const uint32_t wbase = tc::smem_u32(s_wt);
@@ -990,19 +994,20 @@ conv1_tc_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
     const int st_r0 = ct >> 4, st_c4 = (ct & 15) * 4;
     const int sw = ct >> 7, sh = (ct >> 6) & 1, sc = ct & 63;
     bool ok = true;
-    for (int tx = 0; tx < TX && ok; ++tx) {
-      const int w0 = tx * 32;
+    for (int ti = 0; ti < ntile && ok; ++ti) {
+      const int rg = ti / TX, tx = ti - rg * TX;
+      const int w0 = tx * 32, h0 = hbase + 4 * rg;
       // ---- stage the im2col row (16 of the 32 k-slots per thread)
       uint32_t hi[16], lo[16];
-      if (set == 0) c1_stage_row<0>(prow + w0, hi, lo);
-      else c1_stage_row<1>(prow + w0, hi, lo);
+      if (set == 0) c1_stage_row<0>(prow + 4 * rg * kC1PatchW + w0, hi, lo);
+      else c1_stage_row<1>(prow + 4 * rg * kC1PatchW + w0, hi, lo);
       tc::tmem_st16(a_tmem + lane_base + set * 16, hi);
       tc::tmem_st16(a_tmem + lane_base + 32 + set * 16, lo);
       tc::tmem_st_wait();
       tc::tcgen05_fence_before();
       tc::mbar_arrive(&bar_afull);
       // ---- accumulator (+ bias) -> smem tile; pixels outside the image are stored as zeros
-      ok = tc::mbar_wait(&bar_acc, tx & 1);
+      ok = tc::mbar_wait(&bar_acc, ti & 1);
       if (!ok) break;
       tc::tcgen05_fence_after();
       const bool valid = (h0 + py < H) && (w0 + px < W);
@@ -1074,7 +1079,7 @@ conv1_tc_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (mode != kC1_APPLY && partials != nullptr && ct < 128) {
-        const long blk = ((long)b * gridDim.x + blockIdx.x) * TX + tx;
+        const long blk = ((long)b * RGtot + (blockIdx.x * kC1RG + rg)) * TX + tx;
         const int w2 = ct >> 6;                               // 0: sum, 1: sum of squares
         partials[(blk * 2 + w2) * 64 + sc] = s_stat[w2][0][sc] + s_stat[w2][1][sc];
       }
@@ -1219,9 +1224,9 @@ DKTB_EXPORT int dktb_conv1_tc(const float* x, const float* wb1, const float* bia
   DKTB_CHECK_ARG(mode != kC1_APPLY || (mean && invstd && gamma && beta && act));
   CUtensorMap map_w;
   if (tc_make_tmap_2d(&map_w, wb1, 32, 128, 32, 64) != 0) return DKTB_BAD_ARG - 1;
-  const int smem = 16384 + 3 * 6 * kC1PatchW * 4 + kRows * kC1OutLd * 4 + 1024;
+  const int smem = 16384 + 3 * kC1PR * kC1PatchW * 4 + kRows * kC1OutLd * 4 + 1024;
   cudaFuncSetAttribute(conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  dim3 grid((H + 3) / 4, B);
+  dim3 grid(((H + 3) / 4 + kC1RG - 1) / kC1RG, B);
   conv1_tc_kernel<<<grid, kTsThreads, smem, stream>>>(x, map_w, bias, y, partials, mean, invstd, gamma, beta, act, ipe, H,
                                                        W, mode, err);
   return dktb_launch_status();
