@@ -380,6 +380,17 @@ class GPHead:
                       E, C, st)
         return w["loss"]
 
+    def hyper_grads(self, HP, GH, E, N):
+        """After fit(want_grad=True): only the GP hyper-parameter gradients (outputscale, constant, kernel parameter) --
+        the features are constants (test-time adaptation, DKT.correct with N > 0)."""
+        lib, st, w = self.lib, _stream(self.dev), self.w
+        if self.family is not None:
+            lib.kernel_bwd(self.family, None if self.centred else w["gram"], w["d2"] if self.centred else None,
+                           HP.raw_param, w["dk"], w["dg"], w["dparam"], w["kscratch"], E, self.C, N, st)
+            GH.raw_param.copy_(w["dparam"])
+        GH.raw_outputscale.copy_(w["hyper"][:, 0])
+        GH.constant.copy_(w["hyper"][:, 1])
+
     def backward(self, feats, zh, HP, GH, E, N):
         """Gradient w.r.t. the backbone features [E*N, D]; fills GH.{bn_w,bn_b,raw_outputscale,constant,raw_param}."""
         lib, st, w = self.lib, _stream(self.dev), self.w

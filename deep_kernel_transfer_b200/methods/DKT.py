@@ -289,8 +289,9 @@ class DKT(MetaTemplate):
                     epoch, i, n_items, outputscale, lenghtscale, noise, loss, acc_s, acc_q))
             step_i += 1
 
-    def _episode_logits(self, x):
-        """x [C, S+Q, 3, H, W] (any device) -> (mean [C, M] device tensor, pred [M] int32 device tensor)."""
+    def _episode_logits(self, x, adapt_steps=0):
+        """x [C, S+Q, 3, H, W] (any device) -> (mean [C, M] device tensor, pred [M] int32 device tensor).
+        adapt_steps > 0: that many Adam(lr 1e-3) steps on the GP hyper-parameters first (DKT.py:241-256)."""
         self._ensure_packed()
         dev = self._device()
         C, SQ = x.shape[0], x.shape[1]
@@ -307,6 +308,23 @@ class DKT(MetaTemplate):
         zh_q = zh_all.index_select(0, idx[:, S:].reshape(-1)).unsqueeze(0).contiguous()       # [1, C*Q, D]
         N, M = C * S, C * Q
         fit_head = self._test_head(eng, N)
+        self._adapt_loss = 0.0
+        if adapt_steps > 0:
+            # test-time adaptation of the GP hyper-parameters on the (eval-mode, constant) support features; a fresh
+            # Adam over the GP slice of the flat buffer, and -- as in the reference -- the updated values stay in the model
+            g0, g1 = self._gp_range
+            st = _stream(dev)
+            m_, v_ = torch.zeros(g1 - g0, device=dev), torch.zeros(g1 - g0, device=dev)
+            tg = make_targets(C, S, dev)
+            total = torch.zeros((), device=dev)
+            for it in range(adapt_steps):
+                loss = fit_head.fit(zh_s, tg, self._HP, 1, N, want_grad=True, grad_scale=1.0)
+                fit_head.hyper_grads(self._HP, self._GH, 1, N)
+                total += loss[0]
+                self.lib.adam_step(self._pack.flat[g0:g1], self._pack.grad[g0:g1], m_, v_, g1 - g0, 1e-3, 0.9, 0.999, 1e-8,
+                                   it + 1, 1.0, st)
+            check_info(fit_head.w["info"])
+            self._adapt_loss = float(total) / float(adapt_steps + 1e-10)
         fit_head.fit(zh_s, make_targets(C, S, dev), self._HP, 1, N, want_grad=False)
         mean = torch.empty(1, C, M, device=dev)
         pred = torch.empty(1, M, device=dev, dtype=torch.int32)
@@ -324,15 +342,15 @@ class DKT(MetaTemplate):
         return h
 
     def correct(self, x, N=0, laplace=False):
-        if laplace or N != 0:
-            raise NotImplementedError("Laplace / test-time hyper-parameter adaptation are not on the CUDA path yet")
+        if laplace:      # the reference hands this branch to scikit-learn's GaussianProcessClassifier on the CPU (DKT.py:207-224)
+            raise NotImplementedError("the Laplace branch (scikit-learn on CPU features) is outside the CUDA path")
         C = x.shape[0]
         self.n_query = x.size(1) - self.n_support
-        _, pred = self._episode_logits(x)
+        _, pred = self._episode_logits(x, adapt_steps=int(N))
         check_info(self._last_info)
         y_query = np.repeat(range(C), self.n_query)
         top1_correct = np.sum(pred.cpu().numpy() == y_query)
-        return float(top1_correct), len(y_query), 0.0
+        return float(top1_correct), len(y_query), self._adapt_loss
 
     def test_loop(self, test_loader, record=None, return_std=False):
         acc_all = []

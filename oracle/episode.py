@@ -115,13 +115,34 @@ class OracleDKT:
             mean = ogp.predict(self.kernel, z_tr, targets, z_q, self.gp)     # [C, M]
         return mean.t().contiguous()                                          # [C*Q, C] (DKT.py:333-335)
 
-    def correct(self, x):
+    def correct(self, x, N=0):
+        """DKT.correct (methods/DKT.py:199-272, laplace=False).  N > 0: N Adam(lr 1e-3) steps on the GP hyper-parameters
+        with the (eval-mode, detached) support features as training data (DKT.py:241-256); the updated hyper-parameters
+        stay in the model, as in the reference.  Returns (top1_correct, count, avg_loss)."""
         c = x.shape[0]
         n_query = x.shape[1] - self.n_support
+        avg_loss = 0.0
+        if N > 0:
+            x_s = x[:, :self.n_support].reshape(c * self.n_support, *x.shape[2:])
+            targets = make_targets(c, self.n_support, x.dtype)
+            with torch.no_grad():
+                z_tr = features(self.arch, self.bb, x_s, self.kernel, training=False)
+            names = ogp.trainable_gp_names(self.kernel)
+            for k in names:
+                self.gp[k] = self.gp[k].detach().clone().requires_grad_(True)
+            opt = torch.optim.Adam([self.gp[k] for k in names], lr=1e-3)
+            for _ in range(N):
+                opt.zero_grad()
+                loss = ogp.mll_loss(self.kernel, z_tr, targets, self.gp)
+                loss.backward()
+                opt.step()
+                avg_loss += float(loss)
+            for k in names:
+                self.gp[k] = self.gp[k].detach()
         logits = self.get_logits(x)
         y_pred = torch.sigmoid(logits.t()).numpy().argmax(axis=0)
         y_query = np.repeat(range(c), n_query)
-        return float(np.sum(y_pred == y_query)), len(y_query), 0.0
+        return float(np.sum(y_pred == y_query)), len(y_query), avg_loss / float(N + 1e-10)
 
 
 def synthetic_episode(episode_id, n_way=5, n_support=5, n_query=16, image_size=84, dtype=torch.float32):

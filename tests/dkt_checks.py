@@ -180,6 +180,17 @@ def check_correct(model, oracle, dev, image_size=32, n_way=2, n_support=1, n_que
         got_c = model.correct(x)
         assert got_c[:2] == ref_c[:2], (got_c, ref_c)
         assert np.array_equal(got.cpu().numpy().argmax(1), ref_logits.numpy().argmax(1))
+    # test-time adaptation (DKT.correct with N > 0): 3 Adam steps on the GP hyper-parameters, which persist afterwards
+    x = oep.synthetic_episode(950, n_way, n_support, n_query, image_size)
+    ref_c = oracle.correct(x, N=3)
+    got_c = model.correct(x, N=3)
+    assert got_c[:2] == ref_c[:2], (got_c, ref_c)
+    assert abs(got_c[2] - ref_c[2]) <= 2e-4 * max(1.0, abs(ref_c[2])), (got_c, ref_c)
+    for nm in ("raw_outputscale", "constant"):
+        mine = torch.stack([(m.covar_module.raw_outputscale if nm == "raw_outputscale" else m.mean_module.constant).detach().view(())
+                            for m in model.model.models]).cpu()
+        assert float((mine - oracle.gp[nm].detach().view(-1)).abs().max()) <= 2e-5, nm      # 3 steps of +-1e-3 each
+    assert rel_err(model.get_logits(x), oracle.get_logits(x)) <= 10 * tol
 
 
 def check_regression(dev, lib=None, image=36, n=7, n_support=4, tol=2e-4, kernel="rbf"):
