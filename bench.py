@@ -338,7 +338,7 @@ def dominant_kernel_roofline(model, lib, dev, E):
     achieved = flops / (ms / 1e3) / 1e12
     if use_tc:
         peak = peaks.get("bf16_tflops_sustained", 1400.0) / 2.0
-        which = "measured bf16 sustained / 2 (= dense TF32); 3xTF32 error-compensated split issues 3 MMAs per product"
+        which = "measured bf16 sustained / 2 (= dense TF32); 3xTF32 error-compensated split: three tf32 products per fp32 product"
     else:
         peak = 75.0
         which = "nominal fp32 FFMA peak (148 SMs x 128 FMA x ~1.97 GHz); no measured fp32 figure in MEASURED_PEAKS.json"
@@ -351,8 +351,10 @@ def dominant_kernel_roofline(model, lib, dev, E):
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms, "peak_source": which,
             "algorithmic_flops_per_launch": flops,
-            "note": "N = 64 output channels bound tcgen05.mma at ~50-65 cycles per (128xNx8) instruction "
-                    "(profiles/r01_umma_microbench.log): 3xTF32 on this layer tops out near 0.33 of dense TF32"}
+            "note": "per 8 input channels: a_hi x [w_hi|w_lo] (N=128) + a_lo x w_hi (N=64); the A-from-TMEM MMA forms issue at "
+                            "~80 / ~60 cycles (profiles/r01_umma_microbench.log), which caps this schedule near 0.29 of dense "
+                            "TF32 -- with staging and weight streaming switched off the kernel still needs 2.09 ms "
+                            "(profiles/r01_tc3_experiment.txt)"}
 
 
 if __name__ == "__main__":
