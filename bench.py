@@ -145,7 +145,11 @@ def main():
     ap.add_argument("--episodes-per-gpu", type=int, default=32)
     ap.add_argument("--no-monitor", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="train", choices=["train", "feeder"],
+                    help="train = the BASELINE metric (default); feeder = the GPU episode feeder alone (SURVEY 8f-1)")
     args = ap.parse_args()
+    if args.workload == "feeder":
+        return run_feeder(args)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -303,6 +307,139 @@ def main():
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def feeder_cpu_baseline(images, params, factors, size):
+    """The reference's own transform chain (PIL + torchvision, data/datamgr.py:37-46) on one host core over a bounded
+    sample of the same images and augmentation parameters; falls back to the numpy oracle port if PIL is missing."""
+    import numpy as np
+    import torch
+    t0 = time.perf_counter()
+    try:
+        from PIL import Image, ImageEnhance
+        import torchvision.transforms.functional as TF
+        from torchvision.transforms import InterpolationMode
+        kind = "reference"
+        for img, p, f in zip(images, params, factors):
+            o = TF.resized_crop(Image.fromarray(img), int(p[1]), int(p[2]), int(p[3]), int(p[4]), [size, size],
+                                InterpolationMode.BILINEAR)
+            for enh, a in zip((ImageEnhance.Brightness, ImageEnhance.Contrast, ImageEnhance.Color), f):
+                o = enh(o).enhance(float(a)).convert("RGB")
+            if p[5]:
+                o = TF.hflip(o)
+            TF.normalize(TF.to_tensor(o), [0.485, 0.456, 0.406], [0.229, 0.224, 0.225])
+    except ImportError:
+        from oracle import transforms as ot
+        kind = "port"
+        for img, p, f in zip(images, params, factors):
+            ot.transform_aug(img, (int(p[1]), int(p[2]), int(p[3]), int(p[4])), f, int(p[5]), size)
+    dt = time.perf_counter() - t0
+    return kind, dt
+
+
+def run_feeder(args):
+    """The GPU episode feeder alone: E packed 5-way (5+16) episodes per step, augmentation on, built from a
+    device-resident uint8 store of CUB-sized images.  value = kernel only (parameters resident); e2e = through
+    EpisodeFeeder.device_packs (host sampling of the episode composition and augmentation parameters, their H2D copy,
+    the kernel, and a D2H read of one value per step)."""
+    import numpy as np
+    import torch
+    from deep_kernel_transfer_b200 import _lib
+    from deep_kernel_transfer_b200.episode_feed import EpisodeStore, EpisodeFeeder
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    E, K, W = args.episodes_per_gpu, args.steps, max(3, args.warmup)
+    rs = np.random.RandomState(0)
+    shapes = [(375, 500), (333, 500), (500, 375), (400, 500), (281, 500), (500, 500), (357, 500), (500, 332)]
+    n_classes, per_class = 100, 30
+    hw = [shapes[int(rs.randint(len(shapes)))] for _ in range(n_classes * per_class)]
+    labels = np.repeat(np.arange(n_classes), per_class)
+    store = EpisodeStore.from_device_bytes(hw, labels, dev, seed=0)
+    feed = EpisodeFeeder(store, IMAGE, N_WAY, N_SUPPORT, N_QUERY, n_episode=E * (K + W), aug=True, seed=0, lib=lib)
+    n_img = E * N_WAY * (N_SUPPORT + N_QUERY)
+    out = torch.empty(n_img, 3, IMAGE, IMAGE, device=dev)
+    draws = [feed.draw(E) for _ in range(4)]
+    for d in draws[:W]:
+        feed.transform(d, out=out)
+    feed.check()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.3)
+    # kernel-only leg: CUDA events around each launch (the parameter upload of transform() precedes the first event)
+    l0 = lib.launches
+    t_wall0 = time.time()
+    kernel_ms, alg_bytes = [], []
+    for k in range(K):
+        d = draws[k % len(draws)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        feed.transform(d, out=out, events=(e0, e1))
+        torch.cuda.synchronize()
+        kernel_ms.append(e0.elapsed_time(e1))
+        p = d["params"]
+        alg_bytes.append(float((p[:, 3].astype(np.int64) * p[:, 4] * 3).sum() + n_img * 3 * IMAGE * IMAGE * 4))
+    launches = lib.launches - l0
+    ms = float(sum(kernel_ms))
+    # end-to-end leg through the public iterator
+    feed.n_episode = E * K
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    h2d = 0
+    for x in feed.device_packs(E):
+        float(x[0, 0, 0, 0, 0, 0])
+        h2d += feed.last_params[0].numel() * 4 + feed.last_params[1].numel() * 4
+    e1.record()
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    ms_e2e = e0.elapsed_time(e1)
+    clocks = sampler.stop(t_wall0, t_wall1)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("hbm_gbs", 6500.0)
+    ach = sum(alg_bytes) / (ms / 1e3) / 1e9
+    line = {"metric": "episodes/sec (episode feeder, aug)", "value": E * K / (ms / 1e3), "unit": "episodes/s",
+            "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "episode feeder: 5-way 5-shot + 16 queries, 84x84, RandomSizedCrop + ImageJitter + flip + "
+                                   "normalise from a resident uint8 store of %d CUB-sized images (%.2f GB)"
+                                   % (len(store), store.nbytes / 1e9), "episodes_per_step": E, "images_per_step": n_img,
+                       "l2": "each step reads %.0f MB of crops and writes %.0f MB: beyond the 126 MB L2"
+                             % ((alg_bytes[0] - n_img * 3 * IMAGE * IMAGE * 4) / 1e6, n_img * 3 * IMAGE * IMAGE * 4 / 1e6)},
+            "gpu_launches": launches,
+            "e2e": {"value": E * K / (ms_e2e / 1e3), "unit": "episodes/s", "h2d_bytes_per_step": h2d // K,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K,
+                    "note": "host draws class / image ids and augmentation parameters (44 B per image), uploads them, "
+                            "one kernel assembles the packed fp32 episodes in HBM"},
+            "clocks": clocks,
+            "roofline": {"kernel": "episode_transform_kernel", "bound": "hbm", "achieved": ach, "peak": peak,
+                         "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "algorithmic_bytes_per_launch": sum(alg_bytes) / K, "ms_per_launch": ms / K,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6500 GB/s"}}
+    if not args.no_cpu_baseline:
+        n_s = 2 * N_WAY * (N_SUPPORT + N_QUERY)
+        d = draws[0]
+        desc = store.desc_host
+        host_bytes = store.data.cpu().numpy()
+        imgs = []
+        for p in d["params"][:n_s]:
+            o, h, w = desc[int(p[0])]
+            imgs.append(host_bytes[o:o + h * w * 3].reshape(h, w, 3))
+        kind, dt = feeder_cpu_baseline(imgs, d["params"][:n_s], d["factors"][:n_s], IMAGE)
+        line["cpu_baseline"] = {"value": 2.0 / dt, "unit": "episodes/s", "cores": 1, "kind": kind,
+                                "sample": "2 episodes (210 images) of the same store and augmentation parameters through "
+                                          "PIL + torchvision on one host core (the reference spreads this over 12 "
+                                          "DataLoader workers, data/datamgr.py:81)"}
+    print(json.dumps(line))
 
 
 def dominant_kernel_roofline(model, lib, dev, E):

@@ -80,6 +80,8 @@ SIGNATURES = {
     "dktb_add_inplace": ("ppls", ctypes.c_int),
     "dktb_adam_step": ("pppplffffifs", ctypes.c_int),
     "dktb_scale": ("plfs", ctypes.c_int),
+    "dktb_episode_transform_smem": ("iii", ctypes.c_long),
+    "dktb_episode_transform": ("pplpppiiiiiiiiffffffps", ctypes.c_int),
 }
 
 _CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_long, "f": ctypes.c_float, "s": ctypes.c_void_p}

@@ -29,6 +29,19 @@ except ImportError:
     IS_TBX_INSTALLED = False
 
 
+class _DevicePacks:
+    """Adapter giving a generator of device-resident packs the prefetcher's interface."""
+
+    def __init__(self, gen):
+        self.gen = gen
+
+    def __iter__(self):
+        return self.gen
+
+    def release(self, buf):
+        pass
+
+
 class DKT(MetaTemplate):
     def __init__(self, model_func, n_way, n_support, kernel=None, episodes_per_step=1, lib=None):
         super(DKT, self).__init__(model_func, n_way, n_support)
@@ -261,7 +274,10 @@ class DKT(MetaTemplate):
                 yield xs
 
         from ..feeder import DevicePrefetcher
-        feed = DevicePrefetcher(packs(), dev)       # H2D of pack k+1 overlaps the kernels of pack k
+        if hasattr(train_loader, "device_packs"):   # GPU episode feeder: packs are assembled on the device (episode_feed.py)
+            feed = _DevicePacks(train_loader.device_packs(E))
+        else:
+            feed = DevicePrefetcher(packs(), dev)   # H2D of pack k+1 overlaps the kernels of pack k
         step_i = 0
         for x_dev in feed:
             i = min((step_i + 1) * E, n_items) - 1

@@ -226,6 +226,25 @@ int dktb_adam_step(float* p, const float* g, float* m, float* v, long n, float l
                    float eps, int step, float grad_scale, cudaStream_t stream);
 int dktb_scale(float* x, long n, float a, cudaStream_t stream);
 
+/* ---- episode feeder: the per-image transform chain of the reference's episode loader
+ *      (data/datamgr.py:37-46 composed transforms, applied in data/dataset.py:66-70; ImageJitter =
+ *      data/additional_transforms.py:24-34), bit-identical to PIL / torchvision for the same parameters ---------- */
+/* store: HWC uint8 RGB images back to back; desc [n_images][3] long = (byte offset, height, width).
+ * params [B][8] int = (image id, crop top, crop left, crop h, crop w, flip, jitter on/off, unused);
+ * factors [B][3] float = ImageEnhance factors (Brightness, Contrast, Color), read when jitter is on.
+ * Per output image: crop box -> Pillow bilinear resize to RH x RW (two-pass 22-bit fixed point) -> the S x S window
+ * at (oy, ox) [aug: RH = RW = S, window 0,0 = RandomSizedCrop; plain: RH = RW = int(1.15 S) over the whole image,
+ * window = CenterCrop(S)] -> ImageJitter -> horizontal flip -> ToTensor -> Normalize(mean, std) -> out [B,3,S,S] fp32.
+ * kmax: upper bound of resample taps per output pixel (Pillow: 2 ceil(max(in/out, 1)) + 1); tmp_rows: rows of
+ * horizontally resampled input kept in shared memory per band; dktb_episode_transform_smem() must be <= 227 KB.
+ * err: device int, zero-initialised by the caller; 1 = more than kmax taps needed, 2 = one output row needs more than
+ * tmp_rows input rows, 3 = bad image id / crop box outside its image. */
+long dktb_episode_transform_smem(int S, int kmax, int tmp_rows);
+int dktb_episode_transform(const unsigned char* store, const long* desc, long n_images, const int* params,
+                           const float* factors, float* out, int B, int S, int RH, int RW, int oy, int ox, int kmax,
+                           int tmp_rows, float mean_r, float mean_g, float mean_b, float std_r, float std_g,
+                           float std_b, int* err, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,7 +6,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "deep_kernel_transfer_b200", "csrc")
 LIB = os.path.join(HERE, "libdktb200_emu.so")
-SOURCES = ["conv_fp32.cu", "conv1_bwd_mma.cu", "bn_pool.cu", "head.cu", "gp.cu", "gp_large.cu", "gp_kernels.cu", "gp_spectral.cu", "optim.cu", "conv_generic.cu", "resnet_ops.cu"]
+SOURCES = ["conv_fp32.cu", "conv1_bwd_mma.cu", "bn_pool.cu", "head.cu", "gp.cu", "gp_large.cu", "gp_kernels.cu", "gp_spectral.cu", "optim.cu", "conv_generic.cu", "resnet_ops.cu", "episode_feed.cu"]
 
 
 def build(force=False):

@@ -690,3 +690,82 @@ def check_conv1_bwd_fused(lib, dev, E=2, ipe=2, H=10, W=37, out_pad=1, seed=21, 
     dw2, db2 = torch.empty_like(dw), torch.empty_like(db)
     lib.conv1_wgrad(x.to(dev), gy, dw2, db2, scratch, B, H, W, 0)
     _close(dw, dw2, rtol=1e-4, atol=1e-4, what="fused vs split")
+
+
+# ---------------------------------------------------------------------------------------------- episode feeder (8f-1)
+def synth_image(seed, h, w):
+    """Smooth structure + noise over the full 0..255 range (same generator as tests/golden/make_golden_transforms.py)."""
+    r = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    img = np.empty((h, w, 3), np.float64)
+    for c in range(3):
+        img[..., c] = 127 + 90 * np.sin(xx / (7.0 + 3 * c) + seed) * np.cos(yy / (11.0 - 2 * c)) + r.randn(h, w) * 40
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def feeder_oracle(store_images, drawn, S, aug):
+    """oracle/transforms.py applied image by image to a draw() result -> [n,3,S,S] float32."""
+    from oracle import transforms as ot
+    outs = []
+    for p, f in zip(drawn["params"], drawn["factors"]):
+        img = store_images[int(p[0])]
+        if aug:
+            outs.append(ot.transform_aug(img, (int(p[1]), int(p[2]), int(p[3]), int(p[4])), f if p[6] else None,
+                                         int(p[5]), S))
+        else:
+            outs.append(ot.transform_plain(img, S))
+    return np.stack(outs)
+
+
+def check_episode_transform(lib, dev, S=12, shapes=((20, 31), (12, 12), (9, 14), (40, 26), (33, 50), (16, 11)),
+                            n_way=2, batch=3, E=2, seed=90, tmp_budget=None):
+    """Device feeder vs the PIL-pinned oracle, BIT-EXACT, aug and plain pipelines."""
+    from deep_kernel_transfer_b200.episode_feed import EpisodeStore, EpisodeFeeder
+    images, labels = [], []
+    for k, (h, w) in enumerate(shapes):
+        for j in range(batch + 1):
+            images.append(synth_image(seed + 10 * k + j, h + j, w + 2 * j))
+            labels.append(k)
+    store = EpisodeStore(images, labels, dev)
+    for aug in (True, False):
+        feed = EpisodeFeeder(store, S, n_way, batch - 1, 1, n_episode=E, aug=aug, seed=seed, lib=lib)
+        if tmp_budget is not None:
+            feed.SMEM_BUDGET = tmp_budget                       # force several bands per image
+        drawn = feed.draw(E)
+        if aug:                                                 # exercise the blend short-cuts and the clipping branch
+            drawn["factors"][0] = (1.0, 0.0, 1.4)
+            drawn["factors"][1] = (0.0, 1.0, 0.6)
+            drawn["params"][2, 6] = 0
+        got = feed.transform(drawn).cpu().numpy()
+        feed.check()
+        ref = feeder_oracle(images, drawn, S, aug)
+        bad = int((got != ref).sum())
+        assert bad == 0, "episode transform (aug=%s): %d of %d values differ, max |d| = %g" % (
+            aug, bad, ref.size, float(np.abs(got - ref).max()))
+        # labels / composition: class-major episodes, S+Q distinct members of each sampled class
+        ids, lab = drawn["ids"], drawn["labels"]
+        assert ids.shape == (E, n_way, batch)
+        for e in range(E):
+            assert len(set(lab[e, :, 0].tolist())) == n_way
+            for j in range(n_way):
+                assert len(set(ids[e, j].tolist())) == batch
+                assert all(labels[i] == lab[e, j, 0] for i in ids[e, j])
+    return store
+
+
+def check_episode_transform_errors(lib, dev):
+    """The kernel's error flag: a crop box outside its image, more taps than kmax."""
+    from deep_kernel_transfer_b200.episode_feed import EpisodeStore, EpisodeFeeder
+    from deep_kernel_transfer_b200._lib import DktbError
+    images = [synth_image(3 + i, 30, 40) for i in range(4)]
+    store = EpisodeStore(images, [0, 0, 1, 1], dev)
+    feed = EpisodeFeeder(store, 8, 2, 1, 1, n_episode=1, aug=True, seed=1, lib=lib)
+    d = feed.draw(1)
+    d["params"][1, 1:5] = (25, 0, 10, 10)                       # rows 25..34 of a 30-row image
+    feed.transform(d)
+    try:
+        feed.check()
+    except DktbError as ex:
+        assert "code 3" in str(ex)
+    else:
+        raise AssertionError("out-of-image crop box was not reported")

@@ -80,3 +80,15 @@ def test_spectral(lib):
 
 def test_resnet_ops(lib):
     kc.check_resnet_ops(lib, DEV)
+
+
+def test_episode_transform(lib):
+    kc.check_episode_transform(lib, DEV)
+
+
+def test_episode_transform_banded(lib):
+    kc.check_episode_transform(lib, DEV, S=8, shapes=((61, 23), (30, 30), (17, 45)), seed=91, tmp_budget=1)   # several bands per image
+
+
+def test_episode_transform_errors(lib):
+    kc.check_episode_transform_errors(lib, DEV)
