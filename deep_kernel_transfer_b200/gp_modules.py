@@ -113,3 +113,28 @@ class SumMarginalLogLikelihood(nn.Module):
         super().__init__()
         self.likelihood = likelihood
         self.model = model
+
+
+def adapt_reference_state(state, own):
+    """Map a ``state_dict`` written by the reference (GPyTorch parameter containers, any 1.x version) onto this
+    package's containers (SURVEY.md 8f-2; train.py:57-65 writes ``{'epoch', 'state': model.state_dict()}``,
+    test.py:117-126 / train.py:192-197 load it back).  ``own`` is the receiving module's ``state_dict()``.
+
+    Differences handled (GPyTorch is not installable here, so these follow its published module layout, unverified
+    against a real checkpoint -- DESIGN.md section 2):
+      * constraint buffers ``*.raw_<p>_constraint.lower_bound / upper_bound`` (Interval registers its bounds as buffers)
+        have no counterpart here and are dropped;
+      * ``mean_module.raw_constant`` (scalar, GPyTorch >= 1.9) is the older ``mean_module.constant`` ([1]);
+      * the same parameter has carried different singleton shapes across versions (``raw_outputscale`` [] / [1],
+        ``raw_noise`` [1] / [], ``raw_lengthscale`` [1,1] / [1]): tensors are reshaped when the element count agrees.
+    Keys this module does not know are left in place so that ``load_state_dict(strict=True)`` still reports them."""
+    out = {}
+    for k, v in state.items():
+        if k.endswith("_constraint.lower_bound") or k.endswith("_constraint.upper_bound"):
+            continue
+        if k.endswith("mean_module.raw_constant"):
+            k = k[:-len("raw_constant")] + "constant"
+        if k in own and hasattr(v, "shape") and tuple(v.shape) != tuple(own[k].shape) and v.numel() == own[k].numel():
+            v = v.reshape(own[k].shape)
+        out[k] = v
+    return out

@@ -87,6 +87,11 @@ class DKT(MetaTemplate):
         self.mll = gpm.SumMarginalLogLikelihood(self.likelihood, self.model)
         return self.model, self.likelihood, self.mll
 
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        """Accepts checkpoints written by the reference (GPyTorch containers, train.py:57-65) as well as this
+        package's own: see gp_modules.adapt_reference_state.  Loading copies INTO the flat-buffer views."""
+        return super().load_state_dict(gpm.adapt_reference_state(state_dict, self.state_dict()), strict=strict, **kw)
+
     # ------------------------------------------------------------------ flat parameter buffers
     def _device(self):
         return next(self.feature.parameters()).device

@@ -253,6 +253,6 @@ class DKT(nn.Module):
 
     def load_checkpoint(self, checkpoint):
         ckpt = torch.load(checkpoint)
-        self.model.load_state_dict(ckpt['gp'])
-        self.likelihood.load_state_dict(ckpt['likelihood'])
+        self.model.load_state_dict(gpm.adapt_reference_state(ckpt['gp'], self.model.state_dict()))
+        self.likelihood.load_state_dict(gpm.adapt_reference_state(ckpt['likelihood'], self.likelihood.state_dict()))
         self.feature_extractor.load_state_dict(ckpt['net'])
