@@ -310,14 +310,13 @@ class DKT(MetaTemplate):
                     epoch, i, n_items, outputscale, lenghtscale, noise, loss, acc_s, acc_q))
             step_i += 1
 
-    def _episode_logits(self, x, adapt_steps=0):
-        """x [C, S+Q, 3, H, W] (any device) -> (mean [C, M] device tensor, pred [M] int32 device tensor).
-        adapt_steps > 0: that many Adam(lr 1e-3) steps on the GP hyper-parameters first (DKT.py:241-256)."""
+    def _episode_embed(self, x):
+        """x [C, S+Q, 3, H, W] (any device) -> (engine, support embedding [1, C*S, D], query embedding [1, C*Q, D]):
+        eval-mode backbone (+ bn_out, + F.normalize for the cosine kernels), DKT.py:236-237 / 262-263."""
         self._ensure_packed()
         dev = self._device()
         C, SQ = x.shape[0], x.shape[1]
         S = self.n_support
-        Q = SQ - S
         x_dev = x.to(dev, non_blocking=True).float().contiguous().view(C * SQ, *x.shape[2:])
         B = C * SQ
         eng, feats = self._bb_forward(x_dev, B, False)                      # eval-mode BN is per-sample
@@ -327,6 +326,15 @@ class DKT(MetaTemplate):
         idx = torch.arange(B, device=dev).view(C, SQ)
         zh_s = zh_all.index_select(0, idx[:, :S].reshape(-1)).unsqueeze(0).contiguous()       # [1, C*S, D]
         zh_q = zh_all.index_select(0, idx[:, S:].reshape(-1)).unsqueeze(0).contiguous()       # [1, C*Q, D]
+        return eng, zh_s, zh_q
+
+    def _episode_logits(self, x, adapt_steps=0):
+        """x [C, S+Q, 3, H, W] (any device) -> (mean [C, M] device tensor, pred [M] int32 device tensor).
+        adapt_steps > 0: that many Adam(lr 1e-3) steps on the GP hyper-parameters first (DKT.py:241-256)."""
+        eng, zh_s, zh_q = self._episode_embed(x)
+        dev = zh_s.device
+        C, S = x.shape[0], self.n_support
+        Q = x.shape[1] - S
         N, M = C * S, C * Q
         fit_head = self._test_head(eng, N)
         self._adapt_loss = 0.0
@@ -363,10 +371,19 @@ class DKT(MetaTemplate):
         return h
 
     def correct(self, x, N=0, laplace=False):
-        if laplace:      # the reference hands this branch to scikit-learn's GaussianProcessClassifier on the CPU (DKT.py:207-224)
-            raise NotImplementedError("the Laplace branch (scikit-learn on CPU features) is outside the CUDA path")
         C = x.shape[0]
         self.n_query = x.size(1) - self.n_support
+        if laplace:
+            # DKT.py:207-224: the reference itself leaves the GP here -- the (CUDA) embeddings go to scikit-learn's
+            # GaussianProcessClassifier (Laplace approximation, fixed 1.0 * RBF(0.1) kernel, no optimisation) on the host
+            from sklearn.gaussian_process import GaussianProcessClassifier
+            from sklearn.gaussian_process.kernels import RBF
+            _, zh_s, zh_q = self._episode_embed(x)
+            gp = GaussianProcessClassifier(kernel=1.0 * RBF(length_scale=0.1, length_scale_bounds=(0.1, 10.0)), optimizer=None)
+            gp.fit(zh_s[0].cpu().numpy(), np.repeat(range(C), self.n_support))
+            y_pred = gp.predict(zh_q[0].cpu().numpy())
+            y_query = np.repeat(range(C), self.n_query)
+            return float(np.sum(y_pred == y_query)), len(y_query), 0.0
         _, pred = self._episode_logits(x, adapt_steps=int(N))
         check_info(self._last_info)
         y_query = np.repeat(range(C), self.n_query)

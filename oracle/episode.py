@@ -115,6 +115,23 @@ class OracleDKT:
             mean = ogp.predict(self.kernel, z_tr, targets, z_q, self.gp)     # [C, M]
         return mean.t().contiguous()                                          # [C*Q, C] (DKT.py:333-335)
 
+    def correct_laplace(self, x):
+        """DKT.correct(laplace=True) (methods/DKT.py:207-224): scikit-learn's Laplace-approximated GP classifier with
+        the fixed kernel 1.0 * RBF(0.1), no optimisation, on the eval-mode features."""
+        from sklearn.gaussian_process import GaussianProcessClassifier
+        from sklearn.gaussian_process.kernels import RBF
+        c = x.shape[0]
+        s = self.n_support
+        n_query = x.shape[1] - s
+        with torch.no_grad():
+            z_s = features(self.arch, self.bb, x[:, :s].reshape(c * s, *x.shape[2:]), self.kernel, training=False)
+            z_q = features(self.arch, self.bb, x[:, s:].reshape(c * n_query, *x.shape[2:]), self.kernel, training=False)
+        gp = GaussianProcessClassifier(kernel=1.0 * RBF(length_scale=0.1, length_scale_bounds=(0.1, 10.0)), optimizer=None)
+        gp.fit(z_s.numpy(), np.repeat(range(c), s))
+        y_pred = gp.predict(z_q.numpy())
+        y_query = np.repeat(range(c), n_query)
+        return float(np.sum(y_pred == y_query)), len(y_query), 0.0
+
     def correct(self, x, N=0):
         """DKT.correct (methods/DKT.py:199-272, laplace=False).  N > 0: N Adam(lr 1e-3) steps on the GP hyper-parameters
         with the (eval-mode, detached) support features as training data (DKT.py:241-256); the updated hyper-parameters

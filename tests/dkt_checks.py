@@ -180,6 +180,9 @@ def check_correct(model, oracle, dev, image_size=32, n_way=2, n_support=1, n_que
         got_c = model.correct(x)
         assert got_c[:2] == ref_c[:2], (got_c, ref_c)
         assert np.array_equal(got.cpu().numpy().argmax(1), ref_logits.numpy().argmax(1))
+    # Laplace branch: CUDA embeddings handed to scikit-learn, as the reference does (DKT.py:207-224)
+    x = oep.synthetic_episode(940, n_way, n_support, n_query, image_size)
+    assert model.correct(x, laplace=True) == oracle.correct_laplace(x)
     # test-time adaptation (DKT.correct with N > 0): 3 Adam steps on the GP hyper-parameters, which persist afterwards
     x = oep.synthetic_episode(950, n_way, n_support, n_query, image_size)
     ref_c = oracle.correct(x, N=3)
