@@ -265,10 +265,18 @@ def main():
     gap_ms = sorted(marks[i][1].elapsed_time(marks[i + 1][0]) for i in range(len(marks) - 1))
     h2d_ms = sorted(a.elapsed_time(b) for a, b in feed.copy_events)
     h2d_ms_med = h2d_ms[len(h2d_ms) // 2]
-    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    # ---------------- feeder-fed leg: the same steps fed by the GPU episode feeder from a resident uint8 store
+    # (host draws the episode composition + augmentation parameters, one transform kernel per step)
+    ms_feed, feed_info = float("nan"), None
+    try:
+        ms_feed, feed_info = feeder_fed_leg(model, lib, dev, E, K, rank)
+    except Exception as ex:      # the headline legs above stand on their own
+        feed_info = {"error": repr(ex)}
+    barrier()
+    t = torch.tensor([ms, ms_e2e, ms_feed], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    ms, ms_e2e, ms_feed = float(t[0]), float(t[1]), float(t[2])
     # ---------------- roofline of the dominant kernel (64->64 3x3 conv at 42x42), timed live on its stream
     roof = None
     if rank == 0:
@@ -301,12 +309,47 @@ def main():
         "clocks": clocks, "roofline": roof,
     }
     line["e2e"]["feeder_cpus"] = len(numa_cpus) if numa_cpus else None
+    if feed_info is not None and "error" not in feed_info:
+        feed_info.update({"value": E * world * K / (ms_feed / 1000.0), "unit": "episodes/s", "ms_per_step": ms_feed / K})
+    line["e2e_device_feeder"] = feed_info
     if not args.no_cpu_baseline:
         os.sched_setaffinity(0, affinity0)          # the CPU baseline may use every host core
         line["cpu_baseline"] = cpu_baseline()
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def feeder_fed_leg(model, lib, dev, E, K, rank):
+    """K meta-train steps whose episodes are assembled on the device by the episode feeder (RandomSizedCrop + jitter
+    + flip + normalise of uint8 CUB-sized images resident in HBM).  Returns (ms over the K steps, info dict)."""
+    import numpy as np
+    import torch
+    from deep_kernel_transfer_b200.episode_feed import EpisodeStore, EpisodeFeeder
+    rs = np.random.RandomState(rank)
+    shapes = [(375, 500), (333, 500), (500, 375), (400, 500), (281, 500), (500, 500), (357, 500), (500, 332)]
+    n_classes, per_class = 100, 30
+    hw = [shapes[int(rs.randint(len(shapes)))] for _ in range(n_classes * per_class)]
+    store = EpisodeStore.from_device_bytes(hw, np.repeat(np.arange(n_classes), per_class), dev, seed=rank)
+    feed = EpisodeFeeder(store, IMAGE, N_WAY, N_SUPPORT, N_QUERY, n_episode=2 * E, aug=True, seed=rank, lib=lib)
+    for x in feed.device_packs(E):                     # warm-up (allocations, kernel attribute)
+        model.train_step(x)
+    torch.cuda.synchronize()
+    feed.n_episode = K * E
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h2d, loss = 0, None
+    e0.record()
+    for x in feed.device_packs(E):
+        o = model.train_step(x)
+        h2d += feed.last_params[0].numel() * 4 + feed.last_params[1].numel() * 4
+        loss = o["loss"]
+    float(loss.mean())
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1), {"h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": 4,
+                                 "store_images": len(store), "store_gb": store.nbytes / 1e9,
+                                 "note": "train_loop fed by EpisodeFeeder.device_packs: 44 B of parameters per image "
+                                         "cross the host link instead of 84.7 KB of fp32 pixels"}
 
 
 def feeder_cpu_baseline(images, params, factors, size):
