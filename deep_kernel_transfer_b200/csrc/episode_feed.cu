@@ -20,9 +20,13 @@
 struct FeedSmem {
   int* bh;            // [S][2] horizontal (xmin, count)
   int* bv;            // [S][2] vertical
-  int* kh;            // [S][kmax]
-  int* kv;            // [S][kmax]
+  int* kh;            // [S][kstride] horizontal coefficients (kstride odd: conflict-free across output columns)
+  int* kv;            // [S][kstride]
+  int* band;          // [S] end (exclusive) of the band of output rows starting at each band start
   int* red;           // [32] block reduction + broadcast slots
+  float* lut_out;     // [3][256] ((u / 255) - mean_c) / std_c
+  unsigned char* lut_b;  // [256] Brightness blend of every byte value
+  unsigned char* lut_c;  // [256] Contrast blend of every byte value
   unsigned char* img; // [S*S*3] resized image, HWC
   unsigned char* tmp; // [tmp_rows][S][3] horizontally resampled rows of the current band
 };
@@ -90,16 +94,22 @@ episode_transform_kernel(const unsigned char* __restrict__ store, const long* __
                          int S, int RH, int RW, int oy, int ox, int kmax, int tmp_rows, float m0, float m1, float m2,
                          float s0, float s1, float s2, int* __restrict__ err) {
   DKTB_DYN_SMEM(unsigned char, smem);
+  const int kstride = kmax | 1;
   FeedSmem sm;
   sm.bh = reinterpret_cast<int*>(smem);
   sm.bv = sm.bh + 2 * S;
   sm.kh = sm.bv + 2 * S;
-  sm.kv = sm.kh + S * kmax;
-  sm.red = sm.kv + S * kmax;
-  sm.img = reinterpret_cast<unsigned char*>(sm.red + 32);
+  sm.kv = sm.kh + S * kstride;
+  sm.band = sm.kv + S * kstride;
+  sm.red = sm.band + S;
+  sm.lut_out = reinterpret_cast<float*>(sm.red + 32);
+  sm.lut_b = reinterpret_cast<unsigned char*>(sm.lut_out + 768);
+  sm.lut_c = sm.lut_b + 256;
+  sm.img = sm.lut_c + 256;
   sm.tmp = sm.img + ((S * S * 3 + 15) & ~15);
 
   const int b = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
   const int* p = params + (long)b * 8;
   const long id = p[0];
   const int top = p[1], left = p[2], ch = p[3], cw = p[4], flip = p[5], jitter = p[6];
@@ -118,63 +128,117 @@ episode_transform_kernel(const unsigned char* __restrict__ store, const long* __
     if (tid == 0) atomicMax(err, 3);
     return;
   }
-  // -- coefficients of the S output columns / rows that are kept
+  // -- coefficients of the S output columns / rows that are kept; the ToTensor / Normalize table of every byte value
   for (int t = tid; t < 2 * S; t += nthr) {
-    if (t < S) feed_coeffs(ox + t, cw, RW, kmax, sm.bh + 2 * t, sm.kh + t * kmax, sm.red);
-    else feed_coeffs(oy + (t - S), ch, RH, kmax, sm.bv + 2 * (t - S), sm.kv + (t - S) * kmax, sm.red);
+    if (t < S) feed_coeffs(ox + t, cw, RW, kmax, sm.bh + 2 * t, sm.kh + t * kstride, sm.red);
+    else feed_coeffs(oy + (t - S), ch, RH, kmax, sm.bv + 2 * (t - S), sm.kv + (t - S) * kstride, sm.red);
+  }
+  for (int t = tid; t < 768; t += nthr) {
+    const int c = t >> 8;
+    const float mc = c == 0 ? m0 : (c == 1 ? m1 : m2), sc = c == 0 ? s0 : (c == 1 ? s1 : s2);
+    sm.lut_out[t] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)(t & 255), 255.f), mc), sc);
+  }
+  float fb = 1.f, fc = 1.f, fs = 1.f;
+  if (jitter) {
+    fb = factors[b * 3];
+    fc = factors[b * 3 + 1];
+    fs = factors[b * 3 + 2];
+    for (int t = tid; t < 256; t += nthr) sm.lut_b[t] = (unsigned char)feed_blend(0, t, fb);
   }
   __syncthreads();
   if (sm.red[0]) {
     if (tid == 0) atomicMax(err, 1);
     return;
   }
+  // -- bands of output rows whose input rows fit tmp (one thread walks the S rows once)
+  if (tid == 0) {
+    int a = 0, bad = 0;
+    while (a < S) {
+      const int r0 = sm.bv[2 * a];
+      int e = a + 1;
+      while (e < S && sm.bv[2 * e] + sm.bv[2 * e + 1] - r0 <= tmp_rows) ++e;
+      if (sm.bv[2 * (e - 1)] + sm.bv[2 * (e - 1) + 1] - r0 > tmp_rows) bad = 1;
+      sm.band[a] = e;
+      a = e;
+    }
+    sm.red[1] = bad;
+  }
   __syncthreads();
+  if (sm.red[1]) {
+    if (tid == 0) atomicMax(err, 2);
+    return;
+  }
   const unsigned char* src = store + off + ((long)top * W + left) * 3;
   const long rstride = (long)W * 3;
   const int S3 = S * 3;
-  // -- bands of output rows: horizontal pass of the input rows a band needs into tmp, then its vertical pass
-  int a = 0;
-  while (a < S) {
+  const bool words = (S3 & 3) == 0;             // rows of tmp / img are whole 32-bit words
+  // -- per band: horizontal pass of the input rows it needs into tmp, then its vertical pass into img
+  for (int a = 0; a < S; a = sm.band[a]) {
+    const int e = sm.band[a];
     const int r0 = sm.bv[2 * a];
-    int e = a + 1;
-    while (e < S && sm.bv[2 * e] + sm.bv[2 * e + 1] - r0 <= tmp_rows) ++e;
     const int r1 = sm.bv[2 * (e - 1)] + sm.bv[2 * (e - 1) + 1];
-    if (r1 - r0 > tmp_rows) {
-      if (tid == 0) atomicMax(err, 2);
-      return;
-    }
-    const int items = (r1 - r0) * S3;
-    for (int i = tid; i < items; i += nthr) {
-      const int r = i / S3, xc = i - r * S3;
-      const int xx = xc / 3, c = xc - xx * 3;
-      const int xmin = sm.bh[2 * xx], n = sm.bh[2 * xx + 1];
-      const int* k = sm.kh + xx * kmax;
-      const unsigned char* q = src + (long)(r0 + r) * rstride + xmin * 3 + c;
-      int acc = 0;
-      for (int x = 0; x < n; ++x) acc += (int)__ldg(q + 3 * x) * k[x];
-      sm.tmp[i] = feed_clip8(acc);
+    // a warp per input row, a lane per output column, all three channels of the pixel in one thread
+    for (int r = warp; r < r1 - r0; r += nwarp) {
+      const unsigned char* rowp = src + (long)(r0 + r) * rstride;
+      unsigned char* trow = sm.tmp + r * S3;
+      for (int xx = lane; xx < S; xx += 32) {
+        const int n = sm.bh[2 * xx + 1];
+        const int* k = sm.kh + xx * kstride;
+        const unsigned char* q = rowp + sm.bh[2 * xx] * 3;
+        int a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll 4
+        for (int x = 0; x < n; ++x) {
+          const int kk = k[x];
+          a0 += (int)__ldg(q + 3 * x) * kk;
+          a1 += (int)__ldg(q + 3 * x + 1) * kk;
+          a2 += (int)__ldg(q + 3 * x + 2) * kk;
+        }
+        trow[xx * 3] = feed_clip8(a0);
+        trow[xx * 3 + 1] = feed_clip8(a1);
+        trow[xx * 3 + 2] = feed_clip8(a2);
+      }
     }
     __syncthreads();
-    const int vitems = (e - a) * S3;
-    for (int i = tid; i < vitems; i += nthr) {
-      const int yy = a + i / S3, xc = i % S3;
+    // a warp per output row; a lane per 32-bit word (four bytes) of the row
+    for (int yy = a + warp; yy < e; yy += nwarp) {
       const int ymin = sm.bv[2 * yy] - r0, n = sm.bv[2 * yy + 1];
-      const int* k = sm.kv + yy * kmax;
-      const unsigned char* q = sm.tmp + ymin * S3 + xc;
-      int acc = 0;
-      for (int y = 0; y < n; ++y) acc += (int)q[y * S3] * k[y];
-      sm.img[yy * S3 + xc] = feed_clip8(acc);
+      const int* k = sm.kv + yy * kstride;
+      if (words) {
+        const int W4 = S3 >> 2;
+        const unsigned* tw = reinterpret_cast<const unsigned*>(sm.tmp) + ymin * W4;
+        unsigned* iw = reinterpret_cast<unsigned*>(sm.img) + yy * W4;
+        for (int w = lane; w < W4; w += 32) {
+          int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll 4
+          for (int y = 0; y < n; ++y) {
+            const unsigned v = tw[y * W4 + w];
+            const int kk = k[y];
+            a0 += (int)(v & 255u) * kk;
+            a1 += (int)((v >> 8) & 255u) * kk;
+            a2 += (int)((v >> 16) & 255u) * kk;
+            a3 += (int)(v >> 24) * kk;
+          }
+          iw[w] = (unsigned)feed_clip8(a0) | ((unsigned)feed_clip8(a1) << 8) | ((unsigned)feed_clip8(a2) << 16) |
+                  ((unsigned)feed_clip8(a3) << 24);
+        }
+      } else {
+        const unsigned char* tb = sm.tmp + ymin * S3;
+        for (int xc = lane; xc < S3; xc += 32) {
+          int acc = 0;
+          for (int y = 0; y < n; ++y) acc += (int)tb[y * S3 + xc] * k[y];
+          sm.img[yy * S3 + xc] = feed_clip8(acc);
+        }
+      }
     }
     __syncthreads();
-    a = e;
   }
-  // -- ImageJitter: Brightness -> Contrast (needs the mean of the L image) -> Color; a thread owns whole pixels
+  // -- ImageJitter: Brightness (table) -> Contrast (needs the mean of the L image; table) -> Color; a thread owns
+  //    whole pixels
   if (jitter) {
-    const float fb = factors[b * 3], fc = factors[b * 3 + 1], fs = factors[b * 3 + 2];
     int lsum = 0;
     for (int i = tid; i < S * S; i += nthr) {
       unsigned char* px = sm.img + i * 3;
-      const int r = feed_blend(0, px[0], fb), g = feed_blend(0, px[1], fb), bl = feed_blend(0, px[2], fb);
+      const int r = sm.lut_b[px[0]], g = sm.lut_b[px[1]], bl = sm.lut_b[px[2]];
       px[0] = (unsigned char)r;
       px[1] = (unsigned char)g;
       px[2] = (unsigned char)bl;
@@ -182,19 +246,21 @@ episode_transform_kernel(const unsigned char* __restrict__ store, const long* __
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-    if ((tid & 31) == 0) sm.red[1 + (tid >> 5)] = lsum;
+    if (lane == 0) sm.red[2 + warp] = lsum;
     __syncthreads();
     if (tid == 0) {
       long tot = 0;
-      for (int w = 0; w < (nthr + 31) / 32; ++w) tot += sm.red[1 + w];
+      for (int w = 0; w < nwarp; ++w) tot += sm.red[2 + w];
       const long cnt = (long)S * S;
       sm.red[0] = (int)((2 * tot + cnt) / (2 * cnt));        // int(sum / count + 0.5), exact in integers
     }
     __syncthreads();
     const int mean = sm.red[0];
+    for (int t = tid; t < 256; t += nthr) sm.lut_c[t] = (unsigned char)feed_blend(mean, t, fc);
+    __syncthreads();
     for (int i = tid; i < S * S; i += nthr) {
       unsigned char* px = sm.img + i * 3;
-      int r = feed_blend(mean, px[0], fc), g = feed_blend(mean, px[1], fc), bl = feed_blend(mean, px[2], fc);
+      const int r = sm.lut_c[px[0]], g = sm.lut_c[px[1]], bl = sm.lut_c[px[2]];
       const int L = feed_L(r, g, bl);
       px[0] = (unsigned char)feed_blend(L, r, fs);
       px[1] = (unsigned char)feed_blend(L, g, fs);
@@ -202,37 +268,37 @@ episode_transform_kernel(const unsigned char* __restrict__ store, const long* __
     }
     __syncthreads();
   }
-  // -- flip, ToTensor, Normalize; fp32 NCHW, written once
+  // -- flip, ToTensor, Normalize (table); fp32 NCHW, written once
   float* o = out + (long)b * 3 * S * S;
   if ((S & 3) == 0) {
     const int S4 = S >> 2;
-    for (int i = tid; i < 3 * S * S4; i += nthr) {
-      const int c = i / (S * S4), rem = i - c * S * S4;
-      const int y = rem / S4, x4 = (rem - y * S4) * 4;
-      const float mc = c == 0 ? m0 : (c == 1 ? m1 : m2), sc = c == 0 ? s0 : (c == 1 ? s1 : s2);
-      float v[4];
+    for (int c = 0; c < 3; ++c) {
+      const float* lut = sm.lut_out + c * 256;
+      for (int y = warp; y < S; y += nwarp) {
+        const unsigned char* row = sm.img + y * S3 + c;
+        for (int x4 = lane; x4 < S4; x4 += 32) {
+          float v[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int x = flip ? S - 1 - (x4 + j) : x4 + j;
-        const float u = __fdiv_rn((float)sm.img[(y * S + x) * 3 + c], 255.f);
-        v[j] = __fdiv_rn(__fsub_rn(u, mc), sc);
+          for (int j = 0; j < 4; ++j) {
+            const int x = flip ? S - 1 - (4 * x4 + j) : 4 * x4 + j;
+            v[j] = lut[row[x * 3]];
+          }
+          dktb_st4(o + ((long)c * S + y) * S + 4 * x4, make_float4(v[0], v[1], v[2], v[3]));
+        }
       }
-      dktb_st4(o + ((long)c * S + y) * S + x4, make_float4(v[0], v[1], v[2], v[3]));
     }
   } else {
     for (int i = tid; i < 3 * S * S; i += nthr) {
       const int c = i / (S * S), rem = i - c * S * S;
       const int y = rem / S, xo = rem - y * S;
       const int x = flip ? S - 1 - xo : xo;
-      const float mc = c == 0 ? m0 : (c == 1 ? m1 : m2), sc = c == 0 ? s0 : (c == 1 ? s1 : s2);
-      const float u = __fdiv_rn((float)sm.img[(y * S + x) * 3 + c], 255.f);
-      o[i] = __fdiv_rn(__fsub_rn(u, mc), sc);
+      o[i] = sm.lut_out[c * 256 + sm.img[(y * S + x) * 3 + c]];
     }
   }
 }
 
 static long feed_smem_bytes(int S, int kmax, int tmp_rows) {
-  return (long)(4 * S + 2 * S * kmax + 32) * 4 + ((S * S * 3 + 15) & ~15) + (long)tmp_rows * S * 3;
+  return (long)(4 * S + 2 * S * (kmax | 1) + S + 32 + 768) * 4 + 512 + ((S * S * 3 + 15) & ~15) + (long)tmp_rows * S * 3;
 }
 
 // Shared memory the transform needs for output size S, at most kmax taps per output pixel and tmp_rows rows of

@@ -26,6 +26,7 @@ def lib():
 def test_small_vs_oracle(lib):
     kc.check_episode_transform(lib, DEV)
     kc.check_episode_transform(lib, DEV, S=8, shapes=((61, 23), (30, 30), (17, 45)), seed=91, tmp_budget=1)
+    kc.check_episode_transform(lib, DEV, S=7, shapes=((15, 22), (9, 9), (31, 12)), seed=92)
     kc.check_episode_transform_errors(lib, DEV)
 
 

@@ -90,5 +90,9 @@ def test_episode_transform_banded(lib):
     kc.check_episode_transform(lib, DEV, S=8, shapes=((61, 23), (30, 30), (17, 45)), seed=91, tmp_budget=1)   # several bands per image
 
 
+def test_episode_transform_odd_size(lib):
+    kc.check_episode_transform(lib, DEV, S=7, shapes=((15, 22), (9, 9), (31, 12)), seed=92)     # rows are not whole words
+
+
 def test_episode_transform_errors(lib):
     kc.check_episode_transform_errors(lib, DEV)
