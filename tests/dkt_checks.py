@@ -483,3 +483,107 @@ def check_resnet_same_branch(arch, dev, image_size, lib=None, B=4, ipe=4, tol=1e
     assert not bad, bad
     assert stats["relu_flips"] + stats["pool_flips"] <= max(50, stats["gates"] // 100000), stats
     return stats
+
+
+# ----------------------------------------------------------------------------- against the reference's own run
+# tests/golden/dkt_*.npz: outputs of the reference's unmodified methods/DKT.py / DKT_regression.py
+# (tests/golden/make_golden_dkt.py).  The drop-in module is driven through the SAME public calls.
+import os
+
+_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+class _Recorder:
+    def __init__(self):
+        self.scalars = {}
+
+    def add_scalar(self, name, value, iteration):
+        self.scalars.setdefault(name, []).append(float(value))
+
+    def add_histogram(self, *a, **k):
+        pass
+
+
+def _golden_episodes(count, seed, n_way=3, per_class=5, image=84):
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(count):
+        x = torch.randn(n_way, per_class, 3, image, image, generator=g)
+        out.append(x + 0.5 * torch.randn(n_way, 1, 3, 1, 1, generator=g))
+    return out
+
+
+def check_reference_golden_classification(dev, kernel, lib=None, tol=1e-4, drift_tol=5e-3):
+    """train_loop / get_logits / correct / test_loop through the reference's call sequence (train.py:49-56,
+    test.py:160-161) against what the reference's own DKT.py produced.  Step 1 of train_loop and the test path from the
+    initial weights start from identical parameters: 1e-4 relative, arg-max results exact.  Later steps sit behind Adam
+    (sign-like first updates amplify rounding-level gradients): `drift_tol`."""
+    from deep_kernel_transfer_b200 import backbone
+    from deep_kernel_transfer_b200.methods.DKT import DKT
+    gold = np.load(os.path.join(_GOLD, "dkt_cls_%s.npz" % kernel))
+    oracle = oep.OracleDKT("Conv4", kernel, n_way=3, n_support=2, seed=5)      # parameter source only
+    oracle.gp["constant"] = torch.tensor([0.05 * (c + 1) for c in range(3)])
+    oracle.gp["raw_outputscale"] = torch.tensor([0.1 * c - 0.1 for c in range(3)])
+    if kernel == "rbf":
+        oracle.gp["raw_lengthscale"] = torch.tensor([30.0 + 5.0 * c for c in range(3)])
+    if kernel == "linear":
+        oracle.gp["raw_variance"] = torch.tensor([-3.0 + 0.3 * c for c in range(3)])
+    model = DKT(backbone.Conv4, 3, 2, kernel=kernel, lib=lib)
+    load_oracle_params(model, oracle)
+    model = model.to(dev)
+    test_eps = _golden_episodes(2, seed=13, per_class=6)
+    model.eval()
+    logits = torch.stack([model.get_logits(x).detach().cpu() for x in test_eps])
+    assert rel_err(logits, torch.from_numpy(gold["logits_init"])) <= tol
+    for e, x in enumerate(test_eps):
+        model.n_query = x.size(1) - model.n_support
+        assert tuple(model.correct(x)) == tuple(gold["correct_init"][e])
+    acc_mean, acc_std = model.test_loop([(x, None) for x in test_eps], return_std=True)
+    acc = gold["correct_init"][:, 0] / gold["correct_init"][:, 1] * 100
+    assert abs(acc_mean - acc.mean()) < 1e-9 and abs(acc_std - acc.std()) < 1e-9
+    model.train()
+    model.writer = _Recorder()
+    model.train_loop(0, [(x, None) for x in _golden_episodes(3, seed=11)], None, print_freq=1)
+    loss = np.array(model.writer.scalars["loss"])
+    assert abs(loss[0] - gold["loss"][0]) <= tol * abs(gold["loss"][0]), (loss, gold["loss"])
+    assert model.writer.scalars["GP_support_accuracy"][0] == gold["acc_support"][0]
+    assert model.writer.scalars["GP_query_accuracy"][0] == gold["acc_query"][0]
+    np.testing.assert_allclose(loss, gold["loss"], rtol=drift_tol)
+    model.writer = _Recorder()
+    model.train_loop(1, [(x, None) for x in _golden_episodes(1, seed=12)], None, print_freq=1)
+    np.testing.assert_allclose(model.writer.scalars["loss"], gold["loss_second_call"], rtol=drift_tol)
+    # after four Adam steps: hyper-parameters (lr 1e-4: +-1e-4 per step at most) and the trained test path
+    for c, m in enumerate(model.model.models):
+        assert abs(float(m.covar_module.raw_outputscale) - float(gold["after_gp_raw_outputscale"][c])) <= 2.5e-4
+    model.eval()
+    model.writer = None
+    logits = torch.stack([model.get_logits(x).detach().cpu() for x in test_eps])
+    assert rel_err(logits, torch.from_numpy(gold["logits"])) <= 10 * drift_tol
+    return model
+
+
+def check_reference_golden_regression(dev, kernel, lib=None, tol=1e-4, drift_tol=5e-3):
+    """DKT_regression through the reference's calls (train_regression.py:33-41, test_regression.py:34)."""
+    from deep_kernel_transfer_b200 import backbone
+    from deep_kernel_transfer_b200.methods.DKT_regression import DKT as DKTR
+    gold = np.load(os.path.join(_GOLD, "dkt_reg_%s.npz" % kernel))
+    g = torch.Generator().manual_seed(21)
+    batch = torch.rand(3, 19, 3, 100, 100, generator=g)
+    labels = torch.rand(3, 19, generator=g) * 2 - 1
+    o = oep.OracleDKTRegression(kernel, seed=5)                                  # parameter source only
+    model = DKTR(backbone.Conv3(), kernel=kernel, lib=lib, get_batch=lambda who: (batch.clone(), labels.clone()))
+    model.feature_extractor.load_state_dict({k: v.clone() for k, v in o.bb.items()})
+    model = model.to(dev)
+    optimizer = torch.optim.Adam([{"params": model.model.parameters(), "lr": 0.001},
+                                  {"params": model.feature_extractor.parameters(), "lr": 0.001}])
+    losses = []
+    step = model.train_step
+    model.train_step = lambda a, b: (lambda v: (losses.append(float(v)), v)[1])(step(a, b))
+    model.model.train(); model.feature_extractor.train(); model.likelihood.train()
+    model.train_loop(1, optimizer)
+    assert abs(losses[0] - gold["loss"][0]) <= tol * abs(gold["loss"][0]), (losses, gold["loss"])
+    np.testing.assert_allclose(losses, gold["loss"], rtol=drift_tol)
+    np.random.seed(3)
+    mse = model.test_loop(5)
+    assert abs(float(mse) - float(gold["test_mse"])) <= 10 * drift_tol * float(gold["test_mse"]), (float(mse), float(gold["test_mse"]))
+    return model

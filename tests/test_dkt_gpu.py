@@ -102,3 +102,14 @@ def test_regression_spectral():
 
 def test_sines():
     dkt_checks.check_sines(DEV, steps=5)
+
+
+@pytest.mark.parametrize("kernel", ["bncossim", "rbf", "cossim", "linear"])
+def test_matches_reference_run_classification(kernel):
+    """Against outputs of the reference's own methods/DKT.py (tests/golden/make_golden_dkt.py)."""
+    dkt_checks.check_reference_golden_classification(DEV, kernel)
+
+
+@pytest.mark.parametrize("kernel", ["rbf", "spectral"])
+def test_matches_reference_run_regression(kernel):
+    dkt_checks.check_reference_golden_regression(DEV, kernel)

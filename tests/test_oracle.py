@@ -124,3 +124,101 @@ def test_oracle_regression_step():
         assert torch.isfinite(r["loss"])
         mse, mean, lo, hi = o.test_episode(x[:3], y[:3], x, y)
         assert mean.shape == (6,) and bool((hi > lo).all())
+
+
+# ----------------------------------------------------------------------------- control flow pinned to the reference
+# tests/golden/dkt_*.npz were produced by running the reference's own, unmodified methods/DKT.py and
+# methods/DKT_regression.py (tests/golden/make_golden_dkt.py, on oracle/gpytorch_standin because GPyTorch cannot be
+# installed offline).  They pin oracle/episode.py's restatement of train_loop / correct / test_loop / get_logits.
+def _golden_episodes(count, seed, n_way=3, per_class=5, image=84):
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(count):
+        x = torch.randn(n_way, per_class, 3, image, image, generator=g)
+        out.append(x + 0.5 * torch.randn(n_way, 1, 3, 1, 1, generator=g))
+    return out
+
+
+def _golden_gp_start(kernel, n_models):
+    out = {"constant": torch.tensor([0.05 * (c + 1) for c in range(n_models)]),
+           "raw_outputscale": torch.tensor([0.1 * c - 0.1 for c in range(n_models)])}
+    if kernel == "rbf":
+        out["raw_lengthscale"] = torch.tensor([30.0 + 5.0 * c for c in range(n_models)])
+    if kernel == "linear":
+        out["raw_variance"] = torch.tensor([-3.0 + 0.3 * c for c in range(n_models)])
+    return out
+
+
+@pytest.mark.parametrize("kernel", ["bncossim", "rbf", "cossim", "linear"])
+def test_episode_oracle_matches_reference_control_flow(kernel):
+    gold = np.load(os.path.join(GOLD, "dkt_cls_%s.npz" % kernel))
+    torch.set_num_threads(1)
+    o = oep.OracleDKT("Conv4", kernel, n_way=3, n_support=2, seed=5)
+    for k, v in _golden_gp_start(kernel, 3).items():
+        o.gp[k] = v.clone()
+    tol = dict(rtol=2e-5, atol=2e-6)
+    test_eps = _golden_episodes(2, seed=13, per_class=6)
+    np.testing.assert_allclose(np.stack([o.get_logits(x).numpy() for x in test_eps]), gold["logits_init"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_array_equal(np.array([o.correct(x) for x in test_eps], dtype=np.float64), gold["correct_init"])
+    res = [o.train_step(x) for x in _golden_episodes(3, seed=11)]
+    np.testing.assert_allclose([float(r["loss"][0]) for r in res], gold["loss"], **tol)
+    np.testing.assert_array_equal([r["acc_support"][0] for r in res], gold["acc_support"])
+    np.testing.assert_array_equal([r["acc_query"][0] for r in res], gold["acc_query"])
+    # three Adam steps later: same weights, running statistics and hyper-parameters
+    ptol = dict(rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(o.bb["trunk.0.C.bias"].detach().numpy(), gold["after_conv0_bias"], **ptol)
+    np.testing.assert_allclose(o.bb["trunk.3.C.weight"].detach().numpy().reshape(-1)[:256], gold["after_conv3_weight_head"], **ptol)
+    np.testing.assert_allclose(o.bb["trunk.0.BN.running_mean"].numpy(), gold["after_bn0_running_mean"], **ptol)
+    np.testing.assert_allclose(o.bb["trunk.3.BN.running_var"].numpy(), gold["after_bn3_running_var"], **ptol)
+    if kernel == "bncossim":
+        np.testing.assert_allclose(o.bb["trunk.bn_out.weight"].detach().numpy()[:256], gold["after_bn_out_weight_head"], **ptol)
+        np.testing.assert_allclose(o.bb["trunk.bn_out.running_mean"].numpy()[:256], gold["after_bn_out_running_mean_head"], **ptol)
+    total = sum(float(v.double().abs().sum()) for v in o.bb.values() if v.is_floating_point())
+    assert abs(total - float(gold["after_param_abs_sum"])) < 1e-5 * total
+    for k in gold.files:
+        if k.startswith("after_gp_"):
+            np.testing.assert_allclose(o.gp[k[len("after_gp_"):]].detach().numpy(), gold[k], rtol=1e-5, atol=1e-7)
+    # a new train_loop call: Adam restarts (DKT.py:114-115)
+    o.new_optimizer()
+    r = o.train_step(_golden_episodes(1, seed=12)[0])
+    np.testing.assert_allclose([float(r["loss"][0])], gold["loss_second_call"], **tol)
+    # test path: get_logits, test_loop (mean / std of per-episode accuracy), correct, correct(N=3)
+    logits = np.stack([o.get_logits(x).numpy() for x in test_eps])
+    np.testing.assert_allclose(logits, gold["logits"], rtol=1e-4, atol=1e-5)
+    corr = np.array([o.correct(x) for x in test_eps], dtype=np.float64)
+    np.testing.assert_array_equal(corr, gold["correct"])
+    acc = corr[:, 0] / corr[:, 1] * 100
+    assert abs(acc.mean() - float(gold["test_acc_mean"])) < 1e-9 and abs(acc.std() - float(gold["test_acc_std"])) < 1e-9
+    adapt = np.array(o.correct(test_eps[0], N=3), dtype=np.float64)
+    np.testing.assert_array_equal(adapt[:2], gold["correct_adapt"][:2])
+    np.testing.assert_allclose(adapt[2], gold["correct_adapt"][2], rtol=1e-5)
+    for k in gold.files:
+        if k.startswith("adapt_gp_"):
+            np.testing.assert_allclose(o.gp[k[len("adapt_gp_"):]].detach().numpy(), gold[k], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(o.get_logits(test_eps[1]).numpy(), gold["logits_after_adapt"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("kernel", ["rbf", "spectral"])
+def test_regression_oracle_matches_reference_control_flow(kernel):
+    gold = np.load(os.path.join(GOLD, "dkt_reg_%s.npz" % kernel))
+    torch.set_num_threads(1)
+    g = torch.Generator().manual_seed(21)
+    batch = torch.rand(3, 19, 3, 100, 100, generator=g)
+    labels = torch.rand(3, 19, generator=g) * 2 - 1
+    o = oep.OracleDKTRegression(kernel, seed=5)
+    losses = [float(o.train_step(x, y)["loss"]) for x, y in zip(batch, labels)]      # DKT_regression.py:48-57
+    np.testing.assert_allclose(losses, gold["loss"], rtol=2e-5)
+    ptol = dict(rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(o.bb["layer1.bias"].detach().numpy(), gold["after_layer1_bias"], **ptol)
+    np.testing.assert_allclose(o.gp["constant"].detach().numpy(), gold["after_constant"], **ptol)
+    np.testing.assert_allclose(o.gp["raw_noise"].detach().numpy(), gold["after_raw_noise"], **ptol)
+    if kernel == "rbf":
+        np.testing.assert_allclose(o.gp["raw_outputscale"].detach().numpy(), gold["after_raw_outputscale"], **ptol)
+        np.testing.assert_allclose(o.gp["raw_lengthscale"].detach().numpy(), gold["after_raw_lengthscale"], **ptol)
+    else:
+        np.testing.assert_allclose(o.gp["raw_mixture_weights"].detach().numpy(), gold["after_raw_mixture_weights"], **ptol)
+        np.testing.assert_allclose(o.gp["raw_mixture_means"].detach().numpy().reshape(4, -1)[:, :64],
+                                   gold["after_raw_mixture_means_head"], **ptol)
+    ind, n = [int(i) for i in gold["test_support_ind"]], int(gold["test_person"])
+    mse, mean, lo, hi = o.test_episode(batch[n][ind], labels[n][ind], batch[n], labels[n])   # DKT_regression.py:66-95
+    np.testing.assert_allclose(float(mse), float(gold["test_mse"]), rtol=1e-4)
