@@ -257,6 +257,7 @@ class DKT(MetaTemplate):
         hit = (head.w["mon_pred"] == labels.unsqueeze(0)).view(E, C, SQ)
         return {"acc_support": hit[:, :, :self.n_support].float().mean((1, 2)) * 100.0,
                 "acc_query": hit[:, :, self.n_support:].float().mean((1, 2)) * 100.0,
+                "hit_support": hit[:, :, :self.n_support].sum((1, 2)), "hit_query": hit[:, :, self.n_support:].sum((1, 2)),
                 "mean": head.w["mon_mean"], "pred": head.w["mon_pred"]}
 
     # ------------------------------------------------------------------ reference API
@@ -300,8 +301,11 @@ class DKT(MetaTemplate):
                 ls = [m.covar_module.base_kernel.lengthscale for m in ms]
                 lenghtscale = float(np.mean([l.mean().item() for l in ls])) if ls[0] is not None else 0.0
                 loss = out["loss"].mean().item()
-                acc_s = out["acc_support"].mean().item() if self.monitor else float("nan")
-                acc_q = out["acc_query"].mean().item() if self.monitor else float("nan")
+                # percentages from the integer hit counts in double, as the reference's numpy does (DKT.py:181, 191)
+                n_s = float(x_dev.size(0) * x_dev.size(1) * self.n_support)
+                n_q = float(x_dev.size(0) * x_dev.size(1) * self.n_query)
+                acc_s = (out["hit_support"].sum().item() / n_s) * 100.0 if self.monitor else float("nan")
+                acc_q = (out["hit_query"].sum().item() / n_q) * 100.0 if self.monitor else float("nan")
                 if self.writer is not None:
                     self.writer.add_scalar("loss", loss, self.iteration)
                     self.writer.add_scalar("GP_support_accuracy", acc_s, self.iteration)

@@ -554,7 +554,7 @@ def check_reference_golden_classification(dev, kernel, lib=None, tol=1e-4, drift
     np.testing.assert_allclose(model.writer.scalars["loss"], gold["loss_second_call"], rtol=drift_tol)
     # after four Adam steps: hyper-parameters (lr 1e-4: +-1e-4 per step at most) and the trained test path
     for c, m in enumerate(model.model.models):
-        assert abs(float(m.covar_module.raw_outputscale) - float(gold["after_gp_raw_outputscale"][c])) <= 2.5e-4
+        assert abs(float(m.covar_module.raw_outputscale.detach()) - float(gold["after_gp_raw_outputscale"][c])) <= 2.5e-4
     model.eval()
     model.writer = None
     logits = torch.stack([model.get_logits(x).detach().cpu() for x in test_eps])
