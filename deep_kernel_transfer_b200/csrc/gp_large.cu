@@ -12,6 +12,8 @@
 //   K~^-1 = X^T X tile by tile (lower tiles, mirrored through shared memory), fused with the gradient epilogue.
 // Multiplying by the inverted 64 x 64 diagonal block replaces the row-by-row triangular solves (K~ = s K + sigma^2 I
 // keeps those blocks well conditioned).  alpha, log-determinant, loss and hyper-parameter gradients follow gp_fit.
+#include <stdlib.h>
+
 #include "dktb_common.cuh"
 
 #define NOISE_FLOOR 1e-4f
@@ -45,7 +47,7 @@ struct GpFitLargeArgs {
 struct GlSmem {
   float* as;      // [64][36]
   float* bs;      // [64][36]
-  float* d;       // [64][65]  diagonal block / its Cholesky factor
+  float* d;       // [64][65]  diagonal block / its Cholesky factor (shares the storage of t)
   float* w;       // [64][68]  inverse of the factor
   float* t;       // [64][68]  a tile handed from one product to the next
   float* diag;    // [512]
@@ -55,7 +57,7 @@ struct GlSmem {
   float* red;     // [32]
   int* fail;
 };
-#define GL_SMEM_FLOATS (2 * GL_T * GL_LDK + GL_T * GL_LDD + 2 * GL_T * GL_LDT + 4 * GL_MAXN + 32 + 4)
+#define GL_SMEM_FLOATS (2 * GL_T * GL_LDK + 2 * GL_T * GL_LDT + 4 * GL_MAXN + 32 + 4)
 
 __device__ __forceinline__ float gl_block_sum(float v, float* s_red) {
   v = dktb_warp_sum(v);
@@ -90,6 +92,71 @@ __device__ __forceinline__ void gl_core(float (&acc)[4][4], const float* __restr
         acc[i][j] = v;
       }
   }
+}
+
+// The same tile product on the warp-level tensor cores (mma.sync m16n8k8, 3xTF32: operands split into a tf32 `hi` and
+// the exact remainder `lo`, products lo*hi + hi*lo + hi*hi accumulated in fp32): warp w owns rows 32 (w / 4) .. + 31 and
+// columns 16 (w % 4) .. + 15 of the tile as 2 x 2 fragments; acc[i][j] = fragment (i / 2, j / 2), register 2 (i % 2) + j % 2.
+__device__ __forceinline__ void gl_split(float v, unsigned& hi, unsigned& lo) {
+  hi = __float_as_uint(v) & 0xFFFFE000u;
+  lo = __float_as_uint(v - __uint_as_float(hi));
+}
+__device__ __forceinline__ void gl_core_mma(float (&acc)[4][4], const float* __restrict__ A, int lda,
+                                            const float* __restrict__ B, int ldb, int kc) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const float* a0 = A + ((warp >> 2) * 32 + g) * lda + t;
+  const float* b0 = B + ((warp & 3) * 16 + g) * ldb + t;
+#pragma unroll 2
+  for (int k = 0; k < kc; k += 8) {
+    unsigned ah[2][4], al[2][4], bh[2][2], bl[2][2];
+#pragma unroll
+    for (int mf = 0; mf < 2; ++mf) {
+      const float* ap = a0 + mf * 16 * lda + k;
+      gl_split(ap[0], ah[mf][0], al[mf][0]);
+      gl_split(ap[8 * lda], ah[mf][1], al[mf][1]);
+      gl_split(ap[4], ah[mf][2], al[mf][2]);
+      gl_split(ap[8 * lda + 4], ah[mf][3], al[mf][3]);
+    }
+#pragma unroll
+    for (int nf = 0; nf < 2; ++nf) {
+      const float* bp = b0 + nf * 8 * ldb + k;
+      gl_split(bp[0], bh[nf][0], bl[nf][0]);
+      gl_split(bp[4], bh[nf][1], bl[nf][1]);
+    }
+#pragma unroll
+    for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+      for (int nf = 0; nf < 2; ++nf) {
+        float d[4] = {acc[2 * mf][2 * nf], acc[2 * mf][2 * nf + 1], acc[2 * mf + 1][2 * nf], acc[2 * mf + 1][2 * nf + 1]};
+        dktb_mma_m16n8k8_tf32(d, al[mf], bh[nf]);
+        dktb_mma_m16n8k8_tf32(d, ah[mf], bl[nf]);
+        dktb_mma_m16n8k8_tf32(d, ah[mf], bh[nf]);
+        acc[2 * mf][2 * nf] = d[0];
+        acc[2 * mf][2 * nf + 1] = d[1];
+        acc[2 * mf + 1][2 * nf] = d[2];
+        acc[2 * mf + 1][2 * nf + 1] = d[3];
+      }
+  }
+}
+
+// Which tile row / column acc[i][j] of this thread holds, for the two cores.
+template <bool MMA> struct GlMap;
+template <> struct GlMap<false> {
+  __device__ static __forceinline__ int row(int i) { return (threadIdx.x >> 4) + 16 * i; }
+  __device__ static __forceinline__ int col(int j) { return (threadIdx.x & 15) + 16 * j; }
+};
+template <> struct GlMap<true> {
+  __device__ static __forceinline__ int row(int i) {
+    return ((threadIdx.x >> 7) & 1) * 32 + (i >> 1) * 16 + ((threadIdx.x & 31) >> 2) + 8 * (i & 1);
+  }
+  __device__ static __forceinline__ int col(int j) {
+    return ((threadIdx.x >> 5) & 3) * 16 + (j >> 1) * 8 + 2 * (threadIdx.x & 3) + (j & 1);
+  }
+};
+template <bool MMA>
+__device__ __forceinline__ void gl_tile(float (&acc)[4][4], const float* A, int lda, const float* B, int ldb, int kc) {
+  if (MMA) gl_core_mma(acc, A, lda, B, ldb, kc);
+  else gl_core(acc, A, lda, B, ldb, kc, threadIdx.x >> 4, threadIdx.x & 15);
 }
 
 // Operand loaders of one 64 x 32 chunk: element (q, k) of the staged chunk, q = tile row / column, k = reduction index.
@@ -130,9 +197,9 @@ struct GlCols {
 };
 
 // acc += A-operand x B-operand over k in [kbeg, kend) (kbeg a multiple of 32), staged through sm.as / sm.bs.
-template <class LA, class LB>
+template <bool MMA, class LA, class LB>
 __device__ __forceinline__ void gl_product(float (&acc)[4][4], const GlSmem& sm, const LA& la, const LB& lb, int kbeg,
-                                           int kend, int tr, int tc) {
+                                           int kend) {
   float ra[8], rb[8];
   if (kbeg < kend) {
     la.fetch(ra, kbeg);
@@ -147,8 +214,24 @@ __device__ __forceinline__ void gl_product(float (&acc)[4][4], const GlSmem& sm,
       la.fetch(ra, k0 + GL_KC);
       lb.fetch(rb, k0 + GL_KC);
     }
-    gl_core(acc, sm.as, GL_LDK, sm.bs, GL_LDK, GL_KC, tr, tc);
+    gl_tile<MMA>(acc, sm.as, GL_LDK, sm.bs, GL_LDK, GL_KC);
   }
+}
+
+// v - sum_{k < n} a[k * sa] * b[k * sb] out of shared memory: loads issued eight at a time, two independent FMA chains
+// (a plain dependent loop pays the shared-memory latency on every step: profiles/r01_gp_fit_large.summary.txt).
+__device__ __forceinline__ float gl_dot_sub(float v, const float* a, int sa, const float* b, int sb, int n) {
+  float v2 = 0.f;
+  int k = 0;
+  for (; k + 8 <= n; k += 8) {
+    float x[8], y[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { x[q] = a[(k + q) * sa]; y[q] = b[(k + q) * sb]; }
+#pragma unroll
+    for (int q = 0; q < 8; q += 2) { v = fmaf(-x[q], y[q], v); v2 = fmaf(-x[q + 1], y[q + 1], v2); }
+  }
+  for (; k < n; ++k) v = fmaf(-a[k * sa], b[k * sb], v);
+  return v + v2;
 }
 
 __device__ __forceinline__ void gl_zero(float (&acc)[4][4]) {
@@ -158,15 +241,16 @@ __device__ __forceinline__ void gl_zero(float (&acc)[4][4]) {
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 }
 
+template <bool MMA>
 __global__ void __launch_bounds__(GL_THREADS, 2) gp_fit_large_kernel(GpFitLargeArgs p) {
+  typedef GlMap<MMA> M;
   DKTB_DYN_SMEM(float, smem);
   GlSmem sm;
   sm.as = smem;
   sm.bs = sm.as + GL_T * GL_LDK;
-  sm.d = sm.bs + GL_T * GL_LDK;
-  sm.w = sm.d + GL_T * GL_LDD;
-  sm.w += (4 - ((sm.w - smem) & 3)) & 3;                 // 16-byte alignment of the float4-read tiles
+  sm.w = sm.bs + GL_T * GL_LDK;
   sm.t = sm.w + GL_T * GL_LDT;
+  sm.d = sm.t;                                           // the diagonal block is dead once L_jj / W are written out
   sm.diag = sm.t + GL_T * GL_LDT;
   sm.r = sm.diag + GL_MAXN;
   sm.u = sm.r + GL_MAXN;
@@ -175,7 +259,7 @@ __global__ void __launch_bounds__(GL_THREADS, 2) gp_fit_large_kernel(GpFitLargeA
   sm.fail = reinterpret_cast<int*>(sm.red + 32);
   const int N = p.N, C = p.C;
   const int c = blockIdx.x, e = blockIdx.y;
-  const int tid = threadIdx.x, tr = tid >> 4, tc = tid & 15;
+  const int tid = threadIdx.x;
   const float s = p.raw_outputscale ? dktb_softplus(p.raw_outputscale[c]) : 1.f;
   const float noise = dktb_softplus(p.raw_noise[c]) + NOISE_FLOOR;
   const float mconst = p.constant[c];
@@ -184,13 +268,21 @@ __global__ void __launch_bounds__(GL_THREADS, 2) gp_fit_large_kernel(GpFitLargeA
   float* A = p.work + ((long)e * C + c) * 2 * N * N;     // K~ -> L (lower incl. diagonal)
   float* X = A + (long)N * N;                             // L^-1 (lower; entries above the diagonal blocks unused)
   if (tid == 0) *sm.fail = 0;
-  for (int i = tid; i < N * N; i += GL_THREADS) {
-    const int r = i / N, k = i - r * N;
-    float v = s * kb[i];
-    if (r == k) v += noise + p.jitter;
-    A[i] = v;
+  for (int i0 = tid; i0 < N * N; i0 += 4 * GL_THREADS) {     // four independent loads in flight per thread
+    float v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = (i0 + q * GL_THREADS < N * N) ? kb[i0 + q * GL_THREADS] : 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = i0 + q * GL_THREADS;
+      if (i < N * N) A[i] = s * v[q];
+    }
   }
-  for (int i = tid; i < N; i += GL_THREADS) sm.r[i] = yv[i] - mconst;
+  __syncthreads();
+  for (int i = tid; i < N; i += GL_THREADS) {
+    A[(long)i * N + i] += noise + p.jitter;
+    sm.r[i] = yv[i] - mconst;
+  }
   __syncthreads();
 
   const int nT = (N + GL_T - 1) / GL_T;
@@ -202,58 +294,69 @@ __global__ void __launch_bounds__(GL_THREADS, 2) gp_fit_large_kernel(GpFitLargeA
     gl_zero(acc);
     {
       GlRows la{A, N, j0, nb, j0}, lb{A, N, j0, nb, j0};
-      gl_product(acc, sm, la, lb, 0, j0, tr, tc);
+      gl_product<MMA>(acc, sm, la, lb, 0, j0);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int r = tr + 16 * i, cc = tc + 16 * j;
+        const int r = M::row(i), cc = M::col(j);
         sm.d[r * GL_LDD + cc] = (r < nb && cc < nb) ? A[(long)(j0 + r) * N + j0 + cc] - acc[i][j] : (r == cc ? 1.f : 0.f);
       }
     __syncthreads();
-    if (tid < 32) {                                       // lane owns rows lane and lane + 32
-      const int lane = tid;
+    // right-looking Cholesky of the 64 x 64 block by the whole CTA: per column the pivot, the scaled column (one thread
+    // per row) and the rank-1 update of the trailing lower triangle (thread = row x 4-way interleaved columns)
+    {
+      float* colv = sm.as;                                // staging area is idle here
+      const int ur = tid >> 2, uq = tid & 3;
       for (int j = 0; j < nb; ++j) {
-        float v0 = 0.f, v1 = 0.f;
-        const float* dj = sm.d + j * GL_LDD;
-        if (lane >= j && lane < nb) {
-          const float* dr = sm.d + lane * GL_LDD;
-          v0 = dr[j];
-          for (int k = 0; k < j; ++k) v0 = fmaf(-dr[k], dj[k], v0);
-        }
-        if (lane + 32 >= j && lane + 32 < nb) {
-          const float* dr = sm.d + (lane + 32) * GL_LDD;
-          v1 = dr[j];
-          for (int k = 0; k < j; ++k) v1 = fmaf(-dr[k], dj[k], v1);
-        }
-        const float piv = __shfl_sync(0xffffffffu, j < 32 ? v0 : v1, j & 31);
-        if (!(piv > 0.f)) {
-          if (lane == 0) *sm.fail = j0 + j + 1;
+        const float piv = sm.d[j * GL_LDD + j];
+        if (!(piv > 0.f)) {                               // uniform: every thread reads the same pivot
+          if (tid == 0) *sm.fail = j0 + j + 1;
           break;
         }
         const float dg = sqrtf(piv);
-        if (lane == j) { sm.d[j * GL_LDD + j] = dg; sm.diag[j0 + j] = dg; }
-        else if (lane > j && lane < nb) sm.d[lane * GL_LDD + j] = v0 / dg;
-        if (lane + 32 == j) { sm.d[j * GL_LDD + j] = dg; sm.diag[j0 + j] = dg; }
-        else if (lane + 32 > j && lane + 32 < nb) sm.d[(lane + 32) * GL_LDD + j] = v1 / dg;
-        __syncwarp();
+        if (tid > j && tid < nb) colv[tid] = sm.d[tid * GL_LDD + j] / dg;
+        __syncthreads();
+        if (tid == j) { sm.d[j * GL_LDD + j] = dg; sm.diag[j0 + j] = dg; }
+        else if (tid > j && tid < nb) sm.d[tid * GL_LDD + j] = colv[tid];
+        if (ur > j && ur < nb) {
+          const float lr = colv[ur];
+          float* dr = sm.d + ur * GL_LDD;
+          for (int cc = j + 1 + uq; cc <= ur; cc += 4) dr[cc] = fmaf(-lr, colv[cc], dr[cc]);
+        }
+        __syncthreads();
       }
     }
     __syncthreads();
     if (*sm.fail) break;
-    // W = L_jj^-1: a thread per column (forward substitution); rows beyond nb form an identity block
+    // W = L_jj^-1 in two 32-wide halves: the diagonal halves by forward substitution (a thread per column), the
+    // off-diagonal block W21 = -W22 (L21 W11) as two small products by the whole CTA; rows beyond nb form an identity
     if (tid < GL_T) {
-      const int col = tid;
+      const int col = tid, lo = col & 32;
       for (int i = 0; i < GL_T; ++i) {
         float a = 0.f;
-        if (i >= col) {
-          a = (i == col) ? 1.f : 0.f;
+        if (i >= col && i < lo + 32) {
           const float* di = sm.d + i * GL_LDD;
-          for (int k = col; k < i; ++k) a = fmaf(-di[k], sm.w[k * GL_LDT + col], a);
-          a = a / di[i];
+          a = gl_dot_sub((i == col) ? 1.f : 0.f, di + col, 1, sm.w + col * GL_LDT + col, GL_LDT, i - col) / di[i];
         }
-        sm.w[i * GL_LDT + col] = a;
+        if (i < lo + 32) sm.w[i * GL_LDT + col] = a;      // rows 32.. of the first 32 columns come from the products
+      }
+    }
+    __syncthreads();
+    {
+      float* tt = sm.as;                                  // T = L21 W11, [32][33]
+      const int r = tid >> 3, c0 = tid & 7;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int cc = c0 + 8 * q;
+        tt[r * 33 + cc] = -gl_dot_sub(0.f, sm.d + (32 + r) * GL_LDD + cc, 1, sm.w + cc * GL_LDT + cc, GL_LDT, 32 - cc);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int cc = c0 + 8 * q;
+        sm.w[(32 + r) * GL_LDT + cc] = gl_dot_sub(0.f, sm.w + (32 + r) * GL_LDT + 32, 1, tt + cc, 33, r + 1);
       }
     }
     __syncthreads();
@@ -271,24 +374,24 @@ __global__ void __launch_bounds__(GL_THREADS, 2) gp_fit_large_kernel(GpFitLargeA
       gl_zero(acc);
       {
         GlRows la{A, N, i0, nr, j0}, lb{A, N, j0, nb, j0};
-        gl_product(acc, sm, la, lb, 0, j0, tr, tc);
+        gl_product<MMA>(acc, sm, la, lb, 0, j0);
       }
       __syncthreads();                                    // sm.t free (previous tile's second product done)
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int r = tr + 16 * i, cc = tc + 16 * j;
+          const int r = M::row(i), cc = M::col(j);
           sm.t[r * GL_LDT + cc] = (r < nr && cc < nb) ? A[(long)(i0 + r) * N + j0 + cc] - acc[i][j] : 0.f;
         }
       __syncthreads();
       gl_zero(acc);
-      gl_core(acc, sm.t, GL_LDT, sm.w, GL_LDT, GL_T, tr, tc);
+      gl_tile<MMA>(acc, sm.t, GL_LDT, sm.w, GL_LDT, GL_T);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int r = tr + 16 * i, cc = tc + 16 * j;
+          const int r = M::row(i), cc = M::col(j);
           if (r < nr && cc < nb) A[(long)(i0 + r) * N + j0 + cc] = acc[i][j];
         }
     }
@@ -300,21 +403,21 @@ __global__ void __launch_bounds__(GL_THREADS, 2) gp_fit_large_kernel(GpFitLargeA
       {
         GlRows la{A, N, j0, nb, j0};
         GlCols lb{X, N, k0, GL_T, j0};
-        gl_product(acc, sm, la, lb, k0, j0, tr, tc);
+        gl_product<MMA>(acc, sm, la, lb, k0, j0);
       }
       __syncthreads();
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) sm.t[(tc + 16 * j) * GL_LDT + tr + 16 * i] = acc[i][j];     // transposed: t[c][m]
+        for (int j = 0; j < 4; ++j) sm.t[M::col(j) * GL_LDT + M::row(i)] = acc[i][j];     // transposed: t[c][m]
       __syncthreads();
       gl_zero(acc);
-      gl_core(acc, sm.w, GL_LDT, sm.t, GL_LDT, GL_T, tr, tc);
+      gl_tile<MMA>(acc, sm.w, GL_LDT, sm.t, GL_LDT, GL_T);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int r = tr + 16 * i, cc = tc + 16 * j;
+          const int r = M::row(i), cc = M::col(j);
           if (r < nb) X[(long)(j0 + r) * N + k0 + cc] = -acc[i][j];
         }
     }
@@ -375,14 +478,14 @@ __global__ void __launch_bounds__(GL_THREADS, 2) gp_fit_large_kernel(GpFitLargeA
       {
         GlCols la{X, N, i0, ni, N}, lb{X, N, k0, GL_T, N};       // kbk <= ib: the k-tile is full unless it is the last
         lb.nq = min(GL_T, N - k0);
-        gl_product(acc, sm, la, lb, i0, N, tr, tc);
+        gl_product<MMA>(acc, sm, la, lb, i0, N);
       }
       __syncthreads();
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int r = tr + 16 * i, cc = tc + 16 * j;
+          const int r = M::row(i), cc = M::col(j);
           const int gi = i0 + r, gk = k0 + cc;
           float g = 0.f;
           if (gi < N && gk < N) {
@@ -436,7 +539,15 @@ DKTB_EXPORT int dktb_gp_fit_large(const float* kbase, long kbase_class_stride, c
   a.loss_terms = loss_terms; a.info = info; a.dkbase = dkbase; a.dhyper = dhyper; a.work = work;
   a.grad_scale = grad_scale; a.jitter = jitter; a.N = N; a.C = C;
   const size_t smem = (size_t)GL_SMEM_FLOATS * sizeof(float);
-  cudaFuncSetAttribute(gp_fit_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  DKTB_LAUNCH(gp_fit_large_kernel, dim3(C, E), dim3(GL_THREADS), smem, stream, a);
+  // DKTB_GP_LARGE=ffma selects the CUDA-core tile product (default: mma.sync 3xTF32 tiles).  Two CTAs per SM: a third
+  // (80 registers) was slower at every size tried (profiles/r01_gp_size_sweep.txt).
+  static const bool ffma = [] { const char* v = getenv("DKTB_GP_LARGE"); return v && v[0] == 'f'; }();
+  if (ffma) {
+    cudaFuncSetAttribute(gp_fit_large_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    DKTB_LAUNCH(gp_fit_large_kernel<false>, dim3(C, E), dim3(GL_THREADS), smem, stream, a);
+  } else {
+    cudaFuncSetAttribute(gp_fit_large_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    DKTB_LAUNCH(gp_fit_large_kernel<true>, dim3(C, E), dim3(GL_THREADS), smem, stream, a);
+  }
   return dktb_launch_status();
 }

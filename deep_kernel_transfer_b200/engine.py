@@ -18,6 +18,7 @@ import torch
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
+GP_SMEM_CROSSOVER = 105   # largest N served by the all-in-shared-memory gp_fit kernel (the tiled one wins from ~100 on)
 
 
 def _stream(dev):
@@ -363,11 +364,14 @@ class GPHead:
                 lib.gram(zh, zh, w["gram"], E, N, N, self.D, st)
                 lib.kernel_fwd(self.family, w["gram"], None, HP.raw_param, w["kb"], E, C, N, N, st)
             kb, stride = w["kb"], N * N
-        if N <= lib.gp_max_n():
+        # one CTA per system entirely in shared memory up to the BASELINE episode size (N = 105); beyond that the tiled
+        # kernel on a global workspace is faster (N = 128: 0.57 vs 0.21 ms, N = 165: 0.91 vs 0.36 ms per 160 systems,
+        # profiles/r01_gp_size_sweep.txt)
+        if N <= min(lib.gp_max_n(), GP_SMEM_CROSSOVER):
             lib.gp_fit(kb, stride, targets, 0, HP.raw_outputscale, HP.constant, HP.raw_noise, w["alpha"], None,
                        w["loss_terms"], w["info"], w["dk"] if want_grad else None, w["dhyper"] if want_grad else None,
                        grad_scale, jitter, E, C, N, st)
-        else:               # beyond shared memory: blocked factorisation on a global workspace (csrc/gp_large.cu)
+        else:               # tiled block factorisation on a global workspace (csrc/gp_large.cu)
             if N > lib.gp_large_max_n():
                 raise NotImplementedError("exact-GP systems with N = %d > %d" % (N, lib.gp_large_max_n()))
             need = lib.gp_large_work_floats(E, C, N)

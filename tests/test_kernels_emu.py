@@ -56,8 +56,8 @@ def test_gp(lib):
 
 def test_gp_large(lib):
     kc.check_gp(lib, DEV, E=1, C=2, per_class=20, D=24, M=5, seed=6, large=True)     # N = 40: one partial tile
-    kc.check_gp(lib, DEV, E=2, C=3, per_class=23, D=32, M=5, seed=7, large=True)     # N = 69: two tiles
-    kc.check_gp(lib, DEV, E=1, C=2, per_class=75, D=48, M=5, seed=8, large=True)     # N = 150: three tiles (22 rows in the last)
+    kc.check_gp(lib, DEV, E=1, C=3, per_class=23, D=32, M=5, seed=7, large=True)     # N = 69: two tiles
+    kc.check_gp(lib, DEV, E=1, C=1, per_class=133, D=48, M=5, seed=8, large=True)    # N = 133: three tiles (5 rows in the last)
 
 
 def test_adam(lib):
