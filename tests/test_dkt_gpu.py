@@ -25,6 +25,16 @@ def test_train_step_reference_shape():
     dkt_checks.check_correct(model, oracle, DEV, image_size=84, n_way=5, n_support=1, n_query=15)
 
 
+@pytest.mark.parametrize("kernel", ["bncossim", "rbf"])
+def test_train_step_20_way(kernel):
+    """20-way 5-shot, Q=2 (N = 140 > 105): the exact-GP systems go through the tiled global-workspace kernel
+    (csrc/gp_large.cu) inside train_step / monitor_step; shared Gram (bncossim) and per-class kernel matrices (rbf)."""
+    from deep_kernel_transfer_b200 import backbone
+    model, oracle, worst = dkt_checks.check_train_step(lambda: backbone.ConvNet(4, image_size=32), DEV, image_size=32,
+                                                       n_way=20, n_support=5, n_query=2, E=2, steps=1, kernel=kernel)
+    print({k: "%.1e" % v for k, v in worst.items()})
+
+
 def test_full_size_properties():
     """BASELINE config (5-way 5-shot, Q=16, N=105): size-independent properties -- finite decreasing loss,
     packed == unpacked (E episodes in one step give the mean of E single-episode gradients), determinism."""
