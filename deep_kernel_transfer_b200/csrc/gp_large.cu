@@ -492,21 +492,19 @@ __global__ void __launch_bounds__(GL_THREADS, 2) gp_fit_large_kernel(GpFitLargeA
             g = (acc[i][j] - sm.al[gi] * sm.al[gk]) * coef;
             const long idx = (long)gi * N + gk;
             if (dk) dk[idx] = s * g;
-            ds_part = fmaf(g, kb[idx], ds_part);
+            ds_part = fmaf(kbk < ib ? 2.f * g : g, kb[idx], ds_part);     // kbase is a kernel matrix: symmetric
             if (gi == gk) tr_part += g;
           }
           if (kbk < ib) sm.t[cc * GL_LDT + r] = g;
         }
-      if (kbk < ib) {
+      if (kbk < ib && dk) {
         __syncthreads();
         for (int i = tid; i < GL_T * GL_T; i += GL_THREADS) {
           const int cc = i >> 6, r = i & 63;
           const int gi = i0 + r, gk = k0 + cc;
           if (gi < N && gk < N) {
             const float g = sm.t[cc * GL_LDT + r];
-            const long idx = (long)gk * N + gi;
-            if (dk) dk[idx] = s * g;
-            ds_part = fmaf(g, kb[idx], ds_part);
+            if (dk) dk[(long)gk * N + gi] = s * g;
           }
         }
       }

@@ -175,9 +175,10 @@ int dktb_gp_fit(const float* kbase, long kbase_class_stride, const float* y, lon
                 const float* raw_outputscale, const float* constant, const float* raw_noise, float* alpha,
                 float* linv, float* loss_terms, int* info, float* dkbase, float* dhyper, float grad_scale,
                 float jitter, int E, int C, int N, cudaStream_t stream);
-/* The same contract for systems beyond shared memory (dktb_gp_max_n() < N <= dktb_gp_large_max_n() = 512: 20-way
- * training episodes, BASELINE configs[4] Gram-N sweep): blocked Cholesky on a caller-provided global workspace of
- * dktb_gp_large_work_floats(E, C, N) floats. */
+/* The same contract for any N <= dktb_gp_large_max_n() = 512 (20-way training episodes, BASELINE configs[4] Gram-N
+ * sweep; faster than dktb_gp_fit from N ~ 100 on): tiled blocked Cholesky (tensor-core tile products) on a
+ * caller-provided global workspace of dktb_gp_large_work_floats(E, C, N) floats.  kbase must be symmetric (it is a
+ * kernel matrix); the first pivot that is not positive is reported in info like dktb_gp_fit does. */
 int dktb_gp_large_max_n(void);
 long dktb_gp_large_work_floats(int E, int C, int N);
 int dktb_gp_fit_large(const float* kbase, long kbase_class_stride, const float* y, long y_episode_stride,
