@@ -66,6 +66,10 @@ SIGNATURES = {
     "dktb_conv2d_fwd": ("ppppiiiiiiiiiiis", ctypes.c_int),
     "dktb_conv2d_dgrad": ("ppppiiiiiiiiiiis", ctypes.c_int),
     "dktb_conv2d_wgrad_nsplit": ("l", ctypes.c_int),
+    "dktb_conv2d_mma_ok": ("ii", ctypes.c_int),
+    "dktb_conv2d_prep_mma": ("pppiiiis", ctypes.c_int),
+    "dktb_conv2d_fwd_mma": ("ppppiiiiiiiiiis", ctypes.c_int),
+    "dktb_conv2d_dgrad_mma": ("pppiiiiiiiiiis", ctypes.c_int),
     "dktb_conv2d_wgrad": ("ppppppiiiiiiiiiiis", ctypes.c_int),
     "dktb_nchw_to_nhwc": ("ppiiiis", ctypes.c_int),
     "dktb_spectral_fwd": ("pppppppiiiiiiis", ctypes.c_int),

@@ -7,7 +7,9 @@
 //   wgrad   : dw[co,ci,r,s]   = sum_{n,oh,ow} x[n,ih,iw,ci] * gy[n,oh,ow,co]     (split over pixels, fixed-order reduce)
 // Weights stay in the reference layout [Cout][Cin][R][S].  When relu != 0 the forward applies ReLU and the backward
 // entry points take the forward OUTPUT to mask gy (ReLU backward fused into the operand load).
-#include "dktb_common.cuh"
+#include <stdlib.h>
+
+#include "tile_mma.cuh"
 
 struct ConvGeo {
   int N, H, W, Cin, Ho, Wo, Cout, R, S, stride, pad, dil;
@@ -270,6 +272,210 @@ __global__ void __launch_bounds__(256) conv2d_bgrad_kernel(const float* __restri
   if (sl == 0 && c < Cout) db[c] = (s_red[0][threadIdx.x] + s_red[1][threadIdx.x]) + (s_red[2][threadIdx.x] + s_red[3][threadIdx.x]);
 }
 
+// ------------------------------------------------------------------------------------- tensor-core variants (ResNet)
+// The same three products as 64 x 64 x k tiles on the warp-level tensor cores (tile_mma.cuh: mma.sync m16n8k8, 3xTF32
+// split, fp32 accumulate, next k-chunk prefetched into registers), for layers whose reduction width (Cin forward,
+// Cout dgrad) is a multiple of 32 -- every ResNet layer but the stem (reference backbone.py:135-247, 330-376).
+// Operands are read k-contiguous: activations NHWC as they are, weights from two re-laid-out copies the caller refreshes
+// once per step with dktb_conv2d_prep_mma:  wf [R*S][Cout][Cin] (forward),  wd [R*S][Cin][Cout] (dgrad).
+__global__ void conv2d_prep_mma_kernel(const float* __restrict__ w, float* __restrict__ wf, float* __restrict__ wd,
+                                       int Cout, int Cin, int RS) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)Cout * Cin * RS) return;
+  const int t = (int)(i % RS);
+  const int ci = (int)((i / RS) % Cin);
+  const int co = (int)(i / ((long)RS * Cin));
+  const float v = w[i];
+  wf[((long)t * Cout + co) * Cin + ci] = v;
+  wd[((long)t * Cin + ci) * Cout + co] = v;
+}
+
+// A operand of forward (MODE 0: x at the tap's input position of each output pixel) and dgrad (MODE 1: gy at the output
+// position that used this input pixel through the tap, if any).  tbl[q] = (image base in pixels, h0, w0, valid).
+template <int MODE>
+struct CmPixels {
+  const float* src; const int4* tbl; ConvGeo g; int kc;       // kc = channels per tap on the k axis
+  __device__ __forceinline__ void fetch(float (&v)[8], int k0) const {
+    const int tap = k0 / kc, c = k0 - tap * kc + (threadIdx.x & 31);
+    const int r = tap / g.S, s = tap - r * g.S;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int4 t = tbl[(threadIdx.x >> 5) + 8 * i];
+      float val = 0.f;
+      if (MODE == 0) {
+        const int ih = t.y + r * g.dil, iw = t.z + s * g.dil;
+        if (t.w && (unsigned)ih < (unsigned)g.H && (unsigned)iw < (unsigned)g.W)
+          val = src[((long)t.x + (long)ih * g.W + iw) * g.Cin + c];
+      } else {
+        const int th = t.y - r * g.dil, tw = t.z - s * g.dil;
+        if (t.w && th >= 0 && tw >= 0 && th % g.stride == 0 && tw % g.stride == 0) {
+          const int oh = th / g.stride, ow = tw / g.stride;
+          if (oh < g.Ho && ow < g.Wo) val = src[((long)t.x + (long)oh * g.Wo + ow) * g.Cout + c];
+        }
+      }
+      v[i] = val;
+    }
+  }
+  __device__ __forceinline__ void store(float* sdst, const float (&v)[8]) const {
+    const int k = threadIdx.x & 31, q0 = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sdst[(q0 + 8 * i) * GL_LDK + k] = v[i];
+  }
+};
+// B operand: re-laid-out weights [tap][nn][kc], rows n0 .. n0 + 63 of the tap the chunk belongs to.
+struct CmWeights {
+  const float* wt; int nn, n0, kc;
+  __device__ __forceinline__ void fetch(float (&v)[8], int k0) const {
+    const int tap = k0 / kc, c = k0 - tap * kc + (threadIdx.x & 31);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int n = n0 + (threadIdx.x >> 5) + 8 * i;
+      v[i] = n < nn ? wt[((long)tap * nn + n) * kc + c] : 0.f;
+    }
+  }
+  __device__ __forceinline__ void store(float* sdst, const float (&v)[8]) const {
+    const int k = threadIdx.x & 31, q0 = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sdst[(q0 + 8 * i) * GL_LDK + k] = v[i];
+  }
+};
+
+// MODE 0: out[p][co] = bias[co] + sum_{tap,ci} x[p@tap][ci] wf[tap][co][ci]     (p over output pixels)
+// MODE 1: gx[p][ci]  =           sum_{tap,co} gy[p@tap][co] wd[tap][ci][co]     (p over input pixels)
+template <int MODE>
+__global__ void __launch_bounds__(GL_THREADS, 2) conv2d_mma_kernel(const float* __restrict__ src,
+                                                                   const float* __restrict__ wt,
+                                                                   const float* __restrict__ bias,
+                                                                   float* __restrict__ dst, ConvGeo g) {
+  __shared__ __align__(16) float s_as[GL_T * GL_LDK];
+  __shared__ __align__(16) float s_bs[GL_T * GL_LDK];
+  __shared__ int4 s_tbl[GL_T];
+  typedef GlMap<true> M;
+  const int tid = threadIdx.x;
+  const int Hp = MODE == 0 ? g.Ho : g.H, Wp = MODE == 0 ? g.Wo : g.W;      // the pixel grid this kernel tiles
+  const long npix = (long)g.N * Hp * Wp;
+  const long p0 = (long)blockIdx.x * GL_T;
+  const int nn = MODE == 0 ? g.Cout : g.Cin, kc = MODE == 0 ? g.Cin : g.Cout;
+  const int n0 = blockIdx.y * GL_T;
+  if (tid < GL_T) {
+    const long p = p0 + tid;
+    int4 t = make_int4(0, 0, 0, 0);
+    if (p < npix) {
+      const int n = (int)(p / ((long)Hp * Wp));
+      const int rem = (int)(p - (long)n * Hp * Wp);
+      const int ph = rem / Wp, pw = rem - ph * Wp;
+      if (MODE == 0) t = make_int4(n * g.H * g.W, ph * g.stride - g.pad, pw * g.stride - g.pad, 1);
+      else t = make_int4(n * g.Ho * g.Wo, ph + g.pad, pw + g.pad, 1);
+    }
+    s_tbl[tid] = t;
+  }
+  __syncthreads();
+  float acc[4][4];
+  gl_zero(acc);
+  CmPixels<MODE> la{src, s_tbl, g, kc};
+  CmWeights lb{wt, nn, n0, kc};
+  gl_product<true>(acc, s_as, s_bs, la, lb, 0, g.R * g.S * kc);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long p = p0 + M::row(i);
+    if (p >= npix) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + M::col(j);
+      if (n < nn) dst[p * nn + n] = acc[i][j] + ((MODE == 0 && bias != nullptr) ? bias[n] : 0.f);
+    }
+  }
+}
+
+// wgrad: partial[split][tap][ci][co] = sum_{p in split} x[p@tap][ci] gy[p][co]; k = output pixels, both operands read
+// with the channel along the lanes (coalesced) and the pixel coordinates advanced incrementally from chunk to chunk.
+struct CmWgradX {
+  const float* x; ConvGeo g; int c0, r, s; long pbeg, pend;
+  mutable int n, oh, ow; mutable long pcur;                    // pixel of this thread's first element of the next fetch
+  __device__ __forceinline__ void seek(long p) const {
+    pcur = p;
+    n = (int)(p / ((long)g.Ho * g.Wo));
+    const int rem = (int)(p - (long)n * g.Ho * g.Wo);
+    oh = rem / g.Wo;
+    ow = rem - oh * g.Wo;
+  }
+  __device__ __forceinline__ void fetch(float (&v)[8], int k0) const {          // called with k0 = 0, 32, 64, ...
+    const int q = threadIdx.x & 63, c = c0 + q;
+    int nn = n, hh = oh, ww = ow;
+    long p = pcur;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float val = 0.f;
+      if (p < pend && c < g.Cin) {
+        const int ih = hh * g.stride - g.pad + r * g.dil, iw = ww * g.stride - g.pad + s * g.dil;
+        if ((unsigned)ih < (unsigned)g.H && (unsigned)iw < (unsigned)g.W)
+          val = x[(((long)nn * g.H + ih) * g.W + iw) * g.Cin + c];
+      }
+      v[i] = val;
+      p += 4;
+      ww += 4;
+      while (ww >= g.Wo) { ww -= g.Wo; if (++hh == g.Ho) { hh = 0; ++nn; } }
+    }
+    n = nn; oh = hh; ow = ww; pcur = p;                          // 8 elements x 4 pixels = the next chunk's first pixel
+  }
+  __device__ __forceinline__ void store(float* sdst, const float (&v)[8]) const {
+    const int q = threadIdx.x & 63, kk = threadIdx.x >> 6;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sdst[q * GL_LDK + kk + 4 * i] = v[i];
+  }
+};
+struct CmWgradG {
+  const float* gy; int Cout, c0; long pbeg, pend;
+  __device__ __forceinline__ void fetch(float (&v)[8], int k0) const {
+    const int q = threadIdx.x & 63, c = c0 + q;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const long p = pbeg + k0 + (threadIdx.x >> 6) + 4 * i;
+      v[i] = (p < pend && c < Cout) ? gy[p * Cout + c] : 0.f;
+    }
+  }
+  __device__ __forceinline__ void store(float* sdst, const float (&v)[8]) const {
+    const int q = threadIdx.x & 63, kk = threadIdx.x >> 6;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sdst[q * GL_LDK + kk + 4 * i] = v[i];
+  }
+};
+
+__global__ void __launch_bounds__(GL_THREADS, 2) conv2d_wgrad_mma_kernel(const float* __restrict__ x,
+                                                                         const float* __restrict__ gy,
+                                                                         float* __restrict__ partial, ConvGeo g,
+                                                                         int nsplit) {
+  __shared__ __align__(16) float s_as[GL_T * GL_LDK];
+  __shared__ __align__(16) float s_bs[GL_T * GL_LDK];
+  typedef GlMap<true> M;
+  const int ci0 = blockIdx.x * GL_T, co0 = blockIdx.y * GL_T;
+  const int rs = blockIdx.z / nsplit, split = blockIdx.z % nsplit;
+  const int r = rs / g.S, s = rs % g.S;
+  const long npix = (long)g.N * g.Ho * g.Wo;
+  long per = (npix + nsplit - 1) / nsplit;
+  per = (per + GL_KC - 1) / GL_KC * GL_KC;
+  const long pbeg = split * per, pend = (pbeg + per < npix) ? pbeg + per : npix;
+  float acc[4][4];
+  gl_zero(acc);
+  if (pbeg < pend) {
+    CmWgradX la{x, g, ci0, r, s, pbeg, pend};
+    la.seek(pbeg + (threadIdx.x >> 6));
+    CmWgradG lb{gy, g.Cout, co0, pbeg, pend};
+    gl_product<true>(acc, s_as, s_bs, la, lb, 0, (int)(pend - pbeg));
+  }
+  float* o = partial + ((long)split * g.R * g.S + rs) * g.Cin * g.Cout;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ci = ci0 + M::row(i);
+    if (ci >= g.Cin) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = co0 + M::col(j);
+      if (co < g.Cout) o[(long)ci * g.Cout + co] = acc[i][j];
+    }
+  }
+}
+
 static inline ConvGeo make_geo(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int dil) {
   ConvGeo g;
   g.N = N; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout; g.R = R; g.S = S; g.stride = stride; g.pad = pad; g.dil = dil;
@@ -280,6 +486,46 @@ static inline ConvGeo make_geo(int N, int H, int W, int Cin, int Cout, int R, in
 
 DKTB_EXPORT int dktb_conv2d_out_size(int H, int R, int stride, int pad, int dil) {
   return (H + 2 * pad - dil * (R - 1) - 1) / stride + 1;
+}
+
+static bool conv2d_use_mma() {
+  static const bool on = [] { const char* v = getenv("DKTB_RESNET_CONV"); return !(v && v[0] == 'f'); }();   // "fp32": CUDA cores
+  return on;
+}
+
+// 1 if dktb_conv2d_fwd_mma / dktb_conv2d_dgrad_mma serve this layer (reduction widths multiples of 32)
+DKTB_EXPORT int dktb_conv2d_mma_ok(int Cin, int Cout) { return conv2d_use_mma() && Cin % GL_KC == 0 && Cout % GL_KC == 0; }
+
+DKTB_EXPORT int dktb_conv2d_prep_mma(const float* w, float* wf, float* wd, int Cout, int Cin, int R, int S,
+                                     cudaStream_t stream) {
+  DKTB_CHECK_ARG(w && wf && wd && Cout > 0 && Cin > 0 && R > 0 && S > 0);
+  const long total = (long)Cout * Cin * R * S;
+  DKTB_LAUNCH(conv2d_prep_mma_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, w, wf, wd, Cout, Cin,
+              R * S);
+  return dktb_launch_status();
+}
+
+DKTB_EXPORT int dktb_conv2d_fwd_mma(const float* x, const float* wf, const float* bias, float* out, int N, int H, int W,
+                                    int Cin, int Cout, int R, int S, int stride, int pad, int dil, cudaStream_t stream) {
+  DKTB_CHECK_ARG(x && wf && out && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && R > 0 && S > 0 && stride > 0);
+  DKTB_CHECK_ARG(Cin % GL_KC == 0);
+  const ConvGeo g = make_geo(N, H, W, Cin, Cout, R, S, stride, pad, dil);
+  DKTB_CHECK_ARG(g.Ho > 0 && g.Wo > 0 && (long)N * H * W < 2147483647L);
+  const long npix = (long)N * g.Ho * g.Wo;
+  DKTB_LAUNCH(conv2d_mma_kernel<0>, dim3((unsigned)((npix + GL_T - 1) / GL_T), (Cout + GL_T - 1) / GL_T),
+              dim3(GL_THREADS), 0, stream, x, wf, bias, out, g);
+  return dktb_launch_status();
+}
+
+DKTB_EXPORT int dktb_conv2d_dgrad_mma(const float* gy, const float* wd, float* gx, int N, int H, int W, int Cin,
+                                      int Cout, int R, int S, int stride, int pad, int dil, cudaStream_t stream) {
+  DKTB_CHECK_ARG(gy && wd && gx && N > 0 && Cout % GL_KC == 0);
+  const ConvGeo g = make_geo(N, H, W, Cin, Cout, R, S, stride, pad, dil);
+  DKTB_CHECK_ARG(g.Ho > 0 && g.Wo > 0 && (long)N * H * W < 2147483647L);
+  const long npix = (long)N * H * W;
+  DKTB_LAUNCH(conv2d_mma_kernel<1>, dim3((unsigned)((npix + GL_T - 1) / GL_T), (Cin + GL_T - 1) / GL_T),
+              dim3(GL_THREADS), 0, stream, gy, wd, (const float*)nullptr, gx, g);
+  return dktb_launch_status();
 }
 
 DKTB_EXPORT int dktb_conv2d_fwd(const float* x, const float* w, const float* bias, float* out, int N, int H, int W,
@@ -319,8 +565,12 @@ DKTB_EXPORT int dktb_conv2d_wgrad(const float* x, const float* gy, const float* 
   const ConvGeo g = make_geo(N, H, W, Cin, Cout, R, S, stride, pad, dil);
   const long npix = (long)N * g.Ho * g.Wo;
   const int nsplit = dktb_conv2d_wgrad_nsplit(npix);
-  DKTB_LAUNCH(conv2d_wgrad_kernel, dim3((Cin + CG_TM - 1) / CG_TM, (Cout + CG_TN - 1) / CG_TN, R * S * nsplit),
-              dim3(256), 0, stream, x, gy, yout, scratch, g, relu, nsplit);
+  if (!relu && conv2d_use_mma() && Cin >= 16)        // tensor-core tiles (the ReLU-fused form is only used by Conv3)
+    DKTB_LAUNCH(conv2d_wgrad_mma_kernel, dim3((Cin + GL_T - 1) / GL_T, (Cout + GL_T - 1) / GL_T, R * S * nsplit),
+                dim3(GL_THREADS), 0, stream, x, gy, scratch, g, nsplit);
+  else
+    DKTB_LAUNCH(conv2d_wgrad_kernel, dim3((Cin + CG_TM - 1) / CG_TM, (Cout + CG_TN - 1) / CG_TN, R * S * nsplit),
+                dim3(256), 0, stream, x, gy, yout, scratch, g, relu, nsplit);
   const long total = (long)R * S * Cin * Cout;
   DKTB_LAUNCH(conv2d_wgrad_reduce_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream,
               (const float*)scratch, dw, g, nsplit);

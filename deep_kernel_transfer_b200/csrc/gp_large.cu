@@ -14,15 +14,10 @@
 // keeps those blocks well conditioned).  alpha, log-determinant, loss and hyper-parameter gradients follow gp_fit.
 #include <stdlib.h>
 
-#include "dktb_common.cuh"
+#include "tile_mma.cuh"
 
 #define NOISE_FLOOR 1e-4f
-#define GL_T 64              // tile edge
-#define GL_KC 32             // k-chunk staged per step
-#define GL_LDK 36            // pitch of a staged chunk   (36 mod 32 = 4: conflict-free float4 rows)
-#define GL_LDT 68            // pitch of a resident tile  (68 mod 32 = 4)
 #define GL_LDD 65            // pitch of the diagonal block while it is factored (row per lane)
-#define GL_THREADS 256
 #define GL_MAXN 512
 
 struct GpFitLargeArgs {
@@ -70,154 +65,6 @@ __device__ __forceinline__ float gl_block_sum(float v, float* s_red) {
   return t;
 }
 
-// acc[i][j] += sum_k A[tr + 16 i][k] * B[tc + 16 j][k], k < kc (kc a multiple of 4), both operands k-contiguous.
-__device__ __forceinline__ void gl_core(float (&acc)[4][4], const float* __restrict__ A, int lda,
-                                        const float* __restrict__ B, int ldb, int kc, int tr, int tc) {
-#pragma unroll 2
-  for (int k = 0; k < kc; k += 4) {
-    float4 a[4], b[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) a[i] = dktb_ld4(A + (tr + 16 * i) * lda + k);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) b[j] = dktb_ld4(B + (tc + 16 * j) * ldb + k);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float v = acc[i][j];
-        v = fmaf(a[i].x, b[j].x, v);
-        v = fmaf(a[i].y, b[j].y, v);
-        v = fmaf(a[i].z, b[j].z, v);
-        v = fmaf(a[i].w, b[j].w, v);
-        acc[i][j] = v;
-      }
-  }
-}
-
-// The same tile product on the warp-level tensor cores (mma.sync m16n8k8, 3xTF32: operands split into a tf32 `hi` and
-// the exact remainder `lo`, products lo*hi + hi*lo + hi*hi accumulated in fp32): warp w owns rows 32 (w / 4) .. + 31 and
-// columns 16 (w % 4) .. + 15 of the tile as 2 x 2 fragments; acc[i][j] = fragment (i / 2, j / 2), register 2 (i % 2) + j % 2.
-__device__ __forceinline__ void gl_split(float v, unsigned& hi, unsigned& lo) {
-  hi = __float_as_uint(v) & 0xFFFFE000u;
-  lo = __float_as_uint(v - __uint_as_float(hi));
-}
-__device__ __forceinline__ void gl_core_mma(float (&acc)[4][4], const float* __restrict__ A, int lda,
-                                            const float* __restrict__ B, int ldb, int kc) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  const float* a0 = A + ((warp >> 2) * 32 + g) * lda + t;
-  const float* b0 = B + ((warp & 3) * 16 + g) * ldb + t;
-#pragma unroll 2
-  for (int k = 0; k < kc; k += 8) {
-    unsigned ah[2][4], al[2][4], bh[2][2], bl[2][2];
-#pragma unroll
-    for (int mf = 0; mf < 2; ++mf) {
-      const float* ap = a0 + mf * 16 * lda + k;
-      gl_split(ap[0], ah[mf][0], al[mf][0]);
-      gl_split(ap[8 * lda], ah[mf][1], al[mf][1]);
-      gl_split(ap[4], ah[mf][2], al[mf][2]);
-      gl_split(ap[8 * lda + 4], ah[mf][3], al[mf][3]);
-    }
-#pragma unroll
-    for (int nf = 0; nf < 2; ++nf) {
-      const float* bp = b0 + nf * 8 * ldb + k;
-      gl_split(bp[0], bh[nf][0], bl[nf][0]);
-      gl_split(bp[4], bh[nf][1], bl[nf][1]);
-    }
-#pragma unroll
-    for (int mf = 0; mf < 2; ++mf)
-#pragma unroll
-      for (int nf = 0; nf < 2; ++nf) {
-        float d[4] = {acc[2 * mf][2 * nf], acc[2 * mf][2 * nf + 1], acc[2 * mf + 1][2 * nf], acc[2 * mf + 1][2 * nf + 1]};
-        dktb_mma_m16n8k8_tf32(d, al[mf], bh[nf]);
-        dktb_mma_m16n8k8_tf32(d, ah[mf], bl[nf]);
-        dktb_mma_m16n8k8_tf32(d, ah[mf], bh[nf]);
-        acc[2 * mf][2 * nf] = d[0];
-        acc[2 * mf][2 * nf + 1] = d[1];
-        acc[2 * mf + 1][2 * nf] = d[2];
-        acc[2 * mf + 1][2 * nf + 1] = d[3];
-      }
-  }
-}
-
-// Which tile row / column acc[i][j] of this thread holds, for the two cores.
-template <bool MMA> struct GlMap;
-template <> struct GlMap<false> {
-  __device__ static __forceinline__ int row(int i) { return (threadIdx.x >> 4) + 16 * i; }
-  __device__ static __forceinline__ int col(int j) { return (threadIdx.x & 15) + 16 * j; }
-};
-template <> struct GlMap<true> {
-  __device__ static __forceinline__ int row(int i) {
-    return ((threadIdx.x >> 7) & 1) * 32 + (i >> 1) * 16 + ((threadIdx.x & 31) >> 2) + 8 * (i & 1);
-  }
-  __device__ static __forceinline__ int col(int j) {
-    return ((threadIdx.x >> 5) & 3) * 16 + (j >> 1) * 8 + 2 * (threadIdx.x & 3) + (j & 1);
-  }
-};
-template <bool MMA>
-__device__ __forceinline__ void gl_tile(float (&acc)[4][4], const float* A, int lda, const float* B, int ldb, int kc) {
-  if (MMA) gl_core_mma(acc, A, lda, B, ldb, kc);
-  else gl_core(acc, A, lda, B, ldb, kc, threadIdx.x >> 4, threadIdx.x & 15);
-}
-
-// Operand loaders of one 64 x 32 chunk: element (q, k) of the staged chunk, q = tile row / column, k = reduction index.
-//   rows: q-th row of `src` starting at row0, k along the row        (lanes along k: coalesced)
-//   cols: q-th column of `src` starting at col0, k down the column   (lanes along q: coalesced)
-// Out-of-range q (>= nq) and k (>= klim) read as zero.
-struct GlRows {
-  const float* src; int ld, row0, nq, klim;
-  __device__ __forceinline__ void fetch(float (&v)[8], int k0) const {
-    const int k = threadIdx.x & 31, q0 = threadIdx.x >> 5;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int q = q0 + 8 * i;
-      v[i] = (q < nq && k0 + k < klim) ? src[(long)(row0 + q) * ld + k0 + k] : 0.f;
-    }
-  }
-  __device__ __forceinline__ void store(float* s, const float (&v)[8]) const {
-    const int k = threadIdx.x & 31, q0 = threadIdx.x >> 5;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s[(q0 + 8 * i) * GL_LDK + k] = v[i];
-  }
-};
-struct GlCols {
-  const float* src; int ld, col0, nq, klim;
-  __device__ __forceinline__ void fetch(float (&v)[8], int k0) const {
-    const int q = threadIdx.x & 63, kk = threadIdx.x >> 6;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int k = kk + 4 * i;
-      v[i] = (q < nq && k0 + k < klim) ? src[(long)(k0 + k) * ld + col0 + q] : 0.f;
-    }
-  }
-  __device__ __forceinline__ void store(float* s, const float (&v)[8]) const {
-    const int q = threadIdx.x & 63, kk = threadIdx.x >> 6;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s[q * GL_LDK + kk + 4 * i] = v[i];
-  }
-};
-
-// acc += A-operand x B-operand over k in [kbeg, kend) (kbeg a multiple of 32), staged through sm.as / sm.bs.
-template <bool MMA, class LA, class LB>
-__device__ __forceinline__ void gl_product(float (&acc)[4][4], const GlSmem& sm, const LA& la, const LB& lb, int kbeg,
-                                           int kend) {
-  float ra[8], rb[8];
-  if (kbeg < kend) {
-    la.fetch(ra, kbeg);
-    lb.fetch(rb, kbeg);
-  }
-  for (int k0 = kbeg; k0 < kend; k0 += GL_KC) {
-    __syncthreads();                       // the previous chunk (or whatever used the staging area) is consumed
-    la.store(sm.as, ra);
-    lb.store(sm.bs, rb);
-    __syncthreads();
-    if (k0 + GL_KC < kend) {               // next chunk in flight while this one is multiplied
-      la.fetch(ra, k0 + GL_KC);
-      lb.fetch(rb, k0 + GL_KC);
-    }
-    gl_tile<MMA>(acc, sm.as, GL_LDK, sm.bs, GL_LDK, GL_KC);
-  }
-}
-
 // v - sum_{k < n} a[k * sa] * b[k * sb] out of shared memory: loads issued eight at a time, two independent FMA chains
 // (a plain dependent loop pays the shared-memory latency on every step: profiles/r01_gp_fit_large.summary.txt).
 __device__ __forceinline__ float gl_dot_sub(float v, const float* a, int sa, const float* b, int sb, int n) {
@@ -232,13 +79,6 @@ __device__ __forceinline__ float gl_dot_sub(float v, const float* a, int sa, con
   }
   for (; k < n; ++k) v = fmaf(-a[k * sa], b[k * sb], v);
   return v + v2;
-}
-
-__device__ __forceinline__ void gl_zero(float (&acc)[4][4]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 }
 
 template <bool MMA>
@@ -294,7 +134,7 @@ __global__ void __launch_bounds__(GL_THREADS, 2) gp_fit_large_kernel(GpFitLargeA
     gl_zero(acc);
     {
       GlRows la{A, N, j0, nb, j0}, lb{A, N, j0, nb, j0};
-      gl_product<MMA>(acc, sm, la, lb, 0, j0);
+      gl_product<MMA>(acc, sm.as, sm.bs, la, lb, 0, j0);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -374,7 +214,7 @@ __global__ void __launch_bounds__(GL_THREADS, 2) gp_fit_large_kernel(GpFitLargeA
       gl_zero(acc);
       {
         GlRows la{A, N, i0, nr, j0}, lb{A, N, j0, nb, j0};
-        gl_product<MMA>(acc, sm, la, lb, 0, j0);
+        gl_product<MMA>(acc, sm.as, sm.bs, la, lb, 0, j0);
       }
       __syncthreads();                                    // sm.t free (previous tile's second product done)
 #pragma unroll
@@ -403,7 +243,7 @@ __global__ void __launch_bounds__(GL_THREADS, 2) gp_fit_large_kernel(GpFitLargeA
       {
         GlRows la{A, N, j0, nb, j0};
         GlCols lb{X, N, k0, GL_T, j0};
-        gl_product<MMA>(acc, sm, la, lb, k0, j0);
+        gl_product<MMA>(acc, sm.as, sm.bs, la, lb, k0, j0);
       }
       __syncthreads();
 #pragma unroll
@@ -478,7 +318,7 @@ __global__ void __launch_bounds__(GL_THREADS, 2) gp_fit_large_kernel(GpFitLargeA
       {
         GlCols la{X, N, i0, ni, N}, lb{X, N, k0, GL_T, N};       // kbk <= ib: the k-tile is full unless it is the last
         lb.nq = min(GL_T, N - k0);
-        gl_product<MMA>(acc, sm, la, lb, i0, N);
+        gl_product<MMA>(acc, sm.as, sm.bs, la, lb, i0, N);
       }
       __syncthreads();
 #pragma unroll

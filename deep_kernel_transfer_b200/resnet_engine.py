@@ -16,6 +16,7 @@ class ResNetEngine:
         self.trace = None            # tests may set a list: backward appends (record, gy, gx, gres) per op
         self.D = net.final_feat_dim
         self.P = 1
+        self._mma_w = {}             # conv module -> (wf, wd): k-contiguous weight copies for the tensor-core kernels
 
     # ------------------------------------------------------------------ helpers
     def _new(self, *shape, dtype=torch.float32):
@@ -28,10 +29,25 @@ class ResNetEngine:
         Ho = self.lib.conv2d_out_size(H, R, st, pad, dil)
         Wo = self.lib.conv2d_out_size(W, R, st, pad, dil)
         out = self._new(B, Ho, Wo, m.out_channels)
-        self.lib.conv2d_fwd(x, m.weight.data, m.bias.data if m.bias is not None else None, out, B, H, W, Cin,
-                            m.out_channels, R, R, st, pad, dil, relu, _stream(self.dev))
+        bias = m.bias.data if m.bias is not None else None
+        if not relu and self.lib.conv2d_mma_ok(Cin, m.out_channels):
+            # tensor-core tiles (mma.sync 3xTF32): refresh the two k-contiguous weight copies, then forward from `wf`;
+            # the backward of the same step reads `wd`
+            wf, wd = self._mma_weights(m)
+            self.lib.conv2d_prep_mma(m.weight.data, wf, wd, m.out_channels, Cin, R, R, _stream(self.dev))
+            self.lib.conv2d_fwd_mma(x, wf, bias, out, B, H, W, Cin, m.out_channels, R, R, st, pad, dil, _stream(self.dev))
+        else:
+            self.lib.conv2d_fwd(x, m.weight.data, bias, out, B, H, W, Cin, m.out_channels, R, R, st, pad, dil, relu,
+                                _stream(self.dev))
         self.tape.append(("conv", x, out, m, (B, H, W, Cin, R, st, pad, dil)))
         return out
+
+    def _mma_weights(self, m):
+        key = id(m)
+        if key not in self._mma_w:
+            n = m.weight.numel()
+            self._mma_w[key] = (self._new(n), self._new(n))
+        return self._mma_w[key]
 
     def _bn(self, x, m, ipe, training, res=None, relu=0):
         B, H, W, C = x.shape
@@ -142,7 +158,10 @@ class ResNetEngine:
                 gx = None
                 if Cin > 3:      # no input gradient for the stem
                     gx = torch.empty_like(x)
-                    lib.conv2d_dgrad(gy, None, m.weight.data, gx, B, H, W, Cin, Cout, R, R, stv, pad, dil, 0, st)
+                    if lib.conv2d_mma_ok(Cin, Cout):      # `wd` was refreshed by this step's forward (weights unchanged since)
+                        lib.conv2d_dgrad_mma(gy, self._mma_weights(m)[1], gx, B, H, W, Cin, Cout, R, R, stv, pad, dil, st)
+                    else:
+                        lib.conv2d_dgrad(gy, None, m.weight.data, gx, B, H, W, Cin, Cout, R, R, stv, pad, dil, 0, st)
                 if self.trace is not None:
                     self.trace.append((rec, gy, None if gx is None else gx.clone(), m.weight.grad.clone()))
                 if gx is not None:

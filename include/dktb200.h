@@ -109,6 +109,17 @@ int dktb_conv2d_wgrad_nsplit(long npix);
 int dktb_conv2d_wgrad(const float* x, const float* gy, const float* yout, float* dw, float* db, float* scratch, int N,
                       int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int dil, int relu,
                       cudaStream_t stream);
+/* Tensor-core variants (mma.sync 3xTF32 tile products) for layers whose reduction widths are multiples of 32 -- every
+ * ResNet layer but the stem (backbone.py:135-247, 330-376); dktb_conv2d_mma_ok() says whether a layer qualifies
+ * (DKTB_RESNET_CONV=fp32 turns them off).  Weights are read from two k-contiguous copies refreshed once per step by
+ * dktb_conv2d_prep_mma: wf [R*S][Cout][Cin] (forward), wd [R*S][Cin][Cout] (dgrad).  No fused ReLU.  dktb_conv2d_wgrad
+ * picks its tensor-core kernel by itself (same arguments, same scratch). */
+int dktb_conv2d_mma_ok(int Cin, int Cout);
+int dktb_conv2d_prep_mma(const float* w, float* wf, float* wd, int Cout, int Cin, int R, int S, cudaStream_t stream);
+int dktb_conv2d_fwd_mma(const float* x, const float* wf, const float* bias, float* out, int N, int H, int W, int Cin,
+                        int Cout, int R, int S, int stride, int pad, int dil, cudaStream_t stream);
+int dktb_conv2d_dgrad_mma(const float* gy, const float* wd, float* gx, int N, int H, int W, int Cin, int Cout, int R,
+                          int S, int stride, int pad, int dil, cudaStream_t stream);
 int dktb_nchw_to_nhwc(const float* x, float* out, int N, int C, int H, int W, cudaStream_t stream);
 
 /* BatchNorm2d statistics (train: per-episode batch stats from the conv partial sums + running-stat EMA,

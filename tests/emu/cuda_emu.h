@@ -29,6 +29,7 @@ struct alignas(16) float4 { float x, y, z, w; };
 struct alignas(16) int4 { int x, y, z, w; };
 struct alignas(8) int2 { int x, y; };
 static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
+static inline int4 make_int4(int a, int b, int c, int d) { return int4{a, b, c, d}; }
 static inline float2 make_float2(float a, float b) { return float2{a, b}; }
 
 typedef void* cudaStream_t;

@@ -455,6 +455,16 @@ def check_conv2d(lib, dev, N=2, H=13, W=11, Cin=3, Cout=36, R=3, stride=2, pad=0
     lib.conv2d_wgrad(x_nhwc, gyd, out, dw, db, scratch, N, H, W, Cin, Cout, R, R, stride, pad, dil, relu, 0)
     _close(dw, wr.grad, rtol=1e-4, atol=1e-4, what="conv2d wgrad")
     _close(db, br.grad, rtol=1e-4, atol=1e-4, what="conv2d bgrad")
+    if not relu and lib.conv2d_mma_ok(Cin, Cout):       # tensor-core variants (ResNet layers)
+        wf = torch.empty(R * R, Cout, Cin, device=dev)
+        wd = torch.empty(R * R, Cin, Cout, device=dev)
+        lib.conv2d_prep_mma(w.to(dev), wf, wd, Cout, Cin, R, R, 0)
+        out2 = torch.full((N, Ho, Wo, Cout), float("nan"), device=dev)
+        lib.conv2d_fwd_mma(x_nhwc, wf, b.to(dev), out2, N, H, W, Cin, Cout, R, R, stride, pad, dil, 0)
+        _close(out2.cpu().permute(0, 3, 1, 2), ref.detach(), rtol=2e-5, atol=2e-5, what="conv2d fwd (mma)")
+        gx2 = torch.full((N, H, W, Cin), float("nan"), device=dev)
+        lib.conv2d_dgrad_mma(gyd, wd, gx2, N, H, W, Cin, Cout, R, R, stride, pad, dil, 0)
+        _close(gx2.cpu().permute(0, 3, 1, 2), xr.grad, rtol=1e-4, atol=2e-5, what="conv2d dgrad (mma)")
 
 
 def check_spectral(lib, dev, E=2, N=6, M=5, Cch=4, P=3, Q=4, seed=60, rtol=3e-4):

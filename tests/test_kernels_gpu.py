@@ -92,7 +92,13 @@ def test_gp_family(lib, kernel):
 
 @pytest.mark.parametrize("cfg", [dict(), dict(Cin=36, Cout=36, H=48, W=48, N=19), dict(Cin=5, Cout=70, R=1, stride=2, dil=1, relu=0),
                                  dict(Cin=3, Cout=64, R=7, stride=2, pad=3, dil=1, relu=0, H=56, W=56, N=3),
-                                 dict(N=19, H=100, W=100)])
+                                 dict(N=19, H=100, W=100),
+                                 dict(Cin=64, Cout=64, R=3, stride=1, pad=1, dil=1, relu=0, H=56, W=56, N=5),    # ResNet18 layers
+                                 dict(Cin=64, Cout=128, R=3, stride=2, pad=1, dil=1, relu=0, H=56, W=56, N=3),
+                                 dict(Cin=64, Cout=128, R=1, stride=2, pad=0, dil=1, relu=0, H=56, W=56, N=3),
+                                 dict(Cin=256, Cout=512, R=3, stride=2, pad=1, dil=1, relu=0, H=14, W=14, N=4),
+                                 dict(Cin=512, Cout=512, R=3, stride=1, pad=1, dil=1, relu=0, H=7, W=7, N=6),
+                                 dict(Cin=256, Cout=64, R=1, stride=1, pad=0, dil=1, relu=0, H=56, W=56, N=2)])  # bottleneck 1x1
 def test_conv2d_generic(lib, cfg):
     kc.check_conv2d(lib, DEV, **cfg)
 
