@@ -70,6 +70,9 @@ SIGNATURES = {
     "dktb_conv2d_prep_mma": ("pppiiiis", ctypes.c_int),
     "dktb_conv2d_fwd_mma": ("ppppiiiiiiiiiis", ctypes.c_int),
     "dktb_conv2d_dgrad_mma": ("pppiiiiiiiiiis", ctypes.c_int),
+    "dktb_conv2d_flat_k": ("iii", ctypes.c_int),
+    "dktb_conv2d_prep_flat_mma": ("ppiiiis", ctypes.c_int),
+    "dktb_conv2d_fwd_flat_mma": ("ppppiiiiiiiiiis", ctypes.c_int),
     "dktb_conv2d_wgrad": ("ppppppiiiiiiiiiiis", ctypes.c_int),
     "dktb_nchw_to_nhwc": ("ppiiiis", ctypes.c_int),
     "dktb_spectral_fwd": ("pppppppiiiiiiis", ctypes.c_int),

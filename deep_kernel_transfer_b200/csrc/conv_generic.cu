@@ -296,19 +296,32 @@ template <int MODE>
 struct CmPixels {
   const float* src; const int4* tbl; ConvGeo g; int kc;       // kc = channels per tap on the k axis
   __device__ __forceinline__ void fetch(float (&v)[8], int k0) const {
-    const int tap = k0 / kc, c = k0 - tap * kc + (threadIdx.x & 31);
+    int tap, c;
+    bool kok = true;
+    if (MODE == 2) {                 // narrow input: k runs over the flattened (r, s, ci) index, padded to a multiple of 32
+      const int kk = k0 + (threadIdx.x & 31);
+      kok = kk < g.R * g.S * g.Cin;
+      tap = kk / g.Cin;
+      c = kk - tap * g.Cin;
+    } else {
+      tap = k0 / kc;
+      c = k0 - tap * kc + (threadIdx.x & 31);
+    }
     const int r = tap / g.S, s = tap - r * g.S;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int4 t = tbl[(threadIdx.x >> 5) + 8 * i];
       float val = 0.f;
-      if (MODE == 0) {
+      if (MODE == 0 || MODE == 2) {
         const int ih = t.y + r * g.dil, iw = t.z + s * g.dil;
-        if (t.w && (unsigned)ih < (unsigned)g.H && (unsigned)iw < (unsigned)g.W)
+        if (kok && t.w && (unsigned)ih < (unsigned)g.H && (unsigned)iw < (unsigned)g.W)
           val = src[((long)t.x + (long)ih * g.W + iw) * g.Cin + c];
       } else {
         const int th = t.y - r * g.dil, tw = t.z - s * g.dil;
-        if (t.w && th >= 0 && tw >= 0 && th % g.stride == 0 && tw % g.stride == 0) {
+        if (g.stride == 1) {                                    // uniform branch: no divisions on the common layers
+          if (t.w && (unsigned)th < (unsigned)g.Ho && (unsigned)tw < (unsigned)g.Wo)
+            val = src[((long)t.x + (long)th * g.Wo + tw) * g.Cout + c];
+        } else if (t.w && th >= 0 && tw >= 0 && th % g.stride == 0 && tw % g.stride == 0) {
           const int oh = th / g.stride, ow = tw / g.stride;
           if (oh < g.Ho && ow < g.Wo) val = src[((long)t.x + (long)oh * g.Wo + ow) * g.Cout + c];
         }
@@ -352,10 +365,11 @@ __global__ void __launch_bounds__(GL_THREADS, 2) conv2d_mma_kernel(const float* 
   __shared__ int4 s_tbl[GL_T];
   typedef GlMap<true> M;
   const int tid = threadIdx.x;
-  const int Hp = MODE == 0 ? g.Ho : g.H, Wp = MODE == 0 ? g.Wo : g.W;      // the pixel grid this kernel tiles
+  const int Hp = MODE != 1 ? g.Ho : g.H, Wp = MODE != 1 ? g.Wo : g.W;      // the pixel grid this kernel tiles
   const long npix = (long)g.N * Hp * Wp;
   const long p0 = (long)blockIdx.x * GL_T;
-  const int nn = MODE == 0 ? g.Cout : g.Cin, kc = MODE == 0 ? g.Cin : g.Cout;
+  const int nn = MODE != 1 ? g.Cout : g.Cin;
+  const int kc = MODE == 0 ? g.Cin : (MODE == 1 ? g.Cout : (g.R * g.S * g.Cin + GL_KC - 1) / GL_KC * GL_KC);
   const int n0 = blockIdx.y * GL_T;
   if (tid < GL_T) {
     const long p = p0 + tid;
@@ -364,7 +378,7 @@ __global__ void __launch_bounds__(GL_THREADS, 2) conv2d_mma_kernel(const float* 
       const int n = (int)(p / ((long)Hp * Wp));
       const int rem = (int)(p - (long)n * Hp * Wp);
       const int ph = rem / Wp, pw = rem - ph * Wp;
-      if (MODE == 0) t = make_int4(n * g.H * g.W, ph * g.stride - g.pad, pw * g.stride - g.pad, 1);
+      if (MODE != 1) t = make_int4(n * g.H * g.W, ph * g.stride - g.pad, pw * g.stride - g.pad, 1);
       else t = make_int4(n * g.Ho * g.Wo, ph + g.pad, pw + g.pad, 1);
     }
     s_tbl[tid] = t;
@@ -374,7 +388,7 @@ __global__ void __launch_bounds__(GL_THREADS, 2) conv2d_mma_kernel(const float* 
   gl_zero(acc);
   CmPixels<MODE> la{src, s_tbl, g, kc};
   CmWeights lb{wt, nn, n0, kc};
-  gl_product<true>(acc, s_as, s_bs, la, lb, 0, g.R * g.S * kc);
+  gl_product<true>(acc, s_as, s_bs, la, lb, 0, MODE == 2 ? kc : g.R * g.S * kc);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const long p = p0 + M::row(i);
@@ -382,7 +396,7 @@ __global__ void __launch_bounds__(GL_THREADS, 2) conv2d_mma_kernel(const float* 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + M::col(j);
-      if (n < nn) dst[p * nn + n] = acc[i][j] + ((MODE == 0 && bias != nullptr) ? bias[n] : 0.f);
+      if (n < nn) dst[p * nn + n] = acc[i][j] + ((MODE != 1 && bias != nullptr) ? bias[n] : 0.f);
     }
   }
 }
@@ -440,6 +454,81 @@ struct CmWgradG {
     for (int i = 0; i < 8; ++i) sdst[q * GL_LDK + kk + 4 * i] = v[i];
   }
 };
+
+// Narrow inputs (the 3-channel stem, backbone.py:343-347): a 64-wide tile over the flattened (r, s, ci) index instead
+// of one tap x 64 mostly absent channels; consecutive indices are consecutive addresses along a filter row.
+struct CmWgradXFlat {
+  const float* x; ConvGeo g; int q0; long pbeg, pend;
+  mutable int n, oh, ow; mutable long pcur;
+  __device__ __forceinline__ void seek(long p) const {
+    pcur = p;
+    n = (int)(p / ((long)g.Ho * g.Wo));
+    const int rem = (int)(p - (long)n * g.Ho * g.Wo);
+    oh = rem / g.Wo;
+    ow = rem - oh * g.Wo;
+  }
+  __device__ __forceinline__ void fetch(float (&v)[8], int k0) const {
+    const int qq = q0 + (threadIdx.x & 63);
+    const bool qok = qq < g.R * g.S * g.Cin;
+    const int r = qq / (g.S * g.Cin), rem = qq - r * g.S * g.Cin, s = rem / g.Cin, ci = rem - s * g.Cin;
+    int nn = n, hh = oh, ww = ow;
+    long p = pcur;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float val = 0.f;
+      if (p < pend && qok) {
+        const int ih = hh * g.stride - g.pad + r * g.dil, iw = ww * g.stride - g.pad + s * g.dil;
+        if ((unsigned)ih < (unsigned)g.H && (unsigned)iw < (unsigned)g.W)
+          val = x[(((long)nn * g.H + ih) * g.W + iw) * g.Cin + ci];
+      }
+      v[i] = val;
+      p += 4;
+      ww += 4;
+      while (ww >= g.Wo) { ww -= g.Wo; if (++hh == g.Ho) { hh = 0; ++nn; } }
+    }
+    n = nn; oh = hh; ow = ww; pcur = p;
+  }
+  __device__ __forceinline__ void store(float* sdst, const float (&v)[8]) const {
+    const int q = threadIdx.x & 63, kk = threadIdx.x >> 6;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sdst[q * GL_LDK + kk + 4 * i] = v[i];
+  }
+};
+
+// partial[split][(r, s, ci)][co]: the same memory layout as [split][tap][ci][co]
+__global__ void __launch_bounds__(GL_THREADS, 2) conv2d_wgrad_flat_mma_kernel(const float* __restrict__ x,
+                                                                              const float* __restrict__ gy,
+                                                                              float* __restrict__ partial, ConvGeo g,
+                                                                              int nsplit) {
+  __shared__ __align__(16) float s_as[GL_T * GL_LDK];
+  __shared__ __align__(16) float s_bs[GL_T * GL_LDK];
+  typedef GlMap<true> M;
+  const int q0 = blockIdx.x * GL_T, co0 = blockIdx.y * GL_T, split = blockIdx.z;
+  const int Q = g.R * g.S * g.Cin;
+  const long npix = (long)g.N * g.Ho * g.Wo;
+  long per = (npix + nsplit - 1) / nsplit;
+  per = (per + GL_KC - 1) / GL_KC * GL_KC;
+  const long pbeg = split * per, pend = (pbeg + per < npix) ? pbeg + per : npix;
+  float acc[4][4];
+  gl_zero(acc);
+  if (pbeg < pend) {
+    CmWgradXFlat la{x, g, q0, pbeg, pend};
+    la.seek(pbeg + (threadIdx.x >> 6));
+    CmWgradG lb{gy, g.Cout, co0, pbeg, pend};
+    gl_product<true>(acc, s_as, s_bs, la, lb, 0, (int)(pend - pbeg));
+  }
+  float* o = partial + (long)split * Q * g.Cout;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int qq = q0 + M::row(i);
+    if (qq >= Q) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = co0 + M::col(j);
+      if (co < g.Cout) o[(long)qq * g.Cout + co] = acc[i][j];
+    }
+  }
+}
 
 __global__ void __launch_bounds__(GL_THREADS, 2) conv2d_wgrad_mma_kernel(const float* __restrict__ x,
                                                                          const float* __restrict__ gy,
@@ -505,6 +594,45 @@ DKTB_EXPORT int dktb_conv2d_prep_mma(const float* w, float* wf, float* wd, int C
   return dktb_launch_status();
 }
 
+// narrow inputs (the stem): wflat [Cout][Kp], k = (r * S + s) * Cin + ci, Kp = R*S*Cin rounded up to 32 (zero padded)
+__global__ void conv2d_prep_flat_mma_kernel(const float* __restrict__ w, float* __restrict__ wflat, int Cout, int Cin,
+                                            int RS, int Kp) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)Cout * Kp) return;
+  const int k = (int)(i % Kp), co = (int)(i / Kp);
+  float v = 0.f;
+  if (k < RS * Cin) {
+    const int tap = k / Cin, ci = k - tap * Cin;
+    v = w[((long)co * Cin + ci) * RS + tap];
+  }
+  wflat[i] = v;
+}
+
+DKTB_EXPORT int dktb_conv2d_flat_k(int Cin, int R, int S) { return (R * S * Cin + GL_KC - 1) / GL_KC * GL_KC; }
+
+DKTB_EXPORT int dktb_conv2d_prep_flat_mma(const float* w, float* wflat, int Cout, int Cin, int R, int S,
+                                          cudaStream_t stream) {
+  DKTB_CHECK_ARG(w && wflat && Cout > 0 && Cin > 0 && R > 0 && S > 0);
+  const int Kp = dktb_conv2d_flat_k(Cin, R, S);
+  const long total = (long)Cout * Kp;
+  DKTB_LAUNCH(conv2d_prep_flat_mma_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, w, wflat, Cout,
+              Cin, R * S, Kp);
+  return dktb_launch_status();
+}
+
+// forward of a narrow-input layer from wflat (any Cin; meant for Cin < 32)
+DKTB_EXPORT int dktb_conv2d_fwd_flat_mma(const float* x, const float* wflat, const float* bias, float* out, int N, int H,
+                                         int W, int Cin, int Cout, int R, int S, int stride, int pad, int dil,
+                                         cudaStream_t stream) {
+  DKTB_CHECK_ARG(x && wflat && out && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && R > 0 && S > 0 && stride > 0);
+  const ConvGeo g = make_geo(N, H, W, Cin, Cout, R, S, stride, pad, dil);
+  DKTB_CHECK_ARG(g.Ho > 0 && g.Wo > 0 && (long)N * H * W < 2147483647L);
+  const long npix = (long)N * g.Ho * g.Wo;
+  DKTB_LAUNCH(conv2d_mma_kernel<2>, dim3((unsigned)((npix + GL_T - 1) / GL_T), (Cout + GL_T - 1) / GL_T),
+              dim3(GL_THREADS), 0, stream, x, wflat, bias, out, g);
+  return dktb_launch_status();
+}
+
 DKTB_EXPORT int dktb_conv2d_fwd_mma(const float* x, const float* wf, const float* bias, float* out, int N, int H, int W,
                                     int Cin, int Cout, int R, int S, int stride, int pad, int dil, cudaStream_t stream) {
   DKTB_CHECK_ARG(x && wf && out && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && R > 0 && S > 0 && stride > 0);
@@ -565,7 +693,10 @@ DKTB_EXPORT int dktb_conv2d_wgrad(const float* x, const float* gy, const float* 
   const ConvGeo g = make_geo(N, H, W, Cin, Cout, R, S, stride, pad, dil);
   const long npix = (long)N * g.Ho * g.Wo;
   const int nsplit = dktb_conv2d_wgrad_nsplit(npix);
-  if (!relu && conv2d_use_mma() && Cin >= 16)        // tensor-core tiles (the ReLU-fused form is only used by Conv3)
+  if (!relu && conv2d_use_mma() && Cin < 16)         // the stem: tiles over the flattened (r, s, ci) index
+    DKTB_LAUNCH(conv2d_wgrad_flat_mma_kernel, dim3((R * S * Cin + GL_T - 1) / GL_T, (Cout + GL_T - 1) / GL_T, nsplit),
+                dim3(GL_THREADS), 0, stream, x, gy, scratch, g, nsplit);
+  else if (!relu && conv2d_use_mma())                // tensor-core tiles (the ReLU-fused form is only used by Conv3)
     DKTB_LAUNCH(conv2d_wgrad_mma_kernel, dim3((Cin + GL_T - 1) / GL_T, (Cout + GL_T - 1) / GL_T, R * S * nsplit),
                 dim3(GL_THREADS), 0, stream, x, gy, scratch, g, nsplit);
   else

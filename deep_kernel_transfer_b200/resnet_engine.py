@@ -36,6 +36,14 @@ class ResNetEngine:
             wf, wd = self._mma_weights(m)
             self.lib.conv2d_prep_mma(m.weight.data, wf, wd, m.out_channels, Cin, R, R, _stream(self.dev))
             self.lib.conv2d_fwd_mma(x, wf, bias, out, B, H, W, Cin, m.out_channels, R, R, st, pad, dil, _stream(self.dev))
+        elif not relu and Cin < 16 and self.lib.conv2d_mma_ok(32, 32):
+            # the stem: reduction over the flattened (r, s, ci) index
+            key = ("flat", id(m))
+            if key not in self._mma_w:
+                self._mma_w[key] = self._new(m.out_channels * self.lib.conv2d_flat_k(Cin, R, R))
+            self.lib.conv2d_prep_flat_mma(m.weight.data, self._mma_w[key], m.out_channels, Cin, R, R, _stream(self.dev))
+            self.lib.conv2d_fwd_flat_mma(x, self._mma_w[key], bias, out, B, H, W, Cin, m.out_channels, R, R, st, pad, dil,
+                                         _stream(self.dev))
         else:
             self.lib.conv2d_fwd(x, m.weight.data, bias, out, B, H, W, Cin, m.out_channels, R, R, st, pad, dil, relu,
                                 _stream(self.dev))

@@ -120,6 +120,12 @@ int dktb_conv2d_fwd_mma(const float* x, const float* wf, const float* bias, floa
                         int Cout, int R, int S, int stride, int pad, int dil, cudaStream_t stream);
 int dktb_conv2d_dgrad_mma(const float* gy, const float* wd, float* gx, int N, int H, int W, int Cin, int Cout, int R,
                           int S, int stride, int pad, int dil, cudaStream_t stream);
+/* Narrow inputs (the 3-channel 7x7 stem, backbone.py:343-347): the reduction runs over the flattened (r, s, ci) index,
+ * weights from wflat [Cout][dktb_conv2d_flat_k(Cin, R, S)] written by dktb_conv2d_prep_flat_mma. */
+int dktb_conv2d_flat_k(int Cin, int R, int S);
+int dktb_conv2d_prep_flat_mma(const float* w, float* wflat, int Cout, int Cin, int R, int S, cudaStream_t stream);
+int dktb_conv2d_fwd_flat_mma(const float* x, const float* wflat, const float* bias, float* out, int N, int H, int W,
+                             int Cin, int Cout, int R, int S, int stride, int pad, int dil, cudaStream_t stream);
 int dktb_nchw_to_nhwc(const float* x, float* out, int N, int C, int H, int W, cudaStream_t stream);
 
 /* BatchNorm2d statistics (train: per-episode batch stats from the conv partial sums + running-stat EMA,

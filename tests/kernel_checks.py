@@ -455,6 +455,12 @@ def check_conv2d(lib, dev, N=2, H=13, W=11, Cin=3, Cout=36, R=3, stride=2, pad=0
     lib.conv2d_wgrad(x_nhwc, gyd, out, dw, db, scratch, N, H, W, Cin, Cout, R, R, stride, pad, dil, relu, 0)
     _close(dw, wr.grad, rtol=1e-4, atol=1e-4, what="conv2d wgrad")
     _close(db, br.grad, rtol=1e-4, atol=1e-4, what="conv2d bgrad")
+    if not relu and Cin < 16 and lib.conv2d_mma_ok(32, 32):      # narrow-input forward (the ResNet stem)
+        wflat = torch.full((Cout, lib.conv2d_flat_k(Cin, R, R)), float("nan"), device=dev)
+        lib.conv2d_prep_flat_mma(w.to(dev), wflat, Cout, Cin, R, R, 0)
+        out3 = torch.full((N, Ho, Wo, Cout), float("nan"), device=dev)
+        lib.conv2d_fwd_flat_mma(x_nhwc, wflat, b.to(dev), out3, N, H, W, Cin, Cout, R, R, stride, pad, dil, 0)
+        _close(out3.cpu().permute(0, 3, 1, 2), ref.detach(), rtol=2e-5, atol=2e-5, what="conv2d fwd (flat mma)")
     if not relu and lib.conv2d_mma_ok(Cin, Cout):       # tensor-core variants (ResNet layers)
         wf = torch.empty(R * R, Cout, Cin, device=dev)
         wd = torch.empty(R * R, Cin, Cout, device=dev)
