@@ -353,6 +353,83 @@ struct CmWeights {
   }
 };
 
+// The same two operands fetched as 16-byte vectors (4 consecutive channels of one pixel / filter row per thread, two
+// per thread and chunk instead of eight scalars): valid whenever the channel count on the k axis is a multiple of 32,
+// i.e. MODE 0 and 1.  The tap of a chunk is tracked incrementally (gl_product asks for consecutive chunks).
+template <int MODE>
+struct CmPixels4 {
+  const float* src; const int4* tbl; ConvGeo g; int kc;
+  mutable int next_k0, tap, c0;
+  __device__ __forceinline__ void locate(int k0) const {
+    if (k0 == next_k0) {
+      c0 += GL_KC;
+      if (c0 == kc) { c0 = 0; ++tap; }
+    } else {
+      tap = k0 / kc;
+      c0 = k0 - tap * kc;
+    }
+    next_k0 = k0 + GL_KC;
+  }
+  __device__ __forceinline__ void fetch(float (&v)[8], int k0) const {
+    locate(k0);
+    const int r = tap / g.S, s = tap - r * g.S;
+    const int c = c0 + 4 * (threadIdx.x & 7);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int4 t = tbl[(threadIdx.x >> 3) + 32 * i];
+      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (MODE == 0) {
+        const int ih = t.y + r * g.dil, iw = t.z + s * g.dil;
+        if (t.w && (unsigned)ih < (unsigned)g.H && (unsigned)iw < (unsigned)g.W)
+          val = dktb_ld4(src + ((long)t.x + (long)ih * g.W + iw) * g.Cin + c);
+      } else {
+        const int th = t.y - r * g.dil, tw = t.z - s * g.dil;
+        if (g.stride == 1) {
+          if (t.w && (unsigned)th < (unsigned)g.Ho && (unsigned)tw < (unsigned)g.Wo)
+            val = dktb_ld4(src + ((long)t.x + (long)th * g.Wo + tw) * g.Cout + c);
+        } else if (t.w && th >= 0 && tw >= 0 && th % g.stride == 0 && tw % g.stride == 0) {
+          const int oh = th / g.stride, ow = tw / g.stride;
+          if (oh < g.Ho && ow < g.Wo) val = dktb_ld4(src + ((long)t.x + (long)oh * g.Wo + ow) * g.Cout + c);
+        }
+      }
+      v[4 * i] = val.x; v[4 * i + 1] = val.y; v[4 * i + 2] = val.z; v[4 * i + 3] = val.w;
+    }
+  }
+  __device__ __forceinline__ void store(float* sdst, const float (&v)[8]) const {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      dktb_st4(sdst + ((threadIdx.x >> 3) + 32 * i) * GL_LDK + 4 * (threadIdx.x & 7),
+               make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+  }
+};
+struct CmWeights4 {
+  const float* wt; int nn, n0, kc;
+  mutable int next_k0, tap, c0;
+  __device__ __forceinline__ void fetch(float (&v)[8], int k0) const {
+    if (k0 == next_k0) {
+      c0 += GL_KC;
+      if (c0 == kc) { c0 = 0; ++tap; }
+    } else {
+      tap = k0 / kc;
+      c0 = k0 - tap * kc;
+    }
+    next_k0 = k0 + GL_KC;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int n = n0 + (threadIdx.x >> 3) + 32 * i;
+      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n < nn) val = dktb_ld4(wt + ((long)tap * nn + n) * kc + c0 + 4 * (threadIdx.x & 7));
+      v[4 * i] = val.x; v[4 * i + 1] = val.y; v[4 * i + 2] = val.z; v[4 * i + 3] = val.w;
+    }
+  }
+  __device__ __forceinline__ void store(float* sdst, const float (&v)[8]) const {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      dktb_st4(sdst + ((threadIdx.x >> 3) + 32 * i) * GL_LDK + 4 * (threadIdx.x & 7),
+               make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+  }
+};
+
 // MODE 0: out[p][co] = bias[co] + sum_{tap,ci} x[p@tap][ci] wf[tap][co][ci]     (p over output pixels)
 // MODE 1: gx[p][ci]  =           sum_{tap,co} gy[p@tap][co] wd[tap][ci][co]     (p over input pixels)
 template <int MODE>
@@ -386,9 +463,15 @@ __global__ void __launch_bounds__(GL_THREADS, 2) conv2d_mma_kernel(const float* 
   __syncthreads();
   float acc[4][4];
   gl_zero(acc);
-  CmPixels<MODE> la{src, s_tbl, g, kc};
-  CmWeights lb{wt, nn, n0, kc};
-  gl_product<true>(acc, s_as, s_bs, la, lb, 0, MODE == 2 ? kc : g.R * g.S * kc);
+  if (MODE == 2) {
+    CmPixels<MODE> la{src, s_tbl, g, kc};
+    CmWeights lb{wt, nn, n0, kc};
+    gl_product<true>(acc, s_as, s_bs, la, lb, 0, kc);
+  } else {
+    CmPixels4<MODE> la{src, s_tbl, g, kc, -1, 0, 0};
+    CmWeights4 lb{wt, nn, n0, kc, -1, 0, 0};
+    gl_product<true>(acc, s_as, s_bs, la, lb, 0, g.R * g.S * kc);
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const long p = p0 + M::row(i);
@@ -452,6 +535,66 @@ struct CmWgradG {
     const int q = threadIdx.x & 63, kk = threadIdx.x >> 6;
 #pragma unroll
     for (int i = 0; i < 8; ++i) sdst[q * GL_LDK + kk + 4 * i] = v[i];
+  }
+};
+
+// 16-byte versions (channel counts multiples of 4): a thread fetches 4 consecutive channels of one pixel, twice per
+// chunk; lane = (channel-group parity, 16 pixels) makes the transposing shared-memory stores conflict-free.
+struct CmWgradX4 {
+  const float* x; ConvGeo g; int c0, r, s; long pbeg, pend;
+  mutable int n, oh, ow; mutable long pcur;
+  __device__ __forceinline__ void seek(long p) const {
+    pcur = p;
+    n = (int)(p / ((long)g.Ho * g.Wo));
+    const int rem = (int)(p - (long)n * g.Ho * g.Wo);
+    oh = rem / g.Wo;
+    ow = rem - oh * g.Wo;
+  }
+  __device__ __forceinline__ void fetch(float (&v)[8], int k0) const {
+    const int c = c0 + 4 * (2 * (threadIdx.x >> 5) + (threadIdx.x & 1));
+    int nn = n, hh = oh, ww = ow;
+    long p = pcur;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p < pend && c < g.Cin) {
+        const int ih = hh * g.stride - g.pad + r * g.dil, iw = ww * g.stride - g.pad + s * g.dil;
+        if ((unsigned)ih < (unsigned)g.H && (unsigned)iw < (unsigned)g.W)
+          val = dktb_ld4(x + (((long)nn * g.H + ih) * g.W + iw) * g.Cin + c);
+      }
+      v[4 * i] = val.x; v[4 * i + 1] = val.y; v[4 * i + 2] = val.z; v[4 * i + 3] = val.w;
+      p += 16;
+      ww += 16;
+      while (ww >= g.Wo) { ww -= g.Wo; if (++hh == g.Ho) { hh = 0; ++nn; } }
+    }
+    n = nn; oh = hh; ow = ww; pcur = p;
+  }
+  __device__ __forceinline__ void store(float* sdst, const float (&v)[8]) const {
+    const int q = 4 * (2 * (threadIdx.x >> 5) + (threadIdx.x & 1)), kk = (threadIdx.x & 31) >> 1;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sdst[(q + j) * GL_LDK + kk + 16 * i] = v[4 * i + j];
+  }
+};
+struct CmWgradG4 {
+  const float* gy; int Cout, c0; long pbeg, pend;
+  __device__ __forceinline__ void fetch(float (&v)[8], int k0) const {
+    const int c = c0 + 4 * (2 * (threadIdx.x >> 5) + (threadIdx.x & 1));
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const long p = pbeg + k0 + ((threadIdx.x & 31) >> 1) + 16 * i;
+      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p < pend && c < Cout) val = dktb_ld4(gy + p * Cout + c);
+      v[4 * i] = val.x; v[4 * i + 1] = val.y; v[4 * i + 2] = val.z; v[4 * i + 3] = val.w;
+    }
+  }
+  __device__ __forceinline__ void store(float* sdst, const float (&v)[8]) const {
+    const int q = 4 * (2 * (threadIdx.x >> 5) + (threadIdx.x & 1)), kk = (threadIdx.x & 31) >> 1;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sdst[(q + j) * GL_LDK + kk + 16 * i] = v[4 * i + j];
   }
 };
 
@@ -547,10 +690,17 @@ __global__ void __launch_bounds__(GL_THREADS, 2) conv2d_wgrad_mma_kernel(const f
   float acc[4][4];
   gl_zero(acc);
   if (pbeg < pend) {
-    CmWgradX la{x, g, ci0, r, s, pbeg, pend};
-    la.seek(pbeg + (threadIdx.x >> 6));
-    CmWgradG lb{gy, g.Cout, co0, pbeg, pend};
-    gl_product<true>(acc, s_as, s_bs, la, lb, 0, (int)(pend - pbeg));
+    if (g.Cin % 4 == 0 && g.Cout % 4 == 0) {
+      CmWgradX4 la{x, g, ci0, r, s, pbeg, pend};
+      la.seek(pbeg + ((threadIdx.x & 31) >> 1));
+      CmWgradG4 lb{gy, g.Cout, co0, pbeg, pend};
+      gl_product<true>(acc, s_as, s_bs, la, lb, 0, (int)(pend - pbeg));
+    } else {
+      CmWgradX la{x, g, ci0, r, s, pbeg, pend};
+      la.seek(pbeg + (threadIdx.x >> 6));
+      CmWgradG lb{gy, g.Cout, co0, pbeg, pend};
+      gl_product<true>(acc, s_as, s_bs, la, lb, 0, (int)(pend - pbeg));
+    }
   }
   float* o = partial + ((long)split * g.R * g.S + rs) * g.Cin * g.Cout;
 #pragma unroll

@@ -72,7 +72,8 @@ def test_gp_family(lib, kernel):
 @pytest.mark.parametrize("cfg", [dict(), dict(Cin=36, Cout=36, H=12, W=12), dict(Cin=5, Cout=70, R=1, stride=2, dil=1, relu=0),
                                  dict(Cin=3, Cout=20, R=7, stride=2, pad=3, dil=1, relu=0, H=17, W=15),
                                  dict(Cin=32, Cout=64, R=3, stride=1, pad=1, dil=1, relu=0, H=5, W=4, N=2),      # tensor-core tiles
-                                 dict(Cin=64, Cout=32, R=3, stride=2, pad=1, dil=1, relu=0, H=7, W=6, N=1)])
+                                 dict(Cin=64, Cout=32, R=3, stride=2, pad=1, dil=1, relu=0, H=7, W=6, N=1),
+                                 dict(Cin=18, Cout=10, R=1, stride=1, pad=0, dil=1, relu=0, H=6, W=5, N=1)])
 def test_conv2d_generic(lib, cfg):
     kc.check_conv2d(lib, DEV, **cfg)
 
