@@ -437,8 +437,8 @@ __global__ void __launch_bounds__(GL_THREADS, 2) conv2d_mma_kernel(const float* 
                                                                    const float* __restrict__ wt,
                                                                    const float* __restrict__ bias,
                                                                    float* __restrict__ dst, ConvGeo g) {
-  __shared__ __align__(16) float s_as[GL_T * GL_LDK];
-  __shared__ __align__(16) float s_bs[GL_T * GL_LDK];
+  __shared__ __align__(16) float s_as[2 * GL_PLANE];
+  __shared__ __align__(16) float s_bs[2 * GL_PLANE];
   __shared__ int4 s_tbl[GL_T];
   typedef GlMap<true> M;
   const int tid = threadIdx.x;
@@ -466,11 +466,11 @@ __global__ void __launch_bounds__(GL_THREADS, 2) conv2d_mma_kernel(const float* 
   if (MODE == 2) {
     CmPixels<MODE> la{src, s_tbl, g, kc};
     CmWeights lb{wt, nn, n0, kc};
-    gl_product<true>(acc, s_as, s_bs, la, lb, 0, kc);
+    gl_product_ps(acc, s_as, s_bs, la, lb, 0, kc);
   } else {
     CmPixels4<MODE> la{src, s_tbl, g, kc, -1, 0, 0};
     CmWeights4 lb{wt, nn, n0, kc, -1, 0, 0};
-    gl_product<true>(acc, s_as, s_bs, la, lb, 0, g.R * g.S * kc);
+    gl_product_ps(acc, s_as, s_bs, la, lb, 0, g.R * g.S * kc);
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -643,8 +643,8 @@ __global__ void __launch_bounds__(GL_THREADS, 2) conv2d_wgrad_flat_mma_kernel(co
                                                                               const float* __restrict__ gy,
                                                                               float* __restrict__ partial, ConvGeo g,
                                                                               int nsplit) {
-  __shared__ __align__(16) float s_as[GL_T * GL_LDK];
-  __shared__ __align__(16) float s_bs[GL_T * GL_LDK];
+  __shared__ __align__(16) float s_as[2 * GL_PLANE];
+  __shared__ __align__(16) float s_bs[2 * GL_PLANE];
   typedef GlMap<true> M;
   const int q0 = blockIdx.x * GL_T, co0 = blockIdx.y * GL_T, split = blockIdx.z;
   const int Q = g.R * g.S * g.Cin;
@@ -658,7 +658,7 @@ __global__ void __launch_bounds__(GL_THREADS, 2) conv2d_wgrad_flat_mma_kernel(co
     CmWgradXFlat la{x, g, q0, pbeg, pend};
     la.seek(pbeg + (threadIdx.x >> 6));
     CmWgradG lb{gy, g.Cout, co0, pbeg, pend};
-    gl_product<true>(acc, s_as, s_bs, la, lb, 0, (int)(pend - pbeg));
+    gl_product_ps(acc, s_as, s_bs, la, lb, 0, (int)(pend - pbeg));
   }
   float* o = partial + (long)split * Q * g.Cout;
 #pragma unroll
@@ -677,8 +677,8 @@ __global__ void __launch_bounds__(GL_THREADS, 2) conv2d_wgrad_mma_kernel(const f
                                                                          const float* __restrict__ gy,
                                                                          float* __restrict__ partial, ConvGeo g,
                                                                          int nsplit) {
-  __shared__ __align__(16) float s_as[GL_T * GL_LDK];
-  __shared__ __align__(16) float s_bs[GL_T * GL_LDK];
+  __shared__ __align__(16) float s_as[2 * GL_PLANE];
+  __shared__ __align__(16) float s_bs[2 * GL_PLANE];
   typedef GlMap<true> M;
   const int ci0 = blockIdx.x * GL_T, co0 = blockIdx.y * GL_T;
   const int rs = blockIdx.z / nsplit, split = blockIdx.z % nsplit;
@@ -694,12 +694,12 @@ __global__ void __launch_bounds__(GL_THREADS, 2) conv2d_wgrad_mma_kernel(const f
       CmWgradX4 la{x, g, ci0, r, s, pbeg, pend};
       la.seek(pbeg + ((threadIdx.x & 31) >> 1));
       CmWgradG4 lb{gy, g.Cout, co0, pbeg, pend};
-      gl_product<true>(acc, s_as, s_bs, la, lb, 0, (int)(pend - pbeg));
+      gl_product_ps(acc, s_as, s_bs, la, lb, 0, (int)(pend - pbeg));
     } else {
       CmWgradX la{x, g, ci0, r, s, pbeg, pend};
       la.seek(pbeg + (threadIdx.x >> 6));
       CmWgradG lb{gy, g.Cout, co0, pbeg, pend};
-      gl_product<true>(acc, s_as, s_bs, la, lb, 0, (int)(pend - pbeg));
+      gl_product_ps(acc, s_as, s_bs, la, lb, 0, (int)(pend - pbeg));
     }
   }
   float* o = partial + ((long)split * g.R * g.S + rs) * g.Cin * g.Cout;

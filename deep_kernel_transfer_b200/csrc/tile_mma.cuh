@@ -179,3 +179,109 @@ __device__ __forceinline__ void gl_zero(float (&acc)[4][4]) {
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 }
 
+// ---- pre-split variant: the staged chunk is kept as two planes (tf32 `hi`, exact remainder `lo`) written once by the
+// thread that fetched the element, and the fragments are read with ldmatrix (one x4 per 16 x 8 A fragment / per pair of
+// 8 x 8 B fragments: a tf32 fragment is four 8 x 8 matrices of 16-bit pairs).  Per 8-wide k-step a warp issues 6 ldmatrix
+// and 12 mma instead of 12 shared loads, 24 split operations and 12 mma.
+#define GL_PLANE (GL_T * GL_LDK)     // floats per staged plane
+
+// r[m] = 32-bit element (lane / 4, lane % 4) of the 8 x 4 matrix whose row `lane % 8` address is given by lane 8 m + lane % 8
+__device__ __forceinline__ void gl_ldmatrix_x4(unsigned (&r)[4], const float* row) {
+#ifdef DKTB_EMU
+  const int lane = threadIdx.x & 31;
+  const unsigned long long mine = (unsigned long long)(uintptr_t)row;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const unsigned long long p = __shfl_sync(0xffffffffu, mine, m * 8 + (lane >> 2));
+    r[m] = __float_as_uint(reinterpret_cast<const float*>((uintptr_t)p)[lane & 3]);
+  }
+#else
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+#endif
+}
+
+// acc += A x B^T over one 32-wide chunk held as planes a_hi / a_lo / b_hi / b_lo ([64][GL_LDK] each)
+__device__ __forceinline__ void gl_core_mma_ps(float (&acc)[4][4], const float* a_hi, const float* a_lo,
+                                               const float* b_hi, const float* b_lo) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // A: matrices (rows 0-7, k 0-3), (rows 8-15, k 0-3), (rows 0-7, k 4-7), (rows 8-15, k 4-7) -> a0..a3
+  const int a_off = ((warp >> 2) * 32 + ((lane >> 3) & 1) * 8 + (lane & 7)) * GL_LDK + (lane >> 4) * 4;
+  // B: matrices (cols 0-7, k 0-3), (cols 0-7, k 4-7), (cols 8-15, k 0-3), (cols 8-15, k 4-7) -> nf0.b0, nf0.b1, nf1.b0, nf1.b1
+  const int b_off = ((warp & 3) * 16 + (lane >> 4) * 8 + (lane & 7)) * GL_LDK + ((lane >> 3) & 1) * 4;
+  float part[2][2][4];
+#pragma unroll
+  for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+    for (int nf = 0; nf < 2; ++nf)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) part[mf][nf][q] = 0.f;
+#pragma unroll
+  for (int k = 0; k < GL_KC; k += 8) {
+    unsigned ah[2][4], al[2][4], bh4[4], bl4[4];
+#pragma unroll
+    for (int mf = 0; mf < 2; ++mf) {
+      gl_ldmatrix_x4(ah[mf], a_hi + a_off + mf * 16 * GL_LDK + k);
+      gl_ldmatrix_x4(al[mf], a_lo + a_off + mf * 16 * GL_LDK + k);
+    }
+    gl_ldmatrix_x4(bh4, b_hi + b_off + k);
+    gl_ldmatrix_x4(bl4, b_lo + b_off + k);
+#pragma unroll
+    for (int nf = 0; nf < 2; ++nf) {
+      const unsigned bh[2] = {bh4[2 * nf], bh4[2 * nf + 1]}, bl[2] = {bl4[2 * nf], bl4[2 * nf + 1]};
+#pragma unroll
+      for (int mf = 0; mf < 2; ++mf) {
+        dktb_mma_m16n8k8_tf32(part[mf][nf], al[mf], bh);
+        dktb_mma_m16n8k8_tf32(part[mf][nf], ah[mf], bl);
+        dktb_mma_m16n8k8_tf32(part[mf][nf], ah[mf], bh);
+      }
+    }
+  }
+#pragma unroll
+  for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+    for (int nf = 0; nf < 2; ++nf) {
+      acc[2 * mf][2 * nf] += part[mf][nf][0];
+      acc[2 * mf][2 * nf + 1] += part[mf][nf][1];
+      acc[2 * mf + 1][2 * nf] += part[mf][nf][2];
+      acc[2 * mf + 1][2 * nf + 1] += part[mf][nf][3];
+    }
+}
+
+// gl_product on split planes: as / bs hold [hi plane | lo plane] (2 * GL_PLANE floats each).  Accumulator ownership is
+// GlMap<true>.
+template <class LA, class LB>
+__device__ __forceinline__ void gl_product_ps(float (&acc)[4][4], float* as, float* bs, const LA& la, const LB& lb,
+                                              int kbeg, int kend) {
+  float ra[8], rb[8];
+  if (kbeg < kend) {
+    la.fetch(ra, kbeg);
+    lb.fetch(rb, kbeg);
+  }
+  for (int k0 = kbeg; k0 < kend; k0 += GL_KC) {
+    float hi[8], lo[8];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      hi[i] = __uint_as_float(__float_as_uint(ra[i]) & 0xFFFFE000u);
+      lo[i] = ra[i] - hi[i];
+    }
+    la.store(as, hi);
+    la.store(as + GL_PLANE, lo);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      hi[i] = __uint_as_float(__float_as_uint(rb[i]) & 0xFFFFE000u);
+      lo[i] = rb[i] - hi[i];
+    }
+    lb.store(bs, hi);
+    lb.store(bs + GL_PLANE, lo);
+    __syncthreads();
+    if (k0 + GL_KC < kend) {
+      la.fetch(ra, k0 + GL_KC);
+      lb.fetch(rb, k0 + GL_KC);
+    }
+    gl_core_mma_ps(acc, as, as + GL_PLANE, bs, bs + GL_PLANE);
+  }
+}
