@@ -20,7 +20,9 @@ def lib():
 
 
 def test_train_step_and_correct_match_oracle(lib):
-    model, oracle, worst = dkt_checks.check_train_step(lambda: backbone.ConvNet(4, image_size=32), torch.device("cpu"), lib=lib)
+    # one step here (the GPU twin, tests/test_dkt_gpu.py::test_train_step_small, runs two): keeps the CPU suite at ~5 minutes
+    model, oracle, worst = dkt_checks.check_train_step(lambda: backbone.ConvNet(4, image_size=32), torch.device("cpu"), lib=lib,
+                                                       steps=1)
     print(worst)
     dkt_checks.check_correct(model, oracle, torch.device("cpu"))
 
