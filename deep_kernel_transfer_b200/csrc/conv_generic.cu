@@ -255,21 +255,32 @@ __global__ void conv2d_wgrad_reduce_kernel(const float* __restrict__ partial, fl
   dw[((long)co * g.Cin + ci) * g.R * g.S + rs] = t;
 }
 
-// db[co] = sum_p gy[p][co] (masked by ReLU); one CTA per 64 channels, fixed order over pixel slices
+// db[co] = sum_p gy[p][co] (masked by ReLU): grid (64-channel groups, pixel slices) -> part[slice][co], then a
+// fixed-order sum over the slices (deterministic; one CTA per channel group alone left 140 SMs idle: 2 ms per layer).
 __global__ void __launch_bounds__(256) conv2d_bgrad_kernel(const float* __restrict__ gy, const float* __restrict__ yout,
-                                                           float* __restrict__ db, long npix, int Cout, int relu) {
+                                                           float* __restrict__ part, long npix, int Cout, int relu,
+                                                           int nslice) {
   __shared__ float s_red[4][64];
   const int c = blockIdx.x * 64 + threadIdx.x % 64, sl = threadIdx.x / 64;
   float t = 0.f;
   if (c < Cout)
-    for (long p = sl; p < npix; p += 4) {
+    for (long p = (long)blockIdx.y * 4 + sl; p < npix; p += 4L * nslice) {
       float v = gy[p * Cout + c];
       if (relu && !(yout[p * Cout + c] > 0.f)) v = 0.f;
       t += v;
     }
   s_red[sl][threadIdx.x % 64] = t;
   __syncthreads();
-  if (sl == 0 && c < Cout) db[c] = (s_red[0][threadIdx.x] + s_red[1][threadIdx.x]) + (s_red[2][threadIdx.x] + s_red[3][threadIdx.x]);
+  if (sl == 0 && c < Cout)
+    part[(long)blockIdx.y * Cout + c] =
+        (s_red[0][threadIdx.x] + s_red[1][threadIdx.x]) + (s_red[2][threadIdx.x] + s_red[3][threadIdx.x]);
+}
+__global__ void conv2d_bgrad_final_kernel(const float* __restrict__ part, float* __restrict__ db, int Cout, int nslice) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cout) return;
+  float t = 0.f;
+  for (int s = 0; s < nslice; ++s) t += part[(long)s * Cout + c];
+  db[c] = t;
 }
 
 // ------------------------------------------------------------------------------------- tensor-core variants (ResNet)
@@ -855,8 +866,14 @@ DKTB_EXPORT int dktb_conv2d_wgrad(const float* x, const float* gy, const float* 
   const long total = (long)R * S * Cin * Cout;
   DKTB_LAUNCH(conv2d_wgrad_reduce_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream,
               (const float*)scratch, dw, g, nsplit);
-  if (db != nullptr)
-    DKTB_LAUNCH(conv2d_bgrad_kernel, dim3((Cout + 63) / 64), dim3(256), 0, stream, gy, yout, db, npix, Cout, relu);
+  if (db != nullptr) {         // the weight-gradient partials are consumed: the scratch doubles as the slice buffer
+    long cap = (long)nsplit * R * S * Cin;
+    const int nslice = (int)(cap < 128 ? cap : 128);
+    DKTB_LAUNCH(conv2d_bgrad_kernel, dim3((Cout + 63) / 64, nslice), dim3(256), 0, stream, gy, yout, scratch, npix, Cout,
+                relu, nslice);
+    DKTB_LAUNCH(conv2d_bgrad_final_kernel, dim3((Cout + 127) / 128), dim3(128), 0, stream, (const float*)scratch, db, Cout,
+                nslice);
+  }
   return dktb_launch_status();
 }
 
