@@ -40,8 +40,8 @@ struct GpFitLargeArgs {
 };
 
 struct GlSmem {
-  float* as;      // [64][36]
-  float* bs;      // [64][36]
+  float* as;      // [2][64][36]
+  float* bs;      // [2][64][36]
   float* d;       // [64][65]  diagonal block / its Cholesky factor (shares the storage of t)
   float* w;       // [64][68]  inverse of the factor
   float* t;       // [64][68]  a tile handed from one product to the next
@@ -52,7 +52,7 @@ struct GlSmem {
   float* red;     // [32]
   int* fail;
 };
-#define GL_SMEM_FLOATS (2 * GL_T * GL_LDK + 2 * GL_T * GL_LDT + 4 * GL_MAXN + 32 + 4)
+#define GL_SMEM_FLOATS (4 * GL_T * GL_LDK + 2 * GL_T * GL_LDT + 4 * GL_MAXN + 32 + 4)
 
 __device__ __forceinline__ float gl_block_sum(float v, float* s_red) {
   v = dktb_warp_sum(v);
@@ -87,8 +87,8 @@ __global__ void __launch_bounds__(GL_THREADS, 2) gp_fit_large_kernel(GpFitLargeA
   DKTB_DYN_SMEM(float, smem);
   GlSmem sm;
   sm.as = smem;
-  sm.bs = sm.as + GL_T * GL_LDK;
-  sm.w = sm.bs + GL_T * GL_LDK;
+  sm.bs = sm.as + 2 * GL_T * GL_LDK;
+  sm.w = sm.bs + 2 * GL_T * GL_LDK;
   sm.t = sm.w + GL_T * GL_LDT;
   sm.d = sm.t;                                           // the diagonal block is dead once L_jj / W are written out
   sm.diag = sm.t + GL_T * GL_LDT;

@@ -150,25 +150,36 @@ struct GlCols {
   }
 };
 
-// acc += A-operand x B-operand over k in [kbeg, kend) (kbeg a multiple of 32), staged through as / bs ([64][36] floats each).
+// acc += A-operand x B-operand over k in [kbeg, kend) (kbeg a multiple of 32), staged through as / bs, each TWO chunks of
+// [64][36] floats: chunk c + 1 is written into the other half while chunk c is multiplied, so the loop needs one barrier
+// per chunk; chunk c + 2 is in flight in registers meanwhile.
 template <bool MMA, class LA, class LB>
 __device__ __forceinline__ void gl_product(float (&acc)[4][4], float* as, float* bs, const LA& la, const LB& lb,
                                            int kbeg, int kend) {
+  if (kbeg >= kend) return;
   float ra[8], rb[8];
-  if (kbeg < kend) {
-    la.fetch(ra, kbeg);
-    lb.fetch(rb, kbeg);
+  la.fetch(ra, kbeg);
+  lb.fetch(rb, kbeg);
+  __syncthreads();                         // whatever used the staging area before is done with it
+  la.store(as, ra);
+  lb.store(bs, rb);
+  if (kbeg + GL_KC < kend) {
+    la.fetch(ra, kbeg + GL_KC);
+    lb.fetch(rb, kbeg + GL_KC);
   }
-  for (int k0 = kbeg; k0 < kend; k0 += GL_KC) {
-    __syncthreads();                       // the previous chunk (or whatever used the staging area) is consumed
-    la.store(as, ra);
-    lb.store(bs, rb);
-    __syncthreads();
-    if (k0 + GL_KC < kend) {               // next chunk in flight while this one is multiplied
-      la.fetch(ra, k0 + GL_KC);
-      lb.fetch(rb, k0 + GL_KC);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = kbeg; k0 < kend; k0 += GL_KC, buf ^= 1) {
+    gl_tile<MMA>(acc, as + buf * GL_T * GL_LDK, GL_LDK, bs + buf * GL_T * GL_LDK, GL_LDK, GL_KC);
+    if (k0 + GL_KC < kend) {
+      la.store(as + (buf ^ 1) * GL_T * GL_LDK, ra);
+      lb.store(bs + (buf ^ 1) * GL_T * GL_LDK, rb);
+      if (k0 + 2 * GL_KC < kend) {
+        la.fetch(ra, k0 + 2 * GL_KC);
+        lb.fetch(rb, k0 + 2 * GL_KC);
+      }
     }
-    gl_tile<MMA>(acc, as, GL_LDK, bs, GL_LDK, GL_KC);
+    __syncthreads();
   }
 }
 
