@@ -268,58 +268,77 @@ DKTB_EXPORT int dktb_gp_reduce(const float* loss_terms, const float* dhyper, flo
 
 // ------------------------------------------------------------------------------------------------
 // gram_bwd: dZ[e][n][d] = scale * sum_m (S[n][m] + S[m][n]) Z[e][m][d],  S = sum_c W[e][c]
-// grid (ceil(D/64), ceil(N/32), E); 256 threads: (ty: 2 rows) x (tx: 4 columns)
+// grid (d groups, ceil(N/32), E); 256 threads: (ty: 2 rows) x (tx: 4 columns).  The symmetrised 32-row block of S is
+// built ONCE per CTA in shared memory (it was rebuilt for every 64-wide slice of D before: the class sum and its
+// transposed reads dominated the kernel), then the CTA walks its share of the D / 64 slices.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gram_bwd_kernel(const float* __restrict__ w, const float* __restrict__ z,
-                                                       float* __restrict__ dz, int C, int N, int D, float scale) {
-  __shared__ float s_s[32][33];
-  __shared__ __align__(16) float s_z[32][64];
+                                                       float* __restrict__ dz, int C, int N, int D, float scale,
+                                                       int Np) {
+  DKTB_DYN_SMEM(float, smem);
+  float* s_s = smem;                                   // [32][Np + 1]
+  float* s_z = smem + ((32 * (Np + 1) + 3) & ~3);      // [32][64]
   const int e = blockIdx.z;
-  const int n0 = blockIdx.y * 32, d0 = blockIdx.x * 64;
+  const int n0 = blockIdx.y * 32;
   const int tid = threadIdx.x;
   const int ty = tid / 16, tx = tid % 16;
   const float* we = w + (long)e * C * N * N;
   const float* ze = z + (long)e * N * D;
-  float acc[2][4];
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int m0 = 0; m0 < N; m0 += 32) {
-    __syncthreads();
-    for (int i = tid; i < 32 * 32; i += 256) {
-      const int r = i / 32, cc = i % 32;
-      const int n = n0 + r, m = m0 + cc;
+  for (int i = tid; i < 32 * Np; i += 256) {
+    const int r = i / Np, m = i - r * Np;
+    const int n = n0 + r;
+    float v = 0.f;
+    if (n < N && m < N)
+      for (int c = 0; c < C; ++c) v += we[((long)c * N + n) * N + m];
+    s_s[r * (Np + 1) + m] = v;
+  }
+  __syncthreads();
+  for (int i = tid; i < 32 * Np; i += 256) {            // + transpose: lanes along the row index -> coalesced reads
+    const int m = i / 32, r = i - m * 32;
+    const int n = n0 + r;
+    if (n < N && m < N) {
       float v = 0.f;
-      if (n < N && m < N)
-        for (int c = 0; c < C; ++c) v += we[((long)c * N + n) * N + m] + we[((long)c * N + m) * N + n];
-      s_s[r][cc] = v;
-    }
-    for (int i = tid; i < 32 * 64; i += 256) {
-      const int r = i / 64, cc = i % 64;
-      const int m = m0 + r, d = d0 + cc;
-      s_z[r][cc] = (m < N && d < D) ? ze[(long)m * D + d] : 0.f;
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int k = 0; k < 32; ++k) {
-      const float a0 = s_s[ty * 2][k], a1 = s_s[ty * 2 + 1][k];
-      const float4 b = dktb_ld4(&s_z[k][tx * 4]);
-      acc[0][0] = fmaf(a0, b.x, acc[0][0]); acc[0][1] = fmaf(a0, b.y, acc[0][1]);
-      acc[0][2] = fmaf(a0, b.z, acc[0][2]); acc[0][3] = fmaf(a0, b.w, acc[0][3]);
-      acc[1][0] = fmaf(a1, b.x, acc[1][0]); acc[1][1] = fmaf(a1, b.y, acc[1][1]);
-      acc[1][2] = fmaf(a1, b.z, acc[1][2]); acc[1][3] = fmaf(a1, b.w, acc[1][3]);
+      for (int c = 0; c < C; ++c) v += we[((long)c * N + m) * N + n];
+      s_s[r * (Np + 1) + m] += v;
     }
   }
+  const int nslice = (D + 63) / 64;
   float* o = dz + (long)e * N * D;
+  for (int sl = blockIdx.x; sl < nslice; sl += gridDim.x) {
+    const int d0 = sl * 64;
+    float acc[2][4];
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int n = n0 + ty * 2 + i;
-    if (n >= N) continue;
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int d = d0 + tx * 4 + j;
-      if (d < D) o[(long)n * D + d] = scale * acc[i][j];
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int m0 = 0; m0 < N; m0 += 32) {
+      __syncthreads();
+      for (int i = tid; i < 32 * 64; i += 256) {
+        const int r = i / 64, cc = i % 64;
+        const int m = m0 + r, d = d0 + cc;
+        s_z[r * 64 + cc] = (m < N && d < D) ? ze[(long)m * D + d] : 0.f;
+      }
+      __syncthreads();
+      const float* sa = s_s + (ty * 2) * (Np + 1) + m0;
+#pragma unroll 8
+      for (int k = 0; k < 32; ++k) {
+        const float a0 = sa[k], a1 = sa[Np + 1 + k];
+        const float4 b = dktb_ld4(&s_z[k * 64 + tx * 4]);
+        acc[0][0] = fmaf(a0, b.x, acc[0][0]); acc[0][1] = fmaf(a0, b.y, acc[0][1]);
+        acc[0][2] = fmaf(a0, b.z, acc[0][2]); acc[0][3] = fmaf(a0, b.w, acc[0][3]);
+        acc[1][0] = fmaf(a1, b.x, acc[1][0]); acc[1][1] = fmaf(a1, b.y, acc[1][1]);
+        acc[1][2] = fmaf(a1, b.z, acc[1][2]); acc[1][3] = fmaf(a1, b.w, acc[1][3]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int n = n0 + ty * 2 + i;
+      if (n >= N) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int d = d0 + tx * 4 + j;
+        if (d < D) o[(long)n * D + d] = scale * acc[i][j];
+      }
     }
   }
 }
@@ -327,7 +346,15 @@ __global__ void __launch_bounds__(256) gram_bwd_kernel(const float* __restrict__
 DKTB_EXPORT int dktb_gram_bwd(const float* w, const float* z, float* dz, int E, int C, int N, int D, float scale,
                               cudaStream_t stream) {
   DKTB_CHECK_ARG(w && z && dz && E > 0 && C > 0 && N > 0 && D > 0 && E <= 65535);
-  DKTB_LAUNCH(gram_bwd_kernel, dim3((D + 63) / 64, (N + 31) / 32, E), dim3(256), 0, stream, w, z, dz, C, N, D, scale);
+  const int Np = (N + 31) / 32 * 32;
+  const size_t smem = (size_t)(((32 * (Np + 1) + 3) & ~3) + 32 * 64) * sizeof(float);
+  DKTB_CHECK_ARG(smem <= 200 * 1024);
+  // enough CTAs for two per SM, at most one per 64-wide slice of D
+  const int rows = (N + 31) / 32, nslice = (D + 63) / 64;
+  int groups = (2 * 148 + rows * E - 1) / (rows * E);
+  groups = groups < 1 ? 1 : (groups > nslice ? nslice : groups);
+  cudaFuncSetAttribute(gram_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  DKTB_LAUNCH(gram_bwd_kernel, dim3(groups, rows, E), dim3(256), smem, stream, w, z, dz, C, N, D, scale, Np);
   return dktb_launch_status();
 }
 
