@@ -495,6 +495,138 @@ __global__ void __launch_bounds__(GL_THREADS, 2) conv2d_mma_kernel(const float* 
   }
 }
 
+// dgrad through a stride: an input pixel only meets the taps whose offset has its parity class, (ih + pad - r dil) % stride
+// == 0 -- a quarter of a 3x3 filter on average at stride 2, none at all for three of the four classes of a 1x1.  So the
+// input pixels are tiled class by class ((ih + pad) % stride, (iw + pad) % stride) and each CTA runs only its class's
+// taps (the generic kernel multiplied zeros for the rest: 4x the work on the heaviest dgrad launches of a ResNet).
+struct CmStrideClasses {
+  int tile_begin[17];            // first tile of each class (stride <= 4), [nclass] = total
+};
+struct CmPixelsS4 {
+  const float* src; const int4* tbl; const int* taps; ConvGeo g;
+  mutable int next_k0, ti, c0;
+  __device__ __forceinline__ void fetch(float (&v)[8], int k0) const {
+    if (k0 == next_k0) {
+      c0 += GL_KC;
+      if (c0 == g.Cout) { c0 = 0; ++ti; }
+    } else {
+      ti = k0 / g.Cout;
+      c0 = k0 - ti * g.Cout;
+    }
+    next_k0 = k0 + GL_KC;
+    const int tap = taps[ti];
+    const int r = tap / g.S, s = tap - r * g.S;
+    const int c = c0 + 4 * (threadIdx.x & 7);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int4 t = tbl[(threadIdx.x >> 3) + 32 * i];
+      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int th = t.y - r * g.dil, tw = t.z - s * g.dil;          // multiples of the stride by construction
+      if (t.w && th >= 0 && tw >= 0) {
+        const int oh = th / g.stride, ow = tw / g.stride;
+        if (oh < g.Ho && ow < g.Wo) val = dktb_ld4(src + ((long)t.x + (long)oh * g.Wo + ow) * g.Cout + c);
+      }
+      v[4 * i] = val.x; v[4 * i + 1] = val.y; v[4 * i + 2] = val.z; v[4 * i + 3] = val.w;
+    }
+  }
+  __device__ __forceinline__ void store(float* sdst, const float (&v)[8]) const {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      dktb_st4(sdst + ((threadIdx.x >> 3) + 32 * i) * GL_LDK + 4 * (threadIdx.x & 7),
+               make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+  }
+};
+struct CmWeightsS4 {
+  const float* wt; const int* taps; int nn, n0, kc;
+  mutable int next_k0, ti, c0;
+  __device__ __forceinline__ void fetch(float (&v)[8], int k0) const {
+    if (k0 == next_k0) {
+      c0 += GL_KC;
+      if (c0 == kc) { c0 = 0; ++ti; }
+    } else {
+      ti = k0 / kc;
+      c0 = k0 - ti * kc;
+    }
+    next_k0 = k0 + GL_KC;
+    const int tap = taps[ti];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int n = n0 + (threadIdx.x >> 3) + 32 * i;
+      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n < nn) val = dktb_ld4(wt + ((long)tap * nn + n) * kc + c0 + 4 * (threadIdx.x & 7));
+      v[4 * i] = val.x; v[4 * i + 1] = val.y; v[4 * i + 2] = val.z; v[4 * i + 3] = val.w;
+    }
+  }
+  __device__ __forceinline__ void store(float* sdst, const float (&v)[8]) const {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      dktb_st4(sdst + ((threadIdx.x >> 3) + 32 * i) * GL_LDK + 4 * (threadIdx.x & 7),
+               make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+  }
+};
+
+__global__ void __launch_bounds__(GL_THREADS, 2) conv2d_dgrad_strided_mma_kernel(const float* __restrict__ gy,
+                                                                                 const float* __restrict__ wd,
+                                                                                 float* __restrict__ gx, ConvGeo g,
+                                                                                 CmStrideClasses cls) {
+  __shared__ __align__(16) float s_as[2 * GL_PLANE];
+  __shared__ __align__(16) float s_bs[2 * GL_PLANE];
+  __shared__ int4 s_tbl[GL_T];
+  __shared__ int s_out[GL_T];
+  __shared__ int s_taps[64];
+  __shared__ int s_ntaps;
+  typedef GlMap<true> M;
+  const int tid = threadIdx.x, st = g.stride;
+  int c = 0;
+  while (c + 1 < st * st && (int)blockIdx.x >= cls.tile_begin[c + 1]) ++c;
+  const int ca = c / st, cb = c - ca * st;                     // (ih + pad) % st, (iw + pad) % st of this CTA's pixels
+  const int fh = ((ca - g.pad) % st + st) % st, fw = ((cb - g.pad) % st + st) % st;     // first row / column of the class
+  const int Ha = fh < g.H ? (g.H - fh + st - 1) / st : 0, Wb = fw < g.W ? (g.W - fw + st - 1) / st : 0;
+  const long npix = (long)g.N * Ha * Wb;
+  const long q0 = (long)((int)blockIdx.x - cls.tile_begin[c]) * GL_T;
+  const int n0 = blockIdx.y * GL_T;
+  if (tid < GL_T) {
+    const long q = q0 + tid;
+    int4 t = make_int4(0, 0, 0, 0);
+    int o = -1;
+    if (q < npix) {
+      const int n = (int)(q / ((long)Ha * Wb));
+      const int rem = (int)(q - (long)n * Ha * Wb);
+      const int a = rem / Wb, b = rem - a * Wb;
+      const int ih = fh + a * st, iw = fw + b * st;
+      t = make_int4(n * g.Ho * g.Wo, ih + g.pad, iw + g.pad, 1);
+      o = (n * g.H + ih) * g.W + iw;
+    }
+    s_tbl[tid] = t;
+    s_out[tid] = o;
+  }
+  if (tid == 0) {
+    int nt = 0;
+    for (int r = 0; r < g.R; ++r)
+      for (int s = 0; s < g.S; ++s)
+        if ((r * g.dil) % st == ca && (s * g.dil) % st == cb) s_taps[nt++] = r * g.S + s;
+    s_ntaps = nt;
+  }
+  __syncthreads();
+  float acc[4][4];
+  gl_zero(acc);
+  {
+    CmPixelsS4 la{gy, s_tbl, s_taps, g, -1, 0, 0};
+    CmWeightsS4 lb{wd, s_taps, g.Cin, n0, g.Cout, -1, 0, 0};
+    gl_product_ps(acc, s_as, s_bs, la, lb, 0, s_ntaps * g.Cout);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int o = s_out[M::row(i)];
+    if (o < 0) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + M::col(j);
+      if (n < g.Cin) gx[(long)o * g.Cin + n] = acc[i][j];
+    }
+  }
+}
+
 // wgrad: partial[split][tap][ci][co] = sum_{p in split} x[p@tap][ci] gy[p][co]; k = output pixels, both operands read
 // with the channel along the lanes (coalesced) and the pixel coordinates advanced incrementally from chunk to chunk.
 struct CmWgradX {
@@ -812,6 +944,21 @@ DKTB_EXPORT int dktb_conv2d_dgrad_mma(const float* gy, const float* wd, float* g
   const ConvGeo g = make_geo(N, H, W, Cin, Cout, R, S, stride, pad, dil);
   DKTB_CHECK_ARG(g.Ho > 0 && g.Wo > 0 && (long)N * H * W < 2147483647L);
   const long npix = (long)N * H * W;
+  if (stride > 1 && stride <= 4 && R * S <= 64) {        // class-by-class tiles: only the taps a pixel can meet
+    CmStrideClasses cls;
+    int tiles = 0;
+    for (int c = 0; c < stride * stride; ++c) {
+      const int ca = c / stride, cb = c % stride;
+      const int fh = ((ca - pad) % stride + stride) % stride, fw = ((cb - pad) % stride + stride) % stride;
+      const int Ha = fh < H ? (H - fh + stride - 1) / stride : 0, Wb = fw < W ? (W - fw + stride - 1) / stride : 0;
+      cls.tile_begin[c] = tiles;
+      tiles += (int)(((long)N * Ha * Wb + GL_T - 1) / GL_T);
+    }
+    for (int c = stride * stride; c < 17; ++c) cls.tile_begin[c] = tiles;
+    DKTB_LAUNCH(conv2d_dgrad_strided_mma_kernel, dim3((unsigned)tiles, (Cin + GL_T - 1) / GL_T), dim3(GL_THREADS), 0,
+                stream, gy, wd, gx, g, cls);
+    return dktb_launch_status();
+  }
   DKTB_LAUNCH(conv2d_mma_kernel<1>, dim3((unsigned)((npix + GL_T - 1) / GL_T), (Cin + GL_T - 1) / GL_T),
               dim3(GL_THREADS), 0, stream, gy, wd, (const float*)nullptr, gx, g);
   return dktb_launch_status();

@@ -73,7 +73,8 @@ def test_gp_family(lib, kernel):
                                  dict(Cin=3, Cout=20, R=7, stride=2, pad=3, dil=1, relu=0, H=17, W=15),
                                  dict(Cin=32, Cout=64, R=3, stride=1, pad=1, dil=1, relu=0, H=5, W=4, N=2),      # tensor-core tiles
                                  dict(Cin=64, Cout=32, R=3, stride=2, pad=1, dil=1, relu=0, H=7, W=6, N=1),
-                                 dict(Cin=18, Cout=10, R=1, stride=1, pad=0, dil=1, relu=0, H=6, W=5, N=1)])
+                                 dict(Cin=18, Cout=10, R=1, stride=1, pad=0, dil=1, relu=0, H=6, W=5, N=1),
+                                 dict(Cin=32, Cout=12, R=3, stride=2, pad=2, dil=2, relu=0, H=7, W=5, N=1)])
 def test_conv2d_generic(lib, cfg):
     kc.check_conv2d(lib, DEV, **cfg)
 

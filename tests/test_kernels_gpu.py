@@ -98,7 +98,9 @@ def test_gp_family(lib, kernel):
                                  dict(Cin=64, Cout=128, R=1, stride=2, pad=0, dil=1, relu=0, H=56, W=56, N=3),
                                  dict(Cin=256, Cout=512, R=3, stride=2, pad=1, dil=1, relu=0, H=14, W=14, N=4),
                                  dict(Cin=512, Cout=512, R=3, stride=1, pad=1, dil=1, relu=0, H=7, W=7, N=6),
-                                 dict(Cin=256, Cout=64, R=1, stride=1, pad=0, dil=1, relu=0, H=56, W=56, N=2)])  # bottleneck 1x1
+                                 dict(Cin=256, Cout=64, R=1, stride=1, pad=0, dil=1, relu=0, H=56, W=56, N=2),   # bottleneck 1x1
+                                 dict(Cin=32, Cout=48, R=3, stride=1, pad=2, dil=2, relu=0, H=11, W=9, N=2),     # dilation, ragged tiles
+                                 dict(Cin=96, Cout=64, R=3, stride=2, pad=1, dil=1, relu=0, H=15, W=13, N=3)])   # odd sizes through a stride
 def test_conv2d_generic(lib, cfg):
     kc.check_conv2d(lib, DEV, **cfg)
 
