@@ -990,7 +990,7 @@ DKTB_EXPORT int dktb_conv2d_dgrad(const float* gy, const float* yout, const floa
 
 DKTB_EXPORT int dktb_conv2d_wgrad_nsplit(long npix) {
   long n = npix / 2048;
-  return (int)(n < 1 ? 1 : (n > 64 ? 64 : n));
+  return (int)(n < 1 ? 1 : (n > 98 ? 98 : n));     // 3 x 98 (stem) and 9 x 98 (3x3 layers) CTAs are whole waves of 2 x 148
 }
 
 // dw [Cout,Cin,R,S], db [Cout] (nullable); scratch: nsplit*R*S*Cin*Cout floats, nsplit = dktb_conv2d_wgrad_nsplit(N*Ho*Wo)
