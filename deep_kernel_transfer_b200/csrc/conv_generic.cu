@@ -871,8 +871,13 @@ DKTB_EXPORT int dktb_conv2d_out_size(int H, int R, int stride, int pad, int dil)
 }
 
 static bool conv2d_use_mma() {
+#ifdef DKTB_EMU      // tests switch it per test case (the emulated tensor-core tiles are slow at ResNet sizes)
+  const char* v = getenv("DKTB_RESNET_CONV");
+  return !(v && v[0] == 'f');
+#else
   static const bool on = [] { const char* v = getenv("DKTB_RESNET_CONV"); return !(v && v[0] == 'f'); }();   // "fp32": CUDA cores
   return on;
+#endif
 }
 
 // 1 if dktb_conv2d_fwd_mma / dktb_conv2d_dgrad_mma serve this layer (reduction widths multiples of 32)

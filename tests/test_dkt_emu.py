@@ -65,14 +65,18 @@ def test_regression_matches_oracle(lib):
 
 
 @pytest.mark.slow
-def test_resnet10_train_step_matches_oracle(lib):
+def test_resnet10_train_step_matches_oracle(lib, monkeypatch):
+    # engine / tape logic on the CUDA-core convolutions: the shuffle-emulated tensor-core tiles take hours at this size
+    # (they are covered tile by tile in test_kernels_emu.py and end to end on the GPU)
+    monkeypatch.setenv("DKTB_RESNET_CONV", "fp32")
     dkt_checks.check_train_step_arch("ResNet10", backbone.ResNet10, torch.device("cpu"), image_size=32, lib=lib)
 
 
 @pytest.mark.slow
-def test_resnet10_same_branch(lib):
+def test_resnet10_same_branch(lib, monkeypatch):
     """Backbone forward / backward of the tape engine vs fp64 on the device's own gate pattern (bottleneck variant is
     covered on the GPU at 224x224)."""
+    monkeypatch.setenv("DKTB_RESNET_CONV", "fp32")
     stats = dkt_checks.check_resnet_same_branch("ResNet10", torch.device("cpu"), 32, lib=lib)
     assert stats["gates"] > 0
 
