@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(GL_THREADS, 2) conv2d_mma_kernel(const float* 
   gl_zero(acc);
   if (MODE == 2) {
     CmPixels<MODE> la{src, s_tbl, g, kc};
-    CmWeights lb{wt, nn, n0, kc};
+    CmWeights4 lb{wt, nn, n0, kc, -1, 0, 0};              // wflat rows are kc = Kp floats: one "tap" of width Kp
     gl_product_ps(acc, s_as, s_bs, la, lb, 0, kc);
   } else {
     CmPixels4<MODE> la{src, s_tbl, g, kc, -1, 0, 0};
@@ -800,8 +800,13 @@ __global__ void __launch_bounds__(GL_THREADS, 2) conv2d_wgrad_flat_mma_kernel(co
   if (pbeg < pend) {
     CmWgradXFlat la{x, g, q0, pbeg, pend};
     la.seek(pbeg + (threadIdx.x >> 6));
-    CmWgradG lb{gy, g.Cout, co0, pbeg, pend};
-    gl_product_ps(acc, s_as, s_bs, la, lb, 0, (int)(pend - pbeg));
+    if (g.Cout % 4 == 0) {
+      CmWgradG4 lb{gy, g.Cout, co0, pbeg, pend};
+      gl_product_ps(acc, s_as, s_bs, la, lb, 0, (int)(pend - pbeg));
+    } else {
+      CmWgradG lb{gy, g.Cout, co0, pbeg, pend};
+      gl_product_ps(acc, s_as, s_bs, la, lb, 0, (int)(pend - pbeg));
+    }
   }
   float* o = partial + (long)split * Q * g.Cout;
 #pragma unroll
