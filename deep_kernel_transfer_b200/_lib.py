@@ -54,6 +54,7 @@ SIGNATURES = {
     "dktb_gp_large_work_floats": ("iii", ctypes.c_long),
     "dktb_gp_fit_large": ("plplppppppppppffiiis", ctypes.c_int),
     "dktb_gp_reduce": ("ppppiis", ctypes.c_int),
+    "dktb_gp_info_accumulate": ("ppis", ctypes.c_int),
     "dktb_gram_bwd": ("pppiiiifs", ctypes.c_int),
     "dktb_gp_predict": ("plpppppiiiis", ctypes.c_int),
     "dktb_center_rows": ("pppiiiis", ctypes.c_int),
@@ -137,6 +138,7 @@ class DktbLib:
             if len(args) != len(s):
                 raise TypeError("%s expects %d arguments, got %d" % (key, len(s), len(args)))
             conv = []
+            dev = None
             for ch, a in zip(s, args):
                 if ch == "p":
                     if a is None:
@@ -144,6 +146,12 @@ class DktbLib:
                     elif isinstance(a, torch.Tensor):
                         if not a.is_contiguous():
                             raise DktbError("%s: non-contiguous tensor argument" % key)
+                        if a.is_cuda:
+                            # raw pointers carry no device: every tensor of one call must live on the same GPU
+                            if dev is None:
+                                dev = a.device
+                            elif a.device != dev:
+                                raise DktbError("%s: tensor arguments on different devices (%s, %s)" % (key, dev, a.device))
                         conv.append(ctypes.c_void_p(a.data_ptr()))
                     else:
                         conv.append(ctypes.c_void_p(int(a)))
@@ -153,7 +161,12 @@ class DktbLib:
                     conv.append(float(a))
                 else:
                     conv.append(int(a))
-            r = fn(*conv)
+            if dev is not None and dev.index != torch.cuda.current_device():
+                # launch (and cudaFuncSetAttribute) on the tensors' device, not on the thread's current one
+                with torch.cuda.device(dev):
+                    r = fn(*conv)
+            else:
+                r = fn(*conv)
             if s.endswith("s") and r != 0:
                 raise DktbError("%s failed with status %d (%s)" % (
                     key, r, "bad argument" if r < 0 else "CUDA error"))

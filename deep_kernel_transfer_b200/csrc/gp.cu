@@ -77,11 +77,12 @@ struct GpFitArgs {
   float* alpha;              // [E][C][N]
   float* linv;               // optional [E][C][N][N] (L^-1, lower) for predictive variances
   float* loss_terms;         // [E][C] : -log p_c / (N*C)
-  int* info;                 // [E][C] : 0 or 1-based index of the first non-positive pivot
+  int* info;                 // [E][C] : 0 ok; -k ok after the k-th jitter retry; > 0 = 1-based index of the first
+                             //          non-positive pivot of the LAST attempt (not positive definite)
   float* dkbase;             // optional [E][C][N][N] : grad_scale * dLoss/dKb_c
   float* dhyper;             // optional [E][C][3] : grad_scale * d/d(raw_outputscale, constant, raw_noise)
   float grad_scale;
-  float jitter;              // added to the diagonal (psd_safe_cholesky retry value; 0 on the first try)
+  float jitter;              // psd_safe_cholesky retry base: attempts add 0, j, 10 j, 100 j to the diagonal (0: one try)
   int N, C;
 };
 
@@ -115,47 +116,66 @@ __global__ void __launch_bounds__(256) gp_fit_kernel(GpFitArgs p) {
   const float mconst = p.constant[c];
   const float* kb = p.kbase + ((long)e * (p.kbase_class_stride ? C : 1)) * N * N + (long)c * p.kbase_class_stride;
   const float* yv = p.y + (long)e * p.y_episode_stride + (long)c * N;
-  if (tid == 0) s_fail = 0;
-  for (int i = tid; i < N * N; i += nthr) {
-    const int r = i / N, k = i % N;
-    float v = s * kb[i];
-    if (r == k) v += noise + p.jitter;
-    A[r * LD + k] = v;
-    X[r * LD + k] = 0.f;
-  }
   for (int i = tid; i < N; i += nthr) s_r[i] = yv[i] - mconst;
-  __syncthreads();
-  // ---- Cholesky, left-looking by columns (N <= 256: rows i = tid, tid + nthr, ...)
-  for (int j = 0; j < N; ++j) {
-    float t[2] = {0.f, 0.f};
-    int cnt = 0;
-    for (int i = j + tid; i < N; i += nthr, ++cnt) {
-      float acc = A[i * LD + j];
-      const float* ai = A + i * LD;
-      const float* aj = A + j * LD;
-      for (int k = 0; k < j; ++k) acc = fmaf(-ai[k], aj[k], acc);
-      if (cnt < 2) t[cnt] = acc;
-      if (i == j) A[j * LD + j] = acc;      // raw pivot; only this thread touches A[j][j]
+  // GPyTorch's psd_safe_cholesky (the reference relies on it, README.md:27): plain factorisation first; if a pivot is
+  // not positive, start over with 1e-6, 1e-5, 1e-4 (fp32 schedule: jitter * 10^i) added to the diagonal of K~
+  const int attempts = p.jitter > 0.f ? 4 : 1;
+  int attempt = 0;
+  for (;; ++attempt) {
+    const float jit = attempt == 0 ? 0.f : p.jitter * (attempt == 1 ? 1.f : attempt == 2 ? 10.f : 100.f);
+    if (tid == 0) s_fail = 0;
+    for (int i = tid; i < N * N; i += nthr) {
+      const int r = i / N, k = i % N;
+      float v = s * kb[i];
+      if (r == k) v += noise + jit;
+      A[r * LD + k] = v;
+      X[r * LD + k] = 0.f;
     }
     __syncthreads();
-    const float piv = A[j * LD + j];
-    if (!(piv > 0.f)) {                      // uniform: every thread reads the same pivot
-      if (tid == 0) s_fail = j + 1;
-      break;
-    }
-    const float d = sqrtf(piv), invd = 1.f / d;
-    cnt = 0;
-    for (int i = j + tid; i < N; i += nthr, ++cnt) {
-      if (i == j) s_diag[j] = d;
-      else A[i * LD + j] = t[cnt] * invd;
+    // ---- Cholesky, left-looking by columns (N <= 256: rows i = tid, tid + nthr, ...)
+    for (int j = 0; j < N; ++j) {
+      float t[2] = {0.f, 0.f};
+      int cnt = 0;
+      for (int i = j + tid; i < N; i += nthr, ++cnt) {
+        float acc = A[i * LD + j];
+        const float* ai = A + i * LD;
+        const float* aj = A + j * LD;
+        for (int k = 0; k < j; ++k) acc = fmaf(-ai[k], aj[k], acc);
+        if (cnt < 2) t[cnt] = acc;
+        if (i == j) A[j * LD + j] = acc;      // raw pivot; only this thread touches A[j][j]
+      }
+      __syncthreads();
+      const float piv = A[j * LD + j];
+      if (!(piv > 0.f)) {                      // uniform: every thread reads the same pivot
+        if (tid == 0) s_fail = j + 1;
+        break;
+      }
+      const float d = sqrtf(piv), invd = 1.f / d;
+      cnt = 0;
+      for (int i = j + tid; i < N; i += nthr, ++cnt) {
+        if (i == j) s_diag[j] = d;
+        else A[i * LD + j] = t[cnt] * invd;
+      }
+      __syncthreads();
     }
     __syncthreads();
+    if (s_fail == 0 || attempt + 1 >= attempts) break;
+    __syncthreads();                           // everyone has read s_fail before the next attempt resets it
   }
-  __syncthreads();
   const int fail = s_fail;
-  if (tid == 0) p.info[(long)e * C + c] = fail;
-  if (fail) {                                // leave NaNs so a failed system cannot be mistaken for a result
-    if (tid == 0) p.loss_terms[(long)e * C + c] = nanf("");
+  if (tid == 0) p.info[(long)e * C + c] = fail ? fail : -attempt;
+  if (fail) {
+    // not positive definite even with jitter: NaN loss, and ZERO gradients / alpha so that nothing stale from an
+    // earlier step can reach the optimiser before the host raises (the reference raises right here)
+    if (tid == 0) {
+      p.loss_terms[(long)e * C + c] = nanf("");
+      if (p.dhyper) { float* o = p.dhyper + ((long)e * C + c) * 3; o[0] = o[1] = o[2] = 0.f; }
+    }
+    for (int k = tid; k < N; k += nthr) p.alpha[((long)e * C + c) * N + k] = 0.f;
+    if (p.dkbase) {
+      float* dk0 = p.dkbase + ((long)e * C + c) * N * N;
+      for (int i = tid; i < N * N; i += nthr) dk0[i] = 0.f;
+    }
     return;
   }
   // ---- X = L^-1 : thread c0 owns column c0 (independent forward substitutions, no barriers needed)
@@ -263,6 +283,27 @@ DKTB_EXPORT int dktb_gp_reduce(const float* loss_terms, const float* dhyper, flo
   DKTB_CHECK_ARG(loss_terms && E > 0 && C > 0);
   const int n = E > C * 3 ? E : C * 3;
   DKTB_LAUNCH(gp_reduce_kernel, dim3((n + 127) / 128), dim3(128), 0, stream, loss_terms, dhyper, loss, hyper, E, C);
+  return dktb_launch_status();
+}
+
+// sticky[0] = max(sticky[0], max_i info[i]) (a failed factorisation: > 0), sticky[1] = min(sticky[1], min_i info[i])
+// (deepest jitter retry: < 0).  One thread: n = E*C is tiny.  Lets the host look at the Cholesky status of MANY steps
+// with one read-back instead of one per step (the reference raises at the failing step; here the failing system's
+// gradients are zeroed by the kernel and the error surfaces at the next check).
+__global__ void gp_info_accumulate_kernel(const int* __restrict__ info, int* __restrict__ sticky, int n) {
+  int hi = sticky[0], lo = sticky[1];
+  for (int i = 0; i < n; ++i) {
+    const int v = info[i];
+    hi = v > hi ? v : hi;
+    lo = v < lo ? v : lo;
+  }
+  sticky[0] = hi;
+  sticky[1] = lo;
+}
+
+DKTB_EXPORT int dktb_gp_info_accumulate(const int* info, int* sticky, int n, cudaStream_t stream) {
+  DKTB_CHECK_ARG(info && sticky && n > 0);
+  DKTB_LAUNCH(gp_info_accumulate_kernel, dim3(1), dim3(1), 0, stream, info, sticky, n);
   return dktb_launch_status();
 }
 

@@ -107,6 +107,14 @@ __global__ void __launch_bounds__(GL_THREADS, 2) gp_fit_large_kernel(GpFitLargeA
   const float* yv = p.y + (long)e * p.y_episode_stride + (long)c * N;
   float* A = p.work + ((long)e * C + c) * 2 * N * N;     // K~ -> L (lower incl. diagonal)
   float* X = A + (long)N * N;                             // L^-1 (lower; entries above the diagonal blocks unused)
+  const int nT = (N + GL_T - 1) / GL_T;
+  float acc[4][4];
+  // psd_safe_cholesky (GPyTorch; README.md:27): plain factorisation, then retries with jitter * {1, 10, 100} added to
+  // the diagonal (the fp32 schedule 1e-6, 1e-5, 1e-4 when the caller passes 1e-6; jitter == 0: a single attempt)
+  const int attempts = p.jitter > 0.f ? 4 : 1;
+  int attempt = 0;
+  for (;; ++attempt) {
+  const float jit = attempt == 0 ? 0.f : p.jitter * (attempt == 1 ? 1.f : attempt == 2 ? 10.f : 100.f);
   if (tid == 0) *sm.fail = 0;
   for (int i0 = tid; i0 < N * N; i0 += 4 * GL_THREADS) {     // four independent loads in flight per thread
     float v[4];
@@ -120,13 +128,11 @@ __global__ void __launch_bounds__(GL_THREADS, 2) gp_fit_large_kernel(GpFitLargeA
   }
   __syncthreads();
   for (int i = tid; i < N; i += GL_THREADS) {
-    A[(long)i * N + i] += noise + p.jitter;
+    A[(long)i * N + i] += noise + jit;
     sm.r[i] = yv[i] - mconst;
   }
   __syncthreads();
 
-  const int nT = (N + GL_T - 1) / GL_T;
-  float acc[4][4];
   // ---- blocked Cholesky (left-looking by 64-wide block columns) with the block rows of L^-1 produced on the way
   for (int jb = 0; jb < nT; ++jb) {
     const int j0 = jb * GL_T, nb = min(GL_T, N - j0);
@@ -264,10 +270,21 @@ __global__ void __launch_bounds__(GL_THREADS, 2) gp_fit_large_kernel(GpFitLargeA
     __syncthreads();
   }
   __syncthreads();
+  if (*sm.fail == 0 || attempt + 1 >= attempts) break;
+  __syncthreads();                                        // everyone has read the flag before the next attempt resets it
+  }
   const int fail = *sm.fail;
-  if (tid == 0) p.info[(long)e * C + c] = fail;
-  if (fail) {
-    if (tid == 0) p.loss_terms[(long)e * C + c] = nanf("");
+  if (tid == 0) p.info[(long)e * C + c] = fail ? fail : -attempt;
+  if (fail) {      // NaN loss, zero gradients / alpha: nothing stale reaches the optimiser before the host raises
+    if (tid == 0) {
+      p.loss_terms[(long)e * C + c] = nanf("");
+      if (p.dhyper) { float* o = p.dhyper + ((long)e * C + c) * 3; o[0] = o[1] = o[2] = 0.f; }
+    }
+    for (int k = tid; k < N; k += GL_THREADS) p.alpha[((long)e * C + c) * N + k] = 0.f;
+    if (p.dkbase) {
+      float* dk0 = p.dkbase + ((long)e * C + c) * N * N;
+      for (int i = tid; i < N * N; i += GL_THREADS) dk0[i] = 0.f;
+    }
     return;
   }
   // ---- u = L^-1 r (a warp per row), alpha = L^-T u (a thread per column, coalesced down the rows)

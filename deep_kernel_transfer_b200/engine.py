@@ -19,6 +19,7 @@ import torch
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 GP_SMEM_CROSSOVER = 105   # largest N served by the all-in-shared-memory gp_fit kernel (the tiled one wins from ~100 on)
+GP_JITTER = 1e-6          # psd_safe_cholesky retry base for float32 (GPyTorch utils/cholesky.py): 1e-6, 1e-5, 1e-4
 
 
 def _stream(dev):
@@ -315,6 +316,7 @@ class GPHead:
         w["alpha"] = torch.empty(E, C, N, device=dev, dtype=f32)
         w["loss_terms"] = torch.empty(E, C, device=dev, dtype=f32)
         w["info"] = torch.zeros(E, C, device=dev, dtype=torch.int32)
+        w["info_sticky"] = torch.zeros(2, device=dev, dtype=torch.int32)     # (worst failure, deepest jitter retry) so far
         w["dk"] = torch.empty(E, C, N, N, device=dev, dtype=f32)
         w["dhyper"] = torch.empty(E, C, 3, device=dev, dtype=f32)
         w["loss"] = torch.empty(E, device=dev, dtype=f32)
@@ -350,7 +352,7 @@ class GPHead:
             dst.copy_(cur)      # keep the embedding out of the backbone workspace (device memcpy)
         return dst
 
-    def fit(self, zh, targets, HP, E, N, want_grad, grad_scale=1.0, jitter=0.0):
+    def fit(self, zh, targets, HP, E, N, want_grad, grad_scale=1.0, jitter=GP_JITTER):
         """Gram + C Cholesky systems per episode.  targets [C,N] (shared by all episodes)."""
         lib, st, w, C = self.lib, _stream(self.dev), self.w, self.C
         if self.family is None:
@@ -382,7 +384,15 @@ class GPHead:
                              w["dhyper"] if want_grad else None, w["gp_work"], grad_scale, jitter, E, C, N, st)
         lib.gp_reduce(w["loss_terms"], w["dhyper"] if want_grad else None, w["loss"], w["hyper"] if want_grad else None,
                       E, C, st)
+        lib.gp_info_accumulate(w["info"], w["info_sticky"], E * C, st)
         return w["loss"]
+
+    def check(self, what="Cholesky"):
+        """One host read-back of the Cholesky status of every fit since the last call: warns like psd_safe_cholesky when a
+        system needed jitter, raises when one stayed not positive definite (the reference raises at that step)."""
+        hi, lo = self.w["info_sticky"].tolist()
+        self.w["info_sticky"].zero_()
+        report_info(hi, lo, what)
 
     def hyper_grads(self, HP, GH, E, N):
         """After fit(want_grad=True): only the GP hyper-parameter gradients (outputscale, constant, kernel parameter) --
@@ -450,11 +460,22 @@ def make_targets(n_way, per_class, device):
     return t.to(device)
 
 
+def report_info(hi, lo, what="Cholesky"):
+    """hi > 0: a system stayed not positive definite after the jitter retries -> RuntimeError (GPyTorch 1.0.1 re-raises
+    torch's error, later versions raise NotPSDError); lo < 0: -lo retries were needed -> RuntimeWarning with GPyTorch's text."""
+    import warnings
+    if hi > 0:
+        raise RuntimeError("NotPSDError: %s: matrix not positive definite after adding jitter up to %g (first failing "
+                           "pivot %d)" % (what, GP_JITTER * 100, hi))
+    if lo < 0:
+        warnings.warn("A not p.d., added jitter of %.1e to the diagonal" % (GP_JITTER * 10 ** (-lo - 1)), RuntimeWarning)
+
+
 def check_info(info, what="Cholesky"):
-    bad = int((info != 0).sum().item())
-    if bad:
-        raise RuntimeError("NotPSDError: %s failed for %d (episode, class) systems (first pivots: %s)"
-                           % (what, bad, info[info != 0][:4].tolist()))
+    """Status array of ONE fit (host sync)."""
+    if info.numel() == 0:
+        return
+    report_info(int(info.max().item()), int(info.min().item()), what)
 
 
 def adam_hparams():

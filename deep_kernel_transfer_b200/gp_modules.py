@@ -96,23 +96,39 @@ class ExactGPLayer(nn.Module):
         self.covar_module = ScaleKernel(k)
 
 
-class IndependentModelList(nn.Module):
-    def __init__(self, *models):
-        super().__init__()
-        self.models = nn.ModuleList(models)
-
-
 class LikelihoodList(nn.Module):
     def __init__(self, *likelihoods):
         super().__init__()
         self.likelihoods = nn.ModuleList(likelihoods)
 
 
-class SumMarginalLogLikelihood(nn.Module):
+class IndependentModelList(nn.Module):
+    """gpytorch.models.IndependentModelList: ``models`` plus the ``likelihood`` alias list GPyTorch registers (the same
+    likelihood objects: shared parameters, extra ``model.likelihood.likelihoods.N.*`` keys in ``state_dict()``)."""
+
+    def __init__(self, *models):
+        super().__init__()
+        self.models = nn.ModuleList(models)
+        self.likelihood = LikelihoodList(*[m.likelihood for m in models])
+
+
+class ExactMarginalLogLikelihood(nn.Module):
     def __init__(self, likelihood, model):
         super().__init__()
         self.likelihood = likelihood
         self.model = model
+
+
+class SumMarginalLogLikelihood(nn.Module):
+    """gpytorch.mlls.SumMarginalLogLikelihood: besides ``likelihood`` / ``model`` it registers one
+    ExactMarginalLogLikelihood(m.likelihood, m) per sub-model under ``mlls`` -- aliases of the same parameters, which is
+    where the ``mll.mlls.N.*`` keys of a reference checkpoint come from (train.py:57-65)."""
+
+    def __init__(self, likelihood, model):
+        super().__init__()
+        self.likelihood = likelihood
+        self.model = model
+        self.mlls = nn.ModuleList([ExactMarginalLogLikelihood(m.likelihood, m) for m in model.models])
 
 
 def adapt_reference_state(state, own):

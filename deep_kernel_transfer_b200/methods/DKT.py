@@ -29,6 +29,22 @@ except ImportError:
     IS_TBX_INSTALLED = False
 
 
+class _Range:
+    """NVTX range around one phase of the step (shows up in nsys / ncu --nvtx; a few hundred ns when no tool listens)."""
+
+    def __init__(self, name, on):
+        self.name, self.on = name, on
+
+    def __enter__(self):
+        if self.on:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *a):
+        if self.on:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 class _DevicePacks:
     """Adapter giving a generator of device-resident packs the prefetcher's interface."""
 
@@ -152,6 +168,16 @@ class DKT(MetaTemplate):
         self._HP, self._GH = HP, GH
         self._head = None
         self._adam = None
+        self._sync_replicas()
+
+    def _sync_replicas(self):
+        """Data parallelism averages GRADIENTS, so every rank must start from rank 0's parameters / buffers: the
+        reference's default ``--seed 0`` means "do not seed" (train.py), i.e. each torchrun rank would otherwise build
+        a different random backbone and the replicas would silently diverge."""
+        dist, world = self._world()
+        if world > 1:
+            dist.broadcast(self._pack.flat, 0)
+            dist.broadcast(self._bufs.flat, 0)
 
     def _bb_forward(self, x_all, ipe, training):
         """Backbone forward over packed episodes -> (engine, features [B, D])."""
@@ -201,18 +227,24 @@ class DKT(MetaTemplate):
         st = _stream(dev)
         x_all = x_dev.reshape(E * N, *x_dev.shape[3:])
         dist, world = self._world()
-        targets = make_targets(C, SQ, dev)
+        targets = self._targets(C, SQ, dev)
+        nv = dev.type == "cuda"
         # 1-3: train-mode features, prior, -mll
-        eng, feats = self._bb_forward(x_all, N, True)
+        with _Range("dkt.backbone_fwd", nv):
+            eng, feats = self._bb_forward(x_all, N, True)
         head = self._get_head(eng)
         head.ensure(E, N)
-        zh = head.embed(feats, self._HP, E, N, training=True, out=head.w["zh_train"])
-        loss = head.fit(zh, targets, self._HP, E, N, want_grad=True, grad_scale=1.0 / E)
+        with _Range("dkt.gp_fit", nv):
+            zh = head.embed(feats, self._HP, E, N, training=True, out=head.w["zh_train"])
+            loss = head.fit(zh, targets, self._HP, E, N, want_grad=True, grad_scale=1.0 / E)
         # 4: backward + Adam
-        gfeat = head.backward(feats, zh, self._HP, self._GH, E, N)
-        self._bb_backward(eng, x_all, gfeat, N)
+        with _Range("dkt.gp_bwd", nv):
+            gfeat = head.backward(feats, zh, self._HP, self._GH, E, N)
+        with _Range("dkt.backbone_bwd", nv):
+            self._bb_backward(eng, x_all, gfeat, N)
         if world > 1:
-            dist.all_reduce(self._pack.grad)
+            with _Range("dkt.allreduce_grad", nv):
+                dist.all_reduce(self._pack.grad)
         ad = self._adam
         ad["step"] += 1
         (g0, g1), (b0, b1) = self._gp_range, self._bb_range
@@ -230,9 +262,25 @@ class DKT(MetaTemplate):
                 m_.num_batches_tracked += E
         out = {"loss": loss.clone(), "info": head.w["info"]}
         if self.monitor:
-            out.update(self.monitor_step(x_dev))
+            with _Range("dkt.monitor", nv):
+                out.update(self.monitor_step(x_dev))
         self.last_step = out
         return out
+
+    def _targets(self, C, per_class, dev):
+        """+-1 target matrix [C, C*per_class] on the device, built once per shape (not per step)."""
+        key = ("t", C, per_class, str(dev))
+        cache = self.__dict__.setdefault("_const_cache", {})
+        if key not in cache:
+            cache[key] = make_targets(C, per_class, dev)
+        return cache[key]
+
+    def _labels(self, C, per_class, dev):
+        key = ("l", C, per_class, str(dev))
+        cache = self.__dict__.setdefault("_const_cache", {})
+        if key not in cache:
+            cache[key] = torch.arange(C, device=dev, dtype=torch.int32).repeat_interleave(per_class)
+        return cache[key]
 
     def monitor_step(self, x_dev):
         """Steps 5-6 of the loop body (DKT.py:170-193): eval-mode features of the same images; the GP stays
@@ -242,7 +290,7 @@ class DKT(MetaTemplate):
         N = C * SQ
         dev = x_dev.device
         x_all = x_dev.reshape(E * N, *x_dev.shape[3:])
-        targets = make_targets(C, SQ, dev)
+        targets = self._targets(C, SQ, dev)
         eng, feats_e = self._bb_forward(x_all, N, False)
         head = self._get_head(eng)
         zh_e = head.embed(feats_e, self._HP, E, N, training=False, out=head.w["zh"])
@@ -253,7 +301,7 @@ class DKT(MetaTemplate):
             head.w["mon_kx"] = torch.empty(E, N, N, device=dev)
         head.predict(zh_e, head.w["zh_train"], self._HP, E, N, N, head.w["mon_mean"], head.w["mon_pred"],
                      head.w["mon_kx"])
-        labels = torch.arange(C, device=dev, dtype=torch.int32).repeat_interleave(SQ)
+        labels = self._labels(C, SQ, dev)
         hit = (head.w["mon_pred"] == labels.unsqueeze(0)).view(E, C, SQ)
         return {"acc_support": hit[:, :, :self.n_support].float().mean((1, 2)) * 100.0,
                 "acc_query": hit[:, :, self.n_support:].float().mean((1, 2)) * 100.0,
@@ -285,6 +333,29 @@ class DKT(MetaTemplate):
         else:
             feed = DevicePrefetcher(packs(), dev)   # H2D of pack k+1 overlaps the kernels of pack k
         step_i = 0
+        pending = []            # (iteration, loss, hit_support, hit_query, n_s, n_q): device scalars, logged in order
+        self._sync_replicas()
+
+        def flush():
+            """The reference writes loss and both accuracies to the summary writer at EVERY iteration
+            (DKT.py:167, 183, 193).  Same records, same order, same iteration numbers -- delivered in batches (at the
+            print steps and at the end of the loop) so that logging does not force a host sync per step."""
+            if self.writer is not None:
+                for it, loss_t, hs, hq, n_s, n_q in pending:
+                    self.writer.add_scalar("loss", float(loss_t), it)
+                    if hs is not None:
+                        self.writer.add_scalar("GP_support_accuracy", (float(hs) / n_s) * 100.0, it)
+                        self.writer.add_scalar("GP_query_accuracy", (float(hq) / n_q) * 100.0, it)
+            del pending[:]
+
+        def health():
+            """Cholesky status of every fit since the last look + the tcgen05 pipeline time-out flag: one read-back."""
+            if self._head is not None:
+                self._head.check()
+            eng = getattr(self.feature, "_engine", None)
+            if eng is not None and hasattr(eng, "check_tc"):
+                eng.check_tc()
+
         for x_dev in feed:
             i = min((step_i + 1) * E, n_items) - 1
             self.n_query = x_dev.size(2) - self.n_support
@@ -293,8 +364,14 @@ class DKT(MetaTemplate):
             out = self.train_step(x_dev)
             feed.release(x_dev)
             self.iteration = i + (epoch * n_items)
+            n_s = float(x_dev.size(0) * x_dev.size(1) * self.n_support)
+            n_q = float(x_dev.size(0) * x_dev.size(1) * self.n_query)
+            if self.writer is not None:
+                pending.append((self.iteration, out["loss"].mean(),
+                                out["hit_support"].sum() if self.monitor else None,
+                                out["hit_query"].sum() if self.monitor else None, n_s, n_q))
             if step_i % print_freq == 0:
-                check_info(out["info"])
+                health()
                 ms = self.model.models
                 outputscale = float(np.mean([m.covar_module.outputscale.item() for m in ms]))
                 noise = float(np.mean([m.likelihood.noise.item() for m in ms]))
@@ -302,17 +379,14 @@ class DKT(MetaTemplate):
                 lenghtscale = float(np.mean([l.mean().item() for l in ls])) if ls[0] is not None else 0.0
                 loss = out["loss"].mean().item()
                 # percentages from the integer hit counts in double, as the reference's numpy does (DKT.py:181, 191)
-                n_s = float(x_dev.size(0) * x_dev.size(1) * self.n_support)
-                n_q = float(x_dev.size(0) * x_dev.size(1) * self.n_query)
                 acc_s = (out["hit_support"].sum().item() / n_s) * 100.0 if self.monitor else float("nan")
                 acc_q = (out["hit_query"].sum().item() / n_q) * 100.0 if self.monitor else float("nan")
-                if self.writer is not None:
-                    self.writer.add_scalar("loss", loss, self.iteration)
-                    self.writer.add_scalar("GP_support_accuracy", acc_s, self.iteration)
-                    self.writer.add_scalar("GP_query_accuracy", acc_q, self.iteration)
+                flush()
                 print('Epoch [{:d}] [{:d}/{:d}] | Outscale {:f} | Lenghtscale {:f} | Noise {:f} | Loss {:f} | Supp. {:f} | Query {:f}'.format(
                     epoch, i, n_items, outputscale, lenghtscale, noise, loss, acc_s, acc_q))
             step_i += 1
+        flush()
+        health()
 
     def _episode_embed(self, x):
         """x [C, S+Q, 3, H, W] (any device) -> (engine, support embedding [1, C*S, D], query embedding [1, C*Q, D]):
@@ -364,7 +438,8 @@ class DKT(MetaTemplate):
         kx = torch.empty(1, M, N, device=dev)
         fit_head.predict(zh_q, zh_s, self._HP, 1, M, N, mean, pred, kx)
         self._last_info = fit_head.w["info"]
-        return mean[0], pred[0]
+        self._last_mean, self._last_pred = mean[0], pred[0]
+        return eng, pred[0]
 
     def _test_head(self, eng, N):
         h = getattr(self, "_thead", None)
@@ -388,8 +463,10 @@ class DKT(MetaTemplate):
             y_pred = gp.predict(zh_q[0].cpu().numpy())
             y_query = np.repeat(range(C), self.n_query)
             return float(np.sum(y_pred == y_query)), len(y_query), 0.0
-        _, pred = self._episode_logits(x, adapt_steps=int(N))
+        eng, pred = self._episode_logits(x, adapt_steps=int(N))
         check_info(self._last_info)
+        if hasattr(eng, "check_tc"):
+            eng.check_tc()
         y_query = np.repeat(range(C), self.n_query)
         top1_correct = np.sum(pred.cpu().numpy() == y_query)
         return float(top1_correct), len(y_query), self._adapt_loss
@@ -418,5 +495,5 @@ class DKT(MetaTemplate):
 
     def get_logits(self, x):
         self.n_query = x.size(1) - self.n_support
-        mean, _ = self._episode_logits(x)
-        return mean.t().contiguous()          # [C*Q, C]  (torch.stack(means, 1), DKT.py:333-335)
+        self._episode_logits(x)
+        return self._last_mean.t().contiguous()          # [C*Q, C]  (torch.stack(means, 1), DKT.py:333-335)

@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib, configs, gp_modules as gpm
-from ..engine import _stream, check_info
+from ..engine import _stream, check_info, GP_JITTER
 
 kernel_type = configs.kernel_type
 
@@ -60,7 +60,7 @@ class DKT(nn.Module):
         model = ExactGPLayer(likelihood, kernel=self.kernel, feat_dim=self.feat_dim)
         self.model = model
         self.likelihood = likelihood
-        self.mll = gpm.SumMarginalLogLikelihood(likelihood, model)
+        self.mll = gpm.ExactMarginalLogLikelihood(likelihood, model)     # DKT_regression.py:34
         self.mse = nn.MSELoss()
         return self.model, self.likelihood, self.mll
 
@@ -125,7 +125,7 @@ class DKT(nn.Module):
             lib.sqdist(w["xc"], w["xc"], w["gram"], 1, N, N, D, st)          # w["gram"] holds squared distances
             lib.kernel_fwd(1, None, w["gram"], rl, w["kb"], 1, 1, N, N, st)
         lib.gp_fit(w["kb"], N * N, y.contiguous().view(1, 1, N), N, ros, cst, rn, w["alpha"], w["linv"], w["lt"], w["info"],
-                   w["dk"] if want_grad else None, w["dh"] if want_grad else None, 1.0, 0.0, 1, 1, N, st)
+                   w["dk"] if want_grad else None, w["dh"] if want_grad else None, 1.0, GP_JITTER, 1, 1, N, st)
         lib.gp_reduce(w["lt"], w["dh"] if want_grad else None, w["loss"], w["hyper"] if want_grad else None, 1, 1, st)
         return w
 

@@ -13,6 +13,8 @@ class ResNetEngine:
     def __init__(self, lib, net, device):
         self.lib, self.net, self.dev = lib, net, torch.device(device)
         self.tape = []
+        self.keep_tape = False       # tests: keep the consumed tape in `last_tape` (same-branch gradient replay)
+        self.last_tape = None
         self.trace = None            # tests may set a list: backward appends (record, gy, gx, gres) per op
         self.D = net.final_feat_dim
         self.P = 1
@@ -174,4 +176,6 @@ class ResNetEngine:
                     self.trace.append((rec, gy, None if gx is None else gx.clone(), m.weight.grad.clone()))
                 if gx is not None:
                     give(x, gx)
+        if self.keep_tape:
+            self.last_tape = self.tape
         self.tape = []

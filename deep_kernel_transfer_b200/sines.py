@@ -8,7 +8,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, gp_modules as gpm
-from .engine import _stream
+from .engine import _stream, GP_JITTER
 from .flat import FlatPack
 
 
@@ -105,7 +105,7 @@ class SinesDKT(nn.Module):
         lib.spectral_fwd(w["x"], w["x"], rw, rmu, rv, w["kb"], w["ec"], 1, N, N, D, Q, D, 1, st)
         lib.gp_fit(w["kb"], N * N, y.contiguous().view(1, 1, N), N, None, self.mean_module.constant.data.view(1),
                    self.likelihood.noise_covar.raw_noise.data.view(1), w["alpha"], w["linv"], w["lt"], w["info"],
-                   w["dk"] if want_grad else None, w["dh"] if want_grad else None, 1.0, 0.0, 1, 1, N, st)
+                   w["dk"] if want_grad else None, w["dh"] if want_grad else None, 1.0, GP_JITTER, 1, 1, N, st)
         lib.gp_reduce(w["lt"], w["dh"] if want_grad else None, w["loss"], w["hyper"] if want_grad else None, 1, 1, st)
         return w
 

@@ -182,8 +182,12 @@ int dktb_l2norm_bwd(const float* zhat, const float* gzhat, const float* inv, flo
 /* ---- exact GP (GPyTorch call sites methods/DKT.py:161-162,177,187,265; DKT_regression.py:52-54,90-93) -- */
 /* out[e][m][n] = <x1[e][m], x2[e][n]>  (LinearKernel / cross-kernel) */
 int dktb_gram(const float* x1, const float* x2, float* out, int E, int M, int N, int D, cudaStream_t stream);
-/* per (episode, class): K~ = softplus(raw_outputscale_c)*Kb + (softplus(raw_noise_c)+1e-4+jitter) I -> Cholesky ->
- * alpha_c = K~^-1 (y_c - constant_c), loss_terms[e][c] = -log p_c/(N*C), info[e][c] = 0 | failing pivot (1-based).
+/* per (episode, class): K~ = softplus(raw_outputscale_c)*Kb + (softplus(raw_noise_c)+1e-4) I -> Cholesky ->
+ * alpha_c = K~^-1 (y_c - constant_c), loss_terms[e][c] = -log p_c/(N*C).
+ * Cholesky follows GPyTorch's psd_safe_cholesky (utils/cholesky.py; the reference relies on it, README.md:27,
+ * methods/DKT.py:162): a plain attempt, then -- when jitter > 0 -- retries with jitter, 10*jitter, 100*jitter added to the
+ * diagonal (pass 1e-6 for the fp32 schedule).  info[e][c] = 0 ok | -k ok after the k-th retry | > 0 the 1-based failing
+ * pivot of the last attempt; a failed system gets a NaN loss term and ZERO alpha / dkbase / dhyper.
  * Optional: linv [E][C][N][N]; dkbase [E][C][N][N] = grad_scale*dLoss/dKb_c; dhyper [E][C][3] =
  * grad_scale*dLoss/d(raw_outputscale, constant, raw_noise).  raw_outputscale == NULL: no ScaleKernel.
  * N <= dktb_gp_max_n(). */
@@ -204,6 +208,11 @@ int dktb_gp_fit_large(const float* kbase, long kbase_class_stride, const float* 
                       float grad_scale, float jitter, int E, int C, int N, cudaStream_t stream);
 int dktb_gp_reduce(const float* loss_terms, const float* dhyper, float* loss, float* hyper, int E, int C,
                    cudaStream_t stream);
+
+/* Cholesky status over many steps with one read-back: sticky[0] = max(sticky[0], max info), sticky[1] = min(sticky[1],
+ * min info).  info > 0: not positive definite even after the jitter retries (GPyTorch psd_safe_cholesky raises there;
+ * methods/DKT.py:162 relies on it, README.md:27); info = -k: factorised after the k-th retry (jitter * 10^(k-1)). */
+int dktb_gp_info_accumulate(const int* info, int* sticky, int n, cudaStream_t stream);
 /* dZ = scale * (S + S^T) Z,  S = sum_c w[e][c] */
 int dktb_gram_bwd(const float* w, const float* z, float* dz, int E, int C, int N, int D, float scale,
                   cudaStream_t stream);

@@ -38,11 +38,18 @@ def rel_err(a, b):
 
 
 def check_train_step(model_factory, dev, image_size=32, n_way=2, n_support=1, n_query=2, E=2, tol=1e-4,
-                     steps=2, kernel="bncossim", lib=None, loose=None):
+                     steps=2, kernel="bncossim", lib=None, loose=None, report=None, same_branch=False,
+                     gp_override=None):
     """Runs `steps` packed meta-train steps on the device path and on the oracle from identical weights
     and inputs; checks loss, every gradient, the post-Adam parameters, BN running statistics and the
-    monitoring predictions (argmax bit-exact).  Tolerance: 1e-4 relative (north_star)."""
+    monitoring predictions (argmax bit-exact).  Tolerance: 1e-4 relative (north_star).
+
+    Gradients, two modes.  Default (small shapes): device vs the free-running fp64 oracle, bar
+    max(tol, k x the fp32 oracle's own distance to fp64).  ``same_branch=True`` (BASELINE shapes, where gate flips
+    dominate -- tests/branch_checks.py): device vs a float64 replay of the step on the device's own ReLU / max-pool
+    branch, bar `tol` flat; the free-running distances are still reported (keys ``free.*``, not asserted)."""
     from deep_kernel_transfer_b200.methods.DKT import DKT
+    import branch_checks as bc
     torch.manual_seed(0)
     oracle = oep.OracleDKT("Conv4", kernel, n_way=n_way, n_support=n_support, seed=0,
                            feat_dim=64 * (image_size // 16) ** 2)
@@ -54,6 +61,8 @@ def check_train_step(model_factory, dev, image_size=32, n_way=2, n_support=1, n_
             oracle.gp[nm] = torch.linspace(1.5, 2.5, n_way) if nm == "raw_lengthscale" else torch.linspace(0.2, 0.6, n_way)
     if kernel == "linear":
         oracle.gp["raw_variance"] = torch.linspace(-0.2, 0.4, n_way)
+    for k, v in (gp_override or {}).items():
+        oracle.gp[k] = v.clone()
     g = torch.Generator().manual_seed(5)
     for k in oracle.bb:
         if k.endswith("BN.weight") or k.endswith("bn_out.weight"):
@@ -67,8 +76,9 @@ def check_train_step(model_factory, dev, image_size=32, n_way=2, n_support=1, n_
     model = model.to(dev)
     model.train()
     worst = {}
-
     floor = {}
+    info_only = set()
+    branch_stats = {}
 
     def upd(key, val, val32=0.0):
         """val: device vs fp64 oracle; val32: fp32 oracle vs fp64 oracle (the reference's own rounding envelope)."""
@@ -87,6 +97,8 @@ def check_train_step(model_factory, dev, image_size=32, n_way=2, n_support=1, n_
             for k in list(oracle.gp):
                 oracle.gp[k] = oracle.gp[k].detach().clone()
             model_cpu_sync(model, oracle, dev)
+        snap = {k: v.detach().clone() for k, v in oracle.bb.items()}
+        snap_gp = {k: v.detach().clone() for k, v in oracle.gp.items()}
         w_before = [b.C.weight.detach().cpu().clone() for b in model.feature.blocks()]
         oracle64.optimizer = None
         oracle64.bb = {k: (v.detach().double() if v.is_floating_point() else v.clone()) for k, v in oracle.bb.items()}
@@ -95,50 +107,53 @@ def check_train_step(model_factory, dev, image_size=32, n_way=2, n_support=1, n_
         ref = oracle.train_step(xs)
         model._ensure_packed()
         model._new_adam()
+        mon_flag, model.monitor = model.monitor, False      # the monitoring pass re-uses the conv workspaces
         out = model.train_step(xs.to(dev))
+        model.monitor = mon_flag
         assert int(out["info"].cpu().abs().sum()) == 0
         upd("loss", rel_err(out["loss"], r64["loss"]), rel_err(ref["loss"], r64["loss"]))
+        got = bc.device_grads(model, kernel)
+        if same_branch:
+            gates = bc.collect_device_gates(model, snap, n_way * (n_support + n_query))
+            loss_b, truth, _ = bc.replay_step64(xs, snap, snap_gp, gates, kernel, n_way, n_support, branch_stats)
+            upd("loss.branch", rel_err(out["loss"], loss_b))
+        else:
+            truth = r64["grads"]
+        names = {"raw_outputscale": "g.outputscale", "constant": "g.constant", "trunk.bn_out.weight": "g.bn_out.w",
+                 "trunk.bn_out.bias": "g.bn_out.b"}
+        for key, gdev in got.items():
+            if key.endswith(".C.bias"):
+                # the conv bias cancels inside BatchNorm: its gradient is rounding noise around zero;
+                # only require it to be negligible w.r.t. the weight gradient scale
+                scale = float(ref["grads"][key.replace(".C.bias", ".C.weight")].abs().max())
+                assert float(gdev.abs().max()) <= 1e-3 * scale + 1e-6, key
+                continue
+            rk = names.get(key, "g." + key)
+            f32 = rel_err(ref["grads"][key], r64["grads"][key])
+            if same_branch:
+                upd(rk, rel_err(gdev, truth[key]))                       # flat `tol` on the device's own branch
+                upd("free." + rk, rel_err(gdev, r64["grads"][key]), f32)
+                info_only.add("free." + rk)
+            else:
+                upd(rk, rel_err(gdev, truth[key]), f32)
         for i, b in enumerate(model.feature.blocks()):
-            for nm, t in (("C.weight", b.C.weight), ("C.bias", b.C.bias), ("BN.weight", b.BN.weight),
-                          ("BN.bias", b.BN.bias)):
-                key = "trunk.%d.%s" % (i, nm)
-                if nm == "C.bias":
-                    # the conv bias cancels inside BatchNorm: its gradient is rounding noise around zero;
-                    # only require it to be negligible w.r.t. the weight gradient scale
-                    scale = float(ref["grads"]["trunk.%d.C.weight" % i].abs().max())
-                    assert float(t.grad.abs().max()) <= 1e-3 * scale + 1e-6, key
-                    continue
-                upd("g." + key, rel_err(t.grad, r64["grads"][key]), rel_err(ref["grads"][key], r64["grads"][key]))
-            # first Adam step moves every weight by lr*sign(g) (|g| >> eps): compare where the sign is
-            # numerically determined
-            # numerically determined (and |g| >> Adam's eps = 1e-8: below that the update is lr*g/(|g|+eps), which
+            # first Adam step moves every weight by lr*sign(g) (|g| >> eps): compare where the sign is numerically
+            # determined (and |g| >> Adam's eps = 1e-8: below that the update is lr*g/(|g|+eps), which
             # amplifies rounding-level differences of g -- small-gradient kernels such as rbf reach that regime)
-            gref = ref["grads"]["trunk.%d.C.weight" % i]
+            gref = truth["trunk.%d.C.weight" % i].float() if same_branch else ref["grads"]["trunk.%d.C.weight" % i]
             mask = (gref.abs() > 1e-3 * gref.abs().max()) & (gref.abs() > 1e-5)
             d_all = b.C.weight.detach().cpu() - w_before[i]
             if bool(mask.any()):
-                d_ref = (oracle.bb["trunk.%d.C.weight" % i].detach() - w_before[i])[mask]
+                if same_branch:
+                    d_ref = (-1e-3 * gref / (gref.abs() + 1e-8))[mask]
+                else:
+                    d_ref = (oracle.bb["trunk.%d.C.weight" % i].detach() - w_before[i])[mask]
                 upd("adam.w%d" % i, float((d_all[mask] - d_ref).abs().max() / 1e-3))
             # wiring of the fused Adam for EVERY element: first step from the device's own gradient
             gd = b.C.weight.grad.detach().cpu().double()
             expect = -1e-3 * gd / (gd.abs() + 1e-8)
             upd("adam.self%d" % i, float((d_all.double() - expect).abs().max() / 1e-3))
             upd("rv%d" % i, rel_err(b.BN.running_var, oracle.bb["trunk.%d.BN.running_var" % i]))
-        if kernel == "bncossim":
-            bn = model.feature.trunk.bn_out
-            upd("g.bn_out.w", rel_err(bn.weight.grad, r64["grads"]["trunk.bn_out.weight"]),
-                rel_err(ref["grads"]["trunk.bn_out.weight"], r64["grads"]["trunk.bn_out.weight"]))
-            upd("g.bn_out.b", rel_err(bn.bias.grad, r64["grads"]["trunk.bn_out.bias"]),
-                rel_err(ref["grads"]["trunk.bn_out.bias"], r64["grads"]["trunk.bn_out.bias"]))
-        gos = torch.stack([m.covar_module.raw_outputscale.grad for m in model.model.models])
-        gct = torch.stack([m.mean_module.constant.grad.view(()) for m in model.model.models])
-        upd("g.outputscale", rel_err(gos, r64["grads"]["raw_outputscale"]),
-            rel_err(ref["grads"]["raw_outputscale"], r64["grads"]["raw_outputscale"]))
-        upd("g.constant", rel_err(gct, r64["grads"]["constant"]), rel_err(ref["grads"]["constant"], r64["grads"]["constant"]))
-        for nm in ("raw_variance", "raw_lengthscale", "raw_offset"):
-            if nm in ref["grads"]:
-                gp_ = torch.stack([getattr(m.covar_module.base_kernel, nm).grad.view(()) for m in model.model.models])
-                upd("g." + nm, rel_err(gp_, r64["grads"][nm]), rel_err(ref["grads"][nm], r64["grads"][nm]))
         # monitoring (steps 5-6): after Adam the two sides differ by +-lr sign flips of noise-level gradients
         # (conv biases), so the strict check re-synchronises the post-update weights from the oracle and
         # re-runs the device monitoring, which still holds the pre-update train-mode features
@@ -161,24 +176,29 @@ def check_train_step(model_factory, dev, image_size=32, n_way=2, n_support=1, n_
     # test batches make BatchNorm's backward ill-conditioned (the device path must be as good as torch fp32)
     # The tcgen05 path multiplies in 3xTF32 (operands carried to ~2^-22 instead of fp32's 2^-24), so where the
     # envelope applies it is allowed 8x the fp32 reference's own distance to the fp64 truth instead of 3x.
-    import os
-    fac = 8.0 if (os.environ.get("DKTB_CONV", "tc3") != "fp32" and torch.device(dev).type == "cuda") else 3.0
+    fac = 8.0 if torch.device(dev).type == "cuda" else 3.0
     # `loose`: {key prefix: tolerance} for quantities that sit behind ReLU / max-pool gates of a large batch, where a
     # single gate within fp32 rounding of its threshold flips between two correct evaluations
     def bar(k):
+        if k in info_only:
+            return float("inf")
         for pre, t in (loose or {}).items():
             if k.startswith(pre):
                 return t
         return max(tol, fac * floor.get(k, 0.0))
+    if report is not None:       # per key: (device vs fp64 truth, fp32 oracle vs fp64 oracle, bar applied)
+        report.update({k: (v, floor.get(k, 0.0), bar(k)) for k, v in worst.items()})
+        report["_branch"] = branch_stats
     bad = {k: (v, floor.get(k, 0.0)) for k, v in worst.items() if v > bar(k)}
     assert not bad, "parity above max(%g, %gx fp32-reference envelope): %s" % (tol, fac, bad)
     return model, oracle, worst
 
 
-def check_correct(model, oracle, dev, image_size=32, n_way=2, n_support=1, n_query=3, tol=1e-4):
+def check_correct(model, oracle, dev, image_size=32, n_way=2, n_support=1, n_query=3, tol=1e-4, extras=True,
+                  episodes=2):
     model_cpu_sync(model, oracle, dev)      # identical weights / running statistics on both sides
     model.eval()
-    for ep in range(2):
+    for ep in range(episodes):
         x = oep.synthetic_episode(900 + ep, n_way, n_support, n_query, image_size)
         ref_logits = oracle.get_logits(x)
         got = model.get_logits(x)
@@ -187,6 +207,8 @@ def check_correct(model, oracle, dev, image_size=32, n_way=2, n_support=1, n_que
         got_c = model.correct(x)
         assert got_c[:2] == ref_c[:2], (got_c, ref_c)
         assert np.array_equal(got.cpu().numpy().argmax(1), ref_logits.numpy().argmax(1))
+    if not extras:
+        return
     # Laplace branch: CUDA embeddings handed to scikit-learn, as the reference does (DKT.py:207-224)
     x = oep.synthetic_episode(940, n_way, n_support, n_query, image_size)
     assert model.correct(x, laplace=True) == oracle.correct_laplace(x)
@@ -284,7 +306,8 @@ def check_regression(dev, lib=None, image=36, n=7, n_support=4, tol=2e-4, kernel
 
 
 def check_train_step_arch(arch, model_factory, dev, image_size, n_way=2, n_support=1, n_query=2, E=2, kernel="rbf",
-                          lib=None, tol=1e-4, env_factor=4.0, grad_check=True):
+                          lib=None, tol=1e-4, env_factor=4.0, grad_check=True, report=None, lengthscale=(1.5, 2.5),
+                          same_branch=False):
     """One packed meta-train step of an arbitrary backbone (ResNet*) against the oracle: loss, every backbone / GP
     gradient (fp64 arbiter + fp32 envelope), monitoring arg-max after re-synchronising the post-step weights."""
     from deep_kernel_transfer_b200.methods.DKT import DKT
@@ -293,7 +316,7 @@ def check_train_step_arch(arch, model_factory, dev, image_size, n_way=2, n_suppo
     o32.gp["raw_outputscale"] = torch.linspace(-0.3, 0.6, n_way)
     o32.gp["constant"] = torch.linspace(0.1, -0.2, n_way)
     if "raw_lengthscale" in o32.gp:
-        o32.gp["raw_lengthscale"] = torch.linspace(1.5, 2.5, n_way)
+        o32.gp["raw_lengthscale"] = torch.linspace(lengthscale[0], lengthscale[1], n_way)
     o64 = oep.OracleDKT(arch, kernel, n_way=n_way, n_support=n_support, seed=0, dtype=torch.float64)
     o64.bb = {k: (v.detach().double() if v.is_floating_point() else v.clone()) for k, v in o32.bb.items()}
     o64.gp = {k: v.detach().double() for k, v in o32.gp.items()}
@@ -312,9 +335,71 @@ def check_train_step_arch(arch, model_factory, dev, image_size, n_way=2, n_suppo
     ref = o32.train_step(xs)
     model._ensure_packed()
     model._new_adam()
+    snap = {k: v.detach().clone() for k, v in model.feature.state_dict().items()}
+    eng = model.feature.engine(image_size, dev, lib)
+    eng.keep_tape = bool(same_branch)
+    model.monitor = False
     out = model.train_step(xs.to(dev))
+    model.monitor = True
     assert int(out["info"].cpu().abs().sum()) == 0
     assert rel_err(out["loss"], r64["loss"]) <= tol, rel_err(out["loss"], r64["loss"])
+    if report is not None:
+        report["loss"] = (rel_err(out["loss"], r64["loss"]), rel_err(ref["loss"], r64["loss"]), tol)
+    if same_branch:
+        # every gradient against a float64 replay of the whole step (op tape -> head -> -mll) on the DEVICE's branch
+        # (stored ReLU outputs / max-pool taps), flat `tol`; the replay runs in float64 on the same device
+        from oracle import gp as ogp
+        import torch.nn.functional as F
+        name_of = {id(p_): n for n, p_ in model.feature.named_parameters()}
+        leaves = {}
+
+        def leaf(t):
+            n = name_of[id(t)]
+            if n not in leaves:
+                leaves[n] = snap[n].detach().double().clone().requires_grad_(True)
+            return leaves[n]
+        stats = {"relu_flips": 0, "pool_flips": 0, "gates": 0}
+        feats64 = resnet_replay64(eng.last_tape, True, stats, leaf)
+        gp64 = {k: v.detach().double().clone().requires_grad_(k in ogp.trainable_gp_names(kernel)) for k, v in o64.gp.items()}
+        N = n_way * (n_support + n_query)
+        tg = oep.make_targets(n_way, n_support + n_query, torch.float64)
+        tot = 0.0
+        for e in range(E):
+            f = feats64[e * N:(e + 1) * N].cpu()            # the GP head of the replay runs on the host (oracle/gp.py)
+            if kernel in oep.NORMALIZED_KERNELS:
+                f = F.normalize(f, p=2, dim=1)
+            tot = tot + ogp.mll_loss(kernel, f, tg, gp64) / E
+        tot.backward()
+        badb = {}
+        for n, p_ in model.feature.named_parameters():
+            if n not in leaves or leaves[n].grad is None:
+                continue
+            wname = n.replace(".bias", ".weight")
+            if n.endswith(".bias") and p_.dim() == 1 and wname in leaves and \
+                    leaves[n].grad.abs().max() < 1e-6 * leaves[wname].grad.abs().max():
+                continue      # a bias that BatchNorm cancels
+            e_ = rel_err(p_.grad, leaves[n].grad)
+            if report is not None:
+                report["g." + n] = (e_, rel_err(ref["grads"][n], r64["grads"][n]), tol)
+                report["free.g." + n] = (rel_err(p_.grad, r64["grads"][n]), rel_err(ref["grads"][n], r64["grads"][n]), float("inf"))
+            if e_ > tol:
+                badb[n] = e_
+        for nm, getter in (("raw_outputscale", lambda m: m.covar_module.raw_outputscale),
+                           ("constant", lambda m: m.mean_module.constant),
+                           ("raw_lengthscale", lambda m: m.covar_module.base_kernel.raw_lengthscale)):
+            if nm in ogp.trainable_gp_names(kernel):
+                gdev = torch.stack([getter(m).grad.view(()) for m in model.model.models])
+                e_ = rel_err(gdev, gp64[nm].grad)
+                if report is not None:
+                    report["g." + nm] = (e_, rel_err(ref["grads"][nm], r64["grads"][nm]), tol)
+                if e_ > tol:
+                    badb[nm] = e_
+        if report is not None:
+            report["_branch"] = stats
+        assert not badb, ("same-branch gradients", badb)
+        eng.last_tape = None
+        eng.keep_tape = False
+        grad_check = False       # the free-running comparison below is reported, not asserted
     bad = {}
     for name, p_ in model.feature.named_parameters():
         if name.endswith(".bias") and name.replace(".bias", ".weight") in ref["grads"] and p_.dim() == 1 and \
@@ -322,6 +407,8 @@ def check_train_step_arch(arch, model_factory, dev, image_size, n_way=2, n_suppo
             continue      # a bias that BatchNorm cancels: rounding noise on both sides
         e = rel_err(p_.grad, r64["grads"][name])
         floor = rel_err(ref["grads"][name], r64["grads"][name])
+        if report is not None:
+            report["g." + name] = (e, floor, max(tol, env_factor * floor))
         if grad_check and e > max(tol, env_factor * floor):
             bad[name] = (e, floor)
     gos = torch.stack([m.covar_module.raw_outputscale.grad for m in model.model.models])
@@ -340,6 +427,15 @@ def check_train_step_arch(arch, model_factory, dev, image_size, n_way=2, n_suppo
     mon = model.monitor_step(xs.to(dev))
     np.testing.assert_allclose(mon["acc_support"].cpu().numpy(), ref["acc_support"], atol=1e-4)
     np.testing.assert_allclose(mon["acc_query"].cpu().numpy(), ref["acc_query"], atol=1e-4)
+    # predictive means of the monitoring pass: an OUTPUT, held to `tol` without any envelope
+    C, SQ = n_way, n_support + n_query
+    mean = mon["mean"].cpu().view(E, C, C, SQ)
+    mean_s = mean[:, :, :, :n_support].reshape(E, C, C * n_support)
+    mean_q = mean[:, :, :, n_support:].reshape(E, C, C * n_query)
+    e_mean = max(rel_err(mean_s, ref["mean_support"]), rel_err(mean_q, ref["mean_query"]))
+    if report is not None:
+        report["mon.mean"] = (e_mean, 0.0, tol)
+    assert e_mean <= tol, ("monitoring predictive mean", e_mean)
     return model
 
 
@@ -388,6 +484,64 @@ def check_sines(dev, lib=None, steps=3, tol=2e-4):
     assert rel_err(mean, mean_ref) <= tol and rel_err(var, var_ref) <= tol
 
 
+def resnet_replay64(tape, device_gates, stats, leaf):
+    """Float64 replay of a ResNetEngine op tape (NCHW, torch autograd).  ``leaf(param_tensor)`` -> the float64 leaf to use
+    for a module parameter.  device_gates: take the ReLU masks (y > 0 of the stored post-ReLU activations) and the
+    max-pool taps (stored indices) from the device, asserting every disagreement with the free-running choice sits on a
+    near-zero pre-activation / near-tie; otherwise run free.  Returns the features [B, D] (float64, differentiable)."""
+    import torch.nn.functional as F
+
+    def nchw(t):
+        return t.detach().double().permute(0, 3, 1, 2)
+
+    vals = {}
+    vals[tape[0][1].data_ptr()] = nchw(tape[0][1])
+    for rec in tape:
+        if rec[0] == "conv":
+            _, xi, out, m, (_, _, _, _, _, st, pad, dil) = rec
+            bias = leaf(m.bias) if m.bias is not None else None
+            vals[out.data_ptr()] = F.conv2d(vals[xi.data_ptr()], leaf(m.weight), bias, st, pad, dil)
+        elif rec[0] == "bn":
+            _, xi, y, m, _, _, res, relu, ipe = rec
+            v = vals[xi.data_ptr()]
+            o = torch.cat([F.batch_norm(v[e:e + ipe], None, None, leaf(m.weight), leaf(m.bias), True, 0.0, 1e-5)
+                           for e in range(0, v.shape[0], ipe)])
+            if res is not None:
+                o = o + vals[res.data_ptr()]
+            if relu and device_gates:
+                mask = nchw(y) > 0
+                diff = mask != (o > 0)
+                stats["gates"] += mask.numel()
+                if bool(diff.any()):
+                    stats["relu_flips"] += int(diff.sum())
+                    assert float(o[diff].abs().max()) <= 1e-4 * float(o.abs().max()), "ReLU gate differs off zero"
+                o = o * mask
+            elif relu:
+                o = o.relu()
+            vals[y.data_ptr()] = o
+        elif rec[0] == "maxpool":
+            _, xi, y, idx = rec
+            v = vals[xi.data_ptr()]
+            if device_gates:
+                vp = F.pad(v, (1, 1, 1, 1), value=float("-inf"))
+                pt = vp.unfold(2, 3, 2).unfold(3, 3, 2)                      # [B,C,Ho,Wo,3,3]
+                pt = pt.reshape(*pt.shape[:4], 9)
+                tap = idx.permute(0, 3, 1, 2).long().unsqueeze(-1)
+                o = pt.gather(-1, tap).squeeze(-1)
+                best = pt.max(-1).values
+                bad = o != best
+                if bool(bad.any()):
+                    stats["pool_flips"] += int(bad.sum())
+                    assert float((best - o)[bad].max()) <= 1e-4 * float(best.abs().max()), "max-pool tap differs off a tie"
+            else:
+                o = F.max_pool2d(v, 3, 2, 1)
+            vals[y.data_ptr()] = o
+        elif rec[0] == "avgpool":
+            v = vals[rec[1].data_ptr()]
+            vals[rec[2].data_ptr()] = F.avg_pool2d(v, v.shape[-1]).flatten(1)
+    return vals[tape[-1][2].data_ptr()]
+
+
 def check_resnet_same_branch(arch, dev, image_size, lib=None, B=4, ipe=4, tol=1e-4, fwd_tol=3e-5):
     """ResNet forward/backward at a given resolution against exact (fp64) arithmetic on the SAME piecewise-linear branch.
 
@@ -419,60 +573,15 @@ def check_resnet_same_branch(arch, dev, image_size, lib=None, B=4, ipe=4, tol=1e
     gf = torch.randn(feats.shape, generator=g).to(dev)
     eng.backward(gf)
     stats = {"relu_flips": 0, "pool_flips": 0, "gates": 0}
+    params = {}
 
-    def nchw(t):
-        return t.detach().double().permute(0, 3, 1, 2)
+    def leaf(t):
+        if id(t) not in params:
+            params[id(t)] = t.detach().double().clone().requires_grad_(True)
+        return params[id(t)]
 
     def replay(device_gates):
-        vals, params = {}, {}
-
-        def P(t):
-            if id(t) not in params:
-                params[id(t)] = t.detach().double().clone().requires_grad_(True)
-            return params[id(t)]
-
-        vals[tape[0][1].data_ptr()] = nchw(tape[0][1])
-        for rec in tape:
-            if rec[0] == "conv":
-                _, xi, out, m, (_, _, _, _, _, st, pad, dil) = rec
-                vals[out.data_ptr()] = F.conv2d(vals[xi.data_ptr()], P(m.weight), None, st, pad, dil)
-            elif rec[0] == "bn":
-                _, xi, y, m, _, _, res, relu, _ = rec
-                o = F.batch_norm(vals[xi.data_ptr()], None, None, P(m.weight), P(m.bias), True, 0.0, 1e-5)
-                if res is not None:
-                    o = o + vals[res.data_ptr()]
-                if relu and device_gates:
-                    mask = nchw(y) > 0
-                    diff = mask != (o > 0)
-                    stats["gates"] += mask.numel()
-                    if bool(diff.any()):
-                        stats["relu_flips"] += int(diff.sum())
-                        assert float(o[diff].abs().max()) <= 1e-4 * float(o.abs().max()), "ReLU gate differs off zero"
-                    o = o * mask
-                elif relu:
-                    o = o.relu()
-                vals[y.data_ptr()] = o
-            elif rec[0] == "maxpool":
-                _, xi, y, idx = rec
-                v = vals[xi.data_ptr()]
-                if device_gates:
-                    vp = F.pad(v, (1, 1, 1, 1), value=float("-inf"))
-                    pt = vp.unfold(2, 3, 2).unfold(3, 3, 2)                      # [B,C,Ho,Wo,3,3]
-                    pt = pt.reshape(*pt.shape[:4], 9)
-                    tap = idx.permute(0, 3, 1, 2).long().unsqueeze(-1)
-                    o = pt.gather(-1, tap).squeeze(-1)
-                    best = pt.max(-1).values
-                    bad = o != best
-                    if bool(bad.any()):
-                        stats["pool_flips"] += int(bad.sum())
-                        assert float((best - o)[bad].max()) <= 1e-4 * float(best.abs().max()), "max-pool tap differs off a tie"
-                else:
-                    o = F.max_pool2d(v, 3, 2, 1)
-                vals[y.data_ptr()] = o
-            elif rec[0] == "avgpool":
-                v = vals[rec[1].data_ptr()]
-                vals[rec[2].data_ptr()] = F.avg_pool2d(v, v.shape[-1]).flatten(1)
-        return vals[tape[-1][2].data_ptr()], params
+        return resnet_replay64(tape, device_gates, stats, leaf), params
 
     f_free, _ = replay(False)
     sd = {k: v.detach().double().cpu() for k, v in net.state_dict().items()}
@@ -594,3 +703,108 @@ def check_reference_golden_regression(dev, kernel, lib=None, tol=1e-4, drift_tol
     mse = model.test_loop(5)
     assert abs(float(mse) - float(gold["test_mse"])) <= 10 * drift_tol * float(gold["test_mse"]), (float(mse), float(gold["test_mse"]))
     return model
+
+
+# ----------------------------------------------------------------------------- sines: against the reference script's own run
+# tests/golden/sines_reference.npz: observed while running the reference's unmodified sines/train_DKT.py::main()
+# (tests/golden/make_golden_sines.py): data of the first training tasks, parameters before each of those steps, the
+# losses it computed, the trained state after its 50 000 iterations, predictions on its first test tasks.
+_SINES_GP = {"constant": "gp.mean_module.constant", "raw_noise": "gp.likelihood.noise_covar.raw_noise",
+             "raw_mixture_weights": "gp.covar_module.raw_mixture_weights",
+             "raw_mixture_means": "gp.covar_module.raw_mixture_means",
+             "raw_mixture_scales": "gp.covar_module.raw_mixture_scales"}
+
+
+def sines_gold():
+    return np.load(os.path.join(_GOLD, "sines_reference.npz"))
+
+
+def sines_state(gold, prefix):
+    net = {k: torch.from_numpy(gold["%s.net.%s" % (prefix, k)].copy()) for k in
+           ("layer1.weight", "layer1.bias", "layer2.weight", "layer2.bias")}
+    gp = {k: torch.from_numpy(gold["%s.%s" % (prefix, v)].copy()) for k, v in _SINES_GP.items()}
+    return net, gp
+
+
+def sines_test_tasks(gold):
+    """(x_support, y_support, x_query, mean, lower, upper) of the recorded test tasks; the support indices are recovered
+    from the recorded support targets (exact float matches inside y_all)."""
+    out = []
+    j = 0
+    while "test%d.mean" % j in gold.files:
+        x_all, y_all = gold["test%d.x_all" % j], gold["test%d.y_all" % j]
+        ys = gold["test%d.y_support" % j]
+        idx = np.array([int(np.where(y_all == v)[0][0]) for v in ys])
+        q = np.setdiff1d(np.arange(len(y_all)), idx)
+        out.append((torch.from_numpy(x_all[idx]), torch.from_numpy(ys.copy()), torch.from_numpy(x_all[q]),
+                    gold["test%d.mean" % j], gold["test%d.lower" % j], gold["test%d.upper" % j]))
+        j += 1
+    return out
+
+
+def check_sines_oracle_against_reference_run(tol=2e-5):
+    """oracle/episode.py::OracleSines vs the reference script: loss of each recorded step from the recorded
+    parameters, the first Adam update, predictions of the trained model."""
+    gold = sines_gold()
+    n = len(gold["loss"])
+    for i in range(n):
+        o = oep.OracleSines()
+        o.p, o.gp = sines_state(gold, "step%d" % i)
+        r = o.train_step(torch.from_numpy(gold["train_x"][i]), torch.from_numpy(gold["train_y"][i]))
+        assert abs(float(r["loss"]) - gold["loss"][i]) <= tol * abs(gold["loss"][i]), (i, float(r["loss"]), gold["loss"][i])
+        if i == 0:      # a fresh Adam's first update: +-lr on every element whose gradient is not rounding noise
+            nxt_net, nxt_gp = sines_state(gold, "step1")
+            for k, v in o.p.items():
+                big = r["grads"][k].abs() > 1e-6
+                assert float((v.detach() - nxt_net[k]).abs()[big].max()) <= 2e-6, k
+            for k, v in o.gp.items():
+                if v.requires_grad:
+                    big = r["grads"][k].abs() > 1e-6
+                    assert float((v.detach() - nxt_gp[k].view_as(v)).abs()[big].max()) <= 2e-6, k
+    o = oep.OracleSines()
+    o.p, o.gp = sines_state(gold, "trained")
+    mses = []
+    for xs, ys, xq, mean, lower, upper in sines_test_tasks(gold):
+        m, v = o.predict(xs, ys, xq)
+        assert rel_err(m, torch.from_numpy(mean)) <= 1e-4
+        sd2 = 2.0 * v.sqrt()
+        assert rel_err(m - sd2, torch.from_numpy(lower)) <= 1e-4 and rel_err(m + sd2, torch.from_numpy(upper)) <= 1e-4
+    return gold
+
+
+def check_sines_against_reference_run(dev, lib=None, tol=1e-4):
+    """The CUDA SinesDKT vs the reference script's own run: per-step loss from the recorded parameters, first Adam
+    update, and the trained model's predictive mean / confidence region on the recorded test tasks."""
+    from deep_kernel_transfer_b200.sines import SinesDKT
+    gold = sines_gold()
+
+    def load(model, prefix):
+        net, gp = sines_state(gold, prefix)
+        model.net.load_state_dict(net)
+        with torch.no_grad():
+            model.mean_module.constant.copy_(gp["constant"].view(1))
+            model.likelihood.noise_covar.raw_noise.copy_(gp["raw_noise"].view(1))
+            for nm in ("raw_mixture_weights", "raw_mixture_means", "raw_mixture_scales"):
+                getattr(model.covar_module, nm).copy_(gp[nm].view_as(getattr(model.covar_module, nm)))
+    for i in range(len(gold["loss"])):
+        model = SinesDKT(lib=lib)
+        load(model, "step%d" % i)
+        model = model.to(dev)
+        loss = model.train_step(torch.from_numpy(gold["train_x"][i]).to(dev), torch.from_numpy(gold["train_y"][i]).to(dev))
+        assert int(model._last_info.cpu().abs().sum()) == 0
+        assert abs(float(loss) - gold["loss"][i]) <= tol * abs(gold["loss"][i]), (i, float(loss), gold["loss"][i])
+        if i == 0:
+            nxt_net, _ = sines_state(gold, "step1")
+            for k, v in model.net.state_dict().items():
+                g = dict(model.net.named_parameters())[k].grad.cpu()
+                big = g.abs() > 1e-5
+                assert float((v.cpu() - nxt_net[k]).abs()[big].max()) <= 5e-6, k
+    model = SinesDKT(lib=lib)
+    load(model, "trained")
+    model = model.to(dev)
+    for xs, ys, xq, mean, lower, upper in sines_test_tasks(gold):
+        m, v = model.predict(xs.to(dev), ys.to(dev), xq.to(dev))
+        m, v = m.cpu(), v.cpu()
+        assert rel_err(m, torch.from_numpy(mean)) <= tol, rel_err(m, torch.from_numpy(mean))
+        sd2 = 2.0 * v.sqrt()
+        assert rel_err(m - sd2, torch.from_numpy(lower)) <= tol and rel_err(m + sd2, torch.from_numpy(upper)) <= tol

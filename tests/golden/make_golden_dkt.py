@@ -1,15 +1,23 @@
-"""Golden vectors for the CONTROL FLOW of the hot path, produced by RUNNING THE REFERENCE'S OWN, UNMODIFIED
-``methods/DKT.py`` and ``methods/DKT_regression.py`` (imported from /root/reference, which exists only in the authoring
-container -- the fixtures are committed).
+"""Golden vectors of the hot path, produced by RUNNING THE REFERENCE'S OWN, UNMODIFIED ``methods/DKT.py`` and
+``methods/DKT_regression.py`` (imported from /root/reference, which exists only in the authoring container -- the
+fixtures are committed) on its own, unmodified ``backbone.py``.
 
-GPyTorch is not installable offline, so the reference modules are imported on top of oracle/gpytorch_standin (a minimal
-stand-in for the GPyTorch classes those files touch, whose ARITHMETIC is oracle/gp.py).  What these fixtures therefore
-pin is everything the reference itself writes around the GP calls -- which images feed which call, the +-1 target layout,
-train / eval switching of the backbone (batch vs running statistics), the per-call Adam with its two learning rates,
-monitoring predictions conditioned on the pre-update features with post-update hyper-parameters, the ``zip``
-truncations, ``correct`` / ``test_loop`` / ``get_logits``, the regression loops -- i.e. that oracle/episode.py restates
-``train_loop`` / ``correct`` / ``get_logits`` / ``test_loop`` faithfully.  They do NOT pin the GP arithmetic against
-GPyTorch (still unpinned).
+GPyTorch is not installable offline, so the reference modules are imported on top of oracle/gpytorch_standin: a
+self-contained stand-in for the GPyTorch classes those files touch whose arithmetic is INDEPENDENT of oracle/gp.py --
+kernels written the way GPyTorch 1.0.1 evaluates them, LAPACK Cholesky / solves in float64 through scipy, analytic
+gradient of the Gaussian log-density -- and which this script first validates against scikit-learn's
+GaussianProcessRegressor (marginal likelihood, its gradient, predictive mean and standard deviation; linear and RBF
+kernels).  So the chain of evidence for every number in these files is
+
+    scikit-learn GPR  <->  stand-in (scipy/LAPACK fp64)  ->  reference DKT.py / DKT_regression.py / backbone.py (unmodified)
+                      ->  tests/golden/dkt_*.npz  <-  oracle/episode.py + oracle/gp.py (torch.linalg + autograd)   [tests/test_oracle.py]
+                                                  <-  the CUDA path                                                  [tests/test_dkt_gpu.py]
+
+What these fixtures pin: everything the reference itself writes around the GP calls (which images feed which call, the
++-1 target layout, train / eval switching of the backbone, the per-call Adam with its two learning rates, monitoring
+predictions conditioned on the pre-update features with post-update hyper-parameters, the ``zip`` truncations,
+``correct`` / ``test_loop`` / ``get_logits``, the regression loops) AND the GP arithmetic as an evaluation that shares no
+code with oracle/gp.py.  What stays unpinned: a real GPyTorch 1.0.1 install.
 
 ``.cuda()`` is patched to the identity so the reference's hard-coded device moves run on the CPU; no reference source is
 edited or copied.
@@ -67,14 +75,13 @@ def load_backbone(module, p):
 
 def gp_perturbation(kernel, n_models):
     """Non-default, per-class-distinct raw hyper-parameters so the fixtures are sensitive to which model gets which."""
-    from oracle import gp as ogp
     out = {"constant": torch.tensor([0.05 * (c + 1) for c in range(n_models)]),
            "raw_outputscale": torch.tensor([0.1 * c - 0.1 for c in range(n_models)])}
     if kernel in ("rbf", "matern"):
         out["raw_lengthscale"] = torch.tensor([30.0 + 5.0 * c for c in range(n_models)])   # un-normalised D=1600 features
     if kernel == "linear":
         out["raw_variance"] = torch.tensor([-3.0 + 0.3 * c for c in range(n_models)])
-    return {k: v for k, v in out.items() if k in ogp.trainable_gp_names(kernel)}
+    return out
 
 
 def set_ref_gp(models, pert):
@@ -195,6 +202,71 @@ def regression_case(kernel, ref_backbone, ref_reg):
     return out
 
 
+def validate_standin_against_sklearn():
+    """The stand-in's marginal likelihood (+ gradient w.r.t. the log hyper-parameters), predictive mean and standard
+    deviation against scikit-learn's GaussianProcessRegressor for ScaleKernel(Linear) and ScaleKernel(RBF) + learned
+    noise, at float64-rounding level."""
+    import gpytorch
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import RBF, ConstantKernel, DotProduct, WhiteKernel
+    rs = np.random.RandomState(0)
+    n, d, m = 17, 5, 9
+    x, xt, y = rs.randn(n, d), rs.randn(m, d), rs.randn(n)
+    worst = 0.0
+    for kind in ("linear", "rbf"):
+        lik = gpytorch.likelihoods.GaussianLikelihood()
+        base = gpytorch.kernels.LinearKernel() if kind == "linear" else gpytorch.kernels.RBFKernel()
+
+        class Model(gpytorch.models.ExactGP):
+            def __init__(self):
+                super().__init__(torch.from_numpy(x), torch.from_numpy(y), lik)
+                self.mean_module = gpytorch.means.ConstantMean()
+                self.covar_module = gpytorch.kernels.ScaleKernel(base)
+
+            def forward(self, a):
+                return gpytorch.distributions.MultivariateNormal(self.mean_module(a), self.covar_module(a))
+        model = Model().double()
+        lik.double()
+        with torch.no_grad():
+            model.covar_module.raw_outputscale.fill_(0.3)
+            lik.noise_covar.raw_noise.fill_(-0.7)
+            if kind == "rbf":
+                base.raw_lengthscale.fill_(0.9)
+        s = float(model.covar_module.outputscale)
+        noise = float(lik.noise)
+        if kind == "linear":
+            v = float(base.variance)
+            sk = ConstantKernel(s * v) * DotProduct(sigma_0=0.0) + WhiteKernel(noise)
+        else:
+            sk = ConstantKernel(s) * RBF(float(base.lengthscale)) + WhiteKernel(noise)
+        gpr = GaussianProcessRegressor(kernel=sk, optimizer=None, alpha=0.0).fit(x, y)
+        lml, dlml = gpr.log_marginal_likelihood(gpr.kernel_.theta, eval_gradient=True)
+        model.train(); lik.train()
+        mll = gpytorch.mlls.ExactMarginalLogLikelihood(lik, model)
+        val = mll(model(*model.train_inputs), model.train_targets) * n
+        val.backward()
+        worst = max(worst, abs(float(val) - lml) / abs(lml))
+        # d/d log(noise) = d/d raw_noise / (d noise/d raw_noise) * noise ; same chain rule for the output scale
+        sig = lambda r: 1.0 / (1.0 + np.exp(-r))
+        g_noise = float(lik.noise_covar.raw_noise.grad) / sig(-0.7) * noise
+        g_scale = float(model.covar_module.raw_outputscale.grad) / sig(0.3) * s
+        names = [h.name for h in gpr.kernel_.hyperparameters if not h.fixed]
+        g_sk = dict(zip(names, dlml))
+        worst = max(worst, abs(g_noise - g_sk["k2__noise_level"]) / abs(g_sk["k2__noise_level"]))
+        worst = max(worst, abs(g_scale - g_sk["k1__k1__constant_value"]) / abs(g_sk["k1__k1__constant_value"]))
+        if kind == "rbf":
+            g_ls = float(base.raw_lengthscale.grad) / sig(0.9) * float(base.lengthscale)
+            worst = max(worst, abs(g_ls - g_sk["k1__k2__length_scale"]) / abs(g_sk["k1__k2__length_scale"]))
+        model.eval(); lik.eval()
+        with torch.no_grad():
+            pred = lik(model(torch.from_numpy(xt)))
+        mu, sd = gpr.predict(xt, return_std=True)
+        worst = max(worst, float(np.abs(pred.mean.numpy() - mu).max() / np.abs(mu).max()))
+        worst = max(worst, float(np.abs(pred.stddev.numpy() - sd).max() / np.abs(sd).max()))
+    assert worst < 1e-9, worst
+    return worst
+
+
 def main():
     sys.path.insert(0, ROOT)                          # for ``oracle``
     sys.path.insert(0, os.path.join(ROOT, "oracle", "gpytorch_standin"))
@@ -208,6 +280,7 @@ def main():
     import methods.DKT_regression as ref_reg
     assert ref_dkt.__file__.startswith(REF) and ref_reg.__file__.startswith(REF) and ref_backbone.__file__.startswith(REF)
 
+    print("stand-in vs scikit-learn GaussianProcessRegressor: worst relative difference %.2e" % validate_standin_against_sklearn())
     torch.set_num_threads(1)                          # identical reduction order on any host
     for kernel in CLS_KERNELS:
         out = classification_case(kernel, ref_backbone, ref_dkt)

@@ -1,6 +1,8 @@
 """Per-kernel parity checks shared by the CPU-emulation tests (tests/test_kernels_emu.py, host logic of the
 same kernel sources) and the GPU tests proper (tests/test_kernels_gpu.py, through the C ABI on a B200).
 The reference for every check is plain torch fp32/fp64 on CPU (the oracle for single operators)."""
+import math
+
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -785,3 +787,63 @@ def check_episode_transform_errors(lib, dev):
         assert "code 3" in str(ex)
     else:
         raise AssertionError("out-of-image crop box was not reported")
+
+
+def check_gp_jitter(lib, dev, N=12, large=False, seed=90):
+    """psd_safe_cholesky semantics (GPyTorch utils/cholesky.py; the reference relies on them, README.md:27): a system whose
+    K~ has a slightly negative eigenvalue factorises after the 2nd retry (1e-6 fails, 1e-5 passes) and its outputs are
+    those of K~ + 1e-5 I; a plainly indefinite one fails every retry -> positive info, NaN loss, ZERO gradients; with
+    jitter = 0 there is a single attempt."""
+    g = torch.Generator().manual_seed(seed)
+    q, _ = torch.linalg.qr(torch.randn(N, N, generator=g, dtype=torch.float64))
+    noise = float(F.softplus(torch.tensor(-1.0)) + 1e-4)
+    s = float(F.softplus(torch.tensor(0.3)))
+
+    def system(min_eig):
+        ev = torch.linspace(0.5, 2.0, N, dtype=torch.float64)
+        ev[0] = min_eig
+        kt = (q * ev) @ q.T
+        return ((kt - noise * torch.eye(N, dtype=torch.float64)) / s).float(), kt
+    E, C = 3, 1
+    kb_ok, _ = system(0.3)
+    kb_jit, kt_jit = system(-5e-6)
+    kb_bad, _ = system(-1.0)
+    kb = torch.stack([kb_ok, kb_jit, kb_bad]).view(E, 1, N, N).contiguous().to(dev)
+    y = torch.randn(E, C, N, generator=g).to(dev)
+    ros, cst, rn = (torch.tensor([v], device=dev) for v in (0.3, 0.1, -1.0))
+    alpha = torch.full((E, C, N), 7.0, device=dev)
+    lt = torch.zeros(E, C, device=dev)
+    info = torch.zeros(E, C, device=dev, dtype=torch.int32)
+    dk = torch.full((E, C, N, N), 7.0, device=dev)
+    dh = torch.full((E, C, 3), 7.0, device=dev)
+
+    def fit(jitter):
+        if large:
+            work = torch.empty(lib.gp_large_work_floats(E, C, N), device=dev)
+            lib.gp_fit_large(kb, N * N, y, C * N, ros, cst, rn, alpha, None, lt, info, dk, dh, work, 1.0, jitter, E, C, N, 0)
+        else:
+            lib.gp_fit(kb, N * N, y, C * N, ros, cst, rn, alpha, None, lt, info, dk, dh, 1.0, jitter, E, C, N, 0)
+    fit(1e-6)
+    got = info.cpu().view(-1).tolist()
+    assert got[0] == 0 and got[1] == -2 and got[2] > 0, got
+    lt_c = lt.cpu().view(-1)
+    assert bool(torch.isnan(lt_c[2])) and bool(torch.isfinite(lt_c[:2]).all())
+    assert float(dk[2].abs().max()) == 0.0 and float(dh[2].abs().max()) == 0.0 and float(alpha[2].abs().max()) == 0.0
+    # the retried system equals the plain factorisation of K~ + 1e-5 I
+    ktj = kt_jit + 1e-5 * torch.eye(N, dtype=torch.float64)
+    r = (y[1, 0].cpu().double() - 0.1)
+    l = torch.linalg.cholesky(ktj)
+    a_ref = torch.cholesky_solve(r.unsqueeze(-1), l).squeeze(-1)
+    logp = -0.5 * (float(r @ a_ref) + 2.0 * float(torch.log(torch.diagonal(l)).sum()) + N * math.log(2 * math.pi))
+    # the smallest eigenvalue of the retried matrix is 5e-6 +- fp32 rounding of its O(1) entries (~1e-7 .. 1e-6), and the
+    # quadratic form is dominated by 1 / that eigenvalue: the comparison can only hold to ~20 %
+    assert abs(float(lt_c[1]) - (-logp / N)) <= 0.25 * abs(logp / N), (float(lt_c[1]), -logp / N)
+    # sticky status over several fits + a single attempt when jitter == 0
+    sticky = torch.zeros(2, device=dev, dtype=torch.int32)
+    lib.gp_info_accumulate(info, sticky, E * C, 0)
+    fit(0.0)
+    got0 = info.cpu().view(-1).tolist()
+    assert got0[0] == 0 and got0[1] > 0 and got0[2] > 0, got0
+    lib.gp_info_accumulate(info, sticky, E * C, 0)
+    hi, lo = sticky.cpu().tolist()
+    assert hi == max(got + got0) and lo == -2

@@ -1,0 +1,111 @@
+"""Parity against the CPU oracle (fp32 run + fp64 arbiter) AT the shapes BASELINE.json quotes its metric on
+(reference methods/DKT.py:113-272), through the public DKT module -> C ABI.
+
+Bar, per key (printed by every test):
+  * outputs -- loss, monitoring predictive means, test logits, predictive variance: 1e-4 relative (north_star);
+    every class arg-max / hit count: bit-exact;
+  * gradients: 1e-4 relative against a float64 replay of the whole step on the DEVICE's own ReLU / max-pool branch
+    (tests/branch_checks.py: the device's gates are reproduced bit for bit on the host, every gate that differs from the
+    free-running float64 choice is asserted to sit within 1e-4 of its threshold / tie).  The distance to the
+    FREE-running fp64 oracle is printed next to the fp32 oracle's own (keys ``free.*``): both are ~1e-3 at these sizes
+    because single gates within rounding of their threshold flip between any two fp32 evaluations.
+"""
+import numpy as np
+import pytest
+import torch
+
+import dkt_checks
+from oracle import episode as oep
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda", 0) if torch.cuda.is_available() else None
+
+
+def _show(tag, report):
+    print("\n[%s] key: device-vs-fp64 | fp32-oracle-vs-fp64 | bar" % tag)
+    print("   branch:", report.get("_branch"))
+    for k in sorted(report):
+        if k.startswith("_"):
+            continue
+        v, f, b = report[k]
+        print("   %-22s %.2e | %.2e | %.2e" % (k, v, f, b))
+
+
+def test_cfg3_5way_5shot_conv4_bncossim_E2():
+    """configs[2], the headline: 5-way 5-shot, Q=16 (N=105), 84x84, Conv4 + bn_out + cosine kernel, E=2 packed."""
+    from deep_kernel_transfer_b200 import backbone
+    report = {}
+    model, oracle, worst = dkt_checks.check_train_step(backbone.Conv4, DEV, image_size=84, n_way=5, n_support=5,
+                                                       n_query=16, E=2, steps=1, report=report, same_branch=True)
+    _show("cfg3", report)
+    for k in ("loss", "mon.mean_s", "mon.mean_q"):
+        assert report[k][2] == 1e-4 and report[k][0] <= 1e-4, (k, report[k])
+    dkt_checks.check_correct(model, oracle, DEV, image_size=84, n_way=5, n_support=5, n_query=15, extras=False)
+
+
+def test_cfg2_5way_1shot_conv4_bncossim():
+    """configs[1]: 5-way 1-shot, Q=16 (N=85), E=1 (the reference's one-episode-per-step) and E=2."""
+    from deep_kernel_transfer_b200 import backbone
+    for E in (1, 2):
+        report = {}
+        model, oracle, worst = dkt_checks.check_train_step(backbone.Conv4, DEV, image_size=84, n_way=5, n_support=1,
+                                                           n_query=16, E=E, steps=1, report=report, same_branch=True)
+        _show("cfg2 E=%d" % E, report)
+        for k in ("loss", "mon.mean_s", "mon.mean_q"):
+            assert report[k][2] == 1e-4 and report[k][0] <= 1e-4, (k, report[k])
+    dkt_checks.check_correct(model, oracle, DEV, image_size=84, n_way=5, n_support=1, n_query=15, extras=False)
+
+
+def test_cfg4_5way_5shot_resnet18_rbf():
+    """configs[3]: 5-way 5-shot, Q=16 (N=105), 224x224, ResNet18, RBF kernel (no normalisation, D=512)."""
+    from deep_kernel_transfer_b200 import backbone
+    report = {}
+    dkt_checks.check_train_step_arch("ResNet18", backbone.ResNet18, DEV, image_size=224, n_way=5, n_support=5,
+                                     n_query=16, E=1, kernel="rbf", report=report, lengthscale=(18.0, 24.0),
+                                     same_branch=True)
+    _show("cfg4", report)
+    assert report["loss"][0] <= 1e-4 and report["mon.mean"][0] <= 1e-4
+
+
+@pytest.mark.parametrize("kernel", ["bncossim", "rbf"])
+def test_cfg5_20way_5shot_n420_train_step(kernel):
+    """configs[4] episode shape: 20-way 5-shot, Q=16 -> N=420 exact-GP systems (the tiled Cholesky path) through
+    train_step + monitoring.  Backbone = Conv4 at 84x84 so that the fp64 oracle of a 420-image episode fits the host."""
+    from deep_kernel_transfer_b200 import backbone
+    report = {}
+    # un-normalised D=1600 features: a lengthscale of 30..40 keeps |x - x'|^2 / l^2 = O(1) (as tests/golden/make_golden_dkt.py)
+    over = {"raw_lengthscale": torch.linspace(30.0, 40.0, 20)} if kernel == "rbf" else None
+    dkt_checks.check_train_step(backbone.Conv4, DEV, image_size=84, n_way=20, n_support=5, n_query=16, E=1, steps=1,
+                                kernel=kernel, report=report, same_branch=True, gp_override=over)
+    _show("cfg5 " + kernel, report)
+    for k in ("loss", "mon.mean_s", "mon.mean_q"):
+        assert report[k][2] == 1e-4 and report[k][0] <= 1e-4, (k, report[k])
+
+
+def test_cfg5_20way_resnet50_rbf():
+    """configs[4] backbone: ResNet50 at 224x224 with 20 classes (1-shot, Q=1: N=40 keeps the fp64 oracle within host
+    memory; the N=420 GP is covered by the test above and by tests/test_kernels_gpu.py::test_gp_large)."""
+    from deep_kernel_transfer_b200 import backbone
+    report = {}
+    dkt_checks.check_train_step_arch("ResNet50", backbone.ResNet50, DEV, image_size=224, n_way=20, n_support=1,
+                                     n_query=1, E=1, kernel="rbf", report=report, lengthscale=(36.0, 48.0),
+                                     same_branch=True)
+    _show("cfg5 R50", report)
+    assert report["loss"][0] <= 1e-4 and report["mon.mean"][0] <= 1e-4
+
+
+@pytest.mark.parametrize("n_support", [1, 5])
+def test_correct_5way_M75(n_support):
+    """The test path at the reference's evaluation shape (test.py:65-80: 5-way, 15 queries per class -> M=75)."""
+    from deep_kernel_transfer_b200 import backbone
+    from deep_kernel_transfer_b200.methods.DKT import DKT
+    oracle = oep.OracleDKT("Conv4", "bncossim", n_way=5, n_support=n_support, seed=3)
+    oracle.gp["raw_outputscale"] = torch.linspace(-0.3, 0.6, 5)
+    oracle.gp["constant"] = torch.linspace(0.1, -0.2, 5)
+    # running statistics of a trained model are not the identity: take them from two train-mode oracle steps
+    for s in range(2):
+        oracle.train_step(torch.stack([oep.synthetic_episode(50 + s, 5, n_support, 16, 84)]), monitor=False)
+    model = DKT(backbone.Conv4, 5, n_support, kernel="bncossim")
+    dkt_checks.load_oracle_params(model, oracle)
+    model = model.to(DEV)
+    dkt_checks.check_correct(model, oracle, DEV, image_size=84, n_way=5, n_support=n_support, n_query=15, episodes=4)

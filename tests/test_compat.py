@@ -62,6 +62,80 @@ def test_load_reference_style_checkpoint(tmp_path, kernel, new_style):
         dst.load_state_dict({**tmp["state"], "model.models.0.bogus": torch.zeros(1)})
 
 
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.mark.parametrize("kernel", ["bncossim", "rbf"])
+def test_checkpoint_written_by_the_reference_loads(kernel):
+    """tests/golden/ref_checkpoint_cls_*.tar was written by the reference's own DKT(backbone.Conv4) via train.py's
+    ``torch.save({'epoch', 'state': model.state_dict()})`` (tests/golden/make_golden_state.py).  The drop-in has the SAME
+    key set (incl. the mll.mlls / model.likelihood aliases GPyTorch registers), strict-loads it, holds the same tensors."""
+    import numpy as np
+    from deep_kernel_transfer_b200 import backbone
+    from deep_kernel_transfer_b200.methods.DKT import DKT
+    ck = torch.load(os.path.join(GOLD, "ref_checkpoint_cls_%s.tar" % kernel))
+    ref_keys = set(np.load(os.path.join(GOLD, "ref_checkpoint_cls_%s.npz" % kernel))["keys"].tolist())
+    assert ck["epoch"] == 3 and set(ck["state"].keys()) == ref_keys
+    dst = DKT(backbone.Conv4, 5, 1, kernel=kernel)
+    assert set(dst.state_dict().keys()) == ref_keys, set(dst.state_dict().keys()) ^ ref_keys
+    dst.load_state_dict(ck["state"])                                   # strict
+    own = dst.state_dict()
+    for k, v in ck["state"].items():
+        assert own[k].shape == v.shape and torch.equal(own[k], v), k
+    # the frozen pieces stay frozen, the aliases stay aliases
+    assert not dst.model.models[0].likelihood.noise_covar.raw_noise.requires_grad
+    assert dst.mll.mlls[2].model is dst.model.models[2] and dst.model.likelihood.likelihoods[1] is dst.likelihood.likelihoods[1]
+
+
+@pytest.mark.parametrize("kernel", ["rbf", "spectral"])
+def test_regression_checkpoint_written_by_the_reference_loads(kernel):
+    """Same for DKT_regression.save_checkpoint (DKT_regression.py:99-104), written by the reference's own class."""
+    import numpy as np
+    from deep_kernel_transfer_b200 import backbone
+    from deep_kernel_transfer_b200.methods.DKT_regression import DKT as DKTR
+    path = os.path.join(GOLD, "ref_checkpoint_reg_%s.tar" % kernel)
+    meta = np.load(os.path.join(GOLD, "ref_checkpoint_reg_%s.npz" % kernel))
+    ck = torch.load(path)
+    dst = DKTR(backbone.Conv3(), kernel=kernel)
+    assert set(dst.model.state_dict().keys()) == set(meta["gp_keys"].tolist()) == set(ck["gp"].keys())
+    assert set(dst.likelihood.state_dict().keys()) == set(meta["likelihood_keys"].tolist())
+    assert set(dst.feature_extractor.state_dict().keys()) == set(meta["net_keys"].tolist())
+    dst.load_checkpoint(path)
+    for part, mod in (("gp", dst.model), ("likelihood", dst.likelihood), ("net", dst.feature_extractor)):
+        own = mod.state_dict()
+        for k, v in ck[part].items():
+            assert torch.equal(own[k].reshape(v.shape), v), (part, k)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="needs the reference checkout (authoring container only)")
+def test_reference_strict_loads_our_checkpoint(tmp_path):
+    """The other direction: a checkpoint written by the drop-in strict-loads into the reference's own DKT / regression
+    DKT (unmodified methods/*.py + backbone.py on the GPyTorch stand-in)."""
+    code = (
+        "import sys, types, torch\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "torch.Tensor.cuda = lambda self, *a, **k: self; torch.nn.Module.cuda = lambda self, *a, **k: self\n"
+        "sys.modules.setdefault('h5py', types.ModuleType('h5py'))\n"
+        "import backbone, methods.DKT as D, methods.DKT_regression as R\n"
+        "assert D.__file__.startswith(%r)\n"
+        "D.kernel_type = 'bncossim'\n"
+        "m = D.DKT(backbone.Conv4, n_way=5, n_support=1)\n"
+        "ck = torch.load(%r)\n"
+        "m.load_state_dict(ck['state'])\n"
+        "R.kernel_type = 'spectral'\n"
+        "r = R.DKT(backbone.Conv3())\n"
+        "r.load_checkpoint(%r)\n" % (os.path.join(ROOT, "oracle", "gpytorch_standin"), REF, REF,
+                                     str(tmp_path / "ours_cls.tar"), str(tmp_path / "ours_reg.tar")))
+    from deep_kernel_transfer_b200 import backbone
+    from deep_kernel_transfer_b200.methods.DKT import DKT
+    from deep_kernel_transfer_b200.methods.DKT_regression import DKT as DKTR
+    torch.manual_seed(0)
+    torch.save({"epoch": 1, "state": DKT(backbone.Conv4, 5, 1, kernel="bncossim").state_dict()}, str(tmp_path / "ours_cls.tar"))
+    DKTR(backbone.Conv3(), kernel="spectral").save_checkpoint(str(tmp_path / "ours_reg.tar"))
+    r = subprocess.run([sys.executable, "-c", code], cwd="/tmp", capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+
 def test_checkpoint_file_helpers(tmp_path):
     sys.path.insert(0, ROOT)
     import io_utils

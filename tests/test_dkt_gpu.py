@@ -130,3 +130,93 @@ def test_matches_reference_run_classification(kernel):
 @pytest.mark.parametrize("kernel", ["rbf", "spectral"])
 def test_matches_reference_run_regression(kernel):
     dkt_checks.check_reference_golden_regression(DEV, kernel)
+
+
+def test_sines_matches_reference_script_run():
+    """BASELINE configs[0]: against the reference's own sines/train_DKT.py::main() (tests/golden/make_golden_sines.py)."""
+    dkt_checks.check_sines_against_reference_run(DEV)
+
+
+def _state_episode(seed, n_way, per_class, image):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n_way, per_class, 3, image, image, generator=g)
+    return x + 0.5 * torch.randn(n_way, 1, 3, 1, 1, generator=g)
+
+
+@pytest.mark.parametrize("kernel", ["bncossim", "rbf"])
+def test_reference_checkpoint_classification(kernel):
+    """A checkpoint WRITTEN BY THE REFERENCE'S OWN DKT (tests/golden/make_golden_state.py, train.py:57-65 format) loaded
+    with load_state_dict(strict) gives the reference model's own logits / correct() on the CUDA path."""
+    import os
+    from deep_kernel_transfer_b200 import backbone
+    from deep_kernel_transfer_b200.methods.DKT import DKT
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    ck = torch.load(os.path.join(gdir, "ref_checkpoint_cls_%s.tar" % kernel))
+    meta = np.load(os.path.join(gdir, "ref_checkpoint_cls_%s.npz" % kernel))
+    model = DKT(backbone.Conv4, 5, 1, kernel=kernel)
+    model.load_state_dict(ck["state"])
+    model = model.to(DEV)
+    model.eval()
+    x = _state_episode(31, 5, 5, 84)
+    logits = model.get_logits(x).cpu()
+    assert dkt_checks.rel_err(logits, torch.from_numpy(meta["logits"])) <= 1e-4
+    assert np.array_equal(logits.numpy().argmax(1), meta["logits"].argmax(1))
+    assert tuple(model.correct(x)) == tuple(meta["correct"])
+
+
+@pytest.mark.parametrize("kernel", ["rbf", "spectral"])
+def test_reference_checkpoint_regression(kernel):
+    """Same for DKT_regression.save_checkpoint written by the reference's class: predictive mean and confidence region."""
+    import os
+    from deep_kernel_transfer_b200 import backbone
+    from deep_kernel_transfer_b200.methods.DKT_regression import DKT as DKTR
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    meta = np.load(os.path.join(gdir, "ref_checkpoint_reg_%s.npz" % kernel))
+    model = DKTR(backbone.Conv3(), kernel=kernel)
+    model.load_checkpoint(os.path.join(gdir, "ref_checkpoint_reg_%s.tar" % kernel))
+    model = model.to(DEV)
+    g = torch.Generator().manual_seed(41)
+    x_all = torch.rand(19, 3, 100, 100, generator=g)
+    y_all = torch.rand(19, generator=g) * 2 - 1
+    ind = [int(i) for i in meta["support_ind"]]
+    pred = model.predict(x_all[ind].to(DEV), y_all[ind].to(DEV), x_all.to(DEV))
+    lo, hi = pred.confidence_region()
+    assert dkt_checks.rel_err(pred.mean, torch.from_numpy(meta["mean"])) <= 1e-4
+    assert dkt_checks.rel_err(lo, torch.from_numpy(meta["lower"])) <= 1e-4
+    assert dkt_checks.rel_err(hi, torch.from_numpy(meta["upper"])) <= 1e-4
+
+
+def test_cholesky_status_warns_and_raises():
+    """Host side of psd_safe_cholesky: a fit that needed jitter warns (GPyTorch's message), one that stays indefinite
+    raises at the next status check; the sticky status covers every fit since the previous check."""
+    import warnings
+    from deep_kernel_transfer_b200 import _lib
+    from deep_kernel_transfer_b200.engine import GPHead, GPHeadParams, make_targets
+    lib = _lib.load()
+    C, N, D = 2, 8, 4
+    head = GPHead(lib, "linear", C, D, D, 1, DEV)
+    head.ensure(1, N)
+    HP = GPHeadParams()
+    HP.raw_outputscale = torch.zeros(C, device=DEV)
+    HP.constant = torch.zeros(C, device=DEV)
+    HP.raw_noise = torch.full((C,), -20.0, device=DEV)         # noise -> its 1e-4 floor
+    HP.raw_param = torch.zeros(C, device=DEV)
+    z = torch.randn(1, N, D, generator=torch.Generator().manual_seed(0)).to(DEV)      # rank 4 < N: K~ = s G + 1e-4 I
+    tg = make_targets(C, N // C, DEV)
+    head.fit(z, tg, HP, 1, N, want_grad=False)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        head.check()                                           # healthy: no warning, no error
+    # make the kernel matrix indefinite by hand: fit() on a Gram that the kernel epilogue turns negative
+    HP.raw_param = torch.full((C,), 0.0, device=DEV)
+    lib.gp_fit(-torch.eye(N, device=DEV).view(1, 1, N, N).contiguous(), 0, tg, 0, HP.raw_outputscale, HP.constant,
+               HP.raw_noise, head.w["alpha"], None, head.w["loss_terms"], head.w["info"], None, None, 1.0, 1e-6, 1, C, N, 0)
+    lib.gp_info_accumulate(head.w["info"], head.w["info_sticky"], C, 0)
+    head.fit(z, tg, HP, 1, N, want_grad=False)                 # a later healthy fit does not clear the sticky status
+    with pytest.raises(RuntimeError, match="NotPSDError"):
+        head.check()
+    head.check()                                               # ... which the check itself reset
+    head.w["info"].fill_(-2)
+    lib.gp_info_accumulate(head.w["info"], head.w["info_sticky"], C, 0)
+    with pytest.warns(RuntimeWarning, match="added jitter of 1.0e-05"):
+        head.check()

@@ -60,6 +60,11 @@ def test_gp_large(lib):
     kc.check_gp(lib, DEV, E=1, C=1, per_class=133, D=48, M=5, seed=8, large=True)    # N = 133: three tiles (5 rows in the last)
 
 
+def test_gp_jitter_retry(lib):
+    kc.check_gp_jitter(lib, DEV)
+    kc.check_gp_jitter(lib, DEV, N=70, large=True, seed=91)
+
+
 def test_adam(lib):
     kc.check_adam(lib, DEV)
 

@@ -64,6 +64,14 @@ def test_gp_large(lib):
     kc.check_gp(lib, DEV, E=1, C=4, per_class=128, D=512, M=64, seed=14, large=True, rtol=5e-4)    # N = 512
 
 
+def test_gp_jitter_retry(lib):
+    """psd_safe_cholesky retries (1e-6, 1e-5, 1e-4), NaN loss + zero gradients on a system that stays indefinite."""
+    kc.check_gp_jitter(lib, DEV)
+    kc.check_gp_jitter(lib, DEV, N=105, seed=92)
+    kc.check_gp_jitter(lib, DEV, N=70, large=True, seed=91)
+    kc.check_gp_jitter(lib, DEV, N=420, large=True, seed=93)
+
+
 def test_adam(lib):
     kc.check_adam(lib, DEV, n=100003)
 
