@@ -103,17 +103,17 @@ def check_bn_relu_pool(lib, dev, E=2, ipe=3, H=7, W=6, pool=1, in_pad=1, out_pad
     rm0, rv0 = torch.randn(64, generator=g) * 0.1, torch.rand(64, generator=g) + 0.5
     Ho, Wo = (H // 2, W // 2) if pool else (H, W)
     gout = torch.randn(B, 64, Ho, Wo, generator=g)
-    # reference: one BatchNorm batch per episode, sequential running-stat updates
-    yr = y.clone().requires_grad_(True)
-    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
-    rm, rv = rm0.clone(), rv0.clone()
+    # reference in float64: one BatchNorm batch per episode, sequential running-stat updates
+    yr = y.double().clone().requires_grad_(True)
+    gr, br = gamma.double().clone().requires_grad_(True), beta.double().clone().requires_grad_(True)
+    rm, rv = rm0.double().clone(), rv0.double().clone()
     outs = []
     for e in range(E):
         o = F.batch_norm(yr[e * ipe:(e + 1) * ipe], rm, rv, gr, br, True, 0.1, 1e-5)
         o = F.relu(o)
         outs.append(F.max_pool2d(o, 2) if pool else o)
     ref = torch.cat(outs, 0)
-    (ref * gout).sum().backward()
+    (ref * gout.double()).sum().backward()
     # device: partial sums as the conv epilogue would emit them (one "tile" per image)
     part = torch.stack([y.sum((2, 3)), (y * y).sum((2, 3))], 1).reshape(-1).to(dev)   # [B][1][2][64]
     mean = torch.empty(E, 64, device=dev)
@@ -140,15 +140,15 @@ def check_bn_relu_pool(lib, dev, E=2, ipe=3, H=7, W=6, pool=1, in_pad=1, out_pad
     lib.bn_relu_pool_bwd(yd, gd, mean, invstd, gamma.to(dev), beta.to(dev), gy, dg, db, partial, sums, scratch_d, B, H,
                          W, ipe, in_pad, out_pad, pool, 0)
     got_gy = from_padded_nhwc(gy.cpu()) if in_pad else gy.cpu().permute(0, 3, 1, 2)
-    _close(got_gy, yr.grad, rtol=2e-4, atol=1e-5, what="bn_relu_pool bwd gy")
-    _close(dg, gr.grad, rtol=2e-4, atol=1e-4, what="dgamma")
-    _close(db, br.grad, rtol=2e-4, atol=1e-4, what="dbeta")
+    _close(got_gy, yr.grad, rtol=1e-4, atol=1e-6, what="bn_relu_pool bwd gy")
+    _close(dg, gr.grad, rtol=1e-4, atol=1e-5, what="dgamma")
+    _close(db, br.grad, rtol=1e-4, atol=1e-5, what="dbeta")
     # eval mode
     em, ei = torch.empty(64, device=dev), torch.empty(64, device=dev)
     lib.bn_eval_prepare(drm, drv, em, ei, 64, 1e-5, 0)
     out2 = torch.zeros_like(out)
     lib.bn_relu_pool_fwd(yd, em, ei, gamma.to(dev), beta.to(dev), out2, B, H, W, 0, in_pad, out_pad, pool, 0)
-    o = F.relu(F.batch_norm(y, rm, rv, gamma, beta, False, 0.1, 1e-5))
+    o = F.relu(F.batch_norm(y.double(), rm, rv, gamma.double(), beta.double(), False, 0.1, 1e-5))
     ref2 = F.max_pool2d(o, 2) if pool else o
     got2 = from_padded_nhwc(out2.cpu()) if out_pad else out2.cpu().permute(0, 3, 1, 2)
     _close(got2, ref2, what="bn_relu_pool eval")
@@ -162,15 +162,15 @@ def check_head(lib, dev, E=2, N=7, Cch=8, P=4, seed=3):
     rm0, rv0 = torch.randn(D, generator=g) * 0.1, torch.rand(D, generator=g) + 0.5
     gzh = torch.randn(E, N, D, generator=g)
     perm = torch.tensor([(j % Cch) * P + j // Cch for j in range(D)])   # nhwc index j -> reference index
-    fr = f_ref.clone().requires_grad_(True)
-    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
-    rm, rv = rm0.clone(), rv0.clone()
+    fr = f_ref.double().clone().requires_grad_(True)           # reference in float64
+    gr, br = gamma.double().clone().requires_grad_(True), beta.double().clone().requires_grad_(True)
+    rm, rv = rm0.double().clone(), rv0.double().clone()
     zs = []
     for e in range(E):
         z = F.batch_norm(fr[e], rm, rv, gr, br, True, 0.1, 1e-5)
         zs.append(F.normalize(z, p=2, dim=1))
     zh_ref = torch.stack(zs)
-    (zh_ref * gzh).sum().backward()
+    (zh_ref * gzh.double()).sum().backward()
     f_dev = f_ref[:, :, perm].contiguous().to(dev)                      # our NHWC-flatten order
     z = torch.empty(E, N, D, device=dev)
     zh = torch.empty(E, N, D, device=dev)
@@ -188,17 +188,28 @@ def check_head(lib, dev, E=2, N=7, Cch=8, P=4, seed=3):
     pgrad = torch.empty(E * 2 * D, device=dev)
     lib.l2norm_bwd(zh, gzh[:, :, perm].contiguous().to(dev), inv, gz, E * N, D, 0)
     lib.bn1d_bwd(f_dev, gz, gamma.to(dev), mean, invstd, gf, dg, db, pgrad, E, N, D, Cch, P, 0)
-    _close(gf.cpu(), fr.grad[:, :, perm], rtol=2e-4, atol=1e-6, what="head bwd")
-    _close(dg, gr.grad, rtol=2e-4, atol=1e-5, what="bn_out dgamma")
-    _close(db, br.grad, rtol=2e-4, atol=1e-5, what="bn_out dbeta")
+    _close(gf.cpu(), fr.grad[:, :, perm], rtol=1e-4, atol=1e-6, what="head bwd")
+    _close(dg, gr.grad, rtol=1e-4, atol=1e-5, what="bn_out dgamma")
+    _close(db, br.grad, rtol=1e-4, atol=1e-5, what="bn_out dbeta")
     # eval mode
     z2 = torch.empty(E, N, D, device=dev)
     lib.bn1d_fwd(f_dev, gamma.to(dev), beta.to(dev), drm, drv, z2, None, None, None, E, N, D, Cch, P, 0, 0, 0.1, 1e-5, 0)
-    ref2 = F.batch_norm(f_ref.view(E * N, D), rm, rv, gamma, beta, False, 0.1, 1e-5).view(E, N, D)
+    ref2 = F.batch_norm(f_ref.double().view(E * N, D), rm, rv, gamma.double(), beta.double(), False, 0.1, 1e-5).view(E, N, D)
     _close(z2.cpu(), ref2[:, :, perm], what="bn_out eval")
 
 
-def check_gp(lib, dev, E=3, C=3, per_class=4, D=24, M=9, seed=4, rtol=2e-4, large=False):
+def _envelope(ref32, ref64, k=4.0, tol=1e-4):
+    """Gradient bar: `tol`, or k x the fp32 oracle's own max-norm distance to the fp64 oracle where that is larger (an
+    ill-conditioned quantity cannot be reproduced better than the reference's own fp32 evaluation reproduces it)."""
+    a, b = ref32.detach().double().reshape(-1), ref64.detach().double().reshape(-1)
+    floor = float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+    return max(tol, k * floor)
+
+
+def check_gp(lib, dev, E=3, C=3, per_class=4, D=24, M=9, seed=4, tol=1e-4, large=False):
+    """Gram -> C exact-GP systems -> gradients -> prediction against the oracle in float64.  OUTPUTS (loss, predictive
+    mean, L^-1) are held to `tol` = 1e-4 (north_star) at every size; GRADIENTS to max(1e-4, 4 x the fp32 oracle's own
+    distance to float64) -- printed per quantity."""
     g = torch.Generator().manual_seed(seed)
     N = C * per_class
     z = F.normalize(torch.randn(E, N, D, generator=g), dim=2)
@@ -206,18 +217,26 @@ def check_gp(lib, dev, E=3, C=3, per_class=4, D=24, M=9, seed=4, rtol=2e-4, larg
     targets = -torch.ones(C, N)
     for c in range(C):
         targets[c, c * per_class:(c + 1) * per_class] = 1.0
-    p = ogp.default_gp_params("bncossim", C, D)
-    p["raw_outputscale"] = torch.linspace(-0.4, 0.9, C)
-    p["constant"] = torch.linspace(-0.1, 0.2, C)
-    zr = z.clone().requires_grad_(True)
-    p["raw_outputscale"].requires_grad_(True)
-    p["constant"].requires_grad_(True)
-    losses = [ogp.mll_loss("bncossim", zr[e], targets, p) for e in range(E)]
-    (sum(losses) / E).backward()
+
+    def oracle(dt):
+        p = ogp.default_gp_params("bncossim", C, D, dtype=dt)
+        p["raw_outputscale"] = torch.linspace(-0.4, 0.9, C, dtype=dt)
+        p["constant"] = torch.linspace(-0.1, 0.2, C, dtype=dt)
+        zr = z.to(dt).clone().requires_grad_(True)
+        p["raw_outputscale"].requires_grad_(True)
+        p["constant"].requires_grad_(True)
+        losses = [ogp.mll_loss("bncossim", zr[e], targets.to(dt), p) for e in range(E)]
+        (sum(losses) / E).backward()
+        with torch.no_grad():
+            pd = {k: v.detach() for k, v in p.items()}
+            mean = torch.stack([ogp.predict("bncossim", z[e].to(dt), targets.to(dt), zt[e].to(dt), pd) for e in range(E)])
+        return p, zr, torch.stack([l.detach() for l in losses]), mean
+    p, zr, loss32, mean32 = oracle(torch.float32)
+    p64, zr64, loss64, mean64 = oracle(torch.float64)
     zd = z.to(dev)
     gram = torch.empty(E, N, N, device=dev)
     lib.gram(zd, zd, gram, E, N, N, D, 0)
-    _close(gram, z @ z.transpose(1, 2), what="gram")
+    _close(gram, z.double() @ z.double().transpose(1, 2), rtol=1e-5, atol=1e-6, what="gram")
     alpha = torch.empty(E, C, N, device=dev)
     lt = torch.empty(E, C, device=dev)
     info = torch.ones(E, C, device=dev, dtype=torch.int32)
@@ -236,35 +255,36 @@ def check_gp(lib, dev, E=3, C=3, per_class=4, D=24, M=9, seed=4, rtol=2e-4, larg
     fit(gram, alpha, linv, lt, info, dk, dh, 1.0 / E)
     assert int(info.cpu().abs().sum()) == 0
     with torch.no_grad():       # L^-1 of K~ (lower triangular), used by the predictive variance
-        s0 = F.softplus(p["raw_outputscale"].detach()[0])
-        kt = s0 * (z[0] @ z[0].T) + (F.softplus(p["raw_noise"].detach()[0]) + 1e-4) * torch.eye(N)
-        li_ref = torch.linalg.inv(torch.linalg.cholesky(kt.double())).float()
-    _close(linv[0, 0], li_ref, rtol=rtol, atol=1e-5, what="L^-1")
+        s0 = F.softplus(p64["raw_outputscale"].detach()[0])
+        kt = s0 * (z[0].double() @ z[0].double().T) + (F.softplus(p64["raw_noise"].detach()[0]) + 1e-4) * torch.eye(N, dtype=torch.float64)
+        li_ref = torch.linalg.inv(torch.linalg.cholesky(kt))
+    _close(linv[0, 0], li_ref, rtol=tol, atol=1e-6, what="L^-1")
     loss = torch.empty(E, device=dev)
     hyper = torch.empty(C, 3, device=dev)
     lib.gp_reduce(lt, dh, loss, hyper, E, C, 0)
-    _close(loss, torch.stack([l.detach() for l in losses]), rtol=rtol, what="mll loss")
-    _close(hyper[:, 0], p["raw_outputscale"].grad, rtol=rtol, atol=1e-6, what="d raw_outputscale")
-    _close(hyper[:, 1], p["constant"].grad, rtol=rtol, atol=1e-6, what="d constant")
+    _close(loss, loss64, rtol=tol, atol=0.0, what="mll loss")
+    bars = {"d raw_outputscale": _envelope(p["raw_outputscale"].grad, p64["raw_outputscale"].grad),
+            "d constant": _envelope(p["constant"].grad, p64["constant"].grad), "d z": _envelope(zr.grad, zr64.grad)}
+    _close(hyper[:, 0], p64["raw_outputscale"].grad, rtol=bars["d raw_outputscale"], atol=1e-7, what="d raw_outputscale")
+    _close(hyper[:, 1], p64["constant"].grad, rtol=bars["d constant"], atol=1e-7, what="d constant")
     dz = torch.empty(E, N, D, device=dev)
     lib.gram_bwd(dk, zd, dz, E, C, N, D, 1.0, 0)
-    _close(dz, zr.grad, rtol=rtol, atol=1e-6, what="d z")
+    _close(dz, zr64.grad, rtol=bars["d z"], atol=1e-7, what="d z")
     # prediction
     kx = torch.empty(E, M, N, device=dev)
     lib.gram(zt.to(dev), zd, kx, E, M, N, D, 0)
     mean = torch.empty(E, C, M, device=dev)
     pred = torch.empty(E, M, device=dev, dtype=torch.int32)
     lib.gp_predict(kx, 0, alpha, ros, cst, mean, pred, E, C, M, N, 0)
-    with torch.no_grad():
-        pd = {k: v.detach() for k, v in p.items()}
-        ref_mean = torch.stack([ogp.predict("bncossim", z[e], targets, zt[e], pd) for e in range(E)])
-    _close(mean, ref_mean, rtol=rtol, atol=1e-5, what="predictive mean")
-    ref_pred = torch.sigmoid(ref_mean).numpy().argmax(axis=1)
+    _close(mean, mean64, rtol=tol, atol=1e-6, what="predictive mean")
+    ref_pred = torch.sigmoid(mean32).numpy().argmax(axis=1)
     assert np.array_equal(pred.cpu().numpy(), ref_pred)
+    print("check_gp N=%d%s: outputs at %.0e; gradient bars %s" % (N, " (tiled)" if large else "", tol,
+                                                                   {k: "%.1e" % v for k, v in bars.items()}))
     # a non-PD system must be reported, not silently factorised
     bad = -torch.eye(N).repeat(E, 1, 1).to(dev)
     fit(bad, alpha, None, lt, info, None, None, 1.0)
-    assert int((info.cpu() != 0).sum()) == E * C
+    assert int((info.cpu() > 0).sum()) == E * C
 
 
 def check_adam(lib, dev, n=1000, seed=5):
@@ -337,9 +357,10 @@ PARAM_NAME = {"linear": "raw_variance", "rbf": "raw_lengthscale", "matern": "raw
               "poli2": "raw_offset"}
 
 
-def check_gp_family(lib, dev, kernel, E=2, C=3, per_class=3, D=12, M=7, seed=40, rtol=3e-4):
+def check_gp_family(lib, dev, kernel, E=2, C=3, per_class=3, D=12, M=7, seed=40, tol=1e-4):
     """Kernel family (linear / rbf / matern / poli1 / poli2): centre -> Gram -> kernel epilogue -> gp_fit -> backward
-    through the epilogue and the Gram, prediction with mean and variance -- against the oracle's autograd."""
+    through the epilogue and the Gram, prediction with mean and variance -- against the oracle in float64.  OUTPUTS (loss,
+    predictive mean, predictive variance) at `tol` = 1e-4; GRADIENTS at max(1e-4, 4 x fp32-oracle-vs-float64)."""
     g = torch.Generator().manual_seed(seed)
     N = C * per_class
     scale = 1.2 / D ** 0.5 if kernel in ("rbf", "matern") else 0.4     # keep ||x - x'||^2 / l^2 = O(1)
@@ -348,16 +369,25 @@ def check_gp_family(lib, dev, kernel, E=2, C=3, per_class=3, D=12, M=7, seed=40,
     targets = -torch.ones(C, N)
     for c in range(C):
         targets[c, c * per_class:(c + 1) * per_class] = 1.0
-    p = ogp.default_gp_params(kernel, C, D)
     pn = PARAM_NAME[kernel]
-    p["raw_outputscale"] = torch.linspace(-0.4, 0.5, C)
-    p["constant"] = torch.linspace(-0.1, 0.2, C)
-    p[pn] = torch.linspace(0.3, 1.2, C)
-    zr = z.clone().requires_grad_(True)
-    for k in ("raw_outputscale", "constant", pn):
-        p[k].requires_grad_(True)
-    losses = [ogp.mll_loss(kernel, zr[e], targets, p) for e in range(E)]
-    (sum(losses) / E).backward()
+
+    def oracle(dt):
+        p = ogp.default_gp_params(kernel, C, D, dtype=dt)
+        p["raw_outputscale"] = torch.linspace(-0.4, 0.5, C, dtype=dt)
+        p["constant"] = torch.linspace(-0.1, 0.2, C, dtype=dt)
+        p[pn] = torch.linspace(0.3, 1.2, C, dtype=dt)
+        zr = z.to(dt).clone().requires_grad_(True)
+        for k in ("raw_outputscale", "constant", pn):
+            p[k].requires_grad_(True)
+        losses = [ogp.mll_loss(kernel, zr[e], targets.to(dt), p) for e in range(E)]
+        (sum(losses) / E).backward()
+        with torch.no_grad():
+            pd = {k: v.detach() for k, v in p.items()}
+            ref = [ogp.predict(kernel, z[e].to(dt), targets.to(dt), zt[e].to(dt), pd, want_var=True) for e in range(E)]
+        return p, zr, torch.stack([l.detach() for l in losses]), ref
+    p, zr, loss32, ref32 = oracle(torch.float32)
+    p64, zr64, loss64, ref64 = oracle(torch.float64)
+    bar = lambda name, a, b: _envelope(a, b, tol=tol)
     kind = KIND[kernel]
     centred = kernel in ("rbf", "matern")
     zd = z.to(dev)
@@ -366,7 +396,7 @@ def check_gp_family(lib, dev, kernel, E=2, C=3, per_class=3, D=12, M=7, seed=40,
     d2 = torch.empty(E, N, N, device=dev)
     lib.gram(xc, xc, gram, E, N, N, D, 0)
     lib.sqdist(xc, xc, d2, E, N, N, D, 0)
-    _close(d2, torch.cdist(z, z) ** 2, rtol=1e-5, atol=1e-6, what="sqdist")
+    _close(d2, torch.cdist(z.double(), z.double()) ** 2, rtol=1e-5, atol=1e-6, what="sqdist")
     assert float(d2.cpu().diagonal(dim1=1, dim2=2).abs().max()) == 0.0
     sq = torch.empty(E, N, device=dev)
     lib.row_sqnorm(xc, sq, E * N, D, 0)
@@ -385,17 +415,19 @@ def check_gp_family(lib, dev, kernel, E=2, C=3, per_class=3, D=12, M=7, seed=40,
     loss = torch.empty(E, device=dev)
     hyper = torch.empty(C, 3, device=dev)
     lib.gp_reduce(lt, dh, loss, hyper, E, C, 0)
-    _close(loss, torch.stack([l.detach() for l in losses]), rtol=rtol, what=kernel + " loss")
-    _close(hyper[:, 0], p["raw_outputscale"].grad, rtol=rtol, atol=1e-6, what=kernel + " d outputscale")
-    _close(hyper[:, 1], p["constant"].grad, rtol=rtol, atol=1e-6, what=kernel + " d constant")
+    _close(loss, loss64, rtol=tol, atol=0.0, what=kernel + " loss")
+    _close(hyper[:, 0], p64["raw_outputscale"].grad, rtol=bar("s", p["raw_outputscale"].grad, p64["raw_outputscale"].grad),
+           atol=1e-7, what=kernel + " d outputscale")
+    _close(hyper[:, 1], p64["constant"].grad, rtol=bar("c", p["constant"].grad, p64["constant"].grad), atol=1e-7,
+           what=kernel + " d constant")
     dg = torch.empty(E, N, N, device=dev)
     dparam = torch.empty(C, device=dev)
     scratch = torch.empty(E * C * N, device=dev)
     lib.kernel_bwd(kind, None if centred else gram, d2 if centred else None, rp, dk, dg, dparam, scratch, E, C, N, 0)
-    _close(dparam, p[pn].grad, rtol=rtol, atol=1e-6, what=kernel + " d " + pn)
+    _close(dparam, p64[pn].grad, rtol=bar("p", p[pn].grad, p64[pn].grad), atol=1e-7, what=kernel + " d " + pn)
     dz = torch.empty(E, N, D, device=dev)
     lib.gram_bwd(dg, xc, dz, E, 1, N, D, 1.0, 0)
-    _close(dz, zr.grad, rtol=rtol, atol=1e-6, what=kernel + " d z")
+    _close(dz, zr64.grad, rtol=bar("z", zr.grad, zr64.grad), atol=1e-7, what=kernel + " d z")
     # prediction: mean + variance
     ztd = zt.to(dev)
     xtc = ztd
@@ -420,11 +452,8 @@ def check_gp_family(lib, dev, kernel, E=2, C=3, per_class=3, D=12, M=7, seed=40,
         kss[:, c, :] = tmp.view(E, M)
     var = torch.empty(E, C, M, device=dev)
     lib.gp_predict_var(kx, M * N, kss.contiguous(), M, linv, ros, rn, var, E, C, M, N, 0)
-    with torch.no_grad():
-        pd = {k: v.detach() for k, v in p.items()}
-        ref = [ogp.predict(kernel, z[e], targets, zt[e], pd, want_var=True) for e in range(E)]
-    _close(mean, torch.stack([r[0] for r in ref]), rtol=rtol, atol=1e-5, what=kernel + " mean")
-    _close(var, torch.stack([r[1] for r in ref]), rtol=rtol, atol=1e-5, what=kernel + " variance")
+    _close(mean, torch.stack([r[0] for r in ref64]), rtol=tol, atol=1e-6, what=kernel + " mean")
+    _close(var, torch.stack([r[1] for r in ref64]), rtol=tol, atol=1e-6, what=kernel + " variance")
 
 
 def check_conv2d(lib, dev, N=2, H=13, W=11, Cin=3, Cout=36, R=3, stride=2, pad=0, dil=2, relu=1, seed=50):
@@ -597,9 +626,9 @@ def check_resnet_ops(lib, dev, E=2, ipe=2, H=9, W=7, C=8, seed=80):
     rm0, rv0 = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5
     gy = torch.randn(B, C, H, W, generator=g)
     for relu, with_res in ((1, True), (0, False), (1, False)):
-        xr, rr = x.clone().requires_grad_(True), res.clone().requires_grad_(True)
-        gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
-        rm, rv = rm0.clone(), rv0.clone()
+        xr, rr = x.double().clone().requires_grad_(True), res.double().clone().requires_grad_(True)     # float64 reference
+        gr, br = gamma.double().clone().requires_grad_(True), beta.double().clone().requires_grad_(True)
+        rm, rv = rm0.double().clone(), rv0.double().clone()
         outs = []
         for e in range(E):
             o = F.batch_norm(xr[e * ipe:(e + 1) * ipe], rm, rv, gr, br, True, 0.1, 1e-5)
@@ -607,7 +636,7 @@ def check_resnet_ops(lib, dev, E=2, ipe=2, H=9, W=7, C=8, seed=80):
                 o = o + rr[e * ipe:(e + 1) * ipe]
             outs.append(F.relu(o) if relu else o)
         ref = torch.cat(outs)
-        (ref * gy).sum().backward()
+        (ref * gy.double()).sum().backward()
         nh = lambda t: t.permute(0, 2, 3, 1).contiguous().to(dev)
         xd, rd, gyd = nh(x), nh(res), nh(gy)
         mean, invstd = torch.empty(E, C, device=dev), torch.empty(E, C, device=dev)
@@ -624,9 +653,9 @@ def check_resnet_ops(lib, dev, E=2, ipe=2, H=9, W=7, C=8, seed=80):
         sums = torch.empty(E * C * 2, device=dev)
         lib.bn2d_bwd(xd, y, gyd, mean, invstd, gamma.to(dev), gx, gres if with_res else None, dg, db, partial, sums, B,
                      H * W, C, ipe, relu, 0)
-        _close(gx.cpu().permute(0, 3, 1, 2), xr.grad, rtol=2e-4, atol=1e-5, what="bn2d bwd gx")
-        _close(dg, gr.grad, rtol=2e-4, atol=1e-4, what="bn2d dgamma")
-        _close(db, br.grad, rtol=2e-4, atol=1e-4, what="bn2d dbeta")
+        _close(gx.cpu().permute(0, 3, 1, 2), xr.grad, rtol=1e-4, atol=1e-6, what="bn2d bwd gx")
+        _close(dg, gr.grad, rtol=1e-4, atol=1e-5, what="bn2d dgamma")
+        _close(db, br.grad, rtol=1e-4, atol=1e-5, what="bn2d dbeta")
         if with_res:
             _close(gres.cpu().permute(0, 3, 1, 2), rr.grad, rtol=1e-5, atol=1e-6, what="bn2d gres")
     # eval mode (ipe = 0: one statistics row)
@@ -669,22 +698,22 @@ def check_conv1_bwd_fused(lib, dev, E=2, ipe=2, H=10, W=37, out_pad=1, seed=21, 
     g = torch.Generator().manual_seed(seed)
     B = E * ipe
     x = torch.randn(B, 3, H, W, generator=g)
-    w = (torch.randn(64, 3, 3, 3, generator=g) * 0.2).requires_grad_(True)
-    b = torch.randn(64, generator=g).requires_grad_(True)
-    gamma = (1 + 0.2 * torch.randn(64, generator=g)).requires_grad_(True)
-    beta = (0.1 * torch.randn(64, generator=g)).requires_grad_(True)
+    w = (torch.randn(64, 3, 3, 3, generator=g) * 0.2).double().requires_grad_(True)        # float64 reference
+    b = torch.randn(64, generator=g).double().requires_grad_(True)
+    gamma = (1 + 0.2 * torch.randn(64, generator=g)).double().requires_grad_(True)
+    beta = (0.1 * torch.randn(64, generator=g)).double().requires_grad_(True)
     Ho, Wo = H // 2, W // 2
     gout = torch.randn(B, 64, Ho, Wo, generator=g)
-    y = F.conv2d(x, w, b, padding=1)
+    y = F.conv2d(x.double(), w, b, padding=1)
     outs = []
     for e in range(E):
         ye = y[e * ipe:(e + 1) * ipe]
         outs.append(F.max_pool2d(F.relu(F.batch_norm(ye, None, None, gamma, beta, True, 0.0, 1e-5)), 2))
-    (torch.cat(outs) * gout).sum().backward()
-    yd = y.detach().permute(0, 2, 3, 1).contiguous().to(dev)
+    (torch.cat(outs) * gout.double()).sum().backward()
+    yd = y.detach().float().permute(0, 2, 3, 1).contiguous().to(dev)
     yv = y.detach().view(E, ipe, 64, H, W)
-    mean = yv.mean((1, 3, 4)).to(dev).contiguous()
-    invstd = (1.0 / torch.sqrt(yv.var((1, 3, 4), unbiased=False) + 1e-5)).to(dev).contiguous()
+    mean = yv.mean((1, 3, 4)).float().to(dev).contiguous()
+    invstd = (1.0 / torch.sqrt(yv.var((1, 3, 4), unbiased=False) + 1e-5)).float().to(dev).contiguous()
     gpad = torch.zeros(B, Ho + 2 * out_pad, Wo + 2 * out_pad, 64)
     gpad[:, out_pad:out_pad + Ho, out_pad:out_pad + Wo] = gout.permute(0, 2, 3, 1)
     gpad = gpad.to(dev)
@@ -693,14 +722,14 @@ def check_conv1_bwd_fused(lib, dev, E=2, ipe=2, H=10, W=37, out_pad=1, seed=21, 
     sums = torch.empty(E * 128, device=dev)
     scratch_d = torch.empty(lib.bn_scratch_doubles(E), device=dev, dtype=torch.float64)
     dg, dbt = torch.empty(64, device=dev), torch.empty(64, device=dev)
-    gd, bd = gamma.detach().to(dev), beta.detach().to(dev)
+    gd, bd = gamma.detach().float().to(dev), beta.detach().float().to(dev)
     lib.bn_relu_pool_bwd(yd, gpad, mean, invstd, gd, bd, None, dg, dbt, partial, sums, scratch_d, B, H, W, ipe, 0, out_pad, 1, 0)
-    _close(dg, gamma.grad, rtol=2e-4, atol=1e-4, what="fused L0: d gamma")
-    _close(dbt, beta.grad, rtol=2e-4, atol=1e-4, what="fused L0: d beta")
+    _close(dg, gamma.grad, rtol=1e-4, atol=1e-5, what="fused L0: d gamma")
+    _close(dbt, beta.grad, rtol=1e-4, atol=1e-5, what="fused L0: d beta")
     dw, db = torch.empty(64, 3, 3, 3, device=dev), torch.empty(64, device=dev)
     scratch = torch.empty(lib.conv1_wgrad_nsplit() * 28 * 64, device=dev)
     getattr(lib, fn)(x.to(dev), yd, gpad, mean, invstd, gd, bd, sums, dw, db, scratch, B, H, W, ipe, out_pad, 0)
-    _close(dw, w.grad, rtol=2e-4, atol=2e-4, what="fused L0: d conv1 weight")
+    _close(dw, w.grad, rtol=1e-4, atol=2e-5, what="fused L0: d conv1 weight")
     assert float(db.abs().max()) <= 1e-3 * float(w.grad.abs().max()) + 1e-5      # cancelled by BatchNorm
     # split path: same numbers up to summation order
     gy = torch.empty(B, H, W, 64, device=dev)
