@@ -527,7 +527,7 @@ def dominant_kernel_roofline(model, lib, dev, E):
     # padded activation tensor read once + the interior of y written once
     traffic = (833.078272e6 + 718.676736e6) / 1680.0 * B if use_tc else None
     alg_bytes = B * ((H + 2) * (W + 2) * 256.0 + H * W * 256.0)
-    return {"kernel": "conv3x3 64->64 forward, 42x42, B=%d images (%s)" % (B, "tcgen05 3xTF32, " + eng.tc_fn if use_tc else "fp32 FFMA"),
+    return {"kernel": "conv3x3 64->64 forward, 42x42, B=%d images (%s)" % (B, "tcgen05 3xTF32, conv3x3_tc_persistent_kernel" if use_tc else "fp32 FFMA"),
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms, "peak_source": which,
             "algorithmic_flops_per_launch": flops,

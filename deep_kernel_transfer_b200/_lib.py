@@ -33,8 +33,6 @@ SIGNATURES = {
     "dktb_prep_weights_conv1_tc": ("pps", ctypes.c_int),
     "dktb_conv1_tc": ("pppppppppppiiiiis", ctypes.c_int),
     "dktb_conv3x3_tc_fwd": ("ppppppiiis", ctypes.c_int),
-    "dktb_conv3x3_tc2_fwd": ("ppppppiiis", ctypes.c_int),
-    "dktb_conv3x3_tc3_fwd": ("ppppppiiis", ctypes.c_int),
     "dktb_conv3x3_wgrad_tc": ("ppppppiiis", ctypes.c_int),
     "dktb_conv3x3_wgrad_reduce": ("pipps", ctypes.c_int),
     "dktb_bn_finalize": ("piiiipppppffs", ctypes.c_int),

@@ -880,8 +880,7 @@ static bool conv2d_use_mma() {
   const char* v = getenv("DKTB_RESNET_CONV");
   return !(v && v[0] == 'f');
 #else
-  static const bool on = [] { const char* v = getenv("DKTB_RESNET_CONV"); return !(v && v[0] == 'f'); }();   // "fp32": CUDA cores
-  return on;
+  return true;       // device build: the tensor-core tiles, no switch
 #endif
 }
 

@@ -6,10 +6,8 @@
 // K = 9 taps x 64 input channels; tap (r,s) is the same activation matrix shifted by (r-1)*Wp + (s-1) rows, so
 // every operand tile is a plain 2-D TMA box and the zero border of the layout supplies the padding.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
-// warps 2-5 = in-SM splitter (raw fp32 tile -> hi in place + lo copy) and epilogue (TMEM -> regs -> smem ->
-// coalesced global stores + per-tile BatchNorm partial sums).  Pipeline: full[s] (TMA landed) -> conv[s]
-// (split done) -> MMA -> empty[s] (tcgen05.commit), STAGES-deep ring over the 18 (tap, channel-half) k-blocks.
+// Kernels in this file: the persistent forward / dgrad kernel (A operand staged in TMEM by stager warps, weights
+// streamed by TMA, dedicated epilogue warps), the tcgen05 weight-gradient kernel and the first-layer (3 -> 64) kernel.
 #include "dktb_common.cuh"
 
 #ifndef DKTB_EMU
@@ -19,187 +17,8 @@
 namespace {
 
 constexpr int kRows = 128;
-constexpr int kStages = 2;
-constexpr int kStageBytes = 49152;            // A(hi) 16K | A lo 16K | W hi 8K | W lo 8K
-constexpr int kOffALo = 16384, kOffWHi = 32768, kOffWLo = 40960;
-constexpr int kIters = 18;                    // 9 taps x 2 channel halves
-constexpr int kOutLd = 65;                    // epilogue staging row stride (floats)
-constexpr int kSmemBytes = kStages * kStageBytes + 1024;
 
-struct TcErr { int flag; };
-
-__global__ void __launch_bounds__(192, 2)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                  const float* __restrict__ bias, float* __restrict__ out, float* __restrict__ partials, int B, int H,
-                  int W, int* __restrict__ err) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  // the dynamic smem base is only guaranteed 16 B aligned by the ABI: align by hand for SWIZZLE_128B
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t bar_full[kStages], bar_conv[kStages], bar_empty[kStages], bar_acc;
-  __shared__ uint32_t s_tmem;
-  __shared__ int s_err;
-  __shared__ float s_valid[kRows];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (*reinterpret_cast<volatile int*>(err) != 0) return;   // a time-out was already reported: do not pile up waits
-  const int Hp = H + 2, Wp = W + 2;
-  const int img = blockIdx.y;
-  const int q0 = (Wp + 1) + blockIdx.x * kRows;
-  const long img_base = (long)img * Hp * Wp;
-
-  if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      tc::mbar_init(&bar_full[s], 1);
-      tc::mbar_init(&bar_conv[s], 128);
-      tc::mbar_init(&bar_empty[s], 1);
-    }
-    tc::mbar_init(&bar_acc, 1);
-    s_err = 0;
-    tc::fence_barrier_init();
-  }
-  if (warp == 0 && lane == 0) {
-    tc::prefetch_tmap(&map_a);
-    tc::prefetch_tmap(&map_w);
-  }
-  if (warp == 1) tc::tmem_alloc<64>(&s_tmem);
-  tc::tcgen05_fence_before();
-  __syncthreads();
-  tc::tcgen05_fence_after();
-  const uint32_t d_tmem = s_tmem;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    for (int it = 0; it < kIters; ++it) {
-      const int s = it % kStages, ph = (it / kStages) & 1;
-      const int tap = it >> 1, half = it & 1;
-      if (!tc::mbar_wait(&bar_empty[s], ph ^ 1)) { s_err = 1; break; }
-      if (tc::elect_one()) {
-        unsigned char* st = smem + s * kStageBytes;
-        tc::mbar_expect_tx(&bar_full[s], 16384 + 8192 + 8192);
-        const int row = (int)(img_base + q0 - (Wp + 1) + (tap / 3) * Wp + (tap % 3));
-        tc::tma_load_2d(st, &map_a, &bar_full[s], half * 32, row);
-        tc::tma_load_2d(st + kOffWHi, &map_w, &bar_full[s], half * 32, tap * 128);
-        tc::tma_load_2d(st + kOffWLo, &map_w, &bar_full[s], half * 32, tap * 128 + 64);
-      }
-      __syncwarp();
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (warp-converged, one elected lane)
-    {
-      const uint32_t idesc = tc::umma_idesc(2, 128, 64, 0, 0);
-      bool ok = true;
-      for (int it = 0; it < kIters && ok; ++it) {
-        const int s = it % kStages, ph = (it / kStages) & 1;
-        ok = tc::mbar_wait(&bar_conv[s], ph);
-        if (!ok) break;
-        tc::tcgen05_fence_after();
-        const uint32_t base = tc::smem_u32(smem + s * kStageBytes);
-        if (tc::elect_one()) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t a_hi = tc::umma_desc_sw128(base + k * 32, 16, 1024);
-          const uint64_t a_lo = tc::umma_desc_sw128(base + kOffALo + k * 32, 16, 1024);
-          const uint64_t w_hi = tc::umma_desc_sw128(base + kOffWHi + k * 32, 16, 1024);
-          const uint64_t w_lo = tc::umma_desc_sw128(base + kOffWLo + k * 32, 16, 1024);
-          tc::umma_tf32_ss(d_tmem, a_lo, w_hi, idesc, (it | k) ? 1u : 0u);   // small terms first
-          tc::umma_tf32_ss(d_tmem, a_hi, w_lo, idesc, 1u);
-          tc::umma_tf32_ss(d_tmem, a_hi, w_hi, idesc, 1u);
-        }
-        tc::umma_commit(&bar_empty[s]);
-        }
-        __syncwarp();
-      }
-      if (!ok) s_err = 1;
-      if (tc::elect_one()) tc::umma_commit(&bar_acc);
-      __syncwarp();
-    }
-  } else {
-    // ------------------------------------------------------------------ splitter warps (128 threads)
-    const int ct = tid - 64;
-    bool ok = true;
-    for (int it = 0; it < kIters && ok; ++it) {
-      const int s = it % kStages, ph = (it / kStages) & 1;
-      ok = tc::mbar_wait(&bar_full[s], ph);
-      if (!ok) break;
-      unsigned char* st = smem + s * kStageBytes;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4* pa = reinterpret_cast<float4*>(st + j * 2048 + ct * 16);
-        float4* pl = reinterpret_cast<float4*>(st + kOffALo + j * 2048 + ct * 16);
-        const float4 v = *pa;
-        float4 hi, lo;
-        hi.x = tc::to_tf32_rna(v.x); hi.y = tc::to_tf32_rna(v.y); hi.z = tc::to_tf32_rna(v.z); hi.w = tc::to_tf32_rna(v.w);
-        lo.x = tc::to_tf32_rna(v.x - hi.x); lo.y = tc::to_tf32_rna(v.y - hi.y);
-        lo.z = tc::to_tf32_rna(v.z - hi.z); lo.w = tc::to_tf32_rna(v.w - hi.w);
-        *pa = hi;
-        *pl = lo;
-      }
-      tc::fence_proxy_async_smem();
-      tc::mbar_arrive(&bar_conv[s]);
-    }
-    if (!ok) s_err = 1;
-    // ------------------------------------------------------------------ epilogue
-    ok = ok && tc::mbar_wait(&bar_acc, 0);
-    tc::tcgen05_fence_after();
-    float* s_out = reinterpret_cast<float*>(smem);          // [128][kOutLd], stage memory is free now
-    const int quarter = warp & 3;                             // TMEM lane quarter this warp may access
-    const int r = quarter * 32 + lane;                        // accumulator row = padded-flat pixel q0 + r
-    const int q = q0 + r;
-    const int hp = q / Wp, wp = q - hp * Wp;
-    const bool valid = ok && q < Hp * Wp && hp >= 1 && hp <= H && wp >= 1 && wp <= W;
-    s_valid[r] = valid ? 1.f : 0.f;
-    if (ok) {
-#pragma unroll
-      for (int c = 0; c < 64; c += 16) {
-        uint32_t v[16];
-        tc::tmem_ld16(d_tmem + ((uint32_t)(quarter * 32) << 16) + c, v);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float b = bias ? bias[c + j] : 0.f;
-          s_out[r * kOutLd + c + j] = __uint_as_float(v[j]) + b;
-        }
-      }
-    }
-    tc::tcgen05_fence_before();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    // coalesced stores: 16 lanes cover one pixel's 64 channels
-    for (int idx = ct; idx < kRows * 16; idx += 128) {
-      const int rr = idx >> 4, c4 = (idx & 15) * 4;
-      if (s_valid[rr] != 0.f) {
-        const float* src = s_out + rr * kOutLd + c4;
-        dktb_st4(out + (img_base + q0 + rr) * 64 + c4, make_float4(src[0], src[1], src[2], src[3]));
-      }
-    }
-    if (partials != nullptr) {
-      const int which = ct >> 6, c = ct & 63;
-      float t = 0.f;
-      for (int rr = 0; rr < kRows; ++rr) {
-        const float v = s_out[rr * kOutLd + c] * s_valid[rr];
-        t += which ? v * v : v;
-      }
-      const long blk = (long)img * gridDim.x + blockIdx.x;
-      partials[(blk * 2 + which) * 64 + c] = t;
-    }
-  }
-  tc::tcgen05_fence_before();
-  __syncthreads();
-  if (tid == 0 && s_err) atomicExch(err, 1);
-  if (warp == 1) tc::tmem_dealloc<64>(d_tmem);
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// v2: A operand from TMEM.  The activation halo of the tile (128 + 2*(Wp+1) padded-flat rows x 64 channels) is loaded
-// ONCE by TMA (two SWIZZLE_128B channel halves); for every (tap, half) the 128 stager threads read their own shifted
-// row from the halo (conflict-free thanks to the swizzle), split it into tf32 hi / exact lo in registers and write
-// both straight into TMEM (tcgen05.st, lane = output pixel, column = input channel).  tcgen05.mma then takes A from
-// TMEM and only the 2 KB weight slice from shared memory, so the tensor pipe is no longer starved by the 4 KB/MMA
-// A re-read that bounds the SS version at N = 64.  Weights stream through a 3-stage TMA ring (hi + lo, 16 KB/stage).
-// TMEM: 256 columns = accumulator [0,64) + two A stages of {hi 32 | lo 32} columns.
-// ------------------------------------------------------------------------------------------------------------------
 constexpr int kHaloBox = 32;                  // rows per halo TMA box
-constexpr int kWStages = 3;
-constexpr int kWStageBytes = 16384;           // W hi 8K | W lo 8K for one (tap, half)
-constexpr int kAStages = 3;                   // TMEM A stages of {hi 32 | lo 32} columns
 constexpr int kTsThreads = 64 + 256;          // TMA warp, MMA warp, 8 stager / epilogue warps
 
 // tf32 split with full-rate integer ops: hi = round-to-nearest(-away) to 10 mantissa bits, lo = rounded remainder
@@ -220,175 +39,8 @@ __device__ __forceinline__ void split_tf32_exact(float v, uint32_t& hi, uint32_t
   lo = (__float_as_uint(v - __uint_as_float(hi)) + 0x1000u) & 0xFFFFE000u;
 }
 
-__global__ void __launch_bounds__(kTsThreads, 2)
-conv3x3_tc_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                     const float* __restrict__ bias, float* __restrict__ out, float* __restrict__ partials, int B, int H,
-                     int W, int halo_rows_pad, int* __restrict__ err) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t bar_halo, bar_wfull[kWStages], bar_wempty[kWStages], bar_afull[kAStages], bar_aempty[kAStages],
-      bar_acc;
-  __shared__ uint32_t s_tmem;
-  __shared__ int s_err;
-  __shared__ float s_valid[kRows];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (*reinterpret_cast<volatile int*>(err) != 0) return;   // a time-out was already reported: do not pile up waits
-  const int Hp = H + 2, Wp = W + 2;
-  const int img = blockIdx.y;
-  const int q0 = (Wp + 1) + blockIdx.x * kRows;
-  const long img_base = (long)img * Hp * Wp;
-  const int half_bytes = halo_rows_pad * 128;
-  unsigned char* s_halo = smem;                               // [2][halo_rows_pad][128 B]
-  unsigned char* s_w = smem + 2 * half_bytes;                 // [kWStages][16 KB]
-
-  if (tid == 0) {
-    tc::mbar_init(&bar_halo, 1);
-    for (int s = 0; s < kWStages; ++s) { tc::mbar_init(&bar_wfull[s], 1); tc::mbar_init(&bar_wempty[s], 1); }
-    for (int s = 0; s < 2; ++s) { tc::mbar_init(&bar_afull[s], 256); tc::mbar_init(&bar_aempty[s], 1); }
-    tc::mbar_init(&bar_acc, 1);
-    s_err = 0;
-    tc::fence_barrier_init();
-  }
-  if (warp == 0 && lane == 0) { tc::prefetch_tmap(&map_a); tc::prefetch_tmap(&map_w); }
-  if (warp == 1) tc::tmem_alloc<256>(&s_tmem);
-  tc::tcgen05_fence_before();
-  __syncthreads();
-  tc::tcgen05_fence_after();
-  const uint32_t d_tmem = s_tmem;
-  const uint32_t a_tmem = s_tmem + 128;     // accumulator [0,128): columns j (x w_hi) and 64+j (x w_lo) are summed in the epilogue
-
-  if (warp == 0) {
-    if (tc::elect_one()) {
-      tc::mbar_expect_tx(&bar_halo, 2 * half_bytes);
-      const int row0 = (int)(img_base + q0 - (Wp + 1));
-      for (int h = 0; h < 2; ++h)
-        for (int r = 0; r < halo_rows_pad; r += kHaloBox)
-          tc::tma_load_2d(s_halo + h * half_bytes + r * 128, &map_a, &bar_halo, h * 32, row0 + r);
-    }
-    __syncwarp();
-    for (int it = 0; it < kIters; ++it) {
-      const int s = it % kWStages, ph = (it / kWStages) & 1;
-      const int tap = it >> 1, half = it & 1;
-      if (!tc::mbar_wait(&bar_wempty[s], ph ^ 1)) { s_err = 1; break; }
-      if (tc::elect_one()) {
-        tc::mbar_expect_tx(&bar_wfull[s], kWStageBytes);
-        tc::tma_load_2d(s_w + s * kWStageBytes, &map_w, &bar_wfull[s], half * 32, tap * 128);   // [w_hi 64 rows | w_lo 64 rows]
-      }
-      __syncwarp();
-    }
-  } else if (warp == 1) {
-    {
-      // N = 128: the B tile is [w_hi | w_lo] stacked along N, so ONE instruction yields a*w_hi (columns 0..63) and
-      // a*w_lo (columns 64..127).  tcgen05.mma costs ~50-60 cycles per instruction at N = 64 but only ~65 at N = 128
-      // (profiles/r01_umma_microbench.log), so 2 x N128 per k-step beat 3 x N64 and add the lo*lo term for free.
-      const uint32_t idesc = tc::umma_idesc(2, 128, 128, 0, 0);
-      bool ok = true;
-      for (int it = 0; it < kIters && ok; ++it) {
-        const int sw = it % kWStages, pw = (it / kWStages) & 1;
-        const int sa = it & 1, pa = (it >> 1) & 1;
-        ok = tc::mbar_wait(&bar_wfull[sw], pw) && tc::mbar_wait(&bar_afull[sa], pa);
-        if (!ok) break;
-        tc::tcgen05_fence_after();
-        const uint32_t wbase = tc::smem_u32(s_w + sw * kWStageBytes);
-        const uint32_t acol = a_tmem + sa * 64;
-        if (tc::elect_one()) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t w_cat = tc::umma_desc_sw128(wbase + k * 32, 16, 1024);
-          tc::umma_tf32_ts(d_tmem, acol + 32 + k * 8, w_cat, idesc, (it | k) ? 1u : 0u);   // a_lo * [w_hi | w_lo]
-          tc::umma_tf32_ts(d_tmem, acol + k * 8, w_cat, idesc, 1u);                         // a_hi * [w_hi | w_lo]
-        }
-        tc::umma_commit(&bar_aempty[sa]);
-        tc::umma_commit(&bar_wempty[sw]);
-        }
-        __syncwarp();
-      }
-      if (!ok) s_err = 1;
-      if (tc::elect_one()) tc::umma_commit(&bar_acc);
-      __syncwarp();
-    }
-  } else {
-    const int ct = tid - 64;                                 // 0..255
-    const int set = ct >> 7;                                 // which 16-channel quarter-slice of the 32-channel half
-    const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;                       // accumulator row / TMEM lane of this thread
-    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    bool ok = tc::mbar_wait(&bar_halo, 0);
-    for (int it = 0; it < kIters && ok; ++it) {
-      const int sa = it & 1, pa = (it >> 1) & 1;
-      const int tap = it >> 1, half = it & 1;
-      const int row = r + (tap / 3) * Wp + (tap % 3);
-      const unsigned char* src = s_halo + half * half_bytes + row * 128;
-      uint32_t hi[16], lo[16];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 v = *reinterpret_cast<const float4*>(src + (((set * 4 + j) ^ (row & 7)) << 4));
-        split_tf32(v.x, hi[4 * j + 0], lo[4 * j + 0]);
-        split_tf32(v.y, hi[4 * j + 1], lo[4 * j + 1]);
-        split_tf32(v.z, hi[4 * j + 2], lo[4 * j + 2]);
-        split_tf32(v.w, hi[4 * j + 3], lo[4 * j + 3]);
-      }
-      ok = tc::mbar_wait(&bar_aempty[sa], pa ^ 1);
-      if (!ok) break;
-      tc::tcgen05_fence_after();
-      const uint32_t dst = a_tmem + sa * 64 + lane_base + set * 16;
-      tc::tmem_st16(dst, hi);
-      tc::tmem_st16(dst + 32, lo);
-      tc::tmem_st_wait();
-      tc::tcgen05_fence_before();
-      tc::mbar_arrive(&bar_afull[sa]);
-    }
-    if (!ok) s_err = 1;
-    ok = ok && tc::mbar_wait(&bar_acc, 0);
-    tc::tcgen05_fence_after();
-    float* s_out = reinterpret_cast<float*>(smem);          // [128][kOutLd] over the (now idle) halo
-    const int q = q0 + r;
-    const int hp = q / Wp, wp = q - hp * Wp;
-    const bool valid = ok && q < Hp * Wp && hp >= 1 && hp <= H && wp >= 1 && wp <= W;
-    if (set == 0) s_valid[r] = valid ? 1.f : 0.f;
-    if (ok) {
-#pragma unroll
-      for (int cc = 0; cc < 32; cc += 16) {
-        const int c = set * 32 + cc;
-        uint32_t v0[16], v1[16];
-        tc::tmem_ld16(d_tmem + lane_base + c, v0);
-        tc::tmem_ld16(d_tmem + 64 + lane_base + c, v1);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float b = bias ? bias[c + j] : 0.f;
-          s_out[r * kOutLd + c + j] = (__uint_as_float(v0[j]) + __uint_as_float(v1[j])) + b;
-        }
-      }
-    }
-    tc::tcgen05_fence_before();
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    for (int idx = ct; idx < kRows * 16; idx += 256) {
-      const int rr = idx >> 4, c4 = (idx & 15) * 4;
-      if (s_valid[rr] != 0.f) {
-        const float* src = s_out + rr * kOutLd + c4;
-        dktb_st4(out + (img_base + q0 + rr) * 64 + c4, make_float4(src[0], src[1], src[2], src[3]));
-      }
-    }
-    if (partials != nullptr && ct < 128) {
-      const int which = ct >> 6, c = ct & 63;
-      float t = 0.f;
-      for (int rr = 0; rr < kRows; ++rr) {
-        const float v = s_out[rr * kOutLd + c] * s_valid[rr];
-        t += which ? v * v : v;
-      }
-      const long blk = (long)img * gridDim.x + blockIdx.x;
-      partials[(blk * 2 + which) * 64 + c] = t;
-    }
-  }
-  tc::tcgen05_fence_before();
-  __syncthreads();
-  if (tid == 0 && s_err) atomicExch(err, 1);
-  if (warp == 1) tc::tmem_dealloc<256>(d_tmem);
-}
-
 // ------------------------------------------------------------------------------------------------------------------
-// v3: persistent version of the A-in-TMEM kernel.  One CTA per SM walks a static list of (image, tile) pairs; the
+// Persistent A-in-TMEM kernel.  One CTA per SM walks a static list of (image, tile) pairs; the
 // weight ring (6 x 16 KB) streams continuously across tiles, the activation halo and the accumulator are double
 // buffered, and four dedicated epilogue warps drain accumulator t while the stagers / MMA already work on tile t+1:
 // prologue, epilogue and L2 latency all overlap the tensor pipe.
@@ -473,13 +125,9 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
         ok = tc::mbar_wait(&bar_wempty[s], ph ^ 1);
         if (!ok) break;
         if (tc::elect_one()) {
-          if ((lo_n64 & 2) && wi >= kP_WStages) {            // timing experiment only: reuse the stage contents
-            tc::mbar_arrive(&bar_wfull[s]);
-          } else {
-            tc::mbar_expect_tx(&bar_wfull[s], kP_WStageBytes);
-            tc::tma_load_2d(s_w + s * kP_WStageBytes, &map_w, &bar_wfull[s], 0, tap * 128);
-            tc::tma_load_2d(s_w + s * kP_WStageBytes + 16384, &map_w, &bar_wfull[s], 32, tap * 128);
-          }
+          tc::mbar_expect_tx(&bar_wfull[s], kP_WStageBytes);
+          tc::tma_load_2d(s_w + s * kP_WStageBytes, &map_w, &bar_wfull[s], 0, tap * 128);
+          tc::tma_load_2d(s_w + s * kP_WStageBytes + 16384, &map_w, &bar_wfull[s], 32, tap * 128);
         }
         __syncwarp();
         if (tap == 1 && tile + gridDim.x < ntiles) ok = load_halo(tile + gridDim.x, t + 1);
@@ -551,12 +199,6 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
         const int row = r + (tap / 3) * Wp + (tap % 3);
         const unsigned char* src = s_halo + (hb * 2 + set) * half_bytes + row * 128;
         uint32_t hi[32], lo[32];
-        if (lo_n64 & 4) {                                      // timing experiment only: handshakes without the staging work
-          ok = tc::mbar_wait(&bar_aempty[sa], pa ^ 1);
-          if (!ok) break;
-          tc::mbar_arrive(&bar_afull[sa]);
-          continue;
-        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 v = *reinterpret_cast<const float4*>(src + ((j ^ (row & 7)) << 4));
@@ -1131,51 +773,11 @@ DKTB_EXPORT int dktb_prep_weights_tc(const float* w, float* wb_fwd, float* wb_dg
   return dktb_launch_status();
 }
 
-// Same contract as dktb_conv3x3_fwd, with wb = the [9][2][64][64] hi/lo weight tensor of dktb_prep_weights_tc.
-// err: device int, set to 1 if a pipeline wait timed out (must be zero-initialised by the caller).
+// 64 -> 64 3x3 convolution (forward: wb = the forward tensor of dktb_prep_weights_tc + bias + BatchNorm partial sums;
+// dgrad: the flipped / transposed tensor, bias = partials = NULL) over the padded-flat layout [B][H+2][W+2][64].
+// Persistent tcgen05 kernel, one CTA per SM.  err: device int, set to 1 if a pipeline wait timed out (zero-initialised
+// by the caller; checked by ConvNetEngine.check_tc()).
 DKTB_EXPORT int dktb_conv3x3_tc_fwd(const float* a, const float* wb, const float* bias, float* out, float* partials,
-                                    int* err, int B, int H, int W, cudaStream_t stream) {
-  DKTB_CHECK_ARG(a && wb && out && err && B > 0 && H > 0 && W > 0 && B <= 65535);
-  const int Hp = H + 2, Wp = W + 2;
-  const long rows = (long)B * Hp * Wp;
-  DKTB_CHECK_ARG(rows < 2147483000L);
-  CUtensorMap map_a, map_w;
-  if (tc_make_tmap_2d(&map_a, a, 64, (uint64_t)rows, 32, kRows) != 0) return DKTB_BAD_ARG - 1;
-  if (tc_make_tmap_2d(&map_w, wb, 64, 2 * 9 * 64, 32, 64) != 0) return DKTB_BAD_ARG - 1;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    attr_done = true;
-  }
-  const int span = Hp * Wp - 2 * (Wp + 1);
-  dim3 grid((span + kRows - 1) / kRows, B);
-  conv3x3_tc_kernel<<<grid, 192, kSmemBytes, stream>>>(map_a, map_w, bias, out, partials, B, H, W, err);
-  return dktb_launch_status();
-}
-
-// v2 (A operand staged in TMEM): same contract as dktb_conv3x3_tc_fwd.
-DKTB_EXPORT int dktb_conv3x3_tc2_fwd(const float* a, const float* wb, const float* bias, float* out, float* partials,
-                                     int* err, int B, int H, int W, cudaStream_t stream) {
-  DKTB_CHECK_ARG(a && wb && out && err && B > 0 && H > 0 && W > 0 && B <= 65535);
-  const int Hp = H + 2, Wp = W + 2;
-  const long rows = (long)B * Hp * Wp;
-  DKTB_CHECK_ARG(rows < 2147483000L);
-  const int halo = kRows + 2 * (Wp + 1);
-  const int halo_pad = (halo + kHaloBox - 1) / kHaloBox * kHaloBox;
-  const int smem = 2 * halo_pad * 128 + kWStages * kWStageBytes + 1024;
-  DKTB_CHECK_ARG(smem <= 227 * 1024 && 2 * halo_pad * 128 >= kRows * kOutLd * 4);
-  CUtensorMap map_a, map_w;
-  if (tc_make_tmap_2d(&map_a, a, 64, (uint64_t)rows, 32, kHaloBox) != 0) return DKTB_BAD_ARG - 1;
-  if (tc_make_tmap_2d(&map_w, wb, 64, 2 * 9 * 64, 32, 128) != 0) return DKTB_BAD_ARG - 1;
-  cudaFuncSetAttribute(conv3x3_tc_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  const int span = Hp * Wp - 2 * (Wp + 1);
-  dim3 grid((span + kRows - 1) / kRows, B);
-  conv3x3_tc_ts_kernel<<<grid, kTsThreads, smem, stream>>>(map_a, map_w, bias, out, partials, B, H, W, halo_pad, err);
-  return dktb_launch_status();
-}
-
-// v3 (persistent, double-buffered halo / accumulator, dedicated epilogue warps): same contract as dktb_conv3x3_tc_fwd.
-DKTB_EXPORT int dktb_conv3x3_tc3_fwd(const float* a, const float* wb, const float* bias, float* out, float* partials,
                                      int* err, int B, int H, int W, cudaStream_t stream) {
   DKTB_CHECK_ARG(a && wb && out && err && B > 0 && H > 0 && W > 0);
   const int Hp = H + 2, Wp = W + 2;
@@ -1196,13 +798,7 @@ DKTB_EXPORT int dktb_conv3x3_tc3_fwd(const float* a, const float* wb, const floa
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = (int)(ntiles < sms ? ntiles : sms);
-  static int lo_n64 = -1;
-  if (lo_n64 < 0) {
-    const char* v = getenv("DKTB_TC3_LO_N64");
-    lo_n64 = (v != nullptr && v[0] == '0') ? 0 : 1;
-    const char* d = getenv("DKTB_TC3_TIMING_EXPERIMENT");     // bit 1: no weight streaming, bit 2: no staging (wrong results!)
-    if (d != nullptr) lo_n64 |= (atoi(d) & 6);
-  }
+  const int lo_n64 = 1;      // the a_lo pass covers only the w_hi half of the stacked operand (N = 64)
   conv3x3_tc_persistent_kernel<<<grid, kP_Threads, smem, stream>>>(map_a, map_w, bias, out, partials, B, H, W, halo_pad,
                                                                    tiles_per_img, lo_n64, err);
   return dktb_launch_status();

@@ -394,9 +394,14 @@ DKTB_EXPORT int dktb_gp_fit_large(const float* kbase, long kbase_class_stride, c
   a.loss_terms = loss_terms; a.info = info; a.dkbase = dkbase; a.dhyper = dhyper; a.work = work;
   a.grad_scale = grad_scale; a.jitter = jitter; a.N = N; a.C = C;
   const size_t smem = (size_t)GL_SMEM_FLOATS * sizeof(float);
-  // DKTB_GP_LARGE=ffma selects the CUDA-core tile product (default: mma.sync 3xTF32 tiles).  Two CTAs per SM: a third
-  // (80 registers) was slower at every size tried (profiles/r01_gp_size_sweep.txt).
+  // Device build: mma.sync 3xTF32 tile products.  (The g++ emulation build of the tests can select the CUDA-core tile
+  // product with DKTB_GP_LARGE=ffma.)  Two CTAs per SM: a third (80 registers) was slower at every size tried
+  // (profiles/r01_gp_size_sweep.txt).
+#ifdef DKTB_EMU
   static const bool ffma = [] { const char* v = getenv("DKTB_GP_LARGE"); return v && v[0] == 'f'; }();
+#else
+  const bool ffma = false;
+#endif
   if (ffma) {
     cudaFuncSetAttribute(gp_fit_large_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     DKTB_LAUNCH(gp_fit_large_kernel<false>, dim3(C, E), dim3(GL_THREADS), smem, stream, a);

@@ -12,7 +12,6 @@ Data layout in HBM (all fp32):
   gy[i], gact[i]                gradients in the same layouts (gy borders stay zero: dgrad/wgrad read them)
 """
 import math
-import os
 
 import torch
 
@@ -48,20 +47,19 @@ class ConvNetEngine:
         self.lib = lib
         self.depth = depth
         self.dev = torch.device(device)
-        mode = os.environ.get("DKTB_CONV", "tc3")      # tc3 | tc2 | tc (tcgen05 variants) | fp32 (CUDA-core kernels)
+        # CUDA device: the tcgen05 kernels (csrc/conv_tc.cu, conv1_bwd_mma.cu), always.  The fp32 CUDA-core twins
+        # (csrc/conv_fp32.cu) exist for the g++ emulation build that the CPU tests inject (tests/emu): a CPU "device"
+        # is the only way to reach them -- there is no switch between code paths on the GPU.
         if use_tc is None:
-            use_tc = mode in ("tc", "tc2", "tc3")
-        # tcgen05 3xTF32 kernels for the 64->64 convolutions (forward + dgrad); fp32 CUDA-core kernels otherwise
-        self.use_tc = bool(use_tc) and lib.has("dktb_conv3x3_tc_fwd") and self.dev.type == "cuda"
-        self.tc_fn = {"tc": "conv3x3_tc_fwd", "tc3": "conv3x3_tc3_fwd"}.get(mode, "conv3x3_tc2_fwd")
-        self.wgrad_tc = os.environ.get("DKTB_WGRAD", "tc") == "tc" and lib.has("dktb_conv3x3_wgrad_tc")
-        # first layer on tcgen05 (K = 27 im2col staged in TMEM); eval passes fuse BatchNorm + ReLU + pool into its epilogue
-        self.conv1_tc = self.use_tc and os.environ.get("DKTB_CONV1", "tc") == "tc" and lib.has("dktb_conv1_tc") \
-            and image_size + 2 <= 88
+            use_tc = self.dev.type == "cuda"
+        self.use_tc = bool(use_tc)
+        if self.use_tc and image_size + 2 > 88:
+            raise NotImplementedError("ConvNet inputs wider than 86 pixels (the reference's Conv4 / Conv6 run at 84)")
+        self.wgrad_tc = self.use_tc
+        self.conv1_tc = self.use_tc
         # first-block backward: BN/ReLU/pool backward fused into the conv1 weight gradient (no gy[0] tensor at all)
-        l0 = os.environ.get("DKTB_L0BWD", "mma")            # mma (tensor-core wgrad) | fused (FFMA wgrad) | split
-        self.l0_fused = l0 in ("mma", "fused") and lib.has("dktb_conv1_bwd_fused")
-        self.l0_fn = "conv1_bwd_fused_mma" if (l0 == "mma" and lib.has("dktb_conv1_bwd_fused_mma")) else "conv1_bwd_fused"
+        self.l0_fused = True
+        self.l0_fn = "conv1_bwd_fused_mma" if self.use_tc else "conv1_bwd_fused"
         self.layers = []
         h = image_size
         for i in range(depth):
@@ -137,13 +135,15 @@ class ConvNetEngine:
     def conv64(self, a, wt, bias, out, partials, B, H, W, st):
         """64->64 3x3 convolution over the padded layout (forward: wt_f + bias + partials; dgrad: wt_d)."""
         if self.use_tc:
-            getattr(self.lib, self.tc_fn)(a, wt, bias, out, partials, self.ws["tc_err"], B, H, W, st)
+            self.lib.conv3x3_tc_fwd(a, wt, bias, out, partials, self.ws["tc_err"], B, H, W, st)
         else:
             self.lib.conv3x3_fwd(a, wt, bias, out, partials, B, H, W, st)
 
     def check_tc(self):
-        if self.use_tc and int(self.ws["tc_err"].item()) != 0:
-            raise RuntimeError("tcgen05 convolution pipeline reported a barrier time-out")
+        if self.use_tc and self.ws is not None and int(self.ws["tc_err"].item()) != 0:
+            self.ws["tc_err"].zero_()
+            raise RuntimeError("tcgen05 convolution pipeline reported a barrier time-out: activations / gradients of the "
+                               "steps since the last check are not trustworthy")
 
     def forward(self, x, P, ipe, training, update_running=True):
         """x [B,3,H,W] (device, contiguous).  Returns features [B, D] (NHWC-flattened view of a workspace)."""

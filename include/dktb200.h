@@ -68,18 +68,12 @@ int dktb_conv3x3_wgrad(const float* a, const float* gy, float* dw, float* db, fl
 /* tcgen05 + TMA version of the 64->64 convolution (forward and dgrad), fp32-class accuracy via an error-compensated
  * 3xTF32 split.  wb = [9][2][64][64] hi/lo weight tensor written by dktb_prep_weights_tc ([tap][hl][n][k]; wb_dgrad has
  * the taps flipped and n/k swapped).  err: device int, zero-initialised by the caller, set to 1 when a pipeline
- * barrier wait timed out (a bug guard: results are then invalid).  Same layouts/partials as dktb_conv3x3_fwd. */
+ * barrier wait timed out (a bug guard: results are then invalid).  Same layouts/partials as dktb_conv3x3_fwd.
+ * Persistent CTAs (one per SM): activation halo loaded once per tile by TMA, A operand split in registers and staged in
+ * TMEM, weight ring streaming across tiles, double-buffered halo and accumulator, dedicated epilogue warps. */
 int dktb_prep_weights_tc(const float* w, float* wb_fwd, float* wb_dgrad, cudaStream_t stream);
 int dktb_conv3x3_tc_fwd(const float* a, const float* wb, const float* bias, float* out, float* partials, int* err,
                         int B, int H, int W, cudaStream_t stream);
-/* v2 of the same kernel: activation halo loaded once per tile, A operand split in registers and staged in TMEM. */
-int dktb_conv3x3_tc2_fwd(const float* a, const float* wb, const float* bias, float* out, float* partials, int* err,
-                         int B, int H, int W, cudaStream_t stream);
-/* v3: persistent CTAs (one per SM), 6-deep weight ring streaming across tiles, double-buffered halo and accumulator,
- * dedicated epilogue warps. */
-int dktb_conv3x3_tc3_fwd(const float* a, const float* wb, const float* bias, float* out, float* partials, int* err,
-                         int B, int H, int W, cudaStream_t stream);
-
 /* First layer (3->64, K=27 padded to 32) on tcgen05: im2col rows gathered from an NCHW patch, split and staged in TMEM.
  * wb1 [2][64][32] from dktb_prep_weights_conv1_tc.  mode 0: y + BatchNorm partials (tile numbering of dktb_conv1_fwd);
  * mode 1: partials only; mode 2: fused BatchNorm(mean, invstd: [B/ipe][64], ipe == 0: one row) + ReLU + MaxPool2d(2)

@@ -76,7 +76,7 @@ def test_adam(lib):
     kc.check_adam(lib, DEV, n=100003)
 
 
-@pytest.mark.parametrize("fn", ["conv3x3_tc_fwd", "conv3x3_tc2_fwd", "conv3x3_tc3_fwd"])
+@pytest.mark.parametrize("fn", ["conv3x3_tc_fwd"])
 def test_conv3x3_tc(lib, fn):
     """tcgen05 + TMA 3xTF32 convolution (forward and dgrad) at small and at the real layer shapes."""
     kc.check_conv3x3_tc(lib, DEV, fn=fn)
