@@ -85,6 +85,8 @@ SIGNATURES = {
     "dktb_avgpool_bwd": ("ppiiis", ctypes.c_int),
     "dktb_add_inplace": ("ppls", ctypes.c_int),
     "dktb_adam_step": ("pppplffffifs", ctypes.c_int),
+    "dktb_adam_step_dev": ("pppplffffpfs", ctypes.c_int),
+    "dktb_counter_add": ("pis", ctypes.c_int),
     "dktb_scale": ("plfs", ctypes.c_int),
     "dktb_episode_transform_smem": ("iii", ctypes.c_long),
     "dktb_episode_transform": ("pplpppiiiiiiiiffffffps", ctypes.c_int),

@@ -245,6 +245,11 @@ int dktb_spectral_bwd(const float* x, const float* raw_w, const float* raw_mu, c
 /* ---- optimiser (torch.optim.Adam, methods/DKT.py:114-115,164) ---------------------------------------- */
 int dktb_adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2,
                    float eps, int step, float grad_scale, cudaStream_t stream);
+/* The same update with the 1-based step count read from device memory (CUDA-graph replay of a whole meta-step: no
+ * per-step scalar is baked into a launch); dktb_counter_add advances such a counter on the stream. */
+int dktb_adam_step_dev(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2,
+                       float eps, const int* step_dev, float grad_scale, cudaStream_t stream);
+int dktb_counter_add(int* counter, int delta, cudaStream_t stream);
 int dktb_scale(float* x, long n, float a, cudaStream_t stream);
 
 /* ---- episode feeder: the per-image transform chain of the reference's episode loader

@@ -207,6 +207,14 @@ def check_correct(model, oracle, dev, image_size=32, n_way=2, n_support=1, n_que
         got_c = model.correct(x)
         assert got_c[:2] == ref_c[:2], (got_c, ref_c)
         assert np.array_equal(got.cpu().numpy().argmax(1), ref_logits.numpy().argmax(1))
+    # E-packed test path: identical hit counts, one kernel chain; and test_loop (which packs) against the oracle's counts
+    eps = [oep.synthetic_episode(900 + ep, n_way, n_support, n_query, image_size) for ep in range(episodes)]
+    ref_hits = [oracle.correct(x)[0] for x in eps]
+    hits = model.correct_packed(torch.stack(eps))
+    assert [float(h) for h in hits.tolist()] == ref_hits, (hits, ref_hits)
+    model.test_episodes_per_call = 3
+    acc = model.test_loop([(x, None) for x in eps])
+    assert abs(acc - float(np.mean([h / (n_way * n_query) * 100 for h in ref_hits]))) < 1e-9
     if not extras:
         return
     # Laplace branch: CUDA embeddings handed to scikit-learn, as the reference does (DKT.py:207-224)

@@ -220,3 +220,33 @@ def test_cholesky_status_warns_and_raises():
     lib.gp_info_accumulate(head.w["info"], head.w["info_sticky"], C, 0)
     with pytest.warns(RuntimeWarning, match="added jitter of 1.0e-05"):
         head.check()
+
+
+def test_cuda_graph_step_is_the_eager_step():
+    """cuda_graph = True replays the captured meta-step: bit-identical parameters / losses / accuracies to the eager
+    launches over several steps (incl. Adam's device-side step count and a second train_loop-style Adam restart)."""
+    from deep_kernel_transfer_b200 import backbone
+    from deep_kernel_transfer_b200.methods.DKT import DKT
+    batches = [torch.stack([oep.synthetic_episode(10 * k + e, 5, 1, 16, 84) for e in range(2)]).to(DEV) for k in range(6)]
+
+    def run(graph):
+        torch.manual_seed(0)
+        m = DKT(backbone.Conv4, 5, 1, kernel="bncossim", episodes_per_step=2).to(DEV)
+        m.train()
+        m.cuda_graph = graph
+        m._ensure_packed()
+        m._new_adam()
+        outs = []
+        for k, xb in enumerate(batches):
+            if k == 4:
+                m._new_adam()                      # what a second train_loop call does (DKT.py:114-115)
+            o = m.train_step(xb)
+            outs.append((o["loss"].clone(), o["acc_query"].clone()))
+        return m, outs
+    me, oe = run(False)
+    mg, og = run(True)
+    assert mg._graphs and all("graph" in v for v in mg._graphs.values())
+    for (le, ae), (lg, ag) in zip(oe, og):
+        assert torch.equal(le, lg) and torch.equal(ae, ag)
+    assert torch.equal(me._pack.flat, mg._pack.flat) and torch.equal(me._bufs.flat, mg._bufs.flat)
+    assert me._adam["step"] == mg._adam["step"] == 2 and int(mg._adam["step_dev"]) == 2
