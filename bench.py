@@ -21,17 +21,54 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# algorithmic MACs per image (measured from the reference's backbone.py): whole backbone / first conv
+MACS = {"Conv4": (97164288, 12192768), "ResNet18": (1813561344, 118013952), "ResNet50": (4087136256, 118013952)}
+
+# BASELINE.json configs -> what one "step" is.  cfg3 (configs[2]) is the configuration the metric is quoted on: default.
+CONFIGS = {
+    "cfg3": dict(arch="Conv4", kernel="bncossim", n_way=5, n_support=5, n_query=16, image=84, feat=1600, E=32, graph=False,
+                 workload="5-way 5-shot Conv4 bncossim, synthetic 84x84x3, meta-train step incl. monitoring (DKT.train_loop body)"),
+    "cfg2": dict(arch="Conv4", kernel="bncossim", n_way=5, n_support=1, n_query=16, image=84, feat=1600, E=1, graph=True,
+                 workload="5-way 1-shot Conv4 bncossim, synthetic 84x84x3, meta-train step incl. monitoring, ONE episode per "
+                          "Adam step (the reference's own granularity), step replayed from a CUDA graph"),
+    "cfg4": dict(arch="ResNet18", kernel="rbf", n_way=5, n_support=5, n_query=16, image=224, feat=512, E=4, graph=False,
+                 workload="5-way 5-shot ResNet18 RBF, synthetic 224x224x3, meta-train step incl. monitoring"),
+    "cfg5-e2e": dict(arch="ResNet50", kernel="rbf", n_way=20, n_support=5, n_query=16, image=224, feat=2048, E=1, graph=False,
+                     workload="20-way 5-shot ResNet50 RBF, synthetic 224x224x3 (N = 420 exact-GP systems), meta-train step "
+                              "incl. monitoring"),
+}
+CFG = CONFIGS["cfg3"]
 N_WAY, N_SUPPORT, N_QUERY, IMAGE = 5, 5, 16, 84
-WORKLOAD = "5-way 5-shot Conv4 bncossim, synthetic 84x84x3, meta-train step incl. monitoring (DKT.train_loop body)"
-# algorithmic work per training episode: N*(6*M_bb - 2*M_first) + monitoring 2*M_bb*N + GP
-M_BB, M_FIRST = 97164288, 12192768
+WORKLOAD = CFG["workload"]
+M_BB, M_FIRST = MACS["Conv4"]
 
 
-def episode_flops(n=N_WAY * (N_SUPPORT + N_QUERY), d=1600, c=N_WAY, monitor=True):
+def select_config(name):
+    global CFG, N_WAY, N_SUPPORT, N_QUERY, IMAGE, WORKLOAD, M_BB, M_FIRST
+    CFG = CONFIGS[name]
+    N_WAY, N_SUPPORT, N_QUERY, IMAGE = CFG["n_way"], CFG["n_support"], CFG["n_query"], CFG["image"]
+    WORKLOAD = CFG["workload"]
+    M_BB, M_FIRST = MACS[CFG["arch"]]
+
+
+def episode_flops(monitor=True):
+    """Algorithmic work per training episode: N*(6*M_bb - 2*M_first) + monitoring 2*M_bb*N + GP."""
+    n, d, c = N_WAY * (N_SUPPORT + N_QUERY), CFG["feat"], N_WAY
     f = n * (6 * M_BB - 2 * M_FIRST) + 4 * n * n * d + c * n ** 3
     if monitor:
         f += 2 * M_BB * n
     return f
+
+
+def make_model(E, dev=None):
+    from deep_kernel_transfer_b200 import backbone
+    from deep_kernel_transfer_b200.methods.DKT import DKT
+    m = DKT(getattr(backbone, CFG["arch"]), N_WAY, N_SUPPORT, kernel=CFG["kernel"], episodes_per_step=E)
+    if CFG["kernel"] == "rbf":      # un-normalised features: a lengthscale that keeps |x - x'|^2 / l^2 = O(1)
+        import math
+        for mm in m.model.models:
+            mm.covar_module.base_kernel.raw_lengthscale.data.fill_(math.sqrt(CFG["feat"]))
+    return m.to(dev) if dev is not None else m
 
 
 class ClockSampler:
@@ -84,39 +121,69 @@ class ClockSampler:
 
 def cpu_baseline(n_timed=3, n_warm=1):
     """The reference's CPU path (oracle port: reference backbone.py semantics + restated GPyTorch math) on the
-    host cores: full train_loop body per episode, E=1 (the reference's own granularity)."""
+    host cores: full train_loop body per episode, E=1 (the reference's own granularity).  ResNet configs run a BOUNDED
+    sample: the backbone work of `frac` of the episode's images (forward + backward + monitoring forward scale linearly
+    with the image count) plus the full-size GP on features of the right shape, added up and reported as such."""
     import torch
     from oracle import episode as oep
+    from oracle import gp as ogp
     cores = os.cpu_count() or 1
+    arch, kernel = CFG["arch"], CFG["kernel"]
     # pick the intra-op thread count that runs the backbone fastest on this host (large shared hosts are
     # slower with one thread per logical core); the chosen count is reported as `cores`
-    xprobe = oep.synthetic_episode(0, N_WAY, N_SUPPORT, N_QUERY, IMAGE).reshape(-1, 3, IMAGE, IMAGE)
-    probe = oep.OracleDKT("Conv4", "bncossim", n_way=N_WAY, n_support=N_SUPPORT, seed=0)
+    n_probe = N_WAY * (N_SUPPORT + N_QUERY) if arch == "Conv4" else 8
+    xprobe = oep.synthetic_episode(0, N_WAY, N_SUPPORT, N_QUERY, IMAGE).reshape(-1, 3, IMAGE, IMAGE)[:n_probe]
+    probe = oep.OracleDKT(arch, kernel, n_way=N_WAY, n_support=N_SUPPORT, seed=0)
     best = (1e30, cores)
     for th in sorted({c for c in (8, 16, 32, 64, cores) if c <= cores}):
         torch.set_num_threads(th)
         with torch.no_grad():
-            oep.features("Conv4", probe.bb, xprobe, "bncossim", training=False)
+            oep.features(arch, probe.bb, xprobe, kernel, training=False)
             t0 = time.perf_counter()
-            oep.features("Conv4", probe.bb, xprobe, "bncossim", training=False)
+            oep.features(arch, probe.bb, xprobe, kernel, training=False)
             dt = time.perf_counter() - t0
         best = min(best, (dt, th))
     threads = best[1]
     torch.set_num_threads(threads)
-    o = oep.OracleDKT("Conv4", "bncossim", n_way=N_WAY, n_support=N_SUPPORT, seed=0)
-    ts = []
-    for i in range(n_warm + n_timed):
-        x = oep.synthetic_episode(i, N_WAY, N_SUPPORT, N_QUERY, IMAGE)
+    if arch == "Conv4":
+        o = oep.OracleDKT(arch, kernel, n_way=N_WAY, n_support=N_SUPPORT, seed=0)
+        ts = []
+        for i in range(n_warm + n_timed):
+            x = oep.synthetic_episode(i, N_WAY, N_SUPPORT, N_QUERY, IMAGE)
+            t0 = time.perf_counter()
+            o.train_step(x, monitor=True)
+            dt = time.perf_counter() - t0
+            if i >= n_warm:
+                ts.append(dt)
+        ts.sort()
+        med = ts[len(ts) // 2]
+        sample = "%d warm-up + %d timed single-episode meta-train steps (median), same synthetic episodes" % (n_warm, n_timed)
+    else:
+        # bounded sample: per-class shots reduced so that the CPU work stays ~10-30 s; backbone time scales with images
+        n_full = N_WAY * (N_SUPPORT + N_QUERY)
+        q_small = 1 if arch == "ResNet50" else 3
+        o = oep.OracleDKT(arch, kernel, n_way=N_WAY, n_support=1, seed=0)
+        o.gp["raw_lengthscale"] = torch.full((N_WAY,), float(CFG["feat"]) ** 0.5)
+        x = oep.synthetic_episode(0, N_WAY, 1, q_small, IMAGE)
+        n_small = N_WAY * (1 + q_small)
         t0 = time.perf_counter()
         o.train_step(x, monitor=True)
-        dt = time.perf_counter() - t0
-        if i >= n_warm:
-            ts.append(dt)
-    ts.sort()
-    med = ts[len(ts) // 2]
+        t_small = time.perf_counter() - t0
+        # the GP of the full-size episode on features of the right shape (the small episode's GP is negligible)
+        z = torch.randn(n_full, CFG["feat"]).abs().requires_grad_(True)
+        p = {k: v.detach().clone().requires_grad_(k in ogp.trainable_gp_names(kernel)) for k, v in o.gp.items()}
+        tg = oep.make_targets(N_WAY, N_SUPPORT + N_QUERY)
+        t0 = time.perf_counter()
+        ogp.mll_loss(kernel, z, tg, p).backward()
+        with torch.no_grad():
+            ogp.predict(kernel, z.detach(), tg, z.detach(), {k: v.detach() for k, v in p.items()})
+        t_gp = time.perf_counter() - t0
+        med = t_small * n_full / n_small + t_gp
+        sample = ("bounded: one %d-image episode of the same backbone / resolution (%.1f s) scaled by %d/%d images + the "
+                  "full-size GP (N = %d, C = %d: %.1f s) on features of the right shape"
+                  % (n_small, t_small, n_full, n_small, n_full, N_WAY, t_gp))
     return {"value": 1.0 / med, "unit": "episodes/s", "cores": threads, "host_logical_cores": cores, "kind": "port",
-            "sample": "%d warm-up + %d timed single-episode meta-train steps (median), same synthetic episodes"
-                      % (n_warm, n_timed), "s_per_episode": med}
+            "sample": sample, "s_per_episode": med}
 
 
 def run_reference(args):
@@ -142,14 +209,25 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--episodes-per-gpu", type=int, default=32)
+    ap.add_argument("--episodes-per-gpu", type=int, default=None, help="episodes per GPU per step (default: the config's)")
+    ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS) + ["cfg5-sweep", "test"],
+                    help="BASELINE.json configs: cfg3 = configs[2] (the metric's configuration, default), cfg2 = configs[1], "
+                         "cfg4 = configs[3], cfg5-sweep / cfg5-e2e = configs[4], test = the test path (DKT.correct / test_loop)")
     ap.add_argument("--no-monitor", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="train", choices=["train", "feeder"],
                     help="train = the BASELINE metric (default); feeder = the GPU episode feeder alone (SURVEY 8f-1)")
     args = ap.parse_args()
+    if args.config in CONFIGS:
+        select_config(args.config)
+    if args.episodes_per_gpu is None:
+        args.episodes_per_gpu = CFG["E"] if args.config in CONFIGS else 32
     if args.workload == "feeder":
         return run_feeder(args)
+    if args.config == "cfg5-sweep":
+        return run_gp_sweep(args)
+    if args.config == "test":
+        return run_test_path(args)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -177,7 +255,8 @@ def main():
     W = max(3, args.warmup)
     K = args.steps
     torch.manual_seed(0)
-    model = DKT(backbone.Conv4, N_WAY, N_SUPPORT, kernel="bncossim", episodes_per_step=E).to(dev)
+    model = make_model(E, dev)
+    model.cuda_graph = bool(CFG["graph"]) and world == 1
     model.monitor = not args.no_monitor
     model.train()
     model._ensure_packed()
@@ -268,10 +347,11 @@ def main():
     # ---------------- feeder-fed leg: the same steps fed by the GPU episode feeder from a resident uint8 store
     # (host draws the episode composition + augmentation parameters, one transform kernel per step)
     ms_feed, feed_info = float("nan"), None
-    try:
-        ms_feed, feed_info = feeder_fed_leg(model, lib, dev, E, K, rank)
-    except Exception as ex:      # the headline legs above stand on their own
-        feed_info = {"error": repr(ex)}
+    if args.config == "cfg3":
+        try:
+            ms_feed, feed_info = feeder_fed_leg(model, lib, dev, E, K, rank)
+        except Exception as ex:      # the headline legs above stand on their own
+            feed_info = {"error": repr(ex)}
     barrier()
     t = torch.tensor([ms, ms_e2e, ms_feed], device=dev, dtype=torch.float64)
     if world > 1:
@@ -280,7 +360,7 @@ def main():
     # ---------------- roofline of the dominant kernel (64->64 3x3 conv at 42x42), timed live on its stream
     roof = None
     if rank == 0:
-        roof = dominant_kernel_roofline(model, lib, dev, E)
+        roof = dominant_kernel_roofline(model, lib, dev, E) if CFG["arch"] == "Conv4" else resnet_roofline(model, lib, dev, E)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -294,7 +374,9 @@ def main():
         "config": {"workload": WORKLOAD, "n_way": N_WAY, "n_shot": N_SUPPORT, "n_query": N_QUERY, "image": IMAGE,
                    "episodes_per_gpu_per_step": E, "global_episodes_per_step": E * world, "monitor": model.monitor,
                    "parallelism": "episodes sharded dp%d, one all-reduce of the flat gradient per step" % world,
-                   "l2": "per-step working set (~%.1f GB activations) far exceeds the 126 MB L2" % (E * 0.6)},
+                   "cuda_graph": bool(model.cuda_graph), "bench_config": args.config,
+                   "l2": "per-step working set (inputs %.0f MB + activations) exceeds the 126 MB L2; every step re-reads its "
+                         "inputs from HBM" % (step_bytes_in / 1e6)},
         "gpu_launches": launches,
         "tflops_algorithmic": eps * episode_flops(monitor=model.monitor) / 1e12,
         "cholesky_failures": info_bad,
@@ -304,7 +386,7 @@ def main():
                 "step_kernels_ms_median": step_ms[len(step_ms) // 2], "step_kernels_ms_max": step_ms[-1],
                 "inter_step_gap_ms_median": gap_ms[len(gap_ms) // 2] if gap_ms else 0.0,
                 "inter_step_gap_ms_max": gap_ms[-1] if gap_ms else 0.0, "first_step_start_ms": first_start_ms,
-                "note": "H2D of step k+1 overlaps step k on a copy stream; when the host link moves the 284 MB slower "
+                "note": "H2D of step k+1 overlaps step k on a copy stream; when the host link moves the step's input slower "
                         "than one step computes, the end-to-end rate is the link's"},
         "clocks": clocks, "roofline": roof,
     }
@@ -485,7 +567,358 @@ def run_feeder(args):
     print(json.dumps(line))
 
 
-def dominant_kernel_roofline(model, lib, dev, E):
+def tracked_traffic(key, units):
+    """Bytes per launch from profiles/traffic.json: {key: {"bytes": dram read + write of the captured launch, "units": how
+    many images / systems that launch processed, "source": the tracked ncu summary}} scaled to `units`; None if absent."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[key]
+        return float(t["bytes"]) / float(t["units"]) * units
+    except Exception:
+        return None
+
+
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def _time_launch(fn, reps=10, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def resnet_roofline(model, lib, dev, E):
+    """ResNet configs: the dominant layer shape (3x3, 64 -> 64 at 56x56: 4 of ResNet18's 16 3x3 convolutions, the largest
+    single share of the MACs; ResNet50: 3x3 64 -> 64 at 56x56 inside the first bottlenecks) timed alone on its stream."""
+    import torch
+    peaks = _peaks()
+    B = E * N_WAY * (N_SUPPORT + N_QUERY)
+    H = W = 56
+    C = 64
+    x = torch.randn(B, H, W, C, device=dev)
+    w = torch.randn(C, C, 3, 3, device=dev) * 0.05
+    wf, wd = torch.empty(w.numel(), device=dev), torch.empty(w.numel(), device=dev)
+    out = torch.empty(B, H, W, C, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    lib.conv2d_prep_mma(w, wf, wd, C, C, 3, 3, st)
+    ms = _time_launch(lambda: lib.conv2d_fwd_mma(x, wf, None, out, B, H, W, C, C, 3, 3, 1, 1, 1, st))
+    flops = 2.0 * B * H * W * C * C * 9
+    ach = flops / (ms / 1e3) / 1e12
+    peak = peaks.get("bf16_tflops", 1600.0) / 2.0
+    alg_bytes = 2.0 * B * H * W * C * 4
+    return {"kernel": "conv2d_mma_kernel (mma.sync 3xTF32 tiles) 3x3 64->64 forward, 56x56, B=%d images" % B,
+            "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "traffic": tracked_traffic("conv2d_mma_kernel@56x56x64", B), "algorithmic_bytes_per_launch": alg_bytes,
+            "algorithmic_flops_per_launch": flops, "ms_per_launch": ms,
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone) / 2 = dense TF32",
+            "note": "warp-level tensor-core tiles (HMMA path), operands through registers: bounded by that path's "
+                    "throughput, not by tcgen05's (profiles/r01_conv2d_mma.summary.txt)"}
+
+
+def gp_flops(n, c, d):
+    """Gram forward + backward (4 N^2 D) and C Cholesky / solve / inverse systems forward + backward (~C N^3), SURVEY 8d."""
+    return 4.0 * n * n * d + float(c) * n ** 3
+
+
+def run_gp_sweep(args):
+    """BASELINE configs[4]: GP-only sweep on pre-extracted features Z ~ N(0,1) [E, N, 2048], 20 one-vs-rest classes:
+    Gram -> C x (Cholesky, alpha, logdet, K^-1, dLoss/dK) -> dZ, per N in 25..500.  One step = E episodes of size N
+    through that chain; the JSON line's value is at N = 420 (20-way 5-shot, Q = 16), the sweep rides along."""
+    import torch
+    import torch.distributed as dist
+    from deep_kernel_transfer_b200 import _lib
+    from deep_kernel_transfer_b200.engine import GPHead, GPHeadParams, make_targets
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    C, D = 20, 2048
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import gp as ogp
+        torch.set_num_threads(os.cpu_count() or 1)
+        N = 420
+        z = torch.randn(N, D).requires_grad_(True)
+        p = ogp.default_gp_params("rbf", C, D)
+        p["raw_lengthscale"] = torch.full((C,), float(D) ** 0.5)
+        for k in ogp.trainable_gp_names("rbf"):
+            p[k].requires_grad_(True)
+        tg = -torch.ones(C, N)
+        for c in range(C):
+            tg[c, c * 21:(c + 1) * 21] = 1.0
+        ts = []
+        for i in range(max(1, min(args.steps, 3)) + 1):
+            t0 = time.perf_counter()
+            ogp.mll_loss("rbf", z, tg, p).backward()
+            ts.append(time.perf_counter() - t0)
+        med = sorted(ts[1:])[len(ts[1:]) // 2]
+        cb = {"value": 1.0 / med, "unit": "episodes/s", "cores": os.cpu_count(), "kind": "port",
+              "sample": "one N = 420, C = 20, D = 2048 RBF episode (-mll forward + backward) per step, median of %d" % (len(ts) - 1)}
+        print(json.dumps({"metric": "episodes/sec (exact-GP head only, N = 420)", "value": cb["value"], "unit": "episodes/s",
+                          "n_gpus": args.gpus, "steps": len(ts) - 1, "warmup": 1, "ms_per_step": med * 1e3,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "impl": "reference", "config": {"workload": "GP-only, N = 420, C = 20, D = 2048, RBF", "bench_config": "cfg5-sweep"},
+                          "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "episodes/s", "h2d_bytes_per_step": 0,
+                                                      "d2h_bytes_per_step": 0}}))
+        return
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    E = args.episodes_per_gpu if args.episodes_per_gpu != 32 else 8
+    W, K = max(3, args.warmup), args.steps
+    HP, GH = GPHeadParams(), GPHeadParams()
+    HP.raw_outputscale, HP.constant = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    HP.raw_noise = torch.full((C,), -2.2532, device=dev)
+    HP.raw_param = torch.full((C,), float(D) ** 0.5, device=dev)
+    GH.raw_outputscale, GH.constant, GH.raw_param = (torch.zeros(C, device=dev) for _ in range(3))
+    sweep = []
+    result = {}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    sizes = (25, 50, 100, 105, 180, 250, 420, 500)
+    for N in sizes:
+        per = max(1, N // C)
+        head = GPHead(lib, "rbf", C, D, D, 1, dev)
+        head.ensure(E, N)
+        z = torch.randn(E, N, D, device=dev, generator=torch.Generator(device=dev).manual_seed(rank * 100 + N))
+        tg = -torch.ones(C, N, device=dev)
+        for c in range(C):
+            tg[c, c * per:(c + 1) * per] = 1.0
+
+        def step():
+            head.fit(z, tg, HP, E, N, want_grad=True, grad_scale=1.0 / E)
+            head.backward(z.view(E * N, D), z, HP, GH, E, N)
+        for _ in range(W):
+            step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.launches
+        e0.record()
+        for _ in range(K):
+            step()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = lib.launches - l0
+        head.check()
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        eps = E * world * K / (ms / 1e3)
+        sweep.append({"N": N, "ms_per_step": ms / K, "episodes_per_s": eps, "systems_per_s": eps * C,
+                      "tflops_algorithmic": eps * gp_flops(N, C, D) / 1e12})
+        if N == 420:
+            # e2e: features start in pinned host memory, H2D inside the timed region, loss read back
+            host = z.cpu().pin_memory()
+            zb = torch.empty_like(z)
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(K):
+                zb.copy_(host, non_blocking=True)
+                loss = head.fit(zb, tg, HP, E, N, want_grad=True, grad_scale=1.0 / E)
+                head.backward(zb.view(E * N, D), zb, HP, GH, E, N)
+                float(loss.sum())
+            a1.record()
+            barrier()
+            t2 = torch.tensor([a0.elapsed_time(a1)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            # dominant kernel alone: the tiled Cholesky / inverse / gradient kernel
+            w = head.w
+            need = lib.gp_large_work_floats(E, C, N)
+            work = torch.empty(need, device=dev)
+            st = torch.cuda.current_stream(dev).cuda_stream
+            ms_fit = _time_launch(lambda: lib.gp_fit_large(w["kb"], N * N, tg, 0, HP.raw_outputscale, HP.constant, HP.raw_noise,
+                                                           w["alpha"], None, w["loss_terms"], w["info"], w["dk"], w["dhyper"],
+                                                           work, 1.0 / E, 1e-6, E, C, N, st))
+            result = {"ms": ms, "launches": launches, "eps": eps, "ms_e2e": float(t2[0]), "h2d": host.numel() * 4,
+                      "ms_fit": ms_fit}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = _peaks()
+    N = 420
+    fit_flops = float(E * C) * N ** 3              # ~C N^3 per episode (Cholesky + solves + inverse + gradient products)
+    ach = fit_flops / (result["ms_fit"] / 1e3) / 1e12
+    peak = peaks.get("bf16_tflops", 1600.0) / 2.0
+    line = {"metric": "episodes/sec (exact-GP head only, N = 420)", "value": result["eps"], "unit": "episodes/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": result["ms"] / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[4]: GP-only sweep on pre-extracted features Z~N(0,1) [E,N,2048], 20 classes, "
+                                   "RBF kernel: sqdist -> kernel -> C x (Cholesky, alpha, logdet, K^-1, dK) -> dZ; value at N = 420",
+                       "bench_config": "cfg5-sweep", "episodes_per_gpu_per_step": E, "classes": C, "D": D,
+                       "l2": "per step E*C = %d systems x 2 N^2 floats of workspace + kb/dk [E,C,N,N] = %.0f MB > 126 MB L2"
+                             % (E * C, E * C * 4 * N * N * 4 / 1e6)},
+            "gpu_launches": result["launches"], "tflops_algorithmic": result["eps"] * gp_flops(N, C, D) / 1e12,
+            "sweep": sweep,
+            "e2e": {"value": E * world * K / (result["ms_e2e"] / 1e3), "unit": "episodes/s",
+                    "h2d_bytes_per_step": result["h2d"], "d2h_bytes_per_step": 4, "ms_per_step": result["ms_e2e"] / K},
+            "roofline": {"kernel": "gp_fit_large_kernel (N = 420, %d systems per launch)" % (E * C), "bound": "tensor",
+                         "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                         "traffic": tracked_traffic("gp_fit_large_kernel@N420", E * C),
+                         "algorithmic_flops_per_launch": fit_flops, "ms_per_launch": result["ms_fit"],
+                         "algorithmic_bytes_per_launch": float(E * C) * (2 * N * N * 4),
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst) / 2 = dense TF32",
+                         "note": "latency-bound factorisation (sequential pivots, barriers, L2 round trips): the tensor pipe "
+                                 "is not the limiter (profiles/r01_gp_fit_large.summary.txt)"}}
+    if not args.no_cpu_baseline:
+        from oracle import gp as ogp
+        torch.set_num_threads(min(16, os.cpu_count() or 1))
+        z1 = torch.randn(N, D).requires_grad_(True)
+        p = ogp.default_gp_params("rbf", C, D)
+        p["raw_lengthscale"] = torch.full((C,), float(D) ** 0.5)
+        for k in ogp.trainable_gp_names("rbf"):
+            p[k].requires_grad_(True)
+        tg1 = -torch.ones(C, N)
+        for c in range(C):
+            tg1[c, c * 21:(c + 1) * 21] = 1.0
+        ogp.mll_loss("rbf", z1, tg1, p).backward()
+        t0 = time.perf_counter()
+        ogp.mll_loss("rbf", z1, tg1, p).backward()
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "episodes/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": "one N = 420, C = 20, D = 2048 RBF episode (-mll forward + backward) after one warm-up"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_test_path(args):
+    """The test path (DKT.correct / test_loop, methods/DKT.py:199-295) at the reference's evaluation shape: 5-way 5-shot,
+    15 queries per class (test.py:65-80), Conv4 bncossim, 600 episodes per test_loop.  One step = one packed call of 25
+    episodes; value = episodes/s with inputs resident, e2e = test_loop() over host episodes (H2D + the hit counts back)."""
+    import torch
+    from deep_kernel_transfer_b200 import _lib
+    from oracle import episode as oep
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    select_config("cfg3")
+    n_query = 15
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        torch.set_num_threads(min(16, os.cpu_count() or 1))
+        o = oep.OracleDKT("Conv4", "bncossim", n_way=5, n_support=5, seed=0)
+        ts = []
+        for i in range(max(1, min(args.steps, 5)) + 1):
+            x = oep.synthetic_episode(i, 5, 5, n_query, 84)
+            t0 = time.perf_counter()
+            o.correct(x)
+            ts.append(time.perf_counter() - t0)
+        med = sorted(ts[1:])[len(ts[1:]) // 2]
+        cb = {"value": 1.0 / med, "unit": "episodes/s", "cores": torch.get_num_threads(), "kind": "port",
+              "sample": "%d single test episodes through the oracle's correct() (median)" % (len(ts) - 1)}
+        print(json.dumps({"metric": "episodes/sec (meta-test)", "value": cb["value"], "unit": "episodes/s", "n_gpus": args.gpus,
+                          "steps": len(ts) - 1, "warmup": 1, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+                          "config": {"workload": "test path: 5-way 5-shot, 15 queries, Conv4 bncossim, 84x84", "bench_config": "test"},
+                          "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "episodes/s", "h2d_bytes_per_step": 0,
+                                                      "d2h_bytes_per_step": 0}}))
+        return
+    if rank != 0:
+        return      # the test path is single-process in the reference; replicas would only repeat it
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = _lib.load()
+    torch.manual_seed(0)
+    model = make_model(1, dev)
+    model.eval()
+    Et = 25
+    W, K = max(3, args.warmup), args.steps
+    pool = [oep.synthetic_episode(2000 + i, 5, 5, n_query, 84) for i in range(Et)]
+    xs_dev = torch.stack(pool).to(dev)
+    for _ in range(W):
+        model.correct_packed(xs_dev)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    l0 = lib.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_w0 = time.time()
+    e0.record()
+    for _ in range(K):
+        hits = model.correct_packed(xs_dev)
+    e1.record()
+    torch.cuda.synchronize()
+    t_w1 = time.time()
+    ms = e0.elapsed_time(e1)
+    launches = lib.launches - l0
+    clocks = sampler.stop(t_w0, t_w1)
+    # single-episode calls (the reference's granularity: one correct(x) per episode, a host sync each)
+    x1 = pool[0].to(dev)
+    for _ in range(3):
+        model.correct(x1)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        model.correct(x1)
+    torch.cuda.synchronize()
+    single = 20.0 / (time.perf_counter() - t0)
+    # e2e: the public test_loop over host episodes (600 like test.py:65 when steps allow; at least 4 packs)
+    n_ep = min(600, max(4, K) * Et)
+    loader = [(pool[i % Et], None) for i in range(n_ep)]
+    model.test_episodes_per_call = Et
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        model.test_loop(loader[:2 * Et])
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        acc = model.test_loop(loader)
+        a1.record()
+        torch.cuda.synchronize()
+    ms_e2e = a0.elapsed_time(a1)
+    n_img = 5 * (5 + n_query)
+    flops = 2.0 * M_BB * n_img
+    line = {"metric": "episodes/sec (meta-test)", "value": Et * K / (ms / 1e3), "unit": "episodes/s", "n_gpus": 1, "steps": K,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "test path (DKT.correct / test_loop): 5-way 5-shot, 15 queries per class (M = 75), Conv4 "
+                                   "bncossim, 84x84; 25 episodes packed per call",
+                       "bench_config": "test", "episodes_per_call": Et, "replicas": "replicas only: rank 0 measures",
+                       "l2": "25 episodes = 2500 images = 212 MB of input + activations beyond the 126 MB L2"},
+            "gpu_launches": launches, "tflops_algorithmic": Et * K / (ms / 1e3) * flops / 1e12,
+            "single_episode_calls_per_s": single, "test_accuracy": acc,
+            "e2e": {"value": n_ep / (ms_e2e / 1e3), "unit": "episodes/s", "h2d_bytes_per_step": Et * n_img * 3 * 84 * 84 * 4,
+                    "d2h_bytes_per_step": Et * 8, "ms_per_step": ms_e2e / (n_ep / Et), "episodes": n_ep,
+                    "note": "DKT.test_loop over host episodes: stack + H2D of each pack, kernels, hit counts back"},
+            "clocks": clocks, "roofline": dominant_kernel_roofline(model, lib, dev, Et, eval_mode=True)}
+    if not args.no_cpu_baseline:
+        torch.set_num_threads(min(16, os.cpu_count() or 1))
+        o = oep.OracleDKT("Conv4", "bncossim", n_way=5, n_support=5, seed=0)
+        o.correct(pool[0])
+        t0 = time.perf_counter()
+        for i in range(3):
+            o.correct(pool[i])
+        dt = (time.perf_counter() - t0) / 3
+        line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "episodes/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": "3 single test episodes through the oracle's correct() after one warm-up"}
+    print(json.dumps(line))
+
+
+def dominant_kernel_roofline(model, lib, dev, E, eval_mode=False):
     """Time the layer-2 convolution forward (64->64, 42x42: 67% of the backbone MACs) alone on its stream."""
     import torch
     peaks = {}
@@ -517,15 +950,16 @@ def dominant_kernel_roofline(model, lib, dev, E):
     flops = 2.0 * B * H * W * 64 * 576
     achieved = flops / (ms / 1e3) / 1e12
     if use_tc:
-        peak = peaks.get("bf16_tflops_sustained", 1400.0) / 2.0
-        which = "measured bf16 sustained / 2 (= dense TF32); 3xTF32 error-compensated split: three tf32 products per fp32 product"
+        peak = peaks.get("bf16_tflops", 1600.0) / 2.0
+        which = ("MEASURED_PEAKS.json bf16_tflops (burst: the kernel is timed alone) / 2 = dense TF32; 3xTF32 "
+                 "error-compensated split: three tf32 products per fp32 product, i.e. the arithmetic's ceiling is 1/3")
     else:
         peak = 75.0
         which = "nominal fp32 FFMA peak (148 SMs x 128 FMA x ~1.97 GHz); no measured fp32 figure in MEASURED_PEAKS.json"
-    # DRAM traffic of this kernel from the committed ncu --set full capture (profiles/r01_conv3x3_tc_ts.summary.txt:
-    # 833.08 MB read + 718.68 MB written for B = 1680 images), scaled to this launch's B; algorithmic bytes are the
-    # padded activation tensor read once + the interior of y written once
-    traffic = (833.078272e6 + 718.676736e6) / 1680.0 * B if use_tc else None
+    # DRAM traffic of this kernel: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of the SAME
+    # kernel at a recorded image count (profiles/traffic.json, written from the tracked summary it names), scaled to this
+    # launch's B; algorithmic bytes are the padded activation tensor read once + the interior of y written once
+    traffic = tracked_traffic("conv3x3_tc_persistent_kernel@42x42", B) if use_tc else None
     alg_bytes = B * ((H + 2) * (W + 2) * 256.0 + H * W * 256.0)
     return {"kernel": "conv3x3 64->64 forward, 42x42, B=%d images (%s)" % (B, "tcgen05 3xTF32, conv3x3_tc_persistent_kernel" if use_tc else "fp32 FFMA"),
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
