@@ -34,6 +34,12 @@ SIGNATURES = {
     "dktb_conv1_tc": ("pppppppppppiiiiis", ctypes.c_int),
     "dktb_conv3x3_tc_fwd": ("ppppppiiis", ctypes.c_int),
     "dktb_conv3x3_wgrad_tc": ("ppppppiiis", ctypes.c_int),
+    "dktb_conv_tcg_ok": ("iiiiiii", ctypes.c_int),
+    "dktb_conv_tcg_weight_floats": ("iii", ctypes.c_long),
+    "dktb_prep_weights_tcg": ("pppiiis", ctypes.c_int),
+    "dktb_conv_tcg": ("pppppiiiiiis", ctypes.c_int),
+    "dktb_zero_border": ("piiiis", ctypes.c_int),
+    "dktb_pad_copy": ("ppiiiiis", ctypes.c_int),
     "dktb_conv3x3_wgrad_reduce": ("pipps", ctypes.c_int),
     "dktb_bn_finalize": ("piiiipppppffs", ctypes.c_int),
     "dktb_bn_eval_prepare": ("ppppifs", ctypes.c_int),

@@ -1,0 +1,394 @@
+// tcgen05 convolution for the ResNet layers (reference backbone.py:135-247 SimpleBlock / BottleneckBlock): any
+// Cin, Cout that are multiples of 64 (64 ... 2048), 3x3 / stride 1 / pad 1 or 1x1 / stride 1, forward and dgrad, over the
+// padded-flat NHWC layout [B][H+2][W+2][C] (zero border) -- the same GEMM view and the same 3xTF32 error-compensated
+// arithmetic as the 64 -> 64 kernel of csrc/conv_tc.cu, generalised:
+//   work item = (128-pixel tile, 64-channel output block cb);  K = (Cin / 64 input groups g) x taps x 64 channels
+//   out[q][cb*64 + n] = sum_g sum_tap sum_k  A[q + off(tap)][g*64 + k] * W[cb*64 + n][g*64 + k][tap]
+// The activation halo of (tile, g) is one pair of 2-D TMA boxes (channel coordinate g*64 + {0, 32}); the weight ring
+// streams [cb][g][tap] stages of [w_hi | w_lo] x 64 channels (32 KB); the accumulator of a tile stays in TMEM across all
+// groups and taps.  A 1x1 convolution is the same kernel with one tap (a plain GEMM over the padded-flat rows).
+//   warp 0      TMA producer (halo of the next (tile, group) as soon as its buffer is free; weight ring)
+//   warp 1      MMA issuer (elected lane), TMEM owner
+//   warps 2-9   stagers: halo row -> tf32 hi / lo split -> tcgen05.st into one of 4 A stages
+//   warps 10-13 epilogue: tcgen05.ld accumulator -> +bias -> global store
+// Work items are ordered tile-major / cb-minor so that the CTAs resident at any time share their halos through L2.
+#include "dktb_common.cuh"
+
+#ifndef DKTB_EMU
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int kRows = 128;
+constexpr int kHaloBox = 32;
+constexpr int kWStages = 3;
+constexpr int kWStageBytes = 32768;           // [half 0 | half 1] x [w_hi | w_lo] x 64 rows x 128 B
+constexpr int kAStages = 4;
+constexpr int kThreads = 64 + 256 + 128;
+
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u;
+  lo = __float_as_uint(v - __uint_as_float(hi));      // exact remainder; the tensor core truncates it to tf32
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tcg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                const float* __restrict__ bias, float* __restrict__ out, int B, int H, int W, int Cout, int G, int nblk,
+                int ntaps, int halo_rows_pad, int tiles_per_img, int flat, int* __restrict__ err) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar_hfull[2], bar_hempty[2], bar_wfull[kWStages], bar_wempty[kWStages], bar_afull[kAStages],
+      bar_aempty[kAStages], bar_accfull[2], bar_accempty[2];
+  __shared__ uint32_t s_tmem;
+  __shared__ int s_err;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (*reinterpret_cast<volatile int*>(err) != 0) return;
+  const int Hp = H + 2, Wp = W + 2;
+  const int lead = ntaps == 9 ? Wp + 1 : 0;                  // rows of halo in front of the tile
+  const int half_bytes = halo_rows_pad * 128;
+  unsigned char* s_halo = smem;                               // [2 buffers][2 halves][halo_rows_pad][128 B]
+  unsigned char* s_w = smem + 4 * half_bytes;                 // [kWStages][32 KB]
+  const long nwork = (long)B * tiles_per_img * nblk;
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&bar_hfull[s], 1);
+      tc::mbar_init(&bar_hempty[s], 256);
+      tc::mbar_init(&bar_accfull[s], 1);
+      tc::mbar_init(&bar_accempty[s], 128);
+    }
+    for (int s = 0; s < kWStages; ++s) { tc::mbar_init(&bar_wfull[s], 1); tc::mbar_init(&bar_wempty[s], 1); }
+    for (int s = 0; s < kAStages; ++s) { tc::mbar_init(&bar_afull[s], 128); tc::mbar_init(&bar_aempty[s], 1); }
+    s_err = 0;
+    tc::fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { tc::prefetch_tmap(&map_a); tc::prefetch_tmap(&map_w); }
+  if (warp == 1) tc::tmem_alloc<512>(&s_tmem);
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem = s_tmem;
+  const uint32_t a_tmem = tmem + 256;                         // accumulators [0,256): 2 buffers x (x w_hi | x w_lo)
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    long vt = 0;                                              // (work item, group) counter: halo double buffering
+    long wi = 0;                                              // weight stage counter
+    bool ok = true;
+    auto load_halo = [&](long work, int g, long vv) -> bool {
+      const int hb = (int)(vv & 1), hp = (int)((vv >> 1) & 1);
+      const long tile = work / nblk;
+      const int img = (int)(tile / tiles_per_img), tix = (int)(tile % tiles_per_img);
+      const long img_base = flat ? 0 : (long)img * Hp * Wp;
+      const int q0 = flat ? tix * kRows : (Wp + 1) + tix * kRows;
+      if (!tc::mbar_wait(&bar_hempty[hb], hp ^ 1)) return false;
+      if (tc::elect_one()) {
+        tc::mbar_expect_tx(&bar_hfull[hb], 2 * half_bytes);
+        const int row0 = (int)(img_base + q0 - lead);
+        for (int h = 0; h < 2; ++h)
+          for (int r = 0; r < halo_rows_pad; r += kHaloBox)
+            tc::tma_load_2d(s_halo + (hb * 2 + h) * half_bytes + r * 128, &map_a, &bar_hfull[hb], g * 64 + h * 32, row0 + r);
+      }
+      __syncwarp();
+      return true;
+    };
+    if (blockIdx.x < nwork) ok = load_halo(blockIdx.x, 0, 0);
+    const int pre_tap = ntaps > 1 ? 1 : 0;                    // where the next halo is requested
+    for (long work = blockIdx.x; work < nwork && ok; work += gridDim.x) {
+      const int cb = (int)(work % nblk);
+      for (int g = 0; g < G && ok; ++g, ++vt) {
+        for (int tap = 0; tap < ntaps && ok; ++tap, ++wi) {
+          const int s = (int)(wi % kWStages), ph = (int)((wi / kWStages) & 1);
+          ok = tc::mbar_wait(&bar_wempty[s], ph ^ 1);
+          if (!ok) break;
+          if (tc::elect_one()) {
+            const int wrow = (((cb * G + g) * ntaps) + tap) * 128;
+            tc::mbar_expect_tx(&bar_wfull[s], kWStageBytes);
+            tc::tma_load_2d(s_w + s * kWStageBytes, &map_w, &bar_wfull[s], 0, wrow);
+            tc::tma_load_2d(s_w + s * kWStageBytes + 16384, &map_w, &bar_wfull[s], 32, wrow);
+          }
+          __syncwarp();
+          if (tap == pre_tap) {
+            if (g + 1 < G) ok = load_halo(work, g + 1, vt + 1);
+            else if (work + gridDim.x < nwork) ok = load_halo(work + gridDim.x, 0, vt + 1);
+          }
+        }
+      }
+    }
+    if (!ok) s_err = 1;
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer: 16 x (M128, N128|64, K8) per (group, tap)
+    const uint32_t idesc = tc::umma_idesc(2, 128, 128, 0, 0);
+    const uint32_t idesc_lo = tc::umma_idesc(2, 128, 64, 0, 0);      // a_lo only meets the w_hi half of the stacked operand
+    int t = 0;
+    long wi = 0;
+    bool ok = true;
+    for (long work = blockIdx.x; work < nwork && ok; work += gridDim.x, ++t) {
+      const int ab = t & 1, ap = (t >> 1) & 1;
+      ok = tc::mbar_wait(&bar_accempty[ab], ap ^ 1);
+      if (!ok) break;
+      tc::tcgen05_fence_after();
+      const uint32_t d_tmem = tmem + ab * 128;
+      const int nk = G * ntaps;
+      for (int kk = 0; kk < nk && ok; ++kk, ++wi) {
+        const int sw = (int)(wi % kWStages), pw = (int)((wi / kWStages) & 1);
+        const int pa = (int)((wi >> 1) & 1);
+        ok = tc::mbar_wait(&bar_wfull[sw], pw);
+        if (!ok) break;
+        const uint32_t wbase = tc::smem_u32(s_w + sw * kWStageBytes);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int sa = (int)((wi & 1) << 1) | h;
+          ok = tc::mbar_wait(&bar_afull[sa], pa);
+          if (!ok) break;
+          tc::tcgen05_fence_after();
+          const uint32_t acol = a_tmem + sa * 64;             // hi [0,32) | lo [32,64)
+          if (tc::elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t w_cat = tc::umma_desc_sw128(wbase + h * 16384 + k * 32, 16, 1024);
+              tc::umma_tf32_ts(d_tmem, acol + k * 8, w_cat, idesc, (kk | h | k) ? 1u : 0u);      // a_hi * [w_hi | w_lo]
+              tc::umma_tf32_ts(d_tmem, acol + 32 + k * 8, w_cat, idesc_lo, 1u);                    // a_lo * w_hi
+            }
+            tc::umma_commit(&bar_aempty[sa]);
+            if (h == 1) {
+              tc::umma_commit(&bar_wempty[sw]);
+              if (kk == nk - 1) tc::umma_commit(&bar_accfull[ab]);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+    if (!ok) s_err = 1;
+  } else if (warp < 10) {
+    // ------------------------------------------------------------------ stagers (256 threads): 32 channels per thread
+    const int ct = tid - 64;
+    const int set = ct >> 7;                          // channel half handled by this thread
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    long vt = 0;
+    long wi = 0;
+    bool ok = true;
+    for (long work = blockIdx.x; work < nwork && ok; work += gridDim.x) {
+      for (int g = 0; g < G && ok; ++g, ++vt) {
+        const int hb = (int)(vt & 1), hp = (int)((vt >> 1) & 1);
+        ok = tc::mbar_wait(&bar_hfull[hb], hp);
+        if (!ok) break;
+        for (int tap = 0; tap < ntaps && ok; ++tap, ++wi) {
+          const int sa = (int)((wi & 1) << 1) | set, pa = (int)((wi >> 1) & 1);
+          const int row = ntaps == 9 ? r + (tap / 3) * Wp + (tap % 3) : r;
+          const unsigned char* src = s_halo + (hb * 2 + set) * half_bytes + row * 128;
+          uint32_t hi[32], lo[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 v = *reinterpret_cast<const float4*>(src + ((j ^ (row & 7)) << 4));
+            split_tf32(v.x, hi[4 * j + 0], lo[4 * j + 0]);
+            split_tf32(v.y, hi[4 * j + 1], lo[4 * j + 1]);
+            split_tf32(v.z, hi[4 * j + 2], lo[4 * j + 2]);
+            split_tf32(v.w, hi[4 * j + 3], lo[4 * j + 3]);
+          }
+          ok = tc::mbar_wait(&bar_aempty[sa], pa ^ 1);
+          if (!ok) break;
+          tc::tcgen05_fence_after();
+          const uint32_t dst = a_tmem + sa * 64 + lane_base;
+          tc::tmem_st16(dst, hi);
+          tc::tmem_st16(dst + 16, hi + 16);
+          tc::tmem_st16(dst + 32, lo);
+          tc::tmem_st16(dst + 48, lo + 16);
+          tc::tmem_st_wait();
+          tc::tcgen05_fence_before();
+          tc::mbar_arrive(&bar_afull[sa]);
+        }
+        if (ok) tc::mbar_arrive(&bar_hempty[hb]);     // this thread no longer reads the halo buffer
+      }
+    }
+    if (!ok) s_err = 1;
+  } else {
+    // ------------------------------------------------------------------ epilogue (128 threads)
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    int t = 0;
+    bool ok = true;
+    for (long work = blockIdx.x; work < nwork && ok; work += gridDim.x, ++t) {
+      const int ab = t & 1, ap = (t >> 1) & 1;
+      const long tile = work / nblk;
+      const int cb = (int)(work % nblk);
+      const int img = (int)(tile / tiles_per_img), tix = (int)(tile % tiles_per_img);
+      const long img_base = flat ? 0 : (long)img * Hp * Wp;
+      const int q0 = flat ? tix * kRows : (Wp + 1) + tix * kRows;
+      ok = tc::mbar_wait(&bar_accfull[ab], ap);
+      if (!ok) break;
+      tc::tcgen05_fence_after();
+      const int q = q0 + r;
+      const int hp = q / Wp, wp = q - hp * Wp;
+      // flat (1x1 over a dense [rows][C] tensor: H = number of rows, B = 1): every row below H is an output
+      const bool valid = flat ? q < H : (q < Hp * Wp && hp >= 1 && hp <= H && wp >= 1 && wp <= W);
+      float* orow = out + (img_base + q) * (long)Cout + cb * 64;
+      const float* brow = bias ? bias + cb * 64 : nullptr;
+#pragma unroll
+      for (int c = 0; c < 64; c += 16) {
+        uint32_t v[16], u[16];
+        tc::tmem_ld16(tmem + ab * 128 + lane_base + c, v);
+        tc::tmem_ld16(tmem + ab * 128 + 64 + lane_base + c, u);
+        tc::tmem_ld_wait();
+        if (c == 48) {                                // accumulator fully read: hand the buffer back to the MMA warp
+          tc::tcgen05_fence_before();
+          tc::mbar_arrive(&bar_accempty[ab]);
+        }
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 o;
+            o.x = (__uint_as_float(v[j]) + __uint_as_float(u[j])) + (brow ? brow[c + j] : 0.f);
+            o.y = (__uint_as_float(v[j + 1]) + __uint_as_float(u[j + 1])) + (brow ? brow[c + j + 1] : 0.f);
+            o.z = (__uint_as_float(v[j + 2]) + __uint_as_float(u[j + 2])) + (brow ? brow[c + j + 2] : 0.f);
+            o.w = (__uint_as_float(v[j + 3]) + __uint_as_float(u[j + 3])) + (brow ? brow[c + j + 3] : 0.f);
+            dktb_st4(orow + c + j, o);
+          }
+        }
+      }
+    }
+    if (!ok) s_err = 1;
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (tid == 0 && s_err) atomicExch(err, 1);
+  if (warp == 1) tc::tmem_dealloc<512>(tmem);
+}
+
+// w [Cout][Cin][R][R] (R = 3 or 1) -> wb_fwd [Cout/64][Cin/64][taps][hi 64 | lo 64][64]  (row = output channel, col = input
+// channel) and wb_dgrad [Cin/64][Cout/64][taps][hi 64 | lo 64][64] (taps flipped, roles swapped): hi = tf32-rounded, lo =
+// rounded remainder; the hi and lo tiles of one (block, group, tap) are adjacent so that they form one N = 128 operand.
+__global__ void prep_weights_tcg_kernel(const float* __restrict__ w, float* __restrict__ wb_fwd,
+                                        float* __restrict__ wb_dgrad, int Cout, int Cin, int ntaps) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)Cout * Cin * ntaps) return;
+  const int tap = (int)(i % ntaps);
+  const int ci = (int)((i / ntaps) % Cin), co = (int)(i / ((long)ntaps * Cin));
+  const float v = w[i];
+  const float hi = tc::to_tf32_rna(v), lo = tc::to_tf32_rna(v - hi);
+  const int G = Cin / 64, NB = Cout / 64;
+  if (wb_fwd) {
+    const long base = ((((long)(co / 64) * G + ci / 64) * ntaps + tap) * 128 + (co % 64)) * 64 + (ci % 64);
+    wb_fwd[base] = hi;
+    wb_fwd[base + 64 * 64] = lo;
+  }
+  if (wb_dgrad) {
+    const long base = ((((long)(ci / 64) * NB + co / 64) * ntaps + (ntaps - 1 - tap)) * 128 + (ci % 64)) * 64 + (co % 64);
+    wb_dgrad[base] = hi;
+    wb_dgrad[base + 64 * 64] = lo;
+  }
+}
+
+// zero the 1-pixel border of a padded NHWC tensor [B][H+2][W+2][C] (after element-wise passes that ran over the whole
+// flat tensor); one thread per (border pixel, 4 channels)
+__global__ void zero_border_kernel(float* __restrict__ x, int B, int H, int W, int C) {
+  const int Hp = H + 2, Wp = W + 2;
+  const int nb = 2 * Wp + 2 * H;                      // border pixels per image
+  const long total = (long)B * nb * (C / 4);
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c4 = (int)(i % (C / 4)) * 4;
+  long t = i / (C / 4);
+  const int k = (int)(t % nb);
+  const int b = (int)(t / nb);
+  int hp, wp;
+  if (k < Wp) { hp = 0; wp = k; }
+  else if (k < 2 * Wp) { hp = Hp - 1; wp = k - Wp; }
+  else { const int j = k - 2 * Wp; hp = 1 + (j >> 1); wp = (j & 1) ? Wp - 1 : 0; }
+  dktb_st4(x + (((long)b * Hp + hp) * Wp + wp) * C + c4, make_float4(0.f, 0.f, 0.f, 0.f));
+}
+
+// dir 0: padded [B][H+2][W+2][C] interior <- dense [B][H][W][C];  dir 1: dense <- padded interior.  C % 4 == 0
+__global__ void pad_copy_kernel(float* __restrict__ dense, float* __restrict__ padded, int B, int H, int W, int C,
+                                int dir) {
+  const long total = (long)B * H * W * (C / 4);
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c4 = (int)(i % (C / 4)) * 4;
+  long t = i / (C / 4);
+  const int w = (int)(t % W);
+  t /= W;
+  const int h = (int)(t % H);
+  const int b = (int)(t / H);
+  const long po = (((long)b * (H + 2) + h + 1) * (W + 2) + w + 1) * C + c4;
+  const long uo = (((long)b * H + h) * W + w) * C + c4;
+  if (dir == 0) dktb_st4(padded + po, dktb_ld4(dense + uo));
+  else dktb_st4(dense + uo, dktb_ld4(padded + po));
+}
+
+}  // namespace
+
+DKTB_EXPORT int dktb_conv_tcg_ok(int Cin, int Cout, int R, int stride, int pad, int dil, int W) {
+  if (Cin % 64 != 0 || Cout % 64 != 0 || stride != 1 || dil != 1) return 0;
+  if (R == 1 && pad == 0) return 1;
+  return R == 3 && pad == 1 && W + 3 <= 64;       // halo (128 + 2 (W + 3) rows) x 4 buffers + weight ring within 227 KB
+}
+
+DKTB_EXPORT long dktb_conv_tcg_weight_floats(int Cin, int Cout, int R) { return (long)Cin * Cout * R * R * 2; }
+
+DKTB_EXPORT int dktb_prep_weights_tcg(const float* w, float* wb_fwd, float* wb_dgrad, int Cout, int Cin, int R,
+                                      cudaStream_t stream) {
+  DKTB_CHECK_ARG(w && Cin % 64 == 0 && Cout % 64 == 0 && (R == 1 || R == 3));
+  const long n = (long)Cout * Cin * R * R;
+  prep_weights_tcg_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(w, wb_fwd, wb_dgrad, Cout, Cin, R * R);
+  return dktb_launch_status();
+}
+
+// R = 3: convolution (stride 1, pad 1) over padded-flat NHWC tensors: a [B][H+2][W+2][Cin] (zero border) -> out
+// [B][H+2][W+2][Cout] (interior written, border untouched).  R = 1: a plain GEMM over the rows of DENSE tensors:
+// a [B*H*W][Cin] -> out [B*H*W][Cout] (no padding involved).  wb: the forward tensor of dktb_prep_weights_tcg (+ bias
+// [Cout] or NULL), or -- dgrad -- the dgrad tensor with Cin / Cout swapped by the caller (a = dL/dout [.., Cout], out =
+// dL/da [.., Cin]).  err: device int, zero-initialised by the caller, set to 1 when a pipeline wait timed out.
+DKTB_EXPORT int dktb_conv_tcg(const float* a, const float* wb, const float* bias, float* out, int* err, int B, int H,
+                              int W, int Cin, int Cout, int R, cudaStream_t stream) {
+  DKTB_CHECK_ARG(a && wb && out && err && B > 0 && H > 0 && W > 0);
+  DKTB_CHECK_ARG(dktb_conv_tcg_ok(Cin, Cout, R, 1, R == 3 ? 1 : 0, 1, W));
+  const int flat = R == 1;
+  const int Hp = H + 2, Wp = W + 2;
+  const long rows = flat ? (long)B * H * W : (long)B * Hp * Wp;
+  DKTB_CHECK_ARG(rows < 2147483000L);
+  const int ntaps = R * R;
+  const int G = Cin / 64, nblk = Cout / 64;
+  const int halo = kRows + (ntaps == 9 ? 2 * (Wp + 1) : 0);
+  const int halo_pad = (halo + kHaloBox - 1) / kHaloBox * kHaloBox;
+  const int smem = 4 * halo_pad * 128 + kWStages * kWStageBytes + 1024;
+  DKTB_CHECK_ARG(smem <= 227 * 1024);
+  CUtensorMap map_a, map_w;
+  if (tc_make_tmap_2d(&map_a, a, (uint64_t)Cin, (uint64_t)rows, 32, kHaloBox) != 0) return DKTB_BAD_ARG - 1;
+  if (tc_make_tmap_2d(&map_w, wb, 64, (uint64_t)nblk * G * ntaps * 128, 32, 128) != 0) return DKTB_BAD_ARG - 1;
+  cudaFuncSetAttribute(conv_tcg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const long span = flat ? rows : (long)Hp * Wp - 2 * (Wp + 1);
+  const int tiles_per_img = (int)((span + kRows - 1) / kRows);
+  const int nimg = flat ? 1 : B;
+  const long nwork = (long)nimg * tiles_per_img * nblk;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = (int)(nwork < sms ? nwork : sms);
+  // flat: the kernel sees one "image" of `rows` rows (H carries the row count for the validity test)
+  conv_tcg_kernel<<<grid, kThreads, smem, stream>>>(map_a, map_w, bias, out, nimg, flat ? (int)rows : H, W, Cout, G, nblk,
+                                                    ntaps, halo_pad, tiles_per_img, flat, err);
+  return dktb_launch_status();
+}
+
+DKTB_EXPORT int dktb_zero_border(float* x, int B, int H, int W, int C, cudaStream_t stream) {
+  DKTB_CHECK_ARG(x && B > 0 && H > 0 && W > 0 && C % 4 == 0);
+  const long total = (long)B * (2 * (W + 2) + 2 * H) * (C / 4);
+  zero_border_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, B, H, W, C);
+  return dktb_launch_status();
+}
+
+// dir 0: padded [B][H+2][W+2][C] interior <- dense [B][H][W][C] (the border of `padded` is not touched: allocate it
+// zeroed);  dir 1: dense <- padded interior
+DKTB_EXPORT int dktb_pad_copy(float* dense, float* padded, int B, int H, int W, int C, int dir, cudaStream_t stream) {
+  DKTB_CHECK_ARG(dense && padded && B > 0 && H > 0 && W > 0 && C % 4 == 0 && (dir == 0 || dir == 1));
+  const long total = (long)B * H * W * (C / 4);
+  pad_copy_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(dense, padded, B, H, W, C, dir);
+  return dktb_launch_status();
+}
+
+#endif  // DKTB_EMU

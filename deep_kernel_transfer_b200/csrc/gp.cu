@@ -121,8 +121,9 @@ __global__ void __launch_bounds__(256) gp_fit_kernel(GpFitArgs p) {
   // not positive, start over with 1e-6, 1e-5, 1e-4 (fp32 schedule: jitter * 10^i) added to the diagonal of K~
   const int attempts = p.jitter > 0.f ? 4 : 1;
   int attempt = 0;
+  float jit = 0.f;
   for (;; ++attempt) {
-    const float jit = attempt == 0 ? 0.f : p.jitter * (attempt == 1 ? 1.f : attempt == 2 ? 10.f : 100.f);
+    jit = attempt == 0 ? 0.f : p.jitter * (attempt == 1 ? 1.f : attempt == 2 ? 10.f : 100.f);
     if (tid == 0) s_fail = 0;
     for (int i = tid; i < N * N; i += nthr) {
       const int r = i / N, k = i % N;
@@ -189,14 +190,20 @@ __global__ void __launch_bounds__(256) gp_fit_kernel(GpFitArgs p) {
     }
   }
   __syncthreads();
-  // ---- u = L^-1 r ; alpha = L^-T u
+  // ---- u = L^-1 r ; alpha = L^-T u.  sum(alpha) = 1^T K~^-1 r is accumulated as (L^-1 1) . (L^-1 r): summing the alpha_k
+  // themselves cancels ~cond(K~) digits when the kernel matrix is close to rank one (RBF on similar features)
+  float asum_part = 0.f;
   for (int i = tid; i < N; i += nthr) {
-    float acc = 0.f;
-    for (int k = 0; k <= i; ++k) acc = fmaf(X[i * LD + k], s_r[k], acc);
+    float acc = 0.f, wsum = 0.f;
+    for (int k = 0; k <= i; ++k) {
+      acc = fmaf(X[i * LD + k], s_r[k], acc);
+      wsum += X[i * LD + k];
+    }
     s_u[i] = acc;
+    asum_part = fmaf(wsum, acc, asum_part);
   }
   __syncthreads();
-  float quad_part = 0.f, logdet_part = 0.f, asum_part = 0.f;
+  float quad_part = 0.f, logdet_part = 0.f, aa_part = 0.f;
   for (int k = tid; k < N; k += nthr) {
     float acc = 0.f;
     for (int i = k; i < N; ++i) acc = fmaf(X[i * LD + k], s_u[i], acc);
@@ -204,11 +211,12 @@ __global__ void __launch_bounds__(256) gp_fit_kernel(GpFitArgs p) {
     p.alpha[((long)e * C + c) * N + k] = acc;
     quad_part = fmaf(s_r[k], acc, quad_part);
     logdet_part += logf(s_diag[k]);
-    asum_part += acc;
+    aa_part = fmaf(acc, acc, aa_part);
   }
   const float quad = gp_block_sum(quad_part, s_red);
   const float logdet = 2.f * gp_block_sum(logdet_part, s_red);
   const float asum = gp_block_sum(asum_part, s_red);
+  const float aa = gp_block_sum(aa_part, s_red);
   if (tid == 0) {
     const float logp = -0.5f * (quad + logdet + (float)N * 1.8378770664093453f);
     p.loss_terms[(long)e * C + c] = -logp / ((float)N * (float)C);
@@ -221,7 +229,7 @@ __global__ void __launch_bounds__(256) gp_fit_kernel(GpFitArgs p) {
   // ---- gradients: dLoss/dK~ = (K~^-1 - alpha alpha^T) * coef,  K~^-1 = X^T X
   const float coef = p.grad_scale / (2.f * (float)N * (float)C);
   float* dk = p.dkbase ? p.dkbase + ((long)e * C + c) * N * N : nullptr;
-  float ds_part = 0.f, tr_part = 0.f;
+  float trinv_part = 0.f;
   for (int idx = tid; idx < N * N; idx += nthr) {
     const int i = idx / N, k = idx % N;
     const int m0 = i > k ? i : k;
@@ -229,11 +237,15 @@ __global__ void __launch_bounds__(256) gp_fit_kernel(GpFitArgs p) {
     for (int m = m0; m < N; ++m) acc = fmaf(X[m * LD + i], X[m * LD + k], acc);
     const float g = (acc - s_al[i] * s_al[k]) * coef;
     if (dk) dk[idx] = s * g;
-    ds_part = fmaf(g, kb[idx], ds_part);
-    if (i == k) tr_part += g;
+    if (i == k) trinv_part += acc;
   }
-  const float ds = gp_block_sum(ds_part, s_red);
-  const float tr = gp_block_sum(tr_part, s_red);
+  // hyper-parameter gradients in closed form from well-conditioned sums (positive terms only): with K~ = s Kb + nz I,
+  //   sum_ij dK~_ij Kb_ij = [ N - nz tr(K~^-1) - r.alpha + nz alpha.alpha ] coef / s,   sum_i dK~_ii = [tr(K~^-1) - alpha.alpha] coef
+  // (accumulating g_ij * Kb_ij over the N^2 entries instead loses ~cond(K~) digits)
+  const float trinv = gp_block_sum(trinv_part, s_red);
+  const float nz = noise + jit;
+  const float ds = coef * (((float)N - nz * trinv) - (quad - nz * aa)) / s;
+  const float tr = coef * (trinv - aa);
   if (tid == 0 && p.dhyper != nullptr) {
     float* o = p.dhyper + ((long)e * C + c) * 3;
     o[0] = p.raw_outputscale ? ds * dktb_sigmoid(p.raw_outputscale[c]) : 0.f;

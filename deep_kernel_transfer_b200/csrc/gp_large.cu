@@ -113,8 +113,9 @@ __global__ void __launch_bounds__(GL_THREADS, 2) gp_fit_large_kernel(GpFitLargeA
   // the diagonal (the fp32 schedule 1e-6, 1e-5, 1e-4 when the caller passes 1e-6; jitter == 0: a single attempt)
   const int attempts = p.jitter > 0.f ? 4 : 1;
   int attempt = 0;
+  float jit = 0.f;
   for (;; ++attempt) {
-  const float jit = attempt == 0 ? 0.f : p.jitter * (attempt == 1 ? 1.f : attempt == 2 ? 10.f : 100.f);
+  jit = attempt == 0 ? 0.f : p.jitter * (attempt == 1 ? 1.f : attempt == 2 ? 10.f : 100.f);
   if (tid == 0) *sm.fail = 0;
   for (int i0 = tid; i0 < N * N; i0 += 4 * GL_THREADS) {     // four independent loads in flight per thread
     float v[4];
@@ -287,18 +288,28 @@ __global__ void __launch_bounds__(GL_THREADS, 2) gp_fit_large_kernel(GpFitLargeA
     }
     return;
   }
-  // ---- u = L^-1 r (a warp per row), alpha = L^-T u (a thread per column, coalesced down the rows)
+  // ---- u = L^-1 r (a warp per row), alpha = L^-T u (a thread per column, coalesced down the rows).  sum(alpha) =
+  // 1^T K~^-1 r is accumulated as (L^-1 1) . (L^-1 r): summing the alpha_k cancels ~cond(K~) digits (see gp.cu)
+  float asum_part = 0.f;
   {
     const int lane = tid & 31, warp = tid >> 5;
     for (int i = warp; i < N; i += GL_THREADS / 32) {
-      float a = 0.f;
-      for (int k = lane; k <= i; k += 32) a = fmaf(X[(long)i * N + k], sm.r[k], a);
+      float a = 0.f, w1 = 0.f;
+      for (int k = lane; k <= i; k += 32) {
+        const float xv = X[(long)i * N + k];
+        a = fmaf(xv, sm.r[k], a);
+        w1 += xv;
+      }
       a = dktb_warp_sum(a);
-      if (lane == 0) sm.u[i] = a;
+      w1 = dktb_warp_sum(w1);
+      if (lane == 0) {
+        sm.u[i] = a;
+        asum_part = fmaf(w1, a, asum_part);
+      }
     }
   }
   __syncthreads();
-  float quad_part = 0.f, logdet_part = 0.f, asum_part = 0.f;
+  float quad_part = 0.f, logdet_part = 0.f, aa_part = 0.f;
   for (int k = tid; k < N; k += GL_THREADS) {
     float a = 0.f;
     for (int i = k; i < N; ++i) a = fmaf(X[(long)i * N + k], sm.u[i], a);
@@ -306,11 +317,12 @@ __global__ void __launch_bounds__(GL_THREADS, 2) gp_fit_large_kernel(GpFitLargeA
     p.alpha[((long)e * C + c) * N + k] = a;
     quad_part = fmaf(sm.r[k], a, quad_part);
     logdet_part += logf(sm.diag[k]);
-    asum_part += a;
+    aa_part = fmaf(a, a, aa_part);
   }
   const float quad = gl_block_sum(quad_part, sm.red);
   const float logdet = 2.f * gl_block_sum(logdet_part, sm.red);
   const float asum = gl_block_sum(asum_part, sm.red);
+  const float aa = gl_block_sum(aa_part, sm.red);
   if (tid == 0) {
     const float logp = -0.5f * (quad + logdet + (float)N * 1.8378770664093453f);
     p.loss_terms[(long)e * C + c] = -logp / ((float)N * (float)C);
@@ -326,7 +338,7 @@ __global__ void __launch_bounds__(GL_THREADS, 2) gp_fit_large_kernel(GpFitLargeA
   // ---- K~^-1 = X^T X, lower tiles; gradient epilogue on the tile and (through sm.t) on its mirror image
   const float coef = p.grad_scale / (2.f * (float)N * (float)C);
   float* dk = p.dkbase ? p.dkbase + ((long)e * C + c) * N * N : nullptr;
-  float ds_part = 0.f, tr_part = 0.f;
+  float trinv_part = 0.f;
   for (int ib = 0; ib < nT; ++ib) {
     const int i0 = ib * GL_T, ni = min(GL_T, N - i0);
     for (int kbk = 0; kbk <= ib; ++kbk) {
@@ -349,8 +361,7 @@ __global__ void __launch_bounds__(GL_THREADS, 2) gp_fit_large_kernel(GpFitLargeA
             g = (acc[i][j] - sm.al[gi] * sm.al[gk]) * coef;
             const long idx = (long)gi * N + gk;
             if (dk) dk[idx] = s * g;
-            ds_part = fmaf(kbk < ib ? 2.f * g : g, kb[idx], ds_part);     // kbase is a kernel matrix: symmetric
-            if (gi == gk) tr_part += g;
+            if (gi == gk) trinv_part += acc[i][j];
           }
           if (kbk < ib) sm.t[cc * GL_LDT + r] = g;
         }
@@ -367,8 +378,11 @@ __global__ void __launch_bounds__(GL_THREADS, 2) gp_fit_large_kernel(GpFitLargeA
       }
     }
   }
-  const float ds = gl_block_sum(ds_part, sm.red);
-  const float trc = gl_block_sum(tr_part, sm.red);
+  // hyper-parameter gradients in closed form from well-conditioned sums (gp.cu: K~ = s Kb + nz I)
+  const float trinv = gl_block_sum(trinv_part, sm.red);
+  const float nz = noise + jit;
+  const float ds = coef * (((float)N - nz * trinv) - (quad - nz * aa)) / s;
+  const float trc = coef * (trinv - aa);
   if (tid == 0 && p.dhyper != nullptr) {
     float* o = p.dhyper + ((long)e * C + c) * 3;
     o[0] = p.raw_outputscale ? ds * dktb_sigmoid(p.raw_outputscale[c]) : 0.f;

@@ -19,10 +19,40 @@ class ResNetEngine:
         self.D = net.final_feat_dim
         self.P = 1
         self._mma_w = {}             # conv module -> (wf, wd): k-contiguous weight copies for the tensor-core kernels
+        self._pads = {}              # (role, B, H, W, C) -> persistent zero-bordered padded-flat buffer
+        # tcgen05 / TMA kernel for every stride-1 3x3 and 1x1 convolution whose channel counts are multiples of 64
+        # (csrc/conv_tcg.cu); the remaining layers (stem, stride-2 convolutions) run on the mma.sync tiles
+        self.use_tcg = self.dev.type == "cuda" and lib.has("dktb_conv_tcg")
+        self.tc_err = torch.zeros(1, device=self.dev, dtype=torch.int32) if self.use_tcg else None
 
     # ------------------------------------------------------------------ helpers
     def _new(self, *shape, dtype=torch.float32):
         return torch.empty(*shape, device=self.dev, dtype=dtype)
+
+    def check_tc(self):
+        if self.use_tcg and int(self.tc_err.item()) != 0:
+            self.tc_err.zero_()
+            raise RuntimeError("tcgen05 convolution pipeline reported a barrier time-out: activations / gradients of the "
+                               "steps since the last check are not trustworthy")
+
+    def _padbuf(self, role, B, H, W, C):
+        """Persistent padded-flat buffer [B, H+2, W+2, C]: the border is zeroed once and never written again (pad_copy and
+        the convolution only touch the interior)."""
+        key = (role, B, H, W, C)
+        if key not in self._pads:
+            self._pads[key] = torch.zeros(B, H + 2, W + 2, C, device=self.dev)
+        return self._pads[key]
+
+    def _tcg_weights(self, m):
+        key = ("tcg", id(m))
+        if key not in self._mma_w:
+            n = self.lib.conv_tcg_weight_floats(m.in_channels, m.out_channels, m.kernel_size[0])
+            self._mma_w[key] = (self._new(n), self._new(n))
+        return self._mma_w[key]
+
+    def _tcg_ok(self, m, W):
+        return self.use_tcg and self.lib.conv_tcg_ok(m.in_channels, m.out_channels, m.kernel_size[0], m.stride[0],
+                                                     m.padding[0], m.dilation[0], W)
 
     def _conv(self, x, m, relu=0):
         B, H, W, Cin = x.shape
@@ -32,7 +62,19 @@ class ResNetEngine:
         Wo = self.lib.conv2d_out_size(W, R, st, pad, dil)
         out = self._new(B, Ho, Wo, m.out_channels)
         bias = m.bias.data if m.bias is not None else None
-        if not relu and self.lib.conv2d_mma_ok(Cin, m.out_channels):
+        if not relu and self._tcg_ok(m, W):
+            # tcgen05: 3x3 over padded-flat buffers (the zero border is the padding), 1x1 as a GEMM over the dense rows
+            Cout, sm = m.out_channels, _stream(self.dev)
+            wf, wd = self._tcg_weights(m)
+            self.lib.prep_weights_tcg(m.weight.data, wf, wd, Cout, Cin, R, sm)
+            if R == 3:
+                xp, yp = self._padbuf("in", B, H, W, Cin), self._padbuf("out", B, H, W, Cout)
+                self.lib.pad_copy(x, xp, B, H, W, Cin, 0, sm)
+                self.lib.conv_tcg(xp, wf, bias, yp, self.tc_err, B, H, W, Cin, Cout, R, sm)
+                self.lib.pad_copy(out, yp, B, H, W, Cout, 1, sm)
+            else:
+                self.lib.conv_tcg(x, wf, bias, out, self.tc_err, B, H, W, Cin, Cout, R, sm)
+        elif not relu and self.lib.conv2d_mma_ok(Cin, m.out_channels):
             # tensor-core tiles (mma.sync 3xTF32): refresh the two k-contiguous weight copies, then forward from `wf`;
             # the backward of the same step reads `wd`
             wf, wd = self._mma_weights(m)
@@ -166,7 +208,17 @@ class ResNetEngine:
                 lib.conv2d_wgrad(x, gy, None, m.weight.grad, m.bias.grad if m.bias is not None else None, scratch, B, H, W,
                                  Cin, Cout, R, R, stv, pad, dil, 0, st)
                 gx = None
-                if Cin > 3:      # no input gradient for the stem
+                if Cin > 3 and self._tcg_ok(m, W):        # dgrad = the same kernel on the flipped / transposed weights
+                    gx = torch.empty_like(x)
+                    wd = self._tcg_weights(m)[1]
+                    if R == 3:
+                        gyp, gxp = self._padbuf("out", B, H, W, Cout), self._padbuf("in", B, H, W, Cin)
+                        lib.pad_copy(gy, gyp, B, H, W, Cout, 0, st)
+                        lib.conv_tcg(gyp, wd, None, gxp, self.tc_err, B, H, W, Cout, Cin, R, st)
+                        lib.pad_copy(gx, gxp, B, H, W, Cin, 1, st)
+                    else:
+                        lib.conv_tcg(gy, wd, None, gx, self.tc_err, B, H, W, Cout, Cin, R, st)
+                elif Cin > 3:      # no input gradient for the stem
                     gx = torch.empty_like(x)
                     if lib.conv2d_mma_ok(Cin, Cout):      # `wd` was refreshed by this step's forward (weights unchanged since)
                         lib.conv2d_dgrad_mma(gy, self._mma_weights(m)[1], gx, B, H, W, Cin, Cout, R, R, stv, pad, dil, st)

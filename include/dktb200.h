@@ -74,6 +74,20 @@ int dktb_conv3x3_wgrad(const float* a, const float* gy, float* dw, float* db, fl
 int dktb_prep_weights_tc(const float* w, float* wb_fwd, float* wb_dgrad, cudaStream_t stream);
 int dktb_conv3x3_tc_fwd(const float* a, const float* wb, const float* bias, float* out, float* partials, int* err,
                         int B, int H, int W, cudaStream_t stream);
+/* ResNet layers on tcgen05 (reference backbone.py:135-247): any Cin, Cout that are multiples of 64, 3x3 / stride 1 /
+ * pad 1 over padded-flat NHWC tensors [B][H+2][W+2][C] (zero border; interior of `out` written) or 1x1 / stride 1 as a
+ * plain GEMM over the rows of dense [B*H*W][C] tensors; forward (wb_fwd + bias) and dgrad (wb_dgrad, Cin / Cout swapped
+ * by the caller); 3xTF32 error-compensated like dktb_conv3x3_tc_fwd.  dktb_conv_tcg_ok tells whether a layer qualifies;
+ * the weight tensors hold dktb_conv_tcg_weight_floats(Cin, Cout, R) floats each.  dktb_pad_copy moves a dense tensor
+ * into the interior of a (zero-bordered) padded one (dir 0) or back (dir 1); dktb_zero_border clears the border. */
+int dktb_conv_tcg_ok(int Cin, int Cout, int R, int stride, int pad, int dil, int W);
+long dktb_conv_tcg_weight_floats(int Cin, int Cout, int R);
+int dktb_prep_weights_tcg(const float* w, float* wb_fwd, float* wb_dgrad, int Cout, int Cin, int R, cudaStream_t stream);
+int dktb_conv_tcg(const float* a, const float* wb, const float* bias, float* out, int* err, int B, int H, int W, int Cin,
+                  int Cout, int R, cudaStream_t stream);
+int dktb_zero_border(float* x, int B, int H, int W, int C, cudaStream_t stream);
+int dktb_pad_copy(float* dense, float* padded, int B, int H, int W, int C, int dir, cudaStream_t stream);
+
 /* First layer (3->64, K=27 padded to 32) on tcgen05: im2col rows gathered from an NCHW patch, split and staged in TMEM.
  * wb1 [2][64][32] from dktb_prep_weights_conv1_tc.  mode 0: y + BatchNorm partials (tile numbering of dktb_conv1_fwd);
  * mode 1: partials only; mode 2: fused BatchNorm(mean, invstd: [B/ipe][64], ipe == 0: one row) + ReLU + MaxPool2d(2)

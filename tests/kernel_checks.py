@@ -876,3 +876,57 @@ def check_gp_jitter(lib, dev, N=12, large=False, seed=90):
     lib.gp_info_accumulate(info, sticky, E * C, 0)
     hi, lo = sticky.cpu().tolist()
     assert hi == max(got + got0) and lo == -2
+
+
+def check_conv_tcg(lib, dev, B=2, H=6, W=5, Cin=64, Cout=128, R=3, seed=100, rtol=2e-5, bias=True):
+    """ResNet-layer convolution on tcgen05 (csrc/conv_tcg.cu): forward (+bias) and dgrad against torch in float64;
+    3x3 over padded-flat tensors (border of the output untouched), 1x1 as a GEMM over dense rows."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, R, R, generator=g) * (1.0 / (Cin * R * R) ** 0.5)
+    b = torch.randn(Cout, generator=g) if bias else None
+    xr = x.double().clone().requires_grad_(True)
+    ref = F.conv2d(xr, w.double(), b.double() if bias else None, padding=R // 2)
+    gout = torch.randn(ref.shape, generator=g)
+    (ref * gout.double()).sum().backward()
+    n = lib.conv_tcg_weight_floats(Cin, Cout, R)
+    wf, wd = torch.empty(n, device=dev), torch.empty(n, device=dev)
+    lib.prep_weights_tcg(w.to(dev), wf, wd, Cout, Cin, R, 0)
+    err = torch.zeros(1, device=dev, dtype=torch.int32)
+    assert lib.conv_tcg_ok(Cin, Cout, R, 1, R // 2, 1, W)
+    if R == 3:
+        xp = to_padded_nhwc(x).to(dev)
+        yp = torch.full((B, H + 2, W + 2, Cout), 7.0, device=dev)
+        lib.conv_tcg(xp, wf, b.to(dev) if bias else None, yp, err, B, H, W, Cin, Cout, R, 0)
+        assert int(err) == 0
+        got = from_padded_nhwc(yp.cpu())
+        assert float((yp.cpu()[:, 0] - 7.0).abs().max()) == 0.0 and float((yp.cpu()[:, :, 0] - 7.0).abs().max()) == 0.0
+        gp = to_padded_nhwc(gout).to(dev)
+        gxp = torch.zeros(B, H + 2, W + 2, Cin, device=dev)
+        lib.conv_tcg(gp, wd, None, gxp, err, B, H, W, Cout, Cin, R, 0)
+        gx = from_padded_nhwc(gxp.cpu())
+        # pad_copy / zero_border round trip
+        dense = x.permute(0, 2, 3, 1).contiguous().to(dev)
+        pp = torch.zeros(B, H + 2, W + 2, Cin, device=dev)
+        lib.pad_copy(dense, pp, B, H, W, Cin, 0, 0)
+        assert torch.equal(pp, xp)
+        pp.add_(1.0)
+        lib.zero_border(pp, B, H, W, Cin, 0)
+        assert torch.equal(pp[:, 1:-1, 1:-1], xp[:, 1:-1, 1:-1] + 1.0) and float(pp[:, 0].abs().max()) == 0.0 \
+            and float(pp[:, -1].abs().max()) == 0.0 and float(pp[:, :, 0].abs().max()) == 0.0 and float(pp[:, :, -1].abs().max()) == 0.0
+        back = torch.empty_like(dense)
+        lib.pad_copy(back, xp, B, H, W, Cin, 1, 0)
+        assert torch.equal(back, dense)
+    else:
+        xd = x.permute(0, 2, 3, 1).contiguous().to(dev)
+        yd = torch.empty(B, H, W, Cout, device=dev)
+        lib.conv_tcg(xd, wf, b.to(dev) if bias else None, yd, err, B, H, W, Cin, Cout, R, 0)
+        assert int(err) == 0
+        got = yd.cpu().permute(0, 3, 1, 2)
+        gd = gout.permute(0, 2, 3, 1).contiguous().to(dev)
+        gxd = torch.empty(B, H, W, Cin, device=dev)
+        lib.conv_tcg(gd, wd, None, gxd, err, B, H, W, Cout, Cin, R, 0)
+        gx = gxd.cpu().permute(0, 3, 1, 2)
+    assert int(err) == 0
+    _close(got, ref.detach(), rtol=rtol, atol=1e-6, what="conv_tcg fwd %dx%d %d->%d" % (R, R, Cin, Cout))
+    _close(gx, xr.grad, rtol=rtol, atol=1e-6, what="conv_tcg dgrad %dx%d %d->%d" % (R, R, Cin, Cout))

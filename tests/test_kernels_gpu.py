@@ -122,3 +122,16 @@ def test_conv1_tc(lib):
 def test_resnet_ops(lib):
     kc.check_resnet_ops(lib, DEV)
     kc.check_resnet_ops(lib, DEV, E=2, ipe=3, H=14, W=14, C=256, seed=81)
+
+
+@pytest.mark.parametrize("cfg", [dict(), dict(B=3, H=56, W=56, Cin=64, Cout=64, seed=101),          # ResNet18 layer1
+                                 dict(B=3, H=28, W=28, Cin=128, Cout=128, seed=102, bias=False),      # layer2
+                                 dict(B=5, H=14, W=14, Cin=256, Cout=256, seed=103),                  # layer3
+                                 dict(B=7, H=7, W=7, Cin=512, Cout=512, seed=104, bias=False),        # layer4
+                                 dict(B=2, H=56, W=56, Cin=64, Cout=256, R=1, seed=105),              # bottleneck 1x1 up
+                                 dict(B=2, H=28, W=28, Cin=512, Cout=128, R=1, seed=106, bias=False),  # bottleneck 1x1 down
+                                 dict(B=3, H=7, W=7, Cin=2048, Cout=512, R=1, seed=107),              # ResNet50 layer4
+                                 dict(B=1, H=9, W=61, Cin=192, Cout=64, seed=108)])                   # widest supported row, odd group count
+def test_conv_tcg(lib, cfg):
+    """tcgen05 / TMA convolution of the ResNet layers: forward + dgrad, 3x3 padded-flat and 1x1 flat."""
+    kc.check_conv_tcg(lib, DEV, **cfg)
