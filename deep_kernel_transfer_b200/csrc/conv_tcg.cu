@@ -34,7 +34,7 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tcg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                 const float* __restrict__ bias, float* __restrict__ out, int B, int H, int W, int Cout, int G, int nblk,
-                int ntaps, int halo_rows_pad, int tiles_per_img, int flat, int* __restrict__ err) {
+                int ntaps, int halo_rows_pad, int tiles_per_img, int flat, int gchunk, int* __restrict__ err) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar_hfull[2], bar_hempty[2], bar_wfull[kWStages], bar_wempty[kWStages], bar_afull[kAStages],
@@ -120,43 +120,48 @@ conv_tcg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     // ------------------------------------------------------------------ MMA issuer: 16 x (M128, N128|64, K8) per (group, tap)
     const uint32_t idesc = tc::umma_idesc(2, 128, 128, 0, 0);
     const uint32_t idesc_lo = tc::umma_idesc(2, 128, 64, 0, 0);      // a_lo only meets the w_hi half of the stacked operand
-    int t = 0;
+    int t = 0;                                                // accumulator use counter (one per K chunk)
     long wi = 0;
     bool ok = true;
-    for (long work = blockIdx.x; work < nwork && ok; work += gridDim.x, ++t) {
-      const int ab = t & 1, ap = (t >> 1) & 1;
-      ok = tc::mbar_wait(&bar_accempty[ab], ap ^ 1);
-      if (!ok) break;
-      tc::tcgen05_fence_after();
-      const uint32_t d_tmem = tmem + ab * 128;
-      const int nk = G * ntaps;
-      for (int kk = 0; kk < nk && ok; ++kk, ++wi) {
-        const int sw = (int)(wi % kWStages), pw = (int)((wi / kWStages) & 1);
-        const int pa = (int)((wi >> 1) & 1);
-        ok = tc::mbar_wait(&bar_wfull[sw], pw);
+    for (long work = blockIdx.x; work < nwork && ok; work += gridDim.x) {
+      // K is cut into chunks of `gchunk` input groups; every chunk gets a FRESH TMEM accumulator that the epilogue warps
+      // drain into an fp32 running sum in registers: the tensor core's own accumulation does not round to nearest, and
+      // over K = 4608 (512 channels x 9 taps) that bias reaches 2e-5 of the result
+      for (int g0 = 0; g0 < G && ok; g0 += gchunk, ++t) {
+        const int ab = t & 1, ap = (t >> 1) & 1;
+        ok = tc::mbar_wait(&bar_accempty[ab], ap ^ 1);
         if (!ok) break;
-        const uint32_t wbase = tc::smem_u32(s_w + sw * kWStageBytes);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int sa = (int)((wi & 1) << 1) | h;
-          ok = tc::mbar_wait(&bar_afull[sa], pa);
+        tc::tcgen05_fence_after();
+        const uint32_t d_tmem = tmem + ab * 128;
+        const int nk = (min(G, g0 + gchunk) - g0) * ntaps;
+        for (int kk = 0; kk < nk && ok; ++kk, ++wi) {
+          const int sw = (int)(wi % kWStages), pw = (int)((wi / kWStages) & 1);
+          const int pa = (int)((wi >> 1) & 1);
+          ok = tc::mbar_wait(&bar_wfull[sw], pw);
           if (!ok) break;
-          tc::tcgen05_fence_after();
-          const uint32_t acol = a_tmem + sa * 64;             // hi [0,32) | lo [32,64)
-          if (tc::elect_one()) {
+          const uint32_t wbase = tc::smem_u32(s_w + sw * kWStageBytes);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t w_cat = tc::umma_desc_sw128(wbase + h * 16384 + k * 32, 16, 1024);
-              tc::umma_tf32_ts(d_tmem, acol + k * 8, w_cat, idesc, (kk | h | k) ? 1u : 0u);      // a_hi * [w_hi | w_lo]
-              tc::umma_tf32_ts(d_tmem, acol + 32 + k * 8, w_cat, idesc_lo, 1u);                    // a_lo * w_hi
+          for (int h = 0; h < 2; ++h) {
+            const int sa = (int)((wi & 1) << 1) | h;
+            ok = tc::mbar_wait(&bar_afull[sa], pa);
+            if (!ok) break;
+            tc::tcgen05_fence_after();
+            const uint32_t acol = a_tmem + sa * 64;             // hi [0,32) | lo [32,64)
+            if (tc::elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t w_cat = tc::umma_desc_sw128(wbase + h * 16384 + k * 32, 16, 1024);
+                tc::umma_tf32_ts(d_tmem, acol + k * 8, w_cat, idesc, (kk | h | k) ? 1u : 0u);      // a_hi * [w_hi | w_lo]
+                tc::umma_tf32_ts(d_tmem, acol + 32 + k * 8, w_cat, idesc_lo, 1u);                    // a_lo * w_hi
+              }
+              tc::umma_commit(&bar_aempty[sa]);
+              if (h == 1) {
+                tc::umma_commit(&bar_wempty[sw]);
+                if (kk == nk - 1) tc::umma_commit(&bar_accfull[ab]);
+              }
             }
-            tc::umma_commit(&bar_aempty[sa]);
-            if (h == 1) {
-              tc::umma_commit(&bar_wempty[sw]);
-              if (kk == nk - 1) tc::umma_commit(&bar_accfull[ab]);
-            }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
     }
@@ -212,42 +217,47 @@ conv_tcg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     int t = 0;
     bool ok = true;
-    for (long work = blockIdx.x; work < nwork && ok; work += gridDim.x, ++t) {
-      const int ab = t & 1, ap = (t >> 1) & 1;
+    for (long work = blockIdx.x; work < nwork && ok; work += gridDim.x) {
       const long tile = work / nblk;
       const int cb = (int)(work % nblk);
       const int img = (int)(tile / tiles_per_img), tix = (int)(tile % tiles_per_img);
       const long img_base = flat ? 0 : (long)img * Hp * Wp;
       const int q0 = flat ? tix * kRows : (Wp + 1) + tix * kRows;
-      ok = tc::mbar_wait(&bar_accfull[ab], ap);
+      float run[64];
+#pragma unroll
+      for (int j = 0; j < 64; ++j) run[j] = 0.f;
+      for (int g0 = 0; g0 < G && ok; g0 += gchunk, ++t) {       // one accumulator per K chunk, summed here in fp32
+        const int ab = t & 1, ap = (t >> 1) & 1;
+        ok = tc::mbar_wait(&bar_accfull[ab], ap);
+        if (!ok) break;
+        tc::tcgen05_fence_after();
+#pragma unroll
+        for (int c = 0; c < 64; c += 16) {
+          uint32_t v[16], u[16];
+          tc::tmem_ld16(tmem + ab * 128 + lane_base + c, v);
+          tc::tmem_ld16(tmem + ab * 128 + 64 + lane_base + c, u);
+          tc::tmem_ld_wait();
+          if (c == 48) {                              // accumulator fully read: hand the buffer back to the MMA warp
+            tc::tcgen05_fence_before();
+            tc::mbar_arrive(&bar_accempty[ab]);
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) run[c + j] += __uint_as_float(v[j]) + __uint_as_float(u[j]);
+        }
+      }
       if (!ok) break;
-      tc::tcgen05_fence_after();
       const int q = q0 + r;
       const int hp = q / Wp, wp = q - hp * Wp;
       // flat (1x1 over a dense [rows][C] tensor: H = number of rows, B = 1): every row below H is an output
       const bool valid = flat ? q < H : (q < Hp * Wp && hp >= 1 && hp <= H && wp >= 1 && wp <= W);
-      float* orow = out + (img_base + q) * (long)Cout + cb * 64;
-      const float* brow = bias ? bias + cb * 64 : nullptr;
+      if (valid) {
+        float* orow = out + (img_base + q) * (long)Cout + cb * 64;
+        const float* brow = bias ? bias + cb * 64 : nullptr;
 #pragma unroll
-      for (int c = 0; c < 64; c += 16) {
-        uint32_t v[16], u[16];
-        tc::tmem_ld16(tmem + ab * 128 + lane_base + c, v);
-        tc::tmem_ld16(tmem + ab * 128 + 64 + lane_base + c, u);
-        tc::tmem_ld_wait();
-        if (c == 48) {                                // accumulator fully read: hand the buffer back to the MMA warp
-          tc::tcgen05_fence_before();
-          tc::mbar_arrive(&bar_accempty[ab]);
-        }
-        if (valid) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float4 o;
-            o.x = (__uint_as_float(v[j]) + __uint_as_float(u[j])) + (brow ? brow[c + j] : 0.f);
-            o.y = (__uint_as_float(v[j + 1]) + __uint_as_float(u[j + 1])) + (brow ? brow[c + j + 1] : 0.f);
-            o.z = (__uint_as_float(v[j + 2]) + __uint_as_float(u[j + 2])) + (brow ? brow[c + j + 2] : 0.f);
-            o.w = (__uint_as_float(v[j + 3]) + __uint_as_float(u[j + 3])) + (brow ? brow[c + j + 3] : 0.f);
-            dktb_st4(orow + c + j, o);
-          }
+        for (int j = 0; j < 64; j += 4) {
+          float4 o = make_float4(run[j], run[j + 1], run[j + 2], run[j + 3]);
+          if (brow) { o.x += brow[j]; o.y += brow[j + 1]; o.z += brow[j + 2]; o.w += brow[j + 3]; }
+          dktb_st4(orow + j, o);
         }
       }
     }
@@ -370,8 +380,9 @@ DKTB_EXPORT int dktb_conv_tcg(const float* a, const float* wb, const float* bias
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = (int)(nwork < sms ? nwork : sms);
   // flat: the kernel sees one "image" of `rows` rows (H carries the row count for the validity test)
+  const int gchunk = ntaps == 9 ? 2 : 16;        // K per accumulator: 1152 (3x3) / 1024 (1x1)
   conv_tcg_kernel<<<grid, kThreads, smem, stream>>>(map_a, map_w, bias, out, nimg, flat ? (int)rows : H, W, Cout, G, nblk,
-                                                    ntaps, halo_pad, tiles_per_img, flat, err);
+                                                    ntaps, halo_pad, tiles_per_img, flat, gchunk, err);
   return dktb_launch_status();
 }
 

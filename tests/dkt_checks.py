@@ -339,6 +339,7 @@ def check_train_step_arch(arch, model_factory, dev, image_size, n_way=2, n_suppo
     model = model.to(dev)
     model.train()
     xs = torch.stack([oep.synthetic_episode(e, n_way, n_support, n_query, image_size) for e in range(E)])
+    gp0 = {k: v.detach().double().clone() for k, v in o32.gp.items()}      # pre-step hyper-parameters (Adam moves them)
     r64 = o64.train_step(xs.double(), monitor=False)
     ref = o32.train_step(xs)
     model._ensure_packed()
@@ -368,7 +369,7 @@ def check_train_step_arch(arch, model_factory, dev, image_size, n_way=2, n_suppo
             return leaves[n]
         stats = {"relu_flips": 0, "pool_flips": 0, "gates": 0}
         feats64 = resnet_replay64(eng.last_tape, True, stats, leaf)
-        gp64 = {k: v.detach().double().clone().requires_grad_(k in ogp.trainable_gp_names(kernel)) for k, v in o64.gp.items()}
+        gp64 = {k: v.clone().requires_grad_(k in ogp.trainable_gp_names(kernel)) for k, v in gp0.items()}
         N = n_way * (n_support + n_query)
         tg = oep.make_targets(n_way, n_support + n_query, torch.float64)
         tot = 0.0
@@ -402,7 +403,7 @@ def check_train_step_arch(arch, model_factory, dev, image_size, n_way=2, n_suppo
             report["features.branch"] = (e_feat, 0.0, tol)
         if e_feat > tol:
             badb["features"] = e_feat
-        gpd = {k: v.detach().double().clone().requires_grad_(k in ogp.trainable_gp_names(kernel)) for k, v in o64.gp.items()}
+        gpd = {k: v.clone().requires_grad_(k in ogp.trainable_gp_names(kernel)) for k, v in gp0.items()}
         totd = 0.0
         for e in range(E):
             f = feats_dev[e * N:(e + 1) * N]
