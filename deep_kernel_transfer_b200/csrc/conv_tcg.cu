@@ -269,6 +269,250 @@ conv_tcg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   if (warp == 1) tc::tmem_dealloc<512>(tmem);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Weight gradient on tcgen05 for the same layers:  dW[co][ci][tap] = sum_q X[q + off(tap)][ci] * G[q][co]  over all rows
+// (3x3: padded-flat rows, both operands zero-bordered, images concatenate seamlessly; 1x1: dense rows).  The 64 x 64
+// scheme of csrc/conv_tc.cu per (input group g, output block cb) pair = blockIdx.y: GEMM M = 128 = 2 taps x 64 ci, N = 64
+// co, K = rows; A = X^T gathered into TMEM by the stagers (3xTF32 split in registers), B = G re-laid-out K-major in shared
+// memory; accumulators of all tap pairs stay in TMEM; every CTA writes its partial dW once, dktb_wgrad_tcg's second
+// kernel reduces them in a fixed order (deterministic).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kKR = 32;                         // rows per K-block
+constexpr int kWgAStages = 3;
+constexpr int kWgThreads = 64 + 256;
+constexpr int kWgPStride = 9 * 64 * 64 + 64;    // one partial: [tap][ci][co] + bias row
+
+template <int A>
+__device__ __forceinline__ void wg_gather16(const unsigned char* __restrict__ xb, const int (&off)[8], uint32_t (&hi)[16],
+                                            uint32_t (&lo)[16]) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const float v = *reinterpret_cast<const float*>(xb + k * 128 + off[(A + k) & 7]);
+    split_tf32(v, hi[k], lo[k]);
+  }
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_wgrad_tcg_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g,
+                      float* __restrict__ partial, long total_rows, int Wp, int halo_pad, int ntaps, int nblk,
+                      int* __restrict__ err) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar_raw_full[2], bar_raw_empty[2], bar_bfull[2], bar_afull[kWgAStages], bar_aempty[kWgAStages],
+      bar_acc;
+  __shared__ uint32_t s_tmem;
+  __shared__ int s_err;
+  __shared__ float s_bias[4][64];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (*reinterpret_cast<volatile int*>(err) != 0) return;
+  const int pair = blockIdx.y, g_in = pair / nblk, cb = pair % nblk;
+  const int ngroups = (ntaps + 1) / 2;                      // tap pairs
+  const int lead = ntaps == 9 ? Wp + 1 : 0;
+  const int x_half_bytes = halo_pad * 128;
+  const int stage_bytes = 2 * x_half_bytes + 8192 + 16384;   // X raw | G raw | B hi | B lo
+  const long nkb = (total_rows + kKR - 1) / kKR;
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&bar_raw_full[s], 1);
+      tc::mbar_init(&bar_raw_empty[s], 257);      // 256 stagers done reading + 1 tcgen05.commit (B consumed)
+      tc::mbar_init(&bar_bfull[s], 256);
+    }
+    for (int s = 0; s < kWgAStages; ++s) { tc::mbar_init(&bar_afull[s], 256); tc::mbar_init(&bar_aempty[s], 1); }
+    tc::mbar_init(&bar_acc, 1);
+    s_err = 0;
+    tc::fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { tc::prefetch_tmap(&map_x); tc::prefetch_tmap(&map_g); }
+  if (warp == 1) tc::tmem_alloc<512>(&s_tmem);
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem = s_tmem;
+  const uint32_t a_tmem = tmem + 320;
+
+  if (warp == 0) {
+    int n = 0;
+    for (long kb = blockIdx.x; kb < nkb; kb += gridDim.x, ++n) {
+      const int s = n & 1, ph = (n >> 1) & 1;
+      if (!tc::mbar_wait(&bar_raw_empty[s], ph ^ 1)) { s_err = 1; break; }
+      if (tc::elect_one()) {
+        unsigned char* st = smem + s * stage_bytes;
+        tc::mbar_expect_tx(&bar_raw_full[s], 2 * x_half_bytes + 8192);
+        const long q0 = kb * kKR;
+        const int xrow0 = (int)(q0 - lead);
+        for (int h = 0; h < 2; ++h) {
+          for (int r = 0; r < halo_pad; r += kHaloBox)
+            tc::tma_load_2d(st + h * x_half_bytes + r * 128, &map_x, &bar_raw_full[s], g_in * 64 + h * 32, xrow0 + r);
+          tc::tma_load_2d(st + 2 * x_half_bytes + h * 4096, &map_g, &bar_raw_full[s], cb * 64 + h * 32, (int)q0);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = tc::umma_idesc(2, 128, 64, 0, 0);
+    bool ok = true;
+    int n = 0, ai = 0;
+    for (long kb = blockIdx.x; kb < nkb && ok; kb += gridDim.x, ++n) {
+      const int s = n & 1, ph = (n >> 1) & 1;
+      ok = tc::mbar_wait(&bar_bfull[s], ph);
+      if (!ok) break;
+      const uint32_t bbase = tc::smem_u32(smem + s * stage_bytes + 2 * x_half_bytes + 8192);
+      for (int g = 0; g < ngroups && ok; ++g, ++ai) {
+        const int sa = ai % kWgAStages, pa = (ai / kWgAStages) & 1;
+        ok = tc::mbar_wait(&bar_afull[sa], pa);
+        if (!ok) break;
+        tc::tcgen05_fence_after();
+        const uint32_t acol = a_tmem + sa * 64;
+        const uint32_t dcol = tmem + g * 64;
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t b_hi = tc::umma_desc_sw128(bbase + k * 32, 16, 1024);
+            const uint64_t b_lo = tc::umma_desc_sw128(bbase + 8192 + k * 32, 16, 1024);
+            tc::umma_tf32_ts(dcol, acol + 32 + k * 8, b_hi, idesc, (n | k) ? 1u : 0u);
+            tc::umma_tf32_ts(dcol, acol + k * 8, b_lo, idesc, 1u);
+            tc::umma_tf32_ts(dcol, acol + k * 8, b_hi, idesc, 1u);
+          }
+          tc::umma_commit(&bar_aempty[sa]);
+        }
+        __syncwarp();
+      }
+      if (tc::elect_one()) tc::umma_commit(&bar_raw_empty[s]);
+      __syncwarp();
+    }
+    if (!ok) s_err = 1;
+    if (tc::elect_one()) tc::umma_commit(&bar_acc);
+    __syncwarp();
+  } else {
+    const int ct = tid - 64;                                  // 0..255
+    const int set = ct >> 7;                                  // k range [set*16, +16) of the 32-row K-block
+    const int quarter = warp & 3;
+    const int L = quarter * 32 + lane;                        // TMEM lane: (tap-in-pair, ci)
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const int ci = L & 63, tsel = L >> 6;
+    const int co = ct & 63, kq8 = ct >> 6;                    // G transpose: 8 k values [kq8*8, +8) of channel co
+    int xoff[8];
+#pragma unroll
+    for (int p8 = 0; p8 < 8; ++p8) xoff[p8] = ((((ci & 31) >> 2) ^ p8) << 4) + (ci & 3) * 4;
+    float bias_acc = 0.f;
+    bool ok = true;
+    int n = 0, ai = 0;
+    for (long kb = blockIdx.x; kb < nkb && ok; kb += gridDim.x, ++n) {
+      const int s = n & 1, ph = (n >> 1) & 1;
+      ok = tc::mbar_wait(&bar_raw_full[s], ph);
+      if (!ok) break;
+      unsigned char* st = smem + s * stage_bytes;
+      {
+        const unsigned char* graw = st + 2 * x_half_bytes + (co >> 5) * 4096;
+        unsigned char* bhi = st + 2 * x_half_bytes + 8192 + co * 128;
+        unsigned char* blo = bhi + 8192;
+        const int cq = (co & 31) >> 2, cr = co & 3;
+#pragma unroll
+        for (int kq = 0; kq < 2; ++kq) {
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = kq8 * 8 + kq * 4 + j;
+            const float v = *reinterpret_cast<const float*>(graw + k * 128 + ((cq ^ (k & 7)) << 4) + cr * 4);
+            bias_acc += v;
+            split_tf32(v, h[j], l[j]);
+          }
+          const int kchunk = kq8 * 2 + kq;
+          const int off = (kchunk ^ (co & 7)) << 4;
+          *reinterpret_cast<uint4*>(bhi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(blo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+        tc::fence_proxy_async_smem();
+        tc::mbar_arrive(&bar_bfull[s]);
+      }
+      for (int g = 0; g < ngroups && ok; ++g, ++ai) {
+        const int sa = ai % kWgAStages, pa = (ai / kWgAStages) & 1;
+        const int tap = 2 * g + tsel;
+        uint32_t hi[16], lo[16];
+        if (tap < ntaps) {
+          const int shift = (ntaps == 9 ? (tap / 3) * Wp + (tap % 3) : 0) + set * 16;
+          const unsigned char* xb = st + (ci >> 5) * x_half_bytes + shift * 128;
+          switch (shift & 7) {
+            case 0: wg_gather16<0>(xb, xoff, hi, lo); break;
+            case 1: wg_gather16<1>(xb, xoff, hi, lo); break;
+            case 2: wg_gather16<2>(xb, xoff, hi, lo); break;
+            case 3: wg_gather16<3>(xb, xoff, hi, lo); break;
+            case 4: wg_gather16<4>(xb, xoff, hi, lo); break;
+            case 5: wg_gather16<5>(xb, xoff, hi, lo); break;
+            case 6: wg_gather16<6>(xb, xoff, hi, lo); break;
+            default: wg_gather16<7>(xb, xoff, hi, lo); break;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) { hi[k] = 0u; lo[k] = 0u; }
+        }
+        ok = tc::mbar_wait(&bar_aempty[sa], pa ^ 1);
+        if (!ok) break;
+        tc::tcgen05_fence_after();
+        const uint32_t dst = a_tmem + sa * 64 + lane_base + set * 16;
+        tc::tmem_st16(dst, hi);
+        tc::tmem_st16(dst + 32, lo);
+        tc::tmem_st_wait();
+        tc::tcgen05_fence_before();
+        tc::mbar_arrive(&bar_afull[sa]);
+      }
+      if (ok) tc::mbar_arrive(&bar_raw_empty[s]);
+    }
+    if (!ok) s_err = 1;
+    ok = ok && tc::mbar_wait(&bar_acc, 0);
+    tc::tcgen05_fence_after();
+    float* out = partial + ((long)pair * gridDim.x + blockIdx.x) * kWgPStride;
+    if (ok) {
+      for (int g = 0; g < ngroups; ++g) {
+        const int tap = 2 * g + tsel;
+#pragma unroll
+        for (int cc = 0; cc < 32; cc += 16) {
+          const int c = set * 32 + cc;
+          uint32_t v[16];
+          tc::tmem_ld16(tmem + g * 64 + lane_base + c, v);
+          tc::tmem_ld_wait();
+          if (tap < ntaps) {
+            float* o = out + ((long)tap * 64 + ci) * 64 + c;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              dktb_st4(o + j, make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                          __uint_as_float(v[j + 3])));
+          }
+        }
+      }
+    }
+    s_bias[kq8][co] = bias_acc;
+    tc::tcgen05_fence_before();
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (kq8 == 0) out[9 * 64 * 64 + co] = (s_bias[0][co] + s_bias[1][co]) + (s_bias[2][co] + s_bias[3][co]);
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (tid == 0 && s_err) atomicExch(err, 1);
+  if (warp == 1) tc::tmem_dealloc<512>(tmem);
+}
+
+// partial [pair = g*nblk + cb][split][tap][ci][co] (+ bias row) -> dw [Cout][Cin][taps], db [Cout] (from the g = 0 pairs)
+__global__ void conv_wgrad_tcg_reduce_kernel(const float* __restrict__ partial, int nsplit, int nblk, int Cin, int ntaps,
+                                             float* __restrict__ dw, float* __restrict__ db) {
+  const int pair = blockIdx.y, g = pair / nblk, cb = pair % nblk;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nw = ntaps * 64 * 64;
+  if (i >= nw + 64) return;
+  const int src = i < nw ? i : 9 * 64 * 64 + (i - nw);
+  const float* p = partial + (long)pair * nsplit * kWgPStride + src;
+  float t = 0.f;
+  for (int s = 0; s < nsplit; ++s) t += p[(long)s * kWgPStride];
+  if (i < nw) {
+    const int co = i % 64, ci = (i / 64) % 64, tap = i / 4096;
+    dw[((long)(cb * 64 + co) * Cin + g * 64 + ci) * ntaps + tap] = t;
+  } else if (db != nullptr && g == 0) {
+    db[cb * 64 + (i - nw)] = t;
+  }
+}
+
 // w [Cout][Cin][R][R] (R = 3 or 1) -> wb_fwd [Cout/64][Cin/64][taps][hi 64 | lo 64][64]  (row = output channel, col = input
 // channel) and wb_dgrad [Cin/64][Cout/64][taps][hi 64 | lo 64][64] (taps flipped, roles swapped): hi = tf32-rounded, lo =
 // rounded remainder; the hi and lo tiles of one (block, group, tap) are adjacent so that they form one N = 128 operand.
@@ -383,6 +627,53 @@ DKTB_EXPORT int dktb_conv_tcg(const float* a, const float* wb, const float* bias
   const int gchunk = ntaps == 9 ? 2 : 16;        // K per accumulator: 1152 (3x3) / 1024 (1x1)
   conv_tcg_kernel<<<grid, kThreads, smem, stream>>>(map_a, map_w, bias, out, nimg, flat ? (int)rows : H, W, Cout, G, nblk,
                                                     ntaps, halo_pad, tiles_per_img, flat, gchunk, err);
+  return dktb_launch_status();
+}
+
+
+// how many K-splits (CTAs per (group, block) pair) dktb_wgrad_tcg uses, and the scratch it needs (floats)
+static int wgrad_tcg_nsplit(long rows, int npairs) {
+  const long nkb = (rows + kKR - 1) / kKR;
+  int per = 148 / npairs;
+  if (per < 1) per = 1;
+  if (per > 148) per = 148;
+  return (int)(nkb < per ? nkb : per);
+}
+DKTB_EXPORT long dktb_wgrad_tcg_scratch_floats(int B, int H, int W, int Cin, int Cout, int R) {
+  const long rows = R == 1 ? (long)B * H * W : (long)B * (H + 2) * (W + 2);
+  const int npairs = (Cin / 64) * (Cout / 64);
+  return (long)npairs * wgrad_tcg_nsplit(rows, npairs) * kWgPStride;
+}
+
+// Weight gradient of the dktb_conv_tcg layers: x [.., Cin], gy [.., Cout] in the layouts of dktb_conv_tcg (R = 3: both
+// padded-flat with ZERO borders; R = 1: dense rows) -> dw [Cout][Cin][R][R] (overwritten), db [Cout] or NULL.
+DKTB_EXPORT int dktb_wgrad_tcg(const float* x, const float* gy, float* dw, float* db, float* scratch, int* err, int B,
+                               int H, int W, int Cin, int Cout, int R, cudaStream_t stream) {
+  DKTB_CHECK_ARG(x && gy && dw && scratch && err && B > 0 && H > 0 && W > 0);
+  DKTB_CHECK_ARG(dktb_conv_tcg_ok(Cin, Cout, R, 1, R == 3 ? 1 : 0, 1, W));
+  const int flat = R == 1;
+  const int Wp = W + 2;
+  const long rows = flat ? (long)B * H * W : (long)B * (H + 2) * Wp;
+  DKTB_CHECK_ARG(rows < 2147483000L);
+  const int ntaps = R * R;
+  const int G = Cin / 64, nblk = Cout / 64, npairs = G * nblk;
+  DKTB_CHECK_ARG(npairs <= 65535);
+  const int halo = kKR + (ntaps == 9 ? 2 * (Wp + 1) : 0);
+  const int halo_pad = (halo + kHaloBox - 1) / kHaloBox * kHaloBox;
+  const int stage = 2 * halo_pad * 128 + 8192 + 16384;
+  const int smem = 2 * stage + 1024;
+  DKTB_CHECK_ARG(smem <= 227 * 1024);
+  CUtensorMap map_x, map_g;
+  if (tc_make_tmap_2d(&map_x, x, (uint64_t)Cin, (uint64_t)rows, 32, kHaloBox) != 0) return DKTB_BAD_ARG - 1;
+  if (tc_make_tmap_2d(&map_g, gy, (uint64_t)Cout, (uint64_t)rows, 32, kKR) != 0) return DKTB_BAD_ARG - 1;
+  cudaFuncSetAttribute(conv_wgrad_tcg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int nsplit = wgrad_tcg_nsplit(rows, npairs);
+  conv_wgrad_tcg_kernel<<<dim3(nsplit, npairs), kWgThreads, smem, stream>>>(map_x, map_g, scratch, rows, Wp, halo_pad, ntaps,
+                                                                           nblk, err);
+  int rc = dktb_launch_status();
+  if (rc != 0) return rc;
+  conv_wgrad_tcg_reduce_kernel<<<dim3((ntaps * 4096 + 64 + 255) / 256, npairs), 256, 0, stream>>>(scratch, nsplit, nblk, Cin,
+                                                                                                 ntaps, dw, db);
   return dktb_launch_status();
 }
 

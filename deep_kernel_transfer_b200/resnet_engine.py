@@ -203,22 +203,33 @@ class ResNetEngine:
                 _, x, y, m, (B, H, W, Cin, R, stv, pad, dil) = rec
                 gy = grads.pop(y.data_ptr())
                 Cout = m.out_channels
+                gx = None
+                if self._tcg_ok(m, W):
+                    # tcgen05 weight gradient and dgrad (the forward kernel on the flipped / transposed weights); 3x3:
+                    # both operands in the persistent zero-bordered padded-flat buffers, 1x1: straight on the dense rows
+                    gx = torch.empty_like(x)
+                    wd = self._tcg_weights(m)[1]
+                    scratch = self._new(lib.wgrad_tcg_scratch_floats(B, H, W, Cin, Cout, R))
+                    bg = m.bias.grad if m.bias is not None else None
+                    if R == 3:
+                        xp, gyp = self._padbuf("in", B, H, W, Cin), self._padbuf("out", B, H, W, Cout)
+                        lib.pad_copy(x, xp, B, H, W, Cin, 0, st)
+                        lib.pad_copy(gy, gyp, B, H, W, Cout, 0, st)
+                        lib.wgrad_tcg(xp, gyp, m.weight.grad, bg, scratch, self.tc_err, B, H, W, Cin, Cout, R, st)
+                        lib.conv_tcg(gyp, wd, None, xp, self.tc_err, B, H, W, Cout, Cin, R, st)      # xp is free again
+                        lib.pad_copy(gx, xp, B, H, W, Cin, 1, st)
+                    else:
+                        lib.wgrad_tcg(x, gy, m.weight.grad, bg, scratch, self.tc_err, B, H, W, Cin, Cout, R, st)
+                        lib.conv_tcg(gy, wd, None, gx, self.tc_err, B, H, W, Cout, Cin, R, st)
+                    if self.trace is not None:
+                        self.trace.append((rec, gy, gx.clone(), m.weight.grad.clone()))
+                    give(x, gx)
+                    continue
                 ns = lib.conv2d_wgrad_nsplit(y.shape[0] * y.shape[1] * y.shape[2])
                 scratch = self._new(ns * R * R * Cin * Cout)
                 lib.conv2d_wgrad(x, gy, None, m.weight.grad, m.bias.grad if m.bias is not None else None, scratch, B, H, W,
                                  Cin, Cout, R, R, stv, pad, dil, 0, st)
-                gx = None
-                if Cin > 3 and self._tcg_ok(m, W):        # dgrad = the same kernel on the flipped / transposed weights
-                    gx = torch.empty_like(x)
-                    wd = self._tcg_weights(m)[1]
-                    if R == 3:
-                        gyp, gxp = self._padbuf("out", B, H, W, Cout), self._padbuf("in", B, H, W, Cin)
-                        lib.pad_copy(gy, gyp, B, H, W, Cout, 0, st)
-                        lib.conv_tcg(gyp, wd, None, gxp, self.tc_err, B, H, W, Cout, Cin, R, st)
-                        lib.pad_copy(gx, gxp, B, H, W, Cin, 1, st)
-                    else:
-                        lib.conv_tcg(gy, wd, None, gx, self.tc_err, B, H, W, Cout, Cin, R, st)
-                elif Cin > 3:      # no input gradient for the stem
+                if Cin > 3:      # no input gradient for the stem
                     gx = torch.empty_like(x)
                     if lib.conv2d_mma_ok(Cin, Cout):      # `wd` was refreshed by this step's forward (weights unchanged since)
                         lib.conv2d_dgrad_mma(gy, self._mma_weights(m)[1], gx, B, H, W, Cin, Cout, R, R, stv, pad, dil, st)

@@ -85,6 +85,12 @@ long dktb_conv_tcg_weight_floats(int Cin, int Cout, int R);
 int dktb_prep_weights_tcg(const float* w, float* wb_fwd, float* wb_dgrad, int Cout, int Cin, int R, cudaStream_t stream);
 int dktb_conv_tcg(const float* a, const float* wb, const float* bias, float* out, int* err, int B, int H, int W, int Cin,
                   int Cout, int R, cudaStream_t stream);
+/* weight gradient of the same layers on tcgen05: x [.., Cin], gy [.., Cout] in the layouts of dktb_conv_tcg (R = 3: both
+ * padded-flat with zero borders; R = 1: dense rows) -> dw [Cout][Cin][R][R], db [Cout] or NULL; scratch holds
+ * dktb_wgrad_tcg_scratch_floats(...) floats; per-CTA partials are reduced in a fixed order (deterministic). */
+long dktb_wgrad_tcg_scratch_floats(int B, int H, int W, int Cin, int Cout, int R);
+int dktb_wgrad_tcg(const float* x, const float* gy, float* dw, float* db, float* scratch, int* err, int B, int H, int W,
+                   int Cin, int Cout, int R, cudaStream_t stream);
 int dktb_zero_border(float* x, int B, int H, int W, int C, cudaStream_t stream);
 int dktb_pad_copy(float* dense, float* padded, int B, int H, int W, int C, int dir, cudaStream_t stream);
 

@@ -886,10 +886,15 @@ def check_conv_tcg(lib, dev, B=2, H=6, W=5, Cin=64, Cout=128, R=3, seed=100, rto
     w = torch.randn(Cout, Cin, R, R, generator=g) * (1.0 / (Cin * R * R) ** 0.5)
     b = torch.randn(Cout, generator=g) if bias else None
     xr = x.double().clone().requires_grad_(True)
-    ref = F.conv2d(xr, w.double(), b.double() if bias else None, padding=R // 2)
+    wr = w.double().clone().requires_grad_(True)
+    br = b.double().clone().requires_grad_(True) if bias else None
+    ref = F.conv2d(xr, wr, br, padding=R // 2)
     gout = torch.randn(ref.shape, generator=g)
     (ref * gout.double()).sum().backward()
     n = lib.conv_tcg_weight_floats(Cin, Cout, R)
+    dw = torch.empty(Cout, Cin, R, R, device=dev)
+    db = torch.empty(Cout, device=dev) if bias else None
+    scratch = torch.empty(lib.wgrad_tcg_scratch_floats(B, H, W, Cin, Cout, R), device=dev)
     wf, wd = torch.empty(n, device=dev), torch.empty(n, device=dev)
     lib.prep_weights_tcg(w.to(dev), wf, wd, Cout, Cin, R, 0)
     err = torch.zeros(1, device=dev, dtype=torch.int32)
@@ -905,6 +910,7 @@ def check_conv_tcg(lib, dev, B=2, H=6, W=5, Cin=64, Cout=128, R=3, seed=100, rto
         gxp = torch.zeros(B, H + 2, W + 2, Cin, device=dev)
         lib.conv_tcg(gp, wd, None, gxp, err, B, H, W, Cout, Cin, R, 0)
         gx = from_padded_nhwc(gxp.cpu())
+        lib.wgrad_tcg(xp, gp, dw, db, scratch, err, B, H, W, Cin, Cout, R, 0)
         # pad_copy / zero_border round trip
         dense = x.permute(0, 2, 3, 1).contiguous().to(dev)
         pp = torch.zeros(B, H + 2, W + 2, Cin, device=dev)
@@ -927,6 +933,10 @@ def check_conv_tcg(lib, dev, B=2, H=6, W=5, Cin=64, Cout=128, R=3, seed=100, rto
         gxd = torch.empty(B, H, W, Cin, device=dev)
         lib.conv_tcg(gd, wd, None, gxd, err, B, H, W, Cout, Cin, R, 0)
         gx = gxd.cpu().permute(0, 3, 1, 2)
+        lib.wgrad_tcg(xd, gd, dw, db, scratch, err, B, H, W, Cin, Cout, R, 0)
     assert int(err) == 0
     _close(got, ref.detach(), rtol=rtol, atol=1e-6, what="conv_tcg fwd %dx%d %d->%d" % (R, R, Cin, Cout))
     _close(gx, xr.grad, rtol=rtol, atol=1e-6, what="conv_tcg dgrad %dx%d %d->%d" % (R, R, Cin, Cout))
+    _close(dw, wr.grad, rtol=rtol, atol=1e-5, what="conv_tcg wgrad %dx%d %d->%d" % (R, R, Cin, Cout))
+    if bias:
+        _close(db, br.grad, rtol=rtol, atol=1e-4, what="conv_tcg bias grad")
