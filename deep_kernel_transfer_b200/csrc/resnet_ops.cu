@@ -11,10 +11,14 @@ __global__ void __launch_bounds__(256) bn2d_partial_kernel(const float* __restri
                                                            const float* __restrict__ invstd, float* __restrict__ partial,
                                                            int HW, int C, int ipe, int mode) {
   // mode 0: (x, x^2);  mode 1 (backward): g' = g * (y > 0 if y given), (g', g' * xhat)
-  __shared__ float s_red[2][4][64];
+  // Sums in DOUBLE: dbeta / dgamma (and the batch mean) are sums of up to 12 544 signed terms per image that largely cancel
+  // (cond = sum|t| / |sum t| ~ 1e2 .. 1e3 for the first layers' gradients); a sequential float32 chain over HW / 4 pixels
+  // left 1e-4 on the stem BatchNorm's gradients of a ResNet50 step, where torch's cascaded float32 sum leaves 1e-5.  The
+  // kernel is HBM-bound, the extra DADDs are free.
+  __shared__ double s_red[2][4][64];
   const int c = blockIdx.x * 64 + threadIdx.x % 64, sl = threadIdx.x / 64;
   const int b = blockIdx.y;
-  float a0 = 0.f, a1 = 0.f;
+  double a0 = 0.0, a1 = 0.0;
   if (c < C) {
     float m = 0.f, is = 0.f;
     if (mode == 1) {
@@ -26,13 +30,13 @@ __global__ void __launch_bounds__(256) bn2d_partial_kernel(const float* __restri
     for (int p = sl; p < HW; p += 4) {
       const float v = x[base + (long)p * C];
       if (mode == 0) {
-        a0 += v;
-        a1 = fmaf(v, v, a1);
+        a0 += (double)v;
+        a1 += (double)v * (double)v;
       } else {
         float gv = g[base + (long)p * C];
         if (y != nullptr && !(y[base + (long)p * C] > 0.f)) gv = 0.f;
-        a0 += gv;
-        a1 = fmaf(gv, (v - m) * is, a1);
+        a0 += (double)gv;
+        a1 += (double)gv * (double)((v - m) * is);
       }
     }
   }
@@ -41,8 +45,8 @@ __global__ void __launch_bounds__(256) bn2d_partial_kernel(const float* __restri
   __syncthreads();
   if (sl == 0 && c < C) {
     const int t = threadIdx.x;
-    partial[((long)b * C + c) * 2 + 0] = (s_red[0][0][t] + s_red[0][1][t]) + (s_red[0][2][t] + s_red[0][3][t]);
-    partial[((long)b * C + c) * 2 + 1] = (s_red[1][0][t] + s_red[1][1][t]) + (s_red[1][2][t] + s_red[1][3][t]);
+    partial[((long)b * C + c) * 2 + 0] = (float)((s_red[0][0][t] + s_red[0][1][t]) + (s_red[0][2][t] + s_red[0][3][t]));
+    partial[((long)b * C + c) * 2 + 1] = (float)((s_red[1][0][t] + s_red[1][1][t]) + (s_red[1][2][t] + s_red[1][3][t]));
   }
 }
 

@@ -315,7 +315,7 @@ def check_regression(dev, lib=None, image=36, n=7, n_support=4, tol=2e-4, kernel
 
 def check_train_step_arch(arch, model_factory, dev, image_size, n_way=2, n_support=1, n_query=2, E=2, kernel="rbf",
                           lib=None, tol=1e-4, env_factor=4.0, grad_check=True, report=None, lengthscale=(1.5, 2.5),
-                          same_branch=False):
+                          same_branch=False, grad_tol=None):
     """One packed meta-train step of an arbitrary backbone (ResNet*) against the oracle: loss, every backbone / GP
     gradient (fp64 arbiter + fp32 envelope), monitoring arg-max after re-synchronising the post-step weights."""
     from deep_kernel_transfer_b200.methods.DKT import DKT
@@ -408,7 +408,7 @@ def check_train_step_arch(arch, model_factory, dev, image_size, n_way=2, n_suppo
                     leaves[n].grad.abs().max() < 1e-6 * leaves[wname].grad.abs().max():
                 continue      # a bias that BatchNorm cancels
             e_ = rel_err(p_.grad, leaves[n].grad)
-            bar_ = max(tol, 3.0 * floor_b.get(n, 0.0))
+            bar_ = max(grad_tol or tol, 3.0 * floor_b.get(n, 0.0))
             if report is not None:
                 report["g." + n] = (e_, floor_b.get(n, 0.0), bar_)
                 report["free.g." + n] = (rel_err(p_.grad, r64["grads"][n]), rel_err(ref["grads"][n], r64["grads"][n]), float("inf"))
