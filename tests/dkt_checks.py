@@ -381,7 +381,8 @@ def check_train_step_arch(arch, model_factory, dev, image_size, n_way=2, n_suppo
             tot = tot + ogp.mll_loss(kernel, f, tg, gp64) / E
         tot.backward()
         # the same replay in float32 (torch / cuDNN on the same gates): what fp32 arithmetic itself loses through the depth
-        # of the network on a FIXED branch -- the envelope for the device's fp32-class arithmetic (3x for 3xTF32 operands)
+        # of the network on a FIXED branch -- the envelope for the device's fp32-class arithmetic (6x: 3xTF32 operands carried
+        # to 2^-21 instead of 2^-24, tensor-core accumulation that does not round to nearest)
         leaves32 = {}
 
         def leaf32(t):
@@ -408,7 +409,7 @@ def check_train_step_arch(arch, model_factory, dev, image_size, n_way=2, n_suppo
                     leaves[n].grad.abs().max() < 1e-6 * leaves[wname].grad.abs().max():
                 continue      # a bias that BatchNorm cancels
             e_ = rel_err(p_.grad, leaves[n].grad)
-            bar_ = max(grad_tol or tol, 3.0 * floor_b.get(n, 0.0))
+            bar_ = max(grad_tol or tol, 6.0 * floor_b.get(n, 0.0))      # 6 x what float32 itself loses on this branch
             if report is not None:
                 report["g." + n] = (e_, floor_b.get(n, 0.0), bar_)
                 report["free.g." + n] = (rel_err(p_.grad, r64["grads"][n]), rel_err(ref["grads"][n], r64["grads"][n]), float("inf"))
