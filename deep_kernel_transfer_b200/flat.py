@@ -9,8 +9,17 @@ ALIGN = 4  # floats
 
 
 class FlatPack:
-    def __init__(self, tensors, device, with_grad=True):
-        """tensors: ordered list of (name, torch.Tensor or nn.Parameter, start alignment in floats)."""
+    @staticmethod
+    def size_of(tensors):
+        off = 0
+        for _, t, align in tensors:
+            off = (off + align - 1) // align * align + t.numel()
+        return (max(off, 1) + ALIGN - 1) // ALIGN * ALIGN
+
+    def __init__(self, tensors, device, with_grad=True, flat_storage=None, grad_storage=None):
+        """tensors: ordered list of (name, torch.Tensor or nn.Parameter, start alignment in floats).  flat_storage /
+        grad_storage: optional pre-allocated fp32 buffers of ``size_of(tensors)`` elements to live in (so that several
+        packs can share one contiguous communication buffer)."""
         self.names, self.offsets, self.shapes = [], [], []
         off = 0
         for name, t, align in tensors:
@@ -20,8 +29,11 @@ class FlatPack:
             self.shapes.append(tuple(t.shape))
             off += t.numel()
         self.numel = (max(off, 1) + ALIGN - 1) // ALIGN * ALIGN
-        self.flat = torch.zeros(self.numel, device=device, dtype=torch.float32)
-        self.grad = torch.zeros(self.numel, device=device, dtype=torch.float32) if with_grad else None
+        self.flat = flat_storage if flat_storage is not None else torch.zeros(self.numel, device=device, dtype=torch.float32)
+        self.grad = None
+        if with_grad:
+            self.grad = grad_storage if grad_storage is not None else torch.zeros(self.numel, device=device, dtype=torch.float32)
+        assert self.flat.numel() == self.numel and (self.grad is None or self.grad.numel() == self.numel)
         self._tensors = [t for _, t, _ in tensors]
         for t, o, s in zip(self._tensors, self.offsets, self.shapes):
             n = 1

@@ -136,8 +136,12 @@ class DKT(MetaTemplate):
         bn_out = getattr(self.feature.trunk, "bn_out", None)
         bufs = [("gp.raw_noise.%d" % c, ms[c].likelihood.noise_covar.raw_noise, 1) for c in range(C)]
         bufs += [("bb." + n, b_, 4) for n, b_ in self.feature.named_buffers() if b_.is_floating_point()]
-        self._pack = FlatPack(train, dev)
-        self._bufs = FlatPack(bufs, dev, with_grad=False)
+        # ONE communication buffer [gradients | BatchNorm running statistics + fixed noise]: under torch.distributed a
+        # single all-reduce per meta-step covers both (the collective is latency-bound at 0.47 MB)
+        n_train, n_bufs = FlatPack.size_of(train), FlatPack.size_of(bufs)
+        self._comm = torch.zeros(n_train + n_bufs, device=dev, dtype=torch.float32)
+        self._pack = FlatPack(train, dev, grad_storage=self._comm[:n_train])
+        self._bufs = FlatPack(bufs, dev, with_grad=False, flat_storage=self._comm[n_train:])
         gp_end = self._pack.offsets[self._gp_count]
         self._gp_range = (0, gp_end)
         self._bb_range = (gp_end, self._pack.numel)
@@ -284,9 +288,10 @@ class DKT(MetaTemplate):
             gfeat = head.backward(feats, zh, self._HP, self._GH, E, N)
         with _Range("dkt.backbone_bwd", nv):
             self._bb_backward(eng, x_all, gfeat, N)
-        if world > 1:
-            with _Range("dkt.allreduce_grad", nv):
-                dist.all_reduce(self._pack.grad)
+        if world > 1:      # gradients (summed; Adam divides by world) and running statistics (averaged below) in one collective
+            with _Range("dkt.allreduce", nv):
+                dist.all_reduce(self._comm)
+            lib.scale(self._bufs.flat, self._bufs.numel, 1.0 / world, st)
         ad = self._adam
         ad["step"] += 1
         lib.counter_add(ad["step_dev"], 1, st)        # the step count lives on the device (CUDA-graph replay)
@@ -297,9 +302,6 @@ class DKT(MetaTemplate):
                               ad["step_dev"], 1.0 / world, st)
         lib.adam_step_dev(fl[b0:b1], gr[b0:b1], ad["m"][b0:b1], ad["v"][b0:b1], b1 - b0, ad["lr_bb"], 0.9, 0.999, 1e-8,
                           ad["step_dev"], 1.0 / world, st)
-        if world > 1:      # keep replicas identical: average the BatchNorm running statistics
-            dist.all_reduce(self._bufs.flat)
-            lib.scale(self._bufs.flat, self._bufs.numel, 1.0 / world, st)
         for m_ in self.feature.modules():
             if isinstance(m_, (nn.BatchNorm2d, nn.BatchNorm1d)):
                 m_.num_batches_tracked += E
@@ -571,7 +573,17 @@ class DKT(MetaTemplate):
         pend = []
 
         def run(batch):
-            xs = torch.stack(batch, 0)
+            # stack into a pinned staging buffer (one H2D per pack at the host link's rate instead of a pageable copy);
+            # correct_packed ends with a host sync, so the buffer is free again when the next pack is staged
+            shape = (E,) + tuple(batch[0].shape)
+            stage = self.__dict__.get("_test_stage")
+            if stage is None or tuple(stage.shape) != shape:
+                stage = torch.empty(shape, dtype=torch.float32)
+                if self._device().type == "cuda":
+                    stage = stage.pin_memory()
+                self._test_stage = stage
+            xs = stage[:len(batch)]
+            torch.stack([b.float() for b in batch], 0, out=xs)
             hits = self.correct_packed(xs)
             count_this = xs.size(1) * (xs.size(2) - self.n_support)
             return [float(h) / count_this * 100 for h in hits.tolist()]
