@@ -33,9 +33,9 @@ CONFIGS = {
                           "Adam step (the reference's own granularity), step replayed from a CUDA graph"),
     "cfg4": dict(arch="ResNet18", kernel="rbf", n_way=5, n_support=5, n_query=16, image=224, feat=512, E=4, graph=False,
                  workload="5-way 5-shot ResNet18 RBF, synthetic 224x224x3, meta-train step incl. monitoring"),
-    "cfg5-e2e": dict(arch="ResNet50", kernel="rbf", n_way=20, n_support=5, n_query=16, image=224, feat=2048, E=1, graph=False,
-                     workload="20-way 5-shot ResNet50 RBF, synthetic 224x224x3 (N = 420 exact-GP systems), meta-train step "
-                              "incl. monitoring"),
+    "cfg5-e2e": dict(arch="ResNet50", kernel="bncossim", n_way=20, n_support=5, n_query=16, image=224, feat=2048, E=1, graph=False,
+                     workload="20-way 5-shot ResNet50 bncossim (the reference's default kernel), synthetic 224x224x3 (N = 420 "
+                              "exact-GP systems), meta-train step incl. monitoring"),
 }
 CFG = CONFIGS["cfg3"]
 N_WAY, N_SUPPORT, N_QUERY, IMAGE = 5, 5, 16, 84
@@ -650,9 +650,8 @@ def run_gp_sweep(args):
         torch.set_num_threads(os.cpu_count() or 1)
         N = 420
         z = torch.randn(N, D).requires_grad_(True)
-        p = ogp.default_gp_params("rbf", C, D)
-        p["raw_lengthscale"] = torch.full((C,), float(D) ** 0.5)
-        for k in ogp.trainable_gp_names("rbf"):
+        p = ogp.default_gp_params("bncossim", C, D)
+        for k in ogp.trainable_gp_names("bncossim"):
             p[k].requires_grad_(True)
         tg = -torch.ones(C, N)
         for c in range(C):
@@ -660,15 +659,16 @@ def run_gp_sweep(args):
         ts = []
         for i in range(max(1, min(args.steps, 3)) + 1):
             t0 = time.perf_counter()
-            ogp.mll_loss("rbf", z, tg, p).backward()
+            zn = torch.nn.functional.normalize(torch.nn.functional.batch_norm(z, None, None, training=True), dim=1)
+            ogp.mll_loss("bncossim", zn, tg, p).backward()
             ts.append(time.perf_counter() - t0)
         med = sorted(ts[1:])[len(ts[1:]) // 2]
         cb = {"value": 1.0 / med, "unit": "episodes/s", "cores": os.cpu_count(), "kind": "port",
-              "sample": "one N = 420, C = 20, D = 2048 RBF episode (-mll forward + backward) per step, median of %d" % (len(ts) - 1)}
+              "sample": "one N = 420, C = 20, D = 2048 bncossim episode (bn_out, normalise, -mll forward + backward) per step, median of %d" % (len(ts) - 1)}
         print(json.dumps({"metric": "episodes/sec (exact-GP head only, N = 420)", "value": cb["value"], "unit": "episodes/s",
                           "n_gpus": args.gpus, "steps": len(ts) - 1, "warmup": 1, "ms_per_step": med * 1e3,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "impl": "reference", "config": {"workload": "GP-only, N = 420, C = 20, D = 2048, RBF", "bench_config": "cfg5-sweep"},
+                          "impl": "reference", "config": {"workload": "GP-only, N = 420, C = 20, D = 2048, bncossim", "bench_config": "cfg5-sweep"},
                           "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "episodes/s", "h2d_bytes_per_step": 0,
                                                       "d2h_bytes_per_step": 0}}))
         return
@@ -682,8 +682,11 @@ def run_gp_sweep(args):
     HP, GH = GPHeadParams(), GPHeadParams()
     HP.raw_outputscale, HP.constant = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
     HP.raw_noise = torch.full((C,), -2.2532, device=dev)
-    HP.raw_param = torch.full((C,), float(D) ** 0.5, device=dev)
-    GH.raw_outputscale, GH.constant, GH.raw_param = (torch.zeros(C, device=dev) for _ in range(3))
+    GH.raw_outputscale, GH.constant = (torch.zeros(C, device=dev) for _ in range(2))
+    # bncossim (configs.kernel_type default): bn_out over the D features + F.normalize + linear kernel (variance 1)
+    HP.bn_w, HP.bn_b = torch.ones(D, device=dev), torch.zeros(D, device=dev)
+    HP.bn_rm, HP.bn_rv = torch.zeros(D, device=dev), torch.ones(D, device=dev)
+    GH.bn_w, GH.bn_b = torch.zeros(D, device=dev), torch.zeros(D, device=dev)
     sweep = []
     result = {}
 
@@ -694,16 +697,19 @@ def run_gp_sweep(args):
     sizes = (25, 50, 100, 105, 180, 250, 420, 500)
     for N in sizes:
         per = max(1, N // C)
-        head = GPHead(lib, "rbf", C, D, D, 1, dev)
+        head = GPHead(lib, "bncossim", C, D, D, 1, dev)
         head.ensure(E, N)
         z = torch.randn(E, N, D, device=dev, generator=torch.Generator(device=dev).manual_seed(rank * 100 + N))
         tg = -torch.ones(C, N, device=dev)
         for c in range(C):
             tg[c, c * per:(c + 1) * per] = 1.0
 
-        def step():
-            head.fit(z, tg, HP, E, N, want_grad=True, grad_scale=1.0 / E)
-            head.backward(z.view(E * N, D), z, HP, GH, E, N)
+        def step(zz=None):
+            f = z if zz is None else zz
+            zh = head.embed(f.view(E * N, D), HP, E, N, training=True, out=head.w["zh_train"])
+            loss = head.fit(zh, tg, HP, E, N, want_grad=True, grad_scale=1.0 / E)
+            head.backward(f.view(E * N, D), zh, HP, GH, E, N)
+            return loss
         for _ in range(W):
             step()
         barrier()
@@ -733,9 +739,7 @@ def run_gp_sweep(args):
             a0.record()
             for _ in range(K):
                 zb.copy_(host, non_blocking=True)
-                loss = head.fit(zb, tg, HP, E, N, want_grad=True, grad_scale=1.0 / E)
-                head.backward(zb.view(E * N, D), zb, HP, GH, E, N)
-                float(loss.sum())
+                float(step(zb).sum())
             a1.record()
             barrier()
             t2 = torch.tensor([a0.elapsed_time(a1)], device=dev, dtype=torch.float64)
@@ -746,7 +750,7 @@ def run_gp_sweep(args):
             need = lib.gp_large_work_floats(E, C, N)
             work = torch.empty(need, device=dev)
             st = torch.cuda.current_stream(dev).cuda_stream
-            ms_fit = _time_launch(lambda: lib.gp_fit_large(w["kb"], N * N, tg, 0, HP.raw_outputscale, HP.constant, HP.raw_noise,
+            ms_fit = _time_launch(lambda: lib.gp_fit_large(w["gram"], 0, tg, 0, HP.raw_outputscale, HP.constant, HP.raw_noise,
                                                            w["alpha"], None, w["loss_terms"], w["info"], w["dk"], w["dhyper"],
                                                            work, 1.0 / E, 1e-6, E, C, N, st))
             result = {"ms": ms, "launches": launches, "eps": eps, "ms_e2e": float(t2[0]), "h2d": host.numel() * 4,
@@ -764,10 +768,11 @@ def run_gp_sweep(args):
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": result["ms"] / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "BASELINE configs[4]: GP-only sweep on pre-extracted features Z~N(0,1) [E,N,2048], 20 classes, "
-                                   "RBF kernel: sqdist -> kernel -> C x (Cholesky, alpha, logdet, K^-1, dK) -> dZ; value at N = 420",
+                                   "bncossim (reference default): bn_out -> normalise -> Gram -> C x (Cholesky, alpha, logdet, K^-1, dK) -> dZ -> "
+                                   "normalise / bn_out backward; value at N = 420",
                        "bench_config": "cfg5-sweep", "episodes_per_gpu_per_step": E, "classes": C, "D": D,
-                       "l2": "per step E*C = %d systems x 2 N^2 floats of workspace + kb/dk [E,C,N,N] = %.0f MB > 126 MB L2"
-                             % (E * C, E * C * 4 * N * N * 4 / 1e6)},
+                       "l2": "per step E*C = %d systems x 2 N^2 floats of workspace + dk [E,C,N,N] = %.0f MB > 126 MB L2"
+                             % (E * C, E * C * 3 * N * N * 4 / 1e6)},
             "gpu_launches": result["launches"], "tflops_algorithmic": result["eps"] * gp_flops(N, C, D) / 1e12,
             "sweep": sweep,
             "e2e": {"value": E * world * K / (result["ms_e2e"] / 1e3), "unit": "episodes/s",
@@ -784,19 +789,22 @@ def run_gp_sweep(args):
         from oracle import gp as ogp
         torch.set_num_threads(min(16, os.cpu_count() or 1))
         z1 = torch.randn(N, D).requires_grad_(True)
-        p = ogp.default_gp_params("rbf", C, D)
-        p["raw_lengthscale"] = torch.full((C,), float(D) ** 0.5)
-        for k in ogp.trainable_gp_names("rbf"):
+        p = ogp.default_gp_params("bncossim", C, D)
+        for k in ogp.trainable_gp_names("bncossim"):
             p[k].requires_grad_(True)
         tg1 = -torch.ones(C, N)
         for c in range(C):
             tg1[c, c * 21:(c + 1) * 21] = 1.0
-        ogp.mll_loss("rbf", z1, tg1, p).backward()
+
+        def cpu_step():
+            zn = torch.nn.functional.normalize(torch.nn.functional.batch_norm(z1, None, None, training=True), dim=1)
+            ogp.mll_loss("bncossim", zn, tg1, p).backward()
+        cpu_step()
         t0 = time.perf_counter()
-        ogp.mll_loss("rbf", z1, tg1, p).backward()
+        cpu_step()
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "episodes/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": "one N = 420, C = 20, D = 2048 RBF episode (-mll forward + backward) after one warm-up"}
+                                "sample": "one N = 420, C = 20, D = 2048 bncossim episode (bn_out, normalise, -mll forward + backward) after one warm-up"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

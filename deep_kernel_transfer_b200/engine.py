@@ -301,6 +301,18 @@ class GPHead:
         self.family = self.FAMILY.get(kernel)
         self.centred = kernel in ("rbf", "matern")
         self.key = None
+        # Gram / cross-kernel products on tcgen05 (csrc/gram_tc.cu) on a GPU; the FFMA kernel serves the emulation build
+        # and the shapes the tensor-core kernel does not take (fewer than 128 rows in total, D not a multiple of 4)
+        self.use_tc = self.dev.type == "cuda" and lib.has("dktb_gram_tc")
+        self.tc_err = torch.zeros(1, device=self.dev, dtype=torch.int32) if self.use_tc else None
+
+    def gram(self, x1, x2, out, E, M, N):
+        """out [E,M,N] = x1 [E,M,D] . x2 [E,N,D]^T"""
+        st = _stream(self.dev)
+        if self.use_tc and self.lib.gram_tc_ok(E, M, N, self.D):
+            self.lib.gram_tc(x1, x2, out, self.tc_err, E, M, N, self.D, st)
+        else:
+            self.lib.gram(x1, x2, out, E, M, N, self.D, st)
 
     def _alloc(self, E, N):
         dev, f32, C, D = self.dev, torch.float32, self.C, self.D
@@ -356,14 +368,14 @@ class GPHead:
         """Gram + C Cholesky systems per episode.  targets [C,N] (shared by all episodes)."""
         lib, st, w, C = self.lib, _stream(self.dev), self.w, self.C
         if self.family is None:
-            lib.gram(zh, zh, w["gram"], E, N, N, self.D, st)
+            self.gram(zh, zh, w["gram"], E, N, N)
             kb, stride = w["gram"], 0
         else:
             if self.centred:      # rbf / matern: direct squared distances (no Gram cancellation, exact zero diagonal)
                 lib.sqdist(zh, zh, w["d2"], E, N, N, self.D, st)
                 lib.kernel_fwd(self.family, None, w["d2"], HP.raw_param, w["kb"], E, C, N, N, st)
             else:
-                lib.gram(zh, zh, w["gram"], E, N, N, self.D, st)
+                self.gram(zh, zh, w["gram"], E, N, N)
                 lib.kernel_fwd(self.family, w["gram"], None, HP.raw_param, w["kb"], E, C, N, N, st)
             kb, stride = w["kb"], N * N
         # one CTA per system entirely in shared memory up to the BASELINE episode size (N = 105); beyond that the tiled
@@ -392,6 +404,9 @@ class GPHead:
         system needed jitter, raises when one stayed not positive definite (the reference raises at that step)."""
         hi, lo = self.w["info_sticky"].tolist()
         self.w["info_sticky"].zero_()
+        if self.use_tc and int(self.tc_err.item()) != 0:
+            self.tc_err.zero_()
+            raise RuntimeError("tcgen05 Gram pipeline reported a barrier time-out")
         report_info(hi, lo, what)
 
     def hyper_grads(self, HP, GH, E, N):
@@ -433,7 +448,7 @@ class GPHead:
         """Predictive mean [E,C,M] + class arg-max [E,M]; expects alpha of the current fit in the workspace."""
         lib, st = self.lib, _stream(self.dev)
         if self.family is None:
-            lib.gram(zh_test, zh_train, kx_buf, E, M, N, self.D, st)
+            self.gram(zh_test, zh_train, kx_buf, E, M, N)
             lib.gp_predict(kx_buf, 0, self.w["alpha"], HP.raw_outputscale, HP.constant, mean_out, pred_out, E, self.C,
                            M, N, st)
             return
@@ -446,7 +461,7 @@ class GPHead:
             lib.sqdist(zh_test, zh_train, kx_buf, E, M, N, self.D, st)
             lib.kernel_fwd(self.family, None, kx_buf, HP.raw_param, t["kx"], E, C, M, N, st)
         else:
-            lib.gram(zh_test, zh_train, kx_buf, E, M, N, self.D, st)
+            self.gram(zh_test, zh_train, kx_buf, E, M, N)
             lib.kernel_fwd(self.family, kx_buf, None, HP.raw_param, t["kx"], E, C, M, N, st)
         lib.gp_predict(t["kx"], M * N, self.w["alpha"], HP.raw_outputscale, HP.constant, mean_out, pred_out, E, C, M, N,
                        st)

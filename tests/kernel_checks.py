@@ -940,3 +940,22 @@ def check_conv_tcg(lib, dev, B=2, H=6, W=5, Cin=64, Cout=128, R=3, seed=100, rto
     _close(dw, wr.grad, rtol=rtol, atol=1e-5, what="conv_tcg wgrad %dx%d %d->%d" % (R, R, Cin, Cout))
     if bias:
         _close(db, br.grad, rtol=rtol, atol=1e-4, what="conv_tcg bias grad")
+
+
+def check_gram_tc(lib, dev, E=3, M=105, N=105, D=1600, seed=110, same=True):
+    """tcgen05 Gram / cross-kernel product against float64 (3xTF32: fp32-class accuracy), incl. ragged tiles."""
+    g = torch.Generator().manual_seed(seed)
+    x1 = torch.randn(E, M, D, generator=g)
+    x2 = x1 if same else torch.randn(E, N, D, generator=g)
+    assert lib.gram_tc_ok(E, M, N, D)
+    a = x1.to(dev)
+    b = a if same else x2.to(dev)
+    out = torch.full((E, M, N), 7.0, device=dev)
+    err = torch.zeros(1, device=dev, dtype=torch.int32)
+    lib.gram_tc(a, b, out, err, E, M, N, D, 0)
+    assert int(err) == 0
+    ref = x1.double() @ x2.double().transpose(1, 2)
+    _close(out, ref, rtol=2e-6, atol=1e-6 * D ** 0.5, what="gram_tc %dx%dx%d" % (M, N, D))
+    if same:
+        o = out.cpu()
+        assert float((o - o.transpose(1, 2)).abs().max()) <= 1e-5 * float(o.abs().max())
