@@ -163,10 +163,16 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
           tc::tcgen05_fence_after();
           const uint32_t acol = a_tmem + sa * 64;             // hi [0,32) | lo [32,64): channel 32 h + c at column c
           if (tc::elect_one()) {
+            // the four N = 128 instructions first, then the four N = 64 ones: alternating the two instruction shapes
+            // costs a re-configuration bubble per switch (8 switches per stage instead of 2)
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t w_cat = tc::umma_desc_sw128(wbase + h * 16384 + k * 32, 16, 1024);
               tc::umma_tf32_ts(d_tmem, acol + k * 8, w_cat, idesc, (tap | h | k) ? 1u : 0u);   // a_hi * [w_hi | w_lo]
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t w_cat = tc::umma_desc_sw128(wbase + h * 16384 + k * 32, 16, 1024);
               tc::umma_tf32_ts(d_tmem, acol + 32 + k * 8, w_cat, idesc_lo, 1u);                 // a_lo * w_hi (| w_lo)
             }
             tc::umma_commit(&bar_aempty[sa]);

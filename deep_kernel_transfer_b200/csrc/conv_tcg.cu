@@ -152,9 +152,13 @@ conv_tcg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const uint32_t acol = a_tmem + sa * 64;             // hi [0,32) | lo [32,64)
             if (tc::elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
+              for (int k = 0; k < 4; ++k) {       // the N = 128 instructions first, then the N = 64 ones (see conv_tc.cu)
                 const uint64_t w_cat = tc::umma_desc_sw128(wbase + h * 16384 + k * 32, 16, 1024);
                 tc::umma_tf32_ts(d_tmem, acol + k * 8, w_cat, idesc, (kk | h | k) ? 1u : 0u);      // a_hi * [w_hi | w_lo]
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t w_cat = tc::umma_desc_sw128(wbase + h * 16384 + k * 32, 16, 1024);
                 tc::umma_tf32_ts(d_tmem, acol + 32 + k * 8, w_cat, idesc_lo, 1u);                    // a_lo * w_hi
               }
               tc::umma_commit(&bar_aempty[sa]);
