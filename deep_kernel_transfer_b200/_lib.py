@@ -55,7 +55,8 @@ SIGNATURES = {
     "dktb_l2norm_bwd": ("pppplis", ctypes.c_int),
     "dktb_gram": ("pppiiiis", ctypes.c_int),
     "dktb_gram_tc_ok": ("iiii", ctypes.c_int),
-    "dktb_gram_tc": ("ppppiiiis", ctypes.c_int),
+    "dktb_gram_tc_scratch_floats": ("iiii", ctypes.c_long),
+    "dktb_gram_tc": ("pppppiiiis", ctypes.c_int),
     "dktb_gp_max_n": ("", ctypes.c_int),
     "dktb_gp_fit": ("plplpppppppppffiiis", ctypes.c_int),
     "dktb_gp_large_max_n": ("", ctypes.c_int),

@@ -310,7 +310,10 @@ class GPHead:
         """out [E,M,N] = x1 [E,M,D] . x2 [E,N,D]^T"""
         st = _stream(self.dev)
         if self.use_tc and self.lib.gram_tc_ok(E, M, N, self.D):
-            self.lib.gram_tc(x1, x2, out, self.tc_err, E, M, N, self.D, st)
+            need = self.lib.gram_tc_scratch_floats(E, M, N, self.D)
+            if getattr(self, "_gram_scratch", None) is None or self._gram_scratch.numel() < need:
+                self._gram_scratch = torch.empty(need, device=self.dev)
+            self.lib.gram_tc(x1, x2, out, self._gram_scratch, self.tc_err, E, M, N, self.D, st)
         else:
             self.lib.gram(x1, x2, out, E, M, N, self.D, st)
 

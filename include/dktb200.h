@@ -199,7 +199,9 @@ int dktb_gram(const float* x1, const float* x2, float* out, int E, int M, int N,
 /* the same product on tcgen05 / TMA (128 x 128 tiles, 3xTF32 error-compensated, fp32 accumulation in TMEM) for the
  * shapes dktb_gram_tc_ok accepts (D % 4 == 0, D >= 32, at least 128 rows per operand tensor); err as dktb_conv3x3_tc_fwd */
 int dktb_gram_tc_ok(int E, int M, int N, int D);
-int dktb_gram_tc(const float* x1, const float* x2, float* out, int* err, int E, int M, int N, int D, cudaStream_t stream);
+long dktb_gram_tc_scratch_floats(int E, int M, int N, int D);      /* split-K partials, one per 64 features */
+int dktb_gram_tc(const float* x1, const float* x2, float* out, float* scratch, int* err, int E, int M, int N, int D,
+                 cudaStream_t stream);
 /* per (episode, class): K~ = softplus(raw_outputscale_c)*Kb + (softplus(raw_noise_c)+1e-4) I -> Cholesky ->
  * alpha_c = K~^-1 (y_c - constant_c), loss_terms[e][c] = -log p_c/(N*C).
  * Cholesky follows GPyTorch's psd_safe_cholesky (utils/cholesky.py; the reference relies on it, README.md:27,

@@ -952,7 +952,8 @@ def check_gram_tc(lib, dev, E=3, M=105, N=105, D=1600, seed=110, same=True):
     b = a if same else x2.to(dev)
     out = torch.full((E, M, N), 7.0, device=dev)
     err = torch.zeros(1, device=dev, dtype=torch.int32)
-    lib.gram_tc(a, b, out, err, E, M, N, D, 0)
+    scratch = torch.empty(lib.gram_tc_scratch_floats(E, M, N, D), device=dev)
+    lib.gram_tc(a, b, out, scratch, err, E, M, N, D, 0)
     assert int(err) == 0
     ref = x1.double() @ x2.double().transpose(1, 2)
     _close(out, ref, rtol=2e-6, atol=1e-6 * D ** 0.5, what="gram_tc %dx%dx%d" % (M, N, D))
