@@ -139,7 +139,7 @@ def test_conv_tcg(lib, cfg):
 
 @pytest.mark.parametrize("cfg", [dict(), dict(E=2, M=420, N=420, D=2048, seed=111), dict(E=4, M=85, N=85, D=1600, seed=112),
                                  dict(E=2, M=75, N=105, D=1600, same=False, seed=113),         # prediction: queries x train
-                                 dict(E=1, M=300, N=100, D=512, same=False, seed=114),
+                                 dict(E=2, M=300, N=100, D=512, same=False, seed=114),
                                  dict(E=40, M=5, N=5, D=64, seed=115), dict(E=8, M=20, N=20, D=40, seed=116)])
 def test_gram_tc(lib, cfg):
     kc.check_gram_tc(lib, DEV, **cfg)
