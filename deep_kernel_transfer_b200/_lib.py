@@ -30,6 +30,7 @@ SIGNATURES = {
     "dktb_conv3x3_wgrad_scratch_floats": ("", ctypes.c_long),
     "dktb_conv3x3_wgrad": ("pppppiiis", ctypes.c_int),
     "dktb_prep_weights_tc": ("ppps", ctypes.c_int),
+    "dktb_conv3x3_tc_weight_floats": ("", ctypes.c_long),
     "dktb_prep_weights_conv1_tc": ("pps", ctypes.c_int),
     "dktb_conv1_tc": ("pppppppppppiiiiis", ctypes.c_int),
     "dktb_conv3x3_tc_fwd": ("ppppppiiis", ctypes.c_int),

@@ -12,6 +12,7 @@
 
 #ifndef DKTB_EMU
 #include <stdlib.h>
+#include <cuda_bf16.h>
 #include "tc_common.cuh"
 
 namespace {
@@ -34,6 +35,14 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
   lo = __float_as_uint(v - __uint_as_float(hi));
 #endif
 }
+// two neighbouring channels: tf32 hi parts + the two remainders packed as bf16 (low half = the first channel) for the
+// kind::f16 small-term instruction
+__device__ __forceinline__ void split_tf32_bf16(float v0, float v1, uint32_t& hi0, uint32_t& hi1, uint32_t& lo_pair) {
+  hi0 = (__float_as_uint(v0) + 0x1000u) & 0xFFFFE000u;
+  hi1 = (__float_as_uint(v1) + 0x1000u) & 0xFFFFE000u;
+  const float l0 = v0 - __uint_as_float(hi0), l1 = v1 - __uint_as_float(hi1);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo_pair) : "f"(l1), "f"(l0));      // {upper, lower} = {l1, l0}
+}
 __device__ __forceinline__ void split_tf32_exact(float v, uint32_t& hi, uint32_t& lo) {      // weights (prepared once)
   hi = (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u;
   lo = (__float_as_uint(v - __uint_as_float(hi)) + 0x1000u) & 0xFFFFE000u;
@@ -50,8 +59,9 @@ __device__ __forceinline__ void split_tf32_exact(float v, uint32_t& hi, uint32_t
 //   warps 10-13 epilogue: tcgen05.ld accumulator -> +bias -> global store; BatchNorm partial sums by warp shuffles
 // TMEM (512 columns): accumulators [0,128), A stages [128, 512).
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kP_WStages = 3;                 // full-tap weight stages: [half 0 | half 1] x [w_hi | w_lo] = 32 KB
-constexpr int kP_WStageBytes = 32768;
+constexpr int kP_WStages = 4;                 // half-tap weight slots: [w_hi | w_lo] x 32 channels (tf32, 16 KB) and -- in the
+constexpr int kP_WStageBytes = 24576;         // slot of channel half 0 -- the whole tap's w_hi in bf16 (64 x 64, 8 KB)
+constexpr int kP_WFloats = 9 * 2 * 64 * 64;   // tf32 part of a prepared weight tensor; the bf16 part follows
 constexpr int kP_AStages = 4;                 // half-tap A stages (32 channels): {hi 32 | lo 32} columns each; a ring of
                                               // four gives a stage three MMA groups of slack before it is needed again
 constexpr int kP_Taps = 9;
@@ -59,7 +69,7 @@ constexpr int kP_Threads = 64 + 256 + 128;
 
 __global__ void __launch_bounds__(kP_Threads, 1)
 conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                             const float* __restrict__ bias, float* __restrict__ out, float* __restrict__ partials,
+                             const __grid_constant__ CUtensorMap map_wb, const float* __restrict__ bias, float* __restrict__ out, float* __restrict__ partials,
                              int B, int H, int W, int halo_rows_pad, int tiles_per_img, int lo_n64,
                              int* __restrict__ err) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -74,7 +84,7 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
   const int Hp = H + 2, Wp = W + 2;
   const int half_bytes = halo_rows_pad * 128;
   unsigned char* s_halo = smem;                               // [2 buffers][2 halves][halo_rows_pad][128 B]
-  unsigned char* s_w = smem + 4 * half_bytes;                 // [kP_WStages][32 KB]
+  unsigned char* s_w = smem + 4 * half_bytes;                 // [kP_WStages][24 KB]
   const long ntiles = (long)B * tiles_per_img;
 
   if (tid == 0) {
@@ -89,7 +99,7 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
     s_err = 0;
     tc::fence_barrier_init();
   }
-  if (warp == 0 && lane == 0) { tc::prefetch_tmap(&map_a); tc::prefetch_tmap(&map_w); }
+  if (warp == 0 && lane == 0) { tc::prefetch_tmap(&map_a); tc::prefetch_tmap(&map_w); tc::prefetch_tmap(&map_wb); }
   if (warp == 1) tc::tmem_alloc<512>(&s_tmem);
   tc::tcgen05_fence_before();
   __syncthreads();
@@ -120,16 +130,19 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
     };
     if (blockIdx.x < ntiles) ok = load_halo(blockIdx.x, 0);
     for (long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x, ++t) {
-      for (int tap = 0; tap < kP_Taps && ok; ++tap, ++wi) {
-        const int s = (int)(wi % kP_WStages), ph = (int)((wi / kP_WStages) & 1);
-        ok = tc::mbar_wait(&bar_wempty[s], ph ^ 1);
-        if (!ok) break;
-        if (tc::elect_one()) {
-          tc::mbar_expect_tx(&bar_wfull[s], kP_WStageBytes);
-          tc::tma_load_2d(s_w + s * kP_WStageBytes, &map_w, &bar_wfull[s], 0, tap * 128);
-          tc::tma_load_2d(s_w + s * kP_WStageBytes + 16384, &map_w, &bar_wfull[s], 32, tap * 128);
+      for (int tap = 0; tap < kP_Taps && ok; ++tap) {
+        for (int h = 0; h < 2 && ok; ++h, ++wi) {                 // wi counts half-tap weight slots
+          const int s = (int)(wi % kP_WStages), ph = (int)((wi / kP_WStages) & 1);
+          ok = tc::mbar_wait(&bar_wempty[s], ph ^ 1);
+          if (!ok) break;
+          if (tc::elect_one()) {
+            unsigned char* slot = s_w + s * kP_WStageBytes;
+            tc::mbar_expect_tx(&bar_wfull[s], h == 0 ? 16384 + 8192 : 16384);
+            tc::tma_load_2d(slot, &map_w, &bar_wfull[s], h * 32, tap * 128);                // [w_hi | w_lo] x 32 channels
+            if (h == 0) tc::tma_load_2d(slot + 16384, &map_wb, &bar_wfull[s], 0, tap * 64);  // bf16 w_hi, all 64 channels
+          }
+          __syncwarp();
         }
-        __syncwarp();
         if (tap == 1 && tile + gridDim.x < ntiles) ok = load_halo(tile + gridDim.x, t + 1);
       }
     }
@@ -137,11 +150,13 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer: 16 x (M128, N128, K8) per tap
     const uint32_t idesc = tc::umma_idesc(2, 128, 128, 0, 0);
-    // 3xTF32 needs a_hi*w_hi + a_hi*w_lo + a_lo*w_hi: the a_lo pass only has to cover the w_hi half of the stacked
-    // operand (N = 64, ~50 instead of ~65 issue cycles); lo_n64 == 0 keeps the symmetric N = 128 form (adds a_lo*w_lo)
-    const uint32_t idesc_lo = (lo_n64 & 1) ? tc::umma_idesc(2, 128, 64, 0, 0) : idesc;
+    // 3xTF32 needs a_hi*w_hi + a_hi*w_lo + a_lo*w_hi.  The first two are ONE tf32 instruction per 8 channels on the stacked
+    // operand [w_hi | w_lo] (N = 128).  The third is small (|a_lo| <= 2^-11 |a|): it runs as kind::f16 on bf16 copies of
+    // a_lo and w_hi, K = 16 channels per instruction (N = 64) -- half the instructions of the tf32 form at the same issue
+    // cost; its rounding (2^-9 of a term that is 2^-11 of the product) stays at 2^-20 of the result.
+    const uint32_t idesc_lo = tc::umma_idesc(1, 128, 64, 0, 0);
     int t = 0;
-    long wi = 0;
+    long wi = 0;                                               // half-tap counter (weight slots and A stages)
     bool ok = true;
     for (long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x, ++t) {
       const int ab = t & 1, ap = (t >> 1) & 1;
@@ -149,34 +164,36 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
       if (!ok) break;
       tc::tcgen05_fence_after();
       const uint32_t d_tmem = tmem + ab * 128;
-      for (int tap = 0; tap < kP_Taps && ok; ++tap, ++wi) {
-        const int sw = (int)(wi % kP_WStages), pw = (int)((wi / kP_WStages) & 1);
-        const int pa = (int)((wi >> 1) & 1);
-        ok = tc::mbar_wait(&bar_wfull[sw], pw);
-        if (!ok) break;
-        const uint32_t wbase = tc::smem_u32(s_w + sw * kP_WStageBytes);
+      for (int tap = 0; tap < kP_Taps && ok; ++tap) {
+        int sw0 = 0;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {                         // channel halves: separately staged, separately released
-          const int sa = (int)((wi & 1) << 1) | h;
+        for (int h = 0; h < 2; ++h, ++wi) {                     // channel halves: separately staged, separately released
+          const int sw = (int)(wi % kP_WStages), pw = (int)((wi / kP_WStages) & 1);
+          if (h == 0) sw0 = sw;
+          ok = tc::mbar_wait(&bar_wfull[sw], pw);
+          if (!ok) break;
+          const uint32_t wbase = tc::smem_u32(s_w + sw * kP_WStageBytes);
+          const uint32_t wb16 = tc::smem_u32(s_w + sw0 * kP_WStageBytes + 16384);     // the tap's bf16 w_hi (slot of half 0)
+          const int sa = (int)(wi & 3), pa = (int)((wi >> 2) & 1);
           ok = tc::mbar_wait(&bar_afull[sa], pa);
           if (!ok) break;
           tc::tcgen05_fence_after();
-          const uint32_t acol = a_tmem + sa * 64;             // hi [0,32) | lo [32,64): channel 32 h + c at column c
+          const uint32_t acol = a_tmem + sa * 64;             // a_hi tf32 [0,32) | a_lo bf16 pairs [32,48)
           if (tc::elect_one()) {
-            // the four N = 128 instructions first, then the four N = 64 ones: alternating the two instruction shapes
-            // costs a re-configuration bubble per switch (8 switches per stage instead of 2)
+            // the four N = 128 tf32 instructions first, then the two N = 64 bf16 ones (switching shapes costs a bubble)
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const uint64_t w_cat = tc::umma_desc_sw128(wbase + h * 16384 + k * 32, 16, 1024);
+              const uint64_t w_cat = tc::umma_desc_sw128(wbase + k * 32, 16, 1024);
               tc::umma_tf32_ts(d_tmem, acol + k * 8, w_cat, idesc, (tap | h | k) ? 1u : 0u);   // a_hi * [w_hi | w_lo]
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t w_cat = tc::umma_desc_sw128(wbase + h * 16384 + k * 32, 16, 1024);
-              tc::umma_tf32_ts(d_tmem, acol + 32 + k * 8, w_cat, idesc_lo, 1u);                 // a_lo * w_hi (| w_lo)
+            for (int k = 0; k < 2; ++k) {
+              const uint64_t w16 = tc::umma_desc_sw128(wb16 + (h * 2 + k) * 32, 16, 1024);
+              tc::umma_f16_ts(d_tmem, acol + 32 + k * 8, w16, idesc_lo, 1u);                   // a_lo * w_hi (bf16, K = 16)
             }
             tc::umma_commit(&bar_aempty[sa]);
             if (h == 1) {
+              tc::umma_commit(&bar_wempty[sw0]);             // half 0's slot also held the bf16 tile used until here
               tc::umma_commit(&bar_wempty[sw]);
               if (tap == kP_Taps - 1) tc::umma_commit(&bar_accfull[ab]);
             }
@@ -204,14 +221,12 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
         const int sa = (int)((wi & 1) << 1) | set, pa = (int)((wi >> 1) & 1);      // this channel half's own stage ring
         const int row = r + (tap / 3) * Wp + (tap % 3);
         const unsigned char* src = s_halo + (hb * 2 + set) * half_bytes + row * 128;
-        uint32_t hi[32], lo[32];
+        uint32_t hi[32], lo[16];                       // lo: bf16 pairs (low half = even channel), 16 columns
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 v = *reinterpret_cast<const float4*>(src + ((j ^ (row & 7)) << 4));
-          split_tf32(v.x, hi[4 * j + 0], lo[4 * j + 0]);
-          split_tf32(v.y, hi[4 * j + 1], lo[4 * j + 1]);
-          split_tf32(v.z, hi[4 * j + 2], lo[4 * j + 2]);
-          split_tf32(v.w, hi[4 * j + 3], lo[4 * j + 3]);
+          split_tf32_bf16(v.x, v.y, hi[4 * j + 0], hi[4 * j + 1], lo[2 * j + 0]);
+          split_tf32_bf16(v.z, v.w, hi[4 * j + 2], hi[4 * j + 3], lo[2 * j + 1]);
         }
         ok = tc::mbar_wait(&bar_aempty[sa], pa ^ 1);
         if (!ok) break;
@@ -220,7 +235,6 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
         tc::tmem_st16(dst, hi);
         tc::tmem_st16(dst + 16, hi + 16);
         tc::tmem_st16(dst + 32, lo);
-        tc::tmem_st16(dst + 48, lo + 16);
         tc::tmem_st_wait();
         tc::tcgen05_fence_before();
         tc::mbar_arrive(&bar_afull[sa]);
@@ -761,17 +775,23 @@ __global__ void prep_weights_tc_kernel(const float* __restrict__ w, float* __res
   const int tap = i % 9, ci = (i / 9) % 64, co = i / (9 * 64);
   const float v = w[i];
   const float hi = tc::to_tf32_rna(v), lo = tc::to_tf32_rna(v - hi);
+  const unsigned short hb = __bfloat16_as_ushort(__float2bfloat16_rn(hi));      // bf16 copy of w_hi for the small term
   if (wb_fwd) {
     wb_fwd[((tap * 2 + 0) * 64 + co) * 64 + ci] = hi;
     wb_fwd[((tap * 2 + 1) * 64 + co) * 64 + ci] = lo;
+    reinterpret_cast<unsigned short*>(wb_fwd + kP_WFloats)[(tap * 64 + co) * 64 + ci] = hb;
   }
   if (wb_dgrad) {
     wb_dgrad[(((8 - tap) * 2 + 0) * 64 + ci) * 64 + co] = hi;
     wb_dgrad[(((8 - tap) * 2 + 1) * 64 + ci) * 64 + co] = lo;
+    reinterpret_cast<unsigned short*>(wb_dgrad + kP_WFloats)[((8 - tap) * 64 + ci) * 64 + co] = hb;
   }
 }
 
 }  // namespace
+
+// floats per prepared weight tensor: [9][hi | lo][64][64] tf32 + [9][64][64] bf16 (w_hi)
+DKTB_EXPORT long dktb_conv3x3_tc_weight_floats(void) { return (long)kP_WFloats + 9 * 64 * 64 / 2; }
 
 DKTB_EXPORT int dktb_prep_weights_tc(const float* w, float* wb_fwd, float* wb_dgrad, cudaStream_t stream) {
   DKTB_CHECK_ARG(w != nullptr);
@@ -793,9 +813,10 @@ DKTB_EXPORT int dktb_conv3x3_tc_fwd(const float* a, const float* wb, const float
   const int halo_pad = (halo + kHaloBox - 1) / kHaloBox * kHaloBox;
   const int smem = 4 * halo_pad * 128 + kP_WStages * kP_WStageBytes + 1024;
   DKTB_CHECK_ARG(smem <= 227 * 1024);
-  CUtensorMap map_a, map_w;
+  CUtensorMap map_a, map_w, map_wb;
   if (tc_make_tmap_2d(&map_a, a, 64, (uint64_t)rows, 32, kHaloBox) != 0) return DKTB_BAD_ARG - 1;
   if (tc_make_tmap_2d(&map_w, wb, 64, 2 * 9 * 64, 32, 128) != 0) return DKTB_BAD_ARG - 1;
+  if (tc_make_tmap_2d_bf16(&map_wb, wb + kP_WFloats, 64, 9 * 64, 64, 64) != 0) return DKTB_BAD_ARG - 1;
   cudaFuncSetAttribute(conv3x3_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int span = Hp * Wp - 2 * (Wp + 1);
   const int tiles_per_img = (span + kRows - 1) / kRows;
@@ -805,8 +826,8 @@ DKTB_EXPORT int dktb_conv3x3_tc_fwd(const float* a, const float* wb, const float
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = (int)(ntiles < sms ? ntiles : sms);
   const int lo_n64 = 1;      // the a_lo pass covers only the w_hi half of the stacked operand (N = 64)
-  conv3x3_tc_persistent_kernel<<<grid, kP_Threads, smem, stream>>>(map_a, map_w, bias, out, partials, B, H, W, halo_pad,
-                                                                   tiles_per_img, lo_n64, err);
+  conv3x3_tc_persistent_kernel<<<grid, kP_Threads, smem, stream>>>(map_a, map_w, map_wb, bias, out, partials, B, H, W,
+                                                                   halo_pad, tiles_per_img, lo_n64, err);
   return dktb_launch_status();
 }
 

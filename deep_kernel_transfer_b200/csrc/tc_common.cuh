@@ -181,6 +181,20 @@ static inline tc_encode_tiled_fn tc_encode_tiled() {
   }
   return fn;
 }
+// 2D bf16 tensor map {inner (elements), rows}, box {box_inner, box_rows}, SWIZZLE_128B (box_inner * 2 == 128)
+static inline int tc_make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner,
+                                       uint32_t box_rows) {
+  tc_encode_tiled_fn enc = tc_encode_tiled();
+  if (enc == nullptr) return -100;
+  cuuint64_t gdim[2] = {inner, rows};
+  cuuint64_t gstride[1] = {inner * 2};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return (int)r;
+}
 static inline int tc_make_tmap_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner,
                                   uint32_t box_rows) {
   tc_encode_tiled_fn enc = tc_encode_tiled();

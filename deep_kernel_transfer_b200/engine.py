@@ -102,7 +102,7 @@ class ConvNetEngine:
             ws["partials"].append(torch.empty(B * T * 128, device=dev, dtype=f32))
             ws["mean"].append(torch.empty(E, 64, device=dev, dtype=f32))
             ws["invstd"].append(torch.empty(E, 64, device=dev, dtype=f32))
-            shape = (2, 9, 64, 64) if self.use_tc else (9, 64, 64)
+            shape = (lib.conv3x3_tc_weight_floats(),) if self.use_tc else (9, 64, 64)
             ws["wt_f"].append(torch.empty(*shape, device=dev, dtype=f32) if i > 0 else None)
             ws["wt_d"].append(torch.empty(*shape, device=dev, dtype=f32) if i > 0 else None)
             max_part = max(max_part, B * lib.bn_bwd_chunks(H, W, int(L["pool"])) * 128)

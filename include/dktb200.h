@@ -71,6 +71,7 @@ int dktb_conv3x3_wgrad(const float* a, const float* gy, float* dw, float* db, fl
  * barrier wait timed out (a bug guard: results are then invalid).  Same layouts/partials as dktb_conv3x3_fwd.
  * Persistent CTAs (one per SM): activation halo loaded once per tile by TMA, A operand split in registers and staged in
  * TMEM, weight ring streaming across tiles, double-buffered halo and accumulator, dedicated epilogue warps. */
+long dktb_conv3x3_tc_weight_floats(void);      /* floats per prepared tensor: tf32 [9][hi|lo][64][64] + bf16 w_hi [9][64][64] */
 int dktb_prep_weights_tc(const float* w, float* wb_fwd, float* wb_dgrad, cudaStream_t stream);
 int dktb_conv3x3_tc_fwd(const float* a, const float* wb, const float* bias, float* out, float* partials, int* err,
                         int B, int H, int W, cudaStream_t stream);

@@ -311,8 +311,8 @@ def check_conv3x3_tc(lib, dev, B=3, H=6, W=5, seed=21, rtol=2e-5, fn="conv3x3_tc
     xr = x.double().requires_grad_(True)
     ref = F.conv2d(xr, w.double(), b.double(), padding=1)
     (ref * gy.double()).sum().backward()
-    wb_f = torch.empty(2, 9, 64, 64, device=dev)
-    wb_d = torch.empty(2, 9, 64, 64, device=dev)
+    wb_f = torch.empty(lib.conv3x3_tc_weight_floats(), device=dev)
+    wb_d = torch.empty(lib.conv3x3_tc_weight_floats(), device=dev)
     lib.prep_weights_tc(w.to(dev), wb_f, wb_d, 0)
     err = torch.zeros(1, device=dev, dtype=torch.int32)
     a = to_padded_nhwc(x).to(dev)
