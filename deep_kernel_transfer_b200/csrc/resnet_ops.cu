@@ -13,8 +13,7 @@ __global__ void __launch_bounds__(256) bn2d_partial_kernel(const float* __restri
   // mode 0: (x, x^2);  mode 1 (backward): g' = g * (y > 0 if y given), (g', g' * xhat)
   // Sums in DOUBLE: dbeta / dgamma (and the batch mean) are sums of up to 12 544 signed terms per image that largely cancel
   // (cond = sum|t| / |sum t| ~ 1e2 .. 1e3 for the first layers' gradients); a sequential float32 chain over HW / 4 pixels
-  // left 1e-4 on the stem BatchNorm's gradients of a ResNet50 step, where torch's cascaded float32 sum leaves 1e-5.  The
-  // kernel is HBM-bound, the extra DADDs are free.
+  // left 1e-4 on the stem BatchNorm's gradients of a ResNet50 step, where torch's cascaded float32 sum leaves 1e-5.
   __shared__ double s_red[2][4][64];
   const int c = blockIdx.x * 64 + threadIdx.x % 64, sl = threadIdx.x / 64;
   const int b = blockIdx.y;
@@ -27,17 +26,27 @@ __global__ void __launch_bounds__(256) bn2d_partial_kernel(const float* __restri
       is = invstd[(long)e * C + c];
     }
     const long base = (long)b * HW * C + c;
-    for (int p = sl; p < HW; p += 4) {
-      const float v = x[base + (long)p * C];
-      if (mode == 0) {
-        a0 += (double)v;
-        a1 += (double)v * (double)v;
-      } else {
-        float gv = g[base + (long)p * C];
-        if (y != nullptr && !(y[base + (long)p * C] > 0.f)) gv = 0.f;
-        a0 += (double)gv;
-        a1 += (double)gv * (double)((v - m) * is);
+    // float32 chains of 8 pixels, folded into the double totals (one DADD pair per 8 elements: the double pipe is slow)
+    for (int p0 = sl; p0 < HW; p0 += 32) {
+      float f0 = 0.f, f1 = 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int p = p0 + 4 * u;
+        if (p < HW) {
+          const float v = x[base + (long)p * C];
+          if (mode == 0) {
+            f0 += v;
+            f1 = fmaf(v, v, f1);
+          } else {
+            float gv = g[base + (long)p * C];
+            if (y != nullptr && !(y[base + (long)p * C] > 0.f)) gv = 0.f;
+            f0 += gv;
+            f1 = fmaf(gv, (v - m) * is, f1);
+          }
+        }
       }
+      a0 += (double)f0;
+      a1 += (double)f1;
     }
   }
   s_red[0][sl][threadIdx.x % 64] = a0;
