@@ -217,22 +217,16 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
       const int hb = t & 1, hp = (t >> 1) & 1;
       ok = tc::mbar_wait(&bar_hfull[hb], hp);
       if (!ok) break;
-      // Software pipeline: the halo row of tap t+1 is fetched from shared memory while the TMEM stores of tap t complete
-      // (tcgen05.wait::st was the top stall of these warps: long scoreboard 2.5 warps per issue in ncu)
-      float4 raw[8];
-      {
-        const int row = r;                             // tap 0: (0, 0)
-        const unsigned char* src = s_halo + (hb * 2 + set) * half_bytes + row * 128;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) raw[j] = *reinterpret_cast<const float4*>(src + ((j ^ (row & 7)) << 4));
-      }
       for (int tap = 0; tap < kP_Taps && ok; ++tap, ++wi) {
         const int sa = (int)((wi & 1) << 1) | set, pa = (int)((wi >> 1) & 1);      // this channel half's own stage ring
+        const int row = r + (tap / 3) * Wp + (tap % 3);
+        const unsigned char* src = s_halo + (hb * 2 + set) * half_bytes + row * 128;
         uint32_t hi[32], lo[16];                       // lo: bf16 pairs (low half = even channel), 16 columns
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          split_tf32_bf16(raw[j].x, raw[j].y, hi[4 * j + 0], hi[4 * j + 1], lo[2 * j + 0]);
-          split_tf32_bf16(raw[j].z, raw[j].w, hi[4 * j + 2], hi[4 * j + 3], lo[2 * j + 1]);
+          const float4 v = *reinterpret_cast<const float4*>(src + ((j ^ (row & 7)) << 4));
+          split_tf32_bf16(v.x, v.y, hi[4 * j + 0], hi[4 * j + 1], lo[2 * j + 0]);
+          split_tf32_bf16(v.z, v.w, hi[4 * j + 2], hi[4 * j + 3], lo[2 * j + 1]);
         }
         ok = tc::mbar_wait(&bar_aempty[sa], pa ^ 1);
         if (!ok) break;
@@ -241,12 +235,6 @@ conv3x3_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __
         tc::tmem_st16(dst, hi);
         tc::tmem_st16(dst + 16, hi + 16);
         tc::tmem_st16(dst + 32, lo);
-        if (tap + 1 < kP_Taps) {                       // next tap's row: in flight while the stores above land
-          const int row = r + ((tap + 1) / 3) * Wp + ((tap + 1) % 3);
-          const unsigned char* src = s_halo + (hb * 2 + set) * half_bytes + row * 128;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) raw[j] = *reinterpret_cast<const float4*>(src + ((j ^ (row & 7)) << 4));
-        }
         tc::tmem_st_wait();
         tc::tcgen05_fence_before();
         tc::mbar_arrive(&bar_afull[sa]);
