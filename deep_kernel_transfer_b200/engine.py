@@ -48,7 +48,7 @@ class ConvNetEngine:
         self.depth = depth
         self.dev = torch.device(device)
         # CUDA device: the tcgen05 kernels (csrc/conv_tc.cu, conv1_bwd_mma.cu), always.  The fp32 CUDA-core twins
-        # (csrc/conv_fp32.cu) exist for the g++ emulation build that the CPU tests inject (tests/emu): a CPU "device"
+        # (csrc/conv_fp32.cu) exist for the g++ host build of the kernels that the CPU tests inject: a CPU "device"
         # is the only way to reach them -- there is no switch between code paths on the GPU.
         if use_tc is None:
             use_tc = self.dev.type == "cuda"
@@ -301,7 +301,7 @@ class GPHead:
         self.family = self.FAMILY.get(kernel)
         self.centred = kernel in ("rbf", "matern")
         self.key = None
-        # Gram / cross-kernel products on tcgen05 (csrc/gram_tc.cu) on a GPU; the FFMA kernel serves the emulation build
+        # Gram / cross-kernel products on tcgen05 (csrc/gram_tc.cu) on a GPU; the FFMA kernel serves the host test build
         # and the shapes the tensor-core kernel does not take (fewer than 128 rows in total, D not a multiple of 4)
         self.use_tc = self.dev.type == "cuda" and lib.has("dktb_gram_tc")
         self.tc_err = torch.zeros(1, device=self.dev, dtype=torch.int32) if self.use_tc else None
