@@ -70,9 +70,25 @@ __global__ void bn2d_finalize_kernel(const float* __restrict__ partial, float* _
   float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 0.f;
   for (int e = 0; e < E; ++e) {
     double s = 0.0, q = 0.0;
-    for (int i = 0; i < ipe; ++i) {
-      s += (double)partial[(((long)e * ipe + i) * C + c) * 2 + 0];
-      q += (double)partial[(((long)e * ipe + i) * C + c) * 2 + 1];
+    {     // four independent chains: the loads of an episode's per-image partials are in flight together (fixed order)
+      double s4[4] = {0.0, 0.0, 0.0, 0.0}, q4[4] = {0.0, 0.0, 0.0, 0.0};
+      const float2* pp = reinterpret_cast<const float2*>(partial) + ((long)e * ipe) * C + c;
+      int i = 0;
+      for (; i + 4 <= ipe; i += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float2 v = pp[(long)(i + u) * C];
+          s4[u] += (double)v.x;
+          q4[u] += (double)v.y;
+        }
+      }
+      for (; i < ipe; ++i) {
+        const float2 v = pp[(long)i * C];
+        s4[0] += (double)v.x;
+        q4[0] += (double)v.y;
+      }
+      s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      q = (q4[0] + q4[1]) + (q4[2] + q4[3]);
     }
     const double m = s / n;
     double var = q / n - m * m;
@@ -94,9 +110,25 @@ __global__ void bn2d_bwd_finalize_kernel(const float* __restrict__ partial, floa
   double tg = 0.0, tb = 0.0;
   for (int e = 0; e < E; ++e) {
     double s = 0.0, q = 0.0;
-    for (int i = 0; i < ipe; ++i) {
-      s += (double)partial[(((long)e * ipe + i) * C + c) * 2 + 0];
-      q += (double)partial[(((long)e * ipe + i) * C + c) * 2 + 1];
+    {     // four independent chains: the loads of an episode's per-image partials are in flight together (fixed order)
+      double s4[4] = {0.0, 0.0, 0.0, 0.0}, q4[4] = {0.0, 0.0, 0.0, 0.0};
+      const float2* pp = reinterpret_cast<const float2*>(partial) + ((long)e * ipe) * C + c;
+      int i = 0;
+      for (; i + 4 <= ipe; i += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float2 v = pp[(long)(i + u) * C];
+          s4[u] += (double)v.x;
+          q4[u] += (double)v.y;
+        }
+      }
+      for (; i < ipe; ++i) {
+        const float2 v = pp[(long)i * C];
+        s4[0] += (double)v.x;
+        q4[0] += (double)v.y;
+      }
+      s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      q = (q4[0] + q4[1]) + (q4[2] + q4[3]);
     }
     sums[((long)e * C + c) * 2 + 0] = (float)s;
     sums[((long)e * C + c) * 2 + 1] = (float)q;
@@ -161,20 +193,35 @@ __global__ void __launch_bounds__(256) bn2d_bwd_apply_kernel(const float* __rest
                                                              const float* __restrict__ invstd,
                                                              const float* __restrict__ gamma,
                                                              const float* __restrict__ sums, float* __restrict__ gx,
-                                                             float* __restrict__ gres, long total, int HW, int C, int ipe,
+                                                             float* __restrict__ gres, long total4, int HW, int C, int ipe,
                                                              int relu, float inv_n) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c = (int)(i % C);
-  const long pix = i / C;
-  const int e = (int)(pix / HW / ipe);
-  float g = gy[i];
-  if (relu && !(y[i] > 0.f)) g = 0.f;
-  const float m = mean[(long)e * C + c], is = invstd[(long)e * C + c];
-  const float xh = (x[i] - m) * is;
-  const float s1 = sums[((long)e * C + c) * 2 + 0] * inv_n, s2 = sums[((long)e * C + c) * 2 + 1] * inv_n;
-  gx[i] = gamma[c] * is * (g - s1 - xh * s2);
-  if (gres != nullptr) gres[i] = g;
+  // four channels per thread (C % 4 == 0): 16-byte loads / stores, one index decomposition per four elements
+  const long i4 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 >= total4) return;
+  const int c4n = C >> 2;
+  const int c = (int)(i4 % c4n) * 4;
+  const long pix = i4 / c4n;
+  const int e = (int)(pix / ((long)HW * ipe));
+  const long i = i4 * 4;
+  float4 g = dktb_ld4(gy + i);
+  if (relu) {
+    const float4 yy = dktb_ld4(y + i);
+    if (!(yy.x > 0.f)) g.x = 0.f;
+    if (!(yy.y > 0.f)) g.y = 0.f;
+    if (!(yy.z > 0.f)) g.z = 0.f;
+    if (!(yy.w > 0.f)) g.w = 0.f;
+  }
+  const float4 xv = dktb_ld4(x + i);
+  const float4 m = dktb_ld4(mean + (long)e * C + c), is = dktb_ld4(invstd + (long)e * C + c), gm = dktb_ld4(gamma + c);
+  const float* sp = sums + ((long)e * C + c) * 2;
+  const float4 sa = dktb_ld4(sp), sb = dktb_ld4(sp + 4);      // (s1, s2) pairs of channels c, c+1 | c+2, c+3
+  float4 o;
+  o.x = gm.x * is.x * (g.x - sa.x * inv_n - (xv.x - m.x) * is.x * (sa.y * inv_n));
+  o.y = gm.y * is.y * (g.y - sa.z * inv_n - (xv.y - m.y) * is.y * (sa.w * inv_n));
+  o.z = gm.z * is.z * (g.z - sb.x * inv_n - (xv.z - m.z) * is.z * (sb.y * inv_n));
+  o.w = gm.w * is.w * (g.w - sb.z * inv_n - (xv.w - m.w) * is.w * (sb.w * inv_n));
+  dktb_st4(gx + i, o);
+  if (gres != nullptr) dktb_st4(gres + i, g);
 }
 
 // x: BN input; y: block output after add/ReLU (for the ReLU mask; nullable when relu == 0); gy: gradient w.r.t. y.
@@ -188,9 +235,10 @@ DKTB_EXPORT int dktb_bn2d_bwd(const float* x, const float* y, const float* gy, c
               mean, invstd, partial, HW, C, ipe, 1);
   DKTB_LAUNCH(bn2d_bwd_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, stream, (const float*)partial, sums, dgamma,
               dbeta, B / ipe, ipe, C);
-  const long total = (long)B * HW * C;
-  DKTB_LAUNCH(bn2d_bwd_apply_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, x, y, gy, mean, invstd,
-              gamma, (const float*)sums, gx, gres, total, HW, C, ipe, relu, 1.0f / ((float)ipe * (float)HW));
+  DKTB_CHECK_ARG(C % 4 == 0);
+  const long total4 = (long)B * HW * C / 4;
+  DKTB_LAUNCH(bn2d_bwd_apply_kernel, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, stream, x, y, gy, mean, invstd,
+              gamma, (const float*)sums, gx, gres, total4, HW, C, ipe, relu, 1.0f / ((float)ipe * (float)HW));
   return dktb_launch_status();
 }
 
@@ -199,58 +247,74 @@ DKTB_EXPORT int dktb_bn2d_bwd(const float* x, const float* y, const float* gy, c
 __global__ void __launch_bounds__(256) maxpool3_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                            unsigned char* __restrict__ idx, int B, int H, int W, int C,
                                                            int Ho, int Wo) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long total = (long)B * Ho * Wo * C;
-  if (i >= total) return;
-  const int c = (int)(i % C);
-  long t = i / C;
+  // four channels per thread (C % 4 == 0)
+  const long i4 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c4n = C >> 2;
+  const long total4 = (long)B * Ho * Wo * c4n;
+  if (i4 >= total4) return;
+  const int c = (int)(i4 % c4n) * 4;
+  long t = i4 / c4n;
   const int ow = (int)(t % Wo);
   t /= Wo;
   const int oh = (int)(t % Ho);
   const int b = (int)(t / Ho);
-  float best = -INFINITY;
-  int arg = 0;
+  float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
   for (int r = 0; r < 3; ++r)
+#pragma unroll
     for (int s = 0; s < 3; ++s) {
       const int ih = oh * 2 - 1 + r, iw = ow * 2 - 1 + s;
       if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
-      const float v = x[(((long)b * H + ih) * W + iw) * C + c];
-      if (v > best) { best = v; arg = r * 3 + s; }
+      const float4 v = dktb_ld4(x + (((long)b * H + ih) * W + iw) * C + c);
+      if (v.x > best.x) { best.x = v.x; a0 = r * 3 + s; }
+      if (v.y > best.y) { best.y = v.y; a1 = r * 3 + s; }
+      if (v.z > best.z) { best.z = v.z; a2 = r * 3 + s; }
+      if (v.w > best.w) { best.w = v.w; a3 = r * 3 + s; }
     }
-  y[i] = best;
-  idx[i] = (unsigned char)arg;
+  dktb_st4(y + i4 * 4, best);
+  *reinterpret_cast<uchar4*>(idx + i4 * 4) = make_uchar4((unsigned char)a0, (unsigned char)a1, (unsigned char)a2, (unsigned char)a3);
 }
 
 __global__ void __launch_bounds__(256) maxpool3_bwd_kernel(const float* __restrict__ gy,
                                                            const unsigned char* __restrict__ idx, float* __restrict__ gx,
                                                            int B, int H, int W, int C, int Ho, int Wo) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long total = (long)B * H * W * C;
-  if (i >= total) return;
-  const int c = (int)(i % C);
-  long t = i / C;
+  const long i4 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c4n = C >> 2;
+  const long total4 = (long)B * H * W * c4n;
+  if (i4 >= total4) return;
+  const int c = (int)(i4 % c4n) * 4;
+  long t = i4 / c4n;
   const int iw = (int)(t % W);
   t /= W;
   const int ih = (int)(t % H);
   const int b = (int)(t / H);
-  float g = 0.f;
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
   for (int r = 0; r < 3; ++r)
+#pragma unroll
     for (int s = 0; s < 3; ++s) {
       const int th = ih + 1 - r, tw = iw + 1 - s;
       if (th < 0 || tw < 0 || (th & 1) || (tw & 1)) continue;
       const int oh = th >> 1, ow = tw >> 1;
       if (oh >= Ho || ow >= Wo) continue;
       const long o = (((long)b * Ho + oh) * Wo + ow) * C + c;
-      if (idx[o] == r * 3 + s) g += gy[o];
+      const uchar4 a = *reinterpret_cast<const uchar4*>(idx + o);
+      const float4 v = dktb_ld4(gy + o);
+      const unsigned char tap = (unsigned char)(r * 3 + s);
+      if (a.x == tap) g.x += v.x;
+      if (a.y == tap) g.y += v.y;
+      if (a.z == tap) g.z += v.z;
+      if (a.w == tap) g.w += v.w;
     }
-  gx[i] = g;
+  dktb_st4(gx + i4 * 4, g);
 }
 
 DKTB_EXPORT int dktb_maxpool3_fwd(const float* x, float* y, unsigned char* idx, int B, int H, int W, int C,
                                   cudaStream_t stream) {
-  DKTB_CHECK_ARG(x && y && idx && B > 0 && H > 0 && W > 0 && C > 0);
+  DKTB_CHECK_ARG(x && y && idx && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0);
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  const long total = (long)B * Ho * Wo * C;
+  const long total = (long)B * Ho * Wo * (C / 4);
   DKTB_LAUNCH(maxpool3_fwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, x, y, idx, B, H, W, C, Ho,
               Wo);
   return dktb_launch_status();
@@ -258,9 +322,9 @@ DKTB_EXPORT int dktb_maxpool3_fwd(const float* x, float* y, unsigned char* idx, 
 
 DKTB_EXPORT int dktb_maxpool3_bwd(const float* gy, const unsigned char* idx, float* gx, int B, int H, int W, int C,
                                   cudaStream_t stream) {
-  DKTB_CHECK_ARG(gy && idx && gx && B > 0 && H > 0 && W > 0 && C > 0);
+  DKTB_CHECK_ARG(gy && idx && gx && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0);
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  const long total = (long)B * H * W * C;
+  const long total = (long)B * H * W * (C / 4);
   DKTB_LAUNCH(maxpool3_bwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, gy, idx, gx, B, H, W, C,
               Ho, Wo);
   return dktb_launch_status();
@@ -299,11 +363,16 @@ DKTB_EXPORT int dktb_avgpool_bwd(const float* gy, float* gx, int B, int HW, int 
 
 // a += b
 __global__ void add_inplace_kernel(float* __restrict__ a, const float* __restrict__ b, long n) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) a[i] += b[i];
+  const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 4 <= n) {
+    const float4 x = dktb_ld4(a + i), y = dktb_ld4(b + i);
+    dktb_st4(a + i, make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w));
+  } else {
+    for (long j = i; j < n; ++j) a[j] += b[j];
+  }
 }
 DKTB_EXPORT int dktb_add_inplace(float* a, const float* b, long n, cudaStream_t stream) {
   DKTB_CHECK_ARG(a && b && n > 0);
-  DKTB_LAUNCH(add_inplace_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, a, b, n);
+  DKTB_LAUNCH(add_inplace_kernel, dim3((unsigned)((n / 4 + 256) / 256)), dim3(256), 0, stream, a, b, n);
   return dktb_launch_status();
 }

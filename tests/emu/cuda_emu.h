@@ -29,6 +29,8 @@ struct alignas(16) float4 { float x, y, z, w; };
 struct alignas(16) int4 { int x, y, z, w; };
 struct alignas(8) int2 { int x, y; };
 static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
+struct alignas(4) uchar4 { unsigned char x, y, z, w; };
+static inline uchar4 make_uchar4(unsigned char a, unsigned char b, unsigned char c, unsigned char d) { return uchar4{a, b, c, d}; }
 static inline int4 make_int4(int a, int b, int c, int d) { return int4{a, b, c, d}; }
 static inline float2 make_float2(float a, float b) { return float2{a, b}; }
 
