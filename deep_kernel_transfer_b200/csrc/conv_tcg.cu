@@ -2,15 +2,18 @@
 // Cin, Cout that are multiples of 64 (64 ... 2048), 3x3 / stride 1 / pad 1 or 1x1 / stride 1, forward and dgrad, over the
 // padded-flat NHWC layout [B][H+2][W+2][C] (zero border) -- the same GEMM view and the same 3xTF32 error-compensated
 // arithmetic as the 64 -> 64 kernel of csrc/conv_tc.cu, generalised:
-//   work item = (128-pixel tile, 64-channel output block cb);  K = (Cin / 64 input groups g) x taps x 64 channels
-//   out[q][cb*64 + n] = sum_g sum_tap sum_k  A[q + off(tap)][g*64 + k] * W[cb*64 + n][g*64 + k][tap]
+//   work item = (128-pixel tile, NB-channel output block cb), NB = 64 or 128 (tcg_nb below);  K = (Cin / 64 input groups g)
+//   x taps x 64 channels:   out[q][cb*NB + n] = sum_g sum_tap sum_k  A[q + off(tap)][g*64 + k] * W[cb*NB + n][g*64 + k][tap]
 // The activation halo of (tile, g) is one pair of 2-D TMA boxes (channel coordinate g*64 + {0, 32}); the weight ring
-// streams [cb][g][tap] stages of [w_hi | w_lo] x 64 channels (32 KB); the accumulator of a tile stays in TMEM across all
-// groups and taps.  A 1x1 convolution is the same kernel with one tap (a plain GEMM over the padded-flat rows).
-//   warp 0      TMA producer (halo of the next (tile, group) as soon as its buffer is free; weight ring)
-//   warp 1      MMA issuer (elected lane), TMEM owner
-//   warps 2-9   stagers: halo row -> tf32 hi / lo split -> tcgen05.st into one of 4 A stages
-//   warps 10-13 epilogue: tcgen05.ld accumulator -> +bias -> global store
+// streams 32 KB stages of [w_hi | w_lo]; K is cut into chunks (576 for 3x3, 128 for 1x1), each accumulated in a fresh TMEM
+// accumulator and summed in fp32 registers by the epilogue.  A 1x1 convolution is the same kernel with one tap (a plain
+// GEMM over dense rows).  Warp roles are whole warpgroups so that setmaxnreg can move registers to where they are needed:
+//   warps 0-3   epilogue (176 registers): tcgen05.ld accumulator -> NB running sums -> +bias -> global store
+//   warps 4-11  stagers (136): halo row -> tf32 hi / lo split -> tcgen05.st into one of 4 A stages
+//   warp 12     TMA producer (64): halo of the next (tile, group) as soon as its buffer is free; weight ring
+//   warp 13     MMA issuer (elected lane), TMEM owner;  warps 14-15 idle (they only give their registers away)
+// Measured at B = 420 (tests/probe/time_conv_tcg.py): NB = 128 is 1.15-1.3x the NB = 64 item on every layer with
+// Cin >= 128 (each staged A tile feeds twice the MMA work), e.g. 128 -> 128 at 28x28 0.580 -> 0.488 ms.
 // Work items are ordered tile-major / cb-minor so that the CTAs resident at any time share their halos through L2.
 #include "dktb_common.cuh"
 
@@ -24,7 +27,14 @@ constexpr int kHaloBox = 32;
 constexpr int kWStages = 3;
 constexpr int kWStageBytes = 32768;           // [half 0 | half 1] x [w_hi | w_lo] x 64 rows x 128 B
 constexpr int kAStages = 4;
-constexpr int kThreads = 64 + 256 + 128;
+// warp roles by warpgroup (setmaxnreg moves registers between whole warpgroups): 0 = epilogue (4 warps), 1-2 = stagers
+// (8 warps), 3 = TMA producer (warp 12), MMA issuer (warp 13), two idle warps
+constexpr int kThreads = 512;
+constexpr int kRegsEpilogue = 176, kRegsStager = 136, kRegsControl = 64;      // (176 + 2 x 136 + 64) x 128 = 65536 registers
+
+// output channels per work item: 128 when they divide and K spans at least two input groups (with one group the kernel is
+// bound by writing the tile, and the narrower item spreads that over more CTAs).  Decides the weight tensor's layout too.
+__host__ __device__ inline int tcg_nb(int cout, int cin) { return (cout % 128 == 0 && cin >= 128) ? 128 : 64; }
 
 // tf32 split: hi = round-to-nearest(-away) to 10 mantissa bits, lo = the exact remainder (the tensor core truncates it to
 // tf32: the operand is carried to 2^-21).  Rounding the remainder instead (2^-23) was measured: no change of the
@@ -34,13 +44,23 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
   lo = __float_as_uint(v - __uint_as_float(hi));
 }
 
+// NB = output channels per work item.  NB = 64: the three 3xTF32 products are a_hi x [w_hi | w_lo] (one N = 128
+// instruction on the stacked tile) + a_lo x w_hi (N = 64), accumulator = 64 + 64 columns added in the epilogue, one
+// accumulator per K chunk summed in registers.  NB = 128 (Cout % 128 == 0): a_hi x w_hi, a_hi x w_lo, a_lo x w_hi are
+// three full-rate N = 128 instructions into ONE 128-column accumulator, and every staged A tile serves twice as many
+// output channels (the stager / TMEM round trip, not the MMA issue, bounds these kernels).
+// Weight stage (32 KB) = [w_hi NB rows | w_lo NB rows] x 32 channels x 4 B for both channel halves of one (group, tap)
+// (NB = 64) or for one half (NB = 128).
+template <int NB>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tcg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                 const float* __restrict__ bias, float* __restrict__ out, int B, int H, int W, int Cout, int G, int nblk,
                 int ntaps, int halo_rows_pad, int tiles_per_img, int flat, int gchunk, int* __restrict__ err) {
+  constexpr int kHS = NB == 64 ? 2 : 1;                       // channel halves per 32 KB weight stage
+  constexpr int kWRing = kWStages;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t bar_hfull[2], bar_hempty[2], bar_wfull[kWStages], bar_wempty[kWStages], bar_afull[kAStages],
+  __shared__ uint64_t bar_hfull[2], bar_hempty[2], bar_wfull[kWRing], bar_wempty[kWRing], bar_afull[kAStages],
       bar_aempty[kAStages], bar_accfull[2], bar_accempty[2];
   __shared__ uint32_t s_tmem;
   __shared__ int s_err;
@@ -50,7 +70,7 @@ conv_tcg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const int lead = ntaps == 9 ? Wp + 1 : 0;                  // rows of halo in front of the tile
   const int half_bytes = halo_rows_pad * 128;
   unsigned char* s_halo = smem;                               // [2 buffers][2 halves][halo_rows_pad][128 B]
-  unsigned char* s_w = smem + 4 * half_bytes;                 // [kWStages][32 KB]
+  unsigned char* s_w = smem + 4 * half_bytes;                 // [kWRing][kWStageBytes]
   const long nwork = (long)B * tiles_per_img * nblk;
 
   if (tid == 0) {
@@ -60,23 +80,26 @@ conv_tcg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       tc::mbar_init(&bar_accfull[s], 1);
       tc::mbar_init(&bar_accempty[s], 128);
     }
-    for (int s = 0; s < kWStages; ++s) { tc::mbar_init(&bar_wfull[s], 1); tc::mbar_init(&bar_wempty[s], 1); }
+    for (int s = 0; s < kWRing; ++s) { tc::mbar_init(&bar_wfull[s], 1); tc::mbar_init(&bar_wempty[s], 1); }
     for (int s = 0; s < kAStages; ++s) { tc::mbar_init(&bar_afull[s], 128); tc::mbar_init(&bar_aempty[s], 1); }
     s_err = 0;
     tc::fence_barrier_init();
   }
-  if (warp == 0 && lane == 0) { tc::prefetch_tmap(&map_a); tc::prefetch_tmap(&map_w); }
-  if (warp == 1) tc::tmem_alloc<512>(&s_tmem);
+  if (warp == 12 && lane == 0) { tc::prefetch_tmap(&map_a); tc::prefetch_tmap(&map_w); }
+  if (warp == 13) tc::tmem_alloc<512>(&s_tmem);
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::tcgen05_fence_after();
   const uint32_t tmem = s_tmem;
-  const uint32_t a_tmem = tmem + 256;                         // accumulators [0,256): 2 buffers x (x w_hi | x w_lo)
-
-  if (warp == 0) {
+  const uint32_t a_tmem = tmem + 256;                         // accumulators [0,256): 2 buffers x 128 columns
+  // the epilogue keeps NB fp32 running sums per thread: it takes the registers the control warpgroup does not need
+  if (warp >= 12) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(kRegsControl));
+  }
+  if (warp == 12) {
     // ------------------------------------------------------------------ TMA producer
     long vt = 0;                                              // (work item, group) counter: halo double buffering
-    long wi = 0;                                              // weight stage counter
+    long wi = 0;                                              // weight stage counter: (group, tap, half)
     bool ok = true;
     auto load_halo = [&](long work, int g, long vv) -> bool {
       const int hb = (int)(vv & 1), hp = (int)((vv >> 1) & 1);
@@ -100,18 +123,21 @@ conv_tcg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     for (long work = blockIdx.x; work < nwork && ok; work += gridDim.x) {
       const int cb = (int)(work % nblk);
       for (int g = 0; g < G && ok; ++g, ++vt) {
-        for (int tap = 0; tap < ntaps && ok; ++tap, ++wi) {
-          const int s = (int)(wi % kWStages), ph = (int)((wi / kWStages) & 1);
-          ok = tc::mbar_wait(&bar_wempty[s], ph ^ 1);
-          if (!ok) break;
-          if (tc::elect_one()) {
-            const int wrow = (((cb * G + g) * ntaps) + tap) * 128;
-            tc::mbar_expect_tx(&bar_wfull[s], kWStageBytes);
-            tc::tma_load_2d(s_w + s * kWStageBytes, &map_w, &bar_wfull[s], 0, wrow);
-            tc::tma_load_2d(s_w + s * kWStageBytes + 16384, &map_w, &bar_wfull[s], 32, wrow);
+        for (int tap = 0; tap < ntaps && ok; ++tap) {
+          for (int h = 0; h < 2 && ok; h += kHS, ++wi) {
+            const int s = (int)(wi % kWRing), ph = (int)((wi / kWRing) & 1);
+            ok = tc::mbar_wait(&bar_wempty[s], ph ^ 1);
+            if (!ok) break;
+            if (tc::elect_one()) {
+              const int wrow = (((cb * G + g) * ntaps) + tap) * (2 * NB);
+              tc::mbar_expect_tx(&bar_wfull[s], kWStageBytes);
+#pragma unroll
+              for (int j = 0; j < kHS; ++j)
+                tc::tma_load_2d(s_w + s * kWStageBytes + j * (kWStageBytes / kHS), &map_w, &bar_wfull[s], (h + j) * 32, wrow);
+            }
+            __syncwarp();
           }
-          __syncwarp();
-          if (tap == pre_tap) {
+          if (tap == pre_tap && ok) {
             if (g + 1 < G) ok = load_halo(work, g + 1, vt + 1);
             else if (work + gridDim.x < nwork) ok = load_halo(work + gridDim.x, 0, vt + 1);
           }
@@ -119,17 +145,18 @@ conv_tcg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       }
     }
     if (!ok) s_err = 1;
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer: 16 x (M128, N128|64, K8) per (group, tap)
+  } else if (warp == 13) {
+    // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc = tc::umma_idesc(2, 128, 128, 0, 0);
-    const uint32_t idesc_lo = tc::umma_idesc(2, 128, 64, 0, 0);      // a_lo only meets the w_hi half of the stacked operand
+    const uint32_t idesc_lo = tc::umma_idesc(2, 128, 64, 0, 0);      // NB = 64: a_lo only meets the w_hi half of the stacked tile
     int t = 0;                                                // accumulator use counter (one per K chunk)
-    long wi = 0;
+    long wi = 0;                                              // half-tap counter: A stages
+    long ws = 0;                                              // weight stage counter
     bool ok = true;
     for (long work = blockIdx.x; work < nwork && ok; work += gridDim.x) {
       // K is cut into chunks of `gchunk` input groups; every chunk gets a FRESH TMEM accumulator that the epilogue warps
-      // drain into an fp32 running sum in registers: the tensor core's own accumulation does not round to nearest, and
-      // over K = 4608 (512 channels x 9 taps) that bias reaches 2e-5 of the result
+      // drain into NB fp32 running sums in registers: the tensor core's own
+      // accumulation does not round to nearest, and over K = 4608 (512 channels x 9 taps) that bias reaches 2e-5
       for (int g0 = 0; g0 < G && ok; g0 += gchunk, ++t) {
         const int ab = t & 1, ap = (t >> 1) & 1;
         ok = tc::mbar_wait(&bar_accempty[ab], ap ^ 1);
@@ -137,35 +164,47 @@ conv_tcg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         tc::tcgen05_fence_after();
         const uint32_t d_tmem = tmem + ab * 128;
         const int nk = (min(G, g0 + gchunk) - g0) * ntaps;
-        for (int kk = 0; kk < nk && ok; ++kk, ++wi) {
-          const int sw = (int)(wi % kWStages), pw = (int)((wi / kWStages) & 1);
-          const int pa = (int)((wi >> 1) & 1);
-          ok = tc::mbar_wait(&bar_wfull[sw], pw);
-          if (!ok) break;
-          const uint32_t wbase = tc::smem_u32(s_w + sw * kWStageBytes);
+        for (int kk = 0; kk < nk && ok; ++kk) {
+          int sw = 0;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int sa = (int)((wi & 1) << 1) | h;
+          for (int h = 0; h < 2; ++h, ++wi) {
+            if (h % kHS == 0) {
+              sw = (int)(ws % kWRing);
+              ok = tc::mbar_wait(&bar_wfull[sw], (int)((ws / kWRing) & 1));
+              ++ws;
+              if (!ok) break;
+            }
+            const uint32_t wbase = tc::smem_u32(s_w + sw * kWStageBytes + (h % kHS) * (kWStageBytes / kHS));
+            const int sa = (int)(wi & 3), pa = (int)((wi >> 2) & 1);
             ok = tc::mbar_wait(&bar_afull[sa], pa);
             if (!ok) break;
             tc::tcgen05_fence_after();
             const uint32_t acol = a_tmem + sa * 64;             // hi [0,32) | lo [32,64)
             if (tc::elect_one()) {
+              if constexpr (NB == 64) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {       // the N = 128 instructions first, then the N = 64 ones (see conv_tc.cu)
-                const uint64_t w_cat = tc::umma_desc_sw128(wbase + h * 16384 + k * 32, 16, 1024);
-                tc::umma_tf32_ts(d_tmem, acol + k * 8, w_cat, idesc, (kk | h | k) ? 1u : 0u);      // a_hi * [w_hi | w_lo]
-              }
+                for (int k = 0; k < 4; ++k) {     // the N = 128 instructions first, then the N = 64 ones (see conv_tc.cu)
+                  const uint64_t w_cat = tc::umma_desc_sw128(wbase + k * 32, 16, 1024);
+                  tc::umma_tf32_ts(d_tmem, acol + k * 8, w_cat, idesc, (kk | h | k) ? 1u : 0u);    // a_hi * [w_hi | w_lo]
+                }
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t w_cat = tc::umma_desc_sw128(wbase + h * 16384 + k * 32, 16, 1024);
-                tc::umma_tf32_ts(d_tmem, acol + 32 + k * 8, w_cat, idesc_lo, 1u);                    // a_lo * w_hi
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t w_cat = tc::umma_desc_sw128(wbase + k * 32, 16, 1024);
+                  tc::umma_tf32_ts(d_tmem, acol + 32 + k * 8, w_cat, idesc_lo, 1u);                  // a_lo * w_hi
+                }
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t w_hi = tc::umma_desc_sw128(wbase + k * 32, 16, 1024);
+                  const uint64_t w_lo = tc::umma_desc_sw128(wbase + NB * 128 + k * 32, 16, 1024);
+                  tc::umma_tf32_ts(d_tmem, acol + 32 + k * 8, w_hi, idesc, (kk | h | k) ? 1u : 0u);  // a_lo * w_hi (small first)
+                  tc::umma_tf32_ts(d_tmem, acol + k * 8, w_lo, idesc, 1u);                            // a_hi * w_lo
+                  tc::umma_tf32_ts(d_tmem, acol + k * 8, w_hi, idesc, 1u);                            // a_hi * w_hi
+                }
               }
               tc::umma_commit(&bar_aempty[sa]);
-              if (h == 1) {
-                tc::umma_commit(&bar_wempty[sw]);
-                if (kk == nk - 1) tc::umma_commit(&bar_accfull[ab]);
-              }
+              if (h % kHS == kHS - 1) tc::umma_commit(&bar_wempty[sw]);
+              if (h == 1 && kk == nk - 1) tc::umma_commit(&bar_accfull[ab]);
             }
             __syncwarp();
           }
@@ -173,9 +212,10 @@ conv_tcg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       }
     }
     if (!ok) s_err = 1;
-  } else if (warp < 10) {
+  } else if (warp >= 4 && warp < 12) {
     // ------------------------------------------------------------------ stagers (256 threads): 32 channels per thread
-    const int ct = tid - 64;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(kRegsStager));
+    const int ct = tid - 128;
     const int set = ct >> 7;                          // channel half handled by this thread
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
@@ -217,8 +257,9 @@ conv_tcg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       }
     }
     if (!ok) s_err = 1;
-  } else {
+  } else if (warp < 4) {
     // ------------------------------------------------------------------ epilogue (128 threads)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(kRegsEpilogue));
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
@@ -230,38 +271,45 @@ conv_tcg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int img = (int)(tile / tiles_per_img), tix = (int)(tile % tiles_per_img);
       const long img_base = flat ? 0 : (long)img * Hp * Wp;
       const int q0 = flat ? tix * kRows : (Wp + 1) + tix * kRows;
-      float run[64];
+      const int q = q0 + r;
+      const int hp = q / Wp, wp = q - hp * Wp;
+      // flat (1x1 over a dense [rows][C] tensor: H = number of rows, B = 1): every row below H is an output
+      const bool valid = flat ? q < H : (q < Hp * Wp && hp >= 1 && hp <= H && wp >= 1 && wp <= W);
+      float run[NB];
 #pragma unroll
-      for (int j = 0; j < 64; ++j) run[j] = 0.f;
+      for (int j = 0; j < NB; ++j) run[j] = 0.f;
       for (int g0 = 0; g0 < G && ok; g0 += gchunk, ++t) {       // one accumulator per K chunk, summed here in fp32
         const int ab = t & 1, ap = (t >> 1) & 1;
         ok = tc::mbar_wait(&bar_accfull[ab], ap);
         if (!ok) break;
         tc::tcgen05_fence_after();
 #pragma unroll
-        for (int c = 0; c < 64; c += 16) {
-          uint32_t v[16], u[16];
+        for (int c = 0; c < NB; c += 16) {
+          uint32_t v[16];
           tc::tmem_ld16(tmem + ab * 128 + lane_base + c, v);
-          tc::tmem_ld16(tmem + ab * 128 + 64 + lane_base + c, u);
-          tc::tmem_ld_wait();
-          if (c == 48) {                              // accumulator fully read: hand the buffer back to the MMA warp
+          if constexpr (NB == 64) {                     // main and small-term accumulators are separate column ranges
+            uint32_t u[16];
+            tc::tmem_ld16(tmem + ab * 128 + 64 + lane_base + c, u);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+          } else {
+            tc::tmem_ld_wait();
+          }
+          if (c == NB - 16) {                           // accumulator fully read: hand the buffer back to the MMA warp
             tc::tcgen05_fence_before();
             tc::mbar_arrive(&bar_accempty[ab]);
           }
 #pragma unroll
-          for (int j = 0; j < 16; ++j) run[c + j] += __uint_as_float(v[j]) + __uint_as_float(u[j]);
+          for (int j = 0; j < 16; ++j) run[c + j] += __uint_as_float(v[j]);
         }
       }
       if (!ok) break;
-      const int q = q0 + r;
-      const int hp = q / Wp, wp = q - hp * Wp;
-      // flat (1x1 over a dense [rows][C] tensor: H = number of rows, B = 1): every row below H is an output
-      const bool valid = flat ? q < H : (q < Hp * Wp && hp >= 1 && hp <= H && wp >= 1 && wp <= W);
       if (valid) {
-        float* orow = out + (img_base + q) * (long)Cout + cb * 64;
-        const float* brow = bias ? bias + cb * 64 : nullptr;
+        float* orow = out + (img_base + q) * (long)Cout + cb * NB;
+        const float* brow = bias ? bias + cb * NB : nullptr;
 #pragma unroll
-        for (int j = 0; j < 64; j += 4) {
+        for (int j = 0; j < NB; j += 4) {
           float4 o = make_float4(run[j], run[j + 1], run[j + 2], run[j + 3]);
           if (brow) { o.x += brow[j]; o.y += brow[j + 1]; o.z += brow[j + 2]; o.w += brow[j + 3]; }
           dktb_st4(orow + j, o);
@@ -273,9 +321,8 @@ conv_tcg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   tc::tcgen05_fence_before();
   __syncthreads();
   if (tid == 0 && s_err) atomicExch(err, 1);
-  if (warp == 1) tc::tmem_dealloc<512>(tmem);
+  if (warp == 13) tc::tmem_dealloc<512>(tmem);
 }
-
 
 // ------------------------------------------------------------------------------------------------------------------
 // Weight gradient on tcgen05 for the same layers:  dW[co][ci][tap] = sum_q X[q + off(tap)][ci] * G[q][co]  over all rows
@@ -520,9 +567,9 @@ __global__ void conv_wgrad_tcg_reduce_kernel(const float* __restrict__ partial, 
   }
 }
 
-// w [Cout][Cin][R][R] (R = 3 or 1) -> wb_fwd [Cout/64][Cin/64][taps][hi 64 | lo 64][64]  (row = output channel, col = input
-// channel) and wb_dgrad [Cin/64][Cout/64][taps][hi 64 | lo 64][64] (taps flipped, roles swapped): hi = tf32-rounded, lo =
-// rounded remainder; the hi and lo tiles of one (block, group, tap) are adjacent so that they form one N = 128 operand.
+// w [Cout][Cin][R][R] (R = 3 or 1) -> wb_fwd [Cout/NBf][Cin/64][taps][hi NBf | lo NBf][64]  (row = output channel, col =
+// input channel) and wb_dgrad [Cin/NBd][Cout/64][taps][hi NBd | lo NBd][64] (taps flipped, roles swapped): hi = tf32-rounded,
+// lo = rounded remainder.  NBf / NBd = tcg_nb(output channels, input channels) of the respective direction.
 __global__ void prep_weights_tcg_kernel(const float* __restrict__ w, float* __restrict__ wb_fwd,
                                         float* __restrict__ wb_dgrad, int Cout, int Cin, int ntaps) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -531,16 +578,17 @@ __global__ void prep_weights_tcg_kernel(const float* __restrict__ w, float* __re
   const int ci = (int)((i / ntaps) % Cin), co = (int)(i / ((long)ntaps * Cin));
   const float v = w[i];
   const float hi = tc::to_tf32_rna(v), lo = tc::to_tf32_rna(v - hi);
-  const int G = Cin / 64, NB = Cout / 64;
   if (wb_fwd) {
-    const long base = ((((long)(co / 64) * G + ci / 64) * ntaps + tap) * 128 + (co % 64)) * 64 + (ci % 64);
+    const int NB = tcg_nb(Cout, Cin), G = Cin / 64;
+    const long base = ((((long)(co / NB) * G + ci / 64) * ntaps + tap) * (2 * NB) + (co % NB)) * 64 + (ci % 64);
     wb_fwd[base] = hi;
-    wb_fwd[base + 64 * 64] = lo;
+    wb_fwd[base + NB * 64] = lo;
   }
   if (wb_dgrad) {
-    const long base = ((((long)(ci / 64) * NB + co / 64) * ntaps + (ntaps - 1 - tap)) * 128 + (ci % 64)) * 64 + (co % 64);
+    const int NB = tcg_nb(Cin, Cout), G = Cout / 64;
+    const long base = ((((long)(ci / NB) * G + co / 64) * ntaps + (ntaps - 1 - tap)) * (2 * NB) + (ci % NB)) * 64 + (co % 64);
     wb_dgrad[base] = hi;
-    wb_dgrad[base + 64 * 64] = lo;
+    wb_dgrad[base + NB * 64] = lo;
   }
 }
 
@@ -618,25 +666,32 @@ DKTB_EXPORT int dktb_conv_tcg(const float* a, const float* wb, const float* bias
   const int halo_pad = (halo + kHaloBox - 1) / kHaloBox * kHaloBox;
   const int smem = 4 * halo_pad * 128 + kWStages * kWStageBytes + 1024;
   DKTB_CHECK_ARG(smem <= 227 * 1024);
+  const int NB = tcg_nb(Cout, Cin);                 // output channels per work item (the weight tensor was laid out for it)
+  const int nb = Cout / NB;
   CUtensorMap map_a, map_w;
   if (tc_make_tmap_2d(&map_a, a, (uint64_t)Cin, (uint64_t)rows, 32, kHaloBox) != 0) return DKTB_BAD_ARG - 1;
-  if (tc_make_tmap_2d(&map_w, wb, 64, (uint64_t)nblk * G * ntaps * 128, 32, 128) != 0) return DKTB_BAD_ARG - 1;
-  cudaFuncSetAttribute(conv_tcg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (tc_make_tmap_2d(&map_w, wb, 64, (uint64_t)nb * G * ntaps * 2 * NB, 32, 2 * NB) != 0) return DKTB_BAD_ARG - 1;
   const long span = flat ? rows : (long)Hp * Wp - 2 * (Wp + 1);
   const int tiles_per_img = (int)((span + kRows - 1) / kRows);
   const int nimg = flat ? 1 : B;
-  const long nwork = (long)nimg * tiles_per_img * nblk;
+  const long nwork = (long)nimg * tiles_per_img * nb;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = (int)(nwork < sms ? nwork : sms);
   // flat: the kernel sees one "image" of `rows` rows (H carries the row count for the validity test)
   const int gchunk = ntaps == 9 ? 1 : 2;         // K per accumulator: 576 (3x3) / 128 (1x1); no measurable cost vs 1152 / 1024
-  conv_tcg_kernel<<<grid, kThreads, smem, stream>>>(map_a, map_w, bias, out, nimg, flat ? (int)rows : H, W, Cout, G, nblk,
-                                                    ntaps, halo_pad, tiles_per_img, flat, gchunk, err);
+  if (NB == 128) {
+    cudaFuncSetAttribute(conv_tcg_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    conv_tcg_kernel<128><<<grid, kThreads, smem, stream>>>(map_a, map_w, bias, out, nimg, flat ? (int)rows : H, W, Cout, G, nb,
+                                                           ntaps, halo_pad, tiles_per_img, flat, gchunk, err);
+  } else {
+    cudaFuncSetAttribute(conv_tcg_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    conv_tcg_kernel<64><<<grid, kThreads, smem, stream>>>(map_a, map_w, bias, out, nimg, flat ? (int)rows : H, W, Cout, G, nb,
+                                                          ntaps, halo_pad, tiles_per_img, flat, gchunk, err);
+  }
   return dktb_launch_status();
 }
-
 
 // how many K-splits (CTAs per (group, block) pair) dktb_wgrad_tcg uses, and the scratch it needs (floats)
 static int wgrad_tcg_nsplit(long rows, int npairs) {
