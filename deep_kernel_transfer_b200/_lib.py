@@ -88,6 +88,7 @@ SIGNATURES = {
     "dktb_nchw_to_nhwc": ("ppiiiis", ctypes.c_int),
     "dktb_spectral_fwd": ("pppppppiiiiiiis", ctypes.c_int),
     "dktb_spectral_bwd": ("ppppppppppiiiiiis", ctypes.c_int),
+    "dktb_bn2d_partial_floats": ("iii", ctypes.c_long),
     "dktb_bn2d_stats": ("ppppppiiiiffs", ctypes.c_int),
     "dktb_bn2d_apply": ("pppppppiiiiis", ctypes.c_int),
     "dktb_bn2d_bwd": ("ppppppppppppiiiiis", ctypes.c_int),

@@ -5,7 +5,20 @@
 #include "dktb_common.cuh"
 
 // ------------------------------------------------------------------------------------------------ BN statistics
-// partial[b][c][2] = sum, sumsq over the HW pixels of image b.  grid (ceil(C/64), B), 256 threads = 64 ch x 4 slices
+// pixel splits per image: enough CTAs to fill the machine when B x C / 64 alone does not (the 64-channel layers at 56x56 /
+// 112x112 hold most of the bytes); a split is one more row of `partial`, summed by the finalize kernels in a fixed order
+static int bn2d_splits(int B, int HW, int C) {
+  const long ctas = (long)B * ((C + 63) / 64);
+  int s = (int)((4 * 148 + ctas - 1) / ctas);
+  const int smax = HW / 256 > 0 ? HW / 256 : 1;
+  if (s > smax) s = smax;
+  if (s > 8) s = 8;
+  return s < 1 ? 1 : s;
+}
+DKTB_EXPORT long dktb_bn2d_partial_floats(int B, int HW, int C) { return (long)B * bn2d_splits(B, HW, C) * C * 2; }
+
+// partial[b * S + split][c][2] = sum, sumsq over the split's pixels of image b.  grid (ceil(C/64), B, S), 256 threads =
+// 16 channel quads (float4 loads, C % 4 == 0) x 16 pixel slices
 __global__ void __launch_bounds__(256) bn2d_partial_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                            const float* __restrict__ y, const float* __restrict__ mean,
                                                            const float* __restrict__ invstd, float* __restrict__ partial,
@@ -14,139 +27,172 @@ __global__ void __launch_bounds__(256) bn2d_partial_kernel(const float* __restri
   // Sums in DOUBLE: dbeta / dgamma (and the batch mean) are sums of up to 12 544 signed terms per image that largely cancel
   // (cond = sum|t| / |sum t| ~ 1e2 .. 1e3 for the first layers' gradients); a sequential float32 chain over HW / 4 pixels
   // left 1e-4 on the stem BatchNorm's gradients of a ResNet50 step, where torch's cascaded float32 sum leaves 1e-5.
-  __shared__ double s_red[2][4][64];
-  const int c = blockIdx.x * 64 + threadIdx.x % 64, sl = threadIdx.x / 64;
-  const int b = blockIdx.y;
-  double a0 = 0.0, a1 = 0.0;
+  // float32 chains of 8 pixels are folded into the double totals (one DADD per 8 elements: the double pipe is slow).
+  __shared__ double s_red[2][16][64];
+  const int cq = threadIdx.x & 15, ps = threadIdx.x >> 4;
+  const int c = blockIdx.x * 64 + cq * 4;
+  const int b = blockIdx.y, S = gridDim.z;
+  const int per = (HW + S - 1) / S;
+  const int p_lo = blockIdx.z * per, p_hi = min(HW, p_lo + per);
+  double a0[4] = {0.0, 0.0, 0.0, 0.0}, a1[4] = {0.0, 0.0, 0.0, 0.0};
   if (c < C) {
-    float m = 0.f, is = 0.f;
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f), is = m;
     if (mode == 1) {
       const int e = b / ipe;
-      m = mean[(long)e * C + c];
-      is = invstd[(long)e * C + c];
+      m = dktb_ld4(mean + (long)e * C + c);
+      is = dktb_ld4(invstd + (long)e * C + c);
     }
     const long base = (long)b * HW * C + c;
-    // float32 chains of 8 pixels, folded into the double totals (one DADD pair per 8 elements: the double pipe is slow)
-    for (int p0 = sl; p0 < HW; p0 += 32) {
-      float f0 = 0.f, f1 = 0.f;
+    for (int p0 = p_lo + ps; p0 < p_hi; p0 += 16 * 8) {
+      float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int p = p0 + 4 * u;
-        if (p < HW) {
-          const float v = x[base + (long)p * C];
+      for (int h = 0; h < 2; ++h) {             // two batches of four pixels: every load of a batch is issued first
+        float4 xv[4], gv[4], yv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int p = p0 + 16 * (4 * h + u);
+          const bool in = p < p_hi;
+          const long off = base + (long)(in ? p : p_lo) * C;
+          xv[u] = dktb_ld4(x + off);
+          if (mode == 1) {
+            gv[u] = dktb_ld4(g + off);
+            if (y != nullptr) yv[u] = dktb_ld4(y + off);
+          }
+          if (!in) {
+            xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (mode == 1) gv[u] = xv[u];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
           if (mode == 0) {
-            f0 += v;
-            f1 = fmaf(v, v, f1);
+            f0.x += xv[u].x; f0.y += xv[u].y; f0.z += xv[u].z; f0.w += xv[u].w;
+            f1.x = fmaf(xv[u].x, xv[u].x, f1.x); f1.y = fmaf(xv[u].y, xv[u].y, f1.y);
+            f1.z = fmaf(xv[u].z, xv[u].z, f1.z); f1.w = fmaf(xv[u].w, xv[u].w, f1.w);
           } else {
-            float gv = g[base + (long)p * C];
-            if (y != nullptr && !(y[base + (long)p * C] > 0.f)) gv = 0.f;
-            f0 += gv;
-            f1 = fmaf(gv, (v - m) * is, f1);
+            float4 q = gv[u];
+            if (y != nullptr) {
+              if (!(yv[u].x > 0.f)) q.x = 0.f;
+              if (!(yv[u].y > 0.f)) q.y = 0.f;
+              if (!(yv[u].z > 0.f)) q.z = 0.f;
+              if (!(yv[u].w > 0.f)) q.w = 0.f;
+            }
+            f0.x += q.x; f0.y += q.y; f0.z += q.z; f0.w += q.w;
+            f1.x = fmaf(q.x, (xv[u].x - m.x) * is.x, f1.x); f1.y = fmaf(q.y, (xv[u].y - m.y) * is.y, f1.y);
+            f1.z = fmaf(q.z, (xv[u].z - m.z) * is.z, f1.z); f1.w = fmaf(q.w, (xv[u].w - m.w) * is.w, f1.w);
           }
         }
       }
-      a0 += (double)f0;
-      a1 += (double)f1;
+      a0[0] += (double)f0.x; a0[1] += (double)f0.y; a0[2] += (double)f0.z; a0[3] += (double)f0.w;
+      a1[0] += (double)f1.x; a1[1] += (double)f1.y; a1[2] += (double)f1.z; a1[3] += (double)f1.w;
     }
   }
-  s_red[0][sl][threadIdx.x % 64] = a0;
-  s_red[1][sl][threadIdx.x % 64] = a1;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    s_red[0][ps][cq * 4 + j] = a0[j];
+    s_red[1][ps][cq * 4 + j] = a1[j];
+  }
   __syncthreads();
-  if (sl == 0 && c < C) {
-    const int t = threadIdx.x;
-    partial[((long)b * C + c) * 2 + 0] = (float)((s_red[0][0][t] + s_red[0][1][t]) + (s_red[0][2][t] + s_red[0][3][t]));
-    partial[((long)b * C + c) * 2 + 1] = (float)((s_red[1][0][t] + s_red[1][1][t]) + (s_red[1][2][t] + s_red[1][3][t]));
+  if (threadIdx.x < 128) {                     // fixed-order sum over the 16 pixel slices
+    const int st = threadIdx.x >> 6, cc = threadIdx.x & 63;
+    if (blockIdx.x * 64 + cc < C) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) t += s_red[st][k][cc];
+      partial[(((long)b * S + blockIdx.z) * C + blockIdx.x * 64 + cc) * 2 + st] = (float)t;
+    }
   }
 }
 
-// forward statistics: mean / invstd per (episode, channel) + sequential running-stat EMA
-__global__ void bn2d_finalize_kernel(const float* __restrict__ partial, float* __restrict__ mean,
-                                     float* __restrict__ invstd, float* __restrict__ running_mean,
-                                     float* __restrict__ running_var, int E, int ipe, int HW, int C, float momentum,
-                                     float eps) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const double n = (double)ipe * HW;
-  float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 0.f;
-  for (int e = 0; e < E; ++e) {
-    double s = 0.0, q = 0.0;
-    {     // four independent chains: the loads of an episode's per-image partials are in flight together (fixed order)
-      double s4[4] = {0.0, 0.0, 0.0, 0.0}, q4[4] = {0.0, 0.0, 0.0, 0.0};
-      const float2* pp = reinterpret_cast<const float2*>(partial) + ((long)e * ipe) * C + c;
-      int i = 0;
-      for (; i + 4 <= ipe; i += 4) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float2 v = pp[(long)(i + u) * C];
-          s4[u] += (double)v.x;
-          q4[u] += (double)v.y;
-        }
-      }
-      for (; i < ipe; ++i) {
-        const float2 v = pp[(long)i * C];
-        s4[0] += (double)v.x;
-        q4[0] += (double)v.y;
-      }
-      s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
-      q = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+// sum of an episode's `rows` partial rows (images x pixel splits) for 32 channels: 8 slices of the block take every 8th row (loads of different
+// slices are in flight together), then a fixed-order sum over the slices (deterministic).  Call with all 256 threads.
+__device__ __forceinline__ void bn2d_episode_sums(const float* __restrict__ partial, int e, int rows, int C, int c,
+                                                  double (&s_red)[2][8][32], double& s, double& q) {
+  const int cx = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  double a0 = 0.0, a1 = 0.0;
+  if (c < C) {
+    const float2* pp = reinterpret_cast<const float2*>(partial) + ((long)e * rows) * C + c;
+    for (int i = sl; i < rows; i += 8) {
+      const float2 v = pp[(long)i * C];
+      a0 += (double)v.x;
+      a1 += (double)v.y;
     }
-    const double m = s / n;
-    double var = q / n - m * m;
-    if (var < 0.0) var = 0.0;
-    mean[(long)e * C + c] = (float)m;
-    invstd[(long)e * C + c] = (float)(1.0 / sqrt(var + (double)eps));
-    rm = (1.f - momentum) * rm + momentum * (float)m;
-    rv = (1.f - momentum) * rv + momentum * (float)(n > 1.0 ? var * n / (n - 1.0) : var);
   }
-  if (running_mean) running_mean[c] = rm;
-  if (running_var) running_var[c] = rv;
+  __syncthreads();                       // the previous episode's sums have been read
+  s_red[0][sl][cx] = a0;
+  s_red[1][sl][cx] = a1;
+  __syncthreads();
+  s = q = 0.0;
+  if (sl == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s += s_red[0][k][cx];
+      q += s_red[1][k][cx];
+    }
+  }
+}
+
+// forward statistics: mean / invstd per (episode, channel) + sequential running-stat EMA.  Block = 32 channels x 8 slices.
+__global__ void __launch_bounds__(256) bn2d_finalize_kernel(const float* __restrict__ partial, float* __restrict__ mean,
+                                                            float* __restrict__ invstd, float* __restrict__ running_mean,
+                                                            float* __restrict__ running_var, int E, int ipe, int rows,
+                                                            int HW, int C, float momentum, float eps) {
+  __shared__ double s_red[2][8][32];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const bool lead = (threadIdx.x >> 5) == 0 && c < C;
+  const double n = (double)ipe * HW;
+  float rm = (lead && running_mean) ? running_mean[c] : 0.f, rv = (lead && running_var) ? running_var[c] : 0.f;
+  for (int e = 0; e < E; ++e) {
+    double s, q;
+    bn2d_episode_sums(partial, e, rows, C, c, s_red, s, q);
+    if (lead) {
+      const double m = s / n;
+      double var = q / n - m * m;
+      if (var < 0.0) var = 0.0;
+      mean[(long)e * C + c] = (float)m;
+      invstd[(long)e * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+      rm = (1.f - momentum) * rm + momentum * (float)m;
+      rv = (1.f - momentum) * rv + momentum * (float)(n > 1.0 ? var * n / (n - 1.0) : var);
+    }
+  }
+  if (lead && running_mean) running_mean[c] = rm;
+  if (lead && running_var) running_var[c] = rv;
 }
 
 // backward sums: sums[e][c][2] = sum over the episode's images; dgamma / dbeta = sum over episodes
-__global__ void bn2d_bwd_finalize_kernel(const float* __restrict__ partial, float* __restrict__ sums,
-                                         float* __restrict__ dgamma, float* __restrict__ dbeta, int E, int ipe, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+__global__ void __launch_bounds__(256) bn2d_bwd_finalize_kernel(const float* __restrict__ partial, float* __restrict__ sums,
+                                                                float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                int E, int rows, int C) {
+  __shared__ double s_red[2][8][32];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const bool lead = (threadIdx.x >> 5) == 0 && c < C;
   double tg = 0.0, tb = 0.0;
   for (int e = 0; e < E; ++e) {
-    double s = 0.0, q = 0.0;
-    {     // four independent chains: the loads of an episode's per-image partials are in flight together (fixed order)
-      double s4[4] = {0.0, 0.0, 0.0, 0.0}, q4[4] = {0.0, 0.0, 0.0, 0.0};
-      const float2* pp = reinterpret_cast<const float2*>(partial) + ((long)e * ipe) * C + c;
-      int i = 0;
-      for (; i + 4 <= ipe; i += 4) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float2 v = pp[(long)(i + u) * C];
-          s4[u] += (double)v.x;
-          q4[u] += (double)v.y;
-        }
-      }
-      for (; i < ipe; ++i) {
-        const float2 v = pp[(long)i * C];
-        s4[0] += (double)v.x;
-        q4[0] += (double)v.y;
-      }
-      s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
-      q = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+    double s, q;
+    bn2d_episode_sums(partial, e, rows, C, c, s_red, s, q);
+    if (lead) {
+      sums[((long)e * C + c) * 2 + 0] = (float)s;
+      sums[((long)e * C + c) * 2 + 1] = (float)q;
+      tb += s;
+      tg += q;
     }
-    sums[((long)e * C + c) * 2 + 0] = (float)s;
-    sums[((long)e * C + c) * 2 + 1] = (float)q;
-    tb += s;
-    tg += q;
   }
-  dgamma[c] = (float)tg;
-  dbeta[c] = (float)tb;
+  if (lead) {
+    dgamma[c] = (float)tg;
+    dbeta[c] = (float)tb;
+  }
 }
 
 DKTB_EXPORT int dktb_bn2d_stats(const float* x, float* mean, float* invstd, float* running_mean, float* running_var,
                                 float* partial, int B, int HW, int C, int ipe, float momentum, float eps,
                                 cudaStream_t stream) {
   DKTB_CHECK_ARG(x && mean && invstd && partial && B > 0 && HW > 0 && C > 0 && ipe > 0 && B % ipe == 0 && B <= 65535);
-  DKTB_LAUNCH(bn2d_partial_kernel, dim3((C + 63) / 64, B), dim3(256), 0, stream, x, (const float*)nullptr,
+  DKTB_CHECK_ARG(C % 4 == 0);
+  const int S = bn2d_splits(B, HW, C);
+  DKTB_LAUNCH(bn2d_partial_kernel, dim3((C + 63) / 64, B, S), dim3(256), 0, stream, x, (const float*)nullptr,
               (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, partial, HW, C, ipe, 0);
-  DKTB_LAUNCH(bn2d_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, stream, (const float*)partial, mean, invstd,
-              running_mean, running_var, B / ipe, ipe, HW, C, momentum, eps);
+  DKTB_LAUNCH(bn2d_finalize_kernel, dim3((C + 31) / 32), dim3(256), 0, stream, (const float*)partial, mean, invstd,
+              running_mean, running_var, B / ipe, ipe, ipe * S, HW, C, momentum, eps);
   return dktb_launch_status();
 }
 
@@ -225,17 +271,18 @@ __global__ void __launch_bounds__(256) bn2d_bwd_apply_kernel(const float* __rest
 }
 
 // x: BN input; y: block output after add/ReLU (for the ReLU mask; nullable when relu == 0); gy: gradient w.r.t. y.
-// partial: B*C*2 floats, sums: (B/ipe)*C*2 floats.
+// partial: dktb_bn2d_partial_floats(B, HW, C) floats, sums: (B/ipe)*C*2 floats.
 DKTB_EXPORT int dktb_bn2d_bwd(const float* x, const float* y, const float* gy, const float* mean, const float* invstd,
                               const float* gamma, float* gx, float* gres, float* dgamma, float* dbeta, float* partial,
                               float* sums, int B, int HW, int C, int ipe, int relu, cudaStream_t stream) {
   DKTB_CHECK_ARG(x && gy && mean && invstd && gamma && gx && dgamma && dbeta && partial && sums && (!relu || y));
   DKTB_CHECK_ARG(B > 0 && ipe > 0 && B % ipe == 0 && B <= 65535);
-  DKTB_LAUNCH(bn2d_partial_kernel, dim3((C + 63) / 64, B), dim3(256), 0, stream, x, gy, relu ? y : (const float*)nullptr,
-              mean, invstd, partial, HW, C, ipe, 1);
-  DKTB_LAUNCH(bn2d_bwd_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, stream, (const float*)partial, sums, dgamma,
-              dbeta, B / ipe, ipe, C);
   DKTB_CHECK_ARG(C % 4 == 0);
+  const int S = bn2d_splits(B, HW, C);
+  DKTB_LAUNCH(bn2d_partial_kernel, dim3((C + 63) / 64, B, S), dim3(256), 0, stream, x, gy, relu ? y : (const float*)nullptr,
+              mean, invstd, partial, HW, C, ipe, 1);
+  DKTB_LAUNCH(bn2d_bwd_finalize_kernel, dim3((C + 31) / 32), dim3(256), 0, stream, (const float*)partial, sums, dgamma,
+              dbeta, B / ipe, ipe * S, C);
   const long total4 = (long)B * HW * C / 4;
   DKTB_LAUNCH(bn2d_bwd_apply_kernel, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, stream, x, y, gy, mean, invstd,
               gamma, (const float*)sums, gx, gres, total4, HW, C, ipe, relu, 1.0f / ((float)ipe * (float)HW));

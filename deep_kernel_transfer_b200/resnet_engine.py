@@ -107,7 +107,7 @@ class ResNetEngine:
         E = B // ipe if training else 1
         mean, invstd = self._new(E, C), self._new(E, C)
         if training:
-            partial = self._new(B * C * 2)
+            partial = self._new(self.lib.bn2d_partial_floats(B, H * W, C))
             self.lib.bn2d_stats(x, mean, invstd, m.running_mean, m.running_var, partial, B, H * W, C, ipe, BN_MOMENTUM,
                                 BN_EPS, st)
         else:
@@ -190,7 +190,7 @@ class ResNetEngine:
                 gy = grads.pop(y.data_ptr())
                 gx = torch.empty_like(x)
                 gres = torch.empty_like(x) if res is not None else None
-                partial = self._new(B * C * 2)
+                partial = self._new(self.lib.bn2d_partial_floats(B, H * W, C))
                 sums = self._new((B // ipe) * C * 2)
                 lib.bn2d_bwd(x, y, gy, mean, invstd, m.weight.data, gx, gres, m.weight.grad, m.bias.grad, partial, sums, B,
                              H * W, C, ipe, relu, st)

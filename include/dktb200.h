@@ -167,8 +167,9 @@ int dktb_bn_relu_pool_bwd(const float* y, const float* gout, const float* mean, 
 
 /* ---- channel-generic NHWC blocks of the ResNet backbones (backbone.py:135-247, 330-376): BatchNorm2d with per-episode
  * batch statistics for any C (multiple of 4), optional fused residual add + ReLU; MaxPool2d(3,2,1); global AvgPool. */
+long dktb_bn2d_partial_floats(int B, int HW, int C);   /* size of `partial` below (images x pixel splits x C x 2) */
 int dktb_bn2d_stats(const float* x, float* mean, float* invstd, float* running_mean, float* running_var, float* partial,
-                    int B, int HW, int C, int ipe, float momentum, float eps, cudaStream_t stream);   /* partial: B*C*2 */
+                    int B, int HW, int C, int ipe, float momentum, float eps, cudaStream_t stream);
 int dktb_bn2d_apply(const float* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
                     const float* res, float* y, int B, int HW, int C, int ipe, int relu, cudaStream_t stream);
 int dktb_bn2d_bwd(const float* x, const float* y, const float* gy, const float* mean, const float* invstd,

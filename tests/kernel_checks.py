@@ -641,7 +641,7 @@ def check_resnet_ops(lib, dev, E=2, ipe=2, H=9, W=7, C=8, seed=80):
         xd, rd, gyd = nh(x), nh(res), nh(gy)
         mean, invstd = torch.empty(E, C, device=dev), torch.empty(E, C, device=dev)
         drm, drv = rm0.clone().to(dev), rv0.clone().to(dev)
-        partial = torch.empty(B * C * 2, device=dev)
+        partial = torch.empty(lib.bn2d_partial_floats(B, H * W, C), device=dev)
         lib.bn2d_stats(xd, mean, invstd, drm, drv, partial, B, H * W, C, ipe, 0.1, 1e-5, 0)
         _close(drm, rm, what="bn2d running_mean")
         _close(drv, rv, what="bn2d running_var")

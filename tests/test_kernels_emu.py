@@ -90,6 +90,7 @@ def test_spectral(lib):
 
 def test_resnet_ops(lib):
     kc.check_resnet_ops(lib, DEV)
+    kc.check_resnet_ops(lib, DEV, E=2, ipe=2, H=24, W=23, C=8, seed=82)       # BatchNorm sums split over the pixels (2 splits)
 
 
 def test_episode_transform(lib):

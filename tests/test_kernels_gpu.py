@@ -122,6 +122,7 @@ def test_conv1_tc(lib):
 def test_resnet_ops(lib):
     kc.check_resnet_ops(lib, DEV)
     kc.check_resnet_ops(lib, DEV, E=2, ipe=3, H=14, W=14, C=256, seed=81)
+    kc.check_resnet_ops(lib, DEV, E=2, ipe=2, H=32, W=33, C=64, seed=82)      # BatchNorm sums split over the pixels (4 splits)
 
 
 @pytest.mark.parametrize("cfg", [dict(), dict(B=3, H=56, W=56, Cin=64, Cout=64, seed=101),          # ResNet18 layer1
