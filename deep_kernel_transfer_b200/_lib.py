@@ -90,6 +90,10 @@ SIGNATURES = {
     "dktb_spectral_bwd": ("ppppppppppiiiiiis", ctypes.c_int),
     "dktb_bn2d_partial_floats": ("iii", ctypes.c_long),
     "dktb_bn2d_stats": ("ppppppiiiiffs", ctypes.c_int),
+    "dktb_bn2d_stats_l": ("ppppppiiiiffiis", ctypes.c_int),
+    "dktb_bn2d_apply_l": ("pppppppiiiiiiis", ctypes.c_int),
+    "dktb_bn2d_bwd_l": ("ppppppppppppiiiiiiis", ctypes.c_int),
+    "dktb_add_inplace_l": ("ppiiiiis", ctypes.c_int),
     "dktb_bn2d_apply": ("pppppppiiiiis", ctypes.c_int),
     "dktb_bn2d_bwd": ("ppppppppppppiiiiis", ctypes.c_int),
     "dktb_maxpool3_fwd": ("pppiiiis", ctypes.c_int),

@@ -4,6 +4,21 @@
 // element-wise / reduction kernels; reductions are two-stage with a fixed order (deterministic).
 #include "dktb_common.cuh"
 
+// ------------------------------------------------------------------------------------------------ tensor layouts
+// Every NHWC tensor argument of the *_l entry points is either dense [B][H][W][C] or the INTERIOR of a padded-flat buffer
+// [B][H+2][W+2][C] (pointer = buffer base; the layout the tcgen05 convolutions of csrc/conv_tcg.cu read and write, so that
+// no copy separates them from the element-wise kernels).  `lay` holds one bit per argument; the border of a padded buffer
+// is never read or written here.
+enum { kLayX = 1, kLayY = 2, kLayGy = 4, kLayGx = 8, kLayRes = 16 };
+struct NhwcGeom { int HW, W, HWp; };        // HWp = (H + 2) * (W + 2)
+// global pixel index (b * HW + p) -> padded-flat row index
+__device__ __forceinline__ long padded_row(long pix, const NhwcGeom& gm) {
+  const long b = pix / gm.HW;
+  const int p = (int)(pix - b * gm.HW);
+  const int h = p / gm.W, w = p - h * gm.W;
+  return b * gm.HWp + (long)(h + 1) * (gm.W + 2) + (w + 1);
+}
+
 // ------------------------------------------------------------------------------------------------ BN statistics
 // pixel splits per image: enough CTAs to fill the machine when B x C / 64 alone does not (the 64-channel layers at 56x56 /
 // 112x112 hold most of the bytes); a split is one more row of `partial`, summed by the finalize kernels in a fixed order
@@ -22,7 +37,7 @@ DKTB_EXPORT long dktb_bn2d_partial_floats(int B, int HW, int C) { return (long)B
 __global__ void __launch_bounds__(256) bn2d_partial_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                            const float* __restrict__ y, const float* __restrict__ mean,
                                                            const float* __restrict__ invstd, float* __restrict__ partial,
-                                                           int HW, int C, int ipe, int mode) {
+                                                           int HW, int C, int ipe, int mode, NhwcGeom gm, int lay) {
   // mode 0: (x, x^2);  mode 1 (backward): g' = g * (y > 0 if y given), (g', g' * xhat)
   // Sums in DOUBLE: dbeta / dgamma (and the batch mean) are sums of up to 12 544 signed terms per image that largely cancel
   // (cond = sum|t| / |sum t| ~ 1e2 .. 1e3 for the first layers' gradients); a sequential float32 chain over HW / 4 pixels
@@ -42,7 +57,9 @@ __global__ void __launch_bounds__(256) bn2d_partial_kernel(const float* __restri
       m = dktb_ld4(mean + (long)e * C + c);
       is = dktb_ld4(invstd + (long)e * C + c);
     }
-    const long base = (long)b * HW * C + c;
+    const long xb = ((lay & kLayX) ? (long)b * gm.HWp : (long)b * HW) * C + c;
+    const long gb = ((lay & kLayGy) ? (long)b * gm.HWp : (long)b * HW) * C + c;
+    const long yb = ((lay & kLayY) ? (long)b * gm.HWp : (long)b * HW) * C + c;
     for (int p0 = p_lo + ps; p0 < p_hi; p0 += 16 * 8) {
       float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
 #pragma unroll
@@ -52,11 +69,16 @@ __global__ void __launch_bounds__(256) bn2d_partial_kernel(const float* __restri
         for (int u = 0; u < 4; ++u) {
           const int p = p0 + 16 * (4 * h + u);
           const bool in = p < p_hi;
-          const long off = base + (long)(in ? p : p_lo) * C;
-          xv[u] = dktb_ld4(x + off);
+          const int pd = in ? p : p_lo;
+          int pp = pd;                                      // pixel index inside a padded image
+          if (lay) {
+            const int h = pd / gm.W;
+            pp = (h + 1) * (gm.W + 2) + (pd - h * gm.W) + 1;
+          }
+          xv[u] = dktb_ld4(x + xb + (long)((lay & kLayX) ? pp : pd) * C);
           if (mode == 1) {
-            gv[u] = dktb_ld4(g + off);
-            if (y != nullptr) yv[u] = dktb_ld4(y + off);
+            gv[u] = dktb_ld4(g + gb + (long)((lay & kLayGy) ? pp : pd) * C);
+            if (y != nullptr) yv[u] = dktb_ld4(y + yb + (long)((lay & kLayY) ? pp : pd) * C);
           }
           if (!in) {
             xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -183,17 +205,32 @@ __global__ void __launch_bounds__(256) bn2d_bwd_finalize_kernel(const float* __r
   }
 }
 
-DKTB_EXPORT int dktb_bn2d_stats(const float* x, float* mean, float* invstd, float* running_mean, float* running_var,
-                                float* partial, int B, int HW, int C, int ipe, float momentum, float eps,
-                                cudaStream_t stream) {
+static NhwcGeom nhwc_geom(int HW, int W) {
+  NhwcGeom gm;
+  gm.HW = HW;
+  gm.W = W > 0 ? W : HW;
+  gm.HWp = (HW / gm.W + 2) * (gm.W + 2);
+  return gm;
+}
+
+// W, lay: see "tensor layouts" above (lay = 0: every tensor dense, W unused)
+DKTB_EXPORT int dktb_bn2d_stats_l(const float* x, float* mean, float* invstd, float* running_mean, float* running_var,
+                                  float* partial, int B, int HW, int C, int ipe, float momentum, float eps, int W, int lay,
+                                  cudaStream_t stream) {
   DKTB_CHECK_ARG(x && mean && invstd && partial && B > 0 && HW > 0 && C > 0 && ipe > 0 && B % ipe == 0 && B <= 65535);
-  DKTB_CHECK_ARG(C % 4 == 0);
+  DKTB_CHECK_ARG(C % 4 == 0 && (lay == 0 || (W > 0 && HW % W == 0)));
   const int S = bn2d_splits(B, HW, C);
   DKTB_LAUNCH(bn2d_partial_kernel, dim3((C + 63) / 64, B, S), dim3(256), 0, stream, x, (const float*)nullptr,
-              (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, partial, HW, C, ipe, 0);
+              (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, partial, HW, C, ipe, 0, nhwc_geom(HW, W),
+              lay);
   DKTB_LAUNCH(bn2d_finalize_kernel, dim3((C + 31) / 32), dim3(256), 0, stream, (const float*)partial, mean, invstd,
               running_mean, running_var, B / ipe, ipe, ipe * S, HW, C, momentum, eps);
   return dktb_launch_status();
+}
+DKTB_EXPORT int dktb_bn2d_stats(const float* x, float* mean, float* invstd, float* running_mean, float* running_var,
+                                float* partial, int B, int HW, int C, int ipe, float momentum, float eps,
+                                cudaStream_t stream) {
+  return dktb_bn2d_stats_l(x, mean, invstd, running_mean, running_var, partial, B, HW, C, ipe, momentum, eps, 0, 0, stream);
 }
 
 // y = act( (x - mean) * invstd * gamma + beta (+ res) );  stats row = img / ipe (ipe == 0: row 0, eval mode)
@@ -201,13 +238,15 @@ __global__ void __launch_bounds__(256) bn2d_apply_kernel(const float* __restrict
                                                          const float* __restrict__ invstd,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                                          const float* __restrict__ res, float* __restrict__ y, long total4,
-                                                         int HW, int C, int ipe, int relu) {
+                                                         int HW, int C, int ipe, int relu, NhwcGeom gm, int lay) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const int c4 = (int)(i % (C / 4)) * 4;
   const long pix = i / (C / 4);
   const int e = ipe > 0 ? (int)(pix / HW / ipe) : 0;
-  const float4 v = dktb_ld4(x + i * 4);
+  const long prow = lay ? padded_row(pix, gm) : pix;
+  const long ix = ((lay & kLayX) ? prow : pix) * C + c4, iy = ((lay & kLayY) ? prow : pix) * C + c4;
+  const float4 v = dktb_ld4(x + ix);
   const float4 m = dktb_ld4(mean + (long)e * C + c4), is = dktb_ld4(invstd + (long)e * C + c4);
   const float4 g = dktb_ld4(gamma + c4), bt = dktb_ld4(beta + c4);
   float4 o;
@@ -216,21 +255,27 @@ __global__ void __launch_bounds__(256) bn2d_apply_kernel(const float* __restrict
   o.z = fmaf(v.z - m.z, is.z * g.z, bt.z);
   o.w = fmaf(v.w - m.w, is.w * g.w, bt.w);
   if (res != nullptr) {
-    const float4 r = dktb_ld4(res + i * 4);
+    const float4 r = dktb_ld4(res + ((lay & kLayRes) ? prow : pix) * C + c4);
     o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
   }
   if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-  dktb_st4(y + i * 4, o);
+  dktb_st4(y + iy, o);
 }
 
+DKTB_EXPORT int dktb_bn2d_apply_l(const float* x, const float* mean, const float* invstd, const float* gamma,
+                                  const float* beta, const float* res, float* y, int B, int HW, int C, int ipe, int relu,
+                                  int W, int lay, cudaStream_t stream) {
+  DKTB_CHECK_ARG(x && mean && invstd && gamma && beta && y && B > 0 && HW > 0 && C > 0 && C % 4 == 0);
+  DKTB_CHECK_ARG(lay == 0 || (W > 0 && HW % W == 0));
+  const long total4 = (long)B * HW * C / 4;
+  DKTB_LAUNCH(bn2d_apply_kernel, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, stream, x, mean, invstd, gamma,
+              beta, res, y, total4, HW, C, ipe, relu, nhwc_geom(HW, W), lay);
+  return dktb_launch_status();
+}
 DKTB_EXPORT int dktb_bn2d_apply(const float* x, const float* mean, const float* invstd, const float* gamma,
                                 const float* beta, const float* res, float* y, int B, int HW, int C, int ipe, int relu,
                                 cudaStream_t stream) {
-  DKTB_CHECK_ARG(x && mean && invstd && gamma && beta && y && B > 0 && HW > 0 && C > 0 && C % 4 == 0);
-  const long total4 = (long)B * HW * C / 4;
-  DKTB_LAUNCH(bn2d_apply_kernel, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, stream, x, mean, invstd, gamma,
-              beta, res, y, total4, HW, C, ipe, relu);
-  return dktb_launch_status();
+  return dktb_bn2d_apply_l(x, mean, invstd, gamma, beta, res, y, B, HW, C, ipe, relu, 0, 0, stream);
 }
 
 // gx = gamma*invstd*(g' - s1/n - xhat*s2/n),  g' = gy * (y > 0) when relu;  gres (nullable) = g'
@@ -240,7 +285,7 @@ __global__ void __launch_bounds__(256) bn2d_bwd_apply_kernel(const float* __rest
                                                              const float* __restrict__ gamma,
                                                              const float* __restrict__ sums, float* __restrict__ gx,
                                                              float* __restrict__ gres, long total4, int HW, int C, int ipe,
-                                                             int relu, float inv_n) {
+                                                             int relu, float inv_n, NhwcGeom gm, int lay) {
   // four channels per thread (C % 4 == 0): 16-byte loads / stores, one index decomposition per four elements
   const long i4 = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i4 >= total4) return;
@@ -248,45 +293,52 @@ __global__ void __launch_bounds__(256) bn2d_bwd_apply_kernel(const float* __rest
   const int c = (int)(i4 % c4n) * 4;
   const long pix = i4 / c4n;
   const int e = (int)(pix / ((long)HW * ipe));
-  const long i = i4 * 4;
-  float4 g = dktb_ld4(gy + i);
+  const long prow = lay ? padded_row(pix, gm) : pix;
+  float4 g = dktb_ld4(gy + ((lay & kLayGy) ? prow : pix) * C + c);
   if (relu) {
-    const float4 yy = dktb_ld4(y + i);
+    const float4 yy = dktb_ld4(y + ((lay & kLayY) ? prow : pix) * C + c);
     if (!(yy.x > 0.f)) g.x = 0.f;
     if (!(yy.y > 0.f)) g.y = 0.f;
     if (!(yy.z > 0.f)) g.z = 0.f;
     if (!(yy.w > 0.f)) g.w = 0.f;
   }
-  const float4 xv = dktb_ld4(x + i);
-  const float4 m = dktb_ld4(mean + (long)e * C + c), is = dktb_ld4(invstd + (long)e * C + c), gm = dktb_ld4(gamma + c);
+  const float4 xv = dktb_ld4(x + ((lay & kLayX) ? prow : pix) * C + c);
+  const float4 m = dktb_ld4(mean + (long)e * C + c), is = dktb_ld4(invstd + (long)e * C + c), gw = dktb_ld4(gamma + c);
   const float* sp = sums + ((long)e * C + c) * 2;
   const float4 sa = dktb_ld4(sp), sb = dktb_ld4(sp + 4);      // (s1, s2) pairs of channels c, c+1 | c+2, c+3
   float4 o;
-  o.x = gm.x * is.x * (g.x - sa.x * inv_n - (xv.x - m.x) * is.x * (sa.y * inv_n));
-  o.y = gm.y * is.y * (g.y - sa.z * inv_n - (xv.y - m.y) * is.y * (sa.w * inv_n));
-  o.z = gm.z * is.z * (g.z - sb.x * inv_n - (xv.z - m.z) * is.z * (sb.y * inv_n));
-  o.w = gm.w * is.w * (g.w - sb.z * inv_n - (xv.w - m.w) * is.w * (sb.w * inv_n));
-  dktb_st4(gx + i, o);
-  if (gres != nullptr) dktb_st4(gres + i, g);
+  o.x = gw.x * is.x * (g.x - sa.x * inv_n - (xv.x - m.x) * is.x * (sa.y * inv_n));
+  o.y = gw.y * is.y * (g.y - sa.z * inv_n - (xv.y - m.y) * is.y * (sa.w * inv_n));
+  o.z = gw.z * is.z * (g.z - sb.x * inv_n - (xv.z - m.z) * is.z * (sb.y * inv_n));
+  o.w = gw.w * is.w * (g.w - sb.z * inv_n - (xv.w - m.w) * is.w * (sb.w * inv_n));
+  dktb_st4(gx + ((lay & kLayGx) ? prow : pix) * C + c, o);
+  if (gres != nullptr) dktb_st4(gres + ((lay & kLayRes) ? prow : pix) * C + c, g);
 }
 
 // x: BN input; y: block output after add/ReLU (for the ReLU mask; nullable when relu == 0); gy: gradient w.r.t. y.
 // partial: dktb_bn2d_partial_floats(B, HW, C) floats, sums: (B/ipe)*C*2 floats.
-DKTB_EXPORT int dktb_bn2d_bwd(const float* x, const float* y, const float* gy, const float* mean, const float* invstd,
-                              const float* gamma, float* gx, float* gres, float* dgamma, float* dbeta, float* partial,
-                              float* sums, int B, int HW, int C, int ipe, int relu, cudaStream_t stream) {
+DKTB_EXPORT int dktb_bn2d_bwd_l(const float* x, const float* y, const float* gy, const float* mean, const float* invstd,
+                                const float* gamma, float* gx, float* gres, float* dgamma, float* dbeta, float* partial,
+                                float* sums, int B, int HW, int C, int ipe, int relu, int W, int lay, cudaStream_t stream) {
   DKTB_CHECK_ARG(x && gy && mean && invstd && gamma && gx && dgamma && dbeta && partial && sums && (!relu || y));
   DKTB_CHECK_ARG(B > 0 && ipe > 0 && B % ipe == 0 && B <= 65535);
-  DKTB_CHECK_ARG(C % 4 == 0);
+  DKTB_CHECK_ARG(C % 4 == 0 && (lay == 0 || (W > 0 && HW % W == 0)));
   const int S = bn2d_splits(B, HW, C);
+  const NhwcGeom gm = nhwc_geom(HW, W);
   DKTB_LAUNCH(bn2d_partial_kernel, dim3((C + 63) / 64, B, S), dim3(256), 0, stream, x, gy, relu ? y : (const float*)nullptr,
-              mean, invstd, partial, HW, C, ipe, 1);
+              mean, invstd, partial, HW, C, ipe, 1, gm, lay);
   DKTB_LAUNCH(bn2d_bwd_finalize_kernel, dim3((C + 31) / 32), dim3(256), 0, stream, (const float*)partial, sums, dgamma,
               dbeta, B / ipe, ipe * S, C);
   const long total4 = (long)B * HW * C / 4;
   DKTB_LAUNCH(bn2d_bwd_apply_kernel, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, stream, x, y, gy, mean, invstd,
-              gamma, (const float*)sums, gx, gres, total4, HW, C, ipe, relu, 1.0f / ((float)ipe * (float)HW));
+              gamma, (const float*)sums, gx, gres, total4, HW, C, ipe, relu, 1.0f / ((float)ipe * (float)HW), gm, lay);
   return dktb_launch_status();
+}
+DKTB_EXPORT int dktb_bn2d_bwd(const float* x, const float* y, const float* gy, const float* mean, const float* invstd,
+                              const float* gamma, float* gx, float* gres, float* dgamma, float* dbeta, float* partial,
+                              float* sums, int B, int HW, int C, int ipe, int relu, cudaStream_t stream) {
+  return dktb_bn2d_bwd_l(x, y, gy, mean, invstd, gamma, gx, gres, dgamma, dbeta, partial, sums, B, HW, C, ipe, relu, 0, 0,
+                         stream);
 }
 
 // ------------------------------------------------------------------------------------------------ pooling
@@ -421,5 +473,27 @@ __global__ void add_inplace_kernel(float* __restrict__ a, const float* __restric
 DKTB_EXPORT int dktb_add_inplace(float* a, const float* b, long n, cudaStream_t stream) {
   DKTB_CHECK_ARG(a && b && n > 0);
   DKTB_LAUNCH(add_inplace_kernel, dim3((unsigned)((n / 4 + 256) / 256)), dim3(256), 0, stream, a, b, n);
+  return dktb_launch_status();
+}
+
+// a += b over NHWC tensors of either layout (lay: kLayX = a padded, kLayY = b padded); C % 4 == 0
+__global__ void __launch_bounds__(256) add_inplace_l_kernel(float* __restrict__ a, const float* __restrict__ b, long total4,
+                                                            int C, NhwcGeom gm, int lay) {
+  const long i4 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 >= total4) return;
+  const int c4n = C >> 2;
+  const int c = (int)(i4 % c4n) * 4;
+  const long pix = i4 / c4n;
+  const long prow = padded_row(pix, gm);
+  float* pa = a + ((lay & kLayX) ? prow : pix) * C + c;
+  const float4 x = dktb_ld4(pa), y = dktb_ld4(b + ((lay & kLayY) ? prow : pix) * C + c);
+  dktb_st4(pa, make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w));
+}
+DKTB_EXPORT int dktb_add_inplace_l(float* a, const float* b, int B, int HW, int C, int W, int lay, cudaStream_t stream) {
+  DKTB_CHECK_ARG(a && b && B > 0 && HW > 0 && C > 0 && C % 4 == 0 && W > 0 && HW % W == 0);
+  if (lay == 0) return dktb_add_inplace(a, b, (long)B * HW * C, stream);
+  const long total4 = (long)B * HW * C / 4;
+  DKTB_LAUNCH(add_inplace_l_kernel, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, stream, a, b, total4, C,
+              nhwc_geom(HW, W), lay);
   return dktb_launch_status();
 }

@@ -43,6 +43,51 @@ class ResNetEngine:
             self._pads[key] = torch.zeros(B, H + 2, W + 2, C, device=self.dev)
         return self._pads[key]
 
+    # Activations / gradients of the tcgen05 3x3 layers live in padded-flat buffers [B, H+2, W+2, C]; the engine hands
+    # their INTERIOR VIEW around (logical shape [B, H, W, C], non-contiguous), the kernels get the buffer base plus a layout
+    # bit per tensor (dktb_*_l entry points), so no copy separates a convolution from the BatchNorm around it.
+    @staticmethod
+    def _is_pad(t):
+        return t is not None and t.dim() == 4 and not t.is_contiguous()
+
+    @staticmethod
+    def _base(t):
+        return t._base if ResNetEngine._is_pad(t) else t
+
+    def _newpad(self, B, H, W, C, zero=True):
+        """Interior view of a fresh padded-flat buffer; zero: the border is cleared (needed when a convolution reads it)."""
+        buf = self._new(B, H + 2, W + 2, C)
+        if zero:
+            self.lib.zero_border(buf, B, H, W, C, _stream(self.dev))
+        return buf[:, 1:-1, 1:-1, :]
+
+    def _like(self, t):
+        """Gradient buffer in the layout of its activation."""
+        if self._is_pad(t):
+            return self._newpad(*t.shape)
+        return torch.empty(t.shape, device=self.dev, dtype=t.dtype)
+
+    def _dense(self, t):
+        if not self._is_pad(t):
+            return t
+        B, H, W, C = t.shape
+        d = self._new(B, H, W, C)
+        self.lib.pad_copy(d, t._base, B, H, W, C, 1, _stream(self.dev))
+        return d
+
+    def _padded_base(self, t, role):
+        """Padded-flat buffer holding t: its own one, or a persistent scratch buffer filled by pad_copy."""
+        if self._is_pad(t):
+            return t._base
+        B, H, W, C = t.shape
+        buf = self._padbuf(role, B, H, W, C)
+        self.lib.pad_copy(t, buf, B, H, W, C, 0, _stream(self.dev))
+        return buf
+
+    def _lay(self, x=None, y=None, gy=None, gx=None, res=None):
+        return (1 if self._is_pad(x) else 0) | (2 if self._is_pad(y) else 0) | (4 if self._is_pad(gy) else 0) | \
+            (8 if self._is_pad(gx) else 0) | (16 if self._is_pad(res) else 0)
+
     def _tcg_weights(self, m):
         key = ("tcg", id(m))
         if key not in self._mma_w:
@@ -60,7 +105,6 @@ class ResNetEngine:
         st, pad, dil = m.stride[0], m.padding[0], m.dilation[0]
         Ho = self.lib.conv2d_out_size(H, R, st, pad, dil)
         Wo = self.lib.conv2d_out_size(W, R, st, pad, dil)
-        out = self._new(B, Ho, Wo, m.out_channels)
         bias = m.bias.data if m.bias is not None else None
         if not relu and self._tcg_ok(m, W):
             # tcgen05: 3x3 over padded-flat buffers (the zero border is the padding), 1x1 as a GEMM over the dense rows
@@ -68,28 +112,31 @@ class ResNetEngine:
             wf, wd = self._tcg_weights(m)
             self.lib.prep_weights_tcg(m.weight.data, wf, wd, Cout, Cin, R, sm)
             if R == 3:
-                xp, yp = self._padbuf("in", B, H, W, Cin), self._padbuf("out", B, H, W, Cout)
-                self.lib.pad_copy(x, xp, B, H, W, Cin, 0, sm)
-                self.lib.conv_tcg(xp, wf, bias, yp, self.tc_err, B, H, W, Cin, Cout, R, sm)
-                self.lib.pad_copy(out, yp, B, H, W, Cout, 1, sm)
+                out = self._newpad(B, H, W, Cout, zero=False)        # only its interior is ever read (BatchNorm follows)
+                self.lib.conv_tcg(self._padded_base(x, "in"), wf, bias, out._base, self.tc_err, B, H, W, Cin, Cout, R, sm)
             else:
-                self.lib.conv_tcg(x, wf, bias, out, self.tc_err, B, H, W, Cin, Cout, R, sm)
-        elif not relu and self.lib.conv2d_mma_ok(Cin, m.out_channels):
+                out = self._new(B, Ho, Wo, Cout)
+                self.lib.conv_tcg(self._dense(x), wf, bias, out, self.tc_err, B, H, W, Cin, Cout, R, sm)
+            self.tape.append(("conv", x, out, m, (B, H, W, Cin, R, st, pad, dil)))
+            return out
+        out = self._new(B, Ho, Wo, m.out_channels)
+        xd = self._dense(x)
+        if not relu and self.lib.conv2d_mma_ok(Cin, m.out_channels):
             # tensor-core tiles (mma.sync 3xTF32): refresh the two k-contiguous weight copies, then forward from `wf`;
             # the backward of the same step reads `wd`
             wf, wd = self._mma_weights(m)
             self.lib.conv2d_prep_mma(m.weight.data, wf, wd, m.out_channels, Cin, R, R, _stream(self.dev))
-            self.lib.conv2d_fwd_mma(x, wf, bias, out, B, H, W, Cin, m.out_channels, R, R, st, pad, dil, _stream(self.dev))
+            self.lib.conv2d_fwd_mma(xd, wf, bias, out, B, H, W, Cin, m.out_channels, R, R, st, pad, dil, _stream(self.dev))
         elif not relu and Cin < 16 and self.lib.conv2d_mma_ok(32, 32):
             # the stem: reduction over the flattened (r, s, ci) index
             key = ("flat", id(m))
             if key not in self._mma_w:
                 self._mma_w[key] = self._new(m.out_channels * self.lib.conv2d_flat_k(Cin, R, R))
             self.lib.conv2d_prep_flat_mma(m.weight.data, self._mma_w[key], m.out_channels, Cin, R, R, _stream(self.dev))
-            self.lib.conv2d_fwd_flat_mma(x, self._mma_w[key], bias, out, B, H, W, Cin, m.out_channels, R, R, st, pad, dil,
+            self.lib.conv2d_fwd_flat_mma(xd, self._mma_w[key], bias, out, B, H, W, Cin, m.out_channels, R, R, st, pad, dil,
                                          _stream(self.dev))
         else:
-            self.lib.conv2d_fwd(x, m.weight.data, bias, out, B, H, W, Cin, m.out_channels, R, R, st, pad, dil, relu,
+            self.lib.conv2d_fwd(xd, m.weight.data, bias, out, B, H, W, Cin, m.out_channels, R, R, st, pad, dil, relu,
                                 _stream(self.dev))
         self.tape.append(("conv", x, out, m, (B, H, W, Cin, R, st, pad, dil)))
         return out
@@ -101,22 +148,28 @@ class ResNetEngine:
             self._mma_w[key] = (self._new(n), self._new(n))
         return self._mma_w[key]
 
-    def _bn(self, x, m, ipe, training, res=None, relu=0):
+    def _bn(self, x, m, ipe, training, res=None, relu=0, pad_out=False):
+        """pad_out: write the output into a zero-bordered padded-flat buffer (its consumer is a tcgen05 3x3 layer)."""
         B, H, W, C = x.shape
         st = _stream(self.dev)
         E = B // ipe if training else 1
         mean, invstd = self._new(E, C), self._new(E, C)
+        y = self._newpad(B, H, W, C) if pad_out else self._new(B, H, W, C)
+        lay = self._lay(x=x, y=y, res=res)
         if training:
             partial = self._new(self.lib.bn2d_partial_floats(B, H * W, C))
-            self.lib.bn2d_stats(x, mean, invstd, m.running_mean, m.running_var, partial, B, H * W, C, ipe, BN_MOMENTUM,
-                                BN_EPS, st)
+            self.lib.bn2d_stats_l(self._base(x), mean, invstd, m.running_mean, m.running_var, partial, B, H * W, C, ipe,
+                                  BN_MOMENTUM, BN_EPS, W, lay, st)
         else:
             self.lib.bn_eval_prepare(m.running_mean, m.running_var, mean, invstd, C, BN_EPS, st)
-        y = self._new(B, H, W, C)
-        self.lib.bn2d_apply(x, mean, invstd, m.weight.data, m.bias.data, res, y, B, H * W, C, ipe if training else 0, relu,
-                            st)
+        self.lib.bn2d_apply_l(self._base(x), mean, invstd, m.weight.data, m.bias.data, self._base(res), self._base(y), B,
+                              H * W, C, ipe if training else 0, relu, W, lay, st)
         self.tape.append(("bn", x, y, m, mean, invstd, res, relu, ipe))
         return y
+
+    def _feeds_tcg3(self, conv, W):
+        """Is `conv` a 3x3 layer of the tcgen05 kernel at row width W (then its input should be produced padded)?"""
+        return conv.kernel_size[0] == 3 and self._tcg_ok(conv, W)
 
     # ------------------------------------------------------------------ forward
     def forward(self, x, ipe, training):
@@ -136,19 +189,23 @@ class ResNetEngine:
         lib.maxpool3_fwd(out, pooled, idx, Bq, Hq, Wq, Cq, st)
         self.tape.append(("maxpool", out, pooled, idx))
         out = pooled
-        for blk in net.blocks():
+        blocks = list(net.blocks())
+        for bi, blk in enumerate(blocks):
+            nxt = blocks[bi + 1] if bi + 1 < len(blocks) else None
             if blk.kind == "simple":
                 o = self._conv(out, blk.C1)
-                o = self._bn(o, blk.BN1, ipe, training, relu=1)
+                o = self._bn(o, blk.BN1, ipe, training, relu=1, pad_out=self._feeds_tcg3(blk.C2, o.shape[2]))
                 o = self._conv(o, blk.C2)
                 if blk.shortcut_type == "identity":
                     sh = out
                 else:
                     sh = self._bn(self._conv(out, blk.shortcut), blk.BNshortcut, ipe, training, relu=0)
-                out = self._bn(o, blk.BN2, ipe, training, res=sh, relu=1)
+                out = self._bn(o, blk.BN2, ipe, training, res=sh, relu=1,
+                               pad_out=nxt is not None and self._feeds_tcg3(nxt.C1, o.shape[2]))
             else:
                 sh = out if blk.shortcut_type == "identity" else self._conv(out, blk.shortcut)
-                o = self._bn(self._conv(out, blk.C1), blk.BN1, ipe, training, relu=1)
+                o = self._conv(out, blk.C1)
+                o = self._bn(o, blk.BN1, ipe, training, relu=1, pad_out=self._feeds_tcg3(blk.C2, o.shape[2]))
                 o = self._bn(self._conv(o, blk.C2), blk.BN2, ipe, training, relu=1)
                 out = self._bn(self._conv(o, blk.C3), blk.BN3, ipe, training, res=sh, relu=1)
         Bq, Hq, Wq, Cq = out.shape
@@ -165,10 +222,14 @@ class ResNetEngine:
 
         def give(t, g):
             k = t.data_ptr()
-            if k in grads:
-                lib.add_inplace(grads[k], g, g.numel(), st)
-            else:
+            if k not in grads:
                 grads[k] = g
+            elif g.dim() == 4:
+                a = grads[k]
+                lib.add_inplace_l(self._base(a), self._base(g), g.shape[0], g.shape[1] * g.shape[2], g.shape[3], g.shape[2],
+                                  self._lay(x=a, y=g), st)
+            else:
+                lib.add_inplace(grads[k], g, g.numel(), st)
 
         last = self.tape[-1]
         give(last[2], gfeat.contiguous())
@@ -176,24 +237,25 @@ class ResNetEngine:
             kind = rec[0]
             if kind == "avgpool":
                 _, x, y = rec
-                gx = torch.empty_like(x)
+                gx = self._new(*x.shape)
                 lib.avgpool_bwd(grads.pop(y.data_ptr()), gx, x.shape[0], x.shape[1] * x.shape[2], x.shape[3], st)
                 give(x, gx)
             elif kind == "maxpool":
                 _, x, y, idx = rec
-                gx = torch.empty_like(x)
-                lib.maxpool3_bwd(grads.pop(y.data_ptr()), idx, gx, x.shape[0], x.shape[1], x.shape[2], x.shape[3], st)
+                gx = self._new(*x.shape)
+                lib.maxpool3_bwd(self._dense(grads.pop(y.data_ptr())), idx, gx, x.shape[0], x.shape[1], x.shape[2], x.shape[3], st)
                 give(x, gx)
             elif kind == "bn":
                 _, x, y, m, mean, invstd, res, relu, ipe = rec
                 B, H, W, C = x.shape
                 gy = grads.pop(y.data_ptr())
-                gx = torch.empty_like(x)
-                gres = torch.empty_like(x) if res is not None else None
+                gx = self._like(x)
+                gres = self._like(res) if res is not None else None
                 partial = self._new(self.lib.bn2d_partial_floats(B, H * W, C))
                 sums = self._new((B // ipe) * C * 2)
-                lib.bn2d_bwd(x, y, gy, mean, invstd, m.weight.data, gx, gres, m.weight.grad, m.bias.grad, partial, sums, B,
-                             H * W, C, ipe, relu, st)
+                lib.bn2d_bwd_l(self._base(x), self._base(y), self._base(gy), mean, invstd, m.weight.data, self._base(gx),
+                               self._base(gres), m.weight.grad, m.bias.grad, partial, sums, B, H * W, C, ipe, relu, W,
+                               self._lay(x=x, y=y, gy=gy, gx=gx, res=gres), st)
                 if self.trace is not None:
                     self.trace.append((rec, gy, gx.clone(), None if gres is None else gres.clone()))
                 give(x, gx)
@@ -207,30 +269,37 @@ class ResNetEngine:
                 if self._tcg_ok(m, W):
                     # tcgen05 weight gradient and dgrad (the forward kernel on the flipped / transposed weights); 3x3:
                     # both operands in the persistent zero-bordered padded-flat buffers, 1x1: straight on the dense rows
-                    gx = torch.empty_like(x)
+                    gx = self._like(x)
                     wd = self._tcg_weights(m)[1]
                     scratch = self._new(lib.wgrad_tcg_scratch_floats(B, H, W, Cin, Cout, R))
                     bg = m.bias.grad if m.bias is not None else None
                     if R == 3:
-                        xp, gyp = self._padbuf("in", B, H, W, Cin), self._padbuf("out", B, H, W, Cout)
-                        lib.pad_copy(x, xp, B, H, W, Cin, 0, st)
-                        lib.pad_copy(gy, gyp, B, H, W, Cout, 0, st)
+                        xp, gyp = self._padded_base(x, "in"), self._padded_base(gy, "out")
                         lib.wgrad_tcg(xp, gyp, m.weight.grad, bg, scratch, self.tc_err, B, H, W, Cin, Cout, R, st)
-                        lib.conv_tcg(gyp, wd, None, xp, self.tc_err, B, H, W, Cout, Cin, R, st)      # xp is free again
-                        lib.pad_copy(gx, xp, B, H, W, Cin, 1, st)
+                        if self._is_pad(gx):
+                            lib.conv_tcg(gyp, wd, None, gx._base, self.tc_err, B, H, W, Cout, Cin, R, st)
+                        else:           # dense input: through the scratch buffer (free again after the weight gradient)
+                            xp = self._padbuf("in", B, H, W, Cin)
+                            lib.conv_tcg(gyp, wd, None, xp, self.tc_err, B, H, W, Cout, Cin, R, st)
+                            lib.pad_copy(gx, xp, B, H, W, Cin, 1, st)
                     else:
-                        lib.wgrad_tcg(x, gy, m.weight.grad, bg, scratch, self.tc_err, B, H, W, Cin, Cout, R, st)
-                        lib.conv_tcg(gy, wd, None, gx, self.tc_err, B, H, W, Cout, Cin, R, st)
+                        xd, gyd = self._dense(x), self._dense(gy)
+                        gxd = gx if not self._is_pad(gx) else self._new(B, H, W, Cin)
+                        lib.wgrad_tcg(xd, gyd, m.weight.grad, bg, scratch, self.tc_err, B, H, W, Cin, Cout, R, st)
+                        lib.conv_tcg(gyd, wd, None, gxd, self.tc_err, B, H, W, Cout, Cin, R, st)
+                        if gxd is not gx:
+                            lib.pad_copy(gxd, gx._base, B, H, W, Cin, 0, st)
                     if self.trace is not None:
                         self.trace.append((rec, gy, gx.clone(), m.weight.grad.clone()))
                     give(x, gx)
                     continue
                 ns = lib.conv2d_wgrad_nsplit(y.shape[0] * y.shape[1] * y.shape[2])
                 scratch = self._new(ns * R * R * Cin * Cout)
-                lib.conv2d_wgrad(x, gy, None, m.weight.grad, m.bias.grad if m.bias is not None else None, scratch, B, H, W,
+                xd, gy = self._dense(x), self._dense(gy)
+                lib.conv2d_wgrad(xd, gy, None, m.weight.grad, m.bias.grad if m.bias is not None else None, scratch, B, H, W,
                                  Cin, Cout, R, R, stv, pad, dil, 0, st)
                 if Cin > 3:      # no input gradient for the stem
-                    gx = torch.empty_like(x)
+                    gx = self._new(B, H, W, Cin)
                     if lib.conv2d_mma_ok(Cin, Cout):      # `wd` was refreshed by this step's forward (weights unchanged since)
                         lib.conv2d_dgrad_mma(gy, self._mma_weights(m)[1], gx, B, H, W, Cin, Cout, R, R, stv, pad, dil, st)
                     else:

@@ -175,6 +175,19 @@ int dktb_bn2d_apply(const float* x, const float* mean, const float* invstd, cons
 int dktb_bn2d_bwd(const float* x, const float* y, const float* gy, const float* mean, const float* invstd,
                   const float* gamma, float* gx, float* gres, float* dgamma, float* dbeta, float* partial, float* sums,
                   int B, int HW, int C, int ipe, int relu, cudaStream_t stream);   /* sums: (B/ipe)*C*2 */
+/* Layout-aware variants: every NHWC tensor argument is dense [B][H][W][C] or the interior of a padded-flat buffer
+ * [B][H+2][W+2][C] (pointer = buffer base, border never touched) -- the layout dktb_conv_tcg reads and writes, so no copy
+ * separates the tcgen05 convolutions from the BatchNorm kernels.  lay: bit 0 = x (add: a), bit 1 = y (add: b), bit 2 = gy,
+ * bit 3 = gx, bit 4 = res / gres; W = row width (HW % W == 0). */
+int dktb_bn2d_stats_l(const float* x, float* mean, float* invstd, float* running_mean, float* running_var, float* partial,
+                      int B, int HW, int C, int ipe, float momentum, float eps, int W, int lay, cudaStream_t stream);
+int dktb_bn2d_apply_l(const float* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                      const float* res, float* y, int B, int HW, int C, int ipe, int relu, int W, int lay,
+                      cudaStream_t stream);
+int dktb_bn2d_bwd_l(const float* x, const float* y, const float* gy, const float* mean, const float* invstd,
+                    const float* gamma, float* gx, float* gres, float* dgamma, float* dbeta, float* partial, float* sums,
+                    int B, int HW, int C, int ipe, int relu, int W, int lay, cudaStream_t stream);
+int dktb_add_inplace_l(float* a, const float* b, int B, int HW, int C, int W, int lay, cudaStream_t stream);
 int dktb_maxpool3_fwd(const float* x, float* y, unsigned char* idx, int B, int H, int W, int C, cudaStream_t stream);
 int dktb_maxpool3_bwd(const float* gy, const unsigned char* idx, float* gx, int B, int H, int W, int C,
                       cudaStream_t stream);

@@ -658,6 +658,47 @@ def check_resnet_ops(lib, dev, E=2, ipe=2, H=9, W=7, C=8, seed=80):
         _close(db, br.grad, rtol=1e-4, atol=1e-5, what="bn2d dbeta")
         if with_res:
             _close(gres.cpu().permute(0, 3, 1, 2), rr.grad, rtol=1e-5, atol=1e-6, what="bn2d gres")
+        if C % 4 == 0 and lib.has("dktb_bn2d_stats_l"):
+            # layout-aware entry points: padded-flat buffers (border poisoned, must stay untouched) in every combination of
+            # the tensor arguments give the dense results bit for bit
+            def padded(t, fill=7.0):
+                buf = torch.full((B, H + 2, W + 2, C), fill, device=dev)
+                if t is not None:
+                    buf[:, 1:-1, 1:-1] = t
+                return buf
+
+            def border_ok(buf, fill=7.0):
+                bb = buf.clone()
+                bb[:, 1:-1, 1:-1] = fill
+                return bool((bb == fill).all())
+
+            for lay in (31, 1, 2 | 8, 4 | 16, 1 | 4 | 8):
+                lx, ly, lgy, lgx, lres = lay & 1, lay & 2, lay & 4, lay & 8, lay & 16
+                x_a = padded(xd) if lx else xd
+                r_a = (padded(rd) if lres else rd) if with_res else None
+                mean2, invstd2 = torch.empty(E, C, device=dev), torch.empty(E, C, device=dev)
+                drm2, drv2 = rm0.clone().to(dev), rv0.clone().to(dev)
+                lib.bn2d_stats_l(x_a, mean2, invstd2, drm2, drv2, partial, B, H * W, C, ipe, 0.1, 1e-5, W, lay, 0)
+                assert torch.equal(mean2, mean) and torch.equal(invstd2, invstd) and torch.equal(drm2, drm), "bn2d_stats_l"
+                y_a = padded(None) if ly else torch.empty_like(xd)
+                lib.bn2d_apply_l(x_a, mean, invstd, gamma.to(dev), beta.to(dev), r_a, y_a, B, H * W, C, ipe, relu, W, lay, 0)
+                assert torch.equal(y_a[:, 1:-1, 1:-1] if ly else y_a, y), "bn2d_apply_l lay=%d" % lay
+                assert not ly or border_ok(y_a)
+                gy_a = padded(gyd) if lgy else gyd
+                gx_a = padded(None) if lgx else torch.empty_like(xd)
+                gres_a = (padded(None) if lres else torch.empty_like(xd)) if with_res else None
+                dg2, db2 = torch.empty(C, device=dev), torch.empty(C, device=dev)
+                lib.bn2d_bwd_l(x_a, y_a, gy_a, mean, invstd, gamma.to(dev), gx_a, gres_a, dg2, db2, partial, sums, B, H * W,
+                               C, ipe, relu, W, lay, 0)
+                assert torch.equal(gx_a[:, 1:-1, 1:-1] if lgx else gx_a, gx), "bn2d_bwd_l gx lay=%d" % lay
+                assert torch.equal(dg2, dg) and torch.equal(db2, db), "bn2d_bwd_l parameter gradients"
+                assert not lgx or border_ok(gx_a)
+                if with_res:
+                    assert torch.equal(gres_a[:, 1:-1, 1:-1] if lres else gres_a, gres), "bn2d_bwd_l gres"
+                    assert not lres or border_ok(gres_a)
+                acc = padded(xd) if lx else xd.clone()
+                lib.add_inplace_l(acc, padded(gyd) if ly else gyd, B, H * W, C, W, lay & 3, 0)
+                assert torch.equal(acc[:, 1:-1, 1:-1] if lx else acc, xd + gyd) and (not lx or border_ok(acc)), "add_inplace_l"
     # eval mode (ipe = 0: one statistics row)
     em, ei = torch.empty(C, device=dev), torch.empty(C, device=dev)
     lib.bn_eval_prepare(rm0.to(dev), rv0.to(dev), em, ei, C, 1e-5, 0)
