@@ -11,12 +11,13 @@
 // is never read or written here.
 enum { kLayX = 1, kLayY = 2, kLayGy = 4, kLayGx = 8, kLayRes = 16 };
 struct NhwcGeom { int HW, W, HWp; };        // HWp = (H + 2) * (W + 2)
-// global pixel index (b * HW + p) -> padded-flat row index
-__device__ __forceinline__ long padded_row(long pix, const NhwcGeom& gm) {
-  const long b = pix / gm.HW;
-  const int p = (int)(pix - b * gm.HW);
-  const int h = p / gm.W, w = p - h * gm.W;
-  return b * gm.HWp + (long)(h + 1) * (gm.W + 2) + (w + 1);
+// The element-wise kernels run one grid row (blockIdx.y) per image and decompose the in-image index with 32-bit unsigned
+// arithmetic (a 64-bit division per element costs more than the memory access it addresses).
+// pixel p of image b -> row index of a dense / padded-flat tensor
+__device__ __forceinline__ long dense_row(int b, unsigned p, const NhwcGeom& gm) { return (long)b * gm.HW + p; }
+__device__ __forceinline__ long padded_row(int b, unsigned p, const NhwcGeom& gm) {
+  const unsigned h = p / (unsigned)gm.W, w = p - h * (unsigned)gm.W;
+  return (long)b * gm.HWp + (long)(h + 1) * (gm.W + 2) + (w + 1);
 }
 
 // ------------------------------------------------------------------------------------------------ BN statistics
@@ -60,6 +61,11 @@ __global__ void __launch_bounds__(256) bn2d_partial_kernel(const float* __restri
     const long xb = ((lay & kLayX) ? (long)b * gm.HWp : (long)b * HW) * C + c;
     const long gb = ((lay & kLayGy) ? (long)b * gm.HWp : (long)b * HW) * C + c;
     const long yb = ((lay & kLayY) ? (long)b * gm.HWp : (long)b * HW) * C + c;
+    int hh = 0, ww = p_lo + ps;                    // (row, column) of the next pixel, advanced incrementally
+    if (lay) {
+      hh = ww / gm.W;
+      ww -= hh * gm.W;
+    }
     for (int p0 = p_lo + ps; p0 < p_hi; p0 += 16 * 8) {
       float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
 #pragma unroll
@@ -72,8 +78,9 @@ __global__ void __launch_bounds__(256) bn2d_partial_kernel(const float* __restri
           const int pd = in ? p : p_lo;
           int pp = pd;                                      // pixel index inside a padded image
           if (lay) {
-            const int h = pd / gm.W;
-            pp = (h + 1) * (gm.W + 2) + (pd - h * gm.W) + 1;
+            pp = in ? (hh + 1) * (gm.W + 2) + ww + 1 : gm.W + 3;
+            ww += 16;
+            while (ww >= gm.W) { ww -= gm.W; ++hh; }
           }
           xv[u] = dktb_ld4(x + xb + (long)((lay & kLayX) ? pp : pd) * C);
           if (mode == 1) {
@@ -237,16 +244,17 @@ DKTB_EXPORT int dktb_bn2d_stats(const float* x, float* mean, float* invstd, floa
 __global__ void __launch_bounds__(256) bn2d_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
                                                          const float* __restrict__ invstd,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                         const float* __restrict__ res, float* __restrict__ y, long total4,
-                                                         int HW, int C, int ipe, int relu, NhwcGeom gm, int lay) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total4) return;
-  const int c4 = (int)(i % (C / 4)) * 4;
-  const long pix = i / (C / 4);
-  const int e = ipe > 0 ? (int)(pix / HW / ipe) : 0;
-  const long prow = lay ? padded_row(pix, gm) : pix;
-  const long ix = ((lay & kLayX) ? prow : pix) * C + c4, iy = ((lay & kLayY) ? prow : pix) * C + c4;
-  const float4 v = dktb_ld4(x + ix);
+                                                         const float* __restrict__ res, float* __restrict__ y,
+                                                         unsigned per_img4, int C, int ipe, int relu, NhwcGeom gm, int lay) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;       // float4 index inside image blockIdx.y
+  if (i >= per_img4) return;
+  const int b = blockIdx.y;
+  const unsigned c4n = (unsigned)C >> 2;
+  const unsigned p = i / c4n;
+  const int c4 = (int)(i - p * c4n) * 4;
+  const int e = ipe > 0 ? b / ipe : 0;
+  const long drow = dense_row(b, p, gm), prow = lay ? padded_row(b, p, gm) : drow;
+  const float4 v = dktb_ld4(x + ((lay & kLayX) ? prow : drow) * C + c4);
   const float4 m = dktb_ld4(mean + (long)e * C + c4), is = dktb_ld4(invstd + (long)e * C + c4);
   const float4 g = dktb_ld4(gamma + c4), bt = dktb_ld4(beta + c4);
   float4 o;
@@ -255,11 +263,11 @@ __global__ void __launch_bounds__(256) bn2d_apply_kernel(const float* __restrict
   o.z = fmaf(v.z - m.z, is.z * g.z, bt.z);
   o.w = fmaf(v.w - m.w, is.w * g.w, bt.w);
   if (res != nullptr) {
-    const float4 r = dktb_ld4(res + ((lay & kLayRes) ? prow : pix) * C + c4);
+    const float4 r = dktb_ld4(res + ((lay & kLayRes) ? prow : drow) * C + c4);
     o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
   }
   if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-  dktb_st4(y + iy, o);
+  dktb_st4(y + ((lay & kLayY) ? prow : drow) * C + c4, o);
 }
 
 DKTB_EXPORT int dktb_bn2d_apply_l(const float* x, const float* mean, const float* invstd, const float* gamma,
@@ -267,9 +275,10 @@ DKTB_EXPORT int dktb_bn2d_apply_l(const float* x, const float* mean, const float
                                   int W, int lay, cudaStream_t stream) {
   DKTB_CHECK_ARG(x && mean && invstd && gamma && beta && y && B > 0 && HW > 0 && C > 0 && C % 4 == 0);
   DKTB_CHECK_ARG(lay == 0 || (W > 0 && HW % W == 0));
-  const long total4 = (long)B * HW * C / 4;
-  DKTB_LAUNCH(bn2d_apply_kernel, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, stream, x, mean, invstd, gamma,
-              beta, res, y, total4, HW, C, ipe, relu, nhwc_geom(HW, W), lay);
+  DKTB_CHECK_ARG(B <= 65535 && (long)HW * C / 4 < 2147483647L);
+  const unsigned per_img4 = (unsigned)((long)HW * C / 4);
+  DKTB_LAUNCH(bn2d_apply_kernel, dim3((per_img4 + 255) / 256, B), dim3(256), 0, stream, x, mean, invstd, gamma, beta, res, y,
+              per_img4, C, ipe, relu, nhwc_geom(HW, W), lay);
   return dktb_launch_status();
 }
 DKTB_EXPORT int dktb_bn2d_apply(const float* x, const float* mean, const float* invstd, const float* gamma,
@@ -284,16 +293,17 @@ __global__ void __launch_bounds__(256) bn2d_bwd_apply_kernel(const float* __rest
                                                              const float* __restrict__ invstd,
                                                              const float* __restrict__ gamma,
                                                              const float* __restrict__ sums, float* __restrict__ gx,
-                                                             float* __restrict__ gres, long total4, int HW, int C, int ipe,
+                                                             float* __restrict__ gres, unsigned per_img4, int C, int ipe,
                                                              int relu, float inv_n, NhwcGeom gm, int lay) {
-  // four channels per thread (C % 4 == 0): 16-byte loads / stores, one index decomposition per four elements
-  const long i4 = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i4 >= total4) return;
-  const int c4n = C >> 2;
-  const int c = (int)(i4 % c4n) * 4;
-  const long pix = i4 / c4n;
-  const int e = (int)(pix / ((long)HW * ipe));
-  const long prow = lay ? padded_row(pix, gm) : pix;
+  // four channels per thread (C % 4 == 0): 16-byte loads / stores; one grid row per image, 32-bit index arithmetic
+  const unsigned i4 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 >= per_img4) return;
+  const int b = blockIdx.y;
+  const unsigned c4n = (unsigned)C >> 2;
+  const unsigned p = i4 / c4n;
+  const int c = (int)(i4 - p * c4n) * 4;
+  const int e = b / ipe;
+  const long pix = dense_row(b, p, gm), prow = lay ? padded_row(b, p, gm) : pix;
   float4 g = dktb_ld4(gy + ((lay & kLayGy) ? prow : pix) * C + c);
   if (relu) {
     const float4 yy = dktb_ld4(y + ((lay & kLayY) ? prow : pix) * C + c);
@@ -329,9 +339,10 @@ DKTB_EXPORT int dktb_bn2d_bwd_l(const float* x, const float* y, const float* gy,
               mean, invstd, partial, HW, C, ipe, 1, gm, lay);
   DKTB_LAUNCH(bn2d_bwd_finalize_kernel, dim3((C + 31) / 32), dim3(256), 0, stream, (const float*)partial, sums, dgamma,
               dbeta, B / ipe, ipe * S, C);
-  const long total4 = (long)B * HW * C / 4;
-  DKTB_LAUNCH(bn2d_bwd_apply_kernel, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, stream, x, y, gy, mean, invstd,
-              gamma, (const float*)sums, gx, gres, total4, HW, C, ipe, relu, 1.0f / ((float)ipe * (float)HW), gm, lay);
+  DKTB_CHECK_ARG((long)HW * C / 4 < 2147483647L);
+  const unsigned per_img4 = (unsigned)((long)HW * C / 4);
+  DKTB_LAUNCH(bn2d_bwd_apply_kernel, dim3((per_img4 + 255) / 256, B), dim3(256), 0, stream, x, y, gy, mean, invstd, gamma,
+              (const float*)sums, gx, gres, per_img4, C, ipe, relu, 1.0f / ((float)ipe * (float)HW), gm, lay);
   return dktb_launch_status();
 }
 DKTB_EXPORT int dktb_bn2d_bwd(const float* x, const float* y, const float* gy, const float* mean, const float* invstd,
@@ -477,23 +488,25 @@ DKTB_EXPORT int dktb_add_inplace(float* a, const float* b, long n, cudaStream_t 
 }
 
 // a += b over NHWC tensors of either layout (lay: kLayX = a padded, kLayY = b padded); C % 4 == 0
-__global__ void __launch_bounds__(256) add_inplace_l_kernel(float* __restrict__ a, const float* __restrict__ b, long total4,
-                                                            int C, NhwcGeom gm, int lay) {
-  const long i4 = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i4 >= total4) return;
-  const int c4n = C >> 2;
-  const int c = (int)(i4 % c4n) * 4;
-  const long pix = i4 / c4n;
-  const long prow = padded_row(pix, gm);
-  float* pa = a + ((lay & kLayX) ? prow : pix) * C + c;
-  const float4 x = dktb_ld4(pa), y = dktb_ld4(b + ((lay & kLayY) ? prow : pix) * C + c);
+__global__ void __launch_bounds__(256) add_inplace_l_kernel(float* __restrict__ a, const float* __restrict__ b,
+                                                            unsigned per_img4, int C, NhwcGeom gm, int lay) {
+  const unsigned i4 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 >= per_img4) return;
+  const int img = blockIdx.y;
+  const unsigned c4n = (unsigned)C >> 2;
+  const unsigned p = i4 / c4n;
+  const int c = (int)(i4 - p * c4n) * 4;
+  const long drow = dense_row(img, p, gm), prow = padded_row(img, p, gm);
+  float* pa = a + ((lay & kLayX) ? prow : drow) * C + c;
+  const float4 x = dktb_ld4(pa), y = dktb_ld4(b + ((lay & kLayY) ? prow : drow) * C + c);
   dktb_st4(pa, make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w));
 }
 DKTB_EXPORT int dktb_add_inplace_l(float* a, const float* b, int B, int HW, int C, int W, int lay, cudaStream_t stream) {
   DKTB_CHECK_ARG(a && b && B > 0 && HW > 0 && C > 0 && C % 4 == 0 && W > 0 && HW % W == 0);
   if (lay == 0) return dktb_add_inplace(a, b, (long)B * HW * C, stream);
-  const long total4 = (long)B * HW * C / 4;
-  DKTB_LAUNCH(add_inplace_l_kernel, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, stream, a, b, total4, C,
+  DKTB_CHECK_ARG(B <= 65535 && (long)HW * C / 4 < 2147483647L);
+  const unsigned per_img4 = (unsigned)((long)HW * C / 4);
+  DKTB_LAUNCH(add_inplace_l_kernel, dim3((per_img4 + 255) / 256, B), dim3(256), 0, stream, a, b, per_img4, C,
               nhwc_geom(HW, W), lay);
   return dktb_launch_status();
 }
