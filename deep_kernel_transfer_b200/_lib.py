@@ -41,6 +41,10 @@ SIGNATURES = {
     "dktb_conv_tcg": ("pppppiiiiiis", ctypes.c_int),
     "dktb_wgrad_tcg_scratch_floats": ("iiiiii", ctypes.c_long),
     "dktb_wgrad_tcg": ("ppppppiiiiiis", ctypes.c_int),
+    "dktb_stem_tc_ok": ("iiiiiiii", ctypes.c_int),
+    "dktb_stem_tc_weight_floats": ("", ctypes.c_long),
+    "dktb_prep_weights_stem_tc": ("pps", ctypes.c_int),
+    "dktb_stem_tc": ("pppppiiis", ctypes.c_int),
     "dktb_zero_border": ("piiiis", ctypes.c_int),
     "dktb_pad_copy": ("ppiiiiis", ctypes.c_int),
     "dktb_conv3x3_wgrad_reduce": ("pipps", ctypes.c_int),

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdktb200.so")
-SOURCES = ["conv_fp32.cu", "conv1_bwd_mma.cu", "bn_pool.cu", "head.cu", "gp.cu", "gp_large.cu", "gp_kernels.cu", "gp_spectral.cu", "optim.cu", "conv_generic.cu", "resnet_ops.cu", "episode_feed.cu", "conv_tc.cu", "conv_tcg.cu", "gram_tc.cu"]
+SOURCES = ["conv_fp32.cu", "conv1_bwd_mma.cu", "bn_pool.cu", "head.cu", "gp.cu", "gp_large.cu", "gp_kernels.cu", "gp_spectral.cu", "optim.cu", "conv_generic.cu", "resnet_ops.cu", "episode_feed.cu", "conv_tc.cu", "conv_tcg.cu", "gram_tc.cu", "stem_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--use_fast_math=false"]
 

@@ -141,6 +141,24 @@ class ResNetEngine:
         self.tape.append(("conv", x, out, m, (B, H, W, Cin, R, st, pad, dil)))
         return out
 
+    def _stem(self, x, xh, m):
+        """7x7 / stride 2 stem: the tcgen05 kernel reads the NCHW batch directly (csrc/stem_tc.cu); the tape keeps the NHWC
+        copy for the weight gradient.  Other stems (different geometry) take the generic path."""
+        B, _, H, W = x.shape
+        R, sv, pad, dil = m.kernel_size[0], m.stride[0], m.padding[0], m.dilation[0]
+        if not (self.use_tcg and self.lib.has("dktb_stem_tc")
+                and self.lib.stem_tc_ok(m.in_channels, m.out_channels, R, sv, pad, dil, H, W)):
+            return self._conv(xh, m)
+        key = ("stem", id(m))
+        if key not in self._mma_w:
+            self._mma_w[key] = self._new(self.lib.stem_tc_weight_floats())
+        sm = _stream(self.dev)
+        self.lib.prep_weights_stem_tc(m.weight.data, self._mma_w[key], sm)
+        out = self._new(B, H // 2, W // 2, m.out_channels)
+        self.lib.stem_tc(x, self._mma_w[key], m.bias.data if m.bias is not None else None, out, self.tc_err, B, H, W, sm)
+        self.tape.append(("conv", xh, out, m, (B, H, W, m.in_channels, R, sv, pad, dil)))
+        return out
+
     def _mma_weights(self, m):
         key = id(m)
         if key not in self._mma_w:
@@ -180,7 +198,7 @@ class ResNetEngine:
         xh = self._new(B, H, W, 3)
         lib.nchw_to_nhwc(x, xh, B, 3, H, W, st)
         t = net.trunk
-        out = self._conv(xh, t[0])
+        out = self._stem(x, xh, t[0])
         out = self._bn(out, t[1], ipe, training, relu=1)
         Bq, Hq, Wq, Cq = out.shape
         Ho, Wo = (Hq + 2 - 3) // 2 + 1, (Wq + 2 - 3) // 2 + 1

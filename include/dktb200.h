@@ -86,6 +86,15 @@ long dktb_conv_tcg_weight_floats(int Cin, int Cout, int R);
 int dktb_prep_weights_tcg(const float* w, float* wb_fwd, float* wb_dgrad, int Cout, int Cin, int R, cudaStream_t stream);
 int dktb_conv_tcg(const float* a, const float* wb, const float* bias, float* out, int* err, int B, int H, int W, int Cin,
                   int Cout, int R, cudaStream_t stream);
+/* ResNet stem (backbone.py:336-340: Conv2d(3, 64, 7, stride 2, padding 3)) on tcgen05: x [B,3,H,W] NCHW -> y [B,H/2,W/2,64]
+ * NHWC; implicit GEMM over k = ci*49 + r*7 + s (147 -> 160), 3xTF32.  wb: dktb_stem_tc_weight_floats() floats written by
+ * dktb_prep_weights_stem_tc from w [64][3][7][7].  err: device int (zero-initialised), 1 = a pipeline wait timed out. */
+int dktb_stem_tc_ok(int Cin, int Cout, int R, int stride, int pad, int dil, int H, int W);
+long dktb_stem_tc_weight_floats(void);
+int dktb_prep_weights_stem_tc(const float* w, float* wb, cudaStream_t stream);
+int dktb_stem_tc(const float* x, const float* wb, const float* bias, float* y, int* err, int B, int H, int W,
+                 cudaStream_t stream);
+
 /* weight gradient of the same layers on tcgen05: x [.., Cin], gy [.., Cout] in the layouts of dktb_conv_tcg (R = 3: both
  * padded-flat with zero borders; R = 1: dense rows) -> dw [Cout][Cin][R][R], db [Cout] or NULL; scratch holds
  * dktb_wgrad_tcg_scratch_floats(...) floats; per-CTA partials are reduced in a fixed order (deterministic). */

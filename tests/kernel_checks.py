@@ -983,6 +983,23 @@ def check_conv_tcg(lib, dev, B=2, H=6, W=5, Cin=64, Cout=128, R=3, seed=100, rto
         _close(db, br.grad, rtol=rtol, atol=1e-4, what="conv_tcg bias grad")
 
 
+def check_stem_tc(lib, dev, B=2, H=32, W=32, seed=120, rtol=2e-5, bias=False):
+    """ResNet stem (7x7, stride 2, pad 3, 3 -> 64) on tcgen05 (csrc/stem_tc.cu) against torch in float64."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, 3, H, W, generator=g)
+    w = torch.randn(64, 3, 7, 7, generator=g) * (1.0 / 147 ** 0.5)
+    b = torch.randn(64, generator=g) if bias else None
+    ref = F.conv2d(x.double(), w.double(), b.double() if bias else None, stride=2, padding=3)
+    assert lib.stem_tc_ok(3, 64, 7, 2, 3, 1, H, W)
+    wb = torch.empty(lib.stem_tc_weight_floats(), device=dev)
+    lib.prep_weights_stem_tc(w.to(dev), wb, 0)
+    y = torch.full((B, H // 2, W // 2, 64), 7.0, device=dev)
+    err = torch.zeros(1, device=dev, dtype=torch.int32)
+    lib.stem_tc(x.to(dev), wb, b.to(dev) if bias else None, y, err, B, H, W, 0)
+    assert int(err) == 0
+    _close(y.cpu().permute(0, 3, 1, 2), ref, rtol=rtol, atol=1e-6, what="stem_tc %dx%d" % (H, W))
+
+
 def check_gram_tc(lib, dev, E=3, M=105, N=105, D=1600, seed=110, same=True):
     """tcgen05 Gram / cross-kernel product against float64 (3xTF32: fp32-class accuracy), incl. ragged tiles."""
     g = torch.Generator().manual_seed(seed)

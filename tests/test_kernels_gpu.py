@@ -125,6 +125,13 @@ def test_resnet_ops(lib):
     kc.check_resnet_ops(lib, DEV, E=2, ipe=2, H=32, W=33, C=64, seed=82)      # BatchNorm sums split over the pixels (4 splits)
 
 
+@pytest.mark.parametrize("cfg", [dict(), dict(B=1, H=20, W=30, seed=121, bias=True),              # ragged band and column tile
+                                 dict(B=2, H=84, W=84, seed=122),                                # miniImageNet resolution
+                                 dict(B=3, H=224, W=224, seed=123)])                             # the reference's ResNet resolution
+def test_stem_tc(lib, cfg):
+    kc.check_stem_tc(lib, DEV, **cfg)
+
+
 @pytest.mark.parametrize("cfg", [dict(), dict(B=3, H=56, W=56, Cin=64, Cout=64, seed=101),          # ResNet18 layer1
                                  dict(B=3, H=28, W=28, Cin=128, Cout=128, seed=102, bias=False),      # layer2
                                  dict(B=5, H=14, W=14, Cin=256, Cout=256, seed=103),                  # layer3
