@@ -599,13 +599,14 @@ def _time_launch(fn, reps=10, warm=3):
 
 
 def resnet_roofline(model, lib, dev, E):
-    """ResNet configs: the dominant layer shape (3x3, 64 -> 64 at 56x56, stride 1: 4 of ResNet18's 16 3x3 convolutions;
-    every stride-1 3x3 convolution of the network has the same MAC count) on the tcgen05 kernel, timed alone."""
+    """ResNet configs: the dominant kernel by time is conv_tcg_kernel<128> (the stride-1 3x3 layers with >= 128 channels;
+    profiles/r02_launches_cfg4.summary.txt); its most frequent launch -- 3x3, 128 -> 128 at 28x28 (ResNet18 layer2; every
+    stride-1 3x3 layer of the network has the same MAC count) -- is timed alone here."""
     import torch
     peaks = _peaks()
     B = E * N_WAY * (N_SUPPORT + N_QUERY)
-    H = W = 56
-    C = 64
+    H = W = 28
+    C = 128
     xp = torch.zeros(B, H + 2, W + 2, C, device=dev)
     xp[:, 1:-1, 1:-1].normal_()
     yp = torch.zeros(B, H + 2, W + 2, C, device=dev)
@@ -621,14 +622,14 @@ def resnet_roofline(model, lib, dev, E):
     ach = flops / (ms / 1e3) / 1e12
     peak = peaks.get("bf16_tflops", 1600.0) / 2.0
     alg_bytes = B * ((H + 2) * (W + 2) + H * W) * C * 4.0
-    return {"kernel": "conv_tcg_kernel (tcgen05 3xTF32) 3x3 64->64 forward, 56x56, B=%d images" % B,
+    return {"kernel": "conv_tcg_kernel<128> (tcgen05 3xTF32) 3x3 128->128 forward, 28x28, B=%d images" % B,
             "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-            "traffic": tracked_traffic("conv_tcg_kernel@56x56x64", B), "algorithmic_bytes_per_launch": alg_bytes,
+            "traffic": tracked_traffic("conv_tcg_kernel<128>@28x28x128", B), "algorithmic_bytes_per_launch": alg_bytes,
             "algorithmic_flops_per_launch": flops, "ms_per_launch": ms,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone) / 2 = dense TF32; 3xTF32: the "
                            "arithmetic's ceiling is 1/3",
-            "note": "stride-1 3x3 and 1x1 layers run on this kernel (83 % of ResNet18's MACs); stem and stride-2 layers on "
-                    "mma.sync tiles (profiles/r02_launches_cfg4.summary.txt)"}
+            "note": "stride-1 3x3 / 1x1 layers and the 7x7 stem run on tcgen05 kernels; the three stride-2 3x3 layers, their "
+                    "1x1 shortcuts and the stem's weight gradient on mma.sync tiles (profiles/r02_launches_cfg4.summary.txt)"}
 
 
 def gp_flops(n, c, d):

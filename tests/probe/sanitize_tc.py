@@ -15,7 +15,7 @@ from deep_kernel_transfer_b200 import _lib  # noqa: E402
 
 lib = _lib.load()
 dev = torch.device("cuda", 0)
-which = sys.argv[1:] or ["conv3x3", "wgrad", "conv1", "tcg", "gram"]
+which = sys.argv[1:] or ["conv3x3", "wgrad", "conv1", "tcg", "gram", "stem"]
 if "conv3x3" in which:
     kc.check_conv3x3_tc(lib, dev, B=2, H=10, W=10, seed=22, fn="conv3x3_tc_fwd")
     print("conv3x3_tc ok")
@@ -28,9 +28,14 @@ if "conv1" in which:
 if "tcg" in which:
     kc.check_conv_tcg(lib, dev, B=1, H=6, W=5, Cin=128, Cout=64, R=3, seed=100)
     kc.check_conv_tcg(lib, dev, B=1, H=6, W=5, Cin=64, Cout=128, R=1, seed=101)
+    kc.check_conv_tcg(lib, dev, B=1, H=6, W=5, Cin=128, Cout=128, R=3, seed=102)       # the 128-channel work item
+    kc.check_conv_tcg(lib, dev, B=1, H=5, W=4, Cin=256, Cout=128, R=1, seed=103)
     print("conv_tcg ok")
 if "gram" in which and lib.has("dktb_gram_tc"):
     kc.check_gram_tc(lib, dev, E=2, M=70, N=70, D=96, seed=111)
     print("gram_tc ok")
+if "stem" in which and lib.has("dktb_stem_tc"):
+    kc.check_stem_tc(lib, dev, B=1, H=20, W=30, seed=121, bias=True)
+    print("stem_tc ok")
 torch.cuda.synchronize()
 print("done")
