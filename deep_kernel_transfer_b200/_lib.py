@@ -41,6 +41,11 @@ SIGNATURES = {
     "dktb_conv_tcg": ("pppppiiiiiis", ctypes.c_int),
     "dktb_wgrad_tcg_scratch_floats": ("iiiiii", ctypes.c_long),
     "dktb_wgrad_tcg": ("ppppppiiiiiis", ctypes.c_int),
+    "dktb_conv_tcg_s2_ok": ("iiii", ctypes.c_int),
+    "dktb_conv_tcg_s2_weight_floats": ("ii", ctypes.c_long),
+    "dktb_prep_weights_tcg_s2": ("pppiis", ctypes.c_int),
+    "dktb_s2d": ("ppiiiiiis", ctypes.c_int),
+    "dktb_conv_tcg_s2": ("pppppiiiiiis", ctypes.c_int),
     "dktb_stem_tc_ok": ("iiiiiiii", ctypes.c_int),
     "dktb_stem_tc_weight_floats": ("", ctypes.c_long),
     "dktb_prep_weights_stem_tc": ("pps", ctypes.c_int),

@@ -44,6 +44,19 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
   lo = __float_as_uint(v - __uint_as_float(hi));
 }
 
+// Structural zeros of the weight tensor: the K loop visits tap t of input group g (output block cb) only when bit t of the
+// mask of its PLANE is set.  Ordinary layers: one plane, every tap.  A stride-2 3x3 convolution runs as a stride-1
+// convolution over the space-to-depth input (4 parity planes = 4 C channels): 9 of the 36 (plane, tap) pairs are non-zero
+// (forward: plane of the input group; dgrad: plane of the output block).
+struct TapMasks {
+  unsigned long long m;      // 9-bit tap mask per plane, 16 bits apart (packed: no dynamically indexed kernel parameter)
+  int per_plane;             // input groups (by_cb = 0) or output blocks (by_cb = 1) per plane
+  int by_cb;
+  __host__ __device__ unsigned of(int g, int cb) const {
+    return (unsigned)(m >> (16 * ((by_cb ? cb : g) / per_plane))) & 0x1FFu;
+  }
+};
+
 // NB = output channels per work item.  NB = 64: the three 3xTF32 products are a_hi x [w_hi | w_lo] (one N = 128
 // instruction on the stacked tile) + a_lo x w_hi (N = 64), accumulator = 64 + 64 columns added in the epilogue, one
 // accumulator per K chunk summed in registers.  NB = 128 (Cout % 128 == 0): a_hi x w_hi, a_hi x w_lo, a_lo x w_hi are
@@ -55,7 +68,8 @@ template <int NB>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tcg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                 const float* __restrict__ bias, float* __restrict__ out, int B, int H, int W, int Cout, int G, int nblk,
-                int ntaps, int halo_rows_pad, int tiles_per_img, int flat, int gchunk, int* __restrict__ err) {
+                int ntaps, int halo_rows_pad, int tiles_per_img, int flat, int gchunk, TapMasks tm,
+                int* __restrict__ err) {
   constexpr int kHS = NB == 64 ? 2 : 1;                       // channel halves per 32 KB weight stage
   constexpr int kWRing = kWStages;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -119,11 +133,14 @@ conv_tcg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       return true;
     };
     if (blockIdx.x < nwork) ok = load_halo(blockIdx.x, 0, 0);
-    const int pre_tap = ntaps > 1 ? 1 : 0;                    // where the next halo is requested
     for (long work = blockIdx.x; work < nwork && ok; work += gridDim.x) {
       const int cb = (int)(work % nblk);
       for (int g = 0; g < G && ok; ++g, ++vt) {
+        const unsigned mask = tm.of(g, cb);
+        const int pre = min(2, __popc(mask));                 // the next halo is requested after this many taps' weights
+        int nv = 0;
         for (int tap = 0; tap < ntaps && ok; ++tap) {
+          if (!((mask >> tap) & 1)) continue;
           for (int h = 0; h < 2 && ok; h += kHS, ++wi) {
             const int s = (int)(wi % kWRing), ph = (int)((wi / kWRing) & 1);
             ok = tc::mbar_wait(&bar_wempty[s], ph ^ 1);
@@ -137,7 +154,7 @@ conv_tcg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
             __syncwarp();
           }
-          if (tap == pre_tap && ok) {
+          if (++nv == pre && ok) {
             if (g + 1 < G) ok = load_halo(work, g + 1, vt + 1);
             else if (work + gridDim.x < nwork) ok = load_halo(work + gridDim.x, 0, vt + 1);
           }
@@ -163,7 +180,11 @@ conv_tcg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         if (!ok) break;
         tc::tcgen05_fence_after();
         const uint32_t d_tmem = tmem + ab * 128;
-        const int nk = (min(G, g0 + gchunk) - g0) * ntaps;
+        int nk = 0;                                           // (group, tap) steps of this chunk that are not masked out
+        {
+          const int cb = (int)(work % nblk);
+          for (int g = g0; g < min(G, g0 + gchunk); ++g) nk += __popc(tm.of(g, cb) & ((1u << ntaps) - 1));
+        }
         for (int kk = 0; kk < nk && ok; ++kk) {
           int sw = 0;
 #pragma unroll
@@ -228,8 +249,11 @@ conv_tcg_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int hb = (int)(vt & 1), hp = (int)((vt >> 1) & 1);
         ok = tc::mbar_wait(&bar_hfull[hb], hp);
         if (!ok) break;
-        for (int tap = 0; tap < ntaps && ok; ++tap, ++wi) {
+        const unsigned mask = tm.of(g, (int)(work % nblk));
+        for (int tap = 0; tap < ntaps && ok; ++tap) {
+          if (!((mask >> tap) & 1)) continue;
           const int sa = (int)((wi & 1) << 1) | set, pa = (int)((wi >> 1) & 1);
+          ++wi;
           const int row = ntaps == 9 ? r + (tap / 3) * Wp + (tap % 3) : r;
           const unsigned char* src = s_halo + (hb * 2 + set) * half_bytes + row * 128;
           uint32_t hi[32], lo[32];
@@ -647,26 +671,19 @@ DKTB_EXPORT int dktb_prep_weights_tcg(const float* w, float* wb_fwd, float* wb_d
   return dktb_launch_status();
 }
 
-// R = 3: convolution (stride 1, pad 1) over padded-flat NHWC tensors: a [B][H+2][W+2][Cin] (zero border) -> out
-// [B][H+2][W+2][Cout] (interior written, border untouched).  R = 1: a plain GEMM over the rows of DENSE tensors:
-// a [B*H*W][Cin] -> out [B*H*W][Cout] (no padding involved).  wb: the forward tensor of dktb_prep_weights_tcg (+ bias
-// [Cout] or NULL), or -- dgrad -- the dgrad tensor with Cin / Cout swapped by the caller (a = dL/dout [.., Cout], out =
-// dL/da [.., Cin]).  err: device int, zero-initialised by the caller, set to 1 when a pipeline wait timed out.
-DKTB_EXPORT int dktb_conv_tcg(const float* a, const float* wb, const float* bias, float* out, int* err, int B, int H,
-                              int W, int Cin, int Cout, int R, cudaStream_t stream) {
-  DKTB_CHECK_ARG(a && wb && out && err && B > 0 && H > 0 && W > 0);
-  DKTB_CHECK_ARG(dktb_conv_tcg_ok(Cin, Cout, R, 1, R == 3 ? 1 : 0, 1, W));
+// Launch of conv_tcg_kernel<NB>: geometry as dktb_conv_tcg; tm / gchunk: the K loop's tap masks and chunk length.
+static int conv_tcg_launch(const float* a, const float* wb, const float* bias, float* out, int* err, int B, int H, int W,
+                           int Cin, int Cout, int R, int NB, int gchunk, const TapMasks& tm, cudaStream_t stream) {
   const int flat = R == 1;
   const int Hp = H + 2, Wp = W + 2;
   const long rows = flat ? (long)B * H * W : (long)B * Hp * Wp;
   DKTB_CHECK_ARG(rows < 2147483000L);
   const int ntaps = R * R;
-  const int G = Cin / 64, nblk = Cout / 64;
+  const int G = Cin / 64;
   const int halo = kRows + (ntaps == 9 ? 2 * (Wp + 1) : 0);
   const int halo_pad = (halo + kHaloBox - 1) / kHaloBox * kHaloBox;
   const int smem = 4 * halo_pad * 128 + kWStages * kWStageBytes + 1024;
   DKTB_CHECK_ARG(smem <= 227 * 1024);
-  const int NB = tcg_nb(Cout, Cin);                 // output channels per work item (the weight tensor was laid out for it)
   const int nb = Cout / NB;
   CUtensorMap map_a, map_w;
   if (tc_make_tmap_2d(&map_a, a, (uint64_t)Cin, (uint64_t)rows, 32, kHaloBox) != 0) return DKTB_BAD_ARG - 1;
@@ -680,17 +697,156 @@ DKTB_EXPORT int dktb_conv_tcg(const float* a, const float* wb, const float* bias
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = (int)(nwork < sms ? nwork : sms);
   // flat: the kernel sees one "image" of `rows` rows (H carries the row count for the validity test)
-  const int gchunk = ntaps == 9 ? 1 : 2;         // K per accumulator: 576 (3x3) / 128 (1x1); no measurable cost vs 1152 / 1024
   if (NB == 128) {
     cudaFuncSetAttribute(conv_tcg_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     conv_tcg_kernel<128><<<grid, kThreads, smem, stream>>>(map_a, map_w, bias, out, nimg, flat ? (int)rows : H, W, Cout, G, nb,
-                                                           ntaps, halo_pad, tiles_per_img, flat, gchunk, err);
+                                                           ntaps, halo_pad, tiles_per_img, flat, gchunk, tm, err);
   } else {
     cudaFuncSetAttribute(conv_tcg_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     conv_tcg_kernel<64><<<grid, kThreads, smem, stream>>>(map_a, map_w, bias, out, nimg, flat ? (int)rows : H, W, Cout, G, nb,
-                                                          ntaps, halo_pad, tiles_per_img, flat, gchunk, err);
+                                                          ntaps, halo_pad, tiles_per_img, flat, gchunk, tm, err);
   }
   return dktb_launch_status();
+}
+
+// R = 3: convolution (stride 1, pad 1) over padded-flat NHWC tensors: a [B][H+2][W+2][Cin] (zero border) -> out
+// [B][H+2][W+2][Cout] (interior written, border untouched).  R = 1: a plain GEMM over the rows of DENSE tensors:
+// a [B*H*W][Cin] -> out [B*H*W][Cout] (no padding involved).  wb: the forward tensor of dktb_prep_weights_tcg (+ bias
+// [Cout] or NULL), or -- dgrad -- the dgrad tensor with Cin / Cout swapped by the caller (a = dL/dout [.., Cout], out =
+// dL/da [.., Cin]).  err: device int, zero-initialised by the caller, set to 1 when a pipeline wait timed out.
+DKTB_EXPORT int dktb_conv_tcg(const float* a, const float* wb, const float* bias, float* out, int* err, int B, int H,
+                              int W, int Cin, int Cout, int R, cudaStream_t stream) {
+  DKTB_CHECK_ARG(a && wb && out && err && B > 0 && H > 0 && W > 0);
+  DKTB_CHECK_ARG(dktb_conv_tcg_ok(Cin, Cout, R, 1, R == 3 ? 1 : 0, 1, W));
+  TapMasks tm;
+  tm.m = (1ull << (R * R)) - 1;
+  tm.per_plane = 1 << 30;
+  tm.by_cb = 0;
+  // K per accumulator: 576 (3x3) / 128 (1x1); no measurable cost against 1152 / 1024
+  return conv_tcg_launch(a, wb, bias, out, err, B, H, W, Cin, Cout, R, tcg_nb(Cout, Cin), R == 3 ? 1 : 2, tm, stream);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Stride-2 3x3 convolutions (pad 1; reference backbone.py:150-152, 195-197: the first convolution of a down-sampling block)
+// as stride-1 convolutions over the SPACE-TO-DEPTH input: xs [B][H/2+2][W/2+2][4 C] padded-flat, channel = plane * C + c,
+// plane = (ih & 1) * 2 + (iw & 1), block position (ih >> 1, iw >> 1).  Output pixel (oh, ow) reads input row 2 oh - 1 + r:
+// r = 1 -> even plane at block oh; r = 0 / 2 -> odd plane at block oh - 1 / oh; the same along the width.  In the 3x3 tap
+// grid of the stride-1 kernel (dh, dw in {-1, 0, 1}) that is dh in {-1, 0} for odd planes and dh = 0 for even ones: 9 of
+// the 36 (plane, tap) pairs carry weights, the TapMasks skip the rest.  dgrad: dxs [.., 4 C] from dy [.., Cout], taps
+// dh in {0, +1} for odd output planes (r = 2 / 0), dh = 0 for even ones (r = 1), mask by the plane of the output block.
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+__host__ __device__ inline int s2_nb_fwd(int C, int Cout) { return Cout % 128 == 0 ? 128 : 64; }
+__host__ __device__ inline int s2_nb_dgrad(int C, int Cout) { return (C % 128 == 0 && Cout >= 128) ? 128 : 64; }
+
+// w [Cout][C][3][3] -> wb_fwd [Cout/NBf][4C/64][9][hi NBf | lo NBf][64], wb_dgrad [4C/NBd][Cout/64][9][hi NBd | lo NBd][64]
+// (only the slots of the 9 non-zero (plane, tap) pairs are written; the kernel never reads the others)
+__global__ void prep_weights_tcg_s2_kernel(const float* __restrict__ w, float* __restrict__ wb_fwd,
+                                           float* __restrict__ wb_dgrad, int Cout, int C) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)Cout * C * 9) return;
+  const int s = (int)(i % 3), r = (int)((i / 3) % 3);
+  const int c = (int)((i / 9) % C), co = (int)(i / (9L * C));
+  const float v = w[i];
+  const float hi = tc::to_tf32_rna(v), lo = tc::to_tf32_rna(v - hi);
+  const int ph = r != 1, pw = s != 1;                   // parity plane the tap reads (forward) / writes (dgrad)
+  const int plane = ph * 2 + pw;
+  if (wb_fwd) {
+    const int dh = r == 0 ? -1 : 0, dw = s == 0 ? -1 : 0;
+    const int tap = 3 * (dh + 1) + (dw + 1);
+    const int NB = s2_nb_fwd(C, Cout), G = 4 * C / 64;
+    const int g = plane * (C / 64) + c / 64;
+    const long base = ((((long)(co / NB) * G + g) * 9 + tap) * (2 * NB) + (co % NB)) * 64 + (c % 64);
+    wb_fwd[base] = hi;
+    wb_fwd[base + NB * 64] = lo;
+  }
+  if (wb_dgrad) {
+    const int dh = r == 0 ? 1 : 0, dw = s == 0 ? 1 : 0;
+    const int tap = 3 * (dh + 1) + (dw + 1);
+    const int NB = s2_nb_dgrad(C, Cout), G = Cout / 64;
+    const int n = plane * C + c;
+    const long base = ((((long)(n / NB) * G + co / 64) * 9 + tap) * (2 * NB) + (n % NB)) * 64 + (co % 64);
+    wb_dgrad[base] = hi;
+    wb_dgrad[base + NB * 64] = lo;
+  }
+}
+
+// dir 0: x [B][H][W][C] (dense, or the interior of a padded-flat buffer when x_pad) -> xs [B][H/2+2][W/2+2][4C] interior;
+// dir 1: the reverse.  One float4 per thread.
+__global__ void s2d_kernel(float* __restrict__ x, float* __restrict__ xs, int H, int W, int C, int x_pad, int dir,
+                           unsigned per_img4) {
+  const unsigned i4 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 >= per_img4) return;
+  const int b = blockIdx.y;
+  const unsigned c4n = (unsigned)C >> 2;
+  const unsigned p = i4 / c4n;
+  const int c = (int)(i4 - p * c4n) * 4;
+  const int ih = (int)(p / (unsigned)W), iw = (int)(p - (unsigned)ih * W);
+  const int Hs = H / 2 + 2, Ws = W / 2 + 2;
+  const long xo = x_pad ? (((long)b * (H + 2) + ih + 1) * (W + 2) + iw + 1) * C + c : (((long)b * H + ih) * W + iw) * C + c;
+  const long so = (((long)b * Hs + (ih >> 1) + 1) * Ws + (iw >> 1) + 1) * (4L * C) + ((ih & 1) * 2 + (iw & 1)) * C + c;
+  if (dir == 0) dktb_st4(xs + so, dktb_ld4(x + xo));
+  else dktb_st4(x + xo, dktb_ld4(xs + so));
+}
+
+TapMasks s2_masks(int dgrad, int per_plane) {
+  TapMasks tm;
+  tm.m = 0;
+  for (int plane = 0; plane < 4; ++plane) {
+    const int ph = plane >> 1, pw = plane & 1;
+    unsigned m = 0;
+    for (int dh = -1; dh <= 1; ++dh)
+      for (int dw = -1; dw <= 1; ++dw) {
+        const bool vh = dh == 0 || (ph == 1 && dh == (dgrad ? 1 : -1));
+        const bool vw = dw == 0 || (pw == 1 && dw == (dgrad ? 1 : -1));
+        if (vh && vw) m |= 1u << (3 * (dh + 1) + (dw + 1));
+      }
+    tm.m |= (unsigned long long)m << (16 * plane);
+  }
+  tm.per_plane = per_plane;
+  tm.by_cb = dgrad;
+  return tm;
+}
+
+}  // namespace
+
+DKTB_EXPORT int dktb_conv_tcg_s2_ok(int C, int Cout, int H, int W) {
+  return C % 64 == 0 && Cout % 64 == 0 && H % 2 == 0 && W % 2 == 0 && H >= 2 && W >= 2 && W / 2 + 3 <= 64;
+}
+DKTB_EXPORT long dktb_conv_tcg_s2_weight_floats(int C, int Cout) { return 4L * C * Cout * 9 * 2; }
+
+DKTB_EXPORT int dktb_prep_weights_tcg_s2(const float* w, float* wb_fwd, float* wb_dgrad, int Cout, int C,
+                                         cudaStream_t stream) {
+  DKTB_CHECK_ARG(w && C % 64 == 0 && Cout % 64 == 0);
+  const long n = (long)Cout * C * 9;
+  prep_weights_tcg_s2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(w, wb_fwd, wb_dgrad, Cout, C);
+  return dktb_launch_status();
+}
+
+// dir 0: x [B][H][W][C] -> xs [B][H/2+2][W/2+2][4C] (interior; the border of xs must already be zero); dir 1: xs -> x.
+// x_pad: x is the base of a padded-flat buffer [B][H+2][W+2][C] instead of a dense tensor.
+DKTB_EXPORT int dktb_s2d(float* x, float* xs, int B, int H, int W, int C, int x_pad, int dir, cudaStream_t stream) {
+  DKTB_CHECK_ARG(x && xs && B > 0 && B <= 65535 && H % 2 == 0 && W % 2 == 0 && C % 4 == 0 && (long)H * W * C / 4 < 2147483647L);
+  const unsigned per_img4 = (unsigned)((long)H * W * C / 4);
+  s2d_kernel<<<dim3((per_img4 + 255) / 256, B), 256, 0, stream>>>(x, xs, H, W, C, x_pad, dir, per_img4);
+  return dktb_launch_status();
+}
+
+// Ho, Wo: OUTPUT size (input H = 2 Ho, W = 2 Wo).  dgrad = 0: a = xs [B][Ho+2][Wo+2][4C] -> out [B][Ho+2][Wo+2][Cout]
+// (+ bias); dgrad = 1: a = dy [B][Ho+2][Wo+2][Cout] -> out = dxs [B][Ho+2][Wo+2][4C].  Both padded-flat, zero borders on
+// the input, interior of the output written.  wb: the matching tensor of dktb_prep_weights_tcg_s2.
+DKTB_EXPORT int dktb_conv_tcg_s2(const float* a, const float* wb, const float* bias, float* out, int* err, int B, int Ho,
+                                 int Wo, int C, int Cout, int dgrad, cudaStream_t stream) {
+  DKTB_CHECK_ARG(a && wb && out && err && B > 0 && Ho > 0 && Wo > 0);
+  DKTB_CHECK_ARG(dktb_conv_tcg_s2_ok(C, Cout, 2 * Ho, 2 * Wo));
+  if (!dgrad) {
+    const int NB = s2_nb_fwd(C, Cout);
+    // one parity plane per accumulator: K = C x {1, 2, 2, 4} taps
+    return conv_tcg_launch(a, wb, bias, out, err, B, Ho, Wo, 4 * C, Cout, 3, NB, C / 64, s2_masks(0, C / 64), stream);
+  }
+  const int NB = s2_nb_dgrad(C, Cout);
+  return conv_tcg_launch(a, wb, nullptr, out, err, B, Ho, Wo, Cout, 4 * C, 3, NB, 2, s2_masks(1, C / NB), stream);
 }
 
 // how many K-splits (CTAs per (group, block) pair) dktb_wgrad_tcg uses, and the scratch it needs (floats)

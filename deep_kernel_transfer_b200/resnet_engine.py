@@ -99,6 +99,19 @@ class ResNetEngine:
         return self.use_tcg and self.lib.conv_tcg_ok(m.in_channels, m.out_channels, m.kernel_size[0], m.stride[0],
                                                      m.padding[0], m.dilation[0], W)
 
+    def _s2_ok(self, m, H, W):
+        """Stride-2 3x3 / pad 1 layer that runs on the tcgen05 kernel over the space-to-depth input?"""
+        return (self.use_tcg and self.lib.has("dktb_conv_tcg_s2") and m.kernel_size[0] == 3 and m.stride[0] == 2
+                and m.padding[0] == 1 and m.dilation[0] == 1
+                and self.lib.conv_tcg_s2_ok(m.in_channels, m.out_channels, H, W))
+
+    def _s2_weights(self, m):
+        key = ("tcg_s2", id(m))
+        if key not in self._mma_w:
+            n = self.lib.conv_tcg_s2_weight_floats(m.in_channels, m.out_channels)
+            self._mma_w[key] = (self._new(n), self._new(n))
+        return self._mma_w[key]
+
     def _conv(self, x, m, relu=0):
         B, H, W, Cin = x.shape
         R = m.kernel_size[0]
@@ -117,6 +130,17 @@ class ResNetEngine:
             else:
                 out = self._new(B, Ho, Wo, Cout)
                 self.lib.conv_tcg(self._dense(x), wf, bias, out, self.tc_err, B, H, W, Cin, Cout, R, sm)
+            self.tape.append(("conv", x, out, m, (B, H, W, Cin, R, st, pad, dil)))
+            return out
+        if not relu and self._s2_ok(m, H, W):
+            # stride-2 3x3: the same tcgen05 kernel over the space-to-depth input (4 parity planes as 4 Cin channels)
+            Cout, sm = m.out_channels, _stream(self.dev)
+            wf, wd = self._s2_weights(m)
+            self.lib.prep_weights_tcg_s2(m.weight.data, wf, wd, Cout, Cin, sm)
+            xs = self._padbuf("s2", B, Ho, Wo, 4 * Cin)
+            self.lib.s2d(self._base(x), xs, B, H, W, Cin, int(self._is_pad(x)), 0, sm)
+            out = self._newpad(B, Ho, Wo, Cout, zero=False)
+            self.lib.conv_tcg_s2(xs, wf, bias, out._base, self.tc_err, B, Ho, Wo, Cin, Cout, 0, sm)
             self.tape.append(("conv", x, out, m, (B, H, W, Cin, R, st, pad, dil)))
             return out
         out = self._new(B, Ho, Wo, m.out_channels)
@@ -313,6 +337,21 @@ class ResNetEngine:
                     continue
                 ns = lib.conv2d_wgrad_nsplit(y.shape[0] * y.shape[1] * y.shape[2])
                 scratch = self._new(ns * R * R * Cin * Cout)
+                if self._s2_ok(m, H, W):
+                    # input gradient on tcgen05: dy -> gradient of the space-to-depth input -> unpacked into gx's layout
+                    Ho, Wo = y.shape[1], y.shape[2]
+                    dxs = self._padbuf("s2", B, Ho, Wo, 4 * Cin)
+                    lib.conv_tcg_s2(self._padded_base(gy, "out"), self._s2_weights(m)[1], None, dxs, self.tc_err, B, Ho, Wo,
+                                    Cin, Cout, 1, st)
+                    gx = self._like(x)
+                    lib.s2d(self._base(gx), dxs, B, H, W, Cin, int(self._is_pad(gx)), 1, st)
+                    lib.conv2d_wgrad(self._dense(x), self._dense(gy), None, m.weight.grad,
+                                     m.bias.grad if m.bias is not None else None, scratch, B, H, W, Cin, Cout, R, R, stv, pad,
+                                     dil, 0, st)
+                    if self.trace is not None:
+                        self.trace.append((rec, gy, gx.clone(), m.weight.grad.clone()))
+                    give(x, gx)
+                    continue
                 xd, gy = self._dense(x), self._dense(gy)
                 lib.conv2d_wgrad(xd, gy, None, m.weight.grad, m.bias.grad if m.bias is not None else None, scratch, B, H, W,
                                  Cin, Cout, R, R, stv, pad, dil, 0, st)

@@ -86,6 +86,17 @@ long dktb_conv_tcg_weight_floats(int Cin, int Cout, int R);
 int dktb_prep_weights_tcg(const float* w, float* wb_fwd, float* wb_dgrad, int Cout, int Cin, int R, cudaStream_t stream);
 int dktb_conv_tcg(const float* a, const float* wb, const float* bias, float* out, int* err, int B, int H, int W, int Cin,
                   int Cout, int R, cudaStream_t stream);
+/* Stride-2 3x3 / pad 1 layers (backbone.py:150-152, 195-197) on the same tcgen05 kernel: a stride-1 convolution over the
+ * space-to-depth input xs [B][H/2+2][W/2+2][4C] (padded-flat, channel = ((ih&1)*2 + (iw&1))*C + c), the 27 structurally
+ * zero (parity plane, tap) pairs skipped.  dktb_s2d packs x (dense, or padded-flat when x_pad) into xs (dir 0) or unpacks
+ * (dir 1); dktb_conv_tcg_s2: dgrad = 0: xs -> out [B][Ho+2][Wo+2][Cout]; dgrad = 1: dy [.., Cout] -> dxs [.., 4C]. */
+int dktb_conv_tcg_s2_ok(int C, int Cout, int H, int W);
+long dktb_conv_tcg_s2_weight_floats(int C, int Cout);
+int dktb_prep_weights_tcg_s2(const float* w, float* wb_fwd, float* wb_dgrad, int Cout, int C, cudaStream_t stream);
+int dktb_s2d(float* x, float* xs, int B, int H, int W, int C, int x_pad, int dir, cudaStream_t stream);
+int dktb_conv_tcg_s2(const float* a, const float* wb, const float* bias, float* out, int* err, int B, int Ho, int Wo, int C,
+                     int Cout, int dgrad, cudaStream_t stream);
+
 /* ResNet stem (backbone.py:336-340: Conv2d(3, 64, 7, stride 2, padding 3)) on tcgen05: x [B,3,H,W] NCHW -> y [B,H/2,W/2,64]
  * NHWC; implicit GEMM over k = ci*49 + r*7 + s (147 -> 160), 3xTF32.  wb: dktb_stem_tc_weight_floats() floats written by
  * dktb_prep_weights_stem_tc from w [64][3][7][7].  err: device int (zero-initialised), 1 = a pipeline wait timed out. */

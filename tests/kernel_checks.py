@@ -983,6 +983,46 @@ def check_conv_tcg(lib, dev, B=2, H=6, W=5, Cin=64, Cout=128, R=3, seed=100, rto
         _close(db, br.grad, rtol=rtol, atol=1e-4, what="conv_tcg bias grad")
 
 
+def check_conv_tcg_s2(lib, dev, B=2, H=8, W=10, C=64, Cout=128, seed=130, rtol=2e-5, bias=False, x_pad=False):
+    """Stride-2 3x3 / pad 1 convolution through the space-to-depth path of csrc/conv_tcg.cu (dktb_s2d +
+    dktb_conv_tcg_s2): forward and dgrad against torch in float64; pack / unpack round trip."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, C, H, W, generator=g)
+    w = torch.randn(Cout, C, 3, 3, generator=g) * (1.0 / (C * 9) ** 0.5)
+    b = torch.randn(Cout, generator=g) if bias else None
+    xr = x.double().clone().requires_grad_(True)
+    ref = F.conv2d(xr, w.double(), b.double() if bias else None, stride=2, padding=1)
+    gout = torch.randn(ref.shape, generator=g)
+    (ref * gout.double()).sum().backward()
+    Ho, Wo = H // 2, W // 2
+    assert lib.conv_tcg_s2_ok(C, Cout, H, W)
+    n = lib.conv_tcg_s2_weight_floats(C, Cout)
+    wf, wd = torch.full((n,), float("nan"), device=dev), torch.full((n,), float("nan"), device=dev)   # unused slots: never read
+    lib.prep_weights_tcg_s2(w.to(dev), wf, wd, Cout, C, 0)
+    err = torch.zeros(1, device=dev, dtype=torch.int32)
+    xd = (to_padded_nhwc(x) if x_pad else x.permute(0, 2, 3, 1).contiguous()).to(dev)
+    xs = torch.zeros(B, Ho + 2, Wo + 2, 4 * C, device=dev)
+    lib.s2d(xd, xs, B, H, W, C, int(x_pad), 0, 0)
+    yp = torch.full((B, Ho + 2, Wo + 2, Cout), 7.0, device=dev)
+    lib.conv_tcg_s2(xs, wf, b.to(dev) if bias else None, yp, err, B, Ho, Wo, C, Cout, 0, 0)
+    assert int(err) == 0
+    _close(from_padded_nhwc(yp.cpu()), ref.detach(), rtol=rtol, atol=1e-6, what="conv_tcg_s2 fwd %d->%d" % (C, Cout))
+    assert float((yp.cpu()[:, 0] - 7.0).abs().max()) == 0.0 and float((yp.cpu()[:, :, -1] - 7.0).abs().max()) == 0.0
+    gp = to_padded_nhwc(gout).to(dev)
+    dxs = torch.zeros(B, Ho + 2, Wo + 2, 4 * C, device=dev)
+    lib.conv_tcg_s2(gp, wd, None, dxs, err, B, Ho, Wo, C, Cout, 1, 0)
+    assert int(err) == 0
+    gx = torch.full_like(xd, 7.0)
+    lib.s2d(gx, dxs, B, H, W, C, int(x_pad), 1, 0)
+    got = from_padded_nhwc(gx.cpu()) if x_pad else gx.cpu().permute(0, 3, 1, 2)
+    _close(got, xr.grad, rtol=rtol, atol=1e-6, what="conv_tcg_s2 dgrad %d->%d" % (C, Cout))
+    if x_pad:
+        assert float((gx.cpu()[:, 0] - 7.0).abs().max()) == 0.0
+    back = torch.zeros_like(xd)
+    lib.s2d(back, xs, B, H, W, C, int(x_pad), 1, 0)
+    assert torch.equal(back[:, 1:-1, 1:-1] if x_pad else back, xd[:, 1:-1, 1:-1] if x_pad else xd), "s2d round trip"
+
+
 def check_stem_tc(lib, dev, B=2, H=32, W=32, seed=120, rtol=2e-5, bias=False):
     """ResNet stem (7x7, stride 2, pad 3, 3 -> 64) on tcgen05 (csrc/stem_tc.cu) against torch in float64."""
     g = torch.Generator().manual_seed(seed)

@@ -125,6 +125,15 @@ def test_resnet_ops(lib):
     kc.check_resnet_ops(lib, DEV, E=2, ipe=2, H=32, W=33, C=64, seed=82)      # BatchNorm sums split over the pixels (4 splits)
 
 
+@pytest.mark.parametrize("cfg", [dict(), dict(B=3, H=56, W=56, C=64, Cout=128, seed=131),             # ResNet18 layer2 down-sampling
+                                 dict(B=3, H=28, W=28, C=128, Cout=256, seed=132, x_pad=True),  # layer3, padded-flat input
+                                 dict(B=5, H=14, W=14, C=256, Cout=512, seed=133, bias=True),   # layer4
+                                 dict(B=2, H=28, W=28, C=128, Cout=128, seed=134),              # ResNet50 bottleneck C2
+                                 dict(B=1, H=6, W=122, C=64, Cout=64, seed=135)])               # widest supported row
+def test_conv_tcg_s2(lib, cfg):
+    kc.check_conv_tcg_s2(lib, DEV, **cfg)
+
+
 @pytest.mark.parametrize("cfg", [dict(), dict(B=1, H=20, W=30, seed=121, bias=True),              # ragged band and column tile
                                  dict(B=2, H=84, W=84, seed=122),                                # miniImageNet resolution
                                  dict(B=3, H=224, W=224, seed=123)])                             # the reference's ResNet resolution
