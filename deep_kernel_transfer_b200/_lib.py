@@ -45,6 +45,7 @@ SIGNATURES = {
     "dktb_conv_tcg_s2_weight_floats": ("ii", ctypes.c_long),
     "dktb_prep_weights_tcg_s2": ("pppiis", ctypes.c_int),
     "dktb_s2d": ("ppiiiiiis", ctypes.c_int),
+    "dktb_subsample2": ("ppiiiiiis", ctypes.c_int),
     "dktb_conv_tcg_s2": ("pppppiiiiiis", ctypes.c_int),
     "dktb_stem_tc_ok": ("iiiiiiii", ctypes.c_int),
     "dktb_stem_tc_weight_floats": ("", ctypes.c_long),

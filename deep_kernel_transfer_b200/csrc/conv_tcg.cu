@@ -790,6 +790,28 @@ __global__ void s2d_kernel(float* __restrict__ x, float* __restrict__ xs, int H,
   else dktb_st4(x + xo, dktb_ld4(xs + so));
 }
 
+// Stride-2 1x1 convolutions (the shortcut of a down-sampling block, backbone.py:158-160, 205-207) read every second pixel
+// of every second row: dir 0 gathers them into a dense [B][H/2][W/2][C] tensor (then a plain GEMM, dktb_conv_tcg R = 1);
+// dir 1 scatters a gradient back (the skipped pixels get zeros).  x: dense, or padded-flat when x_pad.
+__global__ void subsample2_kernel(float* __restrict__ x, float* __restrict__ xg, int H, int W, int C, int x_pad, int dir,
+                                  unsigned per_img4) {
+  const unsigned i4 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 >= per_img4) return;
+  const int b = blockIdx.y;
+  const unsigned c4n = (unsigned)C >> 2;
+  const unsigned p = i4 / c4n;
+  const int c = (int)(i4 - p * c4n) * 4;
+  const int ih = (int)(p / (unsigned)W), iw = (int)(p - (unsigned)ih * W);
+  const bool even = !((ih | iw) & 1);
+  const long xo = x_pad ? (((long)b * (H + 2) + ih + 1) * (W + 2) + iw + 1) * C + c : (((long)b * H + ih) * W + iw) * C + c;
+  const long go = (((long)b * (H / 2) + (ih >> 1)) * (W / 2) + (iw >> 1)) * C + c;
+  if (dir == 0) {
+    if (even) dktb_st4(xg + go, dktb_ld4(x + xo));
+  } else {
+    dktb_st4(x + xo, even ? dktb_ld4(xg + go) : make_float4(0.f, 0.f, 0.f, 0.f));
+  }
+}
+
 TapMasks s2_masks(int dgrad, int per_plane) {
   TapMasks tm;
   tm.m = 0;
@@ -830,6 +852,14 @@ DKTB_EXPORT int dktb_s2d(float* x, float* xs, int B, int H, int W, int C, int x_
   DKTB_CHECK_ARG(x && xs && B > 0 && B <= 65535 && H % 2 == 0 && W % 2 == 0 && C % 4 == 0 && (long)H * W * C / 4 < 2147483647L);
   const unsigned per_img4 = (unsigned)((long)H * W * C / 4);
   s2d_kernel<<<dim3((per_img4 + 255) / 256, B), 256, 0, stream>>>(x, xs, H, W, C, x_pad, dir, per_img4);
+  return dktb_launch_status();
+}
+
+// dir 0: xg [B][H/2][W/2][C] <- x[:, ::2, ::2, :]; dir 1: x <- xg at the even pixels, zeros elsewhere.  x_pad as dktb_s2d.
+DKTB_EXPORT int dktb_subsample2(float* x, float* xg, int B, int H, int W, int C, int x_pad, int dir, cudaStream_t stream) {
+  DKTB_CHECK_ARG(x && xg && B > 0 && B <= 65535 && H % 2 == 0 && W % 2 == 0 && C % 4 == 0 && (long)H * W * C / 4 < 2147483647L);
+  const unsigned per_img4 = (unsigned)((long)H * W * C / 4);
+  subsample2_kernel<<<dim3((per_img4 + 255) / 256, B), 256, 0, stream>>>(x, xg, H, W, C, x_pad, dir, per_img4);
   return dktb_launch_status();
 }
 

@@ -105,6 +105,12 @@ class ResNetEngine:
                 and m.padding[0] == 1 and m.dilation[0] == 1
                 and self.lib.conv_tcg_s2_ok(m.in_channels, m.out_channels, H, W))
 
+    def _sub2_ok(self, m, H, W):
+        """Stride-2 1x1 shortcut that runs as a gather + tcgen05 GEMM?"""
+        return (self.use_tcg and self.lib.has("dktb_subsample2") and m.kernel_size[0] == 1 and m.stride[0] == 2
+                and m.padding[0] == 0 and H % 2 == 0 and W % 2 == 0
+                and self.lib.conv_tcg_ok(m.in_channels, m.out_channels, 1, 1, 0, 1, W // 2))
+
     def _s2_weights(self, m):
         key = ("tcg_s2", id(m))
         if key not in self._mma_w:
@@ -141,6 +147,17 @@ class ResNetEngine:
             self.lib.s2d(self._base(x), xs, B, H, W, Cin, int(self._is_pad(x)), 0, sm)
             out = self._newpad(B, Ho, Wo, Cout, zero=False)
             self.lib.conv_tcg_s2(xs, wf, bias, out._base, self.tc_err, B, Ho, Wo, Cin, Cout, 0, sm)
+            self.tape.append(("conv", x, out, m, (B, H, W, Cin, R, st, pad, dil)))
+            return out
+        if not relu and self._sub2_ok(m, H, W):
+            # stride-2 1x1 shortcut: every second pixel gathered into a dense tensor, then the tcgen05 GEMM
+            Cout, sm = m.out_channels, _stream(self.dev)
+            wf, wd = self._tcg_weights(m)
+            self.lib.prep_weights_tcg(m.weight.data, wf, wd, Cout, Cin, 1, sm)
+            xg = self._new(B, Ho, Wo, Cin)
+            self.lib.subsample2(self._base(x), xg, B, H, W, Cin, int(self._is_pad(x)), 0, sm)
+            out = self._new(B, Ho, Wo, Cout)
+            self.lib.conv_tcg(xg, wf, bias, out, self.tc_err, B, Ho, Wo, Cin, Cout, 1, sm)
             self.tape.append(("conv", x, out, m, (B, H, W, Cin, R, st, pad, dil)))
             return out
         out = self._new(B, Ho, Wo, m.out_channels)
@@ -337,6 +354,21 @@ class ResNetEngine:
                     continue
                 ns = lib.conv2d_wgrad_nsplit(y.shape[0] * y.shape[1] * y.shape[2])
                 scratch = self._new(ns * R * R * Cin * Cout)
+                if self._sub2_ok(m, H, W):
+                    # stride-2 1x1 shortcut: GEMMs on the gathered input, gradient scattered back (zeros at skipped pixels)
+                    Ho, Wo = y.shape[1], y.shape[2]
+                    xg, gyd = self._new(B, Ho, Wo, Cin), self._dense(gy)
+                    lib.subsample2(self._base(x), xg, B, H, W, Cin, int(self._is_pad(x)), 0, st)
+                    scr = self._new(lib.wgrad_tcg_scratch_floats(B, Ho, Wo, Cin, Cout, 1))
+                    lib.wgrad_tcg(xg, gyd, m.weight.grad, m.bias.grad if m.bias is not None else None, scr, self.tc_err, B,
+                                  Ho, Wo, Cin, Cout, 1, st)
+                    lib.conv_tcg(gyd, self._tcg_weights(m)[1], None, xg, self.tc_err, B, Ho, Wo, Cout, Cin, 1, st)
+                    gx = self._like(x)
+                    lib.subsample2(self._base(gx), xg, B, H, W, Cin, int(self._is_pad(gx)), 1, st)
+                    if self.trace is not None:
+                        self.trace.append((rec, gy, gx.clone(), m.weight.grad.clone()))
+                    give(x, gx)
+                    continue
                 if self._s2_ok(m, H, W):
                     # input gradient on tcgen05: dy -> gradient of the space-to-depth input -> unpacked into gx's layout
                     Ho, Wo = y.shape[1], y.shape[2]

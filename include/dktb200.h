@@ -94,6 +94,9 @@ int dktb_conv_tcg_s2_ok(int C, int Cout, int H, int W);
 long dktb_conv_tcg_s2_weight_floats(int C, int Cout);
 int dktb_prep_weights_tcg_s2(const float* w, float* wb_fwd, float* wb_dgrad, int Cout, int C, cudaStream_t stream);
 int dktb_s2d(float* x, float* xs, int B, int H, int W, int C, int x_pad, int dir, cudaStream_t stream);
+/* stride-2 1x1 shortcuts: gather x[:, ::2, ::2, :] into a dense tensor (dir 0; then dktb_conv_tcg with R = 1) or scatter a
+ * gradient back, zeros at the skipped pixels (dir 1) */
+int dktb_subsample2(float* x, float* xg, int B, int H, int W, int C, int x_pad, int dir, cudaStream_t stream);
 int dktb_conv_tcg_s2(const float* a, const float* wb, const float* bias, float* out, int* err, int B, int Ho, int Wo, int C,
                      int Cout, int dgrad, cudaStream_t stream);
 

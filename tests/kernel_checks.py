@@ -1018,6 +1018,16 @@ def check_conv_tcg_s2(lib, dev, B=2, H=8, W=10, C=64, Cout=128, seed=130, rtol=2
     _close(got, xr.grad, rtol=rtol, atol=1e-6, what="conv_tcg_s2 dgrad %d->%d" % (C, Cout))
     if x_pad:
         assert float((gx.cpu()[:, 0] - 7.0).abs().max()) == 0.0
+    # stride-2 1x1 shortcut helpers: gather of every second pixel, scatter with zeros elsewhere
+    xg = torch.empty(B, Ho, Wo, C, device=dev)
+    lib.subsample2(xd, xg, B, H, W, C, int(x_pad), 0, 0)
+    x_nhwc = x.permute(0, 2, 3, 1)
+    assert torch.equal(xg.cpu(), x_nhwc[:, ::2, ::2, :].contiguous()), "subsample2 gather"
+    sc = torch.full_like(xd, 7.0)
+    lib.subsample2(sc, xg, B, H, W, C, int(x_pad), 1, 0)
+    want = torch.zeros(B, H, W, C)
+    want[:, ::2, ::2, :] = x_nhwc[:, ::2, ::2, :]
+    assert torch.equal(sc.cpu()[:, 1:-1, 1:-1] if x_pad else sc.cpu(), want), "subsample2 scatter"
     back = torch.zeros_like(xd)
     lib.s2d(back, xs, B, H, W, C, int(x_pad), 1, 0)
     assert torch.equal(back[:, 1:-1, 1:-1] if x_pad else back, xd[:, 1:-1, 1:-1] if x_pad else xd), "s2d round trip"
