@@ -47,6 +47,9 @@ SIGNATURES = {
     "dktb_s2d": ("ppiiiiiis", ctypes.c_int),
     "dktb_subsample2": ("ppiiiiiis", ctypes.c_int),
     "dktb_conv_tcg_s2": ("pppppiiiiiis", ctypes.c_int),
+    "dktb_wgrad_tcg_s2_ok": ("iiii", ctypes.c_int),
+    "dktb_wgrad_tcg_s2_scratch_floats": ("iiiii", ctypes.c_long),
+    "dktb_wgrad_tcg_s2": ("ppppppiiiiis", ctypes.c_int),
     "dktb_stem_tc_ok": ("iiiiiiii", ctypes.c_int),
     "dktb_stem_tc_weight_floats": ("", ctypes.c_long),
     "dktb_prep_weights_stem_tc": ("pps", ctypes.c_int),

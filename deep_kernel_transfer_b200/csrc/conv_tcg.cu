@@ -373,7 +373,7 @@ __device__ __forceinline__ void wg_gather16(const unsigned char* __restrict__ xb
 
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_tcg_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g,
-                      float* __restrict__ partial, long total_rows, int Wp, int halo_pad, int ntaps, int nblk,
+                      float* __restrict__ partial, long total_rows, int Wp, int halo_pad, int ntaps, int nblk, int np, int Cs2,
                       int* __restrict__ err) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -385,10 +385,17 @@ conv_wgrad_tcg_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (*reinterpret_cast<volatile int*>(err) != 0) return;
   const int pair = blockIdx.y, g_in = pair / nblk, cb = pair % nblk;
-  const int ngroups = (ntaps + 1) / 2;                      // tap pairs
+  // np = 1: an ordinary layer, slot = tap.  np = 4: the space-to-depth input of a stride-2 3x3 layer (Cs2 channels per
+  // parity plane): this CTA's 64 input channels are loaded from all four planes and the 9 slots are the (plane, tap) pairs
+  // that carry weights -- plane 0: tap 4; plane 1: taps 3, 4; plane 2: taps 1, 4; plane 3: taps 0, 1, 3, 4.
+  constexpr unsigned kS2Plane = 0u | (1u << 2) | (1u << 4) | (2u << 6) | (2u << 8) | (3u << 10) | (3u << 12) | (3u << 14) | (3u << 16);
+  constexpr unsigned long long kS2Tap = 4ull | (3ull << 4) | (4ull << 8) | (1ull << 12) | (4ull << 16) | (0ull << 20) |
+                                        (1ull << 24) | (3ull << 28) | (4ull << 32);
+  const int ngroups = (ntaps + 1) / 2;                      // slot pairs
   const int lead = ntaps == 9 ? Wp + 1 : 0;
   const int x_half_bytes = halo_pad * 128;
-  const int stage_bytes = 2 * x_half_bytes + 8192 + 16384;   // X raw | G raw | B hi | B lo
+  const int xr_bytes = np * 2 * x_half_bytes;                // X raw: [plane][channel half][halo row][128 B]
+  const int stage_bytes = xr_bytes + 8192 + 16384;           // X raw | G raw | B hi | B lo
   const long nkb = (total_rows + kKR - 1) / kKR;
 
   if (tid == 0) {
@@ -417,13 +424,15 @@ conv_wgrad_tcg_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       if (!tc::mbar_wait(&bar_raw_empty[s], ph ^ 1)) { s_err = 1; break; }
       if (tc::elect_one()) {
         unsigned char* st = smem + s * stage_bytes;
-        tc::mbar_expect_tx(&bar_raw_full[s], 2 * x_half_bytes + 8192);
+        tc::mbar_expect_tx(&bar_raw_full[s], xr_bytes + 8192);
         const long q0 = kb * kKR;
         const int xrow0 = (int)(q0 - lead);
         for (int h = 0; h < 2; ++h) {
-          for (int r = 0; r < halo_pad; r += kHaloBox)
-            tc::tma_load_2d(st + h * x_half_bytes + r * 128, &map_x, &bar_raw_full[s], g_in * 64 + h * 32, xrow0 + r);
-          tc::tma_load_2d(st + 2 * x_half_bytes + h * 4096, &map_g, &bar_raw_full[s], cb * 64 + h * 32, (int)q0);
+          for (int pl = 0; pl < np; ++pl)
+            for (int r = 0; r < halo_pad; r += kHaloBox)
+              tc::tma_load_2d(st + (pl * 2 + h) * x_half_bytes + r * 128, &map_x, &bar_raw_full[s],
+                              pl * Cs2 + g_in * 64 + h * 32, xrow0 + r);
+          tc::tma_load_2d(st + xr_bytes + h * 4096, &map_g, &bar_raw_full[s], cb * 64 + h * 32, (int)q0);
         }
       }
       __syncwarp();
@@ -436,7 +445,7 @@ conv_wgrad_tcg_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       const int s = n & 1, ph = (n >> 1) & 1;
       ok = tc::mbar_wait(&bar_bfull[s], ph);
       if (!ok) break;
-      const uint32_t bbase = tc::smem_u32(smem + s * stage_bytes + 2 * x_half_bytes + 8192);
+      const uint32_t bbase = tc::smem_u32(smem + s * stage_bytes + xr_bytes + 8192);
       for (int g = 0; g < ngroups && ok; ++g, ++ai) {
         const int sa = ai % kWgAStages, pa = (ai / kWgAStages) & 1;
         ok = tc::mbar_wait(&bar_afull[sa], pa);
@@ -483,8 +492,8 @@ conv_wgrad_tcg_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       if (!ok) break;
       unsigned char* st = smem + s * stage_bytes;
       {
-        const unsigned char* graw = st + 2 * x_half_bytes + (co >> 5) * 4096;
-        unsigned char* bhi = st + 2 * x_half_bytes + 8192 + co * 128;
+        const unsigned char* graw = st + xr_bytes + (co >> 5) * 4096;
+        unsigned char* bhi = st + xr_bytes + 8192 + co * 128;
         unsigned char* blo = bhi + 8192;
         const int cq = (co & 31) >> 2, cr = co & 3;
 #pragma unroll
@@ -507,11 +516,13 @@ conv_wgrad_tcg_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       }
       for (int g = 0; g < ngroups && ok; ++g, ++ai) {
         const int sa = ai % kWgAStages, pa = (ai / kWgAStages) & 1;
-        const int tap = 2 * g + tsel;
+        const int slot = 2 * g + tsel;
         uint32_t hi[16], lo[16];
-        if (tap < ntaps) {
+        if (slot < ntaps) {
+          const int tap = np == 1 ? slot : (int)((kS2Tap >> (4 * slot)) & 15);
+          const int pl = np == 1 ? 0 : (int)((kS2Plane >> (2 * slot)) & 3);
           const int shift = (ntaps == 9 ? (tap / 3) * Wp + (tap % 3) : 0) + set * 16;
-          const unsigned char* xb = st + (ci >> 5) * x_half_bytes + shift * 128;
+          const unsigned char* xb = st + (pl * 2 + (ci >> 5)) * x_half_bytes + shift * 128;
           switch (shift & 7) {
             case 0: wg_gather16<0>(xb, xoff, hi, lo); break;
             case 1: wg_gather16<1>(xb, xoff, hi, lo); break;
@@ -917,11 +928,73 @@ DKTB_EXPORT int dktb_wgrad_tcg(const float* x, const float* gy, float* dw, float
   cudaFuncSetAttribute(conv_wgrad_tcg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int nsplit = wgrad_tcg_nsplit(rows, npairs);
   conv_wgrad_tcg_kernel<<<dim3(nsplit, npairs), kWgThreads, smem, stream>>>(map_x, map_g, scratch, rows, Wp, halo_pad, ntaps,
-                                                                           nblk, err);
+                                                                           nblk, 1, 0, err);
   int rc = dktb_launch_status();
   if (rc != 0) return rc;
   conv_wgrad_tcg_reduce_kernel<<<dim3((ntaps * 4096 + 64 + 255) / 256, npairs), 256, 0, stream>>>(scratch, nsplit, nblk, Cin,
                                                                                                  ntaps, dw, db);
+  return dktb_launch_status();
+}
+
+// partial [pair = cg*nblk + cb][split][slot][ci][co] of a stride-2 layer (slot = the 9 (parity plane, tap) pairs of
+// conv_wgrad_tcg_kernel) -> dw [Cout][C][3][3], db [Cout] (from the cg = 0 pairs)
+__global__ void conv_wgrad_tcg_s2_reduce_kernel(const float* __restrict__ partial, int nsplit, int nblk, int C,
+                                                float* __restrict__ dw, float* __restrict__ db) {
+  const int pair = blockIdx.y, cg = pair / nblk, cb = pair % nblk;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nw = 9 * 64 * 64;
+  if (i >= nw + 64) return;
+  if (i >= nw && (db == nullptr || cg != 0)) return;
+  const float* p = partial + (long)pair * nsplit * kWgPStride + i;
+  float t = 0.f;
+  for (int s = 0; s < nsplit; ++s) t += p[(long)s * kWgPStride];
+  if (i < nw) {
+    const int co = i % 64, ci = (i / 64) % 64, slot = i / 4096;
+    const int planes[9] = {0, 1, 1, 2, 2, 3, 3, 3, 3}, taps[9] = {4, 3, 4, 1, 4, 0, 1, 3, 4};
+    const int ph = planes[slot] >> 1, pw = planes[slot] & 1, dh = taps[slot] / 3 - 1, dv = taps[slot] % 3 - 1;
+    const int r = ph == 0 ? 1 : (dh == -1 ? 0 : 2), sx = pw == 0 ? 1 : (dv == -1 ? 0 : 2);
+    dw[(((long)(cb * 64 + co) * C + cg * 64 + ci) * 3 + r) * 3 + sx] = t;
+  } else {
+    db[cb * 64 + (i - nw)] = t;
+  }
+}
+
+// Weight gradient of a stride-2 3x3 layer from its space-to-depth input: xs [B][Ho+2][Wo+2][4C], gy [B][Ho+2][Wo+2][Cout]
+// (both padded-flat, zero borders) -> dw [Cout][C][3][3] (overwritten), db [Cout] or NULL.  One CTA column per (64 input
+// channels, 64 output channels) pair: the four parity planes of those channels are staged together, so a K-block feeds
+// the same five tap-pair accumulators as an ordinary 3x3 layer.
+DKTB_EXPORT int dktb_wgrad_tcg_s2_ok(int C, int Cout, int H, int W) {
+  if (!dktb_conv_tcg_s2_ok(C, Cout, H, W)) return 0;
+  const int halo_pad = (kKR + (W / 2 + 3) + kHaloBox - 1) / kHaloBox * kHaloBox;
+  return 2 * (8 * halo_pad * 128 + 8192 + 16384) + 1024 <= 227 * 1024;
+}
+DKTB_EXPORT long dktb_wgrad_tcg_s2_scratch_floats(int B, int Ho, int Wo, int C, int Cout) {
+  const long rows = (long)B * (Ho + 2) * (Wo + 2);
+  const int npairs = (C / 64) * (Cout / 64);
+  return (long)npairs * wgrad_tcg_nsplit(rows, npairs) * kWgPStride;
+}
+DKTB_EXPORT int dktb_wgrad_tcg_s2(const float* xs, const float* gy, float* dw, float* db, float* scratch, int* err, int B,
+                                  int Ho, int Wo, int C, int Cout, cudaStream_t stream) {
+  DKTB_CHECK_ARG(xs && gy && dw && scratch && err && B > 0 && Ho > 0 && Wo > 0);
+  DKTB_CHECK_ARG(dktb_wgrad_tcg_s2_ok(C, Cout, 2 * Ho, 2 * Wo));
+  const int Wp = Wo + 2;
+  const long rows = (long)B * (Ho + 2) * Wp;
+  DKTB_CHECK_ARG(rows < 2147483000L);
+  const int nblk = Cout / 64, npairs = (C / 64) * nblk;
+  DKTB_CHECK_ARG(npairs <= 65535);
+  const int halo_pad = (kKR + (Wp + 1) + kHaloBox - 1) / kHaloBox * kHaloBox;      // taps reach back (dh, dw in {-1, 0}) only
+  const int smem = 2 * (8 * halo_pad * 128 + 8192 + 16384) + 1024;
+  CUtensorMap map_x, map_g;
+  if (tc_make_tmap_2d(&map_x, xs, (uint64_t)(4 * C), (uint64_t)rows, 32, kHaloBox) != 0) return DKTB_BAD_ARG - 1;
+  if (tc_make_tmap_2d(&map_g, gy, (uint64_t)Cout, (uint64_t)rows, 32, kKR) != 0) return DKTB_BAD_ARG - 1;
+  cudaFuncSetAttribute(conv_wgrad_tcg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int nsplit = wgrad_tcg_nsplit(rows, npairs);
+  conv_wgrad_tcg_kernel<<<dim3(nsplit, npairs), kWgThreads, smem, stream>>>(map_x, map_g, scratch, rows, Wp, halo_pad, 9, nblk,
+                                                                           4, C, err);
+  int rc = dktb_launch_status();
+  if (rc != 0) return rc;
+  conv_wgrad_tcg_s2_reduce_kernel<<<dim3((9 * 4096 + 64 + 255) / 256, npairs), 256, 0, stream>>>(scratch, nsplit, nblk, C, dw,
+                                                                                                db);
   return dktb_launch_status();
 }
 

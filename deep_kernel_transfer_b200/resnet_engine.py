@@ -370,16 +370,21 @@ class ResNetEngine:
                     give(x, gx)
                     continue
                 if self._s2_ok(m, H, W):
-                    # input gradient on tcgen05: dy -> gradient of the space-to-depth input -> unpacked into gx's layout
+                    # tcgen05: input gradient dy -> gradient of the space-to-depth input -> unpacked into gx's layout; weight
+                    # gradient from the (re-packed) space-to-depth input where its four-plane staging fits shared memory
                     Ho, Wo = y.shape[1], y.shape[2]
-                    dxs = self._padbuf("s2", B, Ho, Wo, 4 * Cin)
-                    lib.conv_tcg_s2(self._padded_base(gy, "out"), self._s2_weights(m)[1], None, dxs, self.tc_err, B, Ho, Wo,
-                                    Cin, Cout, 1, st)
+                    xs, gyp = self._padbuf("s2", B, Ho, Wo, 4 * Cin), self._padded_base(gy, "out")
+                    bg = m.bias.grad if m.bias is not None else None
+                    if lib.wgrad_tcg_s2_ok(Cin, Cout, H, W):
+                        lib.s2d(self._base(x), xs, B, H, W, Cin, int(self._is_pad(x)), 0, st)
+                        scr = self._new(lib.wgrad_tcg_s2_scratch_floats(B, Ho, Wo, Cin, Cout))
+                        lib.wgrad_tcg_s2(xs, gyp, m.weight.grad, bg, scr, self.tc_err, B, Ho, Wo, Cin, Cout, st)
+                    else:
+                        lib.conv2d_wgrad(self._dense(x), self._dense(gy), None, m.weight.grad, bg, scratch, B, H, W, Cin, Cout,
+                                         R, R, stv, pad, dil, 0, st)
+                    lib.conv_tcg_s2(gyp, self._s2_weights(m)[1], None, xs, self.tc_err, B, Ho, Wo, Cin, Cout, 1, st)
                     gx = self._like(x)
-                    lib.s2d(self._base(gx), dxs, B, H, W, Cin, int(self._is_pad(gx)), 1, st)
-                    lib.conv2d_wgrad(self._dense(x), self._dense(gy), None, m.weight.grad,
-                                     m.bias.grad if m.bias is not None else None, scratch, B, H, W, Cin, Cout, R, R, stv, pad,
-                                     dil, 0, st)
+                    lib.s2d(self._base(gx), xs, B, H, W, Cin, int(self._is_pad(gx)), 1, st)
                     if self.trace is not None:
                         self.trace.append((rec, gy, gx.clone(), m.weight.grad.clone()))
                     give(x, gx)

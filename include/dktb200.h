@@ -99,6 +99,12 @@ int dktb_s2d(float* x, float* xs, int B, int H, int W, int C, int x_pad, int dir
 int dktb_subsample2(float* x, float* xg, int B, int H, int W, int C, int x_pad, int dir, cudaStream_t stream);
 int dktb_conv_tcg_s2(const float* a, const float* wb, const float* bias, float* out, int* err, int B, int Ho, int Wo, int C,
                      int Cout, int dgrad, cudaStream_t stream);
+/* weight gradient of the same layers (W/2 <= 29: the four parity planes of 64 channels are staged together): xs, gy
+ * padded-flat with zero borders -> dw [Cout][C][3][3], db [Cout] or NULL */
+int dktb_wgrad_tcg_s2_ok(int C, int Cout, int H, int W);
+long dktb_wgrad_tcg_s2_scratch_floats(int B, int Ho, int Wo, int C, int Cout);
+int dktb_wgrad_tcg_s2(const float* xs, const float* gy, float* dw, float* db, float* scratch, int* err, int B, int Ho, int Wo,
+                      int C, int Cout, cudaStream_t stream);
 
 /* ResNet stem (backbone.py:336-340: Conv2d(3, 64, 7, stride 2, padding 3)) on tcgen05: x [B,3,H,W] NCHW -> y [B,H/2,W/2,64]
  * NHWC; implicit GEMM over k = ci*49 + r*7 + s (147 -> 160), 3xTF32.  wb: dktb_stem_tc_weight_floats() floats written by

@@ -991,7 +991,9 @@ def check_conv_tcg_s2(lib, dev, B=2, H=8, W=10, C=64, Cout=128, seed=130, rtol=2
     w = torch.randn(Cout, C, 3, 3, generator=g) * (1.0 / (C * 9) ** 0.5)
     b = torch.randn(Cout, generator=g) if bias else None
     xr = x.double().clone().requires_grad_(True)
-    ref = F.conv2d(xr, w.double(), b.double() if bias else None, stride=2, padding=1)
+    wr = w.double().clone().requires_grad_(True)
+    br = b.double().clone().requires_grad_(True) if bias else None
+    ref = F.conv2d(xr, wr, br, stride=2, padding=1)
     gout = torch.randn(ref.shape, generator=g)
     (ref * gout.double()).sum().backward()
     Ho, Wo = H // 2, W // 2
@@ -1018,6 +1020,17 @@ def check_conv_tcg_s2(lib, dev, B=2, H=8, W=10, C=64, Cout=128, seed=130, rtol=2
     _close(got, xr.grad, rtol=rtol, atol=1e-6, what="conv_tcg_s2 dgrad %d->%d" % (C, Cout))
     if x_pad:
         assert float((gx.cpu()[:, 0] - 7.0).abs().max()) == 0.0
+    if lib.wgrad_tcg_s2_ok(C, Cout, H, W):
+        dw = torch.full((Cout, C, 3, 3), 7.0, device=dev)
+        db = torch.empty(Cout, device=dev) if bias else None
+        scratch = torch.empty(lib.wgrad_tcg_s2_scratch_floats(B, Ho, Wo, C, Cout), device=dev)
+        lib.wgrad_tcg_s2(xs, gp, dw, db, scratch, err, B, Ho, Wo, C, Cout, 0)
+        assert int(err) == 0
+        _close(dw, wr.grad, rtol=rtol, atol=1e-5, what="wgrad_tcg_s2 %d->%d" % (C, Cout))
+        if bias:
+            _close(db, br.grad, rtol=rtol, atol=1e-4, what="wgrad_tcg_s2 bias grad")
+    else:
+        assert W // 2 > 29
     # stride-2 1x1 shortcut helpers: gather of every second pixel, scatter with zeros elsewhere
     xg = torch.empty(B, Ho, Wo, C, device=dev)
     lib.subsample2(xd, xg, B, H, W, C, int(x_pad), 0, 0)
