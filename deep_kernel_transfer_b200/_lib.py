@@ -54,6 +54,8 @@ SIGNATURES = {
     "dktb_stem_tc_weight_floats": ("", ctypes.c_long),
     "dktb_prep_weights_stem_tc": ("pps", ctypes.c_int),
     "dktb_stem_tc": ("pppppiiis", ctypes.c_int),
+    "dktb_stem_wgrad_tc_scratch_floats": ("ii", ctypes.c_long),
+    "dktb_stem_wgrad_tc": ("pppppiiis", ctypes.c_int),
     "dktb_zero_border": ("piiiis", ctypes.c_int),
     "dktb_pad_copy": ("ppiiiiis", ctypes.c_int),
     "dktb_conv3x3_wgrad_reduce": ("pipps", ctypes.c_int),

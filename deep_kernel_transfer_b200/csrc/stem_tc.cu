@@ -219,6 +219,240 @@ stem_tc_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap 
   if (warp == 13) tc::tmem_dealloc<512>(tmem);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Stem weight gradient on tcgen05:  dW[co][k] = sum_pix G[pix][co] * P[pix][k]  (k = ci*49 + r*7 + s).  GEMM with M = the
+// k slots (two M = 128 blocks: k = 0..127 | 128..146), N = 64 output channels, K = output pixels.  Persistent CTAs loop
+// over (image, band of 8 output rows) work items with the forward kernel's parity-plane patch; a K-block is 32 pixels =
+// 2 output rows x 16 columns of the band.
+//   A (TMEM, `.ts`)  P^T: lane = k slot, column = pixel: every stager thread OWNS one k slot and reads its 2 x 16 pixels
+//                    as two runs of consecutive words of one parity plane -> tf32 hi / lo -> tcgen05.st (3 stages)
+//   B (smem)         G^T [64 co][32 pixels] hi / lo, K-major SWIZZLE_128B, transposed by the same threads from coalesced
+//                    global loads of dy (issued before the patch gather of the same K-block), double-buffered
+//   accumulators     2 x 64 TMEM columns; drained into fp32 registers every kSWgDrain bands (the tensor core's
+//                    accumulation truncates: ~2e-5 per 1700 accumulating instructions) and written once per CTA
+//   warps 0-7  stagers / transposers / drain;  warp 8  MMA issuer (24 x (M128, N64, K8) per K-block), TMEM owner
+// The partials [CTA][256][64] are summed by stem_wgrad_reduce_kernel in a fixed order (deterministic).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kSWgThreads = 288;
+constexpr int kSWgAStages = 3;
+constexpr int kSWgDrain = 2;                    // bands per accumulator life: 2 x 28 K-blocks x 12 instructions
+
+__global__ void __launch_bounds__(kSWgThreads, 1)
+stem_wgrad_tc_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ partial, int B, int H,
+                     int W, int Ho, int Wo, int* __restrict__ err) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar_afull[kSWgAStages], bar_aempty[kSWgAStages], bar_bfull[2], bar_bempty[2], bar_acc, bar_patch;
+  __shared__ uint32_t s_tmem;
+  __shared__ int s_err;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (*reinterpret_cast<volatile int*>(err) != 0) return;
+  unsigned char* s_b = smem;                                           // [2 stages][hi | lo][64 co][128 B]
+  float* s_patch = reinterpret_cast<float*>(smem + 2 * 16384);         // [3][21][2][kSPL]
+  const int nband = (Ho + kSR - 1) / kSR, ntile = (Wo + kSC - 1) / kSC;
+  const long nwork = (long)B * nband;
+  const int nkb_band = (kSR / 2) * ntile;                              // K-blocks per band: 4 row pairs x column tiles
+
+  if (tid == 0) {
+    for (int s = 0; s < kSWgAStages; ++s) { tc::mbar_init(&bar_afull[s], 256); tc::mbar_init(&bar_aempty[s], 1); }
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(&bar_bfull[s], 256); tc::mbar_init(&bar_bempty[s], 1); }
+    tc::mbar_init(&bar_acc, 1);
+    tc::mbar_init(&bar_patch, 256);
+    s_err = 0;
+    tc::fence_barrier_init();
+  }
+  if (warp == 8) tc::tmem_alloc<512>(&s_tmem);
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem = s_tmem;
+  const uint32_t a_tmem = tmem + 128;                        // accumulators [0,128): M-block 0 | 1; A stages 3 x 128 columns
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = tc::umma_idesc(2, 128, 64, 0, 0);
+    bool ok = true;
+    long n = 0;                                               // K-block counter
+    int wcount = 0;
+    for (long work = blockIdx.x; work < nwork && ok; work += gridDim.x, ++wcount) {
+      const bool fresh = wcount % kSWgDrain == 0;             // first band of an accumulator life: overwrite
+      for (int kb = 0; kb < nkb_band && ok; ++kb, ++n) {
+        const int sb = (int)(n & 1), pb = (int)((n >> 1) & 1);
+        const int sa = (int)(n % kSWgAStages), pa = (int)((n / kSWgAStages) & 1);
+        ok = tc::mbar_wait(&bar_bfull[sb], pb);
+        if (!ok) break;
+        ok = tc::mbar_wait(&bar_afull[sa], pa);
+        if (!ok) break;
+        tc::tcgen05_fence_after();
+        const uint32_t bbase = tc::smem_u32(s_b + sb * 16384);
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int mb = 0; mb < 2; ++mb) {
+            const uint32_t acol = a_tmem + sa * 128 + mb * 64;      // hi [0,32) | lo [32,64)
+            const uint32_t dcol = tmem + mb * 64;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t b_hi = tc::umma_desc_sw128(bbase + k * 32, 16, 1024);
+              const uint64_t b_lo = tc::umma_desc_sw128(bbase + 8192 + k * 32, 16, 1024);
+              tc::umma_tf32_ts(dcol, acol + 32 + k * 8, b_hi, idesc, (fresh && kb == 0 && k == 0) ? 0u : 1u);
+              tc::umma_tf32_ts(dcol, acol + k * 8, b_lo, idesc, 1u);
+              tc::umma_tf32_ts(dcol, acol + k * 8, b_hi, idesc, 1u);
+            }
+          }
+          tc::umma_commit(&bar_aempty[sa]);
+          tc::umma_commit(&bar_bempty[sb]);
+        }
+        __syncwarp();
+      }
+      // end of an accumulator life (or of this CTA's work): the stagers drain the accumulators
+      if (ok && (wcount % kSWgDrain == kSWgDrain - 1 || work + gridDim.x >= nwork)) {
+        if (tc::elect_one()) tc::umma_commit(&bar_acc);
+        __syncwarp();
+      }
+    }
+    if (!ok) s_err = 1;
+  } else {
+    // ------------------------------------------------------------------ stagers (256 threads)
+    const int mb = warp >> 2;                                // M-block of this thread's k slot
+    const int quarter = warp & 3;
+    const int L = quarter * 32 + lane;                       // TMEM lane
+    const int k = mb * 128 + L;
+    const bool kval = k < 147;
+    // tcgen05.st / .ld are warp-collective (.sync.aligned): whether a warp stages at all must not depend on the lane.  The
+    // warp holding k = 128..159 stages all 32 lanes (zeros beyond slot 146); the warps of k >= 160 stage nothing.
+    const bool wval = mb * 128 + quarter * 32 < 147;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    int koff = 0;                                            // patch offset of this k slot (see stem_stage)
+    if (kval) {
+      const int ci = k / 49, r = (k % 49) / 7, sx = k % 7;
+      koff = ci * kSCP + r * kSRP + ((sx & 1) ? 0 : kSPL) + (sx >> 1);
+    }
+    const int co = tid & 63, kq8 = tid >> 6;                 // G transpose: pixels [kq8*8, +8) of channel co
+    float run[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) run[j] = 0.f;
+    bool ok = true;
+    long n = 0;
+    int wcount = 0, ndrain = 0, nsync = 0;
+    // the 256 stagers meet on an mbarrier (bounded wait like every other wait of the kernel, never a bar.sync that a
+    // thread leaving on a time-out would dead-lock)
+    auto stager_sync = [&]() -> bool {
+      tc::mbar_arrive(&bar_patch);
+      const bool r = tc::mbar_wait(&bar_patch, nsync & 1);
+      ++nsync;
+      return r;
+    };
+    for (long work = blockIdx.x; work < nwork && ok; work += gridDim.x, ++wcount) {
+      const int b = (int)(work / nband), oh0 = (int)(work % nband) * kSR;
+      // ---- this band's input patch (all stagers; the previous band's gathers are complete: they ended in registers)
+      ok = stager_sync();
+      if (!ok) break;
+      for (int rowi = warp; rowi < 3 * kSRows; rowi += 8) {
+        const int ci = rowi / kSRows, hh = 2 * oh0 - 3 + rowi % kSRows;
+        const bool rok = hh >= 0 && hh < H;
+        const float* src = x + (((long)b * 3 + ci) * H + (rok ? hh : 0)) * W;
+        float* dst = s_patch + rowi * kSRP;
+        for (int i = lane; i < kSRP; i += 32) {
+          const int par = i >= kSPL, j = i - par * kSPL;
+          const int c = 2 * j - 2 - par;
+          dst[i] = (rok && c >= 0 && c < W) ? src[c] : 0.f;
+        }
+      }
+      ok = stager_sync();
+      if (!ok) break;
+      for (int kb = 0; kb < nkb_band && ok; ++kb, ++n) {
+        const int rp = kb / ntile, ti = kb - rp * ntile;     // row pair of the band, column tile
+        const int sb = (int)(n & 1), pb = (int)((n >> 1) & 1);
+        const int sa = (int)(n % kSWgAStages), pa = (int)((n / kSWgAStages) & 1);
+        // ---- G^T tile: pixel p of the K-block = (row rp*2 + (p >> 4), column ti*16 + (p & 15))
+        float gv[8];
+        {
+          const int prow = kq8 >> 1, pc0 = (kq8 & 1) * 8;
+          const int oh = oh0 + rp * 2 + prow;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int ow = ti * kSC + pc0 + j;
+            gv[j] = (oh < Ho && ow < Wo) ? gy[(((long)b * Ho + oh) * Wo + ow) * 64 + co] : 0.f;
+          }
+        }
+        // ---- P^T: this k slot's 32 pixels
+        uint32_t hi[32], lo[32];
+        if (wval) {
+          const float* base = s_patch + koff + (4 * rp) * kSRP + ti * kSC;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) stem_split(kval ? base[(j >> 4) * 2 * kSRP + (j & 15)] : 0.f, hi[j], lo[j]);
+        }
+        ok = tc::mbar_wait(&bar_bempty[sb], pb ^ 1);
+        if (!ok) break;
+        {
+          unsigned char* bhi = s_b + sb * 16384 + co * 128;
+          unsigned char* blo = bhi + 8192;
+#pragma unroll
+          for (int kq = 0; kq < 2; ++kq) {
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) stem_split(gv[kq * 4 + j], h[j], l[j]);
+            const int off = ((kq8 * 2 + kq) ^ (co & 7)) << 4;
+            *reinterpret_cast<uint4*>(bhi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(blo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+          }
+          tc::fence_proxy_async_smem();
+          tc::mbar_arrive(&bar_bfull[sb]);
+        }
+        ok = tc::mbar_wait(&bar_aempty[sa], pa ^ 1);
+        if (!ok) break;
+        tc::tcgen05_fence_after();
+        if (wval) {
+          const uint32_t dst = a_tmem + sa * 128 + mb * 64 + lane_base;
+          tc::tmem_st16(dst, hi);
+          tc::tmem_st16(dst + 16, hi + 16);
+          tc::tmem_st16(dst + 32, lo);
+          tc::tmem_st16(dst + 48, lo + 16);
+          tc::tmem_st_wait();
+        }
+        tc::tcgen05_fence_before();
+        tc::mbar_arrive(&bar_afull[sa]);
+      }
+      if (ok && (wcount % kSWgDrain == kSWgDrain - 1 || work + gridDim.x >= nwork)) {
+        ok = tc::mbar_wait(&bar_acc, ndrain & 1);
+        ++ndrain;
+        if (!ok) break;
+        tc::tcgen05_fence_after();
+#pragma unroll
+        for (int c = 0; c < 64; c += 16) {
+          uint32_t v[16];
+          tc::tmem_ld16(tmem + mb * 64 + lane_base + c, v);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) run[c + j] += __uint_as_float(v[j]);
+        }
+        tc::tcgen05_fence_before();
+      }
+    }
+    if (!ok) s_err = 1;
+    if (kval) {
+      float* o = partial + ((long)blockIdx.x * 256 + mb * 128 + L) * 64;
+#pragma unroll
+      for (int j = 0; j < 64; j += 4) dktb_st4(o + j, make_float4(run[j], run[j + 1], run[j + 2], run[j + 3]));
+    }
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (tid == 0 && s_err) atomicExch(err, 1);
+  if (warp == 8) tc::tmem_dealloc<512>(tmem);
+}
+
+// partial [nsplit][256 k slots][64 co] -> dw [64][147]
+__global__ void stem_wgrad_reduce_kernel(const float* __restrict__ partial, int nsplit, float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 147 * 64) return;
+  const int co = i % 64, k = i / 64;
+  const float* p = partial + (long)k * 64 + co;
+  float t = 0.f;
+  for (int s = 0; s < nsplit; ++s) t += p[(long)s * 256 * 64];
+  dw[co * 147 + k] = t;
+}
+
 // w [64][3][7][7] -> wb [5 kb][hi | lo][64 co][32 k]: k = ci*49 + r*7 + s = the flattened weight row, slots 147..159 zero
 __global__ void prep_weights_stem_tc_kernel(const float* __restrict__ w, float* __restrict__ wb) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -260,6 +494,29 @@ DKTB_EXPORT int dktb_stem_tc(const float* x, const float* wb, const float* bias,
   const int Ho = H / 2, Wo = W / 2;
   dim3 grid((Ho + kSR - 1) / kSR, B);
   stem_tc_kernel<<<grid, kSThreads, smem, stream>>>(x, map_w, bias, y, H, W, Ho, Wo, err);
+  return dktb_launch_status();
+}
+
+static int stem_wgrad_nsplit(int B, int Ho) {
+  const long nwork = (long)B * ((Ho + kSR - 1) / kSR);
+  return (int)(nwork < 148 ? nwork : 148);
+}
+DKTB_EXPORT long dktb_stem_wgrad_tc_scratch_floats(int B, int H) { return (long)stem_wgrad_nsplit(B, H / 2) * 256 * 64; }
+
+// Weight gradient of the stem: x [B,3,H,W] NCHW, gy [B,H/2,W/2,64] NHWC dense -> dw [64][3][7][7] (overwritten).
+// scratch: dktb_stem_wgrad_tc_scratch_floats(B, H) floats.  err as dktb_stem_tc.
+DKTB_EXPORT int dktb_stem_wgrad_tc(const float* x, const float* gy, float* dw, float* scratch, int* err, int B, int H, int W,
+                                   cudaStream_t stream) {
+  DKTB_CHECK_ARG(x && gy && dw && scratch && err && B > 0);
+  DKTB_CHECK_ARG(dktb_stem_tc_ok(3, 64, 7, 2, 3, 1, H, W));
+  const int smem = 2 * 16384 + 3 * kSCP * 4 + 1024;
+  cudaFuncSetAttribute(stem_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int Ho = H / 2, Wo = W / 2;
+  const int nsplit = stem_wgrad_nsplit(B, Ho);
+  stem_wgrad_tc_kernel<<<nsplit, kSWgThreads, smem, stream>>>(x, gy, scratch, B, H, W, Ho, Wo, err);
+  int rc = dktb_launch_status();
+  if (rc != 0) return rc;
+  stem_wgrad_reduce_kernel<<<(147 * 64 + 255) / 256, 256, 0, stream>>>(scratch, nsplit, dw);
   return dktb_launch_status();
 }
 

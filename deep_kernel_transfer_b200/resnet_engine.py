@@ -198,6 +198,7 @@ class ResNetEngine:
         out = self._new(B, H // 2, W // 2, m.out_channels)
         self.lib.stem_tc(x, self._mma_w[key], m.bias.data if m.bias is not None else None, out, self.tc_err, B, H, W, sm)
         self.tape.append(("conv", xh, out, m, (B, H, W, m.in_channels, R, sv, pad, dil)))
+        self._stem_nchw = (xh.data_ptr(), x)       # the weight-gradient kernel reads the NCHW batch as well
         return out
 
     def _mma_weights(self, m):
@@ -235,6 +236,7 @@ class ResNetEngine:
         """x [B,3,H,W] NCHW -> features [B, D]."""
         lib, st, net = self.lib, _stream(self.dev), self.net
         self.tape = []
+        self._stem_nchw = None
         B, _, H, W = x.shape
         xh = self._new(B, H, W, 3)
         lib.nchw_to_nhwc(x, xh, B, 3, H, W, st)
@@ -354,6 +356,15 @@ class ResNetEngine:
                     continue
                 ns = lib.conv2d_wgrad_nsplit(y.shape[0] * y.shape[1] * y.shape[2])
                 scratch = self._new(ns * R * R * Cin * Cout)
+                xn = getattr(self, "_stem_nchw", None)
+                if Cin == 3 and m.bias is None and xn is not None and xn[0] == x.data_ptr() and \
+                        lib.has("dktb_stem_wgrad_tc") and not self._is_pad(gy):
+                    # the stem's weight gradient on tcgen05 (no input gradient: x is the data)
+                    scr = self._new(lib.stem_wgrad_tc_scratch_floats(B, H))
+                    lib.stem_wgrad_tc(xn[1], gy, m.weight.grad, scr, self.tc_err, B, H, W, st)
+                    if self.trace is not None:
+                        self.trace.append((rec, gy, None, m.weight.grad.clone()))
+                    continue
                 if self._sub2_ok(m, H, W):
                     # stride-2 1x1 shortcut: GEMMs on the gathered input, gradient scattered back (zeros at skipped pixels)
                     Ho, Wo = y.shape[1], y.shape[2]

@@ -114,6 +114,11 @@ long dktb_stem_tc_weight_floats(void);
 int dktb_prep_weights_stem_tc(const float* w, float* wb, cudaStream_t stream);
 int dktb_stem_tc(const float* x, const float* wb, const float* bias, float* y, int* err, int B, int H, int W,
                  cudaStream_t stream);
+/* its weight gradient (K = output pixels; the im2col rows are gathered transposed into TMEM): x NCHW, gy [B,H/2,W/2,64] NHWC
+ * -> dw [64][3][7][7]; scratch: dktb_stem_wgrad_tc_scratch_floats(B, H) floats; deterministic (fixed-order reduce) */
+long dktb_stem_wgrad_tc_scratch_floats(int B, int H);
+int dktb_stem_wgrad_tc(const float* x, const float* gy, float* dw, float* scratch, int* err, int B, int H, int W,
+                       cudaStream_t stream);
 
 /* weight gradient of the same layers on tcgen05: x [.., Cin], gy [.., Cout] in the layouts of dktb_conv_tcg (R = 3: both
  * padded-flat with zero borders; R = 1: dense rows) -> dw [Cout][Cin][R][R], db [Cout] or NULL; scratch holds

@@ -1052,7 +1052,11 @@ def check_stem_tc(lib, dev, B=2, H=32, W=32, seed=120, rtol=2e-5, bias=False):
     x = torch.randn(B, 3, H, W, generator=g)
     w = torch.randn(64, 3, 7, 7, generator=g) * (1.0 / 147 ** 0.5)
     b = torch.randn(64, generator=g) if bias else None
-    ref = F.conv2d(x.double(), w.double(), b.double() if bias else None, stride=2, padding=3)
+    wr = w.double().clone().requires_grad_(True)
+    ref = F.conv2d(x.double(), wr, b.double() if bias else None, stride=2, padding=3)
+    gout = torch.randn(ref.shape, generator=g)
+    (ref * gout.double()).sum().backward()
+    ref = ref.detach()
     assert lib.stem_tc_ok(3, 64, 7, 2, 3, 1, H, W)
     wb = torch.empty(lib.stem_tc_weight_floats(), device=dev)
     lib.prep_weights_stem_tc(w.to(dev), wb, 0)
@@ -1061,6 +1065,11 @@ def check_stem_tc(lib, dev, B=2, H=32, W=32, seed=120, rtol=2e-5, bias=False):
     lib.stem_tc(x.to(dev), wb, b.to(dev) if bias else None, y, err, B, H, W, 0)
     assert int(err) == 0
     _close(y.cpu().permute(0, 3, 1, 2), ref, rtol=rtol, atol=1e-6, what="stem_tc %dx%d" % (H, W))
+    dw = torch.full((64, 3, 7, 7), 7.0, device=dev)
+    scratch = torch.empty(lib.stem_wgrad_tc_scratch_floats(B, H), device=dev)
+    lib.stem_wgrad_tc(x.to(dev), gout.permute(0, 2, 3, 1).contiguous().to(dev), dw, scratch, err, B, H, W, 0)
+    assert int(err) == 0
+    _close(dw, wr.grad, rtol=rtol, atol=1e-5, what="stem_wgrad_tc %dx%d" % (H, W))
 
 
 def check_gram_tc(lib, dev, E=3, M=105, N=105, D=1600, seed=110, same=True):
