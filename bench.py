@@ -628,8 +628,8 @@ def resnet_roofline(model, lib, dev, E):
             "algorithmic_flops_per_launch": flops, "ms_per_launch": ms,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone) / 2 = dense TF32; 3xTF32: the "
                            "arithmetic's ceiling is 1/3",
-            "note": "stride-1 3x3 / 1x1 layers and the 7x7 stem run on tcgen05 kernels; the three stride-2 3x3 layers, their "
-                    "1x1 shortcuts and the stem's weight gradient on mma.sync tiles (profiles/r02_launches_cfg4.summary.txt)"}
+            "note": "every convolution of the network (stem, stride-1 / stride-2 3x3, 1x1, shortcuts; forward, dgrad, wgrad) runs "
+                    "on tcgen05 kernels (profiles/r02_launches_cfg4.summary.txt, profiles/r02_sass_tensor_ops.txt)"}
 
 
 def gp_flops(n, c, d):

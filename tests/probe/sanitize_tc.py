@@ -15,7 +15,7 @@ from deep_kernel_transfer_b200 import _lib  # noqa: E402
 
 lib = _lib.load()
 dev = torch.device("cuda", 0)
-which = sys.argv[1:] or ["conv3x3", "wgrad", "conv1", "tcg", "gram", "stem"]
+which = sys.argv[1:] or ["conv3x3", "wgrad", "conv1", "tcg", "gram", "stem", "s2"]
 if "conv3x3" in which:
     kc.check_conv3x3_tc(lib, dev, B=2, H=10, W=10, seed=22, fn="conv3x3_tc_fwd")
     print("conv3x3_tc ok")
@@ -37,5 +37,9 @@ if "gram" in which and lib.has("dktb_gram_tc"):
 if "stem" in which and lib.has("dktb_stem_tc"):
     kc.check_stem_tc(lib, dev, B=1, H=20, W=30, seed=121, bias=True)
     print("stem_tc ok")
+if "s2" in which and lib.has("dktb_conv_tcg_s2"):
+    kc.check_conv_tcg_s2(lib, dev, B=1, H=8, W=10, C=64, Cout=128, seed=130)
+    kc.check_conv_tcg_s2(lib, dev, B=1, H=6, W=8, C=128, Cout=128, seed=136, x_pad=True, bias=True)
+    print("conv_tcg_s2 ok")
 torch.cuda.synchronize()
 print("done")
